@@ -1,0 +1,93 @@
+"""Deterministic synthetic hg38-shaped interval sets.
+
+Used by bench.py, the oracle timing leg and the parity tests alike, so the
+CUDA path and the CPU oracle always see the same rows.  Chromosome lengths are
+the 24 primary hg38 chromosomes (the rows of the reference's
+``src/bioframe/io/data/hg38.seqinfo.tsv:2-25``).  Rows are left unsorted.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+HG38_CHROMS = [f"chr{i}" for i in range(1, 23)] + ["chrX", "chrY"]
+HG38_SIZES = np.array(
+    [
+        248956422, 242193529, 198295559, 190214555, 181538259, 170805979,
+        159345973, 145138636, 138394717, 133797422, 135086622, 133275309,
+        114364328, 107043718, 101991189, 90338345, 83257441, 80373285,
+        58617616, 64444167, 46709983, 50818468, 156040895, 57227415,
+    ],
+    dtype=np.int64,
+)
+
+
+def _chrom_codes(rng, n):
+    p = HG38_SIZES / HG38_SIZES.sum()
+    # inverse-CDF draw: much cheaper than rng.choice(p=...) at 1e8 rows
+    cdf = np.cumsum(p)
+    cdf[-1] = 1.0
+    return np.searchsorted(cdf, rng.random(n), side="right").astype(np.int32)
+
+
+def _place(rng, codes, lens):
+    span = HG38_SIZES[codes] - lens
+    np.maximum(span, 1, out=span)
+    starts = np.floor(rng.random(codes.shape[0]) * span).astype(np.int64)
+    return starts, starts + lens
+
+
+def lengths(rng, n, kind):
+    """Interval lengths for one of the BASELINE.json config families."""
+    if kind == "geom1k":  # cfg0 / cfg1: Geometric(1/1000), mean 1 kb
+        return rng.geometric(1.0 / 1000.0, n).astype(np.int64)
+    if kind == "geom2k":  # cfg3 queries
+        return rng.geometric(1.0 / 2000.0, n).astype(np.int64)
+    if kind == "pareto":  # cfg2 heavy tail, x_m=200, alpha=1.2, capped at 5 Mb
+        x = np.ceil(200.0 * (1.0 + rng.pareto(1.2, n)))
+        return np.minimum(x, 5_000_000).astype(np.int64)
+    if kind == "peaks":  # cfg3 targets: LogNormal(ln 500, 0.8)
+        x = np.ceil(rng.lognormal(np.log(500.0), 0.8, n))
+        return np.maximum(x, 1).astype(np.int64)
+    raise ValueError(kind)
+
+
+def make_intervals(n, seed, kind="geom1k"):
+    """-> (chrom_code int32[n], start int64[n], end int64[n]); unsorted rows."""
+    rng = np.random.default_rng(seed)
+    codes = _chrom_codes(rng, n)
+    lens = lengths(rng, n, kind)
+    starts, ends = _place(rng, codes, lens)
+    return codes, starts, ends
+
+
+def make_peak_targets(n, seed, hotspot_frac=0.7, n_hotspots=200_000, window=20_000):
+    """cfg3 targets: peak-like lengths, `hotspot_frac` of them inside
+    `n_hotspots` windows of `window` bp (fan-out skew)."""
+    rng = np.random.default_rng(seed)
+    lens = lengths(rng, n, "peaks")
+    n_hot = int(n * hotspot_frac)
+    hs_codes = _chrom_codes(rng, n_hotspots)
+    hs_starts, _ = _place(rng, hs_codes, np.full(n_hotspots, window, dtype=np.int64))
+    pick = rng.integers(0, n_hotspots, n_hot)
+    codes_hot = hs_codes[pick]
+    starts_hot = hs_starts[pick] + np.floor(rng.random(n_hot) * window).astype(np.int64)
+    ends_hot = np.minimum(starts_hot + lens[:n_hot], HG38_SIZES[codes_hot])
+    starts_hot = np.minimum(starts_hot, ends_hot - 1)
+    codes_bg = _chrom_codes(rng, n - n_hot)
+    starts_bg, ends_bg = _place(rng, codes_bg, lens[n_hot:])
+    codes = np.concatenate([codes_hot, codes_bg])
+    starts = np.concatenate([starts_hot, starts_bg])
+    ends = np.concatenate([ends_hot, ends_bg])
+    perm = rng.permutation(n)
+    return codes[perm], starts[perm], ends[perm]
+
+
+def to_frame(codes, starts, ends, categorical=False):
+    import pandas as pd
+
+    names = np.array(HG38_CHROMS, dtype=object)
+    if categorical:
+        chrom = pd.Categorical.from_codes(codes, categories=HG38_CHROMS)
+    else:
+        chrom = names[codes]
+    return pd.DataFrame({"chrom": chrom, "start": starts, "end": ends})
