@@ -1,0 +1,82 @@
+"""ctypes binding of libbioframe_b200.so (the C ABI in include/bioframe_b200.h).
+
+There is no CPU fallback: if the library is missing or cannot be loaded,
+`lib()` raises.  The library is built in-tree by `python -m bioframe_b200.build`
+(nvcc, sm_100a) and is what `__graft_entry__.build()` produces.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libbioframe_b200.so")
+
+BF_OK = 0
+ERRORS = {
+    -1: "BF_ERR_ARG",
+    -2: "BF_ERR_WORKSPACE",
+    -3: "BF_ERR_RANGE",
+    -4: "BF_ERR_CUDA",
+    -5: "BF_ERR_GROUP",
+    -6: "BF_ERR_STATE",
+}
+HOW = {"inner": 0, "left": 1, "right": 2, "outer": 3}
+
+
+class Plan(C.Structure):
+    _fields_ = [("opaque", C.c_int64 * 96)]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int32
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/bioframe_b200.h declares
+SIGNATURES = {
+    "bf_last_error": (C.c_char_p, []),
+    "bf_version": (C.c_int, []),
+    "bf_overlap_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "bf_overlap_count": (
+        C.c_int,
+        [_p, _p, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _sz, C.POINTER(Plan), _p,
+         C.POINTER(_i64), C.POINTER(_i64)],
+    ),
+    "bf_overlap_emit": (C.c_int, [C.POINTER(Plan), _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once; fail loudly if it is not there."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(
+                f"{LIB_PATH} not found: build it with `python -m bioframe_b200.build` "
+                "(there is no CPU fallback)"
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != BF_OK:
+        msg = lib().bf_last_error().decode("utf-8", "replace")
+        kind = ERRORS.get(rc, str(rc))
+        if rc in (-1, -5):
+            raise ValueError(f"{what}: {kind}: {msg}")
+        if rc == -3:
+            raise OverflowError(f"{what}: {kind}: {msg}")
+        raise EngineError(f"{what}: {kind}: {msg}")

@@ -1,0 +1,98 @@
+// Shared device/host helpers for the bioframe_b200 CUDA library (sm_100a).
+// Everything on this path is int64/uint64 integer work bound by HBM bandwidth:
+// no tensor cores, coalesced 8/16-byte accesses, shared-memory staging.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+typedef unsigned long long u64;
+typedef long long i64;
+typedef unsigned int u32;
+typedef int i32;
+typedef unsigned short u16;
+typedef unsigned char u8;
+
+#define BF_OK 0
+#define BF_ERR_ARG -1       // bad argument (null pointer, negative size, bad enum)
+#define BF_ERR_WORKSPACE -2 // workspace too small
+#define BF_ERR_RANGE -3     // coordinate range / group count does not fit the key layouts
+#define BF_ERR_CUDA -4      // CUDA runtime error (see bf_last_error)
+#define BF_ERR_GROUP -5     // group code outside [0, n_groups)
+#define BF_ERR_STATE -6     // emit called on a plan that did not complete count
+
+namespace bf {
+
+void set_error(const char* fmt, ...);
+
+#define BF_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t _e = (call);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      bf::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      return BF_ERR_CUDA;                                                               \
+    }                                                                                   \
+  } while (0)
+
+#define BF_LAUNCH_CHECK() BF_CUDA(cudaGetLastError())
+
+#define BF_TRY(expr)           \
+  do {                         \
+    int _s = (expr);           \
+    if (_s != BF_OK) return _s; \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+static inline i64 ceil_div(i64 a, i64 b) { return (a + b - 1) / b; }
+static inline int bit_width(u64 x) {
+  int b = 0;
+  while (x) {
+    ++b;
+    x >>= 1;
+  }
+  return b;
+}
+
+// Bump allocator over a caller-owned workspace. With base == nullptr it only
+// measures (used by the *_workspace_bytes entry points).
+struct Arena {
+  char* base;
+  size_t off;
+  explicit Arena(void* b) : base((char*)b), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t at = off;
+    off = align_up(off + count * sizeof(T));
+    return base ? (T*)(base + at) : (T*)nullptr;
+  }
+};
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ u32 lanemask_lt() {
+  u32 m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(u64* p, u64 v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// first index in [lo, hi) with !(a[idx] < x)   (np.searchsorted side="left")
+template <typename F>
+__device__ __forceinline__ i64 lower_bound_by(i64 lo, i64 hi, F less_than_x) {
+  while (lo < hi) {
+    i64 mid = lo + ((hi - lo) >> 1);
+    if (less_than_x(mid))
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+}  // namespace bf

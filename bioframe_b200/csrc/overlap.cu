@@ -1,0 +1,645 @@
+// bf_overlap_count / bf_overlap_emit: the whole of ops._overlap_intidxs
+// (src/bioframe/ops.py:242-338) for all groups in one set of launches.
+//
+//   extent  -> pack keys + digit histograms -> onesweep radix argsort (both sets)
+//   -> group segment table -> [running max of end' for outer joins]
+//   -> search + count (A side per sorted query, B side per sorted target)
+//   -> exclusive scans -> per-group offset table -> (host reads the row count)
+//   -> emit A pairs, emit B pairs, emit unpaired rows.
+//
+// Output order is the reference's: per group (in group-rank order) the A block
+// (per sorted row of set 1 the targets whose start is in [s1, e1')), the B
+// block (per sorted row of set 2 the queries whose start is in (s2, e2')),
+// then unpaired rows of set 1 ascending, then of set 2 ascending
+// (arrops.py:338-368, ops.py:319-334).
+#include "common.cuh"
+#include "keys.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+#include "../../include/bioframe_b200.h"
+
+namespace bf {
+
+// ---------------------------------------------------------------- workspace
+struct SetWS {
+  u64 *keyA, *keyB;
+  u32 *idA, *idB;
+  u32 *lo, *cnt;
+  u64 *scan;   // [n+1]
+  u64 *spine;  // [tiles]
+  u64 *pmax;   // [n] running max of ce (only for outer joins on the other side)
+  u8 *rowflag; // [n] 1 = row has no partner (row order)
+  u64 *ukeyA, *ukeyB;  // [n] (rank << 32 | row) of unpaired rows
+  u64 *uspine;
+  u64 *ucnt;   // [n_groups] unpaired rows per group
+  i64 *seg;    // [n_groups+1] first sorted position of each group
+};
+
+struct OverlapWS {
+  SetWS s[2];
+  RadixScratch radix;
+  Extent* extent;
+  // per-group tables, n_groups+1 entries each
+  i64 *cumA, *cumB;      // group boundaries in A-space / B-space (scan values)
+  i64 *deltaA, *deltaB;  // output row = scan-space index + delta[group]
+  i64 *ubase1, *ubase2;  // first output row of the group's unpaired blocks
+  i64 *ustart1, *ustart2;  // first index of the group in the partitioned unpaired lists
+  i64 *header;           // n_rows, n_pairs, nU1, nU2
+  u64 *nU;               // [2] device-side unpaired totals (sort sizes)
+};
+
+static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS* w) {
+  const i64 n[2] = {n1, n2};
+  const bool need[2] = {(how & 1) != 0, (how & 2) != 0};
+  for (int k = 0; k < 2; ++k) {
+    SetWS& s = w->s[k];
+    s.keyA = a.take<u64>(n[k]);
+    s.keyB = a.take<u64>(n[k]);
+    s.idA = a.take<u32>(n[k]);
+    s.idB = a.take<u32>(n[k]);
+    s.lo = a.take<u32>(n[k]);
+    s.cnt = a.take<u32>(n[k]);
+    s.scan = a.take<u64>(n[k] + 1);
+    s.spine = a.take<u64>(scan_tiles(n[k]) + 1);
+    s.seg = a.take<i64>(nb + 1);
+    s.ucnt = a.take<u64>(nb + 1);
+    // set k needs flags / unpaired lists when it is on the kept side; the OTHER
+    // set then needs the running max of its end'.
+    s.pmax = need[1 - k] ? a.take<u64>(n[k]) : nullptr;
+    if (need[k]) {
+      s.rowflag = a.take<u8>(n[k]);
+      s.ukeyA = a.take<u64>(n[k]);
+      s.ukeyB = a.take<u64>(n[k]);
+      s.uspine = a.take<u64>(scan_tiles(n[k]) + 1);
+    } else {
+      s.rowflag = nullptr;
+      s.ukeyA = s.ukeyB = s.uspine = nullptr;
+    }
+  }
+  w->radix = take_radix_scratch(a, (u64)(n1 > n2 ? n1 : n2));
+  w->extent = a.take<Extent>(1);
+  w->cumA = a.take<i64>(nb + 1);
+  w->cumB = a.take<i64>(nb + 1);
+  w->deltaA = a.take<i64>(nb + 1);
+  w->deltaB = a.take<i64>(nb + 1);
+  w->ubase1 = a.take<i64>(nb + 1);
+  w->ubase2 = a.take<i64>(nb + 1);
+  w->ustart1 = a.take<i64>(nb + 1);
+  w->ustart2 = a.take<i64>(nb + 1);
+  w->header = a.take<i64>(8);
+  w->nU = a.take<u64>(2);
+}
+
+struct OverlapPlan {  // lives in the caller's bf_plan
+  u64 magic;
+  i64 n1, n2;
+  i32 nb, how, closed, ready;
+  KeyLayout L;
+  i64 n_rows, n_pairs, nU1, nU2;
+  i64 totA, totB;
+  // sorted results (pointers into the workspace)
+  u64 *key1, *key2;
+  u32 *id1, *id2;
+  u64 *ukeys1, *ukeys2;
+};
+static_assert(sizeof(OverlapPlan) <= sizeof(bf_plan), "bf_plan too small");
+constexpr u64 OVERLAP_MAGIC = 0x62664f7665726c70ull;
+
+// ---------------------------------------------------------------- kernels
+
+// seg[c] = first sorted position whose group rank is >= c
+__global__ void segment_table_kernel(const u64* __restrict__ keys, i64 n, KeyLayout L, i32 nb,
+                                     i64* __restrict__ seg) {
+  i32 c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > nb) return;
+  if (c == nb) {
+    seg[c] = n;
+    return;
+  }
+  seg[c] = lower_bound_by(0, n, [&](i64 m) { return key_rank(keys[m], L) < (u32)c; });
+}
+
+// inclusive running max of ce(key) in sorted order (np.maximum.accumulate over
+// end', group resets come free because the group rank is the high field)
+__global__ void __launch_bounds__(SC_THREADS) tile_max_ce_kernel(const u64* __restrict__ keys, u64 n,
+                                                                 KeyLayout L, u64* __restrict__ spine) {
+  __shared__ u64 s_tmp[8];
+  const u64 base = (u64)blockIdx.x * SC_TILE;
+  u64 acc = 0;
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    u64 i = base + (u64)j * SC_THREADS + threadIdx.x;
+    if (i < n) {
+      u64 v = key_ce(keys[i], L);
+      acc = v > acc ? v : acc;
+    }
+  }
+  acc = block_max_u64(acc, s_tmp);
+  if (threadIdx.x == 0) spine[blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(SC_THREADS) running_max_ce_kernel(const u64* __restrict__ keys, u64 n,
+                                                                    KeyLayout L, const u64* __restrict__ spine,
+                                                                    u64* __restrict__ pmax) {
+  __shared__ u64 s_tmp[8];
+  const u64 base = (u64)blockIdx.x * SC_TILE + (u64)threadIdx.x * SC_IPT;
+  u64 v[SC_IPT];
+  u64 mine = 0;
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    u64 i = base + j;
+    v[j] = i < n ? key_ce(keys[i], L) : 0ull;
+    mine = v[j] > mine ? v[j] : mine;
+  }
+  u64 before = block_excl_max_u64(mine, s_tmp);
+  u64 run = spine[blockIdx.x];
+  run = before > run ? before : run;
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    u64 i = base + j;
+    run = v[j] > run ? v[j] : run;
+    if (i < n) pmax[i] = run;
+  }
+}
+
+// Search + count for one side.
+//   B_SIDE == false: rows of set 1 against starts of set 2:
+//       lo = #(cs2 <  cs1), hi = #(cs2 <  ce1)   (closed: <=)     arrops.py:338-339
+//   B_SIDE == true : rows of set 2 against starts of set 1:
+//       lo = #(cs1 <= cs2), hi = #(cs1 <  ce2)   (closed: <=)     arrops.py:341-342
+// A block of 2048 consecutive sorted rows first brackets its lo range with two
+// full searches (first and last row), then every row searches inside the
+// bracket and gallops from lo to hi.
+template <bool B_SIDE, bool FLAGS>
+__global__ void __launch_bounds__(SC_THREADS)
+    search_count_kernel(const u64* __restrict__ mine, const u32* __restrict__ mine_id, i64 n,
+                        const u64* __restrict__ other, i64 m, const u64* __restrict__ other_pmax,
+                        KeyLayout L, int closed, u32* __restrict__ lo_out, u32* __restrict__ cnt_out,
+                        u64* __restrict__ spine, u8* __restrict__ rowflag, u64* __restrict__ ucnt) {
+  __shared__ u64 s_tmp[8];
+  __shared__ i64 s_bracket[2];
+  const i64 base = (i64)blockIdx.x * SC_TILE;
+  const i64 last = (base + SC_TILE < n ? base + SC_TILE : n) - 1;
+  auto lo_search = [&](u64 x, i64 a, i64 b) {
+    if (B_SIDE) return lower_bound_by(a, b, [&](i64 q) { return key_cs(other[q], L) <= x; });
+    return lower_bound_by(a, b, [&](i64 q) { return key_cs(other[q], L) < x; });
+  };
+  if (threadIdx.x == 0) s_bracket[0] = lo_search(key_cs(mine[base], L), 0, m);
+  if (threadIdx.x == 32) s_bracket[1] = lo_search(key_cs(mine[last], L), 0, m);
+  __syncthreads();
+  const i64 br_lo = s_bracket[0], br_hi = s_bracket[1];
+
+  u64 block_sum = 0;
+#pragma unroll 2
+  for (int j = 0; j < SC_IPT; ++j) {
+    const i64 p = base + (i64)j * SC_THREADS + threadIdx.x;
+    u32 cnt = 0;
+    bool lonely = false;
+    u32 rank = 0;
+    if (p < n) {
+      const u64 k = mine[p];
+      const u64 xs = key_cs(k, L), xe = key_ce(k, L);
+      const i64 lo = lo_search(xs, br_lo, br_hi);
+      // gallop from lo for hi
+      i64 a = lo, step = 1, b = lo;
+      while (true) {
+        b = a + step;
+        if (b >= m) {
+          b = m;
+          break;
+        }
+        u64 v = key_cs(other[b - 1], L);
+        bool below = closed ? (v <= xe) : (v < xe);
+        if (!below) break;
+        a = b;
+        step <<= 1;
+      }
+      i64 hi = closed ? lower_bound_by(a, b, [&](i64 q) { return key_cs(other[q], L) <= xe; })
+                      : lower_bound_by(a, b, [&](i64 q) { return key_cs(other[q], L) < xe; });
+      cnt = (u32)(hi - lo);
+      lo_out[p] = (u32)lo;
+      cnt_out[p] = cnt;
+      if (FLAGS) {
+        bool partner = cnt > 0;
+        if (!partner && lo > 0) {
+          u64 pm = other_pmax[lo - 1];
+          partner = closed ? (pm >= xs) : (pm > xs);
+        }
+        lonely = !partner;
+        rank = key_rank(k, L);
+        if (lonely) rowflag[mine_id[p]] = 1;
+      }
+    }
+    if (FLAGS) {
+      // per-group unpaired counters, merged across the warp first
+      u32 tagd = lonely ? rank : 0xffffffffu - lane_id();
+      u32 peers = __match_any_sync(0xffffffffu, tagd);
+      if (lonely && (peers & lanemask_lt()) == 0) atomicAdd(&ucnt[rank], (u64)__popc(peers));
+    }
+    block_sum += cnt;
+  }
+  block_sum = block_sum_u64(block_sum, s_tmp);
+  if (threadIdx.x == 0) spine[blockIdx.x] = block_sum;
+}
+
+// Per-group output offsets; single thread (n_groups is tens, not millions).
+__global__ void offset_table_kernel(OverlapWS w, i64 n1, i64 n2, i32 nb, i32 how) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const bool need1 = how & 1, need2 = how & 2;
+  const u64* scanA = w.s[0].scan;
+  const u64* scanB = w.s[1].scan;
+  i64 base = 0, runU1 = 0, runU2 = 0, pairs = 0;
+  for (i32 c = 0; c < nb; ++c) {
+    i64 a0 = (i64)scanA[w.s[0].seg[c]], a1 = (i64)scanA[w.s[0].seg[c + 1]];
+    i64 b0 = (i64)scanB[w.s[1].seg[c]], b1 = (i64)scanB[w.s[1].seg[c + 1]];
+    i64 U1 = need1 ? (i64)w.s[0].ucnt[c] : 0;
+    i64 U2 = need2 ? (i64)w.s[1].ucnt[c] : 0;
+    w.cumA[c] = a0;
+    w.cumB[c] = b0;
+    w.deltaA[c] = base - a0;
+    w.deltaB[c] = base + (a1 - a0) - b0;
+    w.ubase1[c] = base + (a1 - a0) + (b1 - b0);
+    w.ubase2[c] = w.ubase1[c] + U1;
+    w.ustart1[c] = runU1;
+    w.ustart2[c] = runU2;
+    base += (a1 - a0) + (b1 - b0) + U1 + U2;
+    pairs += (a1 - a0) + (b1 - b0);
+    runU1 += U1;
+    runU2 += U2;
+  }
+  w.cumA[nb] = (i64)scanA[n1];
+  w.cumB[nb] = (i64)scanB[n2];
+  w.deltaA[nb] = w.deltaB[nb] = 0;
+  w.ubase1[nb] = w.ubase2[nb] = base;
+  w.ustart1[nb] = runU1;
+  w.ustart2[nb] = runU2;
+  w.header[0] = base;
+  w.header[1] = pairs;
+  w.header[2] = runU1;
+  w.header[3] = runU2;
+  w.header[4] = (i64)scanA[n1];
+  w.header[5] = (i64)scanB[n2];
+}
+
+// Emit one block (A or B) of pairs. Thread per output row in scan space:
+//   t -> owner row p = upper_bound(scan, t) - 1, k = t - scan[p]
+//   A: (id1[p], id2[lo[p] + k])      B: (id1[lo[q] + k], id2[q])
+// The block first brackets p with two searches so each row's search touches a
+// few hundred bytes of L1-resident scan values.
+constexpr int EM_THREADS = 256;
+constexpr int EM_IPT = 8;
+constexpr int EM_TILE = EM_THREADS * EM_IPT;
+
+template <bool B_SIDE>
+__global__ void __launch_bounds__(EM_THREADS)
+    emit_pairs_kernel(const u64* __restrict__ scan, const u32* __restrict__ lo, i64 n_owner,
+                      const u32* __restrict__ owner_id, const u32* __restrict__ other_id, i64 total,
+                      const i64* __restrict__ cum, const i64* __restrict__ delta, i32 nb,
+                      i64* __restrict__ ev1, i64* __restrict__ ev2) {
+  __shared__ i64 s_br[4];
+  const i64 t0 = (i64)blockIdx.x * EM_TILE;
+  const i64 t1 = (t0 + EM_TILE < total ? t0 + EM_TILE : total) - 1;
+  auto owner_of = [&](i64 t, i64 a, i64 b) {  // last p in [a,b) with scan[p] <= t
+    return lower_bound_by(a, b, [&](i64 p) { return (i64)scan[p] <= t; }) - 1;
+  };
+  auto group_of = [&](i64 t, i64 a, i64 b) {  // last c with cum[c] <= t
+    return lower_bound_by(a, b, [&](i64 c) { return cum[c] <= t; }) - 1;
+  };
+  if (threadIdx.x == 0) s_br[0] = owner_of(t0, 0, n_owner);
+  if (threadIdx.x == 32) s_br[1] = owner_of(t1, 0, n_owner);
+  if (threadIdx.x == 64) s_br[2] = group_of(t0, 0, nb);
+  if (threadIdx.x == 96) s_br[3] = group_of(t1, 0, nb);
+  __syncthreads();
+  const i64 p_lo = s_br[0], p_hi = s_br[1] + 1;
+  const i64 c_lo = s_br[2], c_hi = s_br[3];
+#pragma unroll 2
+  for (int j = 0; j < EM_IPT; ++j) {
+    const i64 t = t0 + (i64)j * EM_THREADS + threadIdx.x;
+    if (t > t1) break;
+    const i64 p = owner_of(t, p_lo, p_hi);
+    const i64 k = t - (i64)scan[p];
+    const i64 c = (c_lo == c_hi) ? c_lo : group_of(t, c_lo, c_hi + 1);
+    const i64 row = t + delta[c];
+    const i64 own = owner_id[p];
+    const i64 oth = other_id[(i64)lo[p] + k];
+    ev1[row] = B_SIDE ? oth : own;
+    ev2[row] = B_SIDE ? own : oth;
+  }
+}
+
+// ---- unpaired rows: compaction in row order -> stable partition by group ----
+__global__ void __launch_bounds__(SC_THREADS) tile_count_flags_kernel(const u8* __restrict__ flag, u64 n,
+                                                                      u64* __restrict__ spine) {
+  __shared__ u64 s_tmp[8];
+  const u64 base = (u64)blockIdx.x * SC_TILE;
+  u64 acc = 0;
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    u64 i = base + (u64)j * SC_THREADS + threadIdx.x;
+    if (i < n) acc += flag[i];
+  }
+  acc = block_sum_u64(acc, s_tmp);
+  if (threadIdx.x == 0) spine[blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(SC_THREADS)
+    compact_unpaired_kernel(const u8* __restrict__ flag, const i32* __restrict__ grp, u64 n,
+                            const u64* __restrict__ spine, u64* __restrict__ ukeys) {
+  __shared__ u64 s_tmp[8];
+  const u64 base = (u64)blockIdx.x * SC_TILE + (u64)threadIdx.x * SC_IPT;
+  u8 f[SC_IPT];
+  u64 mine = 0;
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    u64 i = base + j;
+    f[j] = i < n ? flag[i] : (u8)0;
+    mine += f[j];
+  }
+  u64 tot;
+  u64 at = spine[blockIdx.x] + block_excl_sum_u64(mine, s_tmp, &tot);
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    if (f[j]) {
+      u64 i = base + j;
+      u64 g = grp ? (u64)(u32)grp[i] : 0ull;
+      ukeys[at++] = (g << 32) | i;
+    }
+  }
+}
+template <bool SECOND>
+__global__ void __launch_bounds__(256) emit_unpaired_kernel(const u64* __restrict__ ukeys, i64 nU,
+                                                            const i64* __restrict__ ustart,
+                                                            const i64* __restrict__ ubase,
+                                                            i64* __restrict__ ev1, i64* __restrict__ ev2) {
+  i64 u = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= nU) return;
+  u64 k = ukeys[u];
+  u32 c = (u32)(k >> 32);
+  i64 row = (i64)(k & 0xffffffffull);
+  i64 out = ubase[c] + (u - ustart[c]);
+  ev1[out] = SECOND ? -1 : row;
+  ev2[out] = SECOND ? row : -1;
+}
+
+// ---------------------------------------------------------------- host side
+
+static int sort_set(const i32* grp, const i64* s, const i64* e, i64 n, const KeyLayout& L,
+                    const RadixPlan& rp, SetWS& ws, const RadixScratch& sc, cudaStream_t st,
+                    SortResult* res) {
+  if (n == 0) {
+    res->keys = ws.keyA;
+    res->vals = ws.idA;
+    res->keys_alt = ws.keyB;
+    res->vals_alt = ws.idB;
+    return BF_OK;
+  }
+  BF_CUDA(cudaMemsetAsync(sc.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
+  pack_keys_kernel<<<stream_grid((u64)n, 2048), 256, 0, st>>>(grp, s, e, (u64)n, L, 1, rp, ws.keyA, sc.hist);
+  BF_LAUNCH_CHECK();
+  return radix_sort_passes<true>(ws.keyA, ws.keyB, ws.idA, ws.idB, true, (u64)n, nullptr, rp, sc, st, res);
+}
+
+static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64 n1, const i32* grp2,
+                              const i64* s2, const i64* e2, i64 n2, i32 nb, i32 how, i32 closed,
+                              void* ws_ptr, size_t ws_bytes, OverlapPlan* plan, cudaStream_t st) {
+  if (n1 < 0 || n2 < 0 || nb < 1 || how < 0 || how > 3 || !plan) {
+    set_error("bf_overlap_count: bad argument (n1=%lld n2=%lld n_groups=%d how=%d)", (long long)n1,
+              (long long)n2, nb, how);
+    return BF_ERR_ARG;
+  }
+  if (n1 >= (1ll << 31) || n2 >= (1ll << 31)) {
+    set_error("bf_overlap_count: more than 2^31-1 rows in one set");
+    return BF_ERR_RANGE;
+  }
+  if ((n1 > 0 && (!s1 || !e1)) || (n2 > 0 && (!s2 || !e2)) || (nb > 1 && ((n1 > 0 && !grp1) || (n2 > 0 && !grp2)))) {
+    set_error("bf_overlap_count: null input pointer");
+    return BF_ERR_ARG;
+  }
+  Arena measure(nullptr);
+  OverlapWS w;
+  layout_overlap(measure, n1, n2, nb, how, &w);
+  if (!ws_ptr || ws_bytes < measure.off) {
+    set_error("bf_overlap_count: workspace %zu bytes < required %zu", ws_bytes, measure.off);
+    return BF_ERR_WORKSPACE;
+  }
+  Arena arena(ws_ptr);
+  layout_overlap(arena, n1, n2, nb, how, &w);
+  const bool need1 = how & 1, need2 = how & 2;
+
+  plan->magic = 0;
+  plan->n1 = n1;
+  plan->n2 = n2;
+  plan->nb = nb;
+  plan->how = how;
+  plan->closed = closed;
+  plan->ready = 0;
+
+  // ---- coordinate extent + group code check (one small D2H) ----
+  Extent ext;
+  extent_init_kernel<<<1, 1, 0, st>>>(w.extent);
+  BF_LAUNCH_CHECK();
+  if (n1 > 0) {
+    extent_kernel<<<stream_grid((u64)n1, 1024), 256, 0, st>>>(nb > 1 ? grp1 : nullptr, s1, e1, (u64)n1, 1, w.extent);
+    BF_LAUNCH_CHECK();
+  }
+  if (n2 > 0) {
+    extent_kernel<<<stream_grid((u64)n2, 1024), 256, 0, st>>>(nb > 1 ? grp2 : nullptr, s2, e2, (u64)n2, 1, w.extent);
+    BF_LAUNCH_CHECK();
+  }
+  BF_CUDA(cudaMemcpyAsync(&ext, w.extent, sizeof(Extent), cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaStreamSynchronize(st));
+  if (n1 + n2 == 0) {
+    ext.cmin = 0;
+    ext.cmax = 0;
+  }
+  if (nb > 1 && n1 + n2 > 0 && (ext.gmin < 0 || ext.gmax >= nb)) {
+    set_error("bf_overlap_count: group code outside [0,%d): min %d max %d", nb, ext.gmin, ext.gmax);
+    return BF_ERR_GROUP;
+  }
+  KeyLayout L;
+  BF_TRY(make_key_layout(ext, nb, &L));
+  plan->L = L;
+  const RadixPlan rp = make_radix_plan(0, L.total_bits);
+
+  // ---- sort both sets ----
+  SortResult r1, r2;
+  BF_TRY(sort_set(nb > 1 ? grp1 : nullptr, s1, e1, n1, L, rp, w.s[0], w.radix, st, &r1));
+  BF_TRY(sort_set(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, rp, w.s[1], w.radix, st, &r2));
+  plan->key1 = r1.keys;
+  plan->id1 = r1.vals;
+  plan->key2 = r2.keys;
+  plan->id2 = r2.vals;
+
+  // ---- group segments ----
+  const unsigned seg_grid = (unsigned)ceil_div(nb + 1, 128);
+  segment_table_kernel<<<seg_grid, 128, 0, st>>>(r1.keys, n1, L, nb, w.s[0].seg);
+  BF_LAUNCH_CHECK();
+  segment_table_kernel<<<seg_grid, 128, 0, st>>>(r2.keys, n2, L, nb, w.s[1].seg);
+  BF_LAUNCH_CHECK();
+
+  // ---- running max of end' (only where an outer side needs it) ----
+  const SortResult* rs[2] = {&r1, &r2};
+  const i64 nn[2] = {n1, n2};
+  for (int k = 0; k < 2; ++k) {
+    if (w.s[k].pmax && nn[k] > 0) {
+      const unsigned tiles = (unsigned)scan_tiles((u64)nn[k]);
+      tile_max_ce_kernel<<<tiles, SC_THREADS, 0, st>>>(rs[k]->keys, (u64)nn[k], L, w.s[k].spine);
+      BF_LAUNCH_CHECK();
+      spine_scan_kernel<true><<<1, 1024, 0, st>>>(w.s[k].spine, tiles, nullptr);
+      BF_LAUNCH_CHECK();
+      running_max_ce_kernel<<<tiles, SC_THREADS, 0, st>>>(rs[k]->keys, (u64)nn[k], L, w.s[k].spine, w.s[k].pmax);
+      BF_LAUNCH_CHECK();
+    }
+  }
+
+  // ---- search + count ----
+  if (need1) {
+    BF_CUDA(cudaMemsetAsync(w.s[0].ucnt, 0, (nb + 1) * sizeof(u64), st));
+    if (n1 > 0) BF_CUDA(cudaMemsetAsync(w.s[0].rowflag, 0, (size_t)n1, st));
+  }
+  if (need2) {
+    BF_CUDA(cudaMemsetAsync(w.s[1].ucnt, 0, (nb + 1) * sizeof(u64), st));
+    if (n2 > 0) BF_CUDA(cudaMemsetAsync(w.s[1].rowflag, 0, (size_t)n2, st));
+  }
+  if (n1 > 0) {
+    const unsigned tiles = (unsigned)scan_tiles((u64)n1);
+    if (need1)
+      search_count_kernel<false, true><<<tiles, SC_THREADS, 0, st>>>(
+          r1.keys, r1.vals, n1, r2.keys, n2, w.s[1].pmax, L, closed, w.s[0].lo, w.s[0].cnt, w.s[0].spine,
+          w.s[0].rowflag, w.s[0].ucnt);
+    else
+      search_count_kernel<false, false><<<tiles, SC_THREADS, 0, st>>>(
+          r1.keys, r1.vals, n1, r2.keys, n2, nullptr, L, closed, w.s[0].lo, w.s[0].cnt, w.s[0].spine, nullptr,
+          nullptr);
+    BF_LAUNCH_CHECK();
+  }
+  if (n2 > 0) {
+    const unsigned tiles = (unsigned)scan_tiles((u64)n2);
+    if (need2)
+      search_count_kernel<true, true><<<tiles, SC_THREADS, 0, st>>>(
+          r2.keys, r2.vals, n2, r1.keys, n1, w.s[0].pmax, L, closed, w.s[1].lo, w.s[1].cnt, w.s[1].spine,
+          w.s[1].rowflag, w.s[1].ucnt);
+    else
+      search_count_kernel<true, false><<<tiles, SC_THREADS, 0, st>>>(
+          r2.keys, r2.vals, n2, r1.keys, n1, nullptr, L, closed, w.s[1].lo, w.s[1].cnt, w.s[1].spine, nullptr,
+          nullptr);
+    BF_LAUNCH_CHECK();
+  }
+  BF_TRY(exclusive_sum_u32(w.s[0].cnt, (u64)n1, w.s[0].spine, true, w.s[0].scan, st));
+  BF_TRY(exclusive_sum_u32(w.s[1].cnt, (u64)n2, w.s[1].spine, true, w.s[1].scan, st));
+
+  // ---- unpaired lists: compact in row order, partition by group ----
+  BF_CUDA(cudaMemsetAsync(w.nU, 0, 2 * sizeof(u64), st));
+  const i32* grps[2] = {nb > 1 ? grp1 : nullptr, nb > 1 ? grp2 : nullptr};
+  u64* ukeys_sorted[2] = {nullptr, nullptr};
+  for (int k = 0; k < 2; ++k) {
+    const bool need = k == 0 ? need1 : need2;
+    if (!need || nn[k] == 0) continue;
+    const unsigned tiles = (unsigned)scan_tiles((u64)nn[k]);
+    tile_count_flags_kernel<<<tiles, SC_THREADS, 0, st>>>(w.s[k].rowflag, (u64)nn[k], w.s[k].uspine);
+    BF_LAUNCH_CHECK();
+    spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.s[k].uspine, tiles, w.nU + k);
+    BF_LAUNCH_CHECK();
+    compact_unpaired_kernel<<<tiles, SC_THREADS, 0, st>>>(w.s[k].rowflag, grps[k], (u64)nn[k], w.s[k].uspine,
+                                                          w.s[k].ukeyA);
+    BF_LAUNCH_CHECK();
+    ukeys_sorted[k] = w.s[k].ukeyA;
+    if (L.rank_bits > 0) {
+      const RadixPlan urp = make_radix_plan(32, 32 + L.rank_bits);
+      BF_CUDA(cudaMemsetAsync(w.radix.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
+      radix_hist_kernel<<<stream_grid((u64)nn[k], 4096), 256, 0, st>>>(w.s[k].ukeyA, 0, w.nU + k, urp, w.radix.hist);
+      BF_LAUNCH_CHECK();
+      SortResult ur;
+      BF_TRY(radix_sort_passes<false>(w.s[k].ukeyA, w.s[k].ukeyB, nullptr, nullptr, false, (u64)nn[k], w.nU + k,
+                                      urp, w.radix, st, &ur));
+      ukeys_sorted[k] = ur.keys;
+    }
+  }
+  plan->ukeys1 = ukeys_sorted[0];
+  plan->ukeys2 = ukeys_sorted[1];
+
+  // ---- per-group offsets and totals ----
+  offset_table_kernel<<<1, 1, 0, st>>>(w, n1, n2, nb, how);
+  BF_LAUNCH_CHECK();
+  i64 header[8];
+  BF_CUDA(cudaMemcpyAsync(header, w.header, sizeof(header), cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaStreamSynchronize(st));
+  plan->n_rows = header[0];
+  plan->n_pairs = header[1];
+  plan->nU1 = header[2];
+  plan->nU2 = header[3];
+  plan->totA = header[4];
+  plan->totB = header[5];
+  plan->magic = OVERLAP_MAGIC;
+  plan->ready = 1;
+  return BF_OK;
+}
+
+static int overlap_emit_impl(const OverlapPlan* plan, void* ws_ptr, i64* ev1, i64* ev2, cudaStream_t st) {
+  if (!plan || plan->magic != OVERLAP_MAGIC || !plan->ready) {
+    set_error("bf_overlap_emit: plan was not produced by a successful bf_overlap_count");
+    return BF_ERR_STATE;
+  }
+  if (plan->n_rows > 0 && (!ev1 || !ev2)) {
+    set_error("bf_overlap_emit: null output pointer");
+    return BF_ERR_ARG;
+  }
+  Arena arena(ws_ptr);
+  OverlapWS w;
+  layout_overlap(arena, plan->n1, plan->n2, plan->nb, plan->how, &w);
+  if (plan->totA > 0) {
+    const unsigned grid = (unsigned)ceil_div(plan->totA, EM_TILE);
+    emit_pairs_kernel<false><<<grid, EM_THREADS, 0, st>>>(w.s[0].scan, w.s[0].lo, plan->n1, plan->id1, plan->id2,
+                                                          plan->totA, w.cumA, w.deltaA, plan->nb, ev1, ev2);
+    BF_LAUNCH_CHECK();
+  }
+  if (plan->totB > 0) {
+    const unsigned grid = (unsigned)ceil_div(plan->totB, EM_TILE);
+    emit_pairs_kernel<true><<<grid, EM_THREADS, 0, st>>>(w.s[1].scan, w.s[1].lo, plan->n2, plan->id2, plan->id1,
+                                                         plan->totB, w.cumB, w.deltaB, plan->nb, ev1, ev2);
+    BF_LAUNCH_CHECK();
+  }
+  if (plan->nU1 > 0) {
+    emit_unpaired_kernel<false><<<(unsigned)ceil_div(plan->nU1, 256), 256, 0, st>>>(plan->ukeys1, plan->nU1,
+                                                                                    w.ustart1, w.ubase1, ev1, ev2);
+    BF_LAUNCH_CHECK();
+  }
+  if (plan->nU2 > 0) {
+    emit_unpaired_kernel<true><<<(unsigned)ceil_div(plan->nU2, 256), 256, 0, st>>>(plan->ukeys2, plan->nU2,
+                                                                                   w.ustart2, w.ubase2, ev1, ev2);
+    BF_LAUNCH_CHECK();
+  }
+  return BF_OK;
+}
+
+}  // namespace bf
+
+extern "C" {
+
+size_t bf_overlap_workspace_bytes(int64_t n1, int64_t n2, int32_t n_groups, int32_t how) {
+  if (n1 < 0 || n2 < 0 || n_groups < 1) return 0;
+  bf::Arena a(nullptr);
+  bf::OverlapWS w;
+  bf::layout_overlap(a, n1, n2, n_groups, how, &w);
+  return a.off;
+}
+
+int bf_overlap_count(const int32_t* grp1, const int64_t* start1, const int64_t* end1, int64_t n1,
+                     const int32_t* grp2, const int64_t* start2, const int64_t* end2, int64_t n2,
+                     int32_t n_groups, int32_t how, int32_t closed, void* ws, size_t ws_bytes, bf_plan* plan,
+                     void* stream, int64_t* n_rows_out, int64_t* n_pairs_out) {
+  bf::OverlapPlan* p = (bf::OverlapPlan*)plan;
+  int rc = bf::overlap_count_impl((const i32*)grp1, (const i64*)start1, (const i64*)end1, n1, (const i32*)grp2,
+                                  (const i64*)start2, (const i64*)end2, n2, n_groups, how, closed, ws, ws_bytes, p,
+                                  (cudaStream_t)stream);
+  if (rc == BF_OK) {
+    if (n_rows_out) *n_rows_out = p->n_rows;
+    if (n_pairs_out) *n_pairs_out = p->n_pairs;
+  }
+  return rc;
+}
+
+int bf_overlap_emit(const bf_plan* plan, void* ws, int64_t* events1_out, int64_t* events2_out, void* stream) {
+  return bf::overlap_emit_impl((const bf::OverlapPlan*)plan, ws, (i64*)events1_out, (i64*)events2_out,
+                               (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+/* bioframe_b200 -- C ABI of the B200-native interval engine.
+ *
+ * Drop-in boundary for the hot path of open2c/bioframe v0.8.0.  The reference
+ * is pure Python and has no FFI of its own; its seams are the frame-level
+ * helpers `_overlap_intidxs` (src/bioframe/ops.py:242-338) and
+ * `_closest_intidxs` (ops.py:919-1040), the group loops of cluster/merge
+ * (ops.py:637-674, 776-810), complement (ops.py:1644-1685), coverage
+ * (ops.py:842-916) and the array functions of src/bioframe/core/arrops.py.
+ * Each entry point below names the reference lines it replaces.  A maintainer
+ * binds them with ctypes; `bioframe_b200/_lib.py` is that
+ * binding.
+ *
+ * Conventions
+ *  - Every data pointer is a DEVICE pointer owned by the caller (e.g. a torch
+ *    CUDA tensor): int32 group codes, int64 starts/ends, int64 outputs.  The
+ *    callee never frees or retains them.  `ws` is caller-owned device scratch of
+ *    at least `*_workspace_bytes(...)` bytes; it carries state from a `_count`
+ *    call to the matching `_emit` call and must not be touched in between.
+ *  - Group codes are the RANK of the row's group in the order the reference
+ *    would visit the groups (set order for overlap/closest, sorted key order
+ *    for cluster/merge; computed by the Python glue), in [0, n_groups).  Rows
+ *    of different groups never interact, so one call covers all chromosomes.
+ *  - Variable-length results are two-phase: `_count` sizes the output and
+ *    returns the row count (it synchronises `stream` once or twice to read it
+ *    back), the caller allocates, `_emit` fills.
+ *  - Return value: 0 = ok, negative = error (BF_ERR_*); `bf_last_error()` gives
+ *    a thread-local message.  No C++ exception crosses the ABI.
+ *  - Calls enqueue on `stream` (a cudaStream_t passed as void*), are re-entrant
+ *    per (device, stream), and keep no global mutable state.
+ *  - Row counts per set must be < 2^31.
+ */
+#ifndef BIOFRAME_B200_H
+#define BIOFRAME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BF_OK 0
+#define BF_ERR_ARG -1
+#define BF_ERR_WORKSPACE -2
+#define BF_ERR_RANGE -3
+#define BF_ERR_CUDA -4
+#define BF_ERR_GROUP -5
+#define BF_ERR_STATE -6
+
+/* how= of bioframe.overlap (ops.py:361) */
+#define BF_HOW_INNER 0
+#define BF_HOW_LEFT 1
+#define BF_HOW_RIGHT 2
+#define BF_HOW_OUTER 3
+
+/* Opaque per-call state written by a *_count call and read by *_emit. */
+typedef struct bf_plan {
+  int64_t opaque[96];
+} bf_plan;
+
+const char* bf_last_error(void);
+int bf_version(void);
+
+/* ---- overlap: replaces ops._overlap_intidxs (ops.py:242-338), i.e. the
+ * per-group loop around arrops.overlap_intervals (arrops.py:290-375) plus
+ * ops._minus (ops.py:228-239).  Output rows, per group in code order:
+ * A-block pairs, B-block pairs (arrops.py:357-368), then (unpaired1, -1)
+ * ascending (how left/outer), then (-1, unpaired2) ascending (how right/outer).
+ * `closed` is the closed= flag of arrops.overlap_intervals. */
+size_t bf_overlap_workspace_bytes(int64_t n1, int64_t n2, int32_t n_groups, int32_t how);
+int bf_overlap_count(const int32_t* grp1, const int64_t* start1, const int64_t* end1, int64_t n1,
+                     const int32_t* grp2, const int64_t* start2, const int64_t* end2, int64_t n2,
+                     int32_t n_groups, int32_t how, int32_t closed, void* ws, size_t ws_bytes,
+                     bf_plan* plan, void* stream, int64_t* n_rows_out, int64_t* n_pairs_out);
+int bf_overlap_emit(const bf_plan* plan, void* ws, int64_t* events1_out, int64_t* events2_out,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIOFRAME_B200_H */
