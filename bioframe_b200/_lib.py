@@ -41,6 +41,11 @@ _sz = C.c_size_t
 SIGNATURES = {
     "bf_last_error": (C.c_char_p, []),
     "bf_version": (C.c_int, []),
+    "bf_prof_enable": (C.c_int, [C.c_int]),
+    "bf_prof_reset": (C.c_int, []),
+    "bf_prof_num_classes": (C.c_int, []),
+    "bf_prof_class_name": (C.c_char_p, [C.c_int]),
+    "bf_prof_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "bf_overlap_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "bf_overlap_count": (
         C.c_int,
@@ -80,3 +85,25 @@ def check(rc, what):
         if rc == -3:
             raise OverflowError(f"{what}: {kind}: {msg}")
         raise EngineError(f"{what}: {kind}: {msg}")
+
+
+def prof_enable(on=True):
+    lib().bf_prof_enable(1 if on else 0)
+
+
+def prof_reset():
+    lib().bf_prof_reset()
+
+
+def prof_read():
+    """-> {class_name: dict(ms, timed, launches, bytes)} for classes that launched."""
+    L = lib()
+    out = {}
+    for c in range(L.bf_prof_num_classes()):
+        ms, timed, launches, nbytes = C.c_double(0), _i64(0), _i64(0), _i64(0)
+        L.bf_prof_read(c, C.byref(ms), C.byref(timed), C.byref(launches), C.byref(nbytes))
+        if launches.value:
+            out[L.bf_prof_class_name(c).decode()] = dict(
+                ms=ms.value, timed=timed.value, launches=launches.value, bytes=nbytes.value
+            )
+    return out

@@ -36,6 +36,39 @@ void set_error(const char* fmt, ...);
 
 #define BF_LAUNCH_CHECK() BF_CUDA(cudaGetLastError())
 
+// Kernel classes for the launch counter / CUDA-event profiler (bf_prof_*).
+enum ProfClass {
+  PC_EXTENT = 0,   // coordinate extent + group-code check
+  PC_PACK,         // key packing + digit histograms
+  PC_SORT_PASS,    // onesweep radix pass (the dominant kernel)
+  PC_SORT_MISC,    // histogram scans, generic histograms, iota
+  PC_SEGMENT,      // group segment table
+  PC_RUNMAX,       // running max of end
+  PC_SEARCH,       // binary search + count
+  PC_SCAN,         // exclusive scans (spine + downsweep)
+  PC_TABLE,        // per-group offset tables
+  PC_EMIT,         // pair emission
+  PC_UNPAIRED,     // unpaired-row compaction / emission
+  PC_CLUSTER,      // cluster/merge/complement kernels
+  PC_CLOSEST,      // closest-k kernels
+  PC_COVERAGE,     // coverage kernels
+  PC_GATHER,       // misc gathers / fills
+  PC_NUM
+};
+void prof_pre(int cls, cudaStream_t st);
+void prof_post(int cls, cudaStream_t st, u64 bytes);
+
+// Every kernel launch of the library goes through this macro: it counts the
+// launch and, when profiling is enabled, brackets it with CUDA events on the
+// launching stream. `bytes` = algorithmic bytes the launch moves.
+#define BF_LAUNCH(cls, bytes, st, ...)            \
+  do {                                            \
+    bf::prof_pre((cls), (st));                    \
+    __VA_ARGS__;                                  \
+    BF_LAUNCH_CHECK();                            \
+    bf::prof_post((cls), (st), (u64)(bytes));     \
+  } while (0)
+
 #define BF_TRY(expr)           \
   do {                         \
     int _s = (expr);           \

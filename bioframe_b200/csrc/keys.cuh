@@ -100,18 +100,19 @@ static inline int make_key_layout(const Extent& x, i32 n_groups, KeyLayout* L) {
 
 // Build keys and, in the same pass over the inputs, the histograms of every
 // radix digit place (so the sort never re-reads the keys to count them).
-__global__ void __launch_bounds__(256) pack_keys_kernel(const i32* __restrict__ grp, const i64* __restrict__ s,
-                                                        const i64* __restrict__ e, u64 n, KeyLayout L,
-                                                        int point_adjust, RadixPlan rp,
-                                                        u64* __restrict__ keys, u64* __restrict__ ghist) {
-  __shared__ u32 h[RS_MAX_PASSES][RS_BINS];
-  hist_clear(h);
+__global__ void __launch_bounds__(HIST_THREADS) pack_keys_kernel(const i32* __restrict__ grp, const i64* __restrict__ s,
+                                                                 const i64* __restrict__ e, u64 n, KeyLayout L,
+                                                                 int point_adjust, RadixPlan rp,
+                                                                 u64* __restrict__ keys, u64* __restrict__ ghist) {
+  extern __shared__ u32 hist_tabs[];
+  hist_clear(hist_tabs, rp);
   __syncthreads();
-  const u64 per_block = 256ull * 8ull;
+  u32* wtab = hist_tabs + (threadIdx.x >> 5) * rp.passes * RS_BINS;
+  const u64 per_block = (u64)HIST_THREADS * 8ull;
   for (u64 base = (u64)blockIdx.x * per_block; base < n; base += (u64)gridDim.x * per_block) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      u64 i = base + (u64)j * 256 + threadIdx.x;
+      u64 i = base + (u64)j * HIST_THREADS + threadIdx.x;
       bool ok = i < n;
       u64 k = 0;
       if (ok) {
@@ -121,12 +122,15 @@ __global__ void __launch_bounds__(256) pack_keys_kernel(const i32* __restrict__ 
         k = (L.rank_bits ? (g << (2 * L.B)) : 0ull) | (((u64)a - L.cmin) << L.B) | ((u64)b - L.cmin);
         keys[i] = k;
       }
-      hist_add(h, rp, k, ok);
+      hist_add(wtab, rp, k, ok);
     }
   }
   __syncthreads();
-  hist_flush(h, rp, ghist);
+  hist_flush(hist_tabs, rp, ghist);
 }
+
+static int launch_pack_keys(const i32* grp, const i64* s, const i64* e, u64 n, const KeyLayout& L, int point_adjust,
+                            const RadixPlan& rp, u64* keys, u64* ghist, cudaStream_t st);
 
 static inline unsigned stream_grid(u64 n, u64 per_block) {
   u64 g = (n + per_block - 1) / per_block;
@@ -134,6 +138,23 @@ static inline unsigned stream_grid(u64 n, u64 per_block) {
   if (g > cap) g = cap;
   if (g == 0) g = 1;
   return (unsigned)g;
+}
+
+static int launch_pack_keys(const i32* grp, const i64* s, const i64* e, u64 n, const KeyLayout& L, int point_adjust,
+                            const RadixPlan& rp, u64* keys, u64* ghist, cudaStream_t st) {
+  const size_t smem = hist_smem_bytes(rp);
+  BF_CUDA(cudaFuncSetAttribute(pack_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BF_LAUNCH(PC_PACK, 28 * n, st,
+            pack_keys_kernel<<<stream_grid(n, 2048), HIST_THREADS, smem, st>>>(grp, s, e, n, L, point_adjust, rp, keys, ghist));
+  return BF_OK;
+}
+static int launch_radix_hist(const u64* keys, u64 n_max, const u64* n_dev, const RadixPlan& rp, u64* ghist,
+                             cudaStream_t st) {
+  const size_t smem = hist_smem_bytes(rp);
+  BF_CUDA(cudaFuncSetAttribute(radix_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BF_LAUNCH(PC_SORT_MISC, 0, st,
+            radix_hist_kernel<<<stream_grid(n_max, 4096), HIST_THREADS, smem, st>>>(keys, n_max, n_dev, rp, ghist));
+  return BF_OK;
 }
 
 }  // namespace bf

@@ -280,11 +280,15 @@ __global__ void offset_table_kernel(OverlapWS w, i64 n1, i64 n2, i32 nb, i32 how
   w.header[5] = (i64)scanB[n2];
 }
 
-// Emit one block (A or B) of pairs. Thread per output row in scan space:
-//   t -> owner row p = upper_bound(scan, t) - 1, k = t - scan[p]
-//   A: (id1[p], id2[lo[p] + k])      B: (id1[lo[q] + k], id2[q])
-// The block first brackets p with two searches so each row's search touches a
-// few hundred bytes of L1-resident scan values.
+// Emit one block (A or B) of pairs:  A: (id1[p], id2[lo[p] + k])   B: (id1[lo[q] + k], id2[q]).
+// Load-balanced over the merged sequence "owner row, its outputs, next owner
+// row, ..." (merge path): a block takes 2048 consecutive positions of that
+// sequence, so it handles at most 2048 owner rows AND at most 2048 outputs no
+// matter how skewed the fan-out is.  Two binary searches per block find its
+// rows; their scan values, lo and ids are staged in shared memory; each owner
+// marks the slot of its first output and a block-wide running max turns the
+// marks into "owner of every output slot" (the np.repeat of arrops.py:359-366
+// without a per-output search).  Stores are 8-byte, coalesced across the warp.
 constexpr int EM_THREADS = 256;
 constexpr int EM_IPT = 8;
 constexpr int EM_TILE = EM_THREADS * EM_IPT;
@@ -295,32 +299,87 @@ __global__ void __launch_bounds__(EM_THREADS)
                       const u32* __restrict__ owner_id, const u32* __restrict__ other_id, i64 total,
                       const i64* __restrict__ cum, const i64* __restrict__ delta, i32 nb,
                       i64* __restrict__ ev1, i64* __restrict__ ev2) {
+  __shared__ i64 s_rel[EM_TILE + 2];  // scan[first_item + i] - t0
+  __shared__ u32 s_lo[EM_TILE + 2];
+  __shared__ u32 s_id[EM_TILE + 2];
+  __shared__ u32 s_owner[EM_TILE];
   __shared__ i64 s_br[4];
-  const i64 t0 = (i64)blockIdx.x * EM_TILE;
-  const i64 t1 = (t0 + EM_TILE < total ? t0 + EM_TILE : total) - 1;
-  auto owner_of = [&](i64 t, i64 a, i64 b) {  // last p in [a,b) with scan[p] <= t
-    return lower_bound_by(a, b, [&](i64 p) { return (i64)scan[p] <= t; }) - 1;
+  __shared__ u32 s_wmax[EM_THREADS / 32];
+  const u32 tid = threadIdx.x;
+  const i64 W = n_owner + total;
+  const i64 D0 = (i64)blockIdx.x * EM_TILE;
+  const i64 D1 = D0 + EM_TILE < W ? D0 + EM_TILE : W;
+  // owner rows consumed before diagonal D = #{p : p + scan[p] < D}
+  auto consumed = [&](i64 D) {
+    return lower_bound_by(0, n_owner, [&](i64 p) { return p + (i64)scan[p] < D; });
   };
   auto group_of = [&](i64 t, i64 a, i64 b) {  // last c with cum[c] <= t
     return lower_bound_by(a, b, [&](i64 c) { return cum[c] <= t; }) - 1;
   };
-  if (threadIdx.x == 0) s_br[0] = owner_of(t0, 0, n_owner);
-  if (threadIdx.x == 32) s_br[1] = owner_of(t1, 0, n_owner);
-  if (threadIdx.x == 64) s_br[2] = group_of(t0, 0, nb);
-  if (threadIdx.x == 96) s_br[3] = group_of(t1, 0, nb);
+  if (tid == 0) s_br[0] = consumed(D0);
+  if (tid == 32) s_br[1] = consumed(D1);
   __syncthreads();
-  const i64 p_lo = s_br[0], p_hi = s_br[1] + 1;
+  const i64 p0 = s_br[0], p1 = s_br[1];
+  const i64 t0 = D0 - p0, t1 = D1 - p1;
+  const i32 nout = (i32)(t1 - t0);
+  if (nout <= 0) return;
+  if (tid == 64) s_br[2] = group_of(t0, 0, nb);
+  if (tid == 96) s_br[3] = group_of(t1 - 1, 0, nb);
+  const i64 first = p0 > 0 ? p0 - 1 : 0;  // owner of the first output may have started earlier
+  const i32 nitems = (i32)(p1 - first);
+  for (i32 i = tid; i <= nitems; i += EM_THREADS) {
+    s_rel[i] = (i64)scan[first + i] - t0;
+    if (i < nitems) {
+      s_lo[i] = lo[first + i];
+      s_id[i] = owner_id[first + i];
+    }
+  }
+  for (i32 x = tid; x < EM_TILE; x += EM_THREADS) s_owner[x] = 0;
+  __syncthreads();
+  for (i32 i = tid; i < nitems; i += EM_THREADS) {
+    const i64 r = s_rel[i];
+    if (s_rel[i + 1] > r && r >= 0 && r < nout) s_owner[r] = (u32)i;
+  }
+  __syncthreads();
+  {  // inclusive running max over the 2048 slots, 8 consecutive slots per thread
+    u32 v[EM_IPT];
+    u32 run = 0;
+#pragma unroll
+    for (int j = 0; j < EM_IPT; ++j) {
+      v[j] = s_owner[tid * EM_IPT + j];
+      run = v[j] > run ? v[j] : run;
+      v[j] = run;
+    }
+    u32 inc = run;
+    const u32 lane = tid & 31, w = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      u32 up = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (u32)o) inc = up > inc ? up : inc;
+    }
+    if (lane == 31) s_wmax[w] = inc;
+    u32 before = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) before = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < EM_THREADS / 32; ++i)
+      if ((u32)i < w) before = s_wmax[i] > before ? s_wmax[i] : before;
+#pragma unroll
+    for (int j = 0; j < EM_IPT; ++j) s_owner[tid * EM_IPT + j] = v[j] > before ? v[j] : before;
+  }
+  __syncthreads();
   const i64 c_lo = s_br[2], c_hi = s_br[3];
-#pragma unroll 2
+#pragma unroll 4
   for (int j = 0; j < EM_IPT; ++j) {
-    const i64 t = t0 + (i64)j * EM_THREADS + threadIdx.x;
-    if (t > t1) break;
-    const i64 p = owner_of(t, p_lo, p_hi);
-    const i64 k = t - (i64)scan[p];
+    const i32 x = j * EM_THREADS + (i32)tid;
+    if (x >= nout) break;
+    const u32 i = s_owner[x];
+    const i64 k = (i64)x - s_rel[i];
+    const i64 t = t0 + x;
     const i64 c = (c_lo == c_hi) ? c_lo : group_of(t, c_lo, c_hi + 1);
     const i64 row = t + delta[c];
-    const i64 own = owner_id[p];
-    const i64 oth = other_id[(i64)lo[p] + k];
+    const i64 own = s_id[i];
+    const i64 oth = other_id[(i64)s_lo[i] + k];
     ev1[row] = B_SIDE ? oth : own;
     ev2[row] = B_SIDE ? own : oth;
   }
@@ -392,8 +451,7 @@ static int sort_set(const i32* grp, const i64* s, const i64* e, i64 n, const Key
     return BF_OK;
   }
   BF_CUDA(cudaMemsetAsync(sc.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
-  pack_keys_kernel<<<stream_grid((u64)n, 2048), 256, 0, st>>>(grp, s, e, (u64)n, L, 1, rp, ws.keyA, sc.hist);
-  BF_LAUNCH_CHECK();
+  BF_TRY(launch_pack_keys(grp, s, e, (u64)n, L, 1, rp, ws.keyA, sc.hist, st));
   return radix_sort_passes<true>(ws.keyA, ws.keyB, ws.idA, ws.idB, true, (u64)n, nullptr, rp, sc, st, res);
 }
 
@@ -434,15 +492,12 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
 
   // ---- coordinate extent + group code check (one small D2H) ----
   Extent ext;
-  extent_init_kernel<<<1, 1, 0, st>>>(w.extent);
-  BF_LAUNCH_CHECK();
+  BF_LAUNCH(PC_EXTENT, 0, st, extent_init_kernel<<<1, 1, 0, st>>>(w.extent));
   if (n1 > 0) {
-    extent_kernel<<<stream_grid((u64)n1, 1024), 256, 0, st>>>(nb > 1 ? grp1 : nullptr, s1, e1, (u64)n1, 1, w.extent);
-    BF_LAUNCH_CHECK();
+    BF_LAUNCH(PC_EXTENT, 0, st, extent_kernel<<<stream_grid((u64)n1, 1024), 256, 0, st>>>(nb > 1 ? grp1 : nullptr, s1, e1, (u64)n1, 1, w.extent));
   }
   if (n2 > 0) {
-    extent_kernel<<<stream_grid((u64)n2, 1024), 256, 0, st>>>(nb > 1 ? grp2 : nullptr, s2, e2, (u64)n2, 1, w.extent);
-    BF_LAUNCH_CHECK();
+    BF_LAUNCH(PC_EXTENT, 0, st, extent_kernel<<<stream_grid((u64)n2, 1024), 256, 0, st>>>(nb > 1 ? grp2 : nullptr, s2, e2, (u64)n2, 1, w.extent));
   }
   BF_CUDA(cudaMemcpyAsync(&ext, w.extent, sizeof(Extent), cudaMemcpyDeviceToHost, st));
   BF_CUDA(cudaStreamSynchronize(st));
@@ -470,10 +525,8 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
 
   // ---- group segments ----
   const unsigned seg_grid = (unsigned)ceil_div(nb + 1, 128);
-  segment_table_kernel<<<seg_grid, 128, 0, st>>>(r1.keys, n1, L, nb, w.s[0].seg);
-  BF_LAUNCH_CHECK();
-  segment_table_kernel<<<seg_grid, 128, 0, st>>>(r2.keys, n2, L, nb, w.s[1].seg);
-  BF_LAUNCH_CHECK();
+  BF_LAUNCH(PC_SEGMENT, 0, st, segment_table_kernel<<<seg_grid, 128, 0, st>>>(r1.keys, n1, L, nb, w.s[0].seg));
+  BF_LAUNCH(PC_SEGMENT, 0, st, segment_table_kernel<<<seg_grid, 128, 0, st>>>(r2.keys, n2, L, nb, w.s[1].seg));
 
   // ---- running max of end' (only where an outer side needs it) ----
   const SortResult* rs[2] = {&r1, &r2};
@@ -481,12 +534,9 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   for (int k = 0; k < 2; ++k) {
     if (w.s[k].pmax && nn[k] > 0) {
       const unsigned tiles = (unsigned)scan_tiles((u64)nn[k]);
-      tile_max_ce_kernel<<<tiles, SC_THREADS, 0, st>>>(rs[k]->keys, (u64)nn[k], L, w.s[k].spine);
-      BF_LAUNCH_CHECK();
-      spine_scan_kernel<true><<<1, 1024, 0, st>>>(w.s[k].spine, tiles, nullptr);
-      BF_LAUNCH_CHECK();
-      running_max_ce_kernel<<<tiles, SC_THREADS, 0, st>>>(rs[k]->keys, (u64)nn[k], L, w.s[k].spine, w.s[k].pmax);
-      BF_LAUNCH_CHECK();
+      BF_LAUNCH(PC_RUNMAX, 0, st, tile_max_ce_kernel<<<tiles, SC_THREADS, 0, st>>>(rs[k]->keys, (u64)nn[k], L, w.s[k].spine));
+      BF_LAUNCH(PC_RUNMAX, 0, st, spine_scan_kernel<true><<<1, 1024, 0, st>>>(w.s[k].spine, tiles, nullptr));
+      BF_LAUNCH(PC_RUNMAX, 0, st, running_max_ce_kernel<<<tiles, SC_THREADS, 0, st>>>(rs[k]->keys, (u64)nn[k], L, w.s[k].spine, w.s[k].pmax));
     }
   }
 
@@ -499,29 +549,30 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
     BF_CUDA(cudaMemsetAsync(w.s[1].ucnt, 0, (nb + 1) * sizeof(u64), st));
     if (n2 > 0) BF_CUDA(cudaMemsetAsync(w.s[1].rowflag, 0, (size_t)n2, st));
   }
+  // algorithmic bytes: key read (8) + lo/cnt written (8) per row
   if (n1 > 0) {
     const unsigned tiles = (unsigned)scan_tiles((u64)n1);
-    if (need1)
-      search_count_kernel<false, true><<<tiles, SC_THREADS, 0, st>>>(
+    if (need1) {
+      BF_LAUNCH(PC_SEARCH, 16 * n1, st, search_count_kernel<false, true><<<tiles, SC_THREADS, 0, st>>>(
           r1.keys, r1.vals, n1, r2.keys, n2, w.s[1].pmax, L, closed, w.s[0].lo, w.s[0].cnt, w.s[0].spine,
-          w.s[0].rowflag, w.s[0].ucnt);
-    else
-      search_count_kernel<false, false><<<tiles, SC_THREADS, 0, st>>>(
+          w.s[0].rowflag, w.s[0].ucnt));
+    } else {
+      BF_LAUNCH(PC_SEARCH, 16 * n1, st, search_count_kernel<false, false><<<tiles, SC_THREADS, 0, st>>>(
           r1.keys, r1.vals, n1, r2.keys, n2, nullptr, L, closed, w.s[0].lo, w.s[0].cnt, w.s[0].spine, nullptr,
-          nullptr);
-    BF_LAUNCH_CHECK();
+          nullptr));
+    }
   }
   if (n2 > 0) {
     const unsigned tiles = (unsigned)scan_tiles((u64)n2);
-    if (need2)
-      search_count_kernel<true, true><<<tiles, SC_THREADS, 0, st>>>(
+    if (need2) {
+      BF_LAUNCH(PC_SEARCH, 16 * n2, st, search_count_kernel<true, true><<<tiles, SC_THREADS, 0, st>>>(
           r2.keys, r2.vals, n2, r1.keys, n1, w.s[0].pmax, L, closed, w.s[1].lo, w.s[1].cnt, w.s[1].spine,
-          w.s[1].rowflag, w.s[1].ucnt);
-    else
-      search_count_kernel<true, false><<<tiles, SC_THREADS, 0, st>>>(
+          w.s[1].rowflag, w.s[1].ucnt));
+    } else {
+      BF_LAUNCH(PC_SEARCH, 16 * n2, st, search_count_kernel<true, false><<<tiles, SC_THREADS, 0, st>>>(
           r2.keys, r2.vals, n2, r1.keys, n1, nullptr, L, closed, w.s[1].lo, w.s[1].cnt, w.s[1].spine, nullptr,
-          nullptr);
-    BF_LAUNCH_CHECK();
+          nullptr));
+    }
   }
   BF_TRY(exclusive_sum_u32(w.s[0].cnt, (u64)n1, w.s[0].spine, true, w.s[0].scan, st));
   BF_TRY(exclusive_sum_u32(w.s[1].cnt, (u64)n2, w.s[1].spine, true, w.s[1].scan, st));
@@ -534,22 +585,18 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
     const bool need = k == 0 ? need1 : need2;
     if (!need || nn[k] == 0) continue;
     const unsigned tiles = (unsigned)scan_tiles((u64)nn[k]);
-    tile_count_flags_kernel<<<tiles, SC_THREADS, 0, st>>>(w.s[k].rowflag, (u64)nn[k], w.s[k].uspine);
-    BF_LAUNCH_CHECK();
-    spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.s[k].uspine, tiles, w.nU + k);
-    BF_LAUNCH_CHECK();
-    compact_unpaired_kernel<<<tiles, SC_THREADS, 0, st>>>(w.s[k].rowflag, grps[k], (u64)nn[k], w.s[k].uspine,
-                                                          w.s[k].ukeyA);
-    BF_LAUNCH_CHECK();
+    BF_LAUNCH(PC_UNPAIRED, 0, st, tile_count_flags_kernel<<<tiles, SC_THREADS, 0, st>>>(w.s[k].rowflag, (u64)nn[k], w.s[k].uspine));
+    BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.s[k].uspine, tiles, w.nU + k));
+    BF_LAUNCH(PC_UNPAIRED, 0, st, compact_unpaired_kernel<<<tiles, SC_THREADS, 0, st>>>(w.s[k].rowflag, grps[k], (u64)nn[k], w.s[k].uspine,
+                                                          w.s[k].ukeyA));
     ukeys_sorted[k] = w.s[k].ukeyA;
     if (L.rank_bits > 0) {
       const RadixPlan urp = make_radix_plan(32, 32 + L.rank_bits);
       BF_CUDA(cudaMemsetAsync(w.radix.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
-      radix_hist_kernel<<<stream_grid((u64)nn[k], 4096), 256, 0, st>>>(w.s[k].ukeyA, 0, w.nU + k, urp, w.radix.hist);
-      BF_LAUNCH_CHECK();
+      BF_TRY(launch_radix_hist(w.s[k].ukeyA, (u64)nn[k], w.nU + k, urp, w.radix.hist, st));
       SortResult ur;
       BF_TRY(radix_sort_passes<false>(w.s[k].ukeyA, w.s[k].ukeyB, nullptr, nullptr, false, (u64)nn[k], w.nU + k,
-                                      urp, w.radix, st, &ur));
+                                      urp, w.radix, st, &ur, PC_UNPAIRED));
       ukeys_sorted[k] = ur.keys;
     }
   }
@@ -557,8 +604,7 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   plan->ukeys2 = ukeys_sorted[1];
 
   // ---- per-group offsets and totals ----
-  offset_table_kernel<<<1, 1, 0, st>>>(w, n1, n2, nb, how);
-  BF_LAUNCH_CHECK();
+  BF_LAUNCH(PC_TABLE, 0, st, offset_table_kernel<<<1, 1, 0, st>>>(w, n1, n2, nb, how));
   i64 header[8];
   BF_CUDA(cudaMemcpyAsync(header, w.header, sizeof(header), cudaMemcpyDeviceToHost, st));
   BF_CUDA(cudaStreamSynchronize(st));
@@ -586,26 +632,22 @@ static int overlap_emit_impl(const OverlapPlan* plan, void* ws_ptr, i64* ev1, i6
   OverlapWS w;
   layout_overlap(arena, plan->n1, plan->n2, plan->nb, plan->how, &w);
   if (plan->totA > 0) {
-    const unsigned grid = (unsigned)ceil_div(plan->totA, EM_TILE);
-    emit_pairs_kernel<false><<<grid, EM_THREADS, 0, st>>>(w.s[0].scan, w.s[0].lo, plan->n1, plan->id1, plan->id2,
-                                                          plan->totA, w.cumA, w.deltaA, plan->nb, ev1, ev2);
-    BF_LAUNCH_CHECK();
+    const unsigned grid = (unsigned)ceil_div(plan->totA + plan->n1, EM_TILE);
+    BF_LAUNCH(PC_EMIT, 20 * plan->totA, st, emit_pairs_kernel<false><<<grid, EM_THREADS, 0, st>>>(w.s[0].scan, w.s[0].lo, plan->n1, plan->id1, plan->id2,
+                                                          plan->totA, w.cumA, w.deltaA, plan->nb, ev1, ev2));
   }
   if (plan->totB > 0) {
-    const unsigned grid = (unsigned)ceil_div(plan->totB, EM_TILE);
-    emit_pairs_kernel<true><<<grid, EM_THREADS, 0, st>>>(w.s[1].scan, w.s[1].lo, plan->n2, plan->id2, plan->id1,
-                                                         plan->totB, w.cumB, w.deltaB, plan->nb, ev1, ev2);
-    BF_LAUNCH_CHECK();
+    const unsigned grid = (unsigned)ceil_div(plan->totB + plan->n2, EM_TILE);
+    BF_LAUNCH(PC_EMIT, 20 * plan->totB, st, emit_pairs_kernel<true><<<grid, EM_THREADS, 0, st>>>(w.s[1].scan, w.s[1].lo, plan->n2, plan->id2, plan->id1,
+                                                         plan->totB, w.cumB, w.deltaB, plan->nb, ev1, ev2));
   }
   if (plan->nU1 > 0) {
-    emit_unpaired_kernel<false><<<(unsigned)ceil_div(plan->nU1, 256), 256, 0, st>>>(plan->ukeys1, plan->nU1,
-                                                                                    w.ustart1, w.ubase1, ev1, ev2);
-    BF_LAUNCH_CHECK();
+    BF_LAUNCH(PC_UNPAIRED, 0, st, emit_unpaired_kernel<false><<<(unsigned)ceil_div(plan->nU1, 256), 256, 0, st>>>(plan->ukeys1, plan->nU1,
+                                                                                    w.ustart1, w.ubase1, ev1, ev2));
   }
   if (plan->nU2 > 0) {
-    emit_unpaired_kernel<true><<<(unsigned)ceil_div(plan->nU2, 256), 256, 0, st>>>(plan->ukeys2, plan->nU2,
-                                                                                   w.ustart2, w.ubase2, ev1, ev2);
-    BF_LAUNCH_CHECK();
+    BF_LAUNCH(PC_UNPAIRED, 0, st, emit_unpaired_kernel<true><<<(unsigned)ceil_div(plan->nU2, 256), 256, 0, st>>>(plan->ukeys2, plan->nU2,
+                                                                                   w.ustart2, w.ubase2, ev1, ev2));
   }
   return BF_OK;
 }

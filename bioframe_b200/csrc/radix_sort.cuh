@@ -68,51 +68,79 @@ static inline RadixScratch take_radix_scratch(Arena& a, u64 n_max) {
   return s;
 }
 
+// Lanes of the warp whose 8-bit digit equals this lane's. Eight ballots: the
+// hardware match.any instruction serialises over distinct values and was the
+// limiter of the first version of these kernels (profiles/r1_notes.md).
+__device__ __forceinline__ u32 match_digit8(u32 d) {
+  u32 peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const u32 m = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? m : ~m;
+  }
+  return peers;
+}
+
 // ---- histogram of all digit places, callable from any key-producing kernel ----
-// h is a [RS_MAX_PASSES][256] shared-memory table. Lanes holding the same digit
-// are merged with match.any so sorted inputs (all lanes equal) cost one atomic.
-__device__ __forceinline__ void hist_add(u32 (*h)[RS_BINS], const RadixPlan& rp, u64 key, bool valid) {
-  const u32 lane = lane_id();
+// Each warp owns a private [passes][256] table in shared memory; per key and
+// digit place the lanes holding the same digit elect a leader that adds the
+// group size with a plain load/store (shared-memory atomics run at ~2 cycles
+// per lane, far too slow for 8 digit places per key). One __syncwarp per key.
+constexpr int HIST_THREADS = 256;
+constexpr int HIST_WARPS = HIST_THREADS / 32;
+static inline size_t hist_smem_bytes(const struct RadixPlan& rp);
+
+__device__ __forceinline__ void hist_add(u32* wtab, const RadixPlan& rp, u64 key, bool valid) {
+  const u32 lt = lanemask_lt();
+  const u32 vmask = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
   for (int i = 0; i < RS_MAX_PASSES; ++i) {
     if (i < rp.passes) {
-      u32 d = (u32)(key >> rp.shift[i]) & ((1u << rp.bits[i]) - 1u);
-      u32 tagd = valid ? d : (RS_BINS + lane);
-      u32 peers = __match_any_sync(0xffffffffu, tagd);
-      if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&h[i][d], (u32)__popc(peers));
+      const u32 d = (u32)(key >> rp.shift[i]) & ((1u << rp.bits[i]) - 1u);
+      const u32 peers = match_digit8(d) & vmask;
+      if (valid && (peers & lt) == 0) wtab[i * RS_BINS + d] += (u32)__popc(peers);
     }
   }
+  __syncwarp();
 }
-__device__ __forceinline__ void hist_clear(u32 (*h)[RS_BINS]) {
-  for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_BINS; i += blockDim.x) (&h[0][0])[i] = 0;
+__device__ __forceinline__ void hist_clear(u32* tabs, const RadixPlan& rp) {
+  for (int i = threadIdx.x; i < HIST_WARPS * rp.passes * RS_BINS; i += blockDim.x) tabs[i] = 0;
 }
-__device__ __forceinline__ void hist_flush(u32 (*h)[RS_BINS], const RadixPlan& rp, u64* ghist) {
+__device__ __forceinline__ void hist_flush(const u32* tabs, const RadixPlan& rp, u64* ghist) {
   for (int i = threadIdx.x; i < rp.passes * RS_BINS; i += blockDim.x) {
-    u32 c = (&h[0][0])[i];
+    u32 c = 0;
+#pragma unroll
+    for (int w = 0; w < HIST_WARPS; ++w) c += tabs[w * rp.passes * RS_BINS + i];
     if (c) atomicAdd(&ghist[i], (u64)c);
   }
 }
+static inline size_t hist_smem_bytes(const RadixPlan& rp) {
+  return (size_t)HIST_WARPS * (rp.passes > 0 ? rp.passes : 1) * RS_BINS * sizeof(u32);
+}
 
 // Generic histogram over an existing key array (n may live on the device).
-__global__ void __launch_bounds__(256) radix_hist_kernel(const u64* __restrict__ keys, u64 n_host,
-                                                          const u64* __restrict__ n_dev, RadixPlan rp,
-                                                          u64* __restrict__ ghist) {
-  __shared__ u32 h[RS_MAX_PASSES][RS_BINS];
+// Dynamic shared memory: hist_smem_bytes(rp).
+__global__ void __launch_bounds__(HIST_THREADS) radix_hist_kernel(const u64* __restrict__ keys, u64 n_host,
+                                                                   const u64* __restrict__ n_dev, RadixPlan rp,
+                                                                   u64* __restrict__ ghist) {
+  extern __shared__ u32 hist_tabs[];
   const u64 n = n_dev ? *n_dev : n_host;
-  hist_clear(h);
+  hist_clear(hist_tabs, rp);
   __syncthreads();
-  const u64 per_block = 256ull * 16ull;
+  u32* wtab = hist_tabs + (threadIdx.x >> 5) * rp.passes * RS_BINS;
+  const u64 per_block = (u64)HIST_THREADS * 16ull;
   for (u64 base = (u64)blockIdx.x * per_block; base < n; base += (u64)gridDim.x * per_block) {
 #pragma unroll 4
     for (int j = 0; j < 16; ++j) {
-      u64 idx = base + (u64)j * 256 + threadIdx.x;
+      u64 idx = base + (u64)j * HIST_THREADS + threadIdx.x;
       bool ok = idx < n;
       u64 k = ok ? keys[idx] : 0;
-      hist_add(h, rp, k, ok);
+      hist_add(wtab, rp, k, ok);
     }
   }
   __syncthreads();
-  hist_flush(h, rp, ghist);
+  hist_flush(hist_tabs, rp, ghist);
 }
 
 // counts -> exclusive digit bases, one block per digit place
@@ -184,7 +212,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
 #pragma unroll
   for (int j = 0; j < RS_IPT; ++j) {
     u32 d = (u32)(key[j] >> shift) & dmask;
-    u32 peers = __match_any_sync(0xffffffffu, d);
+    u32 peers = match_digit8(d);
     u32 before = my_cnt[d];
     u32 ahead = __popc(peers & lt);
     lpos[j] = (u16)(before + ahead);
@@ -299,27 +327,24 @@ struct SortResult {
 template <bool HAS_VAL>
 static int radix_sort_passes(u64* kA, u64* kB, u32* vA, u32* vB, bool iota_vals, u64 n_max,
                              const u64* n_dev, const RadixPlan& rp, const RadixScratch& sc,
-                             cudaStream_t stream, SortResult* out) {
+                             cudaStream_t stream, SortResult* out, int prof_cls = PC_SORT_PASS) {
   BF_CUDA(cudaFuncSetAttribute(onesweep_pass_kernel<HAS_VAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)rs_smem_bytes(HAS_VAL)));
   if (HAS_VAL && iota_vals && n_max > 0 && rp.passes == 0) {  // nothing to sort on: identity order
-    iota_u32_kernel<<<(unsigned)ceil_div((i64)n_max, 256), 256, 0, stream>>>(vA, n_max);
-    BF_LAUNCH_CHECK();
+    BF_LAUNCH(PC_SORT_MISC, 0, stream, iota_u32_kernel<<<(unsigned)ceil_div((i64)n_max, 256), 256, 0, stream>>>(vA, n_max));
   }
   u64 *kin = kA, *kout = kB;
   u32 *vin = vA, *vout = vB;
   if (n_max > 0 && rp.passes > 0) {
     const u64 tiles = (u64)ceil_div((i64)n_max, RS_TILE);
-    radix_bases_kernel<<<rp.passes, RS_BINS, 0, stream>>>(sc.hist);
-    BF_LAUNCH_CHECK();
+    BF_LAUNCH(PC_SORT_MISC, 0, stream, radix_bases_kernel<<<rp.passes, RS_BINS, 0, stream>>>(sc.hist));
     BF_CUDA(cudaMemsetAsync(sc.status, 0, radix_status_words(n_max) * sizeof(u64), stream));
     BF_CUDA(cudaMemsetAsync(sc.tickets, 0, RS_MAX_PASSES * sizeof(u32), stream));
     for (int p = 0; p < rp.passes; ++p) {
       const u32* vsrc = (HAS_VAL && !(iota_vals && p == 0)) ? vin : nullptr;
-      onesweep_pass_kernel<HAS_VAL><<<(unsigned)tiles, RS_THREADS, rs_smem_bytes(HAS_VAL), stream>>>(
+      BF_LAUNCH(prof_cls, n_dev ? 0ull : (HAS_VAL ? 24ull : 16ull) * n_max - ((HAS_VAL && !vsrc) ? 4ull * n_max : 0ull), stream, onesweep_pass_kernel<HAS_VAL><<<(unsigned)tiles, RS_THREADS, rs_smem_bytes(HAS_VAL), stream>>>(
           kin, kout, vsrc, vout, n_max, n_dev, rp.shift[p], (1u << rp.bits[p]) - 1u, (u64)(p + 1) << 58,
-          sc.hist + (size_t)p * RS_BINS, sc.status, sc.tickets + p);
-      BF_LAUNCH_CHECK();
+          sc.hist + (size_t)p * RS_BINS, sc.status, sc.tickets + p));
       u64* tk = kin;
       kin = kout;
       kout = tk;

@@ -179,13 +179,10 @@ static int exclusive_sum_u32(const u32* counts, u64 n, u64* spine, bool spine_re
   }
   const u64 tiles = (u64)scan_tiles(n);
   if (!spine_ready) {
-    tile_sum_u32_kernel<<<(unsigned)tiles, SC_THREADS, 0, stream>>>(counts, n, spine);
-    BF_LAUNCH_CHECK();
+    BF_LAUNCH(PC_SCAN, 0, stream, tile_sum_u32_kernel<<<(unsigned)tiles, SC_THREADS, 0, stream>>>(counts, n, spine));
   }
-  spine_scan_kernel<false><<<1, 1024, 0, stream>>>(spine, tiles, nullptr);
-  BF_LAUNCH_CHECK();
-  excl_sum_u32_kernel<<<(unsigned)tiles, SC_THREADS, 0, stream>>>(counts, n, spine, out);
-  BF_LAUNCH_CHECK();
+  BF_LAUNCH(PC_SCAN, 0, stream, spine_scan_kernel<false><<<1, 1024, 0, stream>>>(spine, tiles, nullptr));
+  BF_LAUNCH(PC_SCAN, 0, stream, excl_sum_u32_kernel<<<(unsigned)tiles, SC_THREADS, 0, stream>>>(counts, n, spine, out));
   return BF_OK;
 }
 

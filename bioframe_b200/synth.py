@@ -21,7 +21,18 @@ HG38_SIZES = np.array(
 )
 
 
-def _chrom_codes(rng, n):
+def subset_fraction(chrom_ids):
+    """Share of the genome the given chromosome indices cover (for bounded samples)."""
+    return float(HG38_SIZES[list(chrom_ids)].sum() / HG38_SIZES.sum())
+
+
+def _chrom_codes(rng, n, chrom_ids=None):
+    if chrom_ids is not None:
+        ids = np.asarray(list(chrom_ids), dtype=np.int32)
+        w = HG38_SIZES[ids] / HG38_SIZES[ids].sum()
+        cdf = np.cumsum(w)
+        cdf[-1] = 1.0
+        return ids[np.searchsorted(cdf, rng.random(n), side="right")]
     p = HG38_SIZES / HG38_SIZES.sum()
     # inverse-CDF draw: much cheaper than rng.choice(p=...) at 1e8 rows
     cdf = np.cumsum(p)
@@ -51,29 +62,31 @@ def lengths(rng, n, kind):
     raise ValueError(kind)
 
 
-def make_intervals(n, seed, kind="geom1k"):
-    """-> (chrom_code int32[n], start int64[n], end int64[n]); unsorted rows."""
+def make_intervals(n, seed, kind="geom1k", chrom_ids=None):
+    """-> (chrom_code int32[n], start int64[n], end int64[n]); unsorted rows.
+    `chrom_ids` restricts the draw to a subset of chromosomes (bounded samples
+    of a workload keep its density by scaling n with `subset_fraction`)."""
     rng = np.random.default_rng(seed)
-    codes = _chrom_codes(rng, n)
+    codes = _chrom_codes(rng, n, chrom_ids)
     lens = lengths(rng, n, kind)
     starts, ends = _place(rng, codes, lens)
     return codes, starts, ends
 
 
-def make_peak_targets(n, seed, hotspot_frac=0.7, n_hotspots=200_000, window=20_000):
+def make_peak_targets(n, seed, hotspot_frac=0.7, n_hotspots=200_000, window=20_000, chrom_ids=None):
     """cfg3 targets: peak-like lengths, `hotspot_frac` of them inside
     `n_hotspots` windows of `window` bp (fan-out skew)."""
     rng = np.random.default_rng(seed)
     lens = lengths(rng, n, "peaks")
     n_hot = int(n * hotspot_frac)
-    hs_codes = _chrom_codes(rng, n_hotspots)
+    hs_codes = _chrom_codes(rng, n_hotspots, chrom_ids)
     hs_starts, _ = _place(rng, hs_codes, np.full(n_hotspots, window, dtype=np.int64))
     pick = rng.integers(0, n_hotspots, n_hot)
     codes_hot = hs_codes[pick]
     starts_hot = hs_starts[pick] + np.floor(rng.random(n_hot) * window).astype(np.int64)
     ends_hot = np.minimum(starts_hot + lens[:n_hot], HG38_SIZES[codes_hot])
     starts_hot = np.minimum(starts_hot, ends_hot - 1)
-    codes_bg = _chrom_codes(rng, n - n_hot)
+    codes_bg = _chrom_codes(rng, n - n_hot, chrom_ids)
     starts_bg, ends_bg = _place(rng, codes_bg, lens[n_hot:])
     codes = np.concatenate([codes_hot, codes_bg])
     starts = np.concatenate([starts_hot, starts_bg])

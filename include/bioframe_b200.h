@@ -61,6 +61,17 @@ typedef struct bf_plan {
 const char* bf_last_error(void);
 int bf_version(void);
 
+/* ---- launch counter and CUDA-event profiler (measurement only; used by
+ * bench.py for `gpu_launches` and the per-kernel roofline).  Launches are
+ * always counted per kernel class; while enabled every launch is bracketed by
+ * two cudaEventRecord on its stream.  bf_prof_read synchronises the pending
+ * events.  `bytes` = algorithmic bytes of the launches. */
+int bf_prof_enable(int on);
+int bf_prof_reset(void);
+int bf_prof_num_classes(void);
+const char* bf_prof_class_name(int cls);
+int bf_prof_read(int cls, double* ms_total, int64_t* timed_launches, int64_t* launches, int64_t* bytes);
+
 /* ---- overlap: replaces ops._overlap_intidxs (ops.py:242-338), i.e. the
  * per-group loop around arrops.overlap_intervals (arrops.py:290-375) plus
  * ops._minus (ops.py:228-239).  Output rows, per group in code order:

@@ -74,6 +74,47 @@ def overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, group
     return np.concatenate(out1).astype(np.int64), np.concatenate(out2).astype(np.int64)
 
 
+def overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, n_groups, how="inner", closed=False):
+    """`overlap_intidxs` on group-coded arrays with the groups visited in code
+    order -- the same contract as the C ABI's bf_overlap_* (ops.py:301-338)."""
+    g1, g2 = np.asarray(g1), np.asarray(g2)
+    take_left = how in ("left", "outer")
+    take_right = how in ("right", "outer")
+    out1, out2 = [], []
+    if n_groups == 1:
+        rows1 = [np.arange(len(s1))]
+        rows2 = [np.arange(len(s2))]
+    else:
+        o1 = np.argsort(g1, kind="stable")
+        o2 = np.argsort(g2, kind="stable")
+        b1 = np.searchsorted(g1[o1], np.arange(n_groups + 1))
+        b2 = np.searchsorted(g2[o2], np.arange(n_groups + 1))
+        rows1 = [o1[b1[c] : b1[c + 1]] for c in range(n_groups)]
+        rows2 = [o2[b2[c] : b2[c + 1]] for c in range(n_groups)]
+    for r1, r2 in zip(rows1, rows2):
+        if len(r1) and len(r2):
+            i, j = ao.overlap_intervals(s1[r1], e1[r1], s2[r2], e2[r2], closed=closed)
+            out1.append(r1[i])
+            out2.append(r2[j])
+            if take_left:
+                lone = np.setdiff1d(np.arange(len(r1)), i)
+                out1.append(r1[lone])
+                out2.append(np.full(len(lone), -1))
+            if take_right:
+                lone = np.setdiff1d(np.arange(len(r2)), j)
+                out1.append(np.full(len(lone), -1))
+                out2.append(r2[lone])
+        elif len(r1) and take_left:
+            out1.append(r1)
+            out2.append(np.full(len(r1), -1))
+        elif len(r2) and take_right:
+            out1.append(np.full(len(r2), -1))
+            out2.append(r2)
+    if not out1:
+        return np.empty(0, np.int64), np.empty(0, np.int64)
+    return np.concatenate(out1).astype(np.int64), np.concatenate(out2).astype(np.int64)
+
+
 def closest_intidxs(
     df1,
     df2=None,

@@ -5,31 +5,11 @@ import pytest
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
-from oracle import arrops_oracle as ao  # noqa: E402
+from oracle import ops_oracle as oo  # noqa: E402
 
 
 def _oracle_frame(g1, s1, e1, g2, s2, e2, nb, how):
-    """Group-coded restatement of ops._overlap_intidxs with groups in code order."""
-    out1, out2 = [], []
-    for c in range(nb):
-        r1 = np.flatnonzero(g1 == c)
-        r2 = np.flatnonzero(g2 == c)
-        if len(r1) and len(r2):
-            i, j = ao.overlap_intervals(s1[r1], e1[r1], s2[r2], e2[r2])
-            out1.append(r1[i]); out2.append(r2[j])
-            if how in ("left", "outer"):
-                u = np.setdiff1d(np.arange(len(r1)), i)
-                out1.append(r1[u]); out2.append(np.full(len(u), -1))
-            if how in ("right", "outer"):
-                u = np.setdiff1d(np.arange(len(r2)), j)
-                out1.append(np.full(len(u), -1)); out2.append(r2[u])
-        elif len(r1) and how in ("left", "outer"):
-            out1.append(r1); out2.append(np.full(len(r1), -1))
-        elif len(r2) and how in ("right", "outer"):
-            out1.append(np.full(len(r2), -1)); out2.append(r2)
-    if not out1:
-        return np.empty(0, np.int64), np.empty(0, np.int64)
-    return np.concatenate(out1).astype(np.int64), np.concatenate(out2).astype(np.int64)
+    return oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, nb, how)
 
 
 def _rand(rng, n, nb, span, maxlen, p_point=0.1, neg=False):
