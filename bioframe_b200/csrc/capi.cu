@@ -31,7 +31,7 @@ static long long g_launches[PC_NUM];
 static long long g_bytes[PC_NUM];
 static double g_ms[PC_NUM];
 static long long g_timed[PC_NUM];
-static const char* const g_names[PC_NUM] = {"extent",  "pack_keys", "sort_pass", "sort_misc", "segment_table",
+static const char* const g_names[PC_NUM] = {"extent",  "pack_keys", "sort_pass", "sort_misc", "tie_fix", "segment_table",
                                             "running_max", "search_count", "scan", "offset_table", "emit_pairs",
                                             "unpaired", "cluster", "closest", "coverage", "gather"};
 

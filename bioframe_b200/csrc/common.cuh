@@ -42,6 +42,7 @@ enum ProfClass {
   PC_PACK,         // key packing + digit histograms
   PC_SORT_PASS,    // onesweep radix pass (the dominant kernel)
   PC_SORT_MISC,    // histogram scans, generic histograms, iota
+  PC_TIEFIX,       // (end', row) order among rows sharing (group, start)
   PC_SEGMENT,      // group segment table
   PC_RUNMAX,       // running max of end
   PC_SEARCH,       // binary search + count

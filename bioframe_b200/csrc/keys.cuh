@@ -1,18 +1,22 @@
 // Sort-key construction shared by overlap / cluster / closest / coverage.
 //
 // Every row becomes ONE 64-bit key
-//     key = group_rank << (2B) | (start - cmin) << B | (end' - cmin)
-// where B = bit width of the coordinate span of the whole call and end' is the
-// point-adjusted end (end + (end == start), arrops.py:271-287) for overlap or
-// the raw end for merge.  One stable LSD radix sort of these keys with the row
-// number as payload gives, for all chromosomes at once, exactly the order
-// np.lexsort([ends, starts]) gives per chromosome (arrops.py:332-333, 459) with
-// the chromosomes laid out in group-rank order.  For hg38 coordinates and 24
-// chromosomes that is 5 + 28 + 28 = 61 bits.  After the sort
-// the key alone yields the composite search values
-//     cs(key) = key >> B                        (group, start)
-//     ce(key) = (key >> 2B) << B | key & mask   (group, end')
-// so the binary searches and running maxima never touch the input columns again.
+//     key = ( group_rank << B | (start - cmin) ) << LB  |  (end' - start)
+// with B = bit width of the coordinate span of the whole call, LB = bit width
+// of the longest interval, and end' the point-adjusted end (end + (end ==
+// start), arrops.py:271-287) for overlap or the raw end for merge.
+//
+// The reference orders each chromosome with np.lexsort([ends, starts])
+// (arrops.py:332-333, 459): by start, ties by end, ties by row.  Here ONE stable
+// LSD radix sort over the HIGH field only -- cs = (group, start), 5 + 28 = 33
+// bits for hg38 -- orders all chromosomes at once; rows that share (group,
+// start) (a few percent of real data) are then put in (end', row) order by a
+// fix-up that extracts just those rows, sorts them by the full key and writes
+// them back into the same slots (tie_fix in overlap.cu).  The length bits ride
+// along in the key, so after the sort the key alone yields
+//     cs(key) = key >> LB                 (group, start)
+//     ce(key) = cs(key) + (key & lmask)   (group, end')
+// and the searches and running maxima never touch the input columns again.
 #pragma once
 #include "common.cuh"
 #include "radix_sort.cuh"
@@ -20,44 +24,51 @@
 namespace bf {
 
 struct KeyLayout {
-  int B;          // bits per coordinate field
+  int B;          // bits of the coordinate field
+  int LB;         // bits of the length field
   int rank_bits;  // bits of the group rank
-  int total_bits; // rank_bits + 2B
+  int total_bits; // rank_bits + B + LB
   u64 cmin;       // coordinate origin (two's complement image of the int64 minimum)
-  u64 fmask;      // (1 << B) - 1
+  u64 lmask;      // (1 << LB) - 1
 };
 
-__host__ __device__ __forceinline__ u64 key_cs(u64 k, const KeyLayout& L) { return k >> L.B; }
-__host__ __device__ __forceinline__ u64 key_ce(u64 k, const KeyLayout& L) {
-  return ((k >> (2 * L.B)) << L.B) | (k & L.fmask);
+__host__ __device__ __forceinline__ u64 key_cs(u64 k, const KeyLayout& L) { return k >> L.LB; }
+__host__ __device__ __forceinline__ u64 key_ce(u64 k, const KeyLayout& L) { return (k >> L.LB) + (k & L.lmask); }
+__host__ __device__ __forceinline__ u32 key_rank(u64 k, const KeyLayout& L) {
+  return L.rank_bits ? (u32)(k >> (L.LB + L.B)) : 0u;
 }
-__host__ __device__ __forceinline__ u32 key_rank(u64 k, const KeyLayout& L) { return (u32)(k >> (2 * L.B)); }
-__host__ __device__ __forceinline__ u64 key_soff(u64 k, const KeyLayout& L) { return (k >> L.B) & L.fmask; }
-__host__ __device__ __forceinline__ u64 key_eoff(u64 k, const KeyLayout& L) { return k & L.fmask; }
 
 struct Extent {  // device-side reduction target
   i64 cmin, cmax;
+  i64 lmin, lmax;  // min / max of end' - start
   i32 gmin, gmax;
 };
 
 __global__ void extent_init_kernel(Extent* x) {
   x->cmin = 0x7fffffffffffffffLL;
   x->cmax = (i64)0x8000000000000000ULL;
+  x->lmin = 0x7fffffffffffffffLL;
+  x->lmax = (i64)0x8000000000000000ULL;
   x->gmin = 0x7fffffff;
   x->gmax = (i32)0x80000000;
 }
 
-// min/max of coordinates (end' when point_adjust) and of group codes
+// min/max of coordinates (end' when point_adjust), of lengths and of group codes
 __global__ void __launch_bounds__(256) extent_kernel(const i32* __restrict__ grp, const i64* __restrict__ s,
                                                      const i64* __restrict__ e, u64 n, int point_adjust,
                                                      Extent* __restrict__ out) {
   i64 lo = 0x7fffffffffffffffLL, hi = (i64)0x8000000000000000ULL;
+  i64 llo = 0x7fffffffffffffffLL, lhi = (i64)0x8000000000000000ULL;
   i32 glo = 0x7fffffff, ghi = (i32)0x80000000;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
     i64 a = s[i], b = e[i];
     if (point_adjust && a == b) b += 1;
     lo = min(lo, min(a, b));
     hi = max(hi, max(a, b));
+    // length in wrapping arithmetic; a span that overflows int64 shows up as negative
+    const i64 len = (i64)((u64)b - (u64)a);
+    llo = min(llo, len);
+    lhi = max(lhi, len);
     if (grp) {
       i32 g = grp[i];
       glo = min(glo, g);
@@ -68,12 +79,16 @@ __global__ void __launch_bounds__(256) extent_kernel(const i32* __restrict__ grp
   for (int o = 16; o > 0; o >>= 1) {
     lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    llo = min(llo, __shfl_xor_sync(0xffffffffu, llo, o));
+    lhi = max(lhi, __shfl_xor_sync(0xffffffffu, lhi, o));
     glo = min(glo, __shfl_xor_sync(0xffffffffu, glo, o));
     ghi = max(ghi, __shfl_xor_sync(0xffffffffu, ghi, o));
   }
   if (lane_id() == 0) {
     atomicMin(&out->cmin, lo);
     atomicMax(&out->cmax, hi);
+    atomicMin(&out->lmin, llo);
+    atomicMax(&out->lmax, lhi);
     if (grp) {
       atomicMin(&out->gmin, glo);
       atomicMax(&out->gmax, ghi);
@@ -82,17 +97,23 @@ __global__ void __launch_bounds__(256) extent_kernel(const i32* __restrict__ grp
 }
 
 static inline int make_key_layout(const Extent& x, i32 n_groups, KeyLayout* L) {
+  if (x.lmin < 0) {
+    set_error("interval with end < start (or a span beyond int64): not a valid bedframe interval");
+    return BF_ERR_ARG;
+  }
   u64 span = (x.cmax >= x.cmin) ? (u64)x.cmax - (u64)x.cmin : 0;
   L->B = bit_width(span);
   if (L->B == 0) L->B = 1;
+  L->LB = bit_width((u64)x.lmax);
+  if (L->LB == 0) L->LB = 1;
   L->rank_bits = n_groups > 1 ? bit_width((u64)(n_groups - 1)) : 0;
-  L->total_bits = L->rank_bits + 2 * L->B;
+  L->total_bits = L->rank_bits + L->B + L->LB;
   L->cmin = (u64)x.cmin;
-  L->fmask = L->B >= 64 ? ~0ull : ((1ull << L->B) - 1ull);
-  if (L->total_bits > 64 || L->B > 31) {
-    set_error("coordinate span needs %d bits per field and %d group bits: %d > 64-bit key "
+  L->lmask = (1ull << L->LB) - 1ull;
+  if (L->total_bits > 64 || L->LB > 62) {
+    set_error("coordinates need %d group + %d start + %d length bits = %d > 64-bit key "
               "(wide-coordinate path not available for this call)",
-              L->B, L->rank_bits, L->total_bits);
+              L->rank_bits, L->B, L->LB, L->total_bits);
     return BF_ERR_RANGE;
   }
   return BF_OK;
@@ -119,7 +140,7 @@ __global__ void __launch_bounds__(HIST_THREADS) pack_keys_kernel(const i32* __re
         i64 a = s[i], b = e[i];
         if (point_adjust && a == b) b += 1;
         u64 g = grp ? (u64)(u32)grp[i] : 0ull;
-        k = (L.rank_bits ? (g << (2 * L.B)) : 0ull) | (((u64)a - L.cmin) << L.B) | ((u64)b - L.cmin);
+        k = ((((L.rank_bits ? (g << L.B) : 0ull) | ((u64)a - L.cmin))) << L.LB) | ((u64)b - (u64)a);
         keys[i] = k;
       }
       hist_add(wtab, rp, k, ok);
@@ -149,10 +170,10 @@ static int launch_pack_keys(const i32* grp, const i64* s, const i64* e, u64 n, c
   return BF_OK;
 }
 static int launch_radix_hist(const u64* keys, u64 n_max, const u64* n_dev, const RadixPlan& rp, u64* ghist,
-                             cudaStream_t st) {
+                             cudaStream_t st, int prof_cls = PC_SORT_MISC) {
   const size_t smem = hist_smem_bytes(rp);
   BF_CUDA(cudaFuncSetAttribute(radix_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  BF_LAUNCH(PC_SORT_MISC, 0, st,
+  BF_LAUNCH(prof_cls, 0, st,
             radix_hist_kernel<<<stream_grid(n_max, 4096), HIST_THREADS, smem, st>>>(keys, n_max, n_dev, rp, ghist));
   return BF_OK;
 }

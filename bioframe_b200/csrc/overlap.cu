@@ -20,6 +20,8 @@
 
 namespace bf {
 
+constexpr i64 EMIT_CHUNK_BLOCKS = 1 << 16;  // emit blocks per partition chunk (fixed-size scratch)
+
 // ---------------------------------------------------------------- workspace
 struct SetWS {
   u64 *keyA, *keyB;
@@ -27,6 +29,7 @@ struct SetWS {
   u32 *lo, *cnt;
   u64 *scan;   // [n+1]
   u64 *spine;  // [tiles]
+  i64 *bracket;  // [tiles+1] window of the other set per block of sorted rows
   u64 *pmax;   // [n] running max of ce (only for outer joins on the other side)
   u8 *rowflag; // [n] 1 = row has no partner (row order)
   u64 *ukeyA, *ukeyB;  // [n] (rank << 32 | row) of unpaired rows
@@ -44,8 +47,10 @@ struct OverlapWS {
   i64 *deltaA, *deltaB;  // output row = scan-space index + delta[group]
   i64 *ubase1, *ubase2;  // first output row of the group's unpaired blocks
   i64 *ustart1, *ustart2;  // first index of the group in the partitioned unpaired lists
+  i64 *partA, *partB;    // merge-path partition of the emit blocks
   i64 *header;           // n_rows, n_pairs, nU1, nU2
   u64 *nU;               // [2] device-side unpaired totals (sort sizes)
+  u64 *nT;               // [2] device-side tied-row totals
 };
 
 static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS* w) {
@@ -61,6 +66,7 @@ static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS*
     s.cnt = a.take<u32>(n[k]);
     s.scan = a.take<u64>(n[k] + 1);
     s.spine = a.take<u64>(scan_tiles(n[k]) + 1);
+    s.bracket = a.take<i64>(scan_tiles(n[k]) + 2);
     s.seg = a.take<i64>(nb + 1);
     s.ucnt = a.take<u64>(nb + 1);
     // set k needs flags / unpaired lists when it is on the kept side; the OTHER
@@ -86,8 +92,11 @@ static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS*
   w->ubase2 = a.take<i64>(nb + 1);
   w->ustart1 = a.take<i64>(nb + 1);
   w->ustart2 = a.take<i64>(nb + 1);
+  w->partA = a.take<i64>(EMIT_CHUNK_BLOCKS + 1);
+  w->partB = a.take<i64>(EMIT_CHUNK_BLOCKS + 1);
   w->header = a.take<i64>(8);
   w->nU = a.take<u64>(2);
+  w->nT = a.take<u64>(2);
 }
 
 struct OverlapPlan {  // lives in the caller's bf_plan
@@ -166,30 +175,57 @@ __global__ void __launch_bounds__(SC_THREADS) running_max_ce_kernel(const u64* _
 //       lo = #(cs2 <  cs1), hi = #(cs2 <  ce1)   (closed: <=)     arrops.py:338-339
 //   B_SIDE == true : rows of set 2 against starts of set 1:
 //       lo = #(cs1 <= cs2), hi = #(cs1 <  ce2)   (closed: <=)     arrops.py:341-342
-// A block of 2048 consecutive sorted rows first brackets its lo range with two
-// full searches (first and last row), then every row searches inside the
-// bracket and gallops from lo to hi.
+// Both arrays are sorted, so the lo positions of a block of 2048 consecutive
+// rows form a window [bracket[b], bracket[b+1]] of the other set; a tiny
+// partition kernel finds all windows up front (one full binary search per
+// block boundary, all in parallel).  A block stages its window (+ slack for
+// the hi searches) in shared memory when it fits, searches lo inside the
+// window and gallops from lo to hi.
+constexpr int SR_STAGE = 4096;  // staged composite starts of the other set (32 KB)
+constexpr int SR_SLACK = 512;
+
+template <bool B_SIDE>
+__global__ void __launch_bounds__(256) search_partition_kernel(const u64* __restrict__ mine, i64 n,
+                                                               const u64* __restrict__ other, i64 m, KeyLayout L,
+                                                               i64 ntiles, i64* __restrict__ bracket) {
+  const i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > ntiles) return;
+  i64 row = b * SC_TILE;
+  if (row > n - 1) row = n - 1;
+  const u64 x = key_cs(mine[row], L);
+  bracket[b] = B_SIDE ? lower_bound_by(0, m, [&](i64 q) { return key_cs(other[q], L) <= x; })
+                      : lower_bound_by(0, m, [&](i64 q) { return key_cs(other[q], L) < x; });
+}
+
 template <bool B_SIDE, bool FLAGS>
 __global__ void __launch_bounds__(SC_THREADS)
     search_count_kernel(const u64* __restrict__ mine, const u32* __restrict__ mine_id, i64 n,
                         const u64* __restrict__ other, i64 m, const u64* __restrict__ other_pmax,
-                        KeyLayout L, int closed, u32* __restrict__ lo_out, u32* __restrict__ cnt_out,
-                        u64* __restrict__ spine, u8* __restrict__ rowflag, u64* __restrict__ ucnt) {
+                        const i64* __restrict__ bracket, KeyLayout L, int closed, u32* __restrict__ lo_out,
+                        u32* __restrict__ cnt_out, u64* __restrict__ spine, u8* __restrict__ rowflag,
+                        u64* __restrict__ ucnt) {
   __shared__ u64 s_tmp[8];
-  __shared__ i64 s_bracket[2];
+  __shared__ u64 s_other[SR_STAGE];
   const i64 base = (i64)blockIdx.x * SC_TILE;
-  const i64 last = (base + SC_TILE < n ? base + SC_TILE : n) - 1;
-  auto lo_search = [&](u64 x, i64 a, i64 b) {
-    if (B_SIDE) return lower_bound_by(a, b, [&](i64 q) { return key_cs(other[q], L) <= x; });
-    return lower_bound_by(a, b, [&](i64 q) { return key_cs(other[q], L) < x; });
-  };
-  if (threadIdx.x == 0) s_bracket[0] = lo_search(key_cs(mine[base], L), 0, m);
-  if (threadIdx.x == 32) s_bracket[1] = lo_search(key_cs(mine[last], L), 0, m);
+  const i64 br_lo = bracket[blockIdx.x], br_hi = bracket[blockIdx.x + 1];
+  i64 nst = 0;  // staged entries: other[br_lo .. br_lo + nst)
+  if (br_hi - br_lo + 1 <= SR_STAGE) {
+    nst = br_hi - br_lo + 1 + SR_SLACK;
+    if (nst > SR_STAGE) nst = SR_STAGE;
+    if (nst > m - br_lo) nst = m - br_lo;
+    for (i64 i = threadIdx.x; i < nst; i += SC_THREADS) s_other[i] = key_cs(other[br_lo + i], L);
+  }
   __syncthreads();
-  const i64 br_lo = s_bracket[0], br_hi = s_bracket[1];
+  auto oth = [&](i64 q) -> u64 {
+    const i64 r = q - br_lo;
+    return (r < nst) ? s_other[r] : key_cs(other[q], L);  // q >= br_lo always
+  };
+
+  u32 pow2_ceil = 1;
+  while ((i64)pow2_ceil < br_hi - br_lo + 1) pow2_ceil <<= 1;
 
   u64 block_sum = 0;
-#pragma unroll 2
+#pragma unroll 1
   for (int j = 0; j < SC_IPT; ++j) {
     const i64 p = base + (i64)j * SC_THREADS + threadIdx.x;
     u32 cnt = 0;
@@ -198,30 +234,83 @@ __global__ void __launch_bounds__(SC_THREADS)
     if (p < n) {
       const u64 k = mine[p];
       const u64 xs = key_cs(k, L), xe = key_ce(k, L);
-      const i64 lo = lo_search(xs, br_lo, br_hi);
-      // gallop from lo for hi
-      i64 a = lo, step = 1, b = lo;
-      while (true) {
-        b = a + step;
-        if (b >= m) {
-          b = m;
-          break;
+      i64 lo, hi;
+      if (nst > 0) {
+        // staged window: branch-free bit-step lower bound over W = br_hi - br_lo candidates
+        const u32 W = (u32)(br_hi - br_lo);
+        u32 pos = 0;
+        for (u32 step = pow2_ceil; step > 0; step >>= 1) {
+          const u32 nx = pos + step;
+          if (nx <= W) {
+            const u64 v = s_other[nx - 1];
+            const bool below = B_SIDE ? (v <= xs) : (v < xs);
+            if (below) pos = nx;
+          }
         }
-        u64 v = key_cs(other[b - 1], L);
-        bool below = closed ? (v <= xe) : (v < xe);
-        if (!below) break;
-        a = b;
-        step <<= 1;
+        lo = br_lo + pos;
+        // hi: short linear probe (fan-out is usually a handful), then gallop
+        u32 h = pos;
+        int probes = 0;
+        bool done = false;
+        while (probes < 8) {
+          if (h >= (u32)nst) break;
+          const u64 v = s_other[h];
+          const bool below = closed ? (v <= xe) : (v < xe);
+          if (!below) {
+            done = true;
+            break;
+          }
+          ++h;
+          ++probes;
+        }
+        hi = br_lo + h;
+        if (!done && hi >= m) {
+          hi = m;
+          done = true;
+        }
+        if (!done) {
+          i64 a = hi, step = 1, b = hi;
+          while (true) {
+            b = a + step;
+            if (b >= m) {
+              b = m;
+              break;
+            }
+            const u64 v = oth(b - 1);
+            const bool below = closed ? (v <= xe) : (v < xe);
+            if (!below) break;
+            a = b;
+            step <<= 1;
+          }
+          hi = closed ? lower_bound_by(a, b, [&](i64 q) { return oth(q) <= xe; })
+                      : lower_bound_by(a, b, [&](i64 q) { return oth(q) < xe; });
+        }
+      } else {
+        lo = B_SIDE ? lower_bound_by(br_lo, br_hi, [&](i64 q) { return key_cs(other[q], L) <= xs; })
+                    : lower_bound_by(br_lo, br_hi, [&](i64 q) { return key_cs(other[q], L) < xs; });
+        i64 a = lo, step = 1, b = lo;
+        while (true) {
+          b = a + step;
+          if (b >= m) {
+            b = m;
+            break;
+          }
+          const u64 v = key_cs(other[b - 1], L);
+          const bool below = closed ? (v <= xe) : (v < xe);
+          if (!below) break;
+          a = b;
+          step <<= 1;
+        }
+        hi = closed ? lower_bound_by(a, b, [&](i64 q) { return key_cs(other[q], L) <= xe; })
+                    : lower_bound_by(a, b, [&](i64 q) { return key_cs(other[q], L) < xe; });
       }
-      i64 hi = closed ? lower_bound_by(a, b, [&](i64 q) { return key_cs(other[q], L) <= xe; })
-                      : lower_bound_by(a, b, [&](i64 q) { return key_cs(other[q], L) < xe; });
       cnt = (u32)(hi - lo);
       lo_out[p] = (u32)lo;
       cnt_out[p] = cnt;
       if (FLAGS) {
         bool partner = cnt > 0;
         if (!partner && lo > 0) {
-          u64 pm = other_pmax[lo - 1];
+          const u64 pm = other_pmax[lo - 1];
           partner = closed ? (pm >= xs) : (pm > xs);
         }
         lonely = !partner;
@@ -230,10 +319,19 @@ __global__ void __launch_bounds__(SC_THREADS)
       }
     }
     if (FLAGS) {
-      // per-group unpaired counters, merged across the warp first
-      u32 tagd = lonely ? rank : 0xffffffffu - lane_id();
-      u32 peers = __match_any_sync(0xffffffffu, tagd);
-      if (lonely && (peers & lanemask_lt()) == 0) atomicAdd(&ucnt[rank], (u64)__popc(peers));
+      // per-group unpaired counters: rows are sorted by group, so a warp almost
+      // always holds one group -> one atomic per warp; mixed warps fall back
+      const u32 lone_mask = __ballot_sync(0xffffffffu, lonely);
+      if (lone_mask) {
+        const u32 lead = __ffs(lone_mask) - 1;
+        const u32 rank0 = __shfl_sync(0xffffffffu, rank, lead);
+        const bool same = __all_sync(0xffffffffu, !lonely || rank == rank0);
+        if (same) {
+          if (lane_id() == lead) atomicAdd(&ucnt[rank0], (u64)__popc(lone_mask));
+        } else if (lonely) {
+          atomicAdd(&ucnt[rank], 1ull);
+        }
+      }
     }
     block_sum += cnt;
   }
@@ -293,12 +391,25 @@ constexpr int EM_THREADS = 256;
 constexpr int EM_IPT = 8;
 constexpr int EM_TILE = EM_THREADS * EM_IPT;
 
+// part[b] = owner rows consumed before diagonal b * EM_TILE = #{p : p + scan[p] < D}.
+// One thread per block boundary, so the ~27-step searches of all blocks run
+// side by side instead of at the head of every emit block.
+__global__ void __launch_bounds__(256) emit_partition_kernel(const u64* __restrict__ scan, i64 n_owner, i64 total,
+                                                             i64 block0, i64 nparts, i64* __restrict__ part) {
+  const i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nparts) return;
+  const i64 W = n_owner + total;
+  i64 D = (block0 + b) * EM_TILE;
+  if (D > W) D = W;
+  part[b] = lower_bound_by(0, n_owner, [&](i64 p) { return p + (i64)scan[p] < D; });
+}
+
 template <bool B_SIDE>
 __global__ void __launch_bounds__(EM_THREADS)
     emit_pairs_kernel(const u64* __restrict__ scan, const u32* __restrict__ lo, i64 n_owner,
                       const u32* __restrict__ owner_id, const u32* __restrict__ other_id, i64 total,
-                      const i64* __restrict__ cum, const i64* __restrict__ delta, i32 nb,
-                      i64* __restrict__ ev1, i64* __restrict__ ev2) {
+                      i64 block0, const i64* __restrict__ part, const i64* __restrict__ cum, const i64* __restrict__ delta,
+                      i32 nb, i64* __restrict__ ev1, i64* __restrict__ ev2) {
   __shared__ i64 s_rel[EM_TILE + 2];  // scan[first_item + i] - t0
   __shared__ u32 s_lo[EM_TILE + 2];
   __shared__ u32 s_id[EM_TILE + 2];
@@ -307,17 +418,15 @@ __global__ void __launch_bounds__(EM_THREADS)
   __shared__ u32 s_wmax[EM_THREADS / 32];
   const u32 tid = threadIdx.x;
   const i64 W = n_owner + total;
-  const i64 D0 = (i64)blockIdx.x * EM_TILE;
+  const i64 D0 = (block0 + (i64)blockIdx.x) * EM_TILE;
   const i64 D1 = D0 + EM_TILE < W ? D0 + EM_TILE : W;
-  // owner rows consumed before diagonal D = #{p : p + scan[p] < D}
-  auto consumed = [&](i64 D) {
-    return lower_bound_by(0, n_owner, [&](i64 p) { return p + (i64)scan[p] < D; });
-  };
   auto group_of = [&](i64 t, i64 a, i64 b) {  // last c with cum[c] <= t
     return lower_bound_by(a, b, [&](i64 c) { return cum[c] <= t; }) - 1;
   };
-  if (tid == 0) s_br[0] = consumed(D0);
-  if (tid == 32) s_br[1] = consumed(D1);
+  if (tid == 0) {
+    s_br[0] = part[blockIdx.x];
+    s_br[1] = part[blockIdx.x + 1];
+  }
   __syncthreads();
   const i64 p0 = s_br[0], p1 = s_br[1];
   const i64 t0 = D0 - p0, t1 = D1 - p1;
@@ -438,21 +547,98 @@ __global__ void __launch_bounds__(256) emit_unpaired_kernel(const u64* __restric
   ev2[out] = SECOND ? row : -1;
 }
 
+// ---- tie fix-up: rows sharing (group, start) into (end', row) order ----
+// After the stable sort on cs the rows of a tie run are in row order; the
+// reference wants them by (end', row).  Tied rows are rare, so: count them,
+// compact (key, id, slot), sort that subset by the FULL key (stable, so equal
+// keys keep row order) and write it back into the same slots in order.
+__device__ __forceinline__ bool row_is_tied(const u64* __restrict__ keys, u64 p, u64 n, const KeyLayout& L) {
+  const u64 c = key_cs(keys[p], L);
+  return (p > 0 && key_cs(keys[p - 1], L) == c) || (p + 1 < n && key_cs(keys[p + 1], L) == c);
+}
+__global__ void __launch_bounds__(SC_THREADS) tie_count_kernel(const u64* __restrict__ keys, u64 n, KeyLayout L,
+                                                               u64* __restrict__ spine) {
+  __shared__ u64 s_tmp[8];
+  const u64 base = (u64)blockIdx.x * SC_TILE;
+  u64 acc = 0;
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    const u64 p = base + (u64)j * SC_THREADS + threadIdx.x;
+    if (p < n && row_is_tied(keys, p, n, L)) ++acc;
+  }
+  acc = block_sum_u64(acc, s_tmp);
+  if (threadIdx.x == 0) spine[blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(SC_THREADS)
+    tie_compact_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, KeyLayout L,
+                       const u64* __restrict__ spine, u64* __restrict__ tkeys, u32* __restrict__ tids,
+                       u32* __restrict__ tpos) {
+  __shared__ u64 s_tmp[8];
+  const u64 base = (u64)blockIdx.x * SC_TILE + (u64)threadIdx.x * SC_IPT;
+  u32 mask = 0;
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    const u64 p = base + j;
+    if (p < n && row_is_tied(keys, p, n, L)) mask |= 1u << j;
+  }
+  u64 tot;
+  u64 at = spine[blockIdx.x] + block_excl_sum_u64((u64)__popc(mask), s_tmp, &tot);
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    if (mask & (1u << j)) {
+      const u64 p = base + j;
+      tkeys[at] = keys[p];
+      tids[at] = ids[p];
+      tpos[at] = (u32)p;
+      ++at;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) tie_scatter_kernel(const u64* __restrict__ tkeys, const u32* __restrict__ tids,
+                                                          const u32* __restrict__ tpos, const u64* __restrict__ nT,
+                                                          u64* __restrict__ keys, u32* __restrict__ ids) {
+  const u64 n = *nT;
+  for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (u64)gridDim.x * blockDim.x) {
+    const u32 p = tpos[t];
+    keys[p] = tkeys[t];
+    ids[p] = tids[t];
+  }
+}
+
 // ---------------------------------------------------------------- host side
 
-static int sort_set(const i32* grp, const i64* s, const i64* e, i64 n, const KeyLayout& L,
-                    const RadixPlan& rp, SetWS& ws, const RadixScratch& sc, cudaStream_t st,
-                    SortResult* res) {
-  if (n == 0) {
-    res->keys = ws.keyA;
-    res->vals = ws.idA;
-    res->keys_alt = ws.keyB;
-    res->vals_alt = ws.idB;
-    return BF_OK;
-  }
+static int sort_set(const i32* grp, const i64* s, const i64* e, i64 n, const KeyLayout& L, SetWS& ws,
+                    const RadixScratch& sc, u64* nT, cudaStream_t st, SortResult* res) {
+  res->keys = ws.keyA;
+  res->vals = ws.idA;
+  res->keys_alt = ws.keyB;
+  res->vals_alt = ws.idB;
+  if (n == 0) return BF_OK;
+  // main sort: stable, on the (group, start) bits only
+  const RadixPlan rp = make_radix_plan(L.LB, L.total_bits);
   BF_CUDA(cudaMemsetAsync(sc.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
   BF_TRY(launch_pack_keys(grp, s, e, (u64)n, L, 1, rp, ws.keyA, sc.hist, st));
-  return radix_sort_passes<true>(ws.keyA, ws.keyB, ws.idA, ws.idB, true, (u64)n, nullptr, rp, sc, st, res);
+  BF_TRY(radix_sort_passes<true>(ws.keyA, ws.keyB, ws.idA, ws.idB, true, (u64)n, nullptr, rp, sc, st, res));
+  // tie fix-up on the subset of rows that share (group, start); scratch aliases
+  // buffers that are not in use yet (the sort's spare buffers, scan/lo/cnt)
+  const unsigned tiles = (unsigned)scan_tiles((u64)n);
+  u64* tkeyA = res->keys_alt;
+  u32* tidA = res->vals_alt;
+  u64* tkeyB = ws.scan;
+  u32* tidB = ws.lo;
+  u32* tpos = ws.cnt;
+  BF_LAUNCH(PC_TIEFIX, 8 * n, st, tie_count_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, (u64)n, L, ws.spine));
+  BF_LAUNCH(PC_TIEFIX, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(ws.spine, tiles, nT));
+  BF_LAUNCH(PC_TIEFIX, 8 * n, st,
+            tie_compact_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, L, ws.spine, tkeyA, tidA, tpos));
+  const RadixPlan full = make_radix_plan(0, L.total_bits);
+  BF_CUDA(cudaMemsetAsync(sc.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
+  BF_TRY(launch_radix_hist(tkeyA, (u64)n, nT, full, sc.hist, st, PC_TIEFIX));
+  SortResult tr;
+  BF_TRY(radix_sort_passes<true>(tkeyA, tkeyB, tidA, tidB, false, (u64)n, nT, full, sc, st, &tr, PC_TIEFIX));
+  BF_LAUNCH(PC_TIEFIX, 0, st,
+            tie_scatter_kernel<<<stream_grid((u64)n, 256 * 64), 256, 0, st>>>(tr.keys, tr.vals, tpos, nT, res->keys, res->vals));
+  return BF_OK;
 }
 
 static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64 n1, const i32* grp2,
@@ -502,8 +688,8 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   BF_CUDA(cudaMemcpyAsync(&ext, w.extent, sizeof(Extent), cudaMemcpyDeviceToHost, st));
   BF_CUDA(cudaStreamSynchronize(st));
   if (n1 + n2 == 0) {
-    ext.cmin = 0;
-    ext.cmax = 0;
+    ext.cmin = ext.cmax = 0;
+    ext.lmin = ext.lmax = 0;
   }
   if (nb > 1 && n1 + n2 > 0 && (ext.gmin < 0 || ext.gmax >= nb)) {
     set_error("bf_overlap_count: group code outside [0,%d): min %d max %d", nb, ext.gmin, ext.gmax);
@@ -512,12 +698,10 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   KeyLayout L;
   BF_TRY(make_key_layout(ext, nb, &L));
   plan->L = L;
-  const RadixPlan rp = make_radix_plan(0, L.total_bits);
-
   // ---- sort both sets ----
   SortResult r1, r2;
-  BF_TRY(sort_set(nb > 1 ? grp1 : nullptr, s1, e1, n1, L, rp, w.s[0], w.radix, st, &r1));
-  BF_TRY(sort_set(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, rp, w.s[1], w.radix, st, &r2));
+  BF_TRY(sort_set(nb > 1 ? grp1 : nullptr, s1, e1, n1, L, w.s[0], w.radix, w.nT + 0, st, &r1));
+  BF_TRY(sort_set(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, w.s[1], w.radix, w.nT + 1, st, &r2));
   plan->key1 = r1.keys;
   plan->id1 = r1.vals;
   plan->key2 = r2.keys;
@@ -552,26 +736,30 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   // algorithmic bytes: key read (8) + lo/cnt written (8) per row
   if (n1 > 0) {
     const unsigned tiles = (unsigned)scan_tiles((u64)n1);
+    BF_LAUNCH(PC_SEARCH, 0, st, search_partition_kernel<false><<<(unsigned)ceil_div(tiles + 1, 256), 256, 0, st>>>(
+        r1.keys, n1, r2.keys, n2, L, tiles, w.s[0].bracket));
     if (need1) {
       BF_LAUNCH(PC_SEARCH, 16 * n1, st, search_count_kernel<false, true><<<tiles, SC_THREADS, 0, st>>>(
-          r1.keys, r1.vals, n1, r2.keys, n2, w.s[1].pmax, L, closed, w.s[0].lo, w.s[0].cnt, w.s[0].spine,
-          w.s[0].rowflag, w.s[0].ucnt));
+          r1.keys, r1.vals, n1, r2.keys, n2, w.s[1].pmax, w.s[0].bracket, L, closed, w.s[0].lo, w.s[0].cnt,
+          w.s[0].spine, w.s[0].rowflag, w.s[0].ucnt));
     } else {
       BF_LAUNCH(PC_SEARCH, 16 * n1, st, search_count_kernel<false, false><<<tiles, SC_THREADS, 0, st>>>(
-          r1.keys, r1.vals, n1, r2.keys, n2, nullptr, L, closed, w.s[0].lo, w.s[0].cnt, w.s[0].spine, nullptr,
-          nullptr));
+          r1.keys, r1.vals, n1, r2.keys, n2, nullptr, w.s[0].bracket, L, closed, w.s[0].lo, w.s[0].cnt,
+          w.s[0].spine, nullptr, nullptr));
     }
   }
   if (n2 > 0) {
     const unsigned tiles = (unsigned)scan_tiles((u64)n2);
+    BF_LAUNCH(PC_SEARCH, 0, st, search_partition_kernel<true><<<(unsigned)ceil_div(tiles + 1, 256), 256, 0, st>>>(
+        r2.keys, n2, r1.keys, n1, L, tiles, w.s[1].bracket));
     if (need2) {
       BF_LAUNCH(PC_SEARCH, 16 * n2, st, search_count_kernel<true, true><<<tiles, SC_THREADS, 0, st>>>(
-          r2.keys, r2.vals, n2, r1.keys, n1, w.s[0].pmax, L, closed, w.s[1].lo, w.s[1].cnt, w.s[1].spine,
-          w.s[1].rowflag, w.s[1].ucnt));
+          r2.keys, r2.vals, n2, r1.keys, n1, w.s[0].pmax, w.s[1].bracket, L, closed, w.s[1].lo, w.s[1].cnt,
+          w.s[1].spine, w.s[1].rowflag, w.s[1].ucnt));
     } else {
       BF_LAUNCH(PC_SEARCH, 16 * n2, st, search_count_kernel<true, false><<<tiles, SC_THREADS, 0, st>>>(
-          r2.keys, r2.vals, n2, r1.keys, n1, nullptr, L, closed, w.s[1].lo, w.s[1].cnt, w.s[1].spine, nullptr,
-          nullptr));
+          r2.keys, r2.vals, n2, r1.keys, n1, nullptr, w.s[1].bracket, L, closed, w.s[1].lo, w.s[1].cnt,
+          w.s[1].spine, nullptr, nullptr));
     }
   }
   BF_TRY(exclusive_sum_u32(w.s[0].cnt, (u64)n1, w.s[0].spine, true, w.s[0].scan, st));
@@ -631,15 +819,30 @@ static int overlap_emit_impl(const OverlapPlan* plan, void* ws_ptr, i64* ev1, i6
   Arena arena(ws_ptr);
   OverlapWS w;
   layout_overlap(arena, plan->n1, plan->n2, plan->nb, plan->how, &w);
-  if (plan->totA > 0) {
-    const unsigned grid = (unsigned)ceil_div(plan->totA + plan->n1, EM_TILE);
-    BF_LAUNCH(PC_EMIT, 20 * plan->totA, st, emit_pairs_kernel<false><<<grid, EM_THREADS, 0, st>>>(w.s[0].scan, w.s[0].lo, plan->n1, plan->id1, plan->id2,
-                                                          plan->totA, w.cumA, w.deltaA, plan->nb, ev1, ev2));
-  }
-  if (plan->totB > 0) {
-    const unsigned grid = (unsigned)ceil_div(plan->totB + plan->n2, EM_TILE);
-    BF_LAUNCH(PC_EMIT, 20 * plan->totB, st, emit_pairs_kernel<true><<<grid, EM_THREADS, 0, st>>>(w.s[1].scan, w.s[1].lo, plan->n2, plan->id2, plan->id1,
-                                                         plan->totB, w.cumB, w.deltaB, plan->nb, ev1, ev2));
+  // pairs: chunks of EMIT_CHUNK_BLOCKS blocks, each preceded by its partition kernel
+  for (int side = 0; side < 2; ++side) {
+    const i64 total = side ? plan->totB : plan->totA;
+    if (total <= 0) continue;
+    const i64 n_owner = side ? plan->n2 : plan->n1;
+    const SetWS& sw = w.s[side];
+    i64* part = side ? w.partB : w.partA;
+    const i64 blocks = ceil_div(n_owner + total, EM_TILE);
+    for (i64 b0 = 0; b0 < blocks; b0 += EMIT_CHUNK_BLOCKS) {
+      const i64 nb_chunk = blocks - b0 < EMIT_CHUNK_BLOCKS ? blocks - b0 : EMIT_CHUNK_BLOCKS;
+      BF_LAUNCH(PC_EMIT, 0, st,
+                emit_partition_kernel<<<(unsigned)ceil_div(nb_chunk + 1, 256), 256, 0, st>>>(sw.scan, n_owner, total, b0,
+                                                                                            nb_chunk + 1, part));
+      const u64 bytes = (u64)(20.0 * (double)total * (double)nb_chunk / (double)blocks);
+      if (side == 0) {
+        BF_LAUNCH(PC_EMIT, bytes, st,
+                  emit_pairs_kernel<false><<<(unsigned)nb_chunk, EM_THREADS, 0, st>>>(
+                      sw.scan, sw.lo, n_owner, plan->id1, plan->id2, total, b0, part, w.cumA, w.deltaA, plan->nb, ev1, ev2));
+      } else {
+        BF_LAUNCH(PC_EMIT, bytes, st,
+                  emit_pairs_kernel<true><<<(unsigned)nb_chunk, EM_THREADS, 0, st>>>(
+                      sw.scan, sw.lo, n_owner, plan->id2, plan->id1, total, b0, part, w.cumB, w.deltaB, plan->nb, ev1, ev2));
+      }
+    }
   }
   if (plan->nU1 > 0) {
     BF_LAUNCH(PC_UNPAIRED, 0, st, emit_unpaired_kernel<false><<<(unsigned)ceil_div(plan->nU1, 256), 256, 0, st>>>(plan->ukeys1, plan->nU1,

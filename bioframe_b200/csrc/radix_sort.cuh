@@ -24,6 +24,7 @@ constexpr int RS_IPT = 16;
 constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 keys per tile
 constexpr int RS_BINS = 256;
 constexpr int RS_MAX_PASSES = 8;
+constexpr u64 RS_PERSISTENT_BLOCKS = 148 * 3;  // one wave of resident blocks, each loops over tiles
 
 struct RadixPlan {
   int passes;
@@ -187,11 +188,14 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
   __shared__ u32 s_wtot[RS_WARPS];
 
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u64 n = n_dev ? *n_dev : n_host;
+  // persistent block: take tiles by ticket until the input is exhausted
+  for (;;) {
+  __syncthreads();  // previous tile fully written out before shared memory is reused
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
   for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) s_wcnt[i] = 0;
   __syncthreads();
   const u64 tile = s_tile;
-  const u64 n = n_dev ? *n_dev : n_host;
   const u64 tile_start = tile * RS_TILE;
   if (tile_start >= n) return;
   const u32 valid = (u32)((n - tile_start < (u64)RS_TILE) ? (n - tile_start) : (u64)RS_TILE);
@@ -306,6 +310,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
       if (HAS_VAL) vout[dst] = s_vals[idx];
     }
   }
+  }  // next tile
 }
 
 __global__ void iota_u32_kernel(u32* __restrict__ out, u64 n) {
@@ -336,7 +341,8 @@ static int radix_sort_passes(u64* kA, u64* kB, u32* vA, u32* vB, bool iota_vals,
   u64 *kin = kA, *kout = kB;
   u32 *vin = vA, *vout = vB;
   if (n_max > 0 && rp.passes > 0) {
-    const u64 tiles = (u64)ceil_div((i64)n_max, RS_TILE);
+    u64 tiles = (u64)ceil_div((i64)n_max, RS_TILE);
+    if (tiles > RS_PERSISTENT_BLOCKS) tiles = RS_PERSISTENT_BLOCKS;
     BF_LAUNCH(PC_SORT_MISC, 0, stream, radix_bases_kernel<<<rp.passes, RS_BINS, 0, stream>>>(sc.hist));
     BF_CUDA(cudaMemsetAsync(sc.status, 0, radix_status_words(n_max) * sizeof(u64), stream));
     BF_CUDA(cudaMemsetAsync(sc.tickets, 0, RS_MAX_PASSES * sizeof(u32), stream));
