@@ -16,6 +16,7 @@
 #include "keys.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
+#include "lookback.cuh"
 #include "../../include/bioframe_b200.h"
 
 namespace bf {
@@ -30,6 +31,7 @@ struct SetWS {
   u64 *scan;   // [n+1]
   u64 *spine;  // [tiles]
   i64 *bracket;  // [tiles+1] window of the other set per block of sorted rows
+  ScanState ss;  // look-back state shared by the fused scans over this set
   u64 *pmax;   // [n] running max of ce (only for outer joins on the other side)
   u8 *rowflag; // [n] 1 = row has no partner (row order)
   u64 *ukeyA, *ukeyB;  // [n] (rank << 32 | row) of unpaired rows
@@ -67,6 +69,7 @@ static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS*
     s.scan = a.take<u64>(n[k] + 1);
     s.spine = a.take<u64>(scan_tiles(n[k]) + 1);
     s.bracket = a.take<i64>(scan_tiles(n[k]) + 2);
+    s.ss = take_scan_state(a, (u64)scan_tiles(n[k]));
     s.seg = a.take<i64>(nb + 1);
     s.ucnt = a.take<u64>(nb + 1);
     // set k needs flags / unpaired lists when it is on the kept side; the OTHER
@@ -181,8 +184,8 @@ __global__ void __launch_bounds__(SC_THREADS) running_max_ce_kernel(const u64* _
 // block boundary, all in parallel).  A block stages its window (+ slack for
 // the hi searches) in shared memory when it fits, searches lo inside the
 // window and gallops from lo to hi.
-constexpr int SR_STAGE = 4096;  // staged composite starts of the other set (32 KB)
-constexpr int SR_SLACK = 512;
+constexpr int SR_STAGE = 4096;  // staged composite starts of the other set, 32-bit relative (16 KB)
+constexpr int SR_SLACK = 1024;
 
 template <bool B_SIDE>
 __global__ void __launch_bounds__(256) search_partition_kernel(const u64* __restrict__ mine, i64 n,
@@ -197,116 +200,140 @@ __global__ void __launch_bounds__(256) search_partition_kernel(const u64* __rest
                       : lower_bound_by(0, m, [&](i64 q) { return key_cs(other[q], L) < x; });
 }
 
+// Staged values are (cs - base_cs + 1) clamped to 32 bits, probes likewise, so
+// a probe below the window maps to 0 and one far above it to 0xffffffff; the
+// window is only staged when its span fits, which keeps every comparison exact.
+__device__ __forceinline__ u32 rel32(u64 x, u64 base_cs) {
+  if (x < base_cs) return 0u;
+  const u64 r = x - base_cs + 1;
+  return r > 0xffffffffull ? 0xffffffffu : (u32)r;
+}
+
 template <bool B_SIDE, bool FLAGS>
 __global__ void __launch_bounds__(SC_THREADS)
     search_count_kernel(const u64* __restrict__ mine, const u32* __restrict__ mine_id, i64 n,
                         const u64* __restrict__ other, i64 m, const u64* __restrict__ other_pmax,
                         const i64* __restrict__ bracket, KeyLayout L, int closed, u32* __restrict__ lo_out,
-                        u32* __restrict__ cnt_out, u64* __restrict__ spine, u8* __restrict__ rowflag,
+                        u64* __restrict__ scan_out, ScanState ss, u8* __restrict__ rowflag,
                         u64* __restrict__ ucnt) {
+  __shared__ u32 s_rel[SR_STAGE];
+  __shared__ u64 s_mine[SC_TILE];
+  __shared__ u32 s_cnt[SC_TILE];
   __shared__ u64 s_tmp[8];
-  __shared__ u64 s_other[SR_STAGE];
-  const i64 base = (i64)blockIdx.x * SC_TILE;
-  const i64 br_lo = bracket[blockIdx.x], br_hi = bracket[blockIdx.x + 1];
-  i64 nst = 0;  // staged entries: other[br_lo .. br_lo + nst)
-  if (br_hi - br_lo + 1 <= SR_STAGE) {
-    nst = br_hi - br_lo + 1 + SR_SLACK;
-    if (nst > SR_STAGE) nst = SR_STAGE;
-    if (nst > m - br_lo) nst = m - br_lo;
-    for (i64 i = threadIdx.x; i < nst; i += SC_THREADS) s_other[i] = key_cs(other[br_lo + i], L);
+  __shared__ u64 s_prefix;
+  __shared__ u32 s_ticket;
+  const u32 tid = threadIdx.x;
+  const i64 tile = take_ticket(ss.ticket, &s_ticket);
+  const i64 base = tile * SC_TILE;
+  // this block's own rows: all loads in flight at once, then served from shared memory
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    const i64 p = base + (i64)j * SC_THREADS + tid;
+    s_mine[j * SC_THREADS + tid] = p < n ? mine[p] : 0ull;
   }
+  const i64 br_lo = bracket[tile], br_hi = bracket[tile + 1];
+  const u32 W = (u32)(br_hi - br_lo);  // lo candidates: other[br_lo .. br_hi)
+  u32 nst = 0;                         // staged entries: other[br_lo .. br_lo + nst)
+  u64 base_cs = 0;
+  if ((i64)W + 1 <= SR_STAGE && br_lo < m) {
+    i64 want = (i64)W + 1 + SR_SLACK;
+    if (want > SR_STAGE) want = SR_STAGE;
+    if (want > m - br_lo) want = m - br_lo;
+    const u64 first = key_cs(other[br_lo], L), last = key_cs(other[br_lo + want - 1], L);
+    if (last - first < 0xfffffff0ull) {
+      nst = (u32)want;
+      base_cs = first;
+    }
+  }
+  for (u32 i = tid; i < nst; i += SC_THREADS) s_rel[i] = (u32)(key_cs(other[br_lo + i], L) - base_cs + 1);
+  u32 pow2 = 1;
+  while (pow2 <= W) pow2 <<= 1;
+  pow2 >>= 1;  // largest power of two <= W (0 if W == 0)
   __syncthreads();
-  auto oth = [&](i64 q) -> u64 {
-    const i64 r = q - br_lo;
-    return (r < nst) ? s_other[r] : key_cs(other[q], L);  // q >= br_lo always
-  };
 
-  u32 pow2_ceil = 1;
-  while ((i64)pow2_ceil < br_hi - br_lo + 1) pow2_ceil <<= 1;
-
-  u64 block_sum = 0;
 #pragma unroll 1
   for (int j = 0; j < SC_IPT; ++j) {
-    const i64 p = base + (i64)j * SC_THREADS + threadIdx.x;
+    const i64 p = base + (i64)j * SC_THREADS + tid;
     u32 cnt = 0;
     bool lonely = false;
     u32 rank = 0;
     if (p < n) {
-      const u64 k = mine[p];
+      const u64 k = s_mine[j * SC_THREADS + tid];
       const u64 xs = key_cs(k, L), xe = key_ce(k, L);
       i64 lo, hi;
       if (nst > 0) {
-        // staged window: branch-free bit-step lower bound over W = br_hi - br_lo candidates
-        const u32 W = (u32)(br_hi - br_lo);
+        const u32 xs_rel = rel32(xs, base_cs), xe_rel = rel32(xe, base_cs);
+        // lo: branch-free bit-step lower bound over the W candidates
         u32 pos = 0;
-        for (u32 step = pow2_ceil; step > 0; step >>= 1) {
+        for (u32 step = pow2; step > 0; step >>= 1) {
           const u32 nx = pos + step;
           if (nx <= W) {
-            const u64 v = s_other[nx - 1];
-            const bool below = B_SIDE ? (v <= xs) : (v < xs);
-            if (below) pos = nx;
+            const u32 v = s_rel[nx - 1];
+            if (B_SIDE ? (v <= xs_rel) : (v < xs_rel)) pos = nx;
           }
         }
         lo = br_lo + pos;
-        // hi: short linear probe (fan-out is usually a handful), then gallop
-        u32 h = pos;
-        int probes = 0;
-        bool done = false;
-        while (probes < 8) {
-          if (h >= (u32)nst) break;
-          const u64 v = s_other[h];
-          const bool below = closed ? (v <= xe) : (v < xe);
-          if (!below) {
-            done = true;
+        // hi: gallop inside the staged window, then bisect
+        u32 a = pos, b = pos, step = 1;
+        bool open_end = false;
+        for (;;) {
+          b = a + step;
+          if (b > nst) {
+            b = nst;
+            open_end = true;
             break;
           }
-          ++h;
-          ++probes;
+          const u32 v = s_rel[b - 1];
+          if (!(closed ? (v <= xe_rel) : (v < xe_rel))) break;
+          a = b;
+          step <<= 1;
         }
-        hi = br_lo + h;
-        if (!done && hi >= m) {
-          hi = m;
-          done = true;
+        while (a < b) {  // first index in [a, b) that is not below; b if none
+          const u32 mid = (a + b) >> 1;
+          const u32 v = s_rel[mid];
+          if (closed ? (v <= xe_rel) : (v < xe_rel))
+            a = mid + 1;
+          else
+            b = mid;
         }
-        if (!done) {
-          i64 a = hi, step = 1, b = hi;
-          while (true) {
-            b = a + step;
-            if (b >= m) {
-              b = m;
+        hi = br_lo + a;
+        if (open_end && a == nst && hi < m) {
+          // ran off the staged window: continue on the full keys
+          i64 ga = hi, gb = hi, gstep = 1;
+          for (;;) {
+            gb = ga + gstep;
+            if (gb >= m) {
+              gb = m;
               break;
             }
-            const u64 v = oth(b - 1);
-            const bool below = closed ? (v <= xe) : (v < xe);
-            if (!below) break;
-            a = b;
-            step <<= 1;
+            const u64 v = key_cs(other[gb - 1], L);
+            if (!(closed ? (v <= xe) : (v < xe))) break;
+            ga = gb;
+            gstep <<= 1;
           }
-          hi = closed ? lower_bound_by(a, b, [&](i64 q) { return oth(q) <= xe; })
-                      : lower_bound_by(a, b, [&](i64 q) { return oth(q) < xe; });
+          hi = closed ? lower_bound_by(ga, gb, [&](i64 q) { return key_cs(other[q], L) <= xe; })
+                      : lower_bound_by(ga, gb, [&](i64 q) { return key_cs(other[q], L) < xe; });
         }
       } else {
         lo = B_SIDE ? lower_bound_by(br_lo, br_hi, [&](i64 q) { return key_cs(other[q], L) <= xs; })
                     : lower_bound_by(br_lo, br_hi, [&](i64 q) { return key_cs(other[q], L) < xs; });
-        i64 a = lo, step = 1, b = lo;
-        while (true) {
-          b = a + step;
-          if (b >= m) {
-            b = m;
+        i64 ga = lo, gb = lo, gstep = 1;
+        for (;;) {
+          gb = ga + gstep;
+          if (gb >= m) {
+            gb = m;
             break;
           }
-          const u64 v = key_cs(other[b - 1], L);
-          const bool below = closed ? (v <= xe) : (v < xe);
-          if (!below) break;
-          a = b;
-          step <<= 1;
+          const u64 v = key_cs(other[gb - 1], L);
+          if (!(closed ? (v <= xe) : (v < xe))) break;
+          ga = gb;
+          gstep <<= 1;
         }
-        hi = closed ? lower_bound_by(a, b, [&](i64 q) { return key_cs(other[q], L) <= xe; })
-                    : lower_bound_by(a, b, [&](i64 q) { return key_cs(other[q], L) < xe; });
+        hi = closed ? lower_bound_by(ga, gb, [&](i64 q) { return key_cs(other[q], L) <= xe; })
+                    : lower_bound_by(ga, gb, [&](i64 q) { return key_cs(other[q], L) < xe; });
       }
       cnt = (u32)(hi - lo);
       lo_out[p] = (u32)lo;
-      cnt_out[p] = cnt;
       if (FLAGS) {
         bool partner = cnt > 0;
         if (!partner && lo > 0) {
@@ -318,6 +345,7 @@ __global__ void __launch_bounds__(SC_THREADS)
         if (lonely) rowflag[mine_id[p]] = 1;
       }
     }
+    s_cnt[j * SC_THREADS + tid] = cnt;
     if (FLAGS) {
       // per-group unpaired counters: rows are sorted by group, so a warp almost
       // always holds one group -> one atomic per warp; mixed warps fall back
@@ -333,10 +361,31 @@ __global__ void __launch_bounds__(SC_THREADS)
         }
       }
     }
-    block_sum += cnt;
   }
-  block_sum = block_sum_u64(block_sum, s_tmp);
-  if (threadIdx.x == 0) spine[blockIdx.x] = block_sum;
+  __syncthreads();
+  // ---- exclusive scan of the counts, fused: tile scan + look-back over tile totals ----
+  u32 c[SC_IPT];
+  u64 mine_sum = 0;
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    c[j] = s_cnt[tid * SC_IPT + j];
+    mine_sum += c[j];
+  }
+  u64 tot;
+  u64 run = block_excl_sum_u64(mine_sum, s_tmp, &tot);
+  if (tid < 32) {
+    const u64 pre = lookback_exclusive(ss.status, (u64)tile, tot);
+    if (tid == 0) s_prefix = pre;
+  }
+  __syncthreads();
+  run += s_prefix;
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    const i64 p = base + (i64)tid * SC_IPT + j;
+    if (p < n) scan_out[p] = run;
+    run += c[j];
+    if (p + 1 == n) scan_out[n] = run;
+  }
 }
 
 // Per-group output offsets; single thread (n_groups is tens, not millions).
@@ -495,42 +544,40 @@ __global__ void __launch_bounds__(EM_THREADS)
 }
 
 // ---- unpaired rows: compaction in row order -> stable partition by group ----
-__global__ void __launch_bounds__(SC_THREADS) tile_count_flags_kernel(const u8* __restrict__ flag, u64 n,
-                                                                      u64* __restrict__ spine) {
-  __shared__ u64 s_tmp[8];
-  const u64 base = (u64)blockIdx.x * SC_TILE;
-  u64 acc = 0;
-#pragma unroll
-  for (int j = 0; j < SC_IPT; ++j) {
-    u64 i = base + (u64)j * SC_THREADS + threadIdx.x;
-    if (i < n) acc += flag[i];
-  }
-  acc = block_sum_u64(acc, s_tmp);
-  if (threadIdx.x == 0) spine[blockIdx.x] = acc;
-}
 __global__ void __launch_bounds__(SC_THREADS)
-    compact_unpaired_kernel(const u8* __restrict__ flag, const i32* __restrict__ grp, u64 n,
-                            const u64* __restrict__ spine, u64* __restrict__ ukeys) {
+    compact_unpaired_kernel(const u8* __restrict__ flag, const i32* __restrict__ grp, u64 n, ScanState ss,
+                            u64* __restrict__ ukeys, u64* __restrict__ nU) {
   __shared__ u64 s_tmp[8];
-  const u64 base = (u64)blockIdx.x * SC_TILE + (u64)threadIdx.x * SC_IPT;
-  u8 f[SC_IPT];
-  u64 mine = 0;
-#pragma unroll
-  for (int j = 0; j < SC_IPT; ++j) {
-    u64 i = base + j;
-    f[j] = i < n ? flag[i] : (u8)0;
-    mine += f[j];
+  __shared__ u64 s_prefix;
+  __shared__ u32 s_ticket;
+  const u32 tid = threadIdx.x;
+  const u64 tile = take_ticket(ss.ticket, &s_ticket);
+  const u64 base = tile * SC_TILE + (u64)tid * SC_IPT;
+  // 8 flag bytes per thread in one 8-byte load (flag array is 256-byte aligned, tile offsets multiples of 8)
+  u64 f8 = 0;
+  if (base + SC_IPT <= n) {
+    f8 = *reinterpret_cast<const u64*>(flag + base);
+  } else {
+    for (int j = 0; j < SC_IPT; ++j)
+      if (base + j < n) f8 |= (u64)flag[base + j] << (8 * j);
   }
   u64 tot;
-  u64 at = spine[blockIdx.x] + block_excl_sum_u64(mine, s_tmp, &tot);
+  u64 at = block_excl_sum_u64((u64)__popcll(f8), s_tmp, &tot);
+  if (tid < 32) {
+    const u64 pre = lookback_exclusive(ss.status, tile, tot);
+    if (tid == 0) s_prefix = pre;
+  }
+  __syncthreads();
+  at += s_prefix;
 #pragma unroll
   for (int j = 0; j < SC_IPT; ++j) {
-    if (f[j]) {
-      u64 i = base + j;
-      u64 g = grp ? (u64)(u32)grp[i] : 0ull;
+    if ((f8 >> (8 * j)) & 1ull) {
+      const u64 i = base + j;
+      const u64 g = grp ? (u64)(u32)grp[i] : 0ull;
       ukeys[at++] = (g << 32) | i;
     }
   }
+  if (tile * SC_TILE + SC_TILE >= n && tid == 0) *nU = s_prefix + tot;
 }
 template <bool SECOND>
 __global__ void __launch_bounds__(256) emit_unpaired_kernel(const u64* __restrict__ ukeys, i64 nU,
@@ -552,47 +599,57 @@ __global__ void __launch_bounds__(256) emit_unpaired_kernel(const u64* __restric
 // reference wants them by (end', row).  Tied rows are rare, so: count them,
 // compact (key, id, slot), sort that subset by the FULL key (stable, so equal
 // keys keep row order) and write it back into the same slots in order.
-__device__ __forceinline__ bool row_is_tied(const u64* __restrict__ keys, u64 p, u64 n, const KeyLayout& L) {
-  const u64 c = key_cs(keys[p], L);
-  return (p > 0 && key_cs(keys[p - 1], L) == c) || (p + 1 < n && key_cs(keys[p + 1], L) == c);
-}
-__global__ void __launch_bounds__(SC_THREADS) tie_count_kernel(const u64* __restrict__ keys, u64 n, KeyLayout L,
-                                                               u64* __restrict__ spine) {
-  __shared__ u64 s_tmp[8];
-  const u64 base = (u64)blockIdx.x * SC_TILE;
-  u64 acc = 0;
-#pragma unroll
-  for (int j = 0; j < SC_IPT; ++j) {
-    const u64 p = base + (u64)j * SC_THREADS + threadIdx.x;
-    if (p < n && row_is_tied(keys, p, n, L)) ++acc;
-  }
-  acc = block_sum_u64(acc, s_tmp);
-  if (threadIdx.x == 0) spine[blockIdx.x] = acc;
-}
+// One pass: stage the tile's keys (+ one halo key each side) in shared memory,
+// flag tied rows, scan the flags (tile scan + look-back) and write the subset.
 __global__ void __launch_bounds__(SC_THREADS)
-    tie_compact_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, KeyLayout L,
-                       const u64* __restrict__ spine, u64* __restrict__ tkeys, u32* __restrict__ tids,
-                       u32* __restrict__ tpos) {
+    tie_compact_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, KeyLayout L, ScanState ss,
+                       u64* __restrict__ tkeys, u32* __restrict__ tids, u32* __restrict__ tpos,
+                       u64* __restrict__ nT) {
+  __shared__ u64 s_k[SC_TILE + 2];
   __shared__ u64 s_tmp[8];
-  const u64 base = (u64)blockIdx.x * SC_TILE + (u64)threadIdx.x * SC_IPT;
+  __shared__ u64 s_prefix;
+  __shared__ u32 s_ticket;
+  const u32 tid = threadIdx.x;
+  const u64 tile = take_ticket(ss.ticket, &s_ticket);
+  const u64 base = tile * SC_TILE;
+  const u64 rows = n - base < (u64)SC_TILE ? n - base : (u64)SC_TILE;
+  for (u32 i = tid; i < rows + 2; i += SC_THREADS) {
+    const i64 p = (i64)base + i - 1;
+    // halo outside the array: a key whose cs differs from every neighbour's
+    s_k[i] = (p >= 0 && (u64)p < n) ? keys[p] : ~0ull;
+  }
+  __syncthreads();
+  const bool lo_edge = base == 0, hi_edge = base + rows == n;
   u32 mask = 0;
 #pragma unroll
   for (int j = 0; j < SC_IPT; ++j) {
-    const u64 p = base + j;
-    if (p < n && row_is_tied(keys, p, n, L)) mask |= 1u << j;
+    const u32 r = tid * SC_IPT + j;  // row inside the tile, s_k index r + 1
+    if (r < rows) {
+      const u64 c = key_cs(s_k[r + 1], L);
+      const bool prev_ok = !(lo_edge && r == 0);
+      const bool next_ok = !(hi_edge && r + 1 == rows);
+      if ((prev_ok && key_cs(s_k[r], L) == c) || (next_ok && key_cs(s_k[r + 2], L) == c)) mask |= 1u << j;
+    }
   }
   u64 tot;
-  u64 at = spine[blockIdx.x] + block_excl_sum_u64((u64)__popc(mask), s_tmp, &tot);
+  u64 at = block_excl_sum_u64((u64)__popc(mask), s_tmp, &tot);
+  if (tid < 32) {
+    const u64 pre = lookback_exclusive(ss.status, tile, tot);
+    if (tid == 0) s_prefix = pre;
+  }
+  __syncthreads();
+  at += s_prefix;
 #pragma unroll
   for (int j = 0; j < SC_IPT; ++j) {
     if (mask & (1u << j)) {
-      const u64 p = base + j;
-      tkeys[at] = keys[p];
-      tids[at] = ids[p];
-      tpos[at] = (u32)p;
+      const u32 r = tid * SC_IPT + j;
+      tkeys[at] = s_k[r + 1];
+      tids[at] = ids[base + r];
+      tpos[at] = (u32)(base + r);
       ++at;
     }
   }
+  if (hi_edge && tid == 0) *nT = s_prefix + tot;
 }
 __global__ void __launch_bounds__(256) tie_scatter_kernel(const u64* __restrict__ tkeys, const u32* __restrict__ tids,
                                                           const u32* __restrict__ tpos, const u64* __restrict__ nT,
@@ -627,10 +684,9 @@ static int sort_set(const i32* grp, const i64* s, const i64* e, i64 n, const Key
   u64* tkeyB = ws.scan;
   u32* tidB = ws.lo;
   u32* tpos = ws.cnt;
-  BF_LAUNCH(PC_TIEFIX, 8 * n, st, tie_count_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, (u64)n, L, ws.spine));
-  BF_LAUNCH(PC_TIEFIX, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(ws.spine, tiles, nT));
+  BF_TRY(reset_scan_state(ws.ss, tiles, st));
   BF_LAUNCH(PC_TIEFIX, 8 * n, st,
-            tie_compact_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, L, ws.spine, tkeyA, tidA, tpos));
+            tie_compact_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, L, ws.ss, tkeyA, tidA, tpos, nT));
   const RadixPlan full = make_radix_plan(0, L.total_bits);
   BF_CUDA(cudaMemsetAsync(sc.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
   BF_TRY(launch_radix_hist(tkeyA, (u64)n, nT, full, sc.hist, st, PC_TIEFIX));
@@ -733,37 +789,41 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
     BF_CUDA(cudaMemsetAsync(w.s[1].ucnt, 0, (nb + 1) * sizeof(u64), st));
     if (n2 > 0) BF_CUDA(cudaMemsetAsync(w.s[1].rowflag, 0, (size_t)n2, st));
   }
-  // algorithmic bytes: key read (8) + lo/cnt written (8) per row
+  // algorithmic bytes: key read (8) + lo (4) + scan offset (8) written per row
   if (n1 > 0) {
     const unsigned tiles = (unsigned)scan_tiles((u64)n1);
+    BF_TRY(reset_scan_state(w.s[0].ss, tiles, st));
     BF_LAUNCH(PC_SEARCH, 0, st, search_partition_kernel<false><<<(unsigned)ceil_div(tiles + 1, 256), 256, 0, st>>>(
         r1.keys, n1, r2.keys, n2, L, tiles, w.s[0].bracket));
     if (need1) {
-      BF_LAUNCH(PC_SEARCH, 16 * n1, st, search_count_kernel<false, true><<<tiles, SC_THREADS, 0, st>>>(
-          r1.keys, r1.vals, n1, r2.keys, n2, w.s[1].pmax, w.s[0].bracket, L, closed, w.s[0].lo, w.s[0].cnt,
-          w.s[0].spine, w.s[0].rowflag, w.s[0].ucnt));
+      BF_LAUNCH(PC_SEARCH, 20 * n1, st, search_count_kernel<false, true><<<tiles, SC_THREADS, 0, st>>>(
+          r1.keys, r1.vals, n1, r2.keys, n2, w.s[1].pmax, w.s[0].bracket, L, closed, w.s[0].lo, w.s[0].scan,
+          w.s[0].ss, w.s[0].rowflag, w.s[0].ucnt));
     } else {
-      BF_LAUNCH(PC_SEARCH, 16 * n1, st, search_count_kernel<false, false><<<tiles, SC_THREADS, 0, st>>>(
-          r1.keys, r1.vals, n1, r2.keys, n2, nullptr, w.s[0].bracket, L, closed, w.s[0].lo, w.s[0].cnt,
-          w.s[0].spine, nullptr, nullptr));
+      BF_LAUNCH(PC_SEARCH, 20 * n1, st, search_count_kernel<false, false><<<tiles, SC_THREADS, 0, st>>>(
+          r1.keys, r1.vals, n1, r2.keys, n2, nullptr, w.s[0].bracket, L, closed, w.s[0].lo, w.s[0].scan,
+          w.s[0].ss, nullptr, nullptr));
     }
+  } else {
+    BF_CUDA(cudaMemsetAsync(w.s[0].scan, 0, sizeof(u64), st));
   }
   if (n2 > 0) {
     const unsigned tiles = (unsigned)scan_tiles((u64)n2);
+    BF_TRY(reset_scan_state(w.s[1].ss, tiles, st));
     BF_LAUNCH(PC_SEARCH, 0, st, search_partition_kernel<true><<<(unsigned)ceil_div(tiles + 1, 256), 256, 0, st>>>(
         r2.keys, n2, r1.keys, n1, L, tiles, w.s[1].bracket));
     if (need2) {
-      BF_LAUNCH(PC_SEARCH, 16 * n2, st, search_count_kernel<true, true><<<tiles, SC_THREADS, 0, st>>>(
-          r2.keys, r2.vals, n2, r1.keys, n1, w.s[0].pmax, w.s[1].bracket, L, closed, w.s[1].lo, w.s[1].cnt,
-          w.s[1].spine, w.s[1].rowflag, w.s[1].ucnt));
+      BF_LAUNCH(PC_SEARCH, 20 * n2, st, search_count_kernel<true, true><<<tiles, SC_THREADS, 0, st>>>(
+          r2.keys, r2.vals, n2, r1.keys, n1, w.s[0].pmax, w.s[1].bracket, L, closed, w.s[1].lo, w.s[1].scan,
+          w.s[1].ss, w.s[1].rowflag, w.s[1].ucnt));
     } else {
-      BF_LAUNCH(PC_SEARCH, 16 * n2, st, search_count_kernel<true, false><<<tiles, SC_THREADS, 0, st>>>(
-          r2.keys, r2.vals, n2, r1.keys, n1, nullptr, w.s[1].bracket, L, closed, w.s[1].lo, w.s[1].cnt,
-          w.s[1].spine, nullptr, nullptr));
+      BF_LAUNCH(PC_SEARCH, 20 * n2, st, search_count_kernel<true, false><<<tiles, SC_THREADS, 0, st>>>(
+          r2.keys, r2.vals, n2, r1.keys, n1, nullptr, w.s[1].bracket, L, closed, w.s[1].lo, w.s[1].scan,
+          w.s[1].ss, nullptr, nullptr));
     }
+  } else {
+    BF_CUDA(cudaMemsetAsync(w.s[1].scan, 0, sizeof(u64), st));
   }
-  BF_TRY(exclusive_sum_u32(w.s[0].cnt, (u64)n1, w.s[0].spine, true, w.s[0].scan, st));
-  BF_TRY(exclusive_sum_u32(w.s[1].cnt, (u64)n2, w.s[1].spine, true, w.s[1].scan, st));
 
   // ---- unpaired lists: compact in row order, partition by group ----
   BF_CUDA(cudaMemsetAsync(w.nU, 0, 2 * sizeof(u64), st));
@@ -773,10 +833,9 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
     const bool need = k == 0 ? need1 : need2;
     if (!need || nn[k] == 0) continue;
     const unsigned tiles = (unsigned)scan_tiles((u64)nn[k]);
-    BF_LAUNCH(PC_UNPAIRED, 0, st, tile_count_flags_kernel<<<tiles, SC_THREADS, 0, st>>>(w.s[k].rowflag, (u64)nn[k], w.s[k].uspine));
-    BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.s[k].uspine, tiles, w.nU + k));
-    BF_LAUNCH(PC_UNPAIRED, 0, st, compact_unpaired_kernel<<<tiles, SC_THREADS, 0, st>>>(w.s[k].rowflag, grps[k], (u64)nn[k], w.s[k].uspine,
-                                                          w.s[k].ukeyA));
+    BF_TRY(reset_scan_state(w.s[k].ss, tiles, st));
+    BF_LAUNCH(PC_UNPAIRED, 0, st, compact_unpaired_kernel<<<tiles, SC_THREADS, 0, st>>>(
+        w.s[k].rowflag, grps[k], (u64)nn[k], w.s[k].ss, w.s[k].ukeyA, w.nU + k));
     ukeys_sorted[k] = w.s[k].ukeyA;
     if (L.rank_bits > 0) {
       const RadixPlan urp = make_radix_plan(32, 32 + L.rank_bits);

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
   u32* s_tbase = s_wcnt + RS_WARPS * RS_BINS;      // [256] exclusive digit offsets inside the tile
   u64* s_gofs = (u64*)(s_tbase + RS_BINS);         // [256] global offset minus s_tbase
   __shared__ u32 s_tile;
-  __shared__ u32 s_wtot[RS_WARPS];
+  __shared__ u32 s_wtot[RS_BINS / 32];
 
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u64 n = n_dev ? *n_dev : n_host;
@@ -226,56 +226,61 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
   }
   __syncthreads();
 
-  // ---- thread d: exclusive offsets of digit d across warps, tile digit count ----
-  u32 tile_cnt = 0;
+  // ---- thread d < 256: exclusive offsets of digit d across warps, tile digit count ----
   {
-    const u32 d = tid;  // RS_THREADS == RS_BINS
+    const bool dthread = tid < RS_BINS;
+    const u32 d = tid & (RS_BINS - 1);
+    u32 tile_cnt = 0;
+    if (dthread) {
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) {
-      u32 c = s_wcnt[w * RS_BINS + d];
-      s_wcnt[w * RS_BINS + d] = tile_cnt;
-      tile_cnt += c;
+      for (int w = 0; w < RS_WARPS; ++w) {
+        u32 c = s_wcnt[w * RS_BINS + d];
+        s_wcnt[w * RS_BINS + d] = tile_cnt;
+        tile_cnt += c;
+      }
     }
-    // exclusive scan of tile_cnt over the 256 digits
+    // exclusive scan of tile_cnt over the 256 digits (warps 0..7)
     u32 inc = tile_cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       u32 t = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= (u32)o) inc += t;
     }
-    if (lane == 31) s_wtot[warp] = inc;
+    if (dthread && lane == 31) s_wtot[warp] = inc;
     __syncthreads();
-    u32 pre = 0;
+    if (dthread) {
+      u32 pre = 0;
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w)
-      if ((u32)w < warp) pre += s_wtot[w];
-    const u32 tbase = pre + inc - tile_cnt;
-    s_tbase[d] = tbase;
+      for (int w = 0; w < RS_BINS / 32; ++w)
+        if ((u32)w < warp) pre += s_wtot[w];
+      const u32 tbase = pre + inc - tile_cnt;
+      s_tbase[d] = tbase;
 
-    // pads all carry digit dmask and sit at the very end of the tile
-    u64 cnt_valid = tile_cnt;
-    if (d == dmask) cnt_valid -= (u64)(RS_TILE - valid);
+      // pads all carry digit dmask and sit at the very end of the tile
+      u64 cnt_valid = tile_cnt;
+      if (d == dmask) cnt_valid -= (u64)(RS_TILE - valid);
 
-    // ---- decoupled look-back: digits before this tile ----
-    u64* mine = status + tile * RS_BINS + d;
-    u64 excl = 0;
-    if (tile == 0) {
-      st_relaxed_u64(mine, tag | RS_FLAG_INC | cnt_valid);
-    } else {
-      st_relaxed_u64(mine, tag | RS_FLAG_AGG | cnt_valid);
-      const u64* prev = mine - RS_BINS;
-      while (true) {
-        u64 w = ld_relaxed_u64(prev);
-        if ((w & ~(RS_VAL_MASK | (3ull << 56))) != tag) continue;  // stale word of an earlier pass
-        u64 flag = w & (3ull << 56);
-        if (flag == 0) continue;
-        excl += w & RS_VAL_MASK;
-        if (flag == RS_FLAG_INC) break;
-        prev -= RS_BINS;
+      // ---- decoupled look-back: digits before this tile ----
+      u64* mine = status + tile * RS_BINS + d;
+      u64 excl = 0;
+      if (tile == 0) {
+        st_relaxed_u64(mine, tag | RS_FLAG_INC | cnt_valid);
+      } else {
+        st_relaxed_u64(mine, tag | RS_FLAG_AGG | cnt_valid);
+        const u64* prev = mine - RS_BINS;
+        while (true) {
+          u64 w = ld_relaxed_u64(prev);
+          if ((w & ~(RS_VAL_MASK | (3ull << 56))) != tag) continue;  // stale word of an earlier pass
+          u64 flag = w & (3ull << 56);
+          if (flag == 0) continue;
+          excl += w & RS_VAL_MASK;
+          if (flag == RS_FLAG_INC) break;
+          prev -= RS_BINS;
+        }
+        st_relaxed_u64(mine, tag | RS_FLAG_INC | (excl + cnt_valid));
       }
-      st_relaxed_u64(mine, tag | RS_FLAG_INC | (excl + cnt_valid));
+      s_gofs[d] = digit_base[d] + excl - (u64)tbase;
     }
-    s_gofs[d] = digit_base[d] + excl - (u64)tbase;
   }
   __syncthreads();
 
