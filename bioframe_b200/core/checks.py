@@ -1,0 +1,41 @@
+"""Entry validation of the six ops: the host-side mirror of
+`bioframe.core.checks.is_bedframe` (reference src/bioframe/core/checks.py:20-87)."""
+from __future__ import annotations
+
+import pandas as pd
+
+from .specs import _get_default_colnames, _verify_column_dtypes, _verify_columns
+
+__all__ = ["is_bedframe"]
+
+
+def is_bedframe(df, raise_errors=False, cols=None):
+    """chrom/start/end present with valid dtypes, nulls only as whole-null rows,
+    and start <= end everywhere.  Same messages and exception classes as the
+    reference (TypeError for names/dtypes, ValueError for nulls and order)."""
+    ck, sk, ek = _get_default_colnames() if cols is None else cols
+
+    def fail(exc):
+        if raise_errors:
+            raise exc
+        return False
+
+    if not _verify_columns(df, [ck, sk, ek], return_as_bool=True):
+        return fail(TypeError("Invalid bedFrame: Invalid column names"))
+    if not _verify_column_dtypes(df, cols=[ck, sk, ek], return_as_bool=True):
+        return fail(TypeError("Invalid bedFrame: Invalid column dtypes"))
+    nulls = pd.isnull(df[[ck, sk, ek]])
+    partial = nulls.any(axis=1) & ~nulls.all(axis=1)
+    if partial.any():
+        return fail(
+            ValueError(
+                "Invalid bedFrame: Invalid null values "
+                "(if any of chrom, start, end are null, then all must be null)"
+            )
+        )
+    backwards = (df[ek] - df[sk]) < 0
+    if backwards.any():
+        return fail(
+            ValueError(f"Invalid bedframe: starts exceed ends for {sum(backwards)} intervals")
+        )
+    return True

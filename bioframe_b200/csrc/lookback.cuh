@@ -69,4 +69,39 @@ __device__ __forceinline__ u64 lookback_exclusive(u64* status, u64 tile, u64 agg
   return excl;
 }
 
+// Same protocol with max as the operator (running maximum across tiles).
+__device__ __forceinline__ u64 lookback_exclusive_max(u64* status, u64 tile, u64 aggregate) {
+  const u32 lane = lane_id();
+  if (tile == 0) {
+    if (lane == 0) st_relaxed_u64(status, LB_INC | aggregate);
+    return 0;
+  }
+  if (lane == 0) st_relaxed_u64(status + tile, LB_AGG | aggregate);
+  u64 excl = 0;
+  i64 base = (i64)tile - 1;
+  for (;;) {
+    const i64 t = base - (i64)lane;
+    u64 w = LB_INC;
+    if (t >= 0) w = ld_relaxed_u64(status + t);
+    const u32 flag = (u32)(w >> 62);
+    const u32 inc_mask = __ballot_sync(0xffffffffu, flag == 2);
+    const u32 wait_mask = __ballot_sync(0xffffffffu, flag == 0);
+    const u32 first_inc = inc_mask ? (u32)(__ffs(inc_mask) - 1) : 31u;
+    const u32 needed = first_inc >= 31u ? 0xffffffffu : ((2u << first_inc) - 1u);
+    if (wait_mask & needed) continue;
+    u64 v = (lane <= first_inc) ? (w & LB_VAL_MASK) : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const u64 x = __shfl_xor_sync(0xffffffffu, v, o);
+      v = x > v ? x : v;
+    }
+    excl = v > excl ? v : excl;
+    if (inc_mask) break;
+    base -= 32;
+  }
+  const u64 inc = excl > aggregate ? excl : aggregate;
+  if (lane == 0) st_relaxed_u64(status + tile, LB_INC | inc);
+  return excl;
+}
+
 }  // namespace bf

@@ -17,6 +17,7 @@
 #include "radix_sort.cuh"
 #include "scan.cuh"
 #include "lookback.cuh"
+#include "sorted_set.cuh"
 #include "../../include/bioframe_b200.h"
 
 namespace bf {
@@ -25,13 +26,12 @@ constexpr i64 EMIT_CHUNK_BLOCKS = 1 << 16;  // emit blocks per partition chunk (
 
 // ---------------------------------------------------------------- workspace
 struct SetWS {
-  u64 *keyA, *keyB;
-  u32 *idA, *idB;
-  u32 *lo, *cnt;
-  u64 *scan;   // [n+1]
-  u64 *spine;  // [tiles]
+  SortBufs sb;   // sort double buffers + per-row temporaries + look-back state
+  u32 *lo;       // = sb.tmp4a after the sort: first partner position per sorted row
+  u64 *scan;     // = sb.tmp8  after the sort: [n+1] exclusive output offsets
+  u64 *spine;    // [tiles]
   i64 *bracket;  // [tiles+1] window of the other set per block of sorted rows
-  ScanState ss;  // look-back state shared by the fused scans over this set
+  ScanState ss;  // = sb.ss
   u64 *pmax;   // [n] running max of ce (only for outer joins on the other side)
   u8 *rowflag; // [n] 1 = row has no partner (row order)
   u64 *ukeyA, *ukeyB;  // [n] (rank << 32 | row) of unpaired rows
@@ -52,7 +52,6 @@ struct OverlapWS {
   i64 *partA, *partB;    // merge-path partition of the emit blocks
   i64 *header;           // n_rows, n_pairs, nU1, nU2
   u64 *nU;               // [2] device-side unpaired totals (sort sizes)
-  u64 *nT;               // [2] device-side tied-row totals
 };
 
 static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS* w) {
@@ -60,16 +59,12 @@ static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS*
   const bool need[2] = {(how & 1) != 0, (how & 2) != 0};
   for (int k = 0; k < 2; ++k) {
     SetWS& s = w->s[k];
-    s.keyA = a.take<u64>(n[k]);
-    s.keyB = a.take<u64>(n[k]);
-    s.idA = a.take<u32>(n[k]);
-    s.idB = a.take<u32>(n[k]);
-    s.lo = a.take<u32>(n[k]);
-    s.cnt = a.take<u32>(n[k]);
-    s.scan = a.take<u64>(n[k] + 1);
+    take_sort_bufs(a, n[k], &s.sb);
+    s.lo = s.sb.tmp4a;
+    s.scan = s.sb.tmp8;
+    s.ss = s.sb.ss;
     s.spine = a.take<u64>(scan_tiles(n[k]) + 1);
     s.bracket = a.take<i64>(scan_tiles(n[k]) + 2);
-    s.ss = take_scan_state(a, (u64)scan_tiles(n[k]));
     s.seg = a.take<i64>(nb + 1);
     s.ucnt = a.take<u64>(nb + 1);
     // set k needs flags / unpaired lists when it is on the kept side; the OTHER
@@ -99,7 +94,6 @@ static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS*
   w->partB = a.take<i64>(EMIT_CHUNK_BLOCKS + 1);
   w->header = a.take<i64>(8);
   w->nU = a.take<u64>(2);
-  w->nT = a.take<u64>(2);
 }
 
 struct OverlapPlan {  // lives in the caller's bf_plan
@@ -118,18 +112,6 @@ static_assert(sizeof(OverlapPlan) <= sizeof(bf_plan), "bf_plan too small");
 constexpr u64 OVERLAP_MAGIC = 0x62664f7665726c70ull;
 
 // ---------------------------------------------------------------- kernels
-
-// seg[c] = first sorted position whose group rank is >= c
-__global__ void segment_table_kernel(const u64* __restrict__ keys, i64 n, KeyLayout L, i32 nb,
-                                     i64* __restrict__ seg) {
-  i32 c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > nb) return;
-  if (c == nb) {
-    seg[c] = n;
-    return;
-  }
-  seg[c] = lower_bound_by(0, n, [&](i64 m) { return key_rank(keys[m], L) < (u32)c; });
-}
 
 // inclusive running max of ce(key) in sorted order (np.maximum.accumulate over
 // end', group resets come free because the group rank is the high field)
@@ -594,109 +576,6 @@ __global__ void __launch_bounds__(256) emit_unpaired_kernel(const u64* __restric
   ev2[out] = SECOND ? row : -1;
 }
 
-// ---- tie fix-up: rows sharing (group, start) into (end', row) order ----
-// After the stable sort on cs the rows of a tie run are in row order; the
-// reference wants them by (end', row).  Tied rows are rare, so: count them,
-// compact (key, id, slot), sort that subset by the FULL key (stable, so equal
-// keys keep row order) and write it back into the same slots in order.
-// One pass: stage the tile's keys (+ one halo key each side) in shared memory,
-// flag tied rows, scan the flags (tile scan + look-back) and write the subset.
-__global__ void __launch_bounds__(SC_THREADS)
-    tie_compact_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, KeyLayout L, ScanState ss,
-                       u64* __restrict__ tkeys, u32* __restrict__ tids, u32* __restrict__ tpos,
-                       u64* __restrict__ nT) {
-  __shared__ u64 s_k[SC_TILE + 2];
-  __shared__ u64 s_tmp[8];
-  __shared__ u64 s_prefix;
-  __shared__ u32 s_ticket;
-  const u32 tid = threadIdx.x;
-  const u64 tile = take_ticket(ss.ticket, &s_ticket);
-  const u64 base = tile * SC_TILE;
-  const u64 rows = n - base < (u64)SC_TILE ? n - base : (u64)SC_TILE;
-  for (u32 i = tid; i < rows + 2; i += SC_THREADS) {
-    const i64 p = (i64)base + i - 1;
-    // halo outside the array: a key whose cs differs from every neighbour's
-    s_k[i] = (p >= 0 && (u64)p < n) ? keys[p] : ~0ull;
-  }
-  __syncthreads();
-  const bool lo_edge = base == 0, hi_edge = base + rows == n;
-  u32 mask = 0;
-#pragma unroll
-  for (int j = 0; j < SC_IPT; ++j) {
-    const u32 r = tid * SC_IPT + j;  // row inside the tile, s_k index r + 1
-    if (r < rows) {
-      const u64 c = key_cs(s_k[r + 1], L);
-      const bool prev_ok = !(lo_edge && r == 0);
-      const bool next_ok = !(hi_edge && r + 1 == rows);
-      if ((prev_ok && key_cs(s_k[r], L) == c) || (next_ok && key_cs(s_k[r + 2], L) == c)) mask |= 1u << j;
-    }
-  }
-  u64 tot;
-  u64 at = block_excl_sum_u64((u64)__popc(mask), s_tmp, &tot);
-  if (tid < 32) {
-    const u64 pre = lookback_exclusive(ss.status, tile, tot);
-    if (tid == 0) s_prefix = pre;
-  }
-  __syncthreads();
-  at += s_prefix;
-#pragma unroll
-  for (int j = 0; j < SC_IPT; ++j) {
-    if (mask & (1u << j)) {
-      const u32 r = tid * SC_IPT + j;
-      tkeys[at] = s_k[r + 1];
-      tids[at] = ids[base + r];
-      tpos[at] = (u32)(base + r);
-      ++at;
-    }
-  }
-  if (hi_edge && tid == 0) *nT = s_prefix + tot;
-}
-__global__ void __launch_bounds__(256) tie_scatter_kernel(const u64* __restrict__ tkeys, const u32* __restrict__ tids,
-                                                          const u32* __restrict__ tpos, const u64* __restrict__ nT,
-                                                          u64* __restrict__ keys, u32* __restrict__ ids) {
-  const u64 n = *nT;
-  for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (u64)gridDim.x * blockDim.x) {
-    const u32 p = tpos[t];
-    keys[p] = tkeys[t];
-    ids[p] = tids[t];
-  }
-}
-
-// ---------------------------------------------------------------- host side
-
-static int sort_set(const i32* grp, const i64* s, const i64* e, i64 n, const KeyLayout& L, SetWS& ws,
-                    const RadixScratch& sc, u64* nT, cudaStream_t st, SortResult* res) {
-  res->keys = ws.keyA;
-  res->vals = ws.idA;
-  res->keys_alt = ws.keyB;
-  res->vals_alt = ws.idB;
-  if (n == 0) return BF_OK;
-  // main sort: stable, on the (group, start) bits only
-  const RadixPlan rp = make_radix_plan(L.LB, L.total_bits);
-  BF_CUDA(cudaMemsetAsync(sc.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
-  BF_TRY(launch_pack_keys(grp, s, e, (u64)n, L, 1, rp, ws.keyA, sc.hist, st));
-  BF_TRY(radix_sort_passes<true>(ws.keyA, ws.keyB, ws.idA, ws.idB, true, (u64)n, nullptr, rp, sc, st, res));
-  // tie fix-up on the subset of rows that share (group, start); scratch aliases
-  // buffers that are not in use yet (the sort's spare buffers, scan/lo/cnt)
-  const unsigned tiles = (unsigned)scan_tiles((u64)n);
-  u64* tkeyA = res->keys_alt;
-  u32* tidA = res->vals_alt;
-  u64* tkeyB = ws.scan;
-  u32* tidB = ws.lo;
-  u32* tpos = ws.cnt;
-  BF_TRY(reset_scan_state(ws.ss, tiles, st));
-  BF_LAUNCH(PC_TIEFIX, 8 * n, st,
-            tie_compact_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, L, ws.ss, tkeyA, tidA, tpos, nT));
-  const RadixPlan full = make_radix_plan(0, L.total_bits);
-  BF_CUDA(cudaMemsetAsync(sc.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
-  BF_TRY(launch_radix_hist(tkeyA, (u64)n, nT, full, sc.hist, st, PC_TIEFIX));
-  SortResult tr;
-  BF_TRY(radix_sort_passes<true>(tkeyA, tkeyB, tidA, tidB, false, (u64)n, nT, full, sc, st, &tr, PC_TIEFIX));
-  BF_LAUNCH(PC_TIEFIX, 0, st,
-            tie_scatter_kernel<<<stream_grid((u64)n, 256 * 64), 256, 0, st>>>(tr.keys, tr.vals, tpos, nT, res->keys, res->vals));
-  return BF_OK;
-}
-
 static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64 n1, const i32* grp2,
                               const i64* s2, const i64* e2, i64 n2, i32 nb, i32 how, i32 closed,
                               void* ws_ptr, size_t ws_bytes, OverlapPlan* plan, cudaStream_t st) {
@@ -756,8 +635,8 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   plan->L = L;
   // ---- sort both sets ----
   SortResult r1, r2;
-  BF_TRY(sort_set(nb > 1 ? grp1 : nullptr, s1, e1, n1, L, w.s[0], w.radix, w.nT + 0, st, &r1));
-  BF_TRY(sort_set(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, w.s[1], w.radix, w.nT + 1, st, &r2));
+  BF_TRY(sort_rows(nb > 1 ? grp1 : nullptr, s1, e1, n1, L, 1, w.s[0].sb, w.radix, st, &r1));
+  BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, 1, w.s[1].sb, w.radix, st, &r2));
   plan->key1 = r1.keys;
   plan->id1 = r1.vals;
   plan->key2 = r2.keys;
