@@ -53,6 +53,20 @@ SIGNATURES = {
          C.POINTER(_i64), C.POINTER(_i64)],
     ),
     "bf_overlap_emit": (C.c_int, [C.POINTER(Plan), _p, _p, _p, _p]),
+    "bf_cluster_workspace_bytes": (_sz, [_i64, _i32]),
+    "bf_cluster_count": (
+        C.c_int,
+        [_p, _p, _p, _i64, _i32, _i64, _i32, _p, _sz, C.POINTER(Plan), _p, _p, C.POINTER(_i64)],
+    ),
+    "bf_cluster_emit": (C.c_int, [C.POINTER(Plan), _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "bf_coverage_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "bf_coverage": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _i32, _p, _sz, _p, _p]),
+    "bf_complement_workspace_bytes": (_sz, [_i64, _i32]),
+    "bf_complement_count": (
+        C.c_int,
+        [_p, _p, _p, _i64, _p, _p, _i32, _p, _sz, C.POINTER(Plan), _p, C.POINTER(_i64)],
+    ),
+    "bf_complement_emit": (C.c_int, [C.POINTER(Plan), _p, _p, _p, _p, _p]),
 }
 
 _lib = None

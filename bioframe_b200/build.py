@@ -21,8 +21,8 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
     "--expt-extended-lambda", "--expt-relaxed-constexpr",
-    "-shared",
 ]
+OBJ_DIR = os.path.join(PKG, "build")
 
 
 def sources():
@@ -37,18 +37,32 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
-        return LIB
-    nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-o", LIB, *sources()]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
+def _run(cmd):
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        log = (proc.stdout + proc.stderr).strip().splitlines()
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + "\n".join(log[:60]))
+    return proc.stderr
+
+
+def build(force=False, verbose=False):
+    """One nvcc -c per translation unit (in parallel), then one link."""
+    if not force and not stale():
+        return LIB
+    from concurrent.futures import ThreadPoolExecutor
+
+    nvcc = os.environ.get("NVCC", "nvcc")
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    extra = ["-Xptxas=-v"] if verbose else []
+    jobs = []
+    for src in sources():
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        jobs.append((obj, [nvcc, *NVCC_FLAGS, *extra, "-I", INCLUDE, "-c", src, "-o", obj]))
+    with ThreadPoolExecutor(max_workers=len(jobs)) as pool:
+        logs = list(pool.map(lambda j: _run(j[1]), jobs))
+    _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *[j[0] for j in jobs]])
     if verbose:
-        print(proc.stderr)
+        print("\n".join(logs))
     return LIB
 
 

@@ -431,7 +431,9 @@ __global__ void __launch_bounds__(256)
   i64 cnt;
   i32 first;
   if (m == 0) {
-    first = b0 < b1;
+    // a region without any interval yields the whole region (ops.py:1652-1657);
+    // one whose merged intervals all fall outside the bounds yields it only if non-empty
+    first = (c0 == c1) ? 1 : (b0 < b1);
     cnt = first;
   } else {
     first = b0 < tab.cstart[lo];

@@ -44,7 +44,7 @@ struct Extent {  // device-side reduction target
   i32 gmin, gmax;
 };
 
-__global__ void extent_init_kernel(Extent* x) {
+static __global__ void extent_init_kernel(Extent* x) {
   x->cmin = 0x7fffffffffffffffLL;
   x->cmax = (i64)0x8000000000000000ULL;
   x->lmin = 0x7fffffffffffffffLL;
@@ -54,7 +54,7 @@ __global__ void extent_init_kernel(Extent* x) {
 }
 
 // min/max of coordinates (end' when point_adjust), of lengths and of group codes
-__global__ void __launch_bounds__(256) extent_kernel(const i32* __restrict__ grp, const i64* __restrict__ s,
+static __global__ void __launch_bounds__(256) extent_kernel(const i32* __restrict__ grp, const i64* __restrict__ s,
                                                      const i64* __restrict__ e, u64 n, int point_adjust,
                                                      Extent* __restrict__ out) {
   i64 lo = 0x7fffffffffffffffLL, hi = (i64)0x8000000000000000ULL;
@@ -121,7 +121,7 @@ static inline int make_key_layout(const Extent& x, i32 n_groups, KeyLayout* L) {
 
 // Build keys and, in the same pass over the inputs, the histograms of every
 // radix digit place (so the sort never re-reads the keys to count them).
-__global__ void __launch_bounds__(HIST_THREADS) pack_keys_kernel(const i32* __restrict__ grp, const i64* __restrict__ s,
+static __global__ void __launch_bounds__(HIST_THREADS) pack_keys_kernel(const i32* __restrict__ grp, const i64* __restrict__ s,
                                                                  const i64* __restrict__ e, u64 n, KeyLayout L,
                                                                  int point_adjust, RadixPlan rp,
                                                                  u64* __restrict__ keys, u64* __restrict__ ghist) {

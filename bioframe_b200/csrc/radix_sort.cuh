@@ -122,7 +122,7 @@ static inline size_t hist_smem_bytes(const RadixPlan& rp) {
 
 // Generic histogram over an existing key array (n may live on the device).
 // Dynamic shared memory: hist_smem_bytes(rp).
-__global__ void __launch_bounds__(HIST_THREADS) radix_hist_kernel(const u64* __restrict__ keys, u64 n_host,
+static __global__ void __launch_bounds__(HIST_THREADS) radix_hist_kernel(const u64* __restrict__ keys, u64 n_host,
                                                                    const u64* __restrict__ n_dev, RadixPlan rp,
                                                                    u64* __restrict__ ghist) {
   extern __shared__ u32 hist_tabs[];
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(HIST_THREADS) radix_hist_kernel(const u64* __r
 }
 
 // counts -> exclusive digit bases, one block per digit place
-__global__ void __launch_bounds__(RS_BINS) radix_bases_kernel(u64* __restrict__ ghist) {
+static __global__ void __launch_bounds__(RS_BINS) radix_bases_kernel(u64* __restrict__ ghist) {
   __shared__ u64 warp_tot[RS_BINS / 32];
   u64* row = ghist + (size_t)blockIdx.x * RS_BINS;
   const u32 d = threadIdx.x, lane = d & 31, w = d >> 5;
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
   }  // next tile
 }
 
-__global__ void iota_u32_kernel(u32* __restrict__ out, u64 n) {
+static __global__ void iota_u32_kernel(u32* __restrict__ out, u64 n) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (u32)i;
 }

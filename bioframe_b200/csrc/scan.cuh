@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(1024) spine_scan_kernel(u64* __restrict__ spin
 }
 
 // ---- per-tile sums of a u32 array (when no producer wrote the spine) ----
-__global__ void __launch_bounds__(SC_THREADS) tile_sum_u32_kernel(const u32* __restrict__ in, u64 n,
+static __global__ void __launch_bounds__(SC_THREADS) tile_sum_u32_kernel(const u32* __restrict__ in, u64 n,
                                                                   u64* __restrict__ spine) {
   __shared__ u64 s_tmp[8];
   const u64 base = (u64)blockIdx.x * SC_TILE;
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(SC_THREADS) tile_sum_u32_kernel(const u32* __r
 }
 
 // ---- downsweep: out[i] = spine[tile] + sum(in[tile_start .. i)), out[n] = total ----
-__global__ void __launch_bounds__(SC_THREADS) excl_sum_u32_kernel(const u32* __restrict__ in, u64 n,
+static __global__ void __launch_bounds__(SC_THREADS) excl_sum_u32_kernel(const u32* __restrict__ in, u64 n,
                                                                   const u64* __restrict__ spine,
                                                                   u64* __restrict__ out) {
   __shared__ u64 s_tmp[8];

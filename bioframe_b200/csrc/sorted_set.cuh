@@ -42,7 +42,7 @@ static inline void take_sort_bufs(Arena& a, i64 n, SortBufs* b) {
 // keys keep row order) and write it back into the same slots in order.
 // One pass: stage the tile's keys (+ one halo key each side) in shared memory,
 // flag tied rows, scan the flags (tile scan + look-back) and write the subset.
-__global__ void __launch_bounds__(SC_THREADS)
+static __global__ void __launch_bounds__(SC_THREADS)
     tie_compact_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, KeyLayout L, ScanState ss,
                        u64* __restrict__ tkeys, u32* __restrict__ tids, u32* __restrict__ tpos,
                        u64* __restrict__ nT) {
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(SC_THREADS)
   }
   if (hi_edge && tid == 0) *nT = s_prefix + tot;
 }
-__global__ void __launch_bounds__(256) tie_scatter_kernel(const u64* __restrict__ tkeys, const u32* __restrict__ tids,
+static __global__ void __launch_bounds__(256) tie_scatter_kernel(const u64* __restrict__ tkeys, const u32* __restrict__ tids,
                                                           const u32* __restrict__ tpos, const u64* __restrict__ nT,
                                                           u64* __restrict__ keys, u32* __restrict__ ids) {
   const u64 n = *nT;
@@ -140,7 +140,7 @@ static int sort_rows(const i32* grp, const i64* s, const i64* e, i64 n, const Ke
 }
 
 // seg[c] = first sorted position whose group rank is >= c   (c = 0..nb, seg[nb] = n)
-__global__ void segment_table_kernel(const u64* __restrict__ keys, i64 n, KeyLayout L, i32 nb,
+static __global__ void segment_table_kernel(const u64* __restrict__ keys, i64 n, KeyLayout L, i32 nb,
                                      i64* __restrict__ seg) {
   i32 c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c > nb) return;

@@ -86,3 +86,92 @@ def overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how="inner
         rc = L.bf_overlap_emit(C.byref(plan), _ptr(ws), _ptr(ev1), _ptr(ev2), stream)
         _lib.check(rc, "bf_overlap_emit")
     return ev1, ev2, n_pairs.value
+
+
+def cluster(grp, start, end, n_groups, min_dist=0, want_ids=True, want_table=True, want_row_spans=False, device=None):
+    """merge_intervals over all groups (group code order = sorted key order).
+
+    Returns dict(ids=int64[n] | None, n_clusters, cgrp=int32[C], cstart, cend,
+    ccount=int64[C], row_start/row_end=int64[n] | None); tensors stay on device."""
+    _require_cuda()
+    L = _lib.lib()
+    device = torch.device(device if device is not None else "cuda")
+    s, e = _as(start, torch.int64, device), _as(end, torch.int64, device)
+    g = _as(grp, torch.int32, device) if n_groups > 1 else None
+    n = int(s.numel())
+    has_md = 0 if min_dist is None else 1
+    md = 0 if min_dist is None else int(min_dist)
+    need_ids = want_ids or want_row_spans
+    with torch.cuda.device(device):
+        ws = Workspace.get(device, max(L.bf_cluster_workspace_bytes(n, n_groups), 256))
+        plan = _lib.Plan()
+        nc = C.c_int64(0)
+        stream = _stream_ptr(device)
+        ids = torch.empty(n, dtype=torch.int64, device=device) if need_ids else None
+        rc = L.bf_cluster_count(_ptr(g), _ptr(s), _ptr(e), n, n_groups, md, has_md, _ptr(ws), ws.numel(),
+                                C.byref(plan), stream, _ptr(ids), C.byref(nc))
+        _lib.check(rc, "bf_cluster_count")
+        c = nc.value
+        out = dict(ids=ids, n_clusters=c, cgrp=None, cstart=None, cend=None, ccount=None, row_start=None, row_end=None)
+        if want_table:
+            out["cgrp"] = torch.empty(c, dtype=torch.int32, device=device)
+            out["cstart"] = torch.empty(c, dtype=torch.int64, device=device)
+            out["cend"] = torch.empty(c, dtype=torch.int64, device=device)
+            out["ccount"] = torch.empty(c, dtype=torch.int64, device=device)
+        if want_row_spans:
+            out["row_start"] = torch.empty(n, dtype=torch.int64, device=device)
+            out["row_end"] = torch.empty(n, dtype=torch.int64, device=device)
+        if want_table or want_row_spans:
+            rc = L.bf_cluster_emit(C.byref(plan), _ptr(ws), _ptr(out["cgrp"]), _ptr(out["cstart"]), _ptr(out["cend"]),
+                                   _ptr(out["ccount"]), _ptr(ids), _ptr(out["row_start"]), _ptr(out["row_end"]), stream)
+            _lib.check(rc, "bf_cluster_emit")
+    return out
+
+
+def coverage(grp1, start1, end1, grp2, start2, end2, n_groups, device=None):
+    """Covered base pairs of every row of set 1 by the union of set 2 -> int64[n1] (device)."""
+    _require_cuda()
+    L = _lib.lib()
+    device = torch.device(device if device is not None else "cuda")
+    s1, e1 = _as(start1, torch.int64, device), _as(end1, torch.int64, device)
+    s2, e2 = _as(start2, torch.int64, device), _as(end2, torch.int64, device)
+    g1 = _as(grp1, torch.int32, device) if n_groups > 1 else None
+    g2 = _as(grp2, torch.int32, device) if n_groups > 1 else None
+    n1, n2 = int(s1.numel()), int(s2.numel())
+    with torch.cuda.device(device):
+        ws = Workspace.get(device, max(L.bf_coverage_workspace_bytes(n1, n2, n_groups), 256))
+        cov = torch.empty(n1, dtype=torch.int64, device=device)
+        rc = L.bf_coverage(_ptr(g1), _ptr(s1), _ptr(e1), n1, _ptr(g2), _ptr(s2), _ptr(e2), n2, n_groups,
+                           _ptr(ws), ws.numel(), _stream_ptr(device), _ptr(cov))
+        _lib.check(rc, "bf_coverage")
+    return cov
+
+
+def complement(region, start, end, bounds_lo, bounds_hi, device=None):
+    """Gaps of the (already clipped) intervals inside each view region.
+    -> (region int32[G], start int64[G], end int64[G]) on device, regions in code order."""
+    _require_cuda()
+    L = _lib.lib()
+    device = torch.device(device if device is not None else "cuda")
+    s, e = _as(start, torch.int64, device), _as(end, torch.int64, device)
+    b0, b1 = _as(bounds_lo, torch.int64, device), _as(bounds_hi, torch.int64, device)
+    nr = int(b0.numel())
+    if nr == 0:
+        z = torch.empty(0, dtype=torch.int64, device=device)
+        return torch.empty(0, dtype=torch.int32, device=device), z, z.clone()
+    g = _as(region, torch.int32, device) if nr > 1 else None
+    n = int(s.numel())
+    with torch.cuda.device(device):
+        ws = Workspace.get(device, max(L.bf_complement_workspace_bytes(n, nr), 256))
+        plan = _lib.Plan()
+        ng = C.c_int64(0)
+        stream = _stream_ptr(device)
+        rc = L.bf_complement_count(_ptr(g), _ptr(s), _ptr(e), n, _ptr(b0), _ptr(b1), nr, _ptr(ws), ws.numel(),
+                                   C.byref(plan), stream, C.byref(ng))
+        _lib.check(rc, "bf_complement_count")
+        reg = torch.empty(ng.value, dtype=torch.int32, device=device)
+        gs = torch.empty(ng.value, dtype=torch.int64, device=device)
+        ge = torch.empty(ng.value, dtype=torch.int64, device=device)
+        rc = L.bf_complement_emit(C.byref(plan), _ptr(ws), _ptr(reg), _ptr(gs), _ptr(ge), stream)
+        _lib.check(rc, "bf_complement_emit")
+    return reg, gs, ge

@@ -86,6 +86,48 @@ int bf_overlap_count(const int32_t* grp1, const int64_t* start1, const int64_t* 
 int bf_overlap_emit(const bf_plan* plan, void* ws, int64_t* events1_out, int64_t* events2_out,
                     void* stream);
 
+/* ---- cluster / merge: replaces the group loops of ops.cluster (ops.py:637-674)
+ * and ops.merge (ops.py:776-810) around arrops.merge_intervals
+ * (arrops.py:415-479).  Groups are visited in code order (= sorted key order,
+ * `df.groupby(...).groups`), cluster ids run on across groups
+ * (ops.py:654-656).  `has_min_dist` = 0 is min_dist=None (adjacent intervals are
+ * NOT merged, arrops.py:470); otherwise borders are start > runmax + min_dist
+ * (arrops.py:468).  `cluster_ids_out` (int64[n], input row order) may be NULL
+ * (merge only needs the table).  bf_cluster_emit writes the cluster table
+ * (group code, start, end, n_intervals -- np.bincount of ops.py:653; any may be
+ * NULL) and, when `cluster_ids` + row outputs are given, cluster_start/end per
+ * input row (ops.py:696-701). */
+size_t bf_cluster_workspace_bytes(int64_t n, int32_t n_groups);
+int bf_cluster_count(const int32_t* grp, const int64_t* start, const int64_t* end, int64_t n,
+                     int32_t n_groups, int64_t min_dist, int32_t has_min_dist, void* ws,
+                     size_t ws_bytes, bf_plan* plan, void* stream, int64_t* cluster_ids_out,
+                     int64_t* n_clusters_out);
+int bf_cluster_emit(const bf_plan* plan, void* ws, int32_t* cgrp_out, int64_t* cstart_out,
+                    int64_t* cend_out, int64_t* ccount_out, const int64_t* cluster_ids,
+                    int64_t* row_start_out, int64_t* row_end_out, void* stream);
+
+/* ---- coverage: replaces ops.coverage (ops.py:842-916): merge(df2), left
+ * overlap with clipped coordinates, per-query sum.  Computed without
+ * enumerating pairs (prefix sums of merged lengths + two searches per query);
+ * same integers out.  coverage_out: int64[n1] in input row order. */
+size_t bf_coverage_workspace_bytes(int64_t n1, int64_t n2, int32_t n_groups);
+int bf_coverage(const int32_t* grp1, const int64_t* start1, const int64_t* end1, int64_t n1,
+                const int32_t* grp2, const int64_t* start2, const int64_t* end2, int64_t n2,
+                int32_t n_groups, void* ws, size_t ws_bytes, void* stream, int64_t* coverage_out);
+
+/* ---- complement: replaces the per-view-region loop of ops.complement
+ * (ops.py:1644-1685) around arrops.complement_intervals (arrops.py:482-503).
+ * `region` = code of the view region each (already clipped) interval belongs
+ * to, regions in sorted name order; bounds_lo/hi = device int64[n_regions]
+ * region start/end.  Output rows: per region in code order its gaps
+ * (region code, start, end). */
+size_t bf_complement_workspace_bytes(int64_t n, int32_t n_regions);
+int bf_complement_count(const int32_t* region, const int64_t* start, const int64_t* end, int64_t n,
+                        const int64_t* bounds_lo, const int64_t* bounds_hi, int32_t n_regions,
+                        void* ws, size_t ws_bytes, bf_plan* plan, void* stream, int64_t* n_gaps_out);
+int bf_complement_emit(const bf_plan* plan, void* ws, int32_t* region_out, int64_t* start_out,
+                       int64_t* end_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -234,3 +234,48 @@ def complement_core(region_codes, starts, ends, region_bounds):
         os_.append(np.asarray(gs, dtype=np.int64))
         oe.append(np.asarray(ge, dtype=np.int64))
     return np.concatenate(oc), np.concatenate(os_), np.concatenate(oe)
+
+
+def _rows_by_code(g, n, n_groups):
+    if n_groups == 1 or g is None:
+        return [np.arange(n)]
+    g = np.asarray(g)
+    o = np.argsort(g, kind="stable")
+    b = np.searchsorted(g[o], np.arange(n_groups + 1))
+    return [o[b[c] : b[c + 1]] for c in range(n_groups)]
+
+
+def cluster_coded(g, s, e, n_groups, min_dist=0):
+    """cluster ids per row + cluster table (start, end, n_intervals) with the
+    groups visited in code order -- the contract of the C ABI's bf_cluster_*
+    (ops.py:637-674 with group codes standing in for sorted group keys)."""
+    s, e = np.asarray(s, dtype=np.int64), np.asarray(e, dtype=np.int64)
+    ids = np.full(len(s), -1, dtype=np.int64)
+    cs, ce, cn, cg = [], [], [], []
+    base = 0
+    for c, rows in enumerate(_rows_by_code(g, len(s), n_groups)):
+        if len(rows) == 0:
+            continue
+        gi, gs, ge = ao.merge_intervals(s[rows], e[rows], min_dist)
+        ids[rows] = gi + base
+        base += len(gs)
+        cs.append(gs)
+        ce.append(ge)
+        cn.append(np.bincount(gi))
+        cg.append(np.full(len(gs), c))
+    cat = lambda xs: np.concatenate(xs).astype(np.int64) if xs else np.empty(0, dtype=np.int64)  # noqa: E731
+    cluster_coded.last_groups = cat(cg)
+    return ids, cat(cs), cat(ce), cat(cn)
+
+
+def coverage_coded(g1, s1, e1, g2, s2, e2, n_groups):
+    """coverage on group-coded arrays, the reference's way: merge set 2, inner
+    overlap, clip, per-query sum (ops.py:888-912)."""
+    s1, e1 = np.asarray(s1, dtype=np.int64), np.asarray(e1, dtype=np.int64)
+    _, ms, me, _ = cluster_coded(g2, s2, e2, n_groups, 0)
+    mg = cluster_coded.last_groups.astype(np.int32)
+    i, j = overlap_intidxs_coded(g1, s1, e1, mg, ms, me, n_groups, how="inner")
+    ov = np.minimum(e1[i], me[j]) - np.maximum(s1[i], ms[j])
+    out = np.zeros(len(s1), dtype=np.int64)
+    np.add.at(out, i, ov)
+    return out
