@@ -22,6 +22,7 @@ ERRORS = {
     -6: "BF_ERR_STATE",
 }
 HOW = {"inner": 0, "left": 1, "right": 2, "outer": 3}
+CLOSEST_IGNORE_OVERLAPS, CLOSEST_IGNORE_UPSTREAM, CLOSEST_IGNORE_DOWNSTREAM, CLOSEST_SELF = 1, 2, 4, 8
 
 
 class Plan(C.Structure):
@@ -53,6 +54,13 @@ SIGNATURES = {
          C.POINTER(_i64), C.POINTER(_i64)],
     ),
     "bf_overlap_emit": (C.c_int, [C.POINTER(Plan), _p, _p, _p, _p]),
+    "bf_closest_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "bf_closest_count": (
+        C.c_int,
+        [_p, _p, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _sz, C.POINTER(Plan), _p,
+         C.POINTER(_i64), C.POINTER(_i64)],
+    ),
+    "bf_closest_emit": (C.c_int, [C.POINTER(Plan), _p, _p, _p, _p]),
     "bf_cluster_workspace_bytes": (_sz, [_i64, _i32]),
     "bf_cluster_count": (
         C.c_int,

@@ -1,0 +1,521 @@
+// bf_closest_count / bf_closest_emit: the whole of ops._closest_intidxs
+// (src/bioframe/ops.py:919-1040) for all groups in one set of launches, i.e. the
+// per-group loop around arrops.closest_intervals (arrops.py:601-754) and
+// arrops._closest_intervals_nooverlap (arrops.py:506-598).
+//
+// The reference materialises every candidate event (all overlaps, k left, k right
+// neighbours of every query) and lexsorts the lot by (query, distance, target)
+// -- 97 % of its run time.  Here nothing global is materialised: the targets
+// are sorted twice (by linear start and by linear end, stable, so ties are in
+// row order exactly like a stable argsort), and every query is one thread that
+//   * finds its four positions by binary search (arrops.py:338-339, 569, 587),
+//   * walks its candidates -- overlaps (distance 0), the last k targets ending
+//     at or before its start (distance start - end + 1, arrops.py:724), the
+//     first k targets starting at or after its end (arrops.py:725) -- and
+//   * keeps the k smallest by (distance, target row) with an insertion into its
+//     own slice of the output (arrops.py:737-754).
+// Candidates form a multiset exactly as in the reference (a point query
+// reports a target starting at the same position both as an overlap and as a
+// right neighbour).
+//
+// Output order (ops.py:997-1035): per group in rank order, the matched rows of
+// the group's queries in ascending row order, then (row, -1) for its unmatched
+// queries in ascending row order.  Queries are put in (group, row) order by one
+// stable radix pass over the group rank; two fused exclusive scans (rows per
+// query, unmatched flags) and a per-group table place every slice.
+#include "common.cuh"
+#include "keys.cuh"
+#include "lookback.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+#include "sorted_set.cuh"
+#include "../../include/bioframe_b200.h"
+
+namespace bf {
+
+struct ClosestWS {
+  SortBufs by_start, by_end;  // the two target orders
+  RadixScratch radix;
+  LayoutScratch layout;
+  u64* pmax;        // [n2] running max of linear end' over the start order
+  i64* seg;         // [nb+1] first sorted target of each group (same for both orders)
+  u64 *qkeyA, *qkeyB;  // [n1] (rank << 32 | row) of the queries
+  i64* qseg;        // [nb+1] first query of each group in (group, row) order
+  uint4* qpos;      // [n1] (loA, hiA, stop, begin) of every query, in (group, row) order
+  u64 *rows, *lone; // [n1+1] exclusive scans: output rows, unmatched queries
+  ScanState ss_rows, ss_lone, ss_tmp;
+  i64 *obase, *ubase;  // [nb+1] first output row of a group's matched / unmatched block
+  i64* header;      // n_rows, n_matched_rows
+  u64* nq;          // [1] device count for the query sort
+};
+static void layout_closest(Arena& a, i64 n1, i64 n2, i32 nb, ClosestWS* w) {
+  take_sort_bufs(a, n2, &w->by_start);
+  take_sort_bufs(a, n2, &w->by_end);
+  w->radix = take_radix_scratch(a, (u64)(n1 > n2 ? n1 : n2));
+  w->layout = take_layout_scratch(a, nb);
+  w->pmax = a.take<u64>(n2 + 1);
+  w->seg = a.take<i64>(nb + 2);
+  w->qkeyA = a.take<u64>(n1 + 1);
+  w->qkeyB = a.take<u64>(n1 + 1);
+  w->qseg = a.take<i64>(nb + 2);
+  w->qpos = a.take<uint4>(n1 + 1);
+  w->rows = a.take<u64>(n1 + 2);
+  w->lone = a.take<u64>(n1 + 2);
+  const u64 tiles = (u64)scan_tiles((u64)(n1 > n2 ? n1 : n2));
+  w->ss_rows = take_scan_state(a, tiles);
+  w->ss_lone = take_scan_state(a, tiles);
+  w->ss_tmp = take_scan_state(a, tiles);
+  w->obase = a.take<i64>(nb + 2);
+  w->ubase = a.take<i64>(nb + 2);
+  w->header = a.take<i64>(4);
+  w->nq = a.take<u64>(1);
+}
+
+struct ClosestArgs {  // everything a query thread needs (kernel parameter)
+  const i32* grp1;
+  const i64 *s1, *e1;
+  const u8* along;   // may be null: every query looks along the axis
+  const u64 *kS, *kE;  // target keys in start order / end order
+  const u32 *idS, *idE;
+  const u64* pmax;
+  const i64 *seg, *qseg;
+  const u64* qkey;   // (rank << 32 | row) in (group, row) order; null: identity (one group)
+  KeyLayout L;
+  i64 n1, n2;
+  i32 k, self, ignore_overlaps, k_up, k_dn;
+};
+
+struct ClosestPlan {
+  u64 magic;
+  i32 ready, pad;
+  i64 n_rows, n_matched;
+  ClosestArgs args;
+};
+static_assert(sizeof(ClosestPlan) <= sizeof(bf_plan), "bf_plan too small");
+constexpr u64 CLOSEST_MAGIC = 0x6266436c6f736573ull;
+
+// ---------------------------------------------------------------- kernels
+
+// running max of linear end' (raw-length keys: end' = end + (len == 0)) in start order
+__device__ __forceinline__ u64 key_ce_adj(u64 k, const KeyLayout& L) {
+  const u64 len = k & L.lmask;
+  return (k >> L.LB) + len + (len == 0);
+}
+__global__ void __launch_bounds__(SC_THREADS)
+    runmax_adj_kernel(const u64* __restrict__ keys, u64 n, KeyLayout L, ScanState ss, u64* __restrict__ pmax) {
+  __shared__ u64 s_tmp[8];
+  __shared__ u64 s_pre;
+  __shared__ u32 s_ticket;
+  const u32 tid = threadIdx.x;
+  const u64 tile = take_ticket(ss.ticket, &s_ticket);
+  const u64 base = tile * SC_TILE + (u64)tid * SC_IPT;
+  u64 v[SC_IPT];
+  u64 mine = 0;
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    v[j] = base + j < n ? key_ce_adj(keys[base + j], L) : 0ull;
+    mine = v[j] > mine ? v[j] : mine;
+  }
+  u64 before = block_excl_max_u64(mine, s_tmp);
+  const u64 tile_max = block_max_u64(mine, s_tmp);
+  if (tid < 32) {
+    const u64 pre = lookback_exclusive_max(ss.status, tile, tile_max);
+    if (tid == 0) s_pre = pre;
+  }
+  __syncthreads();
+  u64 run = before > s_pre ? before : s_pre;
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    run = v[j] > run ? v[j] : run;
+    if (base + j < n) pmax[base + j] = run;
+  }
+}
+
+__global__ void __launch_bounds__(256) query_keys_kernel(const i32* __restrict__ grp, i64 n, u64* __restrict__ qkey) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) qkey[i] = ((u64)(u32)grp[i] << 32) | (u64)i;
+}
+__global__ void query_segments_kernel(const u64* __restrict__ qkey, i64 n, i32 nb, i64* __restrict__ qseg) {
+  const i32 c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > nb) return;
+  if (!qkey) {  // one group, identity order
+    qseg[c] = c == 0 ? 0 : n;
+    return;
+  }
+  qseg[c] = lower_bound_by(0, n, [&](i64 m) { return (qkey[m] >> 32) < (u64)c; });
+}
+
+struct Probe {
+  i64 row;        // query row
+  u32 rank;
+  i64 t0, t1;     // the group's targets: [t0, t1) in both orders
+  i64 loA, hiA;   // start order: targets starting inside [s1, e1')
+  i64 stop;       // end order: targets ending at or before s1 are [t0, stop)
+  i64 begin;      // start order: targets starting at or after e1 are [begin, t1)
+  u64 xs, xe;     // linear start / raw end of the query
+  i32 k_left, k_right;
+};
+
+__device__ __forceinline__ void closest_probe(const ClosestArgs& A, i64 t, Probe* P) {
+  const KeyLayout& L = A.L;
+  i64 row = t;
+  u32 rank = 0;
+  if (A.qkey) {
+    const u64 q = A.qkey[t];
+    row = (i64)(q & 0xffffffffull);
+    rank = (u32)(q >> 32);
+  }
+  P->row = row;
+  P->rank = rank;
+  const i64 t0 = A.seg[rank], t1 = A.seg[rank + 1];
+  P->t0 = t0;
+  P->t1 = t1;
+  const i64 a = A.s1[row], b = A.e1[row];
+  const u64 off = L.goff[rank];
+  const u64 xs = off + ((u64)a - L.cmin), xe = off + ((u64)b - L.cmin);
+  const u64 xe_adj = xe + (a == b);
+  P->xs = xs;
+  P->xe = xe;
+  P->loA = lower_bound_by(t0, t1, [&](i64 m) { return key_cs(A.kS[m], L) < xs; });
+  P->begin = lower_bound_by(P->loA, t1, [&](i64 m) { return key_cs(A.kS[m], L) < xe; });
+  P->hiA = (a == b) ? lower_bound_by(P->begin, t1, [&](i64 m) { return key_cs(A.kS[m], L) < xe_adj; }) : P->begin;
+  P->stop = lower_bound_by(t0, t1, [&](i64 m) { return key_cs(A.kE[m], L) <= xs; });
+  const bool fwd = A.along ? A.along[row] != 0 : true;
+  P->k_left = fwd ? A.k_up : A.k_dn;   // arrops.py:667-706: "-" rows look right for upstream
+  P->k_right = fwd ? A.k_dn : A.k_up;
+}
+
+// number of overlapping targets of the query, counted only up to `need`
+__device__ __forceinline__ i64 count_overlaps_upto(const ClosestArgs& A, const Probe& P, i64 need) {
+  const KeyLayout& L = A.L;
+  i64 c = P.hiA - P.loA;
+  if (A.self && c > 0) {  // drop the query itself if it sits in its own A range
+    for (i64 m = P.loA; m < P.hiA; ++m)
+      if ((i64)A.idS[m] == P.row) {
+        --c;
+        break;
+      }
+  }
+  for (i64 m = P.loA - 1; m >= P.t0 && c < need && A.pmax[m] > P.xs; --m) {
+    if (key_ce_adj(A.kS[m], L) > P.xs && !(A.self && (i64)A.idS[m] == P.row)) ++c;
+  }
+  return c;
+}
+
+// rows this query contributes: min(k, #overlaps + #left + #right)
+__global__ void __launch_bounds__(SC_THREADS)
+    closest_count_kernel(ClosestArgs A, ScanState ss_rows, ScanState ss_lone, uint4* __restrict__ qpos,
+                         u64* __restrict__ rows_out, u64* __restrict__ lone_out) {
+  __shared__ u64 s_tmp[8];
+  __shared__ u64 s_pre[2];
+  __shared__ u32 s_ticket;
+  const u32 tid = threadIdx.x;
+  const u64 tile = take_ticket(ss_rows.ticket, &s_ticket);
+  const i64 base = (i64)tile * SC_TILE + (i64)tid * SC_IPT;
+  u32 cnt[SC_IPT];
+  u64 sum = 0, nlone = 0;
+#pragma unroll 1
+  for (int j = 0; j < SC_IPT; ++j) {
+    const i64 t = base + j;
+    cnt[j] = 0;
+    if (t < A.n1) {
+      Probe P;
+      closest_probe(A, t, &P);
+      i64 nl = P.stop - P.t0, nr = P.t1 - P.begin;
+      if (nl > P.k_left) nl = P.k_left;
+      if (nr > P.k_right) nr = P.k_right;
+      i64 c = nl + nr;
+      if (c < A.k && !A.ignore_overlaps) c += count_overlaps_upto(A, P, (i64)A.k - c);
+      if (c > A.k) c = A.k;
+      cnt[j] = (u32)c;
+      qpos[t] = make_uint4((u32)P.loA, (u32)P.hiA, (u32)P.stop, (u32)P.begin);
+      sum += (u64)c;
+      nlone += c == 0;
+    }
+  }
+  u64 tot_rows, tot_lone;
+  u64 run = block_excl_sum_u64(sum, s_tmp, &tot_rows);
+  u64 lrun = block_excl_sum_u64(nlone, s_tmp, &tot_lone);
+  if (tid < 32) {
+    const u64 p0 = lookback_exclusive(ss_rows.status, tile, tot_rows);
+    const u64 p1 = lookback_exclusive(ss_lone.status, tile, tot_lone);
+    if (tid == 0) {
+      s_pre[0] = p0;
+      s_pre[1] = p1;
+    }
+  }
+  __syncthreads();
+  run += s_pre[0];
+  lrun += s_pre[1];
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    const i64 t = base + j;
+    if (t < A.n1) {
+      rows_out[t] = run;
+      lone_out[t] = lrun;
+    }
+    run += cnt[j];
+    lrun += (t < A.n1 && cnt[j] == 0);
+    if (t + 1 == A.n1) {
+      rows_out[A.n1] = run;
+      lone_out[A.n1] = lrun;
+    }
+  }
+}
+
+// per-group output bases; single thread (n_groups is tens)
+__global__ void closest_table_kernel(const u64* __restrict__ rows, const u64* __restrict__ lone,
+                                     const i64* __restrict__ qseg, i32 nb, i64* __restrict__ obase,
+                                     i64* __restrict__ ubase, i64* __restrict__ header) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  i64 base = 0, matched = 0;
+  for (i32 c = 0; c < nb; ++c) {
+    const i64 m = (i64)(rows[qseg[c + 1]] - rows[qseg[c]]);
+    const i64 u = (i64)(lone[qseg[c + 1]] - lone[qseg[c]]);
+    obase[c] = base - (i64)rows[qseg[c]];       // output row of a matched slice = rows[t] + obase[group]
+    ubase[c] = base + m - (i64)lone[qseg[c]];   // output row of an unmatched query = lone[t] + ubase[group]
+    base += m + u;
+    matched += m;
+  }
+  header[0] = base;
+  header[1] = matched;
+}
+
+// insert (d, j) into the slice sorted by (d, j), keeping at most cap entries
+__device__ __forceinline__ void slice_insert(i64* __restrict__ dist, i64* __restrict__ tgt, i32& len, i32 cap, i64 d,
+                                             i64 j) {
+  if (len == cap) {
+    if (cap == 0) return;
+    const i64 ld = dist[len - 1], lj = tgt[len - 1];
+    if (d > ld || (d == ld && j >= lj)) return;  // not better than the current worst (equal keys: duplicates
+                                                  // are indistinguishable, dropping the newcomer is the same)
+    --len;
+  }
+  i32 at = len;
+  while (at > 0) {
+    const i64 pd = dist[at - 1], pj = tgt[at - 1];
+    if (pd < d || (pd == d && pj <= j)) break;
+    dist[at] = pd;
+    tgt[at] = pj;
+    --at;
+  }
+  dist[at] = d;
+  tgt[at] = j;
+  ++len;
+}
+
+__global__ void __launch_bounds__(256)
+    closest_emit_kernel(ClosestArgs A, const uint4* __restrict__ qpos, const u64* __restrict__ rows,
+                        const u64* __restrict__ lone, const i64* __restrict__ obase, const i64* __restrict__ ubase,
+                        i64* __restrict__ ev1, i64* __restrict__ ev2) {
+  const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.n1) return;
+  const KeyLayout& L = A.L;
+  i64 row = t;
+  u32 rank = 0;
+  if (A.qkey) {
+    const u64 q = A.qkey[t];
+    row = (i64)(q & 0xffffffffull);
+    rank = (u32)(q >> 32);
+  }
+  const i32 cap = (i32)(rows[t + 1] - rows[t]);
+  if (cap == 0) {
+    const i64 out = (i64)lone[t] + ubase[rank];
+    ev1[out] = row;
+    ev2[out] = -1;
+    return;
+  }
+  const i64 out = (i64)rows[t] + obase[rank];
+  i64* dist = ev1 + out;  // the query's slice of ev1 holds distances until the very end
+  i64* tgt = ev2 + out;
+  i32 len = 0;
+  const uint4 qp = qpos[t];
+  const i64 loA = qp.x, hiA = qp.y, stop = qp.z, begin = qp.w;
+  const i64 t0 = A.seg[rank], t1 = A.seg[rank + 1];
+  const i64 a = A.s1[row], b = A.e1[row];
+  const u64 off = L.goff[rank];
+  const u64 xs = off + ((u64)a - L.cmin), xe = off + ((u64)b - L.cmin);
+  const bool fwd = A.along ? A.along[row] != 0 : true;
+  const i32 k_left = fwd ? A.k_up : A.k_dn, k_right = fwd ? A.k_dn : A.k_up;
+  if (!A.ignore_overlaps) {  // distance 0 (arrops.py:650-659)
+    for (i64 m = loA; m < hiA; ++m) {
+      const i64 j = A.idS[m];
+      if (!(A.self && j == row)) slice_insert(dist, tgt, len, cap, 0, j);
+    }
+    for (i64 m = loA - 1; m >= t0 && A.pmax[m] > xs; --m) {
+      const i64 j = A.idS[m];
+      if (key_ce_adj(A.kS[m], L) > xs && !(A.self && j == row)) slice_insert(dist, tgt, len, cap, 0, j);
+    }
+  }
+  {  // left neighbours: last k_left of the targets ending at or before the start (arrops.py:560-576, 724)
+    i64 from = stop - k_left;
+    if (from < t0) from = t0;
+    for (i64 m = stop - 1; m >= from; --m)
+      slice_insert(dist, tgt, len, cap, (i64)(xs - key_cs(A.kE[m], L)) + 1, (i64)A.idE[m]);
+  }
+  {  // right neighbours: first k_right of the targets starting at or after the end (arrops.py:578-596, 725)
+    i64 to = begin + k_right;
+    if (to > t1) to = t1;
+    for (i64 m = begin; m < to; ++m)
+      slice_insert(dist, tgt, len, cap, (i64)(key_cs(A.kS[m], L) - xe) + 1, (i64)A.idS[m]);
+  }
+  for (i32 x = 0; x < cap; ++x) dist[x] = row;  // len == cap by construction of the count
+}
+
+// ---------------------------------------------------------------- host side
+
+static int closest_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64 n1, const i32* grp2, const i64* s2,
+                              const i64* e2, i64 n2, i32 nb, i32 k, i32 flags, const u8* along, void* ws_ptr,
+                              size_t ws_bytes, ClosestPlan* plan, cudaStream_t st) {
+  if (n1 < 0 || n2 < 0 || nb < 1 || k < 1 || !plan) {
+    set_error("bf_closest_count: bad argument (n1=%lld n2=%lld n_groups=%d k=%d)", (long long)n1, (long long)n2, nb, k);
+    return BF_ERR_ARG;
+  }
+  if (n1 >= (1ll << 31) || n2 >= (1ll << 31)) {
+    set_error("bf_closest_count: more than 2^31-1 rows in one set");
+    return BF_ERR_RANGE;
+  }
+  if ((n1 > 0 && (!s1 || !e1)) || (n2 > 0 && (!s2 || !e2)) || (nb > 1 && ((n1 > 0 && !grp1) || (n2 > 0 && !grp2)))) {
+    set_error("bf_closest_count: null input pointer");
+    return BF_ERR_ARG;
+  }
+  Arena measure(nullptr);
+  ClosestWS w;
+  layout_closest(measure, n1, n2, nb, &w);
+  if (!ws_ptr || ws_bytes < measure.off) {
+    set_error("bf_closest_count: workspace %zu bytes < required %zu", ws_bytes, measure.off);
+    return BF_ERR_WORKSPACE;
+  }
+  Arena arena(ws_ptr);
+  layout_closest(arena, n1, n2, nb, &w);
+  plan->magic = 0;
+  plan->ready = 0;
+  plan->n_rows = plan->n_matched = 0;
+
+  // layout over both sets (point-adjusted extent so that end' fits), raw lengths in the keys
+  const RowSet sets[2] = {{grp1, s1, e1, n1}, {grp2, s2, e2, n2}};
+  KeyLayout L;
+  BF_TRY(measure_layout(sets, 2, nb, 1, w.layout, st, &L, "bf_closest_count"));
+  if (L.B > 62) {
+    set_error("bf_closest_count: coordinate span too wide (%d bits)", L.B);
+    return BF_ERR_RANGE;
+  }
+  SortResult rS, rE;
+  BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, KEY_NO_TIE_FIX, w.by_start, w.radix, st, &rS));
+  BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, KEY_NO_TIE_FIX | KEY_BY_END, w.by_end, w.radix, st, &rE));
+  BF_LAUNCH(PC_SEGMENT, 0, st,
+            segment_table_kernel<<<(unsigned)ceil_div(nb + 1, 128), 128, 0, st>>>(rS.keys, n2, L, nb, w.seg));
+  if (n2 > 0) {
+    const unsigned tiles = (unsigned)scan_tiles((u64)n2);
+    BF_TRY(reset_scan_state(w.ss_tmp, tiles, st));
+    BF_LAUNCH(PC_RUNMAX, 16 * n2, st, runmax_adj_kernel<<<tiles, SC_THREADS, 0, st>>>(rS.keys, (u64)n2, L, w.ss_tmp, w.pmax));
+  }
+  // queries in (group, row) order
+  const u64* qkey = nullptr;
+  if (nb > 1 && n1 > 0) {
+    BF_LAUNCH(PC_CLOSEST, 12 * n1, st, query_keys_kernel<<<(unsigned)ceil_div(n1, 256), 256, 0, st>>>(grp1, n1, w.qkeyA));
+    const RadixPlan qp = make_radix_plan(32, 32 + L.rank_bits);
+    BF_CUDA(cudaMemsetAsync(w.radix.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
+    BF_TRY(launch_radix_hist(w.qkeyA, (u64)n1, nullptr, qp, w.radix.hist, st, PC_CLOSEST));
+    SortResult qr;
+    BF_TRY(radix_sort_passes<false>(w.qkeyA, w.qkeyB, nullptr, nullptr, false, (u64)n1, nullptr, qp, w.radix, st, &qr,
+                                    PC_CLOSEST));
+    qkey = qr.keys;
+  }
+  BF_LAUNCH(PC_SEGMENT, 0, st,
+            query_segments_kernel<<<(unsigned)ceil_div(nb + 1, 128), 128, 0, st>>>(qkey, n1, nb, w.qseg));
+
+  ClosestArgs& A = plan->args;
+  A.grp1 = grp1;
+  A.s1 = s1;
+  A.e1 = e1;
+  A.along = along;
+  A.kS = rS.keys;
+  A.kE = rE.keys;
+  A.idS = rS.vals;
+  A.idE = rE.vals;
+  A.pmax = w.pmax;
+  A.seg = w.seg;
+  A.qseg = w.qseg;
+  A.qkey = qkey;
+  A.L = L;
+  A.n1 = n1;
+  A.n2 = n2;
+  A.k = k;
+  A.self = (flags & BF_CLOSEST_SELF) ? 1 : 0;
+  A.ignore_overlaps = (flags & BF_CLOSEST_IGNORE_OVERLAPS) ? 1 : 0;
+  A.k_up = (flags & BF_CLOSEST_IGNORE_UPSTREAM) ? 0 : k;
+  A.k_dn = (flags & BF_CLOSEST_IGNORE_DOWNSTREAM) ? 0 : k;
+
+  if (n1 > 0) {
+    const unsigned tiles = (unsigned)scan_tiles((u64)n1);
+    BF_TRY(reset_scan_state(w.ss_rows, tiles, st));
+    BF_TRY(reset_scan_state(w.ss_lone, tiles, st));
+    BF_LAUNCH(PC_CLOSEST, 52 * n1, st,
+              closest_count_kernel<<<tiles, SC_THREADS, 0, st>>>(A, w.ss_rows, w.ss_lone, w.qpos, w.rows, w.lone));
+  } else {
+    BF_CUDA(cudaMemsetAsync(w.rows, 0, sizeof(u64), st));
+    BF_CUDA(cudaMemsetAsync(w.lone, 0, sizeof(u64), st));
+  }
+  BF_LAUNCH(PC_TABLE, 0, st, closest_table_kernel<<<1, 1, 0, st>>>(w.rows, w.lone, w.qseg, nb, w.obase, w.ubase, w.header));
+  i64 header[2];
+  BF_CUDA(cudaMemcpyAsync(header, w.header, sizeof(header), cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaStreamSynchronize(st));
+  plan->n_rows = header[0];
+  plan->n_matched = header[1];
+  plan->magic = CLOSEST_MAGIC;
+  plan->ready = 1;
+  return BF_OK;
+}
+
+static int closest_emit_impl(const ClosestPlan* plan, void* ws_ptr, i64* ev1, i64* ev2, cudaStream_t st) {
+  if (!plan || plan->magic != CLOSEST_MAGIC || !plan->ready) {
+    set_error("bf_closest_emit: plan was not produced by a successful bf_closest_count");
+    return BF_ERR_STATE;
+  }
+  if (plan->n_rows == 0) return BF_OK;
+  if (!ev1 || !ev2) {
+    set_error("bf_closest_emit: null output pointer");
+    return BF_ERR_ARG;
+  }
+  const ClosestArgs& A = plan->args;
+  Arena arena(ws_ptr);
+  ClosestWS w;
+  layout_closest(arena, A.n1, A.n2, A.L.nb, &w);
+  BF_LAUNCH(PC_CLOSEST, 40 * A.n1 + 16 * plan->n_rows, st,
+            closest_emit_kernel<<<(unsigned)ceil_div(A.n1, 256), 256, 0, st>>>(A, w.qpos, w.rows, w.lone, w.obase, w.ubase,
+                                                                              ev1, ev2));
+  return BF_OK;
+}
+
+}  // namespace bf
+
+extern "C" {
+
+size_t bf_closest_workspace_bytes(int64_t n1, int64_t n2, int32_t n_groups) {
+  if (n1 < 0 || n2 < 0 || n_groups < 1) return 0;
+  bf::Arena a(nullptr);
+  bf::ClosestWS w;
+  bf::layout_closest(a, n1, n2, n_groups, &w);
+  return a.off;
+}
+int bf_closest_count(const int32_t* grp1, const int64_t* start1, const int64_t* end1, int64_t n1, const int32_t* grp2,
+                     const int64_t* start2, const int64_t* end2, int64_t n2, int32_t n_groups, int32_t k, int32_t flags,
+                     const uint8_t* along, void* ws, size_t ws_bytes, bf_plan* plan, void* stream, int64_t* n_rows_out,
+                     int64_t* n_matched_out) {
+  bf::ClosestPlan* p = (bf::ClosestPlan*)plan;
+  int rc = bf::closest_count_impl((const i32*)grp1, (const i64*)start1, (const i64*)end1, n1, (const i32*)grp2,
+                                  (const i64*)start2, (const i64*)end2, n2, n_groups, k, flags, (const u8*)along, ws,
+                                  ws_bytes, p, (cudaStream_t)stream);
+  if (rc == BF_OK) {
+    if (n_rows_out) *n_rows_out = p->n_rows;
+    if (n_matched_out) *n_matched_out = p->n_matched;
+  }
+  return rc;
+}
+int bf_closest_emit(const bf_plan* plan, void* ws, int64_t* events1_out, int64_t* events2_out, void* stream) {
+  return bf::closest_emit_impl((const bf::ClosestPlan*)plan, ws, (i64*)events1_out, (i64*)events2_out,
+                               (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -25,14 +25,14 @@ namespace bf {
 struct ClusterWS {
   SortBufs sb;
   RadixScratch radix;
-  Extent* extent;
+  LayoutScratch layout;
   ScanState ss_max, ss_sum;
   i64* header;  // [0] = number of clusters
 };
-static void layout_cluster(Arena& a, i64 n, ClusterWS* w) {
+static void layout_cluster(Arena& a, i64 n, i32 nb, ClusterWS* w) {
   take_sort_bufs(a, n, &w->sb);
   w->radix = take_radix_scratch(a, (u64)n);
-  w->extent = a.take<Extent>(1);
+  w->layout = take_layout_scratch(a, nb);
   w->ss_max = take_scan_state(a, (u64)scan_tiles((u64)n));
   w->ss_sum = take_scan_state(a, (u64)scan_tiles((u64)n));
   w->header = a.take<i64>(4);
@@ -57,14 +57,14 @@ struct ClusterPlan {
 static_assert(sizeof(ClusterPlan) <= sizeof(bf_plan), "bf_plan too small");
 constexpr u64 CLUSTER_MAGIC = 0x6266436c75737472ull;
 
-__device__ __forceinline__ bool starts_new_cluster(u64 key, u64 prev_key, u64 runmax_prev, const KeyLayout& L,
-                                                   u64 min_dist, int has_min_dist) {
-  const u32 rank = key_rank(key, L);
-  if (key_rank(prev_key, L) != rank) return true;  // first row of its group
-  const u64 gbase = L.rank_bits ? ((u64)rank << L.B) : 0ull;
-  const u64 s_off = key_cs(key, L) - gbase;
-  const u64 r_off = runmax_prev - gbase;  // same group as the previous row, so >= gbase
-  return has_min_dist ? (s_off > r_off + min_dist) : (s_off >= r_off);
+// group of the next row given the group of the previous one (rows are sorted, groups only grow)
+__device__ __forceinline__ u32 advance_rank(u32 rank, u64 cs, const KeyLayout& L) {
+  while ((i32)rank + 1 < L.nb && L.goff[rank + 1] <= cs) ++rank;
+  return rank;
+}
+// border test between two consecutive sorted rows of the SAME group: arrops.py:468 / 470
+__device__ __forceinline__ bool gap_opens_cluster(u64 cs, u64 runmax_prev, u64 min_dist, int has_min_dist) {
+  return has_min_dist ? (cs > runmax_prev + min_dist) : (cs >= runmax_prev);
 }
 
 __global__ void __launch_bounds__(SC_THREADS)
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(SC_THREADS)
   }
   __syncthreads();
 
-  // ---- running max of (group, end) over the sorted rows ----
+  // ---- running max of linear (group, end) over the sorted rows ----
   const u32 r0 = tid * SC_IPT;
   u64 rm[SC_IPT];  // inclusive running max inside the thread
   u64 tmax = 0;
@@ -105,15 +105,20 @@ __global__ void __launch_bounds__(SC_THREADS)
   __syncthreads();
   before = before > s_pre[0] ? before : s_pre[0];  // running max over every earlier row
 
-  // ---- borders ----
+  // ---- group of each row (binary search once per thread, then advance), borders ----
+  u32 rk[SC_IPT + 2];  // [0] row before the thread's first, [1..IPT] own rows, [IPT+1] row after
+  rk[0] = r0 < rows ? rank_of_cs(key_cs(s_k[r0], L), L) : 0u;
   u32 bmask = 0;
 #pragma unroll
   for (int j = 0; j < SC_IPT; ++j) {
     const u32 r = r0 + j;
+    rk[j + 1] = rk[j];
     if (r < rows) {
+      const u64 cs = key_cs(s_k[r + 1], L);
+      rk[j + 1] = advance_rank(rk[j], cs, L);
       const u64 prev_rm = j == 0 ? before : (rm[j - 1] > before ? rm[j - 1] : before);
       const bool first_row = base + r == 0;
-      if (first_row || starts_new_cluster(s_k[r + 1], s_k[r], prev_rm, L, min_dist, has_min_dist)) bmask |= 1u << j;
+      if (first_row || rk[j + 1] != rk[j] || gap_opens_cluster(cs, prev_rm, min_dist, has_min_dist)) bmask |= 1u << j;
     }
   }
   u64 tot;
@@ -135,8 +140,8 @@ __global__ void __launch_bounds__(SC_THREADS)
       const u64 key = s_k[r + 1];
       if (bmask & (1u << j)) ++seen;
       const u64 id = seen - 1;
-      const u32 rank = key_rank(key, L);
-      const u64 gbase = L.rank_bits ? ((u64)rank << L.B) : 0ull;
+      const u32 rank = rk[j + 1];
+      const u64 gbase = L.goff[rank];
       const u64 run = rm[j] > before ? rm[j] : before;  // running max including this row
       if (ids_out) ids_out[ids[k]] = (i64)id;
       if (bmask & (1u << j)) {
@@ -144,7 +149,11 @@ __global__ void __launch_bounds__(SC_THREADS)
         tab.cfirst[id] = (u32)k;
         tab.cgrp[id] = rank;
       }
-      const bool closes = (k + 1 == n) || starts_new_cluster(s_k[r + 2], key, run, L, min_dist, has_min_dist);
+      bool closes = k + 1 == n;
+      if (!closes) {
+        const u64 ncs = key_cs(s_k[r + 2], L);
+        closes = advance_rank(rank, ncs, L) != rank || gap_opens_cluster(ncs, run, min_dist, has_min_dist);
+      }
       if (closes) tab.cend[id] = (i64)(run - gbase + L.cmin);
     }
   }
@@ -174,20 +183,11 @@ __global__ void __launch_bounds__(256)
 // Sort + fused scan; leaves the cluster table in the workspace. No host sync.
 static int cluster_run(const i32* grp, const i64* s, const i64* e, i64 n, i32 nb, i64 min_dist, int has_min_dist,
                        ClusterWS& w, i64* ids_out, cudaStream_t st, ClusterTable* tab, KeyLayout* L_out) {
-  Extent ext;
-  BF_LAUNCH(PC_EXTENT, 0, st, extent_init_kernel<<<1, 1, 0, st>>>(w.extent));
-  BF_LAUNCH(PC_EXTENT, 20 * n, st,
-            extent_kernel<<<stream_grid((u64)n, 1024), 256, 0, st>>>(nb > 1 ? grp : nullptr, s, e, (u64)n, 0, w.extent));
-  BF_CUDA(cudaMemcpyAsync(&ext, w.extent, sizeof(Extent), cudaMemcpyDeviceToHost, st));
-  BF_CUDA(cudaStreamSynchronize(st));
-  if (nb > 1 && (ext.gmin < 0 || ext.gmax >= nb)) {
-    set_error("group code outside [0,%d): min %d max %d", nb, ext.gmin, ext.gmax);
-    return BF_ERR_GROUP;
-  }
+  const RowSet sets[1] = {{grp, s, e, n}};
   KeyLayout L;
-  BF_TRY(make_key_layout(ext, nb, &L));
-  if (L.rank_bits + L.B > 62) {
-    set_error("coordinate span too wide for the running-max scan (%d bits)", L.rank_bits + L.B);
+  BF_TRY(measure_layout(sets, 1, nb, 0, w.layout, st, &L, "bf_cluster"));
+  if (L.B > 62) {
+    set_error("coordinate span too wide for the running-max scan (%d bits)", L.B);
     return BF_ERR_RANGE;
   }
   SortResult r;
@@ -228,13 +228,13 @@ static int cluster_count_impl(const i32* grp, const i64* s, const i64* e, i64 n,
   }
   Arena measure(nullptr);
   ClusterWS w;
-  layout_cluster(measure, n, &w);
+  layout_cluster(measure, n, nb, &w);
   if (!ws_ptr || ws_bytes < measure.off) {
     set_error("bf_cluster_count: workspace %zu bytes < required %zu", ws_bytes, measure.off);
     return BF_ERR_WORKSPACE;
   }
   Arena arena(ws_ptr);
-  layout_cluster(arena, n, &w);
+  layout_cluster(arena, n, nb, &w);
   plan->magic = 0;
   plan->n = n;
   plan->nb = nb;
@@ -283,8 +283,8 @@ struct CoverageWS {
   i64* plen;  // [n2+1] exclusive prefix of merged lengths
   ScanState ss;
 };
-static void layout_coverage(Arena& a, i64 n2, CoverageWS* w) {
-  layout_cluster(a, n2, &w->cl);
+static void layout_coverage(Arena& a, i64 n2, i32 nb, CoverageWS* w) {
+  layout_cluster(a, n2, nb, &w->cl);
   w->plen = a.take<i64>(n2 + 1);
   w->ss = take_scan_state(a, (u64)scan_tiles((u64)n2));
 }
@@ -366,13 +366,13 @@ static int coverage_impl(const i32* grp1, const i64* s1, const i64* e1, i64 n1, 
   }
   Arena measure(nullptr);
   CoverageWS w;
-  layout_coverage(measure, n2, &w);
+  layout_coverage(measure, n2, nb, &w);
   if (!ws_ptr || ws_bytes < measure.off) {
     set_error("bf_coverage: workspace %zu bytes < required %zu", ws_bytes, measure.off);
     return BF_ERR_WORKSPACE;
   }
   Arena arena(ws_ptr);
-  layout_coverage(arena, n2, &w);
+  layout_coverage(arena, n2, nb, &w);
   ClusterTable tab;
   BF_TRY(cluster_run(grp2, s2, e2, n2, nb, 0, 1, w.cl, nullptr, st, &tab, nullptr));
   const unsigned tiles = (unsigned)scan_tiles((u64)n2);
@@ -396,7 +396,7 @@ struct ComplementWS {
   i64* total;                // [1]
 };
 static void layout_complement(Arena& a, i64 n, i32 nr, ComplementWS* w) {
-  layout_cluster(a, n, &w->cl);
+  layout_cluster(a, n, nr, &w->cl);
   w->r_lo = a.take<i64>(nr + 1);
   w->r_hi = a.take<i64>(nr + 1);
   w->r_off = a.take<i64>(nr + 1);
@@ -574,11 +574,10 @@ static int complement_emit_impl(const ComplementPlan* plan, void* ws_ptr, i32* r
 extern "C" {
 
 size_t bf_cluster_workspace_bytes(int64_t n, int32_t n_groups) {
-  (void)n_groups;
-  if (n < 0) return 0;
+  if (n < 0 || n_groups < 1) return 0;
   bf::Arena a(nullptr);
   bf::ClusterWS w;
-  bf::layout_cluster(a, n, &w);
+  bf::layout_cluster(a, n, n_groups, &w);
   return a.off;
 }
 int bf_cluster_count(const int32_t* grp, const int64_t* start, const int64_t* end, int64_t n, int32_t n_groups,
@@ -601,11 +600,10 @@ int bf_cluster_emit(const bf_plan* plan, void* ws, int32_t* cgrp_out, int64_t* c
 
 size_t bf_coverage_workspace_bytes(int64_t n1, int64_t n2, int32_t n_groups) {
   (void)n1;
-  (void)n_groups;
-  if (n2 < 0) return 0;
+  if (n2 < 0 || n_groups < 1) return 0;
   bf::Arena a(nullptr);
   bf::CoverageWS w;
-  bf::layout_coverage(a, n2, &w);
+  bf::layout_coverage(a, n2, n_groups, &w);
   return a.off;
 }
 int bf_coverage(const int32_t* grp1, const int64_t* start1, const int64_t* end1, int64_t n1, const int32_t* grp2,

@@ -1,22 +1,27 @@
 // Sort-key construction shared by overlap / cluster / closest / coverage.
 //
 // Every row becomes ONE 64-bit key
-//     key = ( group_rank << B | (start - cmin) ) << LB  |  (end' - start)
-// with B = bit width of the coordinate span of the whole call, LB = bit width
-// of the longest interval, and end' the point-adjusted end (end + (end ==
-// start), arrops.py:271-287) for overlap or the raw end for merge.
+//     key = ( goff[group] + (start - cmin) ) << LB  |  (end' - start)
+// where goff[g] is the exclusive prefix sum of the coordinate spans of the
+// groups before g (span_g = max coordinate seen in group g - cmin + 1, over all
+// sets of the call), i.e. the groups are laid end to end on one linear axis
+// -- for hg38 that axis is 3.09e9 long and fits 32 bits, one radix pass less
+// than a (group rank, start) bit field.  LB = bit width of the longest
+// interval; end' is the point-adjusted end (end + (end == start),
+// arrops.py:271-287) for overlap or the raw end for merge/closest.
 //
 // The reference orders each chromosome with np.lexsort([ends, starts])
 // (arrops.py:332-333, 459): by start, ties by end, ties by row.  Here ONE stable
-// LSD radix sort over the HIGH field only -- cs = (group, start), 5 + 28 = 33
-// bits for hg38 -- orders all chromosomes at once; rows that share (group,
-// start) (a few percent of real data) are then put in (end', row) order by a
-// fix-up that extracts just those rows, sorts them by the full key and writes
-// them back into the same slots (tie_fix in overlap.cu).  The length bits ride
-// along in the key, so after the sort the key alone yields
-//     cs(key) = key >> LB                 (group, start)
-//     ce(key) = cs(key) + (key & lmask)   (group, end')
+// LSD radix sort over the HIGH field only -- cs = linear (group, start) --
+// orders all chromosomes at once; rows that share (group, start) (a few
+// percent of real data) are then put in (end', row) order by a fix-up
+// (sorted_set.cuh).  The length bits ride along in the key, so after the sort
+// the key alone yields
+//     cs(key) = key >> LB                 linear (group, start)
+//     ce(key) = cs(key) + (key & lmask)   linear (group, end')
 // and the searches and running maxima never touch the input columns again.
+// ce of a row never reaches goff[g+1], so rows of different groups never
+// interact in any comparison of cs / ce values.
 #pragma once
 #include "common.cuh"
 #include "radix_sort.cuh"
@@ -24,56 +29,103 @@
 namespace bf {
 
 struct KeyLayout {
-  int B;          // bits of the coordinate field
+  int B;          // bits of the linear coordinate field
   int LB;         // bits of the length field
-  int rank_bits;  // bits of the group rank
-  int total_bits; // rank_bits + B + LB
+  int rank_bits;  // bits of a group rank (for sorting lists keyed by rank)
+  int total_bits; // B + LB
+  i32 nb;         // number of groups
   u64 cmin;       // coordinate origin (two's complement image of the int64 minimum)
   u64 lmask;      // (1 << LB) - 1
+  const u64* goff;  // device [nb+1]: linear offset of every group, goff[nb] = total span
 };
 
 __host__ __device__ __forceinline__ u64 key_cs(u64 k, const KeyLayout& L) { return k >> L.LB; }
 __host__ __device__ __forceinline__ u64 key_ce(u64 k, const KeyLayout& L) { return (k >> L.LB) + (k & L.lmask); }
-__host__ __device__ __forceinline__ u32 key_rank(u64 k, const KeyLayout& L) {
-  return L.rank_bits ? (u32)(k >> (L.LB + L.B)) : 0u;
+// group of a linear coordinate: the last g with goff[g] <= cs (empty groups have zero span)
+__device__ __forceinline__ u32 rank_of_cs(u64 cs, const KeyLayout& L) {
+  if (L.nb <= 1) return 0u;
+  i32 lo = 1, hi = L.nb;  // count g in [1, nb) with goff[g] <= cs
+  while (lo < hi) {
+    const i32 mid = (lo + hi) >> 1;
+    if (L.goff[mid] <= cs)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return (u32)(lo - 1);
 }
+__device__ __forceinline__ u32 key_rank(u64 k, const KeyLayout& L) { return rank_of_cs(key_cs(k, L), L); }
 
 struct Extent {  // device-side reduction target
   i64 cmin, cmax;
   i64 lmin, lmax;  // min / max of end' - start
   i32 gmin, gmax;
+  u64 total;       // sum of the group spans (written by layout_offsets_kernel)
 };
+struct LayoutScratch {
+  Extent* extent;
+  i64* gmax;  // [nb] max coordinate per group
+  u64* goff;  // [nb+1]
+};
+static inline LayoutScratch take_layout_scratch(Arena& a, i32 nb) {
+  LayoutScratch s;
+  s.extent = a.take<Extent>(1);
+  s.gmax = a.take<i64>(nb + 1);
+  s.goff = a.take<u64>(nb + 2);
+  return s;
+}
+constexpr i64 I64_MIN = (i64)0x8000000000000000ULL;
+constexpr i64 I64_MAX = 0x7fffffffffffffffLL;
+constexpr int EXTENT_SMEM_GROUPS = 2048;  // per-group maxima staged in shared memory up to this many groups
 
-static __global__ void extent_init_kernel(Extent* x) {
-  x->cmin = 0x7fffffffffffffffLL;
-  x->cmax = (i64)0x8000000000000000ULL;
-  x->lmin = 0x7fffffffffffffffLL;
-  x->lmax = (i64)0x8000000000000000ULL;
-  x->gmin = 0x7fffffff;
-  x->gmax = (i32)0x80000000;
+static __global__ void extent_init_kernel(Extent* x, i64* gmax, i32 nb) {
+  const i32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    x->cmin = I64_MAX;
+    x->cmax = I64_MIN;
+    x->lmin = I64_MAX;
+    x->lmax = I64_MIN;
+    x->gmin = 0x7fffffff;
+    x->gmax = (i32)0x80000000;
+    x->total = 0;
+  }
+  if (i < nb) gmax[i] = I64_MIN;
 }
 
-// min/max of coordinates (end' when point_adjust), of lengths and of group codes
+// min/max of coordinates (end' when point_adjust), of lengths and of group
+// codes, plus the max coordinate of every group.  The per-group table is read
+// with a plain load and only touched with an atomic when a row raises it, which
+// after the first few rows of a block almost never happens.
 static __global__ void __launch_bounds__(256) extent_kernel(const i32* __restrict__ grp, const i64* __restrict__ s,
-                                                     const i64* __restrict__ e, u64 n, int point_adjust,
-                                                     Extent* __restrict__ out) {
-  i64 lo = 0x7fffffffffffffffLL, hi = (i64)0x8000000000000000ULL;
-  i64 llo = 0x7fffffffffffffffLL, lhi = (i64)0x8000000000000000ULL;
+                                                            const i64* __restrict__ e, u64 n, int point_adjust, i32 nb,
+                                                            Extent* __restrict__ out, i64* __restrict__ gmax_out) {
+  extern __shared__ i64 s_gmax[];
+  const bool staged = nb <= EXTENT_SMEM_GROUPS;
+  volatile i64* table = staged ? s_gmax : gmax_out;
+  if (staged) {
+    for (i32 i = threadIdx.x; i < nb; i += blockDim.x) s_gmax[i] = I64_MIN;
+    __syncthreads();
+  }
+  i64 lo = I64_MAX, hi = I64_MIN;
+  i64 llo = I64_MAX, lhi = I64_MIN;
   i32 glo = 0x7fffffff, ghi = (i32)0x80000000;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
     i64 a = s[i], b = e[i];
     if (point_adjust && a == b) b += 1;
+    const i64 top = max(a, b);
     lo = min(lo, min(a, b));
-    hi = max(hi, max(a, b));
+    hi = max(hi, top);
     // length in wrapping arithmetic; a span that overflows int64 shows up as negative
     const i64 len = (i64)((u64)b - (u64)a);
     llo = min(llo, len);
     lhi = max(lhi, len);
+    i32 g = 0;
     if (grp) {
-      i32 g = grp[i];
+      g = grp[i];
       glo = min(glo, g);
       ghi = max(ghi, g);
     }
+    if ((u32)g < (u32)nb && table[g] < top) atomicMax((i64*)&table[g], top);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -94,30 +146,120 @@ static __global__ void __launch_bounds__(256) extent_kernel(const i32* __restric
       atomicMax(&out->gmax, ghi);
     }
   }
+  if (staged) {
+    __syncthreads();
+    for (i32 i = threadIdx.x; i < nb; i += blockDim.x)
+      if (s_gmax[i] != I64_MIN) atomicMax(&gmax_out[i], s_gmax[i]);
+  }
 }
 
-static inline int make_key_layout(const Extent& x, i32 n_groups, KeyLayout* L) {
+// goff[g] = sum of spans of the groups before g; one block, sequential over a
+// few dozen (at most a few thousand) groups per thread chunk.
+static __global__ void __launch_bounds__(1024) layout_offsets_kernel(Extent* __restrict__ x, const i64* __restrict__ gmax,
+                                                                     i32 nb, u64* __restrict__ goff) {
+  __shared__ u64 s_part[1024];
+  const u32 tid = threadIdx.x;
+  const u64 cmin = (u64)x->cmin;
+  const i32 per = (nb + 1023) / 1024;
+  const i32 lo = tid * per, hi = min(nb, lo + per);
+  auto span = [&](i32 g) -> u64 { return gmax[g] == I64_MIN ? 0ull : (u64)gmax[g] - cmin + 1ull; };
+  u64 acc = 0;
+  for (i32 g = lo; g < hi; ++g) acc += span(g);
+  s_part[tid] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    u64 run = 0;
+    for (int i = 0; i < 1024; ++i) {
+      const u64 v = s_part[i];
+      s_part[i] = run;
+      run += v;
+    }
+    goff[nb] = run;
+    x->total = run;
+  }
+  __syncthreads();
+  u64 run = s_part[tid];
+  for (i32 g = lo; g < hi; ++g) {
+    goff[g] = run;
+    run += span(g);
+  }
+}
+
+static inline int make_key_layout(const Extent& x, i32 n_groups, const u64* goff, KeyLayout* L) {
   if (x.lmin < 0) {
     set_error("interval with end < start (or a span beyond int64): not a valid bedframe interval");
     return BF_ERR_ARG;
   }
-  u64 span = (x.cmax >= x.cmin) ? (u64)x.cmax - (u64)x.cmin : 0;
-  L->B = bit_width(span);
+  // total span = sum over groups of (group max - cmin + 1); 0 when there are no rows
+  L->B = bit_width(x.total > 0 ? x.total - 1 : 0);
   if (L->B == 0) L->B = 1;
   L->LB = bit_width((u64)x.lmax);
   if (L->LB == 0) L->LB = 1;
   L->rank_bits = n_groups > 1 ? bit_width((u64)(n_groups - 1)) : 0;
-  L->total_bits = L->rank_bits + L->B + L->LB;
+  L->total_bits = L->B + L->LB;
+  L->nb = n_groups;
   L->cmin = (u64)x.cmin;
   L->lmask = (1ull << L->LB) - 1ull;
-  if (L->total_bits > 64 || L->LB > 62) {
-    set_error("coordinates need %d group + %d start + %d length bits = %d > 64-bit key "
+  L->goff = goff;
+  // a group span that wrapped (coordinates spread over more than 2^63) shows up as a huge total
+  if (L->total_bits > 64 || L->LB > 62 || x.total > (1ull << 63)) {
+    set_error("coordinates need %d position + %d length bits = %d > 64-bit key "
               "(wide-coordinate path not available for this call)",
-              L->rank_bits, L->B, L->LB, L->total_bits);
+              L->B, L->LB, L->total_bits);
     return BF_ERR_RANGE;
   }
   return BF_OK;
 }
+
+struct RowSet {  // one input interval set of a call
+  const i32* grp;
+  const i64* s;
+  const i64* e;
+  i64 n;
+};
+static inline unsigned stream_grid(u64 n, u64 per_block) {
+  u64 g = (n + per_block - 1) / per_block;
+  const u64 cap = 148ull * 8ull;  // a few resident blocks per SM, grid-stride beyond that
+  if (g > cap) g = cap;
+  if (g == 0) g = 1;
+  return (unsigned)g;
+}
+
+// Coordinate extent + per-group spans of all sets of a call -> key layout.
+// One small D2H copy and one stream synchronisation.
+static int measure_layout(const RowSet* sets, int n_sets, i32 nb, int point_adjust, const LayoutScratch& sc,
+                          cudaStream_t st, KeyLayout* L, const char* who) {
+  BF_LAUNCH(PC_EXTENT, 0, st, extent_init_kernel<<<(unsigned)ceil_div(nb + 1, 256), 256, 0, st>>>(sc.extent, sc.gmax, nb));
+  const size_t smem = nb <= EXTENT_SMEM_GROUPS ? (size_t)nb * sizeof(i64) : 0;
+  i64 total_rows = 0;
+  for (int k = 0; k < n_sets; ++k) {
+    const RowSet& r = sets[k];
+    total_rows += r.n;
+    if (r.n <= 0) continue;
+    BF_LAUNCH(PC_EXTENT, 20 * r.n, st,
+              extent_kernel<<<stream_grid((u64)r.n, 1024), 256, smem, st>>>(nb > 1 ? r.grp : nullptr, r.s, r.e, (u64)r.n,
+                                                                           point_adjust, nb, sc.extent, sc.gmax));
+  }
+  BF_LAUNCH(PC_EXTENT, 0, st, layout_offsets_kernel<<<1, 1024, 0, st>>>(sc.extent, sc.gmax, nb, sc.goff));
+  Extent ext;
+  BF_CUDA(cudaMemcpyAsync(&ext, sc.extent, sizeof(Extent), cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaStreamSynchronize(st));
+  if (total_rows == 0) {
+    ext.cmin = ext.cmax = 0;
+    ext.lmin = ext.lmax = 0;
+    ext.total = 0;
+  }
+  if (nb > 1 && total_rows > 0 && (ext.gmin < 0 || ext.gmax >= nb)) {
+    set_error("%s: group code outside [0,%d): min %d max %d", who, nb, ext.gmin, ext.gmax);
+    return BF_ERR_GROUP;
+  }
+  return make_key_layout(ext, nb, sc.goff, L);
+}
+
+// key modes (the `point_adjust` argument of pack_keys / sort_rows is a bit set)
+constexpr int KEY_POINT_ADJUST = 1;  // end' = end + (end == start)
+constexpr int KEY_BY_END = 2;        // high field = linear END coordinate (closest: left neighbours)
+constexpr int KEY_NO_TIE_FIX = 4;    // keep rows that share the high field in row order
 
 // Build keys and, in the same pass over the inputs, the histograms of every
 // radix digit place (so the sort never re-reads the keys to count them).
@@ -138,9 +280,10 @@ static __global__ void __launch_bounds__(HIST_THREADS) pack_keys_kernel(const i3
       u64 k = 0;
       if (ok) {
         i64 a = s[i], b = e[i];
-        if (point_adjust && a == b) b += 1;
-        u64 g = grp ? (u64)(u32)grp[i] : 0ull;
-        k = ((((L.rank_bits ? (g << L.B) : 0ull) | ((u64)a - L.cmin))) << L.LB) | ((u64)b - (u64)a);
+        if ((point_adjust & KEY_POINT_ADJUST) && a == b) b += 1;
+        const u64 off = grp ? L.goff[grp[i]] : 0ull;
+        const u64 at = (point_adjust & KEY_BY_END) ? (u64)b : (u64)a;  // field the rows are ordered by
+        k = ((off + (at - L.cmin)) << L.LB) | ((u64)b - (u64)a);
         keys[i] = k;
       }
       hist_add(wtab, rp, k, ok);
@@ -148,17 +291,6 @@ static __global__ void __launch_bounds__(HIST_THREADS) pack_keys_kernel(const i3
   }
   __syncthreads();
   hist_flush(hist_tabs, rp, ghist);
-}
-
-static int launch_pack_keys(const i32* grp, const i64* s, const i64* e, u64 n, const KeyLayout& L, int point_adjust,
-                            const RadixPlan& rp, u64* keys, u64* ghist, cudaStream_t st);
-
-static inline unsigned stream_grid(u64 n, u64 per_block) {
-  u64 g = (n + per_block - 1) / per_block;
-  const u64 cap = 148ull * 8ull;  // a few resident blocks per SM, grid-stride beyond that
-  if (g > cap) g = cap;
-  if (g == 0) g = 1;
-  return (unsigned)g;
 }
 
 static int launch_pack_keys(const i32* grp, const i64* s, const i64* e, u64 n, const KeyLayout& L, int point_adjust,

@@ -23,6 +23,7 @@
 namespace bf {
 
 constexpr i64 EMIT_CHUNK_BLOCKS = 1 << 16;  // emit blocks per partition chunk (fixed-size scratch)
+constexpr i64 SEARCH_MIN_ROWS = 256;        // == SR_MIN_ROWS (smallest block of rows of the search kernels)
 
 // ---------------------------------------------------------------- workspace
 struct SetWS {
@@ -32,6 +33,7 @@ struct SetWS {
   u64 *spine;    // [tiles]
   i64 *bracket;  // [tiles+1] window of the other set per block of sorted rows
   ScanState ss;  // = sb.ss
+  ScanState ss_search;  // sized for the smallest search tile (SR_MIN_ROWS rows)
   u64 *pmax;   // [n] running max of ce (only for outer joins on the other side)
   u8 *rowflag; // [n] 1 = row has no partner (row order)
   u64 *ukeyA, *ukeyB;  // [n] (rank << 32 | row) of unpaired rows
@@ -43,7 +45,7 @@ struct SetWS {
 struct OverlapWS {
   SetWS s[2];
   RadixScratch radix;
-  Extent* extent;
+  LayoutScratch layout;
   // per-group tables, n_groups+1 entries each
   i64 *cumA, *cumB;      // group boundaries in A-space / B-space (scan values)
   i64 *deltaA, *deltaB;  // output row = scan-space index + delta[group]
@@ -64,7 +66,8 @@ static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS*
     s.scan = s.sb.tmp8;
     s.ss = s.sb.ss;
     s.spine = a.take<u64>(scan_tiles(n[k]) + 1);
-    s.bracket = a.take<i64>(scan_tiles(n[k]) + 2);
+    s.bracket = a.take<i64>(ceil_div(n[k], SEARCH_MIN_ROWS) + 2);
+    s.ss_search = take_scan_state(a, (u64)ceil_div(n[k], SEARCH_MIN_ROWS));
     s.seg = a.take<i64>(nb + 1);
     s.ucnt = a.take<u64>(nb + 1);
     // set k needs flags / unpaired lists when it is on the kept side; the OTHER
@@ -81,7 +84,7 @@ static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS*
     }
   }
   w->radix = take_radix_scratch(a, (u64)(n1 > n2 ? n1 : n2));
-  w->extent = a.take<Extent>(1);
+  w->layout = take_layout_scratch(a, nb);
   w->cumA = a.take<i64>(nb + 1);
   w->cumB = a.take<i64>(nb + 1);
   w->deltaA = a.take<i64>(nb + 1);
@@ -160,22 +163,38 @@ __global__ void __launch_bounds__(SC_THREADS) running_max_ce_kernel(const u64* _
 //       lo = #(cs2 <  cs1), hi = #(cs2 <  ce1)   (closed: <=)     arrops.py:338-339
 //   B_SIDE == true : rows of set 2 against starts of set 1:
 //       lo = #(cs1 <= cs2), hi = #(cs1 <  ce2)   (closed: <=)     arrops.py:341-342
-// Both arrays are sorted, so the lo positions of a block of 2048 consecutive
-// rows form a window [bracket[b], bracket[b+1]] of the other set; a tiny
-// partition kernel finds all windows up front (one full binary search per
-// block boundary, all in parallel).  A block stages its window (+ slack for
-// the hi searches) in shared memory when it fits, searches lo inside the
-// window and gallops from lo to hi.
-constexpr int SR_STAGE = 4096;  // staged composite starts of the other set, 32-bit relative (16 KB)
-constexpr int SR_SLACK = 1024;
+// Both arrays are sorted, so the lo positions of a block of consecutive rows
+// form a window [bracket[b], bracket[b+1]] of the other set; a tiny partition
+// kernel finds all windows up front (one full binary search per block boundary,
+// all in parallel).  The rows per block (256 * IPT) are chosen on the host from
+// the size ratio of the two sets so that the expected window is a few thousand
+// entries.  A block stages its window (+ slack for the hi searches) in shared
+// memory as 32-bit offsets; every thread owns IPT consecutive rows: one
+// bit-step search for the first row's lo, a short linear advance for the next
+// rows (lo is monotone), and a branch-free bit-step search for every hi (same
+// trip count in every lane: no divergence).  Counts stay in registers for the
+// fused exclusive scan (tile scan + look-back over tile totals).
+constexpr int SR_STAGE = 6144;  // staged composite starts of the other set, 32-bit relative (24 KB)
+constexpr int SR_SLACK = 1536;
+constexpr int SR_MIN_ROWS = 256;  // smallest block of rows (IPT = 1)
+
+static inline i64 search_tiles(i64 n, int ipt) { return ceil_div(n, (i64)SC_THREADS * ipt); }
+// rows per thread for a side with n rows searching m entries
+static inline int pick_search_ipt(i64 n, i64 m) {
+  if (n <= 0) return 8;
+  const double ratio = (double)m / (double)n;
+  int ipt = 8;
+  while (ipt > 1 && (double)(SC_THREADS * ipt) * ratio > 3072.0) ipt >>= 1;
+  return ipt;
+}
 
 template <bool B_SIDE>
 __global__ void __launch_bounds__(256) search_partition_kernel(const u64* __restrict__ mine, i64 n,
                                                                const u64* __restrict__ other, i64 m, KeyLayout L,
-                                                               i64 ntiles, i64* __restrict__ bracket) {
+                                                               i64 tile_rows, i64 ntiles, i64* __restrict__ bracket) {
   const i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (b > ntiles) return;
-  i64 row = b * SC_TILE;
+  i64 row = b * tile_rows;
   if (row > n - 1) row = n - 1;
   const u64 x = key_cs(mine[row], L);
   bracket[b] = B_SIDE ? lower_bound_by(0, m, [&](i64 q) { return key_cs(other[q], L) <= x; })
@@ -191,27 +210,57 @@ __device__ __forceinline__ u32 rel32(u64 x, u64 base_cs) {
   return r > 0xffffffffull ? 0xffffffffu : (u32)r;
 }
 
-template <bool B_SIDE, bool FLAGS>
+// hi on the full keys, starting from position `from` (gallop, then bisect)
+__device__ __forceinline__ i64 gallop_hi(const u64* __restrict__ other, i64 from, i64 m, u64 xe, int closed,
+                                         const KeyLayout& L) {
+  i64 ga = from, gb = from, gstep = 1;
+  for (;;) {
+    gb = ga + gstep;
+    if (gb >= m) {
+      gb = m;
+      break;
+    }
+    const u64 v = key_cs(other[gb - 1], L);
+    if (!(closed ? (v <= xe) : (v < xe))) break;
+    ga = gb;
+    gstep <<= 1;
+  }
+  return closed ? lower_bound_by(ga, gb, [&](i64 q) { return key_cs(other[q], L) <= xe; })
+                : lower_bound_by(ga, gb, [&](i64 q) { return key_cs(other[q], L) < xe; });
+}
+
+template <bool B_SIDE, bool FLAGS, int IPT>
 __global__ void __launch_bounds__(SC_THREADS)
     search_count_kernel(const u64* __restrict__ mine, const u32* __restrict__ mine_id, i64 n,
                         const u64* __restrict__ other, i64 m, const u64* __restrict__ other_pmax,
                         const i64* __restrict__ bracket, KeyLayout L, int closed, u32* __restrict__ lo_out,
                         u64* __restrict__ scan_out, ScanState ss, u8* __restrict__ rowflag,
                         u64* __restrict__ ucnt) {
+  constexpr int TILE = SC_THREADS * IPT;
   __shared__ u32 s_rel[SR_STAGE];
-  __shared__ u64 s_mine[SC_TILE];
-  __shared__ u32 s_cnt[SC_TILE];
   __shared__ u64 s_tmp[8];
   __shared__ u64 s_prefix;
   __shared__ u32 s_ticket;
   const u32 tid = threadIdx.x;
   const i64 tile = take_ticket(ss.ticket, &s_ticket);
-  const i64 base = tile * SC_TILE;
-  // this block's own rows: all loads in flight at once, then served from shared memory
+  const i64 base = tile * TILE + (i64)tid * IPT;  // this thread's first row
+  // own rows: IPT consecutive keys per thread, 16-byte loads
+  u64 key[IPT];
+  if (base + IPT <= n) {
+    if (IPT >= 2) {
+      const ulonglong2* src = reinterpret_cast<const ulonglong2*>(mine + base);
 #pragma unroll
-  for (int j = 0; j < SC_IPT; ++j) {
-    const i64 p = base + (i64)j * SC_THREADS + tid;
-    s_mine[j * SC_THREADS + tid] = p < n ? mine[p] : 0ull;
+      for (int j = 0; j < IPT / 2; ++j) {
+        const ulonglong2 v = src[j];
+        key[2 * j] = v.x;
+        key[2 * j + 1] = v.y;
+      }
+    } else {
+      key[0] = mine[base];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) key[j] = base + j < n ? mine[base + j] : 0ull;
   }
   const i64 br_lo = bracket[tile], br_hi = bracket[tile + 1];
   const u32 W = (u32)(br_hi - br_lo);  // lo candidates: other[br_lo .. br_hi)
@@ -228,96 +277,67 @@ __global__ void __launch_bounds__(SC_THREADS)
     }
   }
   for (u32 i = tid; i < nst; i += SC_THREADS) s_rel[i] = (u32)(key_cs(other[br_lo + i], L) - base_cs + 1);
-  u32 pow2 = 1;
-  while (pow2 <= W) pow2 <<= 1;
-  pow2 >>= 1;  // largest power of two <= W (0 if W == 0)
+  u32 pow2w = 1, pow2n = 1;
+  while (pow2w <= W) pow2w <<= 1;
+  pow2w >>= 1;  // largest power of two <= W (0 if W == 0)
+  while (pow2n <= nst) pow2n <<= 1;
+  pow2n >>= 1;
   __syncthreads();
 
-#pragma unroll 1
-  for (int j = 0; j < SC_IPT; ++j) {
-    const i64 p = base + (i64)j * SC_THREADS + tid;
-    u32 cnt = 0;
+  u32 cnt[IPT];
+  u32 lo32[IPT];
+  u32 pos = 0;  // lo of the previous row, relative to br_lo (staged path)
+#pragma unroll
+  for (int j = 0; j < IPT; ++j) {
+    const i64 p = base + j;
+    cnt[j] = 0;
+    lo32[j] = 0;
     bool lonely = false;
     u32 rank = 0;
     if (p < n) {
-      const u64 k = s_mine[j * SC_THREADS + tid];
+      const u64 k = key[j];
       const u64 xs = key_cs(k, L), xe = key_ce(k, L);
       i64 lo, hi;
       if (nst > 0) {
         const u32 xs_rel = rel32(xs, base_cs), xe_rel = rel32(xe, base_cs);
-        // lo: branch-free bit-step lower bound over the W candidates
-        u32 pos = 0;
-        for (u32 step = pow2; step > 0; step >>= 1) {
-          const u32 nx = pos + step;
-          if (nx <= W) {
-            const u32 v = s_rel[nx - 1];
-            if (B_SIDE ? (v <= xs_rel) : (v < xs_rel)) pos = nx;
+        bool searched = false;
+        if (j > 0) {  // lo is monotone over consecutive rows: short linear advance
+          const u32 lim = pos + 6 < W ? pos + 6 : W;
+          while (pos < lim && (B_SIDE ? (s_rel[pos] <= xs_rel) : (s_rel[pos] < xs_rel))) ++pos;
+          searched = pos < lim || pos == W || !(B_SIDE ? (s_rel[pos] <= xs_rel) : (s_rel[pos] < xs_rel));
+        }
+        if (!searched) {  // bit-step lower bound over the W candidates
+          u32 q = 0;
+          for (u32 step = pow2w; step > 0; step >>= 1) {
+            const u32 nx = q + step;
+            if (nx <= W) {
+              const u32 v = s_rel[nx - 1];
+              if (B_SIDE ? (v <= xs_rel) : (v < xs_rel)) q = nx;
+            }
           }
+          pos = q;
         }
         lo = br_lo + pos;
-        // hi: gallop inside the staged window, then bisect
-        u32 a = pos, b = pos, step = 1;
-        bool open_end = false;
-        for (;;) {
-          b = a + step;
-          if (b > nst) {
-            b = nst;
-            open_end = true;
-            break;
+        // hi >= lo: bit-step from lo over the staged entries, same trip count in every lane
+        u32 h = pos;
+        for (u32 step = pow2n; step > 0; step >>= 1) {
+          const u32 nx = h + step;
+          if (nx <= nst) {
+            const u32 v = s_rel[nx - 1];
+            if (closed ? (v <= xe_rel) : (v < xe_rel)) h = nx;
           }
-          const u32 v = s_rel[b - 1];
-          if (!(closed ? (v <= xe_rel) : (v < xe_rel))) break;
-          a = b;
-          step <<= 1;
         }
-        while (a < b) {  // first index in [a, b) that is not below; b if none
-          const u32 mid = (a + b) >> 1;
-          const u32 v = s_rel[mid];
-          if (closed ? (v <= xe_rel) : (v < xe_rel))
-            a = mid + 1;
-          else
-            b = mid;
-        }
-        hi = br_lo + a;
-        if (open_end && a == nst && hi < m) {
-          // ran off the staged window: continue on the full keys
-          i64 ga = hi, gb = hi, gstep = 1;
-          for (;;) {
-            gb = ga + gstep;
-            if (gb >= m) {
-              gb = m;
-              break;
-            }
-            const u64 v = key_cs(other[gb - 1], L);
-            if (!(closed ? (v <= xe) : (v < xe))) break;
-            ga = gb;
-            gstep <<= 1;
-          }
-          hi = closed ? lower_bound_by(ga, gb, [&](i64 q) { return key_cs(other[q], L) <= xe; })
-                      : lower_bound_by(ga, gb, [&](i64 q) { return key_cs(other[q], L) < xe; });
-        }
+        hi = br_lo + h;
+        if (h == nst && hi < m) hi = gallop_hi(other, hi, m, xe, closed, L);  // ran off the staged window
       } else {
         lo = B_SIDE ? lower_bound_by(br_lo, br_hi, [&](i64 q) { return key_cs(other[q], L) <= xs; })
                     : lower_bound_by(br_lo, br_hi, [&](i64 q) { return key_cs(other[q], L) < xs; });
-        i64 ga = lo, gb = lo, gstep = 1;
-        for (;;) {
-          gb = ga + gstep;
-          if (gb >= m) {
-            gb = m;
-            break;
-          }
-          const u64 v = key_cs(other[gb - 1], L);
-          if (!(closed ? (v <= xe) : (v < xe))) break;
-          ga = gb;
-          gstep <<= 1;
-        }
-        hi = closed ? lower_bound_by(ga, gb, [&](i64 q) { return key_cs(other[q], L) <= xe; })
-                    : lower_bound_by(ga, gb, [&](i64 q) { return key_cs(other[q], L) < xe; });
+        hi = gallop_hi(other, lo, m, xe, closed, L);
       }
-      cnt = (u32)(hi - lo);
-      lo_out[p] = (u32)lo;
+      cnt[j] = (u32)(hi - lo);
+      lo32[j] = (u32)lo;
       if (FLAGS) {
-        bool partner = cnt > 0;
+        bool partner = cnt[j] > 0;
         if (!partner && lo > 0) {
           const u64 pm = other_pmax[lo - 1];
           partner = closed ? (pm >= xs) : (pm > xs);
@@ -327,7 +347,6 @@ __global__ void __launch_bounds__(SC_THREADS)
         if (lonely) rowflag[mine_id[p]] = 1;
       }
     }
-    s_cnt[j * SC_THREADS + tid] = cnt;
     if (FLAGS) {
       // per-group unpaired counters: rows are sorted by group, so a warp almost
       // always holds one group -> one atomic per warp; mixed warps fall back
@@ -344,15 +363,10 @@ __global__ void __launch_bounds__(SC_THREADS)
       }
     }
   }
-  __syncthreads();
   // ---- exclusive scan of the counts, fused: tile scan + look-back over tile totals ----
-  u32 c[SC_IPT];
   u64 mine_sum = 0;
 #pragma unroll
-  for (int j = 0; j < SC_IPT; ++j) {
-    c[j] = s_cnt[tid * SC_IPT + j];
-    mine_sum += c[j];
-  }
+  for (int j = 0; j < IPT; ++j) mine_sum += cnt[j];
   u64 tot;
   u64 run = block_excl_sum_u64(mine_sum, s_tmp, &tot);
   if (tid < 32) {
@@ -361,12 +375,32 @@ __global__ void __launch_bounds__(SC_THREADS)
   }
   __syncthreads();
   run += s_prefix;
+  if (base + IPT <= n && IPT >= 4) {
+    // 16-byte stores: IPT u64 offsets and IPT u32 positions per thread are contiguous
+    u64 sc[IPT];
 #pragma unroll
-  for (int j = 0; j < SC_IPT; ++j) {
-    const i64 p = base + (i64)tid * SC_IPT + j;
-    if (p < n) scan_out[p] = run;
-    run += c[j];
-    if (p + 1 == n) scan_out[n] = run;
+    for (int j = 0; j < IPT; ++j) {
+      sc[j] = run;
+      run += cnt[j];
+    }
+    ulonglong2* so = reinterpret_cast<ulonglong2*>(scan_out + base);
+#pragma unroll
+    for (int j = 0; j < IPT / 2; ++j) so[j] = make_ulonglong2(sc[2 * j], sc[2 * j + 1]);
+    uint4* lo4 = reinterpret_cast<uint4*>(lo_out + base);
+#pragma unroll
+    for (int j = 0; j < IPT / 4; ++j) lo4[j] = make_uint4(lo32[4 * j], lo32[4 * j + 1], lo32[4 * j + 2], lo32[4 * j + 3]);
+    if (base + IPT == n) scan_out[n] = run;
+  } else {
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+      const i64 p = base + j;
+      if (p < n) {
+        scan_out[p] = run;
+        lo_out[p] = lo32[j];
+      }
+      run += cnt[j];
+      if (p + 1 == n) scan_out[n] = run;
+    }
   }
 }
 
@@ -509,19 +543,30 @@ __global__ void __launch_bounds__(EM_THREADS)
   }
   __syncthreads();
   const i64 c_lo = s_br[2], c_hi = s_br[3];
-#pragma unroll 4
+  // all gathers of the thread's 8 outputs in flight before the first store
+  u32 own[EM_IPT], oth[EM_IPT];
+#pragma unroll
   for (int j = 0; j < EM_IPT; ++j) {
     const i32 x = j * EM_THREADS + (i32)tid;
-    if (x >= nout) break;
-    const u32 i = s_owner[x];
-    const i64 k = (i64)x - s_rel[i];
-    const i64 t = t0 + x;
-    const i64 c = (c_lo == c_hi) ? c_lo : group_of(t, c_lo, c_hi + 1);
-    const i64 row = t + delta[c];
-    const i64 own = s_id[i];
-    const i64 oth = other_id[(i64)s_lo[i] + k];
-    ev1[row] = B_SIDE ? oth : own;
-    ev2[row] = B_SIDE ? own : oth;
+    own[j] = 0;
+    oth[j] = 0;
+    if (x < nout) {
+      const u32 i = s_owner[x];
+      const i64 k = (i64)x - s_rel[i];
+      own[j] = s_id[i];
+      oth[j] = other_id[(i64)s_lo[i] + k];
+    }
+  }
+  const i64 d_lo = delta[c_lo];
+#pragma unroll
+  for (int j = 0; j < EM_IPT; ++j) {
+    const i32 x = j * EM_THREADS + (i32)tid;
+    if (x < nout) {
+      const i64 t = t0 + x;
+      const i64 row = t + ((c_lo == c_hi) ? d_lo : delta[group_of(t, c_lo, c_hi + 1)]);
+      ev1[row] = B_SIDE ? (i64)oth[j] : (i64)own[j];
+      ev2[row] = B_SIDE ? (i64)own[j] : (i64)oth[j];
+    }
   }
 }
 
@@ -576,6 +621,40 @@ __global__ void __launch_bounds__(256) emit_unpaired_kernel(const u64* __restric
   ev2[out] = SECOND ? row : -1;
 }
 
+template <bool B_SIDE, bool FLAGS, int IPT>
+static int launch_search_ipt(const SortResult& mine, i64 n, const SortResult& other, i64 m, const SetWS& sw,
+                             const u64* other_pmax, const KeyLayout& L, int closed, cudaStream_t st) {
+  const i64 tiles = search_tiles(n, IPT);
+  BF_TRY(reset_scan_state(sw.ss_search, (u64)tiles, st));
+  BF_LAUNCH(PC_SEARCH, 0, st, search_partition_kernel<B_SIDE><<<(unsigned)ceil_div(tiles + 1, 256), 256, 0, st>>>(
+      mine.keys, n, other.keys, m, L, (i64)SC_THREADS * IPT, tiles, sw.bracket));
+  BF_LAUNCH(PC_SEARCH, 20 * n, st, (search_count_kernel<B_SIDE, FLAGS, IPT><<<(unsigned)tiles, SC_THREADS, 0, st>>>(
+      mine.keys, mine.vals, n, other.keys, m, other_pmax, sw.bracket, L, closed, sw.lo, sw.scan, sw.ss_search,
+      FLAGS ? sw.rowflag : nullptr, FLAGS ? sw.ucnt : nullptr)));
+  return BF_OK;
+}
+template <bool B_SIDE>
+static int launch_search(const SortResult& mine, i64 n, const SortResult& other, i64 m, bool flags, const SetWS& sw,
+                         const u64* other_pmax, const KeyLayout& L, int closed, cudaStream_t st) {
+  if (n == 0) {
+    BF_CUDA(cudaMemsetAsync(sw.scan, 0, sizeof(u64), st));
+    return BF_OK;
+  }
+  const int ipt = pick_search_ipt(n, m);
+#define BF_SEARCH_CASE(I)                                                                                          \
+  case I:                                                                                                          \
+    return flags ? launch_search_ipt<B_SIDE, true, I>(mine, n, other, m, sw, other_pmax, L, closed, st)            \
+                 : launch_search_ipt<B_SIDE, false, I>(mine, n, other, m, sw, other_pmax, L, closed, st);
+  switch (ipt) {
+    BF_SEARCH_CASE(8)
+    BF_SEARCH_CASE(4)
+    BF_SEARCH_CASE(2)
+    default:
+      BF_SEARCH_CASE(1)
+  }
+#undef BF_SEARCH_CASE
+}
+
 static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64 n1, const i32* grp2,
                               const i64* s2, const i64* e2, i64 n2, i32 nb, i32 how, i32 closed,
                               void* ws_ptr, size_t ws_bytes, OverlapPlan* plan, cudaStream_t st) {
@@ -611,27 +690,10 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   plan->closed = closed;
   plan->ready = 0;
 
-  // ---- coordinate extent + group code check (one small D2H) ----
-  Extent ext;
-  BF_LAUNCH(PC_EXTENT, 0, st, extent_init_kernel<<<1, 1, 0, st>>>(w.extent));
-  if (n1 > 0) {
-    BF_LAUNCH(PC_EXTENT, 0, st, extent_kernel<<<stream_grid((u64)n1, 1024), 256, 0, st>>>(nb > 1 ? grp1 : nullptr, s1, e1, (u64)n1, 1, w.extent));
-  }
-  if (n2 > 0) {
-    BF_LAUNCH(PC_EXTENT, 0, st, extent_kernel<<<stream_grid((u64)n2, 1024), 256, 0, st>>>(nb > 1 ? grp2 : nullptr, s2, e2, (u64)n2, 1, w.extent));
-  }
-  BF_CUDA(cudaMemcpyAsync(&ext, w.extent, sizeof(Extent), cudaMemcpyDeviceToHost, st));
-  BF_CUDA(cudaStreamSynchronize(st));
-  if (n1 + n2 == 0) {
-    ext.cmin = ext.cmax = 0;
-    ext.lmin = ext.lmax = 0;
-  }
-  if (nb > 1 && n1 + n2 > 0 && (ext.gmin < 0 || ext.gmax >= nb)) {
-    set_error("bf_overlap_count: group code outside [0,%d): min %d max %d", nb, ext.gmin, ext.gmax);
-    return BF_ERR_GROUP;
-  }
+  // ---- coordinate extent, group code check, key layout (one small D2H) ----
+  const RowSet sets[2] = {{grp1, s1, e1, n1}, {grp2, s2, e2, n2}};
   KeyLayout L;
-  BF_TRY(make_key_layout(ext, nb, &L));
+  BF_TRY(measure_layout(sets, 2, nb, 1, w.layout, st, &L, "bf_overlap_count"));
   plan->L = L;
   // ---- sort both sets ----
   SortResult r1, r2;
@@ -669,40 +731,8 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
     if (n2 > 0) BF_CUDA(cudaMemsetAsync(w.s[1].rowflag, 0, (size_t)n2, st));
   }
   // algorithmic bytes: key read (8) + lo (4) + scan offset (8) written per row
-  if (n1 > 0) {
-    const unsigned tiles = (unsigned)scan_tiles((u64)n1);
-    BF_TRY(reset_scan_state(w.s[0].ss, tiles, st));
-    BF_LAUNCH(PC_SEARCH, 0, st, search_partition_kernel<false><<<(unsigned)ceil_div(tiles + 1, 256), 256, 0, st>>>(
-        r1.keys, n1, r2.keys, n2, L, tiles, w.s[0].bracket));
-    if (need1) {
-      BF_LAUNCH(PC_SEARCH, 20 * n1, st, search_count_kernel<false, true><<<tiles, SC_THREADS, 0, st>>>(
-          r1.keys, r1.vals, n1, r2.keys, n2, w.s[1].pmax, w.s[0].bracket, L, closed, w.s[0].lo, w.s[0].scan,
-          w.s[0].ss, w.s[0].rowflag, w.s[0].ucnt));
-    } else {
-      BF_LAUNCH(PC_SEARCH, 20 * n1, st, search_count_kernel<false, false><<<tiles, SC_THREADS, 0, st>>>(
-          r1.keys, r1.vals, n1, r2.keys, n2, nullptr, w.s[0].bracket, L, closed, w.s[0].lo, w.s[0].scan,
-          w.s[0].ss, nullptr, nullptr));
-    }
-  } else {
-    BF_CUDA(cudaMemsetAsync(w.s[0].scan, 0, sizeof(u64), st));
-  }
-  if (n2 > 0) {
-    const unsigned tiles = (unsigned)scan_tiles((u64)n2);
-    BF_TRY(reset_scan_state(w.s[1].ss, tiles, st));
-    BF_LAUNCH(PC_SEARCH, 0, st, search_partition_kernel<true><<<(unsigned)ceil_div(tiles + 1, 256), 256, 0, st>>>(
-        r2.keys, n2, r1.keys, n1, L, tiles, w.s[1].bracket));
-    if (need2) {
-      BF_LAUNCH(PC_SEARCH, 20 * n2, st, search_count_kernel<true, true><<<tiles, SC_THREADS, 0, st>>>(
-          r2.keys, r2.vals, n2, r1.keys, n1, w.s[0].pmax, w.s[1].bracket, L, closed, w.s[1].lo, w.s[1].scan,
-          w.s[1].ss, w.s[1].rowflag, w.s[1].ucnt));
-    } else {
-      BF_LAUNCH(PC_SEARCH, 20 * n2, st, search_count_kernel<true, false><<<tiles, SC_THREADS, 0, st>>>(
-          r2.keys, r2.vals, n2, r1.keys, n1, nullptr, w.s[1].bracket, L, closed, w.s[1].lo, w.s[1].scan,
-          w.s[1].ss, nullptr, nullptr));
-    }
-  } else {
-    BF_CUDA(cudaMemsetAsync(w.s[1].scan, 0, sizeof(u64), st));
-  }
+  BF_TRY((launch_search<false>(r1, n1, r2, n2, need1, w.s[0], w.s[1].pmax, L, closed, st)));
+  BF_TRY((launch_search<true>(r2, n2, r1, n1, need2, w.s[1], w.s[0].pmax, L, closed, st)));
 
   // ---- unpaired lists: compact in row order, partition by group ----
   BF_CUDA(cudaMemsetAsync(w.nU, 0, 2 * sizeof(u64), st));

@@ -24,6 +24,7 @@ constexpr int RS_IPT = 16;
 constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 keys per tile
 constexpr int RS_BINS = 256;
 constexpr int RS_MAX_PASSES = 8;
+constexpr int RS_LOOK = 4;  // look-back predecessors fetched per round trip
 constexpr u64 RS_PERSISTENT_BLOCKS = 148 * 3;  // one wave of resident blocks, each loops over tiles
 
 struct RadixPlan {
@@ -261,21 +262,39 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
       if (d == dmask) cnt_valid -= (u64)(RS_TILE - valid);
 
       // ---- decoupled look-back: digits before this tile ----
+      // RS_LOOK predecessors are fetched per round trip (independent loads), so the
+      // chain of "wait for the tile before me" that forms when all persistent
+      // blocks start together resolves RS_LOOK times faster than one load per step.
       u64* mine = status + tile * RS_BINS + d;
       u64 excl = 0;
       if (tile == 0) {
         st_relaxed_u64(mine, tag | RS_FLAG_INC | cnt_valid);
       } else {
         st_relaxed_u64(mine, tag | RS_FLAG_AGG | cnt_valid);
-        const u64* prev = mine - RS_BINS;
-        while (true) {
-          u64 w = ld_relaxed_u64(prev);
-          if ((w & ~(RS_VAL_MASK | (3ull << 56))) != tag) continue;  // stale word of an earlier pass
-          u64 flag = w & (3ull << 56);
-          if (flag == 0) continue;
-          excl += w & RS_VAL_MASK;
-          if (flag == RS_FLAG_INC) break;
-          prev -= RS_BINS;
+        i64 pt = (i64)tile - 1;  // nearest predecessor not yet accounted for
+        for (;;) {
+          u64 w[RS_LOOK];
+#pragma unroll
+          for (int b = 0; b < RS_LOOK; ++b)
+            w[b] = pt - b >= 0 ? ld_relaxed_u64(status + (u64)(pt - b) * RS_BINS + d) : (tag | RS_FLAG_INC);
+          bool finished = false, stalled = false;
+          int consumed = 0;
+#pragma unroll
+          for (int b = 0; b < RS_LOOK; ++b) {
+            if (!finished && !stalled) {
+              const u64 flag = w[b] & (3ull << 56);
+              // a word of an earlier pass (other tag) or an unpublished one: poll again from here
+              if ((w[b] & ~(RS_VAL_MASK | (3ull << 56))) != tag || flag == 0) {
+                stalled = true;
+              } else {
+                excl += w[b] & RS_VAL_MASK;
+                ++consumed;
+                finished = flag == RS_FLAG_INC;
+              }
+            }
+          }
+          if (finished) break;
+          pt -= consumed;
         }
         st_relaxed_u64(mine, tag | RS_FLAG_INC | (excl + cnt_valid));
       }

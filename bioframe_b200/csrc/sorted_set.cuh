@@ -118,6 +118,7 @@ static int sort_rows(const i32* grp, const i64* s, const i64* e, i64 n, const Ke
   BF_CUDA(cudaMemsetAsync(sc.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
   BF_TRY(launch_pack_keys(grp, s, e, (u64)n, L, point_adjust, rp, ws.keyA, sc.hist, st));
   BF_TRY(radix_sort_passes<true>(ws.keyA, ws.keyB, ws.idA, ws.idB, true, (u64)n, nullptr, rp, sc, st, res));
+  if (point_adjust & KEY_NO_TIE_FIX) return BF_OK;
   // tie fix-up on the subset of rows that share (group, start); scratch = the
   // sort's spare buffers and the per-row temporaries
   const unsigned tiles = (unsigned)scan_tiles((u64)n);
@@ -148,7 +149,8 @@ static __global__ void segment_table_kernel(const u64* __restrict__ keys, i64 n,
     seg[c] = n;
     return;
   }
-  seg[c] = lower_bound_by(0, n, [&](i64 m) { return key_rank(keys[m], L) < (u32)c; });
+  const u64 first_cs = L.goff[c];  // rows of groups >= c start at this linear coordinate
+  seg[c] = lower_bound_by(0, n, [&](i64 m) { return key_cs(keys[m], L) < first_cs; });
 }
 
 }  // namespace bf

@@ -175,3 +175,44 @@ def complement(region, start, end, bounds_lo, bounds_hi, device=None):
         rc = L.bf_complement_emit(C.byref(plan), _ptr(ws), _ptr(reg), _ptr(gs), _ptr(ge), stream)
         _lib.check(rc, "bf_complement_emit")
     return reg, gs, ge
+
+
+def closest_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, k=1, ignore_overlaps=False,
+                    ignore_upstream=False, ignore_downstream=False, along=None, self_closest=False, device=None):
+    """All groups of `_closest_intidxs` (ops.py:919-1040) in one pass.
+    `self_closest`: set 2 is set 1 (grp2/start2/end2 are ignored).  `along`: bool per
+    query, False = "-" strand.  Returns (events1, events2, n_matched_rows) on device."""
+    _require_cuda()
+    if k < 1:
+        raise ValueError("k>=1 required")
+    L = _lib.lib()
+    device = torch.device(device if device is not None else "cuda")
+    s1, e1 = _as(start1, torch.int64, device), _as(end1, torch.int64, device)
+    g1 = _as(grp1, torch.int32, device) if n_groups > 1 else None
+    if self_closest:
+        s2, e2, g2 = s1, e1, g1
+    else:
+        s2, e2 = _as(start2, torch.int64, device), _as(end2, torch.int64, device)
+        g2 = _as(grp2, torch.int32, device) if n_groups > 1 else None
+    al = _as(along, torch.uint8, device) if along is not None else None
+    n1, n2 = int(s1.numel()), int(s2.numel())
+    flags = (
+        (_lib.CLOSEST_IGNORE_OVERLAPS if ignore_overlaps else 0)
+        | (_lib.CLOSEST_IGNORE_UPSTREAM if ignore_upstream else 0)
+        | (_lib.CLOSEST_IGNORE_DOWNSTREAM if ignore_downstream else 0)
+        | (_lib.CLOSEST_SELF if self_closest else 0)
+    )
+    with torch.cuda.device(device):
+        ws = Workspace.get(device, max(L.bf_closest_workspace_bytes(n1, n2, n_groups), 256))
+        plan = _lib.Plan()
+        n_rows, n_matched = C.c_int64(0), C.c_int64(0)
+        stream = _stream_ptr(device)
+        rc = L.bf_closest_count(_ptr(g1), _ptr(s1), _ptr(e1), n1, _ptr(g2), _ptr(s2), _ptr(e2), n2, n_groups, int(k),
+                                flags, _ptr(al), _ptr(ws), ws.numel(), C.byref(plan), stream, C.byref(n_rows),
+                                C.byref(n_matched))
+        _lib.check(rc, "bf_closest_count")
+        ev1 = torch.empty(n_rows.value, dtype=torch.int64, device=device)
+        ev2 = torch.empty(n_rows.value, dtype=torch.int64, device=device)
+        rc = L.bf_closest_emit(C.byref(plan), _ptr(ws), _ptr(ev1), _ptr(ev2), stream)
+        _lib.check(rc, "bf_closest_emit")
+    return ev1, ev2, n_matched.value

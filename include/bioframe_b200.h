@@ -86,6 +86,35 @@ int bf_overlap_count(const int32_t* grp1, const int64_t* start1, const int64_t* 
 int bf_overlap_emit(const bf_plan* plan, void* ws, int64_t* events1_out, int64_t* events2_out,
                     void* stream);
 
+/* ---- closest: replaces ops._closest_intidxs (ops.py:919-1040), i.e. the
+ * per-group loop around arrops.closest_intervals (arrops.py:601-754) and
+ * arrops._closest_intervals_nooverlap (arrops.py:506-598), plus the
+ * np.setdiff1d of unmatched queries (ops.py:1027-1031).  Output rows, per group
+ * in code order: for every query of the group in ascending row order its up to
+ * k targets sorted by (distance, target row) -- overlaps have distance 0,
+ * non-overlapping neighbours distance gap + 1 (arrops.py:724-730) -- then
+ * (query, -1) for the group's queries without any candidate.
+ *   flags: BF_CLOSEST_* bits; SELF = set 2 is set 1 (pass the same pointers):
+ *          a query never reports itself as an overlap (arrops.py:652-657).
+ *   along: device uint8[n1] or NULL; 0 marks a query on the "-" strand
+ *          (direction_col, ops.py:1009-1012): upstream/downstream swap sides.
+ * Ties among targets with equal end (left) / equal start (right) are resolved
+ * in row order (stable); the reference uses an unstable argsort there
+ * (arrops.py:562,580), so only tie-free inputs have a defined reference answer.
+ * tie_breaking_col is not supported (raises in the reference, arrops.py:740). */
+#define BF_CLOSEST_IGNORE_OVERLAPS 1
+#define BF_CLOSEST_IGNORE_UPSTREAM 2
+#define BF_CLOSEST_IGNORE_DOWNSTREAM 4
+#define BF_CLOSEST_SELF 8
+size_t bf_closest_workspace_bytes(int64_t n1, int64_t n2, int32_t n_groups);
+int bf_closest_count(const int32_t* grp1, const int64_t* start1, const int64_t* end1, int64_t n1,
+                     const int32_t* grp2, const int64_t* start2, const int64_t* end2, int64_t n2,
+                     int32_t n_groups, int32_t k, int32_t flags, const uint8_t* along, void* ws,
+                     size_t ws_bytes, bf_plan* plan, void* stream, int64_t* n_rows_out,
+                     int64_t* n_matched_out);
+int bf_closest_emit(const bf_plan* plan, void* ws, int64_t* events1_out, int64_t* events2_out,
+                    void* stream);
+
 /* ---- cluster / merge: replaces the group loops of ops.cluster (ops.py:637-674)
  * and ops.merge (ops.py:776-810) around arrops.merge_intervals
  * (arrops.py:415-479).  Groups are visited in code order (= sorted key order,

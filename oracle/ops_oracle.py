@@ -279,3 +279,33 @@ def coverage_coded(g1, s1, e1, g2, s2, e2, n_groups):
     out = np.zeros(len(s1), dtype=np.int64)
     np.add.at(out, i, ov)
     return out
+
+
+def closest_intidxs_coded(g1, s1, e1, g2, s2, e2, n_groups, k=1, ignore_overlaps=False, ignore_upstream=False,
+                          ignore_downstream=False, along=None, self_closest=False):
+    """`closest_intidxs` on group-coded arrays, groups visited in code order --
+    the contract of the C ABI's bf_closest_* (ops.py:997-1035)."""
+    s1, e1 = np.asarray(s1, dtype=np.int64), np.asarray(e1, dtype=np.int64)
+    if self_closest:
+        g2, s2, e2 = g1, s1, e1
+    s2, e2 = np.asarray(s2, dtype=np.int64), np.asarray(e2, dtype=np.int64)
+    rows1 = _rows_by_code(g1, len(s1), n_groups)
+    rows2 = _rows_by_code(g2, len(s2), n_groups)
+    out1, out2 = [], []
+    for r1, r2 in zip(rows1, rows2):
+        if len(r1) and len(r2):
+            al = np.asarray(along, dtype=bool)[r1] if along is not None else None
+            i, j = ao.closest_intervals(
+                s1[r1], e1[r1], None if self_closest else s2[r2], None if self_closest else e2[r2], k=k,
+                ignore_overlaps=ignore_overlaps, ignore_upstream=ignore_upstream,
+                ignore_downstream=ignore_downstream, along=al,
+            )
+            lone = np.setdiff1d(np.arange(len(r1)), i)
+            out1 += [r1[i], r1[lone]]
+            out2 += [r2[j], np.full(len(lone), -1)]
+        elif len(r1):
+            out1.append(r1)
+            out2.append(np.full(len(r1), -1))
+    if not out1:
+        return np.empty(0, np.int64), np.empty(0, np.int64)
+    return np.concatenate(out1).astype(np.int64), np.concatenate(out2).astype(np.int64)
