@@ -270,7 +270,7 @@ static __global__ void __launch_bounds__(HIST_THREADS) pack_keys_kernel(const i3
   extern __shared__ u32 hist_tabs[];
   hist_clear(hist_tabs, rp);
   __syncthreads();
-  u32* wtab = hist_tabs + (threadIdx.x >> 5) * rp.passes * RS_BINS;
+  u32* wtab = hist_tabs;
   const u64 per_block = (u64)HIST_THREADS * 8ull;
   for (u64 base = (u64)blockIdx.x * per_block; base < n; base += (u64)gridDim.x * per_block) {
 #pragma unroll

@@ -29,11 +29,12 @@ constexpr i64 SEARCH_MIN_ROWS = 256;        // == SR_MIN_ROWS (smallest block of
 struct SetWS {
   SortBufs sb;   // sort double buffers + per-row temporaries + look-back state
   u32 *lo;       // = sb.tmp4a after the sort: first partner position per sorted row
-  u64 *scan;     // = sb.tmp8  after the sort: [n+1] exclusive output offsets
+  u32 *loc;      // = sb.tmp4b after the sort: [n] exclusive output offset inside the row's search tile
+  u64 *tilepre;  // [search tiles + 1] exclusive output offset of every search tile; last = total
+  int shift;     // log2(rows per search tile) of this side (host copy, set by launch_search)
   u64 *spine;    // [tiles]
   i64 *bracket;  // [tiles+1] window of the other set per block of sorted rows
   ScanState ss;  // = sb.ss
-  ScanState ss_search;  // sized for the smallest search tile (SR_MIN_ROWS rows)
   u64 *pmax;   // [n] running max of ce (only for outer joins on the other side)
   u8 *rowflag; // [n] 1 = row has no partner (row order)
   u64 *ukeyA, *ukeyB;  // [n] (rank << 32 | row) of unpaired rows
@@ -63,11 +64,12 @@ static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS*
     SetWS& s = w->s[k];
     take_sort_bufs(a, n[k], &s.sb);
     s.lo = s.sb.tmp4a;
-    s.scan = s.sb.tmp8;
+    s.loc = s.sb.tmp4b;
+    s.tilepre = a.take<u64>(ceil_div(n[k], SEARCH_MIN_ROWS) + 2);
+    s.shift = 0;
     s.ss = s.sb.ss;
     s.spine = a.take<u64>(scan_tiles(n[k]) + 1);
     s.bracket = a.take<i64>(ceil_div(n[k], SEARCH_MIN_ROWS) + 2);
-    s.ss_search = take_scan_state(a, (u64)ceil_div(n[k], SEARCH_MIN_ROWS));
     s.seg = a.take<i64>(nb + 1);
     s.ucnt = a.take<u64>(nb + 1);
     // set k needs flags / unpaired lists when it is on the kept side; the OTHER
@@ -106,6 +108,7 @@ struct OverlapPlan {  // lives in the caller's bf_plan
   KeyLayout L;
   i64 n_rows, n_pairs, nU1, nU2;
   i64 totA, totB;
+  i32 shift1, shift2;  // log2(rows per search tile) of the two sides
   // sorted results (pointers into the workspace)
   u64 *key1, *key2;
   u32 *id1, *id2;
@@ -157,6 +160,21 @@ __global__ void __launch_bounds__(SC_THREADS) running_max_ce_kernel(const u64* _
     if (i < n) pmax[i] = run;
   }
 }
+
+// Output offsets of a side, two levels: offset of the row's search tile (u64,
+// scanned by one small kernel) + offset of the row inside its tile (u32, block
+// scan in the search kernel).  No device-wide scan ever touches the rows again,
+// and no block waits on another (a fused look-back made every tile wait for
+// the slowest of its predecessors: 15-20 % of the search time, profiles/).
+struct ScanView {
+  const u64* tilepre;
+  const u32* loc;
+  i64 n;
+  int shift;
+  __device__ __forceinline__ i64 at(i64 p) const {
+    return p >= n ? (i64)tilepre[(n + (1ll << shift) - 1) >> shift] : (i64)(tilepre[p >> shift] + loc[p]);
+  }
+};
 
 // Search + count for one side.
 //   B_SIDE == false: rows of set 1 against starts of set 2:
@@ -234,15 +252,13 @@ __global__ void __launch_bounds__(SC_THREADS)
     search_count_kernel(const u64* __restrict__ mine, const u32* __restrict__ mine_id, i64 n,
                         const u64* __restrict__ other, i64 m, const u64* __restrict__ other_pmax,
                         const i64* __restrict__ bracket, KeyLayout L, int closed, u32* __restrict__ lo_out,
-                        u64* __restrict__ scan_out, ScanState ss, u8* __restrict__ rowflag,
-                        u64* __restrict__ ucnt) {
+                        u32* __restrict__ loc_out, u64* __restrict__ tile_tot, i64* __restrict__ overflow,
+                        u8* __restrict__ rowflag, u64* __restrict__ ucnt) {
   constexpr int TILE = SC_THREADS * IPT;
   __shared__ u32 s_rel[SR_STAGE];
   __shared__ u64 s_tmp[8];
-  __shared__ u64 s_prefix;
-  __shared__ u32 s_ticket;
   const u32 tid = threadIdx.x;
-  const i64 tile = take_ticket(ss.ticket, &s_ticket);
+  const i64 tile = blockIdx.x;
   const i64 base = tile * TILE + (i64)tid * IPT;  // this thread's first row
   // own rows: IPT consecutive keys per thread, 16-byte loads
   u64 key[IPT];
@@ -363,43 +379,40 @@ __global__ void __launch_bounds__(SC_THREADS)
       }
     }
   }
-  // ---- exclusive scan of the counts, fused: tile scan + look-back over tile totals ----
+  // ---- exclusive scan of the counts inside the tile; the tile total goes to the spine ----
   u64 mine_sum = 0;
 #pragma unroll
   for (int j = 0; j < IPT; ++j) mine_sum += cnt[j];
   u64 tot;
-  u64 run = block_excl_sum_u64(mine_sum, s_tmp, &tot);
-  if (tid < 32) {
-    const u64 pre = lookback_exclusive(ss.status, (u64)tile, tot);
-    if (tid == 0) s_prefix = pre;
+  u32 run = (u32)block_excl_sum_u64(mine_sum, s_tmp, &tot);  // < 2^32: TILE rows x < 2^31 partners, checked below
+  if (tid == 0) {
+    tile_tot[tile] = tot;
+    if (tot >> 32) *overflow = 1;  // in-tile offsets are 32-bit
   }
-  __syncthreads();
-  run += s_prefix;
   if (base + IPT <= n && IPT >= 4) {
-    // 16-byte stores: IPT u64 offsets and IPT u32 positions per thread are contiguous
-    u64 sc[IPT];
+    // 16-byte stores: the thread's IPT offsets and IPT positions are contiguous
+    u32 sc[IPT];
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
       sc[j] = run;
       run += cnt[j];
     }
-    ulonglong2* so = reinterpret_cast<ulonglong2*>(scan_out + base);
-#pragma unroll
-    for (int j = 0; j < IPT / 2; ++j) so[j] = make_ulonglong2(sc[2 * j], sc[2 * j + 1]);
+    uint4* so = reinterpret_cast<uint4*>(loc_out + base);
     uint4* lo4 = reinterpret_cast<uint4*>(lo_out + base);
 #pragma unroll
-    for (int j = 0; j < IPT / 4; ++j) lo4[j] = make_uint4(lo32[4 * j], lo32[4 * j + 1], lo32[4 * j + 2], lo32[4 * j + 3]);
-    if (base + IPT == n) scan_out[n] = run;
+    for (int j = 0; j < IPT / 4; ++j) {
+      so[j] = make_uint4(sc[4 * j], sc[4 * j + 1], sc[4 * j + 2], sc[4 * j + 3]);
+      lo4[j] = make_uint4(lo32[4 * j], lo32[4 * j + 1], lo32[4 * j + 2], lo32[4 * j + 3]);
+    }
   } else {
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
       const i64 p = base + j;
       if (p < n) {
-        scan_out[p] = run;
+        loc_out[p] = run;
         lo_out[p] = lo32[j];
       }
       run += cnt[j];
-      if (p + 1 == n) scan_out[n] = run;
     }
   }
 }
@@ -408,12 +421,12 @@ __global__ void __launch_bounds__(SC_THREADS)
 __global__ void offset_table_kernel(OverlapWS w, i64 n1, i64 n2, i32 nb, i32 how) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const bool need1 = how & 1, need2 = how & 2;
-  const u64* scanA = w.s[0].scan;
-  const u64* scanB = w.s[1].scan;
+  const ScanView scanA = {w.s[0].tilepre, w.s[0].loc, n1, w.s[0].shift};
+  const ScanView scanB = {w.s[1].tilepre, w.s[1].loc, n2, w.s[1].shift};
   i64 base = 0, runU1 = 0, runU2 = 0, pairs = 0;
   for (i32 c = 0; c < nb; ++c) {
-    i64 a0 = (i64)scanA[w.s[0].seg[c]], a1 = (i64)scanA[w.s[0].seg[c + 1]];
-    i64 b0 = (i64)scanB[w.s[1].seg[c]], b1 = (i64)scanB[w.s[1].seg[c + 1]];
+    i64 a0 = scanA.at(w.s[0].seg[c]), a1 = scanA.at(w.s[0].seg[c + 1]);
+    i64 b0 = scanB.at(w.s[1].seg[c]), b1 = scanB.at(w.s[1].seg[c + 1]);
     i64 U1 = need1 ? (i64)w.s[0].ucnt[c] : 0;
     i64 U2 = need2 ? (i64)w.s[1].ucnt[c] : 0;
     w.cumA[c] = a0;
@@ -429,8 +442,8 @@ __global__ void offset_table_kernel(OverlapWS w, i64 n1, i64 n2, i32 nb, i32 how
     runU1 += U1;
     runU2 += U2;
   }
-  w.cumA[nb] = (i64)scanA[n1];
-  w.cumB[nb] = (i64)scanB[n2];
+  w.cumA[nb] = scanA.at(n1);
+  w.cumB[nb] = scanB.at(n2);
   w.deltaA[nb] = w.deltaB[nb] = 0;
   w.ubase1[nb] = w.ubase2[nb] = base;
   w.ustart1[nb] = runU1;
@@ -439,8 +452,8 @@ __global__ void offset_table_kernel(OverlapWS w, i64 n1, i64 n2, i32 nb, i32 how
   w.header[1] = pairs;
   w.header[2] = runU1;
   w.header[3] = runU2;
-  w.header[4] = (i64)scanA[n1];
-  w.header[5] = (i64)scanB[n2];
+  w.header[4] = scanA.at(n1);
+  w.header[5] = scanB.at(n2);
 }
 
 // Emit one block (A or B) of pairs:  A: (id1[p], id2[lo[p] + k])   B: (id1[lo[q] + k], id2[q]).
@@ -459,23 +472,23 @@ constexpr int EM_TILE = EM_THREADS * EM_IPT;
 // part[b] = owner rows consumed before diagonal b * EM_TILE = #{p : p + scan[p] < D}.
 // One thread per block boundary, so the ~27-step searches of all blocks run
 // side by side instead of at the head of every emit block.
-__global__ void __launch_bounds__(256) emit_partition_kernel(const u64* __restrict__ scan, i64 n_owner, i64 total,
+__global__ void __launch_bounds__(256) emit_partition_kernel(const ScanView scan, i64 n_owner, i64 total,
                                                              i64 block0, i64 nparts, i64* __restrict__ part) {
   const i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nparts) return;
   const i64 W = n_owner + total;
   i64 D = (block0 + b) * EM_TILE;
   if (D > W) D = W;
-  part[b] = lower_bound_by(0, n_owner, [&](i64 p) { return p + (i64)scan[p] < D; });
+  part[b] = lower_bound_by(0, n_owner, [&](i64 p) { return p + scan.at(p) < D; });
 }
 
 template <bool B_SIDE>
-__global__ void __launch_bounds__(EM_THREADS)
-    emit_pairs_kernel(const u64* __restrict__ scan, const u32* __restrict__ lo, i64 n_owner,
+__global__ void __launch_bounds__(EM_THREADS, 6)
+    emit_pairs_kernel(const ScanView scan, const u32* __restrict__ lo, i64 n_owner,
                       const u32* __restrict__ owner_id, const u32* __restrict__ other_id, i64 total,
                       i64 block0, const i64* __restrict__ part, const i64* __restrict__ cum, const i64* __restrict__ delta,
                       i32 nb, i64* __restrict__ ev1, i64* __restrict__ ev2) {
-  __shared__ i64 s_rel[EM_TILE + 2];  // scan[first_item + i] - t0
+  __shared__ i32 s_rel[EM_TILE + 2];  // scan[first_item + i] - t0, clamped to 32 bits
   __shared__ u32 s_lo[EM_TILE + 2];
   __shared__ u32 s_id[EM_TILE + 2];
   __shared__ u32 s_owner[EM_TILE];
@@ -502,7 +515,10 @@ __global__ void __launch_bounds__(EM_THREADS)
   const i64 first = p0 > 0 ? p0 - 1 : 0;  // owner of the first output may have started earlier
   const i32 nitems = (i32)(p1 - first);
   for (i32 i = tid; i <= nitems; i += EM_THREADS) {
-    s_rel[i] = (i64)scan[first + i] - t0;
+    // only offsets in [0, nout] are ever used exactly; the first owner may have started up to
+    // 2^31 - 1 outputs earlier (a row has < 2^31 partners), later owners may start far ahead
+    const i64 rel = scan.at(first + i) - t0;
+    s_rel[i] = rel > 0x7fffffffLL ? 0x7fffffff : (i32)rel;
     if (i < nitems) {
       s_lo[i] = lo[first + i];
       s_id[i] = owner_id[first + i];
@@ -511,7 +527,7 @@ __global__ void __launch_bounds__(EM_THREADS)
   for (i32 x = tid; x < EM_TILE; x += EM_THREADS) s_owner[x] = 0;
   __syncthreads();
   for (i32 i = tid; i < nitems; i += EM_THREADS) {
-    const i64 r = s_rel[i];
+    const i32 r = s_rel[i];
     if (s_rel[i + 1] > r && r >= 0 && r < nout) s_owner[r] = (u32)i;
   }
   __syncthreads();
@@ -543,68 +559,100 @@ __global__ void __launch_bounds__(EM_THREADS)
   }
   __syncthreads();
   const i64 c_lo = s_br[2], c_hi = s_br[3];
-  // all gathers of the thread's 8 outputs in flight before the first store
-  u32 own[EM_IPT], oth[EM_IPT];
-#pragma unroll
-  for (int j = 0; j < EM_IPT; ++j) {
-    const i32 x = j * EM_THREADS + (i32)tid;
-    own[j] = 0;
-    oth[j] = 0;
-    if (x < nout) {
-      const u32 i = s_owner[x];
-      const i64 k = (i64)x - s_rel[i];
-      own[j] = s_id[i];
-      oth[j] = other_id[(i64)s_lo[i] + k];
-    }
-  }
+  // gathers of 4 outputs in flight before their stores
   const i64 d_lo = delta[c_lo];
+#pragma unroll 1
+  for (int h = 0; h < EM_IPT; h += 4) {
+    u32 own[4], oth[4];
 #pragma unroll
-  for (int j = 0; j < EM_IPT; ++j) {
-    const i32 x = j * EM_THREADS + (i32)tid;
-    if (x < nout) {
-      const i64 t = t0 + x;
-      const i64 row = t + ((c_lo == c_hi) ? d_lo : delta[group_of(t, c_lo, c_hi + 1)]);
-      ev1[row] = B_SIDE ? (i64)oth[j] : (i64)own[j];
-      ev2[row] = B_SIDE ? (i64)own[j] : (i64)oth[j];
+    for (int j = 0; j < 4; ++j) {
+      const i32 x = (h + j) * EM_THREADS + (i32)tid;
+      own[j] = 0;
+      oth[j] = 0;
+      if (x < nout) {
+        const u32 i = s_owner[x];
+        const i64 k = (i64)x - (i64)s_rel[i];
+        own[j] = s_id[i];
+        oth[j] = other_id[(i64)s_lo[i] + k];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const i32 x = (h + j) * EM_THREADS + (i32)tid;
+      if (x < nout) {
+        const i64 t = t0 + x;
+        const i64 row = t + ((c_lo == c_hi) ? d_lo : delta[group_of(t, c_lo, c_hi + 1)]);
+        ev1[row] = B_SIDE ? (i64)oth[j] : (i64)own[j];
+        ev2[row] = B_SIDE ? (i64)own[j] : (i64)oth[j];
+      }
     }
   }
 }
 
 // ---- unpaired rows: compaction in row order -> stable partition by group ----
-__global__ void __launch_bounds__(SC_THREADS)
-    compact_unpaired_kernel(const u8* __restrict__ flag, const i32* __restrict__ grp, u64 n, ScanState ss,
-                            u64* __restrict__ ukeys, u64* __restrict__ nU) {
-  __shared__ u64 s_tmp[8];
-  __shared__ u64 s_prefix;
-  __shared__ u32 s_ticket;
-  const u32 tid = threadIdx.x;
-  const u64 tile = take_ticket(ss.ticket, &s_ticket);
-  const u64 base = tile * SC_TILE + (u64)tid * SC_IPT;
-  // 8 flag bytes per thread in one 8-byte load (flag array is 256-byte aligned, tile offsets multiples of 8)
-  u64 f8 = 0;
-  if (base + SC_IPT <= n) {
-    f8 = *reinterpret_cast<const u64*>(flag + base);
-  } else {
-    for (int j = 0; j < SC_IPT; ++j)
-      if (base + j < n) f8 |= (u64)flag[base + j] << (8 * j);
-  }
-  u64 tot;
-  u64 at = block_excl_sum_u64((u64)__popcll(f8), s_tmp, &tot);
-  if (tid < 32) {
-    const u64 pre = lookback_exclusive(ss.status, tile, tot);
-    if (tid == 0) s_prefix = pre;
-  }
-  __syncthreads();
-  at += s_prefix;
+// Two launches around a spine scan (count per tile, then write), no look-back: a
+// single-pass chained scan over 1-byte flags is bound by the latency of the
+// chain (one L2 round trip per 32 tiles), not by the 0.1 GB it reads.
+constexpr int UP_BYTES = 64;                       // flag bytes per thread (4 x 16-byte loads)
+constexpr int UP_TILE = SC_THREADS * UP_BYTES;     // 16384 rows per block
+static inline i64 unpaired_tiles(i64 n) { return ceil_div(n, UP_TILE); }
+
+__device__ __forceinline__ void load_flags64(const u8* __restrict__ flag, u64 base, u64 n, u64 (&f)[8]) {
+  if (base + UP_BYTES <= n) {
+    const uint4* src = reinterpret_cast<const uint4*>(flag + base);
 #pragma unroll
-  for (int j = 0; j < SC_IPT; ++j) {
-    if ((f8 >> (8 * j)) & 1ull) {
-      const u64 i = base + j;
+    for (int q = 0; q < 4; ++q) {
+      const uint4 v = src[q];
+      f[2 * q] = (u64)v.x | ((u64)v.y << 32);
+      f[2 * q + 1] = (u64)v.z | ((u64)v.w << 32);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      f[q] = 0;
+      for (int j = 0; j < 8; ++j) {
+        const u64 i = base + q * 8 + j;
+        if (i < n) f[q] |= (u64)flag[i] << (8 * j);
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(SC_THREADS)
+    unpaired_count_kernel(const u8* __restrict__ flag, u64 n, u64* __restrict__ spine) {
+  __shared__ u64 s_tmp[8];
+  const u64 base = (u64)blockIdx.x * UP_TILE + (u64)threadIdx.x * UP_BYTES;
+  u64 f[8];
+  load_flags64(flag, base, n, f);
+  u64 c = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) c += (u64)__popcll(f[q]);
+  c = block_sum_u64(c, s_tmp);
+  if (threadIdx.x == 0) spine[blockIdx.x] = c;
+}
+__global__ void __launch_bounds__(SC_THREADS)
+    unpaired_write_kernel(const u8* __restrict__ flag, const i32* __restrict__ grp, u64 n,
+                          const u64* __restrict__ spine, u64* __restrict__ ukeys) {
+  __shared__ u64 s_tmp[8];
+  const u64 base = (u64)blockIdx.x * UP_TILE + (u64)threadIdx.x * UP_BYTES;
+  u64 f[8];
+  load_flags64(flag, base, n, f);
+  u64 c = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) c += (u64)__popcll(f[q]);
+  u64 tot;
+  u64 at = spine[blockIdx.x] + block_excl_sum_u64(c, s_tmp, &tot);
+  if (c == 0) return;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    u64 bits = f[q];
+    while (bits) {
+      const int j = (__ffsll((long long)bits) - 1) >> 3;  // flags are 0/1 bytes
+      bits &= ~(0xffull << (8 * j));
+      const u64 i = base + q * 8 + j;
       const u64 g = grp ? (u64)(u32)grp[i] : 0ull;
       ukeys[at++] = (g << 32) | i;
     }
   }
-  if (tile * SC_TILE + SC_TILE >= n && tid == 0) *nU = s_prefix + tot;
 }
 template <bool SECOND>
 __global__ void __launch_bounds__(256) emit_unpaired_kernel(const u64* __restrict__ ukeys, i64 nU,
@@ -622,29 +670,34 @@ __global__ void __launch_bounds__(256) emit_unpaired_kernel(const u64* __restric
 }
 
 template <bool B_SIDE, bool FLAGS, int IPT>
-static int launch_search_ipt(const SortResult& mine, i64 n, const SortResult& other, i64 m, const SetWS& sw,
-                             const u64* other_pmax, const KeyLayout& L, int closed, cudaStream_t st) {
+static int launch_search_ipt(const SortResult& mine, i64 n, const SortResult& other, i64 m, SetWS& sw,
+                             const u64* other_pmax, const KeyLayout& L, int closed, i64* overflow, cudaStream_t st) {
   const i64 tiles = search_tiles(n, IPT);
-  BF_TRY(reset_scan_state(sw.ss_search, (u64)tiles, st));
   BF_LAUNCH(PC_SEARCH, 0, st, search_partition_kernel<B_SIDE><<<(unsigned)ceil_div(tiles + 1, 256), 256, 0, st>>>(
       mine.keys, n, other.keys, m, L, (i64)SC_THREADS * IPT, tiles, sw.bracket));
-  BF_LAUNCH(PC_SEARCH, 20 * n, st, (search_count_kernel<B_SIDE, FLAGS, IPT><<<(unsigned)tiles, SC_THREADS, 0, st>>>(
-      mine.keys, mine.vals, n, other.keys, m, other_pmax, sw.bracket, L, closed, sw.lo, sw.scan, sw.ss_search,
+  BF_LAUNCH(PC_SEARCH, 16 * n, st, (search_count_kernel<B_SIDE, FLAGS, IPT><<<(unsigned)tiles, SC_THREADS, 0, st>>>(
+      mine.keys, mine.vals, n, other.keys, m, other_pmax, sw.bracket, L, closed, sw.lo, sw.loc, sw.tilepre, overflow,
       FLAGS ? sw.rowflag : nullptr, FLAGS ? sw.ucnt : nullptr)));
+  // tile totals -> exclusive tile offsets, grand total in tilepre[tiles]
+  BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(sw.tilepre, (u64)tiles, sw.tilepre + tiles));
+  int shift = 0;
+  while ((1 << shift) < SC_THREADS * IPT) ++shift;
+  sw.shift = shift;
   return BF_OK;
 }
 template <bool B_SIDE>
-static int launch_search(const SortResult& mine, i64 n, const SortResult& other, i64 m, bool flags, const SetWS& sw,
-                         const u64* other_pmax, const KeyLayout& L, int closed, cudaStream_t st) {
+static int launch_search(const SortResult& mine, i64 n, const SortResult& other, i64 m, bool flags, SetWS& sw,
+                         const u64* other_pmax, const KeyLayout& L, int closed, i64* overflow, cudaStream_t st) {
   if (n == 0) {
-    BF_CUDA(cudaMemsetAsync(sw.scan, 0, sizeof(u64), st));
+    BF_CUDA(cudaMemsetAsync(sw.tilepre, 0, 2 * sizeof(u64), st));
+    sw.shift = 8;
     return BF_OK;
   }
   const int ipt = pick_search_ipt(n, m);
 #define BF_SEARCH_CASE(I)                                                                                          \
   case I:                                                                                                          \
-    return flags ? launch_search_ipt<B_SIDE, true, I>(mine, n, other, m, sw, other_pmax, L, closed, st)            \
-                 : launch_search_ipt<B_SIDE, false, I>(mine, n, other, m, sw, other_pmax, L, closed, st);
+    return flags ? launch_search_ipt<B_SIDE, true, I>(mine, n, other, m, sw, other_pmax, L, closed, overflow, st)  \
+                 : launch_search_ipt<B_SIDE, false, I>(mine, n, other, m, sw, other_pmax, L, closed, overflow, st);
   switch (ipt) {
     BF_SEARCH_CASE(8)
     BF_SEARCH_CASE(4)
@@ -731,8 +784,11 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
     if (n2 > 0) BF_CUDA(cudaMemsetAsync(w.s[1].rowflag, 0, (size_t)n2, st));
   }
   // algorithmic bytes: key read (8) + lo (4) + scan offset (8) written per row
-  BF_TRY((launch_search<false>(r1, n1, r2, n2, need1, w.s[0], w.s[1].pmax, L, closed, st)));
-  BF_TRY((launch_search<true>(r2, n2, r1, n1, need2, w.s[1], w.s[0].pmax, L, closed, st)));
+  BF_CUDA(cudaMemsetAsync(w.header, 0, 8 * sizeof(i64), st));
+  BF_TRY((launch_search<false>(r1, n1, r2, n2, need1, w.s[0], w.s[1].pmax, L, closed, w.header + 6, st)));
+  BF_TRY((launch_search<true>(r2, n2, r1, n1, need2, w.s[1], w.s[0].pmax, L, closed, w.header + 6, st)));
+  plan->shift1 = w.s[0].shift;
+  plan->shift2 = w.s[1].shift;
 
   // ---- unpaired lists: compact in row order, partition by group ----
   BF_CUDA(cudaMemsetAsync(w.nU, 0, 2 * sizeof(u64), st));
@@ -741,10 +797,10 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   for (int k = 0; k < 2; ++k) {
     const bool need = k == 0 ? need1 : need2;
     if (!need || nn[k] == 0) continue;
-    const unsigned tiles = (unsigned)scan_tiles((u64)nn[k]);
-    BF_TRY(reset_scan_state(w.s[k].ss, tiles, st));
-    BF_LAUNCH(PC_UNPAIRED, 0, st, compact_unpaired_kernel<<<tiles, SC_THREADS, 0, st>>>(
-        w.s[k].rowflag, grps[k], (u64)nn[k], w.s[k].ss, w.s[k].ukeyA, w.nU + k));
+    const unsigned tiles = (unsigned)unpaired_tiles(nn[k]);
+    BF_LAUNCH(PC_UNPAIRED, nn[k], st, unpaired_count_kernel<<<tiles, SC_THREADS, 0, st>>>(w.s[k].rowflag, (u64)nn[k], w.s[k].uspine));
+    BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.s[k].uspine, (u64)tiles, w.nU + k));
+    BF_LAUNCH(PC_UNPAIRED, nn[k], st, unpaired_write_kernel<<<tiles, SC_THREADS, 0, st>>>(w.s[k].rowflag, grps[k], (u64)nn[k], w.s[k].uspine, w.s[k].ukeyA));
     ukeys_sorted[k] = w.s[k].ukeyA;
     if (L.rank_bits > 0) {
       const RadixPlan urp = make_radix_plan(32, 32 + L.rank_bits);
@@ -770,6 +826,10 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   plan->nU2 = header[3];
   plan->totA = header[4];
   plan->totB = header[5];
+  if (header[6]) {
+    set_error("bf_overlap_count: more than 2^32-1 pairs inside one block of %d consecutive sorted rows", SC_TILE);
+    return BF_ERR_RANGE;
+  }
   plan->magic = OVERLAP_MAGIC;
   plan->ready = 1;
   return BF_OK;
@@ -793,22 +853,23 @@ static int overlap_emit_impl(const OverlapPlan* plan, void* ws_ptr, i64* ev1, i6
     if (total <= 0) continue;
     const i64 n_owner = side ? plan->n2 : plan->n1;
     const SetWS& sw = w.s[side];
+    const ScanView scan = {sw.tilepre, sw.loc, n_owner, side ? plan->shift2 : plan->shift1};
     i64* part = side ? w.partB : w.partA;
     const i64 blocks = ceil_div(n_owner + total, EM_TILE);
     for (i64 b0 = 0; b0 < blocks; b0 += EMIT_CHUNK_BLOCKS) {
       const i64 nb_chunk = blocks - b0 < EMIT_CHUNK_BLOCKS ? blocks - b0 : EMIT_CHUNK_BLOCKS;
       BF_LAUNCH(PC_EMIT, 0, st,
-                emit_partition_kernel<<<(unsigned)ceil_div(nb_chunk + 1, 256), 256, 0, st>>>(sw.scan, n_owner, total, b0,
+                emit_partition_kernel<<<(unsigned)ceil_div(nb_chunk + 1, 256), 256, 0, st>>>(scan, n_owner, total, b0,
                                                                                             nb_chunk + 1, part));
       const u64 bytes = (u64)(20.0 * (double)total * (double)nb_chunk / (double)blocks);
       if (side == 0) {
         BF_LAUNCH(PC_EMIT, bytes, st,
                   emit_pairs_kernel<false><<<(unsigned)nb_chunk, EM_THREADS, 0, st>>>(
-                      sw.scan, sw.lo, n_owner, plan->id1, plan->id2, total, b0, part, w.cumA, w.deltaA, plan->nb, ev1, ev2));
+                      scan, sw.lo, n_owner, plan->id1, plan->id2, total, b0, part, w.cumA, w.deltaA, plan->nb, ev1, ev2));
       } else {
         BF_LAUNCH(PC_EMIT, bytes, st,
                   emit_pairs_kernel<true><<<(unsigned)nb_chunk, EM_THREADS, 0, st>>>(
-                      sw.scan, sw.lo, n_owner, plan->id2, plan->id1, total, b0, part, w.cumB, w.deltaB, plan->nb, ev1, ev2));
+                      scan, sw.lo, n_owner, plan->id2, plan->id1, total, b0, part, w.cumB, w.deltaB, plan->nb, ev1, ev2));
       }
     }
   }

@@ -85,40 +85,34 @@ __device__ __forceinline__ u32 match_digit8(u32 d) {
 }
 
 // ---- histogram of all digit places, callable from any key-producing kernel ----
-// Each warp owns a private [passes][256] table in shared memory; per key and
-// digit place the lanes holding the same digit elect a leader that adds the
-// group size with a plain load/store (shared-memory atomics run at ~2 cycles
-// per lane, far too slow for 8 digit places per key). One __syncwarp per key.
+// One [passes][256] table per block in shared memory, updated with shared-memory
+// atomics.  Measured on B200 (profiles/microbench/hist_bench.cu, 1e8 keys, four
+// digit places): 0.18 ms with atomics against 1.28 ms for ballot-based
+// warp aggregation and 2.75 ms for match.any -- even when every lane of a warp
+// hits the same counter (sorted input), so there is no reason to aggregate by hand.
 constexpr int HIST_THREADS = 256;
-constexpr int HIST_WARPS = HIST_THREADS / 32;
 static inline size_t hist_smem_bytes(const struct RadixPlan& rp);
 
-__device__ __forceinline__ void hist_add(u32* wtab, const RadixPlan& rp, u64 key, bool valid) {
-  const u32 lt = lanemask_lt();
-  const u32 vmask = __ballot_sync(0xffffffffu, valid);
+__device__ __forceinline__ void hist_add(u32* tab, const RadixPlan& rp, u64 key, bool valid) {
 #pragma unroll
   for (int i = 0; i < RS_MAX_PASSES; ++i) {
-    if (i < rp.passes) {
+    if (i < rp.passes && valid) {
       const u32 d = (u32)(key >> rp.shift[i]) & ((1u << rp.bits[i]) - 1u);
-      const u32 peers = match_digit8(d) & vmask;
-      if (valid && (peers & lt) == 0) wtab[i * RS_BINS + d] += (u32)__popc(peers);
+      atomicAdd(&tab[i * RS_BINS + d], 1u);
     }
   }
-  __syncwarp();
 }
 __device__ __forceinline__ void hist_clear(u32* tabs, const RadixPlan& rp) {
-  for (int i = threadIdx.x; i < HIST_WARPS * rp.passes * RS_BINS; i += blockDim.x) tabs[i] = 0;
+  for (int i = threadIdx.x; i < rp.passes * RS_BINS; i += blockDim.x) tabs[i] = 0;
 }
 __device__ __forceinline__ void hist_flush(const u32* tabs, const RadixPlan& rp, u64* ghist) {
   for (int i = threadIdx.x; i < rp.passes * RS_BINS; i += blockDim.x) {
-    u32 c = 0;
-#pragma unroll
-    for (int w = 0; w < HIST_WARPS; ++w) c += tabs[w * rp.passes * RS_BINS + i];
+    const u32 c = tabs[i];
     if (c) atomicAdd(&ghist[i], (u64)c);
   }
 }
 static inline size_t hist_smem_bytes(const RadixPlan& rp) {
-  return (size_t)HIST_WARPS * (rp.passes > 0 ? rp.passes : 1) * RS_BINS * sizeof(u32);
+  return (size_t)(rp.passes > 0 ? rp.passes : 1) * RS_BINS * sizeof(u32);
 }
 
 // Generic histogram over an existing key array (n may live on the device).
@@ -130,7 +124,7 @@ static __global__ void __launch_bounds__(HIST_THREADS) radix_hist_kernel(const u
   const u64 n = n_dev ? *n_dev : n_host;
   hist_clear(hist_tabs, rp);
   __syncthreads();
-  u32* wtab = hist_tabs + (threadIdx.x >> 5) * rp.passes * RS_BINS;
+  u32* wtab = hist_tabs;
   const u64 per_block = (u64)HIST_THREADS * 16ull;
   for (u64 base = (u64)blockIdx.x * per_block; base < n; base += (u64)gridDim.x * per_block) {
 #pragma unroll 4
@@ -227,83 +221,43 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
   }
   __syncthreads();
 
-  // ---- thread d < 256: exclusive offsets of digit d across warps, tile digit count ----
+  // ---- thread d: exclusive offsets of digit d across warps, tile digit count; publish the tile's
+  //      digit counts right away so that later tiles can start summing them ----
+  const u32 d_own = tid & (RS_BINS - 1);  // RS_THREADS == RS_BINS: every thread owns one digit
+  u64 cnt_valid;
+  u32 tbase_own;
   {
-    const bool dthread = tid < RS_BINS;
-    const u32 d = tid & (RS_BINS - 1);
     u32 tile_cnt = 0;
-    if (dthread) {
 #pragma unroll
-      for (int w = 0; w < RS_WARPS; ++w) {
-        u32 c = s_wcnt[w * RS_BINS + d];
-        s_wcnt[w * RS_BINS + d] = tile_cnt;
-        tile_cnt += c;
-      }
+    for (int w = 0; w < RS_WARPS; ++w) {
+      u32 c = s_wcnt[w * RS_BINS + d_own];
+      s_wcnt[w * RS_BINS + d_own] = tile_cnt;
+      tile_cnt += c;
     }
-    // exclusive scan of tile_cnt over the 256 digits (warps 0..7)
+    // exclusive scan of tile_cnt over the 256 digits
     u32 inc = tile_cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       u32 t = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= (u32)o) inc += t;
     }
-    if (dthread && lane == 31) s_wtot[warp] = inc;
+    if (lane == 31) s_wtot[warp] = inc;
     __syncthreads();
-    if (dthread) {
-      u32 pre = 0;
+    u32 pre = 0;
 #pragma unroll
-      for (int w = 0; w < RS_BINS / 32; ++w)
-        if ((u32)w < warp) pre += s_wtot[w];
-      const u32 tbase = pre + inc - tile_cnt;
-      s_tbase[d] = tbase;
-
-      // pads all carry digit dmask and sit at the very end of the tile
-      u64 cnt_valid = tile_cnt;
-      if (d == dmask) cnt_valid -= (u64)(RS_TILE - valid);
-
-      // ---- decoupled look-back: digits before this tile ----
-      // RS_LOOK predecessors are fetched per round trip (independent loads), so the
-      // chain of "wait for the tile before me" that forms when all persistent
-      // blocks start together resolves RS_LOOK times faster than one load per step.
-      u64* mine = status + tile * RS_BINS + d;
-      u64 excl = 0;
-      if (tile == 0) {
-        st_relaxed_u64(mine, tag | RS_FLAG_INC | cnt_valid);
-      } else {
-        st_relaxed_u64(mine, tag | RS_FLAG_AGG | cnt_valid);
-        i64 pt = (i64)tile - 1;  // nearest predecessor not yet accounted for
-        for (;;) {
-          u64 w[RS_LOOK];
-#pragma unroll
-          for (int b = 0; b < RS_LOOK; ++b)
-            w[b] = pt - b >= 0 ? ld_relaxed_u64(status + (u64)(pt - b) * RS_BINS + d) : (tag | RS_FLAG_INC);
-          bool finished = false, stalled = false;
-          int consumed = 0;
-#pragma unroll
-          for (int b = 0; b < RS_LOOK; ++b) {
-            if (!finished && !stalled) {
-              const u64 flag = w[b] & (3ull << 56);
-              // a word of an earlier pass (other tag) or an unpublished one: poll again from here
-              if ((w[b] & ~(RS_VAL_MASK | (3ull << 56))) != tag || flag == 0) {
-                stalled = true;
-              } else {
-                excl += w[b] & RS_VAL_MASK;
-                ++consumed;
-                finished = flag == RS_FLAG_INC;
-              }
-            }
-          }
-          if (finished) break;
-          pt -= consumed;
-        }
-        st_relaxed_u64(mine, tag | RS_FLAG_INC | (excl + cnt_valid));
-      }
-      s_gofs[d] = digit_base[d] + excl - (u64)tbase;
-    }
+    for (int w = 0; w < RS_BINS / 32; ++w)
+      if ((u32)w < warp) pre += s_wtot[w];
+    tbase_own = pre + inc - tile_cnt;
+    s_tbase[d_own] = tbase_own;
+    // pads all carry digit dmask and sit at the very end of the tile
+    cnt_valid = tile_cnt;
+    if (d_own == dmask) cnt_valid -= (u64)(RS_TILE - valid);
+    st_relaxed_u64(status + tile * RS_BINS + d_own, tag | (tile == 0 ? RS_FLAG_INC : RS_FLAG_AGG) | cnt_valid);
   }
   __syncthreads();
 
-  // ---- stage keys in shared memory in sorted order ----
+  // ---- stage keys in shared memory in sorted order (needs only tile-local offsets; the
+  //      predecessors get this much more time to publish before the look-back polls them) ----
 #pragma unroll
   for (int j = 0; j < RS_IPT; ++j) {
     u32 d = (u32)(key[j] >> shift) & dmask;
@@ -319,6 +273,41 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
       if (li < valid) v = vin ? vin[tile_start + li] : (u32)(tile_start + li);
       s_vals[lpos[j]] = v;
     }
+  }
+
+  // ---- decoupled look-back: digits before this tile ----
+  // RS_LOOK predecessors are fetched per round trip (independent loads).
+  {
+    u64 excl = 0;
+    if (tile > 0) {
+      i64 pt = (i64)tile - 1;  // nearest predecessor not yet accounted for
+      for (;;) {
+        u64 w[RS_LOOK];
+#pragma unroll
+        for (int b = 0; b < RS_LOOK; ++b)
+          w[b] = pt - b >= 0 ? ld_relaxed_u64(status + (u64)(pt - b) * RS_BINS + d_own) : (tag | RS_FLAG_INC);
+        bool finished = false, stalled = false;
+        int consumed = 0;
+#pragma unroll
+        for (int b = 0; b < RS_LOOK; ++b) {
+          if (!finished && !stalled) {
+            const u64 flag = w[b] & (3ull << 56);
+            // a word of an earlier pass (other tag) or an unpublished one: poll again from here
+            if ((w[b] & ~(RS_VAL_MASK | (3ull << 56))) != tag || flag == 0) {
+              stalled = true;
+            } else {
+              excl += w[b] & RS_VAL_MASK;
+              ++consumed;
+              finished = flag == RS_FLAG_INC;
+            }
+          }
+        }
+        if (finished) break;
+        pt -= consumed;
+      }
+      st_relaxed_u64(status + tile * RS_BINS + d_own, tag | RS_FLAG_INC | (excl + cnt_valid));
+    }
+    s_gofs[d_own] = digit_base[d_own] + excl - (u64)tbase_own;
   }
   __syncthreads();
 

@@ -98,37 +98,57 @@ __device__ __forceinline__ u64 block_excl_max_u64(u64 v, u64* s_tmp) {
 }
 
 // ---- spine: one block turns per-tile partials into exclusive prefixes ----
+// Coalesced chunks of 1024 entries, block scan per chunk with a carried prefix
+// (a few microseconds for the ~5e4 tiles of a 1e8-row call).
 template <bool IS_MAX>
-__global__ void __launch_bounds__(1024) spine_scan_kernel(u64* __restrict__ spine, u64 ntiles,
-                                                          u64* __restrict__ total_out) {
-  __shared__ u64 s_part[1024];
-  const u32 tid = threadIdx.x;
-  const u64 per = (ntiles + 1023) / 1024;
-  const u64 lo = (u64)tid * per;
-  const u64 hi = lo + per < ntiles ? lo + per : ntiles;
-  u64 acc = 0;
-  for (u64 i = lo; i < hi; ++i) {
-    u64 v = spine[i];
-    acc = IS_MAX ? (v > acc ? v : acc) : acc + v;
-  }
-  s_part[tid] = acc;
+static __global__ void __launch_bounds__(1024) spine_scan_kernel(u64* __restrict__ spine, u64 ntiles,
+                                                                 u64* __restrict__ total_out) {
+  __shared__ u64 s_warp[32];
+  __shared__ u64 s_carry;
+  const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) s_carry = 0;
   __syncthreads();
-  if (tid == 0) {
-    u64 run = 0;
-    for (int i = 0; i < 1024; ++i) {
-      u64 v = s_part[i];
-      s_part[i] = run;
-      run = IS_MAX ? (v > run ? v : run) : run + v;
+  for (u64 base = 0; base < ntiles; base += 1024) {
+    const u64 i = base + tid;
+    const u64 v = i < ntiles ? spine[i] : 0ull;
+    u64 inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u64 t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (u32)o) inc = IS_MAX ? (t > inc ? t : inc) : inc + t;
     }
-    if (total_out) *total_out = run;
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {  // scan of the 32 warp totals
+      const u64 x = s_warp[lane];
+      u64 y = x;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(0xffffffffu, y, o);
+        if (lane >= (u32)o) y = IS_MAX ? (t > y ? t : y) : y + t;
+      }
+      // exclusive prefix of the warps
+      u64 ex = __shfl_up_sync(0xffffffffu, y, 1);
+      if (lane == 0) ex = 0;
+      s_warp[lane] = ex;
+    }
+    __syncthreads();
+    const u64 carry = s_carry;
+    u64 before_warp = s_warp[w];
+    // exclusive value for this entry = carry (op) warps before (op) lanes before
+    u64 up = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) up = 0;
+    u64 excl = IS_MAX ? (before_warp > up ? before_warp : up) : before_warp + up;
+    excl = IS_MAX ? (carry > excl ? carry : excl) : carry + excl;
+    if (i < ntiles) spine[i] = excl;
+    __syncthreads();
+    if (tid == 1023) {
+      const u64 incl = IS_MAX ? (excl > v ? excl : v) : excl + v;
+      s_carry = incl;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  u64 run = s_part[tid];
-  for (u64 i = lo; i < hi; ++i) {
-    u64 v = spine[i];
-    spine[i] = run;
-    run = IS_MAX ? (v > run ? v : run) : run + v;
-  }
+  if (tid == 0 && total_out) *total_out = s_carry;
 }
 
 // ---- per-tile sums of a u32 array (when no producer wrote the spine) ----

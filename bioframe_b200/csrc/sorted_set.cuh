@@ -21,7 +21,8 @@ struct SortBufs {
   u32 *tmp4a;  // [n]
   u32 *tmp4b;  // [n]
   ScanState ss;
-  u64 *nT;     // device-side count of tied rows
+  u64 *spine;  // [scan tiles + 1] per-tile counts / offsets of rows in long tie runs
+  u64 *nT;     // device-side count of rows in long tie runs
 };
 static inline void take_sort_bufs(Arena& a, i64 n, SortBufs* b) {
   b->keyA = a.take<u64>(n);
@@ -32,65 +33,125 @@ static inline void take_sort_bufs(Arena& a, i64 n, SortBufs* b) {
   b->tmp4a = a.take<u32>(n);
   b->tmp4b = a.take<u32>(n);
   b->ss = take_scan_state(a, (u64)scan_tiles((u64)n));
+  b->spine = a.take<u64>(scan_tiles((u64)n) + 2);
   b->nT = a.take<u64>(1);
 }
 
 // ---- tie fix-up: rows sharing (group, start) into (end', row) order ----
 // After the stable sort on cs the rows of a tie run are in row order; the
-// reference wants them by (end', row).  Tied rows are rare, so: count them,
-// compact (key, id, slot), sort that subset by the FULL key (stable, so equal
-// keys keep row order) and write it back into the same slots in order.
-// One pass: stage the tile's keys (+ one halo key each side) in shared memory,
-// flag tied rows, scan the flags (tile scan + look-back) and write the subset.
-static __global__ void __launch_bounds__(SC_THREADS)
-    tie_compact_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, KeyLayout L, ScanState ss,
-                       u64* __restrict__ tkeys, u32* __restrict__ tids, u32* __restrict__ tpos,
-                       u64* __restrict__ nT) {
-  __shared__ u64 s_k[SC_TILE + 2];
-  __shared__ u64 s_tmp[8];
-  __shared__ u64 s_prefix;
-  __shared__ u32 s_ticket;
+// reference wants them by (end', row).  One pass over the sorted keys: a tile's
+// keys (+ TIE_HALO keys each side) are staged in shared memory and every tied
+// row measures its run.  Runs of up to TIE_SMALL rows (nearly all of them: two
+// or three intervals that happen to start at the same base) are insertion-
+// sorted in place by the thread that owns the run's first row -- stable, so
+// equal keys keep row order.  Rows of longer runs (heavily duplicated input)
+// are compacted as (key, id, slot), sorted by the FULL key with the stable
+// radix sort and written back into the same slots in order.
+constexpr int TIE_SMALL = 32;
+constexpr int TIE_HALO = TIE_SMALL + 1;
+
+// Stage a tile's keys (+ halo), measure the run of every tied row; with FIX,
+// sort short runs in place.  Returns the mask of this thread's rows that belong
+// to long runs.
+template <bool FIX>
+__device__ __forceinline__ u32 tie_scan_tile(u64* __restrict__ keys, u32* __restrict__ ids, u64 n, const KeyLayout& L,
+                                             u64 base, u64 rows, u64* s_k) {
   const u32 tid = threadIdx.x;
-  const u64 tile = take_ticket(ss.ticket, &s_ticket);
-  const u64 base = tile * SC_TILE;
-  const u64 rows = n - base < (u64)SC_TILE ? n - base : (u64)SC_TILE;
-  for (u32 i = tid; i < rows + 2; i += SC_THREADS) {
-    const i64 p = (i64)base + i - 1;
-    // halo outside the array: a key whose cs differs from every neighbour's
+  // s_k[i] = keys[base - TIE_HALO + i]
+  for (u32 i = tid; i < rows + 2 * TIE_HALO; i += SC_THREADS) {
+    const i64 p = (i64)base + i - TIE_HALO;
     s_k[i] = (p >= 0 && (u64)p < n) ? keys[p] : ~0ull;
   }
   __syncthreads();
-  const bool lo_edge = base == 0, hi_edge = base + rows == n;
   u32 mask = 0;
-#pragma unroll
+#pragma unroll 1
   for (int j = 0; j < SC_IPT; ++j) {
-    const u32 r = tid * SC_IPT + j;  // row inside the tile, s_k index r + 1
-    if (r < rows) {
-      const u64 c = key_cs(s_k[r + 1], L);
-      const bool prev_ok = !(lo_edge && r == 0);
-      const bool next_ok = !(hi_edge && r + 1 == rows);
-      if ((prev_ok && key_cs(s_k[r], L) == c) || (next_ok && key_cs(s_k[r + 2], L) == c)) mask |= 1u << j;
+    const u32 r = tid * SC_IPT + j;  // row inside the tile, s_k index r + TIE_HALO
+    if (r >= rows) break;
+    const u32 at = r + TIE_HALO;
+    const u64 c = key_cs(s_k[at], L);
+    const bool prev_same = (base + r > 0) && key_cs(s_k[at - 1], L) == c;
+    const bool next_same = (base + r + 1 < n) && key_cs(s_k[at + 1], L) == c;
+    if (!prev_same && !next_same) continue;
+    u32 back = 0, fwd = 0;
+    while (back < TIE_SMALL && base + r > back && key_cs(s_k[at - back - 1], L) == c) ++back;
+    while (fwd < TIE_SMALL && base + r + fwd + 1 < n && key_cs(s_k[at + fwd + 1], L) == c) ++fwd;
+    const u32 m = back + fwd + 1;
+    if (m > TIE_SMALL) {
+      mask |= 1u << j;  // long run: general path
+    } else if (FIX && back == 0) {
+      // owner of a short run: stable insertion sort of (key, id) by key, in place
+      const u64 p0 = base + r;
+      if (m == 2) {
+        if (s_k[at] > s_k[at + 1]) {
+          const u32 v0 = ids[p0], v1 = ids[p0 + 1];
+          keys[p0] = s_k[at + 1];
+          keys[p0 + 1] = s_k[at];
+          ids[p0] = v1;
+          ids[p0 + 1] = v0;
+        }
+      } else {
+        u64 k[TIE_SMALL];
+        u32 v[TIE_SMALL];
+        for (u32 x = 0; x < m; ++x) {
+          const u64 kx = s_k[at + x];
+          const u32 vx = ids[p0 + x];
+          u32 y = x;
+          while (y > 0 && k[y - 1] > kx) {
+            k[y] = k[y - 1];
+            v[y] = v[y - 1];
+            --y;
+          }
+          k[y] = kx;
+          v[y] = vx;
+        }
+        for (u32 x = 0; x < m; ++x) {
+          if (k[x] != s_k[at + x]) keys[p0 + x] = k[x];
+          ids[p0 + x] = v[x];  // equal keys may still have traded places with each other's neighbours
+        }
+      }
     }
   }
+  return mask;
+}
+
+// pass 1: fix short runs in place, count rows of long runs per tile
+static __global__ void __launch_bounds__(SC_THREADS)
+    tie_fix_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u64 n, KeyLayout L, u64* __restrict__ spine) {
+  __shared__ u64 s_k[SC_TILE + 2 * TIE_HALO];
+  __shared__ u64 s_tmp[8];
+  const u64 base = (u64)blockIdx.x * SC_TILE;
+  const u64 rows = n - base < (u64)SC_TILE ? n - base : (u64)SC_TILE;
+  const u32 mask = tie_scan_tile<true>(keys, ids, n, L, base, rows, s_k);
+  const u64 c = block_sum_u64((u64)__popc(mask), s_tmp);
+  if (threadIdx.x == 0) spine[blockIdx.x] = c;
+}
+// pass 2 (after the spine scan): tiles that hold rows of long runs compact them as (key, id, slot)
+static __global__ void __launch_bounds__(SC_THREADS)
+    tie_gather_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u64 n, KeyLayout L, const u64* __restrict__ spine,
+                      u64 ntiles, const u64* __restrict__ nT, u64* __restrict__ tkeys, u32* __restrict__ tids,
+                      u32* __restrict__ tpos) {
+  __shared__ u64 s_k[SC_TILE + 2 * TIE_HALO];
+  __shared__ u64 s_tmp[8];
+  const u64 tile = blockIdx.x;
+  const u64 first = spine[tile];
+  const u64 next = tile + 1 < ntiles ? spine[tile + 1] : *nT;
+  if (next == first) return;  // nearly every tile of real data
+  const u64 base = tile * SC_TILE;
+  const u64 rows = n - base < (u64)SC_TILE ? n - base : (u64)SC_TILE;
+  const u32 mask = tie_scan_tile<false>(keys, ids, n, L, base, rows, s_k);
   u64 tot;
-  u64 at = block_excl_sum_u64((u64)__popc(mask), s_tmp, &tot);
-  if (tid < 32) {
-    const u64 pre = lookback_exclusive(ss.status, tile, tot);
-    if (tid == 0) s_prefix = pre;
-  }
-  __syncthreads();
-  at += s_prefix;
+  u64 at_out = first + block_excl_sum_u64((u64)__popc(mask), s_tmp, &tot);
 #pragma unroll
   for (int j = 0; j < SC_IPT; ++j) {
     if (mask & (1u << j)) {
-      const u32 r = tid * SC_IPT + j;
-      tkeys[at] = s_k[r + 1];
-      tids[at] = ids[base + r];
-      tpos[at] = (u32)(base + r);
-      ++at;
+      const u32 r = threadIdx.x * SC_IPT + j;
+      tkeys[at_out] = s_k[r + TIE_HALO];
+      tids[at_out] = ids[base + r];
+      tpos[at_out] = (u32)(base + r);
+      ++at_out;
     }
   }
-  if (hi_edge && tid == 0) *nT = s_prefix + tot;
 }
 static __global__ void __launch_bounds__(256) tie_scatter_kernel(const u64* __restrict__ tkeys, const u32* __restrict__ tids,
                                                           const u32* __restrict__ tpos, const u64* __restrict__ nT,
@@ -127,9 +188,11 @@ static int sort_rows(const i32* grp, const i64* s, const i64* e, i64 n, const Ke
   u64* tkeyB = ws.tmp8;
   u32* tidB = ws.tmp4a;
   u32* tpos = ws.tmp4b;
-  BF_TRY(reset_scan_state(ws.ss, tiles, st));
-  BF_LAUNCH(PC_TIEFIX, 8 * n, st,
-            tie_compact_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, L, ws.ss, tkeyA, tidA, tpos, ws.nT));
+  BF_LAUNCH(PC_TIEFIX, 8 * n, st, tie_fix_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, L, ws.spine));
+  BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(ws.spine, (u64)tiles, ws.nT));
+  BF_LAUNCH(PC_TIEFIX, 0, st,
+            tie_gather_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, L, ws.spine, (u64)tiles, ws.nT,
+                                                            tkeyA, tidA, tpos));
   const RadixPlan full = make_radix_plan(0, L.total_bits);
   BF_CUDA(cudaMemsetAsync(sc.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
   BF_TRY(launch_radix_hist(tkeyA, (u64)n, ws.nT, full, sc.hist, st, PC_TIEFIX));

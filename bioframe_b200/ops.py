@@ -57,7 +57,8 @@ def _group_keys(df, by):
     if len(by) == 1:
         return _factorize_column(df[by[0]])
     gb = df.groupby(by, observed=True, sort=True, dropna=True)
-    codes = np.asarray(gb.ngroup(), dtype=np.int64)  # -1 for rows with an NA key
+    ng = gb.ngroup().to_numpy(dtype=np.float64, na_value=np.nan)  # NaN (or -1) for rows with an NA key
+    codes = np.where(np.isnan(ng) | (ng < 0), -1, ng).astype(np.int64)
     keys = list(gb.size().index)
     return codes, keys
 
@@ -250,3 +251,352 @@ def overlap(
         out.drop([icol1, icol2], axis=1, inplace=True)
     out.reset_index(drop=True, inplace=True)
     return out
+
+
+# --------------------------------------------------------------------------
+# closest
+# --------------------------------------------------------------------------
+def _closest_intidxs(
+    df1,
+    df2=None,
+    k=1,
+    ignore_overlaps=False,
+    ignore_upstream=False,
+    ignore_downstream=False,
+    direction_col=None,
+    tie_breaking_col=None,
+    cols1=None,
+    cols2=None,
+    _group_order=None,
+):
+    """Integer row positions of the k closest intervals, -1 where a query has
+    none.  Mirrors ops._closest_intidxs (ops.py:919-1040): chromosome blocks in
+    the iteration order of `set.union(set(groups1), set(groups2))`
+    (ops.py:985,997); rows with a null chromosome take no part (groupby drops
+    them).  `tie_breaking_col` is not supported: the reference's own path for it
+    fails whenever the candidate count differs from the target count
+    (arrops.py:740)."""
+    ck1, sk1, ek1 = _get_default_colnames() if cols1 is None else cols1
+    ck2, sk2, ek2 = _get_default_colnames() if cols2 is None else cols2
+    if tie_breaking_col is not None:
+        raise NotImplementedError("tie_breaking_col is not supported by the CUDA engine")
+    self_closest = (df2 is None) or (df2 is df1)
+    if self_closest:
+        if len(df1) == 1:
+            raise ValueError("df1 must have more than one interval to find closest non-identical interval")
+        df2 = df1
+
+    codes1, keys1 = _group_keys(df1, [ck1])
+    codes2, keys2 = (codes1, keys1) if self_closest else _group_keys(df2, [ck2])
+    order = list(set.union(set(keys1), set(keys2))) if _group_order is None else list(_group_order)
+    rank = {key: r for r, key in enumerate(order)}
+    n_groups = max(len(order), 1)
+
+    def coded(df, codes, keys, sk, ek):
+        """rows with a valid chromosome: (positions, group ranks, starts, ends)"""
+        valid = np.flatnonzero(codes >= 0)
+        table = np.array([rank[key] for key in keys], dtype=np.int32)
+        ranks = table[codes[valid]] if len(valid) else np.empty(0, np.int32)
+        return valid, ranks, _int64_coords(df, sk)[valid], _int64_coords(df, ek)[valid]
+
+    rows1, g1, s1, e1 = coded(df1, codes1, keys1, sk1, ek1)
+    along = None
+    if direction_col is not None:
+        along = (df1[direction_col].values != "-")[rows1]
+    if self_closest:
+        rows2 = rows1
+        ev1, ev2, _ = _engine.closest_intidxs(
+            g1, s1, e1, None, None, None, n_groups, k=k, ignore_overlaps=ignore_overlaps,
+            ignore_upstream=ignore_upstream, ignore_downstream=ignore_downstream, along=along, self_closest=True,
+        )
+    else:
+        rows2, g2, s2, e2 = coded(df2, codes2, keys2, sk2, ek2)
+        ev1, ev2, _ = _engine.closest_intidxs(
+            g1, s1, e1, g2, s2, e2, n_groups, k=k, ignore_overlaps=ignore_overlaps,
+            ignore_upstream=ignore_upstream, ignore_downstream=ignore_downstream, along=along,
+        )
+    ev1, ev2 = _to_host(ev1), _to_host(ev2)
+    # kernel rows index the NA-free subsets; map back to frame positions
+    if len(rows1) != len(df1):
+        ev1 = rows1[ev1]
+    if len(rows2) != len(df2):
+        ev2 = np.where(ev2 >= 0, rows2[np.maximum(ev2, 0)], -1)
+    return ev1, ev2
+
+
+def closest(
+    df1,
+    df2=None,
+    k=1,
+    ignore_overlaps=False,
+    ignore_upstream=False,
+    ignore_downstream=False,
+    direction_col=None,
+    tie_breaking_col=None,
+    return_input=True,
+    return_index=False,
+    return_distance=True,
+    return_overlap=False,
+    suffixes=("", "_"),
+    cols1=None,
+    cols2=None,
+):
+    """For every interval of df1 the k closest intervals of df2 (ops.py:1043-1240).
+    Same arguments, errors and output columns as `bioframe.closest`."""
+    if k < 1:
+        raise ValueError("k>=1 required")
+    if df2 is df1:
+        raise ValueError("pass df2=None to find closest non-identical intervals within the same set.")
+    if df2 is None:
+        df2 = df1
+    ck1, sk1, ek1 = _get_default_colnames() if cols1 is None else cols1
+    ck2, sk2, ek2 = _get_default_colnames() if cols2 is None else cols2
+    checks.is_bedframe(df1, raise_errors=True, cols=[ck1, sk1, ek1])
+    checks.is_bedframe(df2, raise_errors=True, cols=[ck2, sk2, ek2])
+
+    ev1, ev2 = _closest_intidxs(
+        df1, df2, k=k, ignore_overlaps=ignore_overlaps, ignore_upstream=ignore_upstream,
+        ignore_downstream=ignore_downstream, direction_col=direction_col, tie_breaking_col=tie_breaking_col,
+        cols1=cols1, cols2=cols2,
+    )
+    lone = ev2 == -1
+    a1, b1 = df1[sk1].values[ev1], df1[ek1].values[ev1]
+    a2, b2 = df2[sk2].values[ev2], df2[ek2].values[ev2]
+
+    pieces = []
+    if return_index:
+        stem = return_index if isinstance(return_index, str) else "index"
+        idx2 = pd.DataFrame({stem + suffixes[1]: df2.index[ev2]})
+        idx2[lone] = pd.NA
+        pieces.append(("i1", pd.DataFrame({stem + suffixes[0]: df1.index[ev1]})))
+        pieces.append(("i2", idx2))
+    if return_input:
+        in2 = _suffixed_rows(df2, ev2, suffixes[1]).astype(
+            {sk2 + suffixes[1]: pd.Int64Dtype(), ek2 + suffixes[1]: pd.Int64Dtype()}
+        )
+        in2[lone] = pd.NA
+        pieces.append(("in1", _suffixed_rows(df1, ev1, suffixes[0])))
+        pieces.append(("in2", in2))
+    if return_overlap:
+        lo, hi = np.maximum(a1, a2), np.minimum(b1, b2)
+        have = lo < hi
+        ov = pd.DataFrame(
+            {"have_overlap": have, "overlap_start": np.where(have, lo, None), "overlap_end": np.where(have, hi, None)}
+        ).astype({"have_overlap": pd.BooleanDtype(), "overlap_start": pd.Int64Dtype(), "overlap_end": pd.Int64Dtype()})
+        ov[lone] = pd.NA
+        pieces.append(("ov", ov))
+    if return_distance:
+        gap = np.maximum(np.maximum(0, a1 - b2), np.maximum(0, a2 - b1))
+        dist = pd.DataFrame({"distance": gap}, dtype=pd.Int64Dtype())
+        dist[lone] = pd.NA
+        pieces.append(("d", dist))
+    by_tag = dict(pieces)
+    return pd.concat([by_tag.get(t) for t in ("i1", "in1", "i2", "in2", "ov", "d")], axis=1)
+
+
+# --------------------------------------------------------------------------
+# cluster / merge
+# --------------------------------------------------------------------------
+def _check_min_dist_and_on(df, min_dist, ck, on):
+    if min_dist is not None and min_dist < 0:
+        raise ValueError("min_dist>=0 currently required")
+    group_list = [ck]
+    if on is not None:
+        if not isinstance(on, list):
+            raise ValueError("on=[] must be None or list")
+        if ck in on:
+            raise ValueError("on=[] should not contain chromosome colnames")
+        _verify_columns(df, on)
+        group_list = group_list + on
+    return group_list
+
+
+def _merge_groups(df, group_list, sk, ek, min_dist, want_ids):
+    """One kernel call for all (chrom, *on) groups in sorted key order
+    (`df.groupby(group_list, observed=True).groups`, ops.py:631/772).
+    -> (valid row positions, engine result, group keys)."""
+    codes, keys = _group_keys(df, group_list)
+    has_coords = ~np.asarray(pd.isnull(df[[sk, ek]]).any(axis=1))
+    valid = np.flatnonzero((codes >= 0) & has_coords)
+    md = None if min_dist is None else int(np.floor(min_dist))  # integer coordinates: s > r + d <=> s > r + floor(d)
+    res = _engine.cluster(
+        codes[valid].astype(np.int32),
+        _int64_coords(df, sk)[valid],
+        _int64_coords(df, ek)[valid],
+        max(len(keys), 1),
+        min_dist=md,
+        want_ids=want_ids,
+        want_table=True,
+    )
+    return valid, res, keys
+
+
+def _cluster_table(df, res, keys, group_list, sk, ek):
+    """Frame of merged intervals: group columns, start, end, n_intervals (ops.py:663-674)."""
+    cgrp = _to_host(res["cgrp"]).astype(np.int64)
+    out = {}
+    for pos, col in enumerate(group_list):
+        if len(group_list) == 1:
+            values = [keys[g] for g in cgrp]
+        else:
+            values = [keys[g][pos] for g in cgrp]
+        out[col] = pd.Series(values, dtype=df[col].dtype)
+    out[sk] = _to_host(res["cstart"])
+    out[ek] = _to_host(res["cend"])
+    out["n_intervals"] = _to_host(res["ccount"])
+    return pd.DataFrame(out)
+
+
+def cluster(
+    df,
+    min_dist=0,
+    cols=None,
+    on=None,
+    return_input=True,
+    return_cluster_ids=True,
+    return_cluster_intervals=True,
+):
+    """Cluster overlapping intervals (ops.py:559-708).  Cluster ids follow the
+    groups in sorted key order; rows with a null chromosome/coordinate get one
+    cluster each after all others (ops.py:676-685)."""
+    ck, sk, ek = _get_default_colnames() if cols is None else cols
+    if min_dist is not None and min_dist < 0:
+        raise ValueError("min_dist>=0 currently required")
+    _verify_columns(df, [ck, sk, ek])
+    df = df.reset_index(drop=True)
+    group_list = _check_min_dist_and_on(df, min_dist, ck, on)
+
+    valid, res, keys = _merge_groups(df, group_list, sk, ek, min_dist, want_ids=True)
+    n_clusters = res["n_clusters"]
+    ids = np.full(len(df), -1)
+    ids[valid] = _to_host(res["ids"])
+    null_rows = np.asarray(pd.isnull(df[[sk, ek, *group_list]]).any(axis=1))
+    n_null = int(null_rows.sum())
+    if n_null:
+        ids[null_rows] = n_clusters + np.arange(n_null)
+    assert np.all(ids >= 0)
+
+    out = {}
+    if return_cluster_ids:
+        out["cluster"] = ids
+    if return_cluster_intervals:
+        cs, ce = _to_host(res["cstart"]), _to_host(res["cend"])
+        if n_null:  # null rows are their own "cluster" with their own (null) coordinates
+            cs = pd.array(np.concatenate([cs, np.zeros(n_null, np.int64)]), dtype=pd.Int64Dtype())
+            ce = pd.array(np.concatenate([ce, np.zeros(n_null, np.int64)]), dtype=pd.Int64Dtype())
+            null_s = df.loc[null_rows, sk].astype(pd.Int64Dtype()).values
+            null_e = df.loc[null_rows, ek].astype(pd.Int64Dtype()).values
+            cs[n_clusters:] = null_s
+            ce[n_clusters:] = null_e
+        out["cluster_start"] = cs[ids]
+        out["cluster_end"] = ce[ids]
+    out = pd.DataFrame(out)
+    if return_input:
+        out = pd.concat([df, out], axis="columns")
+    return out
+
+
+def merge(df, min_dist=0, cols=None, on=None):
+    """Merge overlapping intervals (ops.py:711-839): one row per cluster with
+    `n_intervals`; null rows are appended unmerged with n_intervals = NA."""
+    if min_dist is not None and min_dist < 0:
+        raise ValueError("min_dist>=0 currently required")
+    ck, sk, ek = _get_default_colnames() if cols is None else cols
+    checks.is_bedframe(df, raise_errors=True, cols=[ck, sk, ek])
+    df = df.copy()
+    df.reset_index(inplace=True, drop=True)
+    group_list = _check_min_dist_and_on(df, min_dist, ck, on)
+
+    _, res, keys = _merge_groups(df, group_list, sk, ek, min_dist, want_ids=False)
+    parts = [_cluster_table(df, res, keys, group_list, sk, ek)] if res["n_clusters"] else []
+    null_rows = pd.isnull(df[[sk, ek, *group_list]]).any(axis=1)
+    n_null = int(null_rows.sum())
+    if n_null:
+        extra = pd.DataFrame([pd.NA] * n_null, columns=["n_intervals"], index=df.loc[null_rows].index)
+        parts.append(pd.concat([df.loc[null_rows], extra], axis=1))
+    if not parts:
+        raise ValueError("No objects to concatenate")  # what pd.concat([]) raises in the reference
+    clusters = pd.concat(parts).reset_index(drop=True)
+    if n_null:
+        clusters = clusters.astype({sk: pd.Int64Dtype(), ek: pd.Int64Dtype(), "n_intervals": pd.Int64Dtype()})
+    names = list(clusters.keys())
+    return clusters[[ck, sk, ek] + [c for c in names if c not in (ck, sk, ek)]]
+
+
+# --------------------------------------------------------------------------
+# coverage
+# --------------------------------------------------------------------------
+def coverage(df1, df2, suffixes=("", "_"), return_input=True, cols1=None, cols2=None):
+    """Base pairs of every df1 interval covered by df2 (ops.py:842-916).  The
+    reference merges df2, left-overlaps and sums clipped lengths per query; the
+    kernel gets the same integers from prefix sums over the merged targets
+    without enumerating pairs.  Like the reference, resets df1's index in place."""
+    ck1, sk1, ek1 = _get_default_colnames() if cols1 is None else cols1
+    ck2, sk2, ek2 = _get_default_colnames() if cols2 is None else cols2
+    df1.reset_index(inplace=True, drop=True)
+    checks.is_bedframe(df2, raise_errors=True, cols=[ck2, sk2, ek2])  # merge(df2) validates
+    checks.is_bedframe(df1, raise_errors=True, cols=[ck1, sk1, ek1])  # overlap(df1, ...) validates
+
+    codes1, keys1 = _group_keys(df1, [ck1])
+    codes2, keys2 = _group_keys(df2, [ck2])
+    union = sorted(set(keys1) | set(keys2), key=str)
+    rank = {key: r for r, key in enumerate(union)}
+    n_groups = max(len(union), 1)
+    v1 = np.flatnonzero(codes1 >= 0)
+    v2 = np.flatnonzero(codes2 >= 0)
+    t1 = np.array([rank[k] for k in keys1], dtype=np.int32)
+    t2 = np.array([rank[k] for k in keys2], dtype=np.int32)
+    cov = np.zeros(len(df1), dtype=np.int64)
+    if len(v1):
+        got = _engine.coverage(
+            t1[codes1[v1]], _int64_coords(df1, sk1)[v1], _int64_coords(df1, ek1)[v1],
+            t2[codes2[v2]] if len(v2) else np.empty(0, np.int32),
+            _int64_coords(df2, sk2)[v2], _int64_coords(df2, ek2)[v2], n_groups,
+        )
+        cov[v1] = _to_host(got)
+    out = pd.DataFrame({"coverage": pd.Series(cov).astype(df1[sk1].dtype)})
+    if return_input:
+        out = pd.concat([df1, out], axis="columns")
+    return out
+
+
+# --------------------------------------------------------------------------
+# complement
+# --------------------------------------------------------------------------
+def complement(df, view_df=None, view_name_col="name", cols=None, cols_view=None):
+    """Intervals of the view not covered by df (ops.py:1560-1687).  df intervals
+    are first clipped to the view regions they overlap (the reference does that
+    with `overlap(view_df, df, return_overlap=True)`, ops.py:1614-1622), then one
+    kernel call computes the gaps of every region, regions in sorted name order."""
+    from . import _viewframe
+
+    ck, sk, ek = _get_default_colnames() if cols is None else cols
+    _verify_columns(df, [ck, sk, ek])
+    if view_df is None:
+        view_df = {i: _INT64_MAX for i in set(df[ck].dropna().values)}
+    ckv, skv, ekv = _get_default_colnames() if cols_view is None else cols_view
+    view_df = _viewframe.make_viewframe(view_df, view_name_col=view_name_col, cols=[ckv, skv, ekv]).rename(
+        columns=dict(zip([ckv, skv, ekv], [ck, sk, ek]))
+    )
+
+    clipped = overlap(view_df, df, return_overlap=True, how="inner", suffixes=("", "_df"), cols1=cols, cols2=cols)
+    region_of = clipped[view_name_col].values
+    names = sorted(set(view_df[view_name_col]))
+    code = {name: r for r, name in enumerate(names)}
+    first_row = view_df.drop_duplicates(view_name_col).set_index(view_name_col)
+    bounds_lo = np.array([first_row.loc[name, sk] for name in names], dtype=np.int64)
+    bounds_hi = np.array([first_row.loc[name, ek] for name in names], dtype=np.int64)
+    chroms = [first_row.loc[name, ck] for name in names]
+
+    reg, gs, ge = _engine.complement(
+        np.array([code[r] for r in region_of], dtype=np.int32),
+        np.asarray(clipped["overlap_" + sk], dtype=np.int64),
+        np.asarray(clipped["overlap_" + ek], dtype=np.int64),
+        bounds_lo,
+        bounds_hi,
+    )
+    reg = _to_host(reg).astype(np.int64)
+    chrom_col = pd.Series([chroms[r] for r in reg], dtype=view_df[ck].dtype if len(reg) else object)
+    return pd.DataFrame(
+        {ck: chrom_col, sk: _to_host(gs), ek: _to_host(ge), "view_region": [names[r] for r in reg]}
+    ).reset_index(drop=True)

@@ -1,0 +1,90 @@
+"""Frame-level golden outputs from the REFERENCE itself (bioframe v0.8.0 imported
+from /root/reference/src with a stub matplotlib).  Run in the build container only:
+
+    python tests/golden/make_frame_golden.py
+
+Writes tests/golden/frames.pkl: {case name: dict(args..., expected DataFrame)}.
+The reference cannot travel to the GPU box; these fixtures do.  `overlap`
+(how != 'left') and `closest` visit chromosomes in `set` order, which depends on
+PYTHONHASHSEED: the tests compare those frames after a canonical row sort (the
+exact block order is pinned at the index level by frame_cases.npz)."""
+from __future__ import annotations
+
+import os
+import pickle
+import sys
+
+import numpy as np
+import pandas as pd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from make_golden import import_reference  # noqa: E402
+
+
+def frames(rng, n1=60, n2=45, with_na=False, categorical=False):
+    chroms = np.array(["chr1", "chr2", "chrX", "chr10"], dtype=object)
+
+    def one(n, only=None):
+        c = rng.choice(chroms[:3] if only is None else only, n)
+        s = rng.integers(0, 400, n)
+        ln = rng.integers(0, 40, n)
+        strand = rng.choice(np.array(["+", "-", "."], dtype=object), n)
+        return pd.DataFrame({"chrom": c, "start": s, "end": s + ln, "strand": strand, "score": rng.integers(0, 9, n)})
+
+    df1, df2 = one(n1), one(n2, only=chroms[1:])
+    if with_na:
+        for df in (df1, df2):
+            df["start"] = df["start"].astype(pd.Int64Dtype())
+            df["end"] = df["end"].astype(pd.Int64Dtype())
+            df.loc[df.index[::17], ["chrom", "start", "end"]] = pd.NA
+    if categorical:
+        df1["chrom"] = pd.Categorical(df1["chrom"], categories=["chrX", "chr2", "chr1", "chr10"])
+        df2["chrom"] = pd.Categorical(df2["chrom"], categories=["chr10", "chrX", "chr2", "chr1"])
+    return df1, df2
+
+
+def main():
+    bf = import_reference()
+    pd.set_option("future.infer_string", False)
+    rng = np.random.default_rng(2024)
+    cases = {}
+
+    def add(name, fn, **kw):
+        cases[name] = dict(fn=fn, kwargs=kw, expected=getattr(bf, fn)(**{k: (v.copy() if isinstance(v, pd.DataFrame) else v) for k, v in kw.items()}))
+
+    for tag, opts in (("plain", {}), ("na", dict(with_na=True)), ("cat", dict(categorical=True))):
+        df1, df2 = frames(rng, **opts)
+        for how in ("left", "inner", "right", "outer"):
+            add(f"overlap_{tag}_{how}", "overlap", df1=df1, df2=df2, how=how, return_index=True, return_overlap=True)
+        add(f"overlap_{tag}_left_noorder", "overlap", df1=df1, df2=df2, how="left", keep_order=False, suffixes=("_a", "_b"))
+        if tag != "na":
+            add(f"overlap_{tag}_on", "overlap", df1=df1, df2=df2, how="outer", on=["strand"], return_index=True)
+        add(f"cluster_{tag}", "cluster", df=df1)
+        add(f"cluster_{tag}_d5", "cluster", df=df1, min_dist=5)
+        add(f"cluster_{tag}_none", "cluster", df=df1, min_dist=None, return_input=False)
+        add(f"merge_{tag}", "merge", df=df1)
+        add(f"merge_{tag}_d7", "merge", df=df1, min_dist=7)
+        if tag != "na":
+            add(f"cluster_{tag}_on", "cluster", df=df1, on=["strand"])
+            add(f"merge_{tag}_on", "merge", df=df1, on=["strand"], min_dist=None)
+        add(f"coverage_{tag}", "coverage", df1=df1, df2=df2)
+        add(f"closest_{tag}_k1", "closest", df1=df1, df2=df2)
+        add(f"closest_{tag}_k3", "closest", df1=df1, df2=df2, k=3, return_index=True, return_overlap=True)
+        add(f"closest_{tag}_noov", "closest", df1=df1, df2=df2, k=2, ignore_overlaps=True)
+        if tag != "na":
+            add(f"closest_{tag}_strand_up", "closest", df1=df1, df2=df2, k=2, direction_col="strand", ignore_upstream=True)
+            add(f"closest_{tag}_strand_dn", "closest", df1=df1, df2=df2, k=2, direction_col="strand", ignore_downstream=True)
+        add(f"closest_{tag}_self", "closest", df1=df1, df2=None, k=2)
+        add(f"complement_{tag}", "complement", df=df1)
+        view = pd.DataFrame({"chrom": ["chr1", "chr1", "chr2", "chrX", "chr10"], "start": [0, 150, 10, 0, 0],
+                             "end": [120, 500, 300, 350, 80], "name": ["p", "q", "chr2", "x", "ten"]})
+        add(f"complement_{tag}_view", "complement", df=df1, view_df=view)
+        add(f"complement_{tag}_dict", "complement", df=df1, view_df={"chr1": 500, "chr2": 450, "chrX": 10**6, "chr10": 77})
+    with open(os.path.join(HERE, "frames.pkl"), "wb") as f:
+        pickle.dump(cases, f, protocol=4)
+    print(len(cases), "cases ->", os.path.join(HERE, "frames.pkl"))
+
+
+if __name__ == "__main__":
+    main()

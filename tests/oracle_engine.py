@@ -1,0 +1,57 @@
+"""TEST DOUBLE for `bioframe_b200.engine`, backed by the CPU oracle.
+
+The pandas glue of `bioframe_b200.ops` / `core.arrops` cannot reach a GPU in
+the build container; these stand-ins have the engine's signatures and return
+numpy arrays, so the `-m "not gpu"` tests can check the glue (group encoding,
+NA handling, frame assembly, errors) against the reference.  On the GPU box
+the same frame-level tests run with the real engine.  Never imported by the
+product."""
+import numpy as np
+
+from oracle import ops_oracle as oo
+
+
+def _i64(x):
+    return np.asarray(x, dtype=np.int64) if x is not None else None
+
+
+def overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how="inner", closed=False, device=None):
+    s1, e1, s2, e2 = _i64(start1), _i64(end1), _i64(start2), _i64(end2)
+    ev1, ev2 = oo.overlap_intidxs_coded(grp1, s1, e1, grp2, s2, e2, n_groups, how=how, closed=closed)
+    return ev1, ev2, int(((ev1 >= 0) & (ev2 >= 0)).sum())
+
+
+def closest_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, k=1, ignore_overlaps=False,
+                    ignore_upstream=False, ignore_downstream=False, along=None, self_closest=False, device=None):
+    ev1, ev2 = oo.closest_intidxs_coded(
+        grp1, _i64(start1), _i64(end1), grp2, _i64(start2), _i64(end2), n_groups, k=k,
+        ignore_overlaps=ignore_overlaps, ignore_upstream=ignore_upstream, ignore_downstream=ignore_downstream,
+        along=along, self_closest=self_closest,
+    )
+    return ev1, ev2, int((ev2 >= 0).sum())
+
+
+def cluster(grp, start, end, n_groups, min_dist=0, want_ids=True, want_table=True, want_row_spans=False, device=None):
+    s, e = _i64(start), _i64(end)
+    ids, cs, ce, cn = oo.cluster_coded(grp, s, e, n_groups, min_dist)
+    out = dict(ids=ids if (want_ids or want_row_spans) else None, n_clusters=len(cs), cgrp=None, cstart=None,
+               cend=None, ccount=None, row_start=None, row_end=None)
+    if want_table:
+        out.update(cgrp=oo.cluster_coded.last_groups.astype(np.int32), cstart=cs, cend=ce, ccount=cn)
+    if want_row_spans:
+        out.update(row_start=cs[ids], row_end=ce[ids])
+    return out
+
+
+def coverage(grp1, start1, end1, grp2, start2, end2, n_groups, device=None):
+    return oo.coverage_coded(grp1, _i64(start1), _i64(end1), grp2, _i64(start2), _i64(end2), n_groups)
+
+
+def complement(region, start, end, bounds_lo, bounds_hi, device=None):
+    b0, b1 = _i64(bounds_lo), _i64(bounds_hi)
+    if len(b0) == 0:
+        z = np.empty(0, np.int64)
+        return z.astype(np.int32), z, z
+    region = np.zeros(len(start), np.int32) if region is None else np.asarray(region)
+    oc, os_, oe = oo.complement_core(region, _i64(start), _i64(end), list(zip(b0.tolist(), b1.tolist())))
+    return oc.astype(np.int32), os_, oe

@@ -1,0 +1,55 @@
+"""pytest plugin (loaded with `-p refsuite_plugin`) that runs the REFERENCE's own test files
+against this repo's implementation: the reference package is imported from /root/reference/src (with a
+stub matplotlib) and its six hot-path operations plus the two `_intidxs` helpers are replaced by
+`bioframe_b200.ops`, so `bioframe.overlap(...)` in a reference test calls our glue -> our engine.
+Derived reference ops (subtract, setdiff, count_overlaps, trim, ...) then run on top of ours too.
+Without a GPU the engine is the oracle-backed test double (tests/oracle_engine.py): that checks the
+pandas glue; with a GPU it is the CUDA engine."""
+import os
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SRC = "/root/reference/src"
+
+
+def _install():
+    sys.dont_write_bytecode = True
+    if os.environ.get("REFSUITE_INFER_STRING", "0") == "0":
+        # pandas 3 infers str columns as StringDtype; three reference tests expect object dtype
+        import pandas as pd
+
+        pd.set_option("future.infer_string", False)
+    stub = tempfile.mkdtemp(prefix="mplstub")
+    os.makedirs(os.path.join(stub, "matplotlib"))
+    for name, body in (("__init__", ""), ("pyplot", ""), ("colors", "def to_rgb(c):\n    return (0.0, 0.0, 0.0)\n")):
+        with open(os.path.join(stub, "matplotlib", name + ".py"), "w") as f:
+            f.write(body)
+    sys.path[:0] = [stub, REF_SRC, ROOT, os.path.join(ROOT, "tests")]
+    import bioframe
+    import bioframe.ops as ref_ops
+
+    import bioframe_b200.core.arrops as our_arrops
+    import bioframe_b200.ops as our_ops
+
+    use_gpu = False
+    try:
+        import torch
+
+        use_gpu = torch.cuda.is_available()
+    except Exception:
+        pass
+    if not use_gpu:
+        import oracle_engine
+
+        our_ops._engine = oracle_engine
+        our_arrops._engine = oracle_engine
+    for name in ("overlap", "closest", "cluster", "merge", "complement", "coverage",
+                 "_overlap_intidxs", "_closest_intidxs"):
+        setattr(ref_ops, name, getattr(our_ops, name))
+        if hasattr(bioframe, name):
+            setattr(bioframe, name, getattr(our_ops, name))
+    print(f"[refsuite] reference ops patched with bioframe_b200 ({'CUDA engine' if use_gpu else 'oracle test double'})")
+
+
+_install()
