@@ -71,7 +71,10 @@ __global__ void __launch_bounds__(SC_THREADS)
     cluster_scan_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, KeyLayout L, u64 min_dist,
                         int has_min_dist, ScanState ss_max, ScanState ss_sum, i64* __restrict__ ids_out,
                         ClusterTable tab) {
-  __shared__ u64 s_k[SC_TILE + 2];  // [0] row before the tile, [1..rows] tile, [rows+1] row after
+  // [0] row before the tile, [1..rows] tile, [rows+1] row after; one pad slot every 8 entries so that
+  // threads reading 8 consecutive rows each do not collide on the shared-memory banks
+  __shared__ u64 s_kp[SC_TILE + 2 + (SC_TILE + 2) / 8 + 1];
+#define s_k(i) s_kp[(i) + ((i) >> 3)]
   __shared__ u64 s_tmp[8];
   __shared__ u64 s_pre[2];
   __shared__ u32 s_ticket;
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(SC_THREADS)
   const u64 rows = n - base < (u64)SC_TILE ? n - base : (u64)SC_TILE;
   for (u32 i = tid; i < rows + 2; i += SC_THREADS) {
     const i64 p = (i64)base + i - 1;
-    s_k[i] = (p >= 0 && (u64)p < n) ? keys[p] : 0ull;
+    s_k(i) = (p >= 0 && (u64)p < n) ? keys[p] : 0ull;
   }
   __syncthreads();
 
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(SC_THREADS)
 #pragma unroll
   for (int j = 0; j < SC_IPT; ++j) {
     const u32 r = r0 + j;
-    const u64 v = r < rows ? key_ce(s_k[r + 1], L) : 0ull;
+    const u64 v = r < rows ? key_ce(s_k(r + 1), L) : 0ull;
     tmax = v > tmax ? v : tmax;
     rm[j] = tmax;
   }
@@ -107,14 +110,14 @@ __global__ void __launch_bounds__(SC_THREADS)
 
   // ---- group of each row (binary search once per thread, then advance), borders ----
   u32 rk[SC_IPT + 2];  // [0] row before the thread's first, [1..IPT] own rows, [IPT+1] row after
-  rk[0] = r0 < rows ? rank_of_cs(key_cs(s_k[r0], L), L) : 0u;
+  rk[0] = r0 < rows ? rank_of_cs(key_cs(s_k(r0), L), L) : 0u;
   u32 bmask = 0;
 #pragma unroll
   for (int j = 0; j < SC_IPT; ++j) {
     const u32 r = r0 + j;
     rk[j + 1] = rk[j];
     if (r < rows) {
-      const u64 cs = key_cs(s_k[r + 1], L);
+      const u64 cs = key_cs(s_k(r + 1), L);
       rk[j + 1] = advance_rank(rk[j], cs, L);
       const u64 prev_rm = j == 0 ? before : (rm[j - 1] > before ? rm[j - 1] : before);
       const bool first_row = base + r == 0;
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(SC_THREADS)
     const u32 r = r0 + j;
     if (r < rows) {
       const u64 k = base + r;
-      const u64 key = s_k[r + 1];
+      const u64 key = s_k(r + 1);
       if (bmask & (1u << j)) ++seen;
       const u64 id = seen - 1;
       const u32 rank = rk[j + 1];
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(SC_THREADS)
       }
       bool closes = k + 1 == n;
       if (!closes) {
-        const u64 ncs = key_cs(s_k[r + 2], L);
+        const u64 ncs = key_cs(s_k(r + 2), L);
         closes = advance_rank(rank, ncs, L) != rank || gap_opens_cluster(ncs, run, min_dist, has_min_dist);
       }
       if (closes) tab.cend[id] = (i64)(run - gbase + L.cmin);
@@ -159,6 +162,7 @@ __global__ void __launch_bounds__(SC_THREADS)
   }
   if (base + rows == n && tid == 0) *tab.n_clusters = (i64)(s_pre[1] + tot);
 }
+#undef s_k
 
 __global__ void __launch_bounds__(256)
     cluster_emit_kernel(ClusterTable tab, i64 n_clusters, i64 n, i32* __restrict__ cgrp_out,

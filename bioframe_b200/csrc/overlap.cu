@@ -53,6 +53,7 @@ struct OverlapWS {
   i64 *ubase1, *ubase2;  // first output row of the group's unpaired blocks
   i64 *ustart1, *ustart2;  // first index of the group in the partitioned unpaired lists
   i64 *partA, *partB;    // merge-path partition of the emit blocks
+  i32 *pgrpA, *pgrpB;    // group of the first output of every emit block
   i64 *header;           // n_rows, n_pairs, nU1, nU2
   u64 *nU;               // [2] device-side unpaired totals (sort sizes)
 };
@@ -97,6 +98,8 @@ static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS*
   w->ustart2 = a.take<i64>(nb + 1);
   w->partA = a.take<i64>(EMIT_CHUNK_BLOCKS + 1);
   w->partB = a.take<i64>(EMIT_CHUNK_BLOCKS + 1);
+  w->pgrpA = a.take<i32>(EMIT_CHUNK_BLOCKS + 1);
+  w->pgrpB = a.take<i32>(EMIT_CHUNK_BLOCKS + 1);
   w->header = a.take<i64>(8);
   w->nU = a.take<u64>(2);
 }
@@ -469,66 +472,71 @@ constexpr int EM_THREADS = 256;
 constexpr int EM_IPT = 8;
 constexpr int EM_TILE = EM_THREADS * EM_IPT;
 
-// part[b] = owner rows consumed before diagonal b * EM_TILE = #{p : p + scan[p] < D}.
-// One thread per block boundary, so the ~27-step searches of all blocks run
-// side by side instead of at the head of every emit block.
+// part[b] = owner rows consumed before diagonal b * EM_TILE = #{p : p + scan[p] < D};
+// pgrp[b] = group of the first output of block b.  One thread per block
+// boundary, so the ~27-step searches of all blocks run side by side instead of
+// at the head of every emit block.
 __global__ void __launch_bounds__(256) emit_partition_kernel(const ScanView scan, i64 n_owner, i64 total,
-                                                             i64 block0, i64 nparts, i64* __restrict__ part) {
+                                                             i64 block0, i64 nparts, const i64* __restrict__ cum,
+                                                             i32 nb, i64* __restrict__ part, i32* __restrict__ pgrp) {
   const i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nparts) return;
   const i64 W = n_owner + total;
   i64 D = (block0 + b) * EM_TILE;
   if (D > W) D = W;
-  part[b] = lower_bound_by(0, n_owner, [&](i64 p) { return p + scan.at(p) < D; });
+  const i64 p = lower_bound_by(0, n_owner, [&](i64 q) { return q + scan.at(q) < D; });
+  part[b] = p;
+  const i64 t = D - p;  // outputs before the diagonal
+  pgrp[b] = (i32)(lower_bound_by(0, nb, [&](i64 c) { return cum[c] <= t; }) - 1);  // last c with cum[c] <= t
 }
+
+struct EmitItem {  // one owner row staged in shared memory
+  u32 src;  // lo - (first output slot of the row in this block), wrapping: partner = other_id[src + slot]
+  u32 id;   // row id of the owner
+};
 
 template <bool B_SIDE>
 __global__ void __launch_bounds__(EM_THREADS, 6)
     emit_pairs_kernel(const ScanView scan, const u32* __restrict__ lo, i64 n_owner,
                       const u32* __restrict__ owner_id, const u32* __restrict__ other_id, i64 total,
-                      i64 block0, const i64* __restrict__ part, const i64* __restrict__ cum, const i64* __restrict__ delta,
-                      i32 nb, i64* __restrict__ ev1, i64* __restrict__ ev2) {
+                      i64 block0, const i64* __restrict__ part, const i32* __restrict__ pgrp,
+                      const i64* __restrict__ cum, const i64* __restrict__ delta, i32 nb, i64* __restrict__ ev1,
+                      i64* __restrict__ ev2) {
   __shared__ i32 s_rel[EM_TILE + 2];  // scan[first_item + i] - t0, clamped to 32 bits
-  __shared__ u32 s_lo[EM_TILE + 2];
-  __shared__ u32 s_id[EM_TILE + 2];
-  __shared__ u32 s_owner[EM_TILE];
-  __shared__ i64 s_br[4];
+  __shared__ EmitItem s_item[EM_TILE + 2];
+  __shared__ u32 s_owner[EM_TILE + EM_TILE / 8];  // padded: 8 consecutive slots per thread without bank conflicts
   __shared__ u32 s_wmax[EM_THREADS / 32];
   const u32 tid = threadIdx.x;
   const i64 W = n_owner + total;
   const i64 D0 = (block0 + (i64)blockIdx.x) * EM_TILE;
   const i64 D1 = D0 + EM_TILE < W ? D0 + EM_TILE : W;
-  auto group_of = [&](i64 t, i64 a, i64 b) {  // last c with cum[c] <= t
-    return lower_bound_by(a, b, [&](i64 c) { return cum[c] <= t; }) - 1;
-  };
-  if (tid == 0) {
-    s_br[0] = part[blockIdx.x];
-    s_br[1] = part[blockIdx.x + 1];
-  }
-  __syncthreads();
-  const i64 p0 = s_br[0], p1 = s_br[1];
+  // every thread reads the block's partition entries itself (broadcast loads, no barrier)
+  const i64 p0 = part[blockIdx.x], p1 = part[blockIdx.x + 1];
+  const i32 c_lo = pgrp[blockIdx.x], c_hi = pgrp[blockIdx.x + 1];  // c_hi: upper bound of the last output's group
   const i64 t0 = D0 - p0, t1 = D1 - p1;
   const i32 nout = (i32)(t1 - t0);
   if (nout <= 0) return;
-  if (tid == 64) s_br[2] = group_of(t0, 0, nb);
-  if (tid == 96) s_br[3] = group_of(t1 - 1, 0, nb);
   const i64 first = p0 > 0 ? p0 - 1 : 0;  // owner of the first output may have started earlier
   const i32 nitems = (i32)(p1 - first);
   for (i32 i = tid; i <= nitems; i += EM_THREADS) {
     // only offsets in [0, nout] are ever used exactly; the first owner may have started up to
     // 2^31 - 1 outputs earlier (a row has < 2^31 partners), later owners may start far ahead
-    const i64 rel = scan.at(first + i) - t0;
-    s_rel[i] = rel > 0x7fffffffLL ? 0x7fffffff : (i32)rel;
+    const i64 rel64 = scan.at(first + i) - t0;
+    const i32 rel = rel64 > 0x7fffffffLL ? 0x7fffffff : (i32)rel64;
+    s_rel[i] = rel;
     if (i < nitems) {
-      s_lo[i] = lo[first + i];
-      s_id[i] = owner_id[first + i];
+      EmitItem it;
+      it.src = lo[first + i] - (u32)rel;
+      it.id = owner_id[first + i];
+      s_item[i] = it;
     }
   }
-  for (i32 x = tid; x < EM_TILE; x += EM_THREADS) s_owner[x] = 0;
+#define EM_PAD(x) ((x) + ((x) >> 3))
+  for (i32 x = tid; x < EM_TILE; x += EM_THREADS) s_owner[EM_PAD(x)] = 0;
   __syncthreads();
   for (i32 i = tid; i < nitems; i += EM_THREADS) {
     const i32 r = s_rel[i];
-    if (s_rel[i + 1] > r && r >= 0 && r < nout) s_owner[r] = (u32)i;
+    if (s_rel[i + 1] > r && r >= 0 && r < nout) s_owner[EM_PAD(r)] = (u32)i;
   }
   __syncthreads();
   {  // inclusive running max over the 2048 slots, 8 consecutive slots per thread
@@ -536,7 +544,7 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
     u32 run = 0;
 #pragma unroll
     for (int j = 0; j < EM_IPT; ++j) {
-      v[j] = s_owner[tid * EM_IPT + j];
+      v[j] = s_owner[tid * (EM_IPT + 1) + j];
       run = v[j] > run ? v[j] : run;
       v[j] = run;
     }
@@ -555,12 +563,17 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
     for (int i = 0; i < EM_THREADS / 32; ++i)
       if ((u32)i < w) before = s_wmax[i] > before ? s_wmax[i] : before;
 #pragma unroll
-    for (int j = 0; j < EM_IPT; ++j) s_owner[tid * EM_IPT + j] = v[j] > before ? v[j] : before;
+    for (int j = 0; j < EM_IPT; ++j) s_owner[tid * (EM_IPT + 1) + j] = v[j] > before ? v[j] : before;
   }
   __syncthreads();
-  const i64 c_lo = s_br[2], c_hi = s_br[3];
+  auto group_of = [&](i64 t, i64 a, i64 b) {  // last c with cum[c] <= t
+    return lower_bound_by(a, b, [&](i64 c) { return cum[c] <= t; }) - 1;
+  };
+  // outputs of one group (nearly every block): row = t0 + delta[group] + slot
+  const bool one_group = c_lo == c_hi;
+  i64* const out1 = ev1 + (t0 + delta[c_lo]);
+  i64* const out2 = ev2 + (t0 + delta[c_lo]);
   // gathers of 4 outputs in flight before their stores
-  const i64 d_lo = delta[c_lo];
 #pragma unroll 1
   for (int h = 0; h < EM_IPT; h += 4) {
     u32 own[4], oth[4];
@@ -570,23 +583,29 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
       own[j] = 0;
       oth[j] = 0;
       if (x < nout) {
-        const u32 i = s_owner[x];
-        const i64 k = (i64)x - (i64)s_rel[i];
-        own[j] = s_id[i];
-        oth[j] = other_id[(i64)s_lo[i] + k];
+        const EmitItem it = s_item[s_owner[EM_PAD(x)]];
+        own[j] = it.id;
+        oth[j] = other_id[it.src + (u32)x];
       }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const i32 x = (h + j) * EM_THREADS + (i32)tid;
       if (x < nout) {
-        const i64 t = t0 + x;
-        const i64 row = t + ((c_lo == c_hi) ? d_lo : delta[group_of(t, c_lo, c_hi + 1)]);
-        ev1[row] = B_SIDE ? (i64)oth[j] : (i64)own[j];
-        ev2[row] = B_SIDE ? (i64)own[j] : (i64)oth[j];
+        const i64 a = B_SIDE ? (i64)oth[j] : (i64)own[j], b = B_SIDE ? (i64)own[j] : (i64)oth[j];
+        if (one_group) {
+          out1[x] = a;
+          out2[x] = b;
+        } else {
+          const i64 t = t0 + x;
+          const i64 row = t + delta[group_of(t, c_lo, (i64)c_hi + 1)];
+          ev1[row] = a;
+          ev2[row] = b;
+        }
       }
     }
   }
+#undef EM_PAD
 }
 
 // ---- unpaired rows: compaction in row order -> stable partition by group ----
@@ -855,21 +874,24 @@ static int overlap_emit_impl(const OverlapPlan* plan, void* ws_ptr, i64* ev1, i6
     const SetWS& sw = w.s[side];
     const ScanView scan = {sw.tilepre, sw.loc, n_owner, side ? plan->shift2 : plan->shift1};
     i64* part = side ? w.partB : w.partA;
+    i32* pgrp = side ? w.pgrpB : w.pgrpA;
+    const i64* cum = side ? w.cumB : w.cumA;
+    const i64* delta = side ? w.deltaB : w.deltaA;
     const i64 blocks = ceil_div(n_owner + total, EM_TILE);
     for (i64 b0 = 0; b0 < blocks; b0 += EMIT_CHUNK_BLOCKS) {
       const i64 nb_chunk = blocks - b0 < EMIT_CHUNK_BLOCKS ? blocks - b0 : EMIT_CHUNK_BLOCKS;
       BF_LAUNCH(PC_EMIT, 0, st,
                 emit_partition_kernel<<<(unsigned)ceil_div(nb_chunk + 1, 256), 256, 0, st>>>(scan, n_owner, total, b0,
-                                                                                            nb_chunk + 1, part));
+                                                                                            nb_chunk + 1, cum, plan->nb, part, pgrp));
       const u64 bytes = (u64)(20.0 * (double)total * (double)nb_chunk / (double)blocks);
       if (side == 0) {
         BF_LAUNCH(PC_EMIT, bytes, st,
                   emit_pairs_kernel<false><<<(unsigned)nb_chunk, EM_THREADS, 0, st>>>(
-                      scan, sw.lo, n_owner, plan->id1, plan->id2, total, b0, part, w.cumA, w.deltaA, plan->nb, ev1, ev2));
+                      scan, sw.lo, n_owner, plan->id1, plan->id2, total, b0, part, pgrp, cum, delta, plan->nb, ev1, ev2));
       } else {
         BF_LAUNCH(PC_EMIT, bytes, st,
                   emit_pairs_kernel<true><<<(unsigned)nb_chunk, EM_THREADS, 0, st>>>(
-                      scan, sw.lo, n_owner, plan->id2, plan->id1, total, b0, part, w.cumB, w.deltaB, plan->nb, ev1, ev2));
+                      scan, sw.lo, n_owner, plan->id2, plan->id1, total, b0, part, pgrp, cum, delta, plan->nb, ev1, ev2));
       }
     }
   }

@@ -66,8 +66,14 @@ __device__ __forceinline__ u32 tie_scan_tile(u64* __restrict__ keys, u32* __rest
   u32 mask = 0;
 #pragma unroll 1
   for (int j = 0; j < SC_IPT; ++j) {
-    const u32 r = tid * SC_IPT + j;  // row inside the tile, s_k index r + TIE_HALO
-    if (r >= rows) break;
+    // row inside the tile (s_k index r + TIE_HALO).  The fix pass only counts, so its threads take
+    // strided rows (conflict-free shared-memory reads); the gather pass needs consecutive rows per
+    // thread for the ordered compaction.
+    const u32 r = FIX ? (u32)j * SC_THREADS + tid : tid * SC_IPT + j;
+    if (r >= rows) {
+      if (FIX) continue;
+      break;
+    }
     const u32 at = r + TIE_HALO;
     const u64 c = key_cs(s_k[at], L);
     const bool prev_same = (base + r > 0) && key_cs(s_k[at - 1], L) == c;

@@ -1,0 +1,66 @@
+"""Query-sharded overlap across the GPUs of one box.
+
+One process per GPU (`torch.distributed`, backend nccl; gloo in the CPU tests).  The
+query set is split into contiguous row ranges, one per rank; the smaller target
+set is replicated with ONE broadcast from `src` (NCCL over NVLink); every rank
+runs the single-GPU engine on (its queries) x (all targets); the only other
+communication is an all-gather of the per-rank row counts so that every rank
+knows the offset of its slice in the concatenated result.  Any partition of the
+queries is valid because every query-side quantity depends only on the
+replicated targets.
+
+Row order of the concatenated result: rank-major, inside a rank the reference's
+order for that shard.  For how='left' the frame-level `keep_order=True` sort
+(by query row, then target row) makes the final frame identical to the
+single-GPU one; for the other joins the pair SET is identical and the order is
+(shard, group, A-block, B-block)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n, world):
+    """Contiguous, balanced row ranges: rank r owns [bounds[r], bounds[r+1])."""
+    base, extra = divmod(int(n), int(world))
+    sizes = [base + (1 if r < extra else 0) for r in range(world)]
+    return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+
+
+def broadcast_targets(tensors, src=0, group=None):
+    """Replicate the target columns (same shapes allocated on every rank) from `src`."""
+    for t in tensors:
+        if t is not None:
+            dist.broadcast(t, src=src, group=group)
+    return tensors
+
+
+def overlap_sharded(grp1, start1, end1, row_offset, grp2, start2, end2, n_groups, how="left", engine=None,
+                    group=None, broadcast=True, src=0):
+    """This rank's slice of `_overlap_intidxs` over the union of all ranks' queries.
+
+    grp1/start1/end1: this rank's query shard (rows [row_offset, row_offset + n_local) of the full set).
+    grp2/start2/end2: target columns; valid on `src`, allocated (any content) elsewhere when broadcast=True.
+    Returns (events1 with GLOBAL query row numbers, events2, offset of this slice in the concatenated
+    result, total rows over all ranks)."""
+    if engine is None:
+        from . import engine as engine  # the CUDA engine; tests inject an oracle-backed double
+    if how in ("right", "outer"):
+        raise ValueError("query-sharded overlap supports how='inner' and how='left' (unpaired targets need a reduction)")
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world > 1 and broadcast:
+        broadcast_targets([grp2, start2, end2], src=src, group=group)
+    ev1, ev2, _ = engine.overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how=how)
+    ev1 = torch.as_tensor(ev1)
+    ev2 = torch.as_tensor(ev2)
+    ev1 = torch.where(ev1 >= 0, ev1 + int(row_offset), ev1)
+    n_local = torch.tensor([ev1.numel()], dtype=torch.int64, device=ev1.device)
+    if world > 1:
+        counts = [torch.zeros_like(n_local) for _ in range(world)]
+        dist.all_gather(counts, n_local, group=group)
+        counts = [int(c.item()) for c in counts]
+    else:
+        counts = [int(n_local.item())]
+    return ev1, ev2, int(sum(counts[:rank])), int(sum(counts))

@@ -22,13 +22,24 @@ sys.path.insert(0, HERE)
 from make_golden import import_reference  # noqa: E402
 
 
-def frames(rng, n1=60, n2=45, with_na=False, categorical=False):
+def frames(rng, n1=60, n2=45, with_na=False, categorical=False, tie_free=False):
+    """tie_free: unique starts and unique ends (closest picks among targets with equal end / equal
+    start through an unstable argsort in the reference, so only tie-free inputs have a defined answer)"""
     chroms = np.array(["chr1", "chr2", "chrX", "chr10"], dtype=object)
 
     def one(n, only=None):
         c = rng.choice(chroms[:3] if only is None else only, n)
-        s = rng.integers(0, 400, n)
-        ln = rng.integers(0, 40, n)
+        if tie_free:
+            s = rng.choice(np.arange(0, 4000, 7), n, replace=False)  # multiples of 7
+            ln = 1 + 7 * rng.integers(0, 6, n) + rng.integers(0, 6, n)  # end = 7a + r, r in 1..6 -> unique per start
+            e = s + ln
+            while len(set(e)) < n:  # re-draw colliding ends
+                dup = pd.Series(e).duplicated().values
+                e[dup] = s[dup] + 1 + rng.integers(0, 60, dup.sum())
+            ln = e - s
+        else:
+            s = rng.integers(0, 400, n)
+            ln = rng.integers(0, 40, n)
         strand = rng.choice(np.array(["+", "-", "."], dtype=object), n)
         return pd.DataFrame({"chrom": c, "start": s, "end": s + ln, "strand": strand, "score": rng.integers(0, 9, n)})
 
@@ -69,6 +80,7 @@ def main():
             add(f"cluster_{tag}_on", "cluster", df=df1, on=["strand"])
             add(f"merge_{tag}_on", "merge", df=df1, on=["strand"], min_dist=None)
         add(f"coverage_{tag}", "coverage", df1=df1, df2=df2)
+        df1, df2 = frames(rng, tie_free=True, **opts)
         add(f"closest_{tag}_k1", "closest", df1=df1, df2=df2)
         add(f"closest_{tag}_k3", "closest", df1=df1, df2=df2, k=3, return_index=True, return_overlap=True)
         add(f"closest_{tag}_noov", "closest", df1=df1, df2=df2, k=2, ignore_overlaps=True)

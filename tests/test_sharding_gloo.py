@@ -1,0 +1,90 @@
+"""N>1 host logic of the query-sharded overlap (bioframe_b200/sharded.py) with world_size 2 on CPU
+(gloo).  The per-rank engine is the oracle-backed test double; what is checked is the sharding, the
+target broadcast, the row offsets and that the concatenated pairs equal the single-process result."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+from conftest import ROOT  # noqa: E402
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, how, out_dir):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    import oracle_engine
+    from bioframe_b200 import sharded, synth
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g1, s1, e1 = synth.make_intervals(6000, 1)
+        g2, s2, e2 = synth.make_intervals(2500, 2)
+        s1, e1, s2, e2 = s1 // 3000, e1 // 3000 + 1, s2 // 3000, e2 // 3000 + 1
+        b = sharded.shard_bounds(len(s1), world)
+        lo, hi = int(b[rank]), int(b[rank + 1])
+        # targets: real data on rank 0 only, garbage elsewhere until the broadcast
+        t = [torch.from_numpy(x.copy()) for x in (g2, s2, e2)]
+        if rank != 0:
+            for x in t:
+                x.zero_()
+        ev1, ev2, off, total = sharded.overlap_sharded(
+            torch.from_numpy(g1[lo:hi]), torch.from_numpy(s1[lo:hi]), torch.from_numpy(e1[lo:hi]), lo,
+            t[0], t[1], t[2], 24, how=how, engine=_TensorEngine(oracle_engine))
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), ev1=ev1.numpy(), ev2=ev2.numpy(), off=off, total=total)
+    finally:
+        dist.destroy_process_group()
+
+
+class _TensorEngine:
+    """oracle double taking torch CPU tensors"""
+
+    def __init__(self, mod):
+        self.mod = mod
+
+    def overlap_intidxs(self, g1, s1, e1, g2, s2, e2, nb, how="inner", closed=False):
+        a, b, n = self.mod.overlap_intidxs(g1.numpy(), s1.numpy(), e1.numpy(), g2.numpy(), s2.numpy(), e2.numpy(), nb,
+                                           how=how, closed=closed)
+        return torch.from_numpy(a), torch.from_numpy(b), n
+
+
+@pytest.mark.parametrize("how", ["inner", "left"])
+def test_sharded_overlap_world2(how, tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), how, str(tmp_path)), nprocs=world, join=True)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from bioframe_b200 import synth
+    from oracle import ops_oracle as oo
+
+    parts = [np.load(os.path.join(str(tmp_path), f"r{r}.npz")) for r in range(world)]
+    assert parts[0]["off"] == 0 and parts[1]["off"] == len(parts[0]["ev1"])
+    assert parts[0]["total"] == parts[1]["total"] == sum(len(p["ev1"]) for p in parts)
+    ev1 = np.concatenate([p["ev1"] for p in parts])
+    ev2 = np.concatenate([p["ev2"] for p in parts])
+    g1, s1, e1 = synth.make_intervals(6000, 1)
+    g2, s2, e2 = synth.make_intervals(2500, 2)
+    s1, e1, s2, e2 = s1 // 3000, e1 // 3000 + 1, s2 // 3000, e2 // 3000 + 1
+    o1, o2 = oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, 24, how=how)
+    # same rows; after the (query row, target row) ordering of keep_order=True they are identical arrays
+    got = np.lexsort([ev2, ev1])
+    want = np.lexsort([o2, o1])
+    assert np.array_equal(ev1[got], o1[want]) and np.array_equal(ev2[got], o2[want])
+
+
+def test_shard_bounds():
+    from bioframe_b200 import sharded
+
+    b = sharded.shard_bounds(10, 4)
+    assert list(b) == [0, 3, 6, 8, 10]
+    assert list(sharded.shard_bounds(0, 2)) == [0, 0, 0]
