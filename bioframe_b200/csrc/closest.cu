@@ -170,7 +170,7 @@ __device__ __forceinline__ void closest_probe(const ClosestArgs& A, i64 t, Probe
   const i64 t0 = A.seg[rank], t1 = A.seg[rank + 1];
   P->t0 = t0;
   P->t1 = t1;
-  const i64 a = A.s1[row], b = A.e1[row];
+  const i64 a = A.s1[row], b = min(A.e1[row], L.endcap);  // ends are clamped like the packed ones (keys.cuh)
   const u64 off = L.goff[rank];
   const u64 xs = off + ((u64)a - L.cmin), xe = off + ((u64)b - L.cmin);
   const u64 xe_adj = xe + (a == b);
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256)
   const uint4 qp = qpos[t];
   const i64 loA = qp.x, hiA = qp.y, stop = qp.z, begin = qp.w;
   const i64 t0 = A.seg[rank], t1 = A.seg[rank + 1];
-  const i64 a = A.s1[row], b = A.e1[row];
+  const i64 a = A.s1[row], b = min(A.e1[row], L.endcap);
   const u64 off = L.goff[rank];
   const u64 xs = off + ((u64)a - L.cmin), xe = off + ((u64)b - L.cmin);
   const bool fwd = A.along ? A.along[row] != 0 : true;
@@ -395,7 +395,7 @@ static int closest_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   // layout over both sets (point-adjusted extent so that end' fits), raw lengths in the keys
   const RowSet sets[2] = {{grp1, s1, e1, n1}, {grp2, s2, e2, n2}};
   KeyLayout L;
-  BF_TRY(measure_layout(sets, 2, nb, 1, w.layout, st, &L, "bf_closest_count"));
+  BF_TRY(measure_layout(sets, 2, nb, 1, 1, w.layout, st, &L, "bf_closest_count"));
   if (L.B > 62) {
     set_error("bf_closest_count: coordinate span too wide (%d bits)", L.B);
     return BF_ERR_RANGE;

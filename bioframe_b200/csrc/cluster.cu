@@ -189,7 +189,7 @@ static int cluster_run(const i32* grp, const i64* s, const i64* e, i64 n, i32 nb
                        ClusterWS& w, i64* ids_out, cudaStream_t st, ClusterTable* tab, KeyLayout* L_out) {
   const RowSet sets[1] = {{grp, s, e, n}};
   KeyLayout L;
-  BF_TRY(measure_layout(sets, 1, nb, 0, w.layout, st, &L, "bf_cluster"));
+  BF_TRY(measure_layout(sets, 1, nb, 0, 0, w.layout, st, &L, "bf_cluster"));
   if (L.B > 62) {
     set_error("coordinate span too wide for the running-max scan (%d bits)", L.B);
     return BF_ERR_RANGE;

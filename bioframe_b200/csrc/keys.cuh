@@ -36,6 +36,7 @@ struct KeyLayout {
   i32 nb;         // number of groups
   u64 cmin;       // coordinate origin (two's complement image of the int64 minimum)
   u64 lmask;      // (1 << LB) - 1
+  i64 endcap;     // ends are clamped to this value before packing (I64_MAX: no clamp), see KEY_CLAMP_END
   const u64* goff;  // device [nb+1]: linear offset of every group, goff[nb] = total span
 };
 
@@ -58,8 +59,11 @@ __device__ __forceinline__ u32 key_rank(u64 k, const KeyLayout& L) { return rank
 
 struct Extent {  // device-side reduction target
   i64 cmin, cmax;
-  i64 lmin, lmax;  // min / max of end' - start
+  i64 smax;        // largest start
+  u64 lmax;        // largest end' - start (exact in unsigned arithmetic for any int64 pair with end >= start)
   i32 gmin, gmax;
+  i32 bad, pad;    // bad: some row has end < start
+  i64 endcap;      // in: clamp for the ends when measuring spans (I64_MAX: none); set by the host wrapper
   u64 total;       // sum of the group spans (written by layout_offsets_kernel)
 };
 struct LayoutScratch {
@@ -83,8 +87,10 @@ static __global__ void extent_init_kernel(Extent* x, i64* gmax, i32 nb) {
   if (i == 0) {
     x->cmin = I64_MAX;
     x->cmax = I64_MIN;
-    x->lmin = I64_MAX;
-    x->lmax = I64_MIN;
+    x->smax = I64_MIN;
+    x->lmax = 0;
+    x->bad = 0;
+    x->pad = 0;
     x->gmin = 0x7fffffff;
     x->gmax = (i32)0x80000000;
     x->total = 0;
@@ -107,7 +113,9 @@ static __global__ void __launch_bounds__(256) extent_kernel(const i32* __restric
     __syncthreads();
   }
   i64 lo = I64_MAX, hi = I64_MIN;
-  i64 llo = I64_MAX, lhi = I64_MIN;
+  i64 shi = I64_MIN;
+  u64 lhi = 0;
+  bool bad = false;
   i32 glo = 0x7fffffff, ghi = (i32)0x80000000;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
     i64 a = s[i], b = e[i];
@@ -115,10 +123,10 @@ static __global__ void __launch_bounds__(256) extent_kernel(const i32* __restric
     const i64 top = max(a, b);
     lo = min(lo, min(a, b));
     hi = max(hi, top);
-    // length in wrapping arithmetic; a span that overflows int64 shows up as negative
-    const i64 len = (i64)((u64)b - (u64)a);
-    llo = min(llo, len);
-    lhi = max(lhi, len);
+    shi = max(shi, a);
+    bad |= b < a;
+    const u64 len = (u64)b - (u64)a;  // exact for b >= a, whatever the magnitudes
+    lhi = b < a ? lhi : max(lhi, len);
     i32 g = 0;
     if (grp) {
       g = grp[i];
@@ -131,15 +139,16 @@ static __global__ void __launch_bounds__(256) extent_kernel(const i32* __restric
   for (int o = 16; o > 0; o >>= 1) {
     lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    llo = min(llo, __shfl_xor_sync(0xffffffffu, llo, o));
+    shi = max(shi, __shfl_xor_sync(0xffffffffu, shi, o));
     lhi = max(lhi, __shfl_xor_sync(0xffffffffu, lhi, o));
     glo = min(glo, __shfl_xor_sync(0xffffffffu, glo, o));
     ghi = max(ghi, __shfl_xor_sync(0xffffffffu, ghi, o));
   }
+  if (__any_sync(0xffffffffu, bad) && lane_id() == 0) out->bad = 1;
   if (lane_id() == 0) {
     atomicMin(&out->cmin, lo);
     atomicMax(&out->cmax, hi);
-    atomicMin(&out->lmin, llo);
+    atomicMax(&out->smax, shi);
     atomicMax(&out->lmax, lhi);
     if (grp) {
       atomicMin(&out->gmin, glo);
@@ -156,13 +165,15 @@ static __global__ void __launch_bounds__(256) extent_kernel(const i32* __restric
 // goff[g] = sum of spans of the groups before g; one block, sequential over a
 // few dozen (at most a few thousand) groups per thread chunk.
 static __global__ void __launch_bounds__(1024) layout_offsets_kernel(Extent* __restrict__ x, const i64* __restrict__ gmax,
-                                                                     i32 nb, u64* __restrict__ goff) {
+                                                                     i32 nb, int clamp_ends, u64* __restrict__ goff) {
   __shared__ u64 s_part[1024];
   const u32 tid = threadIdx.x;
   const u64 cmin = (u64)x->cmin;
+  // with clamped ends (overlap / closest) no coordinate above max start + 1 is ever packed
+  const i64 cap = (clamp_ends && x->smax < I64_MAX) ? x->smax + 1 : I64_MAX;
   const i32 per = (nb + 1023) / 1024;
   const i32 lo = tid * per, hi = min(nb, lo + per);
-  auto span = [&](i32 g) -> u64 { return gmax[g] == I64_MIN ? 0ull : (u64)gmax[g] - cmin + 1ull; };
+  auto span = [&](i32 g) -> u64 { return gmax[g] == I64_MIN ? 0ull : (u64)min(gmax[g], cap) - cmin + 1ull; };
   u64 acc = 0;
   for (i32 g = lo; g < hi; ++g) acc += span(g);
   s_part[tid] = acc;
@@ -176,6 +187,7 @@ static __global__ void __launch_bounds__(1024) layout_offsets_kernel(Extent* __r
     }
     goff[nb] = run;
     x->total = run;
+    x->endcap = cap;
   }
   __syncthreads();
   u64 run = s_part[tid];
@@ -186,15 +198,19 @@ static __global__ void __launch_bounds__(1024) layout_offsets_kernel(Extent* __r
 }
 
 static inline int make_key_layout(const Extent& x, i32 n_groups, const u64* goff, KeyLayout* L) {
-  if (x.lmin < 0) {
-    set_error("interval with end < start (or a span beyond int64): not a valid bedframe interval");
+  if (x.bad) {
+    set_error("interval with end < start: not a valid bedframe interval");
     return BF_ERR_ARG;
   }
   // total span = sum over groups of (group max - cmin + 1); 0 when there are no rows
   L->B = bit_width(x.total > 0 ? x.total - 1 : 0);
   if (L->B == 0) L->B = 1;
-  L->LB = bit_width((u64)x.lmax);
+  // longest packed length: bounded by the longest interval and, with clamped ends, by the clamped span
+  u64 lmax = x.lmax;
+  if (x.endcap != I64_MAX && (u64)x.endcap - (u64)x.cmin < lmax) lmax = (u64)x.endcap - (u64)x.cmin;
+  L->LB = bit_width(lmax);
   if (L->LB == 0) L->LB = 1;
+  L->endcap = x.endcap;
   L->rank_bits = n_groups > 1 ? bit_width((u64)(n_groups - 1)) : 0;
   L->total_bits = L->B + L->LB;
   L->nb = n_groups;
@@ -227,8 +243,14 @@ static inline unsigned stream_grid(u64 n, u64 per_block) {
 
 // Coordinate extent + per-group spans of all sets of a call -> key layout.
 // One small D2H copy and one stream synchronisation.
-static int measure_layout(const RowSet* sets, int n_sets, i32 nb, int point_adjust, const LayoutScratch& sc,
-                          cudaStream_t st, KeyLayout* L, const char* who) {
+// clamp_ends (allowed for overlap and closest): when the plain layout does not fit 64 key bits, ends
+// above (largest start + 1) are packed as that value.  An end is only ever compared with starts, so all
+// ends beyond the largest start behave alike; this keeps the INT64_MAX ends that complement / subtract /
+// trim inject (ops.py:1309,1499,1604) packable.  The one thing the clamp can change is the (end', row)
+// order among rows that share a start AND both reach beyond the largest start; the tie fix-up compares
+// the original ends of such rows (sorted_set.cuh).
+static int measure_layout(const RowSet* sets, int n_sets, i32 nb, int point_adjust, int clamp_ends,
+                          const LayoutScratch& sc, cudaStream_t st, KeyLayout* L, const char* who) {
   BF_LAUNCH(PC_EXTENT, 0, st, extent_init_kernel<<<(unsigned)ceil_div(nb + 1, 256), 256, 0, st>>>(sc.extent, sc.gmax, nb));
   const size_t smem = nb <= EXTENT_SMEM_GROUPS ? (size_t)nb * sizeof(i64) : 0;
   i64 total_rows = 0;
@@ -240,20 +262,29 @@ static int measure_layout(const RowSet* sets, int n_sets, i32 nb, int point_adju
               extent_kernel<<<stream_grid((u64)r.n, 1024), 256, smem, st>>>(nb > 1 ? r.grp : nullptr, r.s, r.e, (u64)r.n,
                                                                            point_adjust, nb, sc.extent, sc.gmax));
   }
-  BF_LAUNCH(PC_EXTENT, 0, st, layout_offsets_kernel<<<1, 1024, 0, st>>>(sc.extent, sc.gmax, nb, sc.goff));
-  Extent ext;
-  BF_CUDA(cudaMemcpyAsync(&ext, sc.extent, sizeof(Extent), cudaMemcpyDeviceToHost, st));
-  BF_CUDA(cudaStreamSynchronize(st));
-  if (total_rows == 0) {
-    ext.cmin = ext.cmax = 0;
-    ext.lmin = ext.lmax = 0;
-    ext.total = 0;
+  // first without clamping (the packed lengths then order tied starts exactly as the reference does);
+  // only coordinates that do not fit 64 key bits otherwise -- INT64_MAX ends -- get the clamp
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    BF_LAUNCH(PC_EXTENT, 0, st, layout_offsets_kernel<<<1, 1024, 0, st>>>(sc.extent, sc.gmax, nb, attempt, sc.goff));
+    Extent ext;
+    BF_CUDA(cudaMemcpyAsync(&ext, sc.extent, sizeof(Extent), cudaMemcpyDeviceToHost, st));
+    BF_CUDA(cudaStreamSynchronize(st));
+    if (total_rows == 0) {
+      ext.cmin = ext.cmax = 0;
+      ext.smax = 0;
+      ext.lmax = 0;
+      ext.bad = 0;
+      ext.endcap = I64_MAX;
+      ext.total = 0;
+    }
+    if (nb > 1 && total_rows > 0 && (ext.gmin < 0 || ext.gmax >= nb)) {
+      set_error("%s: group code outside [0,%d): min %d max %d", who, nb, ext.gmin, ext.gmax);
+      return BF_ERR_GROUP;
+    }
+    const int rc = make_key_layout(ext, nb, sc.goff, L);
+    if (rc != BF_ERR_RANGE || !clamp_ends || attempt == 1) return rc;
   }
-  if (nb > 1 && total_rows > 0 && (ext.gmin < 0 || ext.gmax >= nb)) {
-    set_error("%s: group code outside [0,%d): min %d max %d", who, nb, ext.gmin, ext.gmax);
-    return BF_ERR_GROUP;
-  }
-  return make_key_layout(ext, nb, sc.goff, L);
+  return BF_ERR_RANGE;
 }
 
 // key modes (the `point_adjust` argument of pack_keys / sort_rows is a bit set)
@@ -281,6 +312,7 @@ static __global__ void __launch_bounds__(HIST_THREADS) pack_keys_kernel(const i3
       if (ok) {
         i64 a = s[i], b = e[i];
         if ((point_adjust & KEY_POINT_ADJUST) && a == b) b += 1;
+        b = min(b, L.endcap);
         const u64 off = grp ? L.goff[grp[i]] : 0ull;
         const u64 at = (point_adjust & KEY_BY_END) ? (u64)b : (u64)a;  // field the rows are ordered by
         k = ((off + (at - L.cmin)) << L.LB) | ((u64)b - (u64)a);

@@ -765,7 +765,7 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   // ---- coordinate extent, group code check, key layout (one small D2H) ----
   const RowSet sets[2] = {{grp1, s1, e1, n1}, {grp2, s2, e2, n2}};
   KeyLayout L;
-  BF_TRY(measure_layout(sets, 2, nb, 1, w.layout, st, &L, "bf_overlap_count"));
+  BF_TRY(measure_layout(sets, 2, nb, 1, 1, w.layout, st, &L, "bf_overlap_count"));
   plan->L = L;
   // ---- sort both sets ----
   SortResult r1, r2;

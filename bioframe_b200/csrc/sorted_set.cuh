@@ -53,9 +53,15 @@ constexpr int TIE_HALO = TIE_SMALL + 1;
 // Stage a tile's keys (+ halo), measure the run of every tied row; with FIX,
 // sort short runs in place.  Returns the mask of this thread's rows that belong
 // to long runs.
+// `e_raw` is null unless the layout clamps ends (keys.cuh measure_layout): then rows whose keys are
+// equal may still differ in their original ends, which decide their order.
 template <bool FIX>
 __device__ __forceinline__ u32 tie_scan_tile(u64* __restrict__ keys, u32* __restrict__ ids, u64 n, const KeyLayout& L,
-                                             u64 base, u64 rows, u64* s_k) {
+                                             u64 base, u64 rows, u64* s_k, const i64* __restrict__ e_raw) {
+  auto after = [&](u64 k1, u32 v1, u64 k2, u32 v2) {  // (k1, row v1) sorts strictly after (k2, row v2)
+    if (k1 != k2) return k1 > k2;
+    return e_raw ? e_raw[v1] > e_raw[v2] : false;
+  };
   const u32 tid = threadIdx.x;
   // s_k[i] = keys[base - TIE_HALO + i]
   for (u32 i = tid; i < rows + 2 * TIE_HALO; i += SC_THREADS) {
@@ -89,7 +95,9 @@ __device__ __forceinline__ u32 tie_scan_tile(u64* __restrict__ keys, u32* __rest
       // owner of a short run: stable insertion sort of (key, id) by key, in place
       const u64 p0 = base + r;
       if (m == 2) {
-        if (s_k[at] > s_k[at + 1]) {
+        bool swap = s_k[at] > s_k[at + 1];
+        if (e_raw && s_k[at] == s_k[at + 1]) swap = after(s_k[at], ids[p0], s_k[at + 1], ids[p0 + 1]);
+        if (swap) {
           const u32 v0 = ids[p0], v1 = ids[p0 + 1];
           keys[p0] = s_k[at + 1];
           keys[p0 + 1] = s_k[at];
@@ -103,7 +111,7 @@ __device__ __forceinline__ u32 tie_scan_tile(u64* __restrict__ keys, u32* __rest
           const u64 kx = s_k[at + x];
           const u32 vx = ids[p0 + x];
           u32 y = x;
-          while (y > 0 && k[y - 1] > kx) {
+          while (y > 0 && after(k[y - 1], v[y - 1], kx, vx)) {
             k[y] = k[y - 1];
             v[y] = v[y - 1];
             --y;
@@ -123,12 +131,13 @@ __device__ __forceinline__ u32 tie_scan_tile(u64* __restrict__ keys, u32* __rest
 
 // pass 1: fix short runs in place, count rows of long runs per tile
 static __global__ void __launch_bounds__(SC_THREADS)
-    tie_fix_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u64 n, KeyLayout L, u64* __restrict__ spine) {
+    tie_fix_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u64 n, KeyLayout L, const i64* __restrict__ e_raw,
+                   u64* __restrict__ spine) {
   __shared__ u64 s_k[SC_TILE + 2 * TIE_HALO];
   __shared__ u64 s_tmp[8];
   const u64 base = (u64)blockIdx.x * SC_TILE;
   const u64 rows = n - base < (u64)SC_TILE ? n - base : (u64)SC_TILE;
-  const u32 mask = tie_scan_tile<true>(keys, ids, n, L, base, rows, s_k);
+  const u32 mask = tie_scan_tile<true>(keys, ids, n, L, base, rows, s_k, e_raw);
   const u64 c = block_sum_u64((u64)__popc(mask), s_tmp);
   if (threadIdx.x == 0) spine[blockIdx.x] = c;
 }
@@ -145,7 +154,7 @@ static __global__ void __launch_bounds__(SC_THREADS)
   if (next == first) return;  // nearly every tile of real data
   const u64 base = tile * SC_TILE;
   const u64 rows = n - base < (u64)SC_TILE ? n - base : (u64)SC_TILE;
-  const u32 mask = tie_scan_tile<false>(keys, ids, n, L, base, rows, s_k);
+  const u32 mask = tie_scan_tile<false>(keys, ids, n, L, base, rows, s_k, nullptr);
   u64 tot;
   u64 at_out = first + block_excl_sum_u64((u64)__popc(mask), s_tmp, &tot);
 #pragma unroll
@@ -194,7 +203,8 @@ static int sort_rows(const i32* grp, const i64* s, const i64* e, i64 n, const Ke
   u64* tkeyB = ws.tmp8;
   u32* tidB = ws.tmp4a;
   u32* tpos = ws.tmp4b;
-  BF_LAUNCH(PC_TIEFIX, 8 * n, st, tie_fix_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, L, ws.spine));
+  BF_LAUNCH(PC_TIEFIX, 8 * n, st, tie_fix_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, L,
+                                                                             L.endcap != I64_MAX ? e : nullptr, ws.spine));
   BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(ws.spine, (u64)tiles, ws.nT));
   BF_LAUNCH(PC_TIEFIX, 0, st,
             tie_gather_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, L, ws.spine, (u64)tiles, ws.nT,

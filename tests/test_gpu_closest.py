@@ -118,3 +118,18 @@ def test_closest_golden(arrops_golden):
             keep = b.cpu().numpy() >= 0
             assert np.array_equal(a.cpu().numpy()[keep], g[f"{name}/{tag}_1"]), (name, tag)
             assert np.array_equal(b.cpu().numpy()[keep], g[f"{name}/{tag}_2"]), (name, tag)
+
+
+def test_closest_int64_max_ends():
+    from bioframe_b200 import engine
+
+    big = np.iinfo(np.int64).max
+    rng = np.random.default_rng(4)
+    g1, s1, e1 = _rand(rng, 3000, 3, 10**8, 4000)
+    g2, s2, e2 = _rand(rng, 2000, 3, 10**8, 4000)
+    e1[::9] = big
+    e2[::13] = big
+    for kw in (dict(k=2), dict(k=2, ignore_overlaps=True)):
+        got = engine.closest_intidxs(g1, s1, e1, g2, s2, e2, 3, **kw)
+        want = oo.closest_intidxs_coded(g1, s1, e1, g2, s2, e2, 3, **kw)
+        _check(got, want)

@@ -64,3 +64,38 @@ def test_overlap_medium_synthetic():
         o1, o2 = _oracle_frame(g1, s1, e1, g2, s2, e2, 24, how)
         assert np.array_equal(ev1.cpu().numpy(), o1)
         assert np.array_equal(ev2.cpu().numpy(), o2)
+
+
+@pytest.mark.parametrize("how", ["inner", "outer"])
+def test_overlap_int64_max_ends(how):
+    """complement / subtract / trim feed INT64_MAX ends into overlap (ops.py:1309,1499,1604)"""
+    from bioframe_b200 import engine
+
+    big = np.iinfo(np.int64).max
+    rng = np.random.default_rng(9)
+    g1 = np.arange(5, dtype=np.int32)
+    s1 = np.zeros(5, dtype=np.int64)
+    e1 = np.full(5, big, dtype=np.int64)  # a view: one whole-chromosome region per group
+    g2, s2, e2 = _rand(rng, 4000, 5, 10**9, 5000)
+    e2[::7] = big
+    s2[::11] -= 10**6  # negative starts are legal
+    ev1, ev2, _ = engine.overlap_intidxs(g1, s1, e1, g2, s2, e2, 5, how=how)
+    o1, o2 = _oracle_frame(g1, s1, e1, g2, s2, e2, 5, how)
+    assert np.array_equal(ev1.cpu().numpy(), o1)
+    assert np.array_equal(ev2.cpu().numpy(), o2)
+
+
+def test_overlap_clamped_tie_order():
+    """rows sharing a start whose ends all lie beyond the largest start: the clamp (INT64_MAX present)
+    must not change their (end, row) order"""
+    from bioframe_b200 import engine
+
+    big = np.iinfo(np.int64).max
+    s1 = np.array([10, 10, 10, 10, 3, 3, 10], dtype=np.int64)
+    e1 = np.array([big, 500, 400, big - 5, 900, 800, 450], dtype=np.int64)
+    s2 = np.array([0, 5, 12, 12], dtype=np.int64)
+    e2 = np.array([big, 20, 13, big - 1], dtype=np.int64)
+    for how in ("inner", "outer"):
+        ev1, ev2, _ = engine.overlap_intidxs(None, s1, e1, None, s2, e2, 1, how=how)
+        o1, o2 = _oracle_frame(None, s1, e1, None, s2, e2, 1, how)
+        assert np.array_equal(ev1.cpu().numpy(), o1) and np.array_equal(ev2.cpu().numpy(), o2)
