@@ -196,7 +196,7 @@ struct ScanView {
 // trip count in every lane: no divergence).  Counts stay in registers for the
 // fused exclusive scan (tile scan + look-back over tile totals).
 constexpr int SR_STAGE = 6144;  // staged composite starts of the other set, 32-bit relative (24 KB)
-constexpr int SR_SLACK = 1536;
+constexpr int SR_SLACK = 512;
 constexpr int SR_MIN_ROWS = 256;  // smallest block of rows (IPT = 1)
 
 static inline i64 search_tiles(i64 n, int ipt) { return ceil_div(n, (i64)SC_THREADS * ipt); }
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(SC_THREADS)
                         const u64* __restrict__ other, i64 m, const u64* __restrict__ other_pmax,
                         const i64* __restrict__ bracket, KeyLayout L, int closed, u32* __restrict__ lo_out,
                         u32* __restrict__ loc_out, u64* __restrict__ tile_tot, i64* __restrict__ overflow,
-                        u8* __restrict__ rowflag, u64* __restrict__ ucnt) {
+                        u8* __restrict__ rowflag) {
   constexpr int TILE = SC_THREADS * IPT;
   __shared__ u32 s_rel[SR_STAGE];
   __shared__ u64 s_tmp[8];
@@ -311,8 +311,6 @@ __global__ void __launch_bounds__(SC_THREADS)
     const i64 p = base + j;
     cnt[j] = 0;
     lo32[j] = 0;
-    bool lonely = false;
-    u32 rank = 0;
     if (p < n) {
       const u64 k = key[j];
       const u64 xs = key_cs(k, L), xe = key_ce(k, L);
@@ -337,13 +335,29 @@ __global__ void __launch_bounds__(SC_THREADS)
           pos = q;
         }
         lo = br_lo + pos;
-        // hi >= lo: bit-step from lo over the staged entries, same trip count in every lane
+        // hi >= lo.  Nearly every row has fewer than 64 partners: probe the entry 64 ahead, then six
+        // bit-steps inside that window; rows with more partners (or near the end of the staged
+        // entries) take the full bit-step search from lo.
         u32 h = pos;
-        for (u32 step = pow2n; step > 0; step >>= 1) {
-          const u32 nx = h + step;
-          if (nx <= nst) {
-            const u32 v = s_rel[nx - 1];
-            if (closed ? (v <= xe_rel) : (v < xe_rel)) h = nx;
+        const u32 probe = pos + 64;
+        bool near = false;
+        if (probe <= nst) {
+          const u32 v = s_rel[probe - 1];
+          near = !(closed ? (v <= xe_rel) : (v < xe_rel));
+        }
+        if (near) {
+#pragma unroll
+          for (u32 step = 32; step > 0; step >>= 1) {
+            const u32 v = s_rel[h + step - 1];
+            if (closed ? (v <= xe_rel) : (v < xe_rel)) h += step;
+          }
+        } else {
+          for (u32 step = pow2n; step > 0; step >>= 1) {
+            const u32 nx = h + step;
+            if (nx <= nst) {
+              const u32 v = s_rel[nx - 1];
+              if (closed ? (v <= xe_rel) : (v < xe_rel)) h = nx;
+            }
           }
         }
         hi = br_lo + h;
@@ -361,24 +375,7 @@ __global__ void __launch_bounds__(SC_THREADS)
           const u64 pm = other_pmax[lo - 1];
           partner = closed ? (pm >= xs) : (pm > xs);
         }
-        lonely = !partner;
-        rank = key_rank(k, L);
-        if (lonely) rowflag[mine_id[p]] = 1;
-      }
-    }
-    if (FLAGS) {
-      // per-group unpaired counters: rows are sorted by group, so a warp almost
-      // always holds one group -> one atomic per warp; mixed warps fall back
-      const u32 lone_mask = __ballot_sync(0xffffffffu, lonely);
-      if (lone_mask) {
-        const u32 lead = __ffs(lone_mask) - 1;
-        const u32 rank0 = __shfl_sync(0xffffffffu, rank, lead);
-        const bool same = __all_sync(0xffffffffu, !lonely || rank == rank0);
-        if (same) {
-          if (lane_id() == lead) atomicAdd(&ucnt[rank0], (u64)__popc(lone_mask));
-        } else if (lonely) {
-          atomicAdd(&ucnt[rank], 1ull);
-        }
+        if (!partner) rowflag[mine_id[p]] = 1;  // per-group counts come later from the compacted list
       }
     }
   }
@@ -673,6 +670,18 @@ __global__ void __launch_bounds__(SC_THREADS)
     }
   }
 }
+// unpaired rows per group from the list sorted by (group, row): ucnt[c] = #{keys with group c}
+__global__ void __launch_bounds__(128) unpaired_group_counts_kernel(const u64* __restrict__ ukeys,
+                                                                    const u64* __restrict__ nU, i32 nb,
+                                                                    u64* __restrict__ ucnt) {
+  const i32 c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nb) return;
+  const i64 n = (i64)*nU;
+  const i64 a = lower_bound_by(0, n, [&](i64 m) { return (ukeys[m] >> 32) < (u64)c; });
+  const i64 b = lower_bound_by(a, n, [&](i64 m) { return (ukeys[m] >> 32) <= (u64)c; });
+  ucnt[c] = (u64)(b - a);
+}
+
 template <bool SECOND>
 __global__ void __launch_bounds__(256) emit_unpaired_kernel(const u64* __restrict__ ukeys, i64 nU,
                                                             const i64* __restrict__ ustart,
@@ -696,7 +705,7 @@ static int launch_search_ipt(const SortResult& mine, i64 n, const SortResult& ot
       mine.keys, n, other.keys, m, L, (i64)SC_THREADS * IPT, tiles, sw.bracket));
   BF_LAUNCH(PC_SEARCH, 16 * n, st, (search_count_kernel<B_SIDE, FLAGS, IPT><<<(unsigned)tiles, SC_THREADS, 0, st>>>(
       mine.keys, mine.vals, n, other.keys, m, other_pmax, sw.bracket, L, closed, sw.lo, sw.loc, sw.tilepre, overflow,
-      FLAGS ? sw.rowflag : nullptr, FLAGS ? sw.ucnt : nullptr)));
+      FLAGS ? sw.rowflag : nullptr)));
   // tile totals -> exclusive tile offsets, grand total in tilepre[tiles]
   BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(sw.tilepre, (u64)tiles, sw.tilepre + tiles));
   int shift = 0;
@@ -830,6 +839,9 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
                                       urp, w.radix, st, &ur, PC_UNPAIRED));
       ukeys_sorted[k] = ur.keys;
     }
+    BF_LAUNCH(PC_UNPAIRED, 0, st,
+              unpaired_group_counts_kernel<<<(unsigned)ceil_div(nb, 128), 128, 0, st>>>(ukeys_sorted[k], w.nU + k, nb,
+                                                                                       w.s[k].ucnt));
   }
   plan->ukeys1 = ukeys_sorted[0];
   plan->ukeys2 = ukeys_sorted[1];
