@@ -50,6 +50,10 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="overlap", choices=["overlap", "closest", "cluster", "coverage"],
+                    help="overlap = the north-star line (cfg3); the others are the secondary BASELINE.json configs "
+                         "(closest: cfg1 1e7 x 1e6 k=1; cluster: cfg2 1e8 heavy-tailed; coverage: cfg3 sets)")
+    ap.add_argument("--k", type=int, default=1)
     return ap.parse_args()
 
 
@@ -151,16 +155,120 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_secondary(args):
+    """closest / cluster / coverage at their BASELINE.json sizes, single GPU: device-resident inputs,
+    CUDA-event timing of the whole call, whole-call algorithmic bytes against the measured
+    HBM peak, and the oracle port on a bounded sample beside it."""
+    import torch
+
+    from bioframe_b200 import _lib, engine, synth
+    from oracle import ops_oracle as oo
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    wl = args.workload
+    if wl == "closest":
+        n1, n2 = (args.n1 if args.n1 != 100_000_000 else 10_000_000), (args.n2 if args.n2 != 10_000_000 else 1_000_000)
+        q = synth.make_intervals(n1, 1, "geom1k")
+        t = synth.make_intervals(n2, 2, "geom1k")
+        d = [torch.from_numpy(a).to(dev) for a in (*q, *t)]
+        call = lambda: engine.closest_intidxs(d[0], d[1], d[2], d[3], d[4], d[5], N_GROUPS, k=args.k)  # noqa: E731
+        rows_of = lambda r: int(r[0].numel())  # noqa: E731
+        a_alg = lambda R: 2 * 256 * n2 + 36 * n1 + 20 * R  # noqa: E731
+        units, name = n1 + n2, f"bf.closest(k={args.k}) input intervals/s"
+        desc = f"_closest_intidxs cfg1: {n1} hg38 queries x {n2} targets (geom 1kb), k={args.k}, unsorted"
+        frac = synth.subset_fraction(SAMPLE_CHROMS)
+        sq = synth.make_intervals(int(n1 * frac), 1, "geom1k", chrom_ids=SAMPLE_CHROMS)
+        stt = synth.make_intervals(int(n2 * frac), 2, "geom1k", chrom_ids=SAMPLE_CHROMS)
+        cpu = lambda: oo.closest_intidxs_coded(*sq, *stt, N_GROUPS, k=args.k)  # noqa: E731
+        cpu_units = len(sq[1]) + len(stt[1])
+    elif wl == "cluster":
+        n1 = args.n1
+        q = synth.make_intervals(n1, 1, "pareto")
+        d = [torch.from_numpy(a).to(dev) for a in q]
+        call = lambda: engine.cluster(d[0], d[1], d[2], N_GROUPS, min_dist=0, want_ids=True, want_table=True)  # noqa: E731
+        rows_of = lambda r: int(r["n_clusters"])  # noqa: E731
+        a_alg = lambda C: 256 * n1 + 12 * n1 + 28 * C  # noqa: E731
+        units, name = n1, "bf.cluster input intervals/s"
+        desc = f"cluster+merge table cfg2: {n1} hg38 intervals, Pareto(1.2) lengths capped 5 Mb, unsorted"
+        frac = synth.subset_fraction(SAMPLE_CHROMS)
+        sq = synth.make_intervals(int(n1 * frac), 1, "pareto", chrom_ids=SAMPLE_CHROMS)
+        cpu = lambda: oo.cluster_coded(*sq, N_GROUPS, 0)  # noqa: E731
+        cpu_units = len(sq[1])
+    else:  # coverage
+        n1, n2 = args.n1, args.n2
+        (q, t) = workload(n1, n2, 0)
+        d = [torch.from_numpy(a).to(dev) for a in (*q, *t)]
+        call = lambda: engine.coverage(d[0], d[1], d[2], d[3], d[4], d[5], N_GROUPS)  # noqa: E731
+        rows_of = lambda r: int(r.numel())  # noqa: E731
+        a_alg = lambda R: 256 * n2 + 36 * n1  # noqa: E731
+        units, name = n1 + n2, "bf.coverage input intervals/s"
+        desc = f"coverage cfg3: {n1} hg38 queries (geom 2kb) x {n2} peak-like targets"
+        (sq, stt) = workload(n1, n2, 0, chrom_ids=SAMPLE_CHROMS)
+        cpu = lambda: oo.coverage_coded(*sq, *stt, N_GROUPS)  # noqa: E731
+        cpu_units = len(sq[1]) + len(stt[1])
+
+    for _ in range(max(args.warmup, 3)):
+        r = call()
+    R = rows_of(r)
+    del r
+    _lib.prof_reset()
+    _lib.prof_enable(True)
+    torch.cuda.synchronize(dev)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        r = call()
+        del r
+    t1.record()
+    torch.cuda.synchronize(dev)
+    ms = t0.elapsed_time(t1) / args.steps
+    prof = _lib.prof_read()
+    _lib.prof_enable(False)
+    peak = 6554.6
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f).get("hbm_gbs", peak))
+    except Exception:
+        pass
+    alg = a_alg(R)
+    line = {
+        "metric": name, "value": units / (ms * 1e-3), "unit": "intervals/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": desc, "rows_out": R, "l2": "inputs and intermediates exceed the 126 MB L2"},
+        "gpu_launches": sum(v["launches"] for v in prof.values()),
+        "roofline": {"bound": "hbm", "kernel": "whole call (A_alg of SURVEY.md 8d)", "achieved": alg / (ms * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}},
+    }
+    if not args.no_cpu:
+        times = []
+        for it in range(2):
+            w0 = time.perf_counter()
+            cpu()
+            times.append(time.perf_counter() - w0)
+        line["cpu_baseline"] = {"value": cpu_units / min(times), "unit": "intervals/s", "cores": 1, "kind": "port",
+                                "sample": f"chr21+chr22 share of the workload at full density ({cpu_units} intervals), numpy oracle port",
+                                "ms_per_step": min(times) * 1e3}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
         return
+    if args.workload != "overlap":
+        run_secondary(args)
+        return
 
     import torch
     import torch.distributed as dist
 
-    from bioframe_b200 import _lib, engine
+    from bioframe_b200 import _lib, engine, sharded
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -183,11 +291,23 @@ def main():
             t.zero_()  # targets arrive by broadcast
     h2d_bytes = sum(h.numel() * h.element_size() for h in host)
 
+    row_offset = rank * n1  # weak scaling: rank r owns query rows [r*n1, (r+1)*n1) of the whole job
+
     def step():
         if world > 1:
-            for t in d[3:]:
-                dist.broadcast(t, src=0)
-        return engine.overlap_intidxs(d[0], d[1], d[2], d[3], d[4], d[5], N_GROUPS, how=args.how)
+            # targets broadcast from rank 0 over NCCL/NVLink inside the step, queries stay local,
+            # one all-gather of the per-rank row counts (bioframe_b200/sharded.py)
+            ev1, ev2, _off, _tot = sharded.overlap_sharded(d[0], d[1], d[2], row_offset, d[3], d[4], d[5], N_GROUPS,
+                                                           how=args.how)
+            return ev1, ev2, last_pairs[0]
+        a, b, npairs = engine.overlap_intidxs(d[0], d[1], d[2], d[3], d[4], d[5], N_GROUPS, how=args.how)
+        last_pairs[0] = npairs
+        return a, b, npairs
+
+    last_pairs = [0]
+    if world > 1:  # pair count of this rank's shard (for pairs/s), measured once outside the timed region
+        _a, _b, last_pairs[0] = engine.overlap_intidxs(d[0], d[1], d[2], d[3], d[4], d[5], N_GROUPS, how=args.how)
+        del _a, _b
 
     def fence():
         if world > 1:
@@ -220,6 +340,11 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total = float(tt.item())
     ms_step = ms_total / args.steps
+    total_pairs, total_rows = int(n_pairs), n_rows
+    if world > 1:
+        tt = torch.tensor([int(n_pairs), n_rows], device=dev, dtype=torch.int64)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        total_pairs, total_rows = int(tt[0].item()), int(tt[1].item())
     units = n1 * world + n2
     value = units / (ms_step * 1e-3)
 
@@ -291,7 +416,8 @@ def main():
                 "n2": n2,
                 "rows_out_per_gpu": n_rows,
                 "pairs_out_per_gpu": int(n_pairs),
-                "pairs_per_s": n_pairs * world / (ms_step * 1e-3),
+                "pairs_per_s": total_pairs / (ms_step * 1e-3),
+                "rows_out_total": total_rows,
                 "l2": "inputs (2.2 GB) and every intermediate exceed the 126 MB L2; no flush needed",
                 "parallelism": f"query-sharded x{world}, targets NCCL-broadcast" if world > 1 else "single GPU",
             },

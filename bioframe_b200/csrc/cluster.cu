@@ -26,15 +26,15 @@ struct ClusterWS {
   SortBufs sb;
   RadixScratch radix;
   LayoutScratch layout;
-  ScanState ss_max, ss_sum;
+  u64 *spine_max, *spine_cnt;  // [tiles + 1]
   i64* header;  // [0] = number of clusters
 };
 static void layout_cluster(Arena& a, i64 n, i32 nb, ClusterWS* w) {
   take_sort_bufs(a, n, &w->sb);
   w->radix = take_radix_scratch(a, (u64)n);
   w->layout = take_layout_scratch(a, nb);
-  w->ss_max = take_scan_state(a, (u64)scan_tiles((u64)n));
-  w->ss_sum = take_scan_state(a, (u64)scan_tiles((u64)n));
+  w->spine_max = a.take<u64>(scan_tiles((u64)n) + 2);
+  w->spine_cnt = a.take<u64>(scan_tiles((u64)n) + 2);
   w->header = a.take<i64>(4);
 }
 
@@ -67,21 +67,43 @@ __device__ __forceinline__ bool gap_opens_cluster(u64 cs, u64 runmax_prev, u64 m
   return has_min_dist ? (cs > runmax_prev + min_dist) : (cs >= runmax_prev);
 }
 
+// Three short passes instead of one pass with two chained look-backs (a chain of ~5e4 tiles costs more
+// than re-reading 8 B/row twice, see profiles/NOTES.md):
+//   cluster_tile_max_kernel  -> per-tile max of linear end            -> spine scan (exclusive max)
+//   cluster_pass_kernel<2>   -> running max, borders, per-tile count  -> spine scan (exclusive sum)
+//   cluster_pass_kernel<3>   -> the same again + ids, cluster table
 __global__ void __launch_bounds__(SC_THREADS)
-    cluster_scan_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, KeyLayout L, u64 min_dist,
-                        int has_min_dist, ScanState ss_max, ScanState ss_sum, i64* __restrict__ ids_out,
-                        ClusterTable tab) {
+    cluster_tile_max_kernel(const u64* __restrict__ keys, u64 n, KeyLayout L, u64* __restrict__ spine_max) {
+  __shared__ u64 s_tmp[8];
+  const u64 base = (u64)blockIdx.x * SC_TILE;
+  u64 acc = 0;
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    const u64 i = base + (u64)j * SC_THREADS + threadIdx.x;
+    if (i < n) {
+      const u64 v = key_ce(keys[i], L);
+      acc = v > acc ? v : acc;
+    }
+  }
+  acc = block_max_u64(acc, s_tmp);
+  if (threadIdx.x == 0) spine_max[blockIdx.x] = acc;
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(SC_THREADS)
+    cluster_pass_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, KeyLayout L, u64 min_dist,
+                        int has_min_dist, const u64* __restrict__ spine_max, u64* __restrict__ spine_cnt,
+                        i64* __restrict__ ids_out, ClusterTable tab) {
   // [0] row before the tile, [1..rows] tile, [rows+1] row after; one pad slot every 8 entries so that
   // threads reading 8 consecutive rows each do not collide on the shared-memory banks
   __shared__ u64 s_kp[SC_TILE + 2 + (SC_TILE + 2) / 8 + 1];
 #define s_k(i) s_kp[(i) + ((i) >> 3)]
   __shared__ u64 s_tmp[8];
-  __shared__ u64 s_pre[2];
-  __shared__ u32 s_ticket;
   const u32 tid = threadIdx.x;
-  const u64 tile = take_ticket(ss_max.ticket, &s_ticket);
+  const u64 tile = blockIdx.x;
   const u64 base = tile * SC_TILE;
   const u64 rows = n - base < (u64)SC_TILE ? n - base : (u64)SC_TILE;
+#pragma unroll 9
   for (u32 i = tid; i < rows + 2; i += SC_THREADS) {
     const i64 p = (i64)base + i - 1;
     s_k(i) = (p >= 0 && (u64)p < n) ? keys[p] : 0ull;
@@ -100,16 +122,11 @@ __global__ void __launch_bounds__(SC_THREADS)
     rm[j] = tmax;
   }
   u64 before = block_excl_max_u64(tmax, s_tmp);
-  const u64 tile_max = block_max_u64(tmax, s_tmp);
-  if (tid < 32) {
-    const u64 pre = lookback_exclusive_max(ss_max.status, tile, tile_max);
-    if (tid == 0) s_pre[0] = pre;
-  }
-  __syncthreads();
-  before = before > s_pre[0] ? before : s_pre[0];  // running max over every earlier row
+  const u64 tile_pre = spine_max[tile];
+  before = before > tile_pre ? before : tile_pre;  // running max over every earlier row
 
   // ---- group of each row (binary search once per thread, then advance), borders ----
-  u32 rk[SC_IPT + 2];  // [0] row before the thread's first, [1..IPT] own rows, [IPT+1] row after
+  u32 rk[SC_IPT + 1];  // [0] row before the thread's first, [1..IPT] own rows
   rk[0] = r0 < rows ? rank_of_cs(key_cs(s_k(r0), L), L) : 0u;
   u32 bmask = 0;
 #pragma unroll
@@ -126,12 +143,11 @@ __global__ void __launch_bounds__(SC_THREADS)
   }
   u64 tot;
   u64 nborders_before = block_excl_sum_u64((u64)__popc(bmask), s_tmp, &tot);
-  if (tid < 32) {
-    const u64 pre = lookback_exclusive(ss_sum.status, tile, tot);
-    if (tid == 0) s_pre[1] = pre;
+  if (PHASE == 2) {
+    if (tid == 0) spine_cnt[tile] = tot;
+    return;
   }
-  __syncthreads();
-  nborders_before += s_pre[1];
+  nborders_before += spine_cnt[tile];
 
   // ---- ids, cluster table ----
   u64 seen = nborders_before;
@@ -160,9 +176,8 @@ __global__ void __launch_bounds__(SC_THREADS)
       if (closes) tab.cend[id] = (i64)(run - gbase + L.cmin);
     }
   }
-  if (base + rows == n && tid == 0) *tab.n_clusters = (i64)(s_pre[1] + tot);
-}
 #undef s_k
+}
 
 __global__ void __launch_bounds__(256)
     cluster_emit_kernel(ClusterTable tab, i64 n_clusters, i64 n, i32* __restrict__ cgrp_out,
@@ -203,14 +218,18 @@ static int cluster_run(const i32* grp, const i64* s, const i64* e, i64 n, i32 nb
   tab->cgrp = w.sb.tmp4b;
   tab->n_clusters = w.header;
   const unsigned tiles = (unsigned)scan_tiles((u64)n);
-  BF_TRY(reset_scan_state(w.ss_max, tiles, st));
-  BF_TRY(reset_scan_state(w.ss_sum, tiles, st));
   u64 md = 0;
   if (has_min_dist) md = min_dist < 0 ? 0ull : (u64)min_dist;
   if (md > (1ull << 62)) md = 1ull << 62;
+  BF_LAUNCH(PC_CLUSTER, 8 * n, st, cluster_tile_max_kernel<<<tiles, SC_THREADS, 0, st>>>(r.keys, (u64)n, L, w.spine_max));
+  BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<true><<<1, 1024, 0, st>>>(w.spine_max, (u64)tiles, nullptr));
+  BF_LAUNCH(PC_CLUSTER, 8 * n, st,
+            cluster_pass_kernel<2><<<tiles, SC_THREADS, 0, st>>>(r.keys, r.vals, (u64)n, L, md, has_min_dist, w.spine_max,
+                                                                 w.spine_cnt, nullptr, *tab));
+  BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.spine_cnt, (u64)tiles, (u64*)w.header));
   BF_LAUNCH(PC_CLUSTER, (u64)(12 + (ids_out ? 12 : 0)) * (u64)n, st,
-            cluster_scan_kernel<<<tiles, SC_THREADS, 0, st>>>(r.keys, r.vals, (u64)n, L, md, has_min_dist, w.ss_max,
-                                                              w.ss_sum, ids_out, *tab));
+            cluster_pass_kernel<3><<<tiles, SC_THREADS, 0, st>>>(r.keys, r.vals, (u64)n, L, md, has_min_dist, w.spine_max,
+                                                                 w.spine_cnt, ids_out, *tab));
   if (L_out) *L_out = L;
   return BF_OK;
 }
@@ -284,25 +303,40 @@ static int cluster_emit_impl(const ClusterPlan* plan, i32* cgrp_out, i64* cstart
 // and coverage = F(end) - F(start): two binary searches per query, no pairs.
 struct CoverageWS {
   ClusterWS cl;
-  i64* plen;  // [n2+1] exclusive prefix of merged lengths
-  ScanState ss;
+  u64 *slin, *elin;  // [n2+1] merged intervals on the linear (group, coordinate) axis of the key layout
+  u64* plen;         // [n2+1] exclusive prefix of merged lengths
+  u64* spine;        // [tiles + 1]
 };
 static void layout_coverage(Arena& a, i64 n2, i32 nb, CoverageWS* w) {
   layout_cluster(a, n2, nb, &w->cl);
-  w->plen = a.take<i64>(n2 + 1);
-  w->ss = take_scan_state(a, (u64)scan_tiles((u64)n2));
+  w->slin = a.take<u64>(n2 + 1);
+  w->elin = a.take<u64>(n2 + 1);
+  w->plen = a.take<u64>(n2 + 1);
+  w->spine = a.take<u64>(scan_tiles((u64)n2) + 2);
 }
 
-__global__ void __launch_bounds__(SC_THREADS)
-    merged_length_scan_kernel(ClusterTable tab, ScanState ss, i64* __restrict__ plen) {
+// per-tile sums of the merged lengths (n lives on the device)
+__global__ void __launch_bounds__(SC_THREADS) merged_length_tiles_kernel(ClusterTable tab, u64* __restrict__ spine) {
   __shared__ u64 s_tmp[8];
-  __shared__ u64 s_pre;
-  __shared__ u32 s_ticket;
-  const u32 tid = threadIdx.x;
-  const u64 tile = take_ticket(ss.ticket, &s_ticket);
   const u64 n = (u64)*tab.n_clusters;
-  const u64 base = tile * SC_TILE + (u64)tid * SC_IPT;
-  if (tile * SC_TILE >= n && tile > 0) return;  // block-uniform
+  const u64 base = (u64)blockIdx.x * SC_TILE;
+  u64 acc = 0;
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    const u64 c = base + (u64)j * SC_THREADS + threadIdx.x;
+    if (c < n) acc += (u64)(tab.cend[c] - tab.cstart[c]);
+  }
+  acc = block_sum_u64(acc, s_tmp);
+  if (threadIdx.x == 0) spine[blockIdx.x] = acc;
+}
+// linear start / end and exclusive length prefix of every merged interval
+__global__ void __launch_bounds__(SC_THREADS)
+    merged_table_kernel(ClusterTable tab, KeyLayout L, const u64* __restrict__ spine, u64* __restrict__ slin,
+                        u64* __restrict__ elin, u64* __restrict__ plen) {
+  __shared__ u64 s_tmp[8];
+  const u64 n = (u64)*tab.n_clusters;
+  const u64 base = (u64)blockIdx.x * SC_TILE + (u64)threadIdx.x * SC_IPT;
+  if ((u64)blockIdx.x * SC_TILE > n) return;  // block-uniform
   u64 len[SC_IPT];
   u64 mine = 0;
 #pragma unroll
@@ -312,41 +346,65 @@ __global__ void __launch_bounds__(SC_THREADS)
     mine += len[j];
   }
   u64 tot;
-  u64 run = block_excl_sum_u64(mine, s_tmp, &tot);
-  if (tid < 32) {
-    const u64 pre = lookback_exclusive(ss.status, tile, tot);
-    if (tid == 0) s_pre = pre;
-  }
-  __syncthreads();
-  run += s_pre;
+  u64 run = spine[blockIdx.x] + block_excl_sum_u64(mine, s_tmp, &tot);
 #pragma unroll
   for (int j = 0; j < SC_IPT; ++j) {
     const u64 c = base + j;
-    if (c <= n) plen[c] = (i64)run;  // plen[n] = total
+    if (c < n) {
+      const u64 off = L.goff[tab.cgrp[c]];
+      slin[c] = off + ((u64)tab.cstart[c] - L.cmin);
+      elin[c] = off + ((u64)tab.cend[c] - L.cmin);
+    }
+    if (c <= n) plen[c] = run;  // plen[n] = total
     run += len[j];
   }
 }
 
+// Covered length below a linear coordinate x:  F(x) = plen[j-1] + min(x, E[j-1]) - S[j-1],  j = #{S < x}
+// (0 when j == 0).  On the linear axis no group test is needed: merged intervals of earlier groups end
+// before the group's offset, so they count in full in both F(end) and F(start) and cancel.
 __global__ void __launch_bounds__(256)
     coverage_kernel(const i32* __restrict__ grp1, const i64* __restrict__ s1, const i64* __restrict__ e1, i64 n1,
-                    ClusterTable tab, const i64* __restrict__ plen, i64* __restrict__ cov) {
+                    const i64* __restrict__ n_clusters, KeyLayout L, const u64* __restrict__ slin,
+                    const u64* __restrict__ elin, const u64* __restrict__ plen, i64* __restrict__ cov) {
   const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n1) return;
-  const i64 C = *tab.n_clusters;
+  const i64 C = *n_clusters;
   const u32 g = grp1 ? (u32)grp1[r] : 0u;
-  auto covered_below = [&](i64 x) -> i64 {
-    // j = #{clusters with (group, S) < (g, x)}
-    const i64 j = lower_bound_by(0, C, [&](i64 m) {
-      const u32 cg = tab.cgrp[m];
-      return cg < g || (cg == g && tab.cstart[m] < x);
-    });
-    if (j == 0 || tab.cgrp[j - 1] != g) return plen[j];
-    const i64 E = tab.cend[j - 1];
-    return plen[j - 1] + ((x < E ? x : E) - tab.cstart[j - 1]);
+  if (g >= (u32)L.nb) {  // group code outside the call's groups: nothing can cover it
+    cov[r] = 0;
+    return;
+  }
+  // query coordinates clamped into the group's stretch of the axis (the layout was measured on the
+  // targets only; nothing of a group lies outside its stretch, so clamping cannot change the coverage)
+  const u64 g0 = L.goff[g], span = L.goff[g + 1] - g0;
+  auto lin = [&](i64 x) -> u64 {
+    if ((u64)x - L.cmin > (1ull << 63)) return g0;  // x below the origin (wrapped difference)
+    const u64 d = (u64)x - L.cmin;
+    return g0 + (d < span ? d : span);
   };
-  const i64 a = s1[r], b = e1[r];
-  i64 c = covered_below(b) - covered_below(a);
-  cov[r] = c > 0 ? c : 0;
+  auto below = [&](i64 j, u64 x) -> u64 {
+    if (j == 0) return 0ull;
+    const u64 E = elin[j - 1];
+    return plen[j - 1] + ((x < E ? x : E) - slin[j - 1]);
+  };
+  const u64 xs = lin(s1[r]), xe = lin(e1[r]);
+  const i64 js = lower_bound_by(0, C, [&](i64 m) { return slin[m] < xs; });
+  // the end is rarely more than a few merged intervals further on: gallop from js
+  i64 lo = js, hi = js, step = 1;
+  for (;;) {
+    hi = lo + step;
+    if (hi >= C) {
+      hi = C;
+      break;
+    }
+    if (!(slin[hi - 1] < xe)) break;
+    lo = hi;
+    step <<= 1;
+  }
+  const i64 je = lower_bound_by(lo, hi, [&](i64 m) { return slin[m] < xe; });
+  const u64 fe = below(je, xe), fs = below(js, xs);
+  cov[r] = fe > fs ? (i64)(fe - fs) : 0;
 }
 
 static int coverage_impl(const i32* grp1, const i64* s1, const i64* e1, i64 n1, const i32* grp2, const i64* s2,
@@ -378,12 +436,15 @@ static int coverage_impl(const i32* grp1, const i64* s1, const i64* e1, i64 n1, 
   Arena arena(ws_ptr);
   layout_coverage(arena, n2, nb, &w);
   ClusterTable tab;
-  BF_TRY(cluster_run(grp2, s2, e2, n2, nb, 0, 1, w.cl, nullptr, st, &tab, nullptr));
+  KeyLayout L;
+  BF_TRY(cluster_run(grp2, s2, e2, n2, nb, 0, 1, w.cl, nullptr, st, &tab, &L));
   const unsigned tiles = (unsigned)scan_tiles((u64)n2);
-  BF_TRY(reset_scan_state(w.ss, tiles, st));
-  BF_LAUNCH(PC_COVERAGE, 0, st, merged_length_scan_kernel<<<tiles, SC_THREADS, 0, st>>>(tab, w.ss, w.plen));
+  BF_LAUNCH(PC_COVERAGE, 16 * n2, st, merged_length_tiles_kernel<<<tiles, SC_THREADS, 0, st>>>(tab, w.spine));
+  BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.spine, (u64)tiles, nullptr));
+  BF_LAUNCH(PC_COVERAGE, 44 * n2, st, merged_table_kernel<<<tiles, SC_THREADS, 0, st>>>(tab, L, w.spine, w.slin, w.elin, w.plen));
   BF_LAUNCH(PC_COVERAGE, 28 * n1, st,
-            coverage_kernel<<<(unsigned)ceil_div(n1, 256), 256, 0, st>>>(nb > 1 ? grp1 : nullptr, s1, e1, n1, tab, w.plen, cov));
+            coverage_kernel<<<(unsigned)ceil_div(n1, 256), 256, 0, st>>>(nb > 1 ? grp1 : nullptr, s1, e1, n1, tab.n_clusters, L,
+                                                                        w.slin, w.elin, w.plen, cov));
   return BF_OK;
 }
 

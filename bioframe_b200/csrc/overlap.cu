@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(SC_THREADS)
       base_cs = first;
     }
   }
+#pragma unroll 4
   for (u32 i = tid; i < nst; i += SC_THREADS) s_rel[i] = (u32)(key_cs(other[br_lo + i], L) - base_cs + 1);
   u32 pow2w = 1, pow2n = 1;
   while (pow2w <= W) pow2w <<= 1;

@@ -20,6 +20,8 @@ namespace bf {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_LANES = 1;  // independent counter tables per warp (rounds ranked RS_LANES at a time; 2 measured slower on B200)
+constexpr int RS_TABLES = RS_WARPS * RS_LANES;
 constexpr int RS_IPT = 16;
 constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 keys per tile
 constexpr int RS_BINS = 256;
@@ -163,7 +165,7 @@ constexpr u64 RS_FLAG_AGG = 1ull << 56;
 constexpr u64 RS_FLAG_INC = 2ull << 56;
 
 constexpr size_t rs_smem_bytes(bool has_val) {
-  return (size_t)RS_TILE * 8 + (has_val ? (size_t)RS_TILE * 4 : 0) + (size_t)RS_WARPS * RS_BINS * 4 +
+  return (size_t)RS_TILE * 8 + (has_val ? (size_t)RS_TILE * 4 : 0) + (size_t)RS_TABLES * RS_BINS * 4 +
          (size_t)RS_BINS * 4 + (size_t)RS_BINS * 8;
 }
 
@@ -176,8 +178,8 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
   extern __shared__ __align__(16) unsigned char rs_smem[];
   u64* s_keys = (u64*)rs_smem;
   u32* s_vals = (u32*)(s_keys + RS_TILE);
-  u32* s_wcnt = s_vals + (HAS_VAL ? RS_TILE : 0);  // [RS_WARPS][256]
-  u32* s_tbase = s_wcnt + RS_WARPS * RS_BINS;      // [256] exclusive digit offsets inside the tile
+  u32* s_wcnt = s_vals + (HAS_VAL ? RS_TILE : 0);  // [RS_TABLES][256]: table (warp w, half h) = w * RS_LANES + h
+  u32* s_tbase = s_wcnt + RS_TABLES * RS_BINS;     // [256] exclusive digit offsets inside the tile
   u64* s_gofs = (u64*)(s_tbase + RS_BINS);         // [256] global offset minus s_tbase
   __shared__ u32 s_tile;
   __shared__ u32 s_wtot[RS_BINS / 32];
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
   for (;;) {
   __syncthreads();  // previous tile fully written out before shared memory is reused
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-  for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) s_wcnt[i] = 0;
+  for (int i = tid; i < RS_TABLES * RS_BINS; i += RS_THREADS) s_wcnt[i] = 0;
   __syncthreads();
   const u64 tile = s_tile;
   const u64 tile_start = tile * RS_TILE;
@@ -210,21 +212,34 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
   // the same digit.  Alone (the common case for 8-bit digits) its rank is the old count; otherwise the
   // few lanes that collided order themselves by lane with one match.any over just those lanes, which
   // keeps the pass stable.  Replaces 8 ballots + mask logic per key.
+  // The warp's 16 rounds are split in two halves with their own counter tables (rounds 0-7 and 8-15
+  // are consecutive stretches of the tile, so "half" is just a finer warp); one round of each half is
+  // ranked per step, which gives two independent shared-memory dependency chains per warp.
   u16 lpos[RS_IPT];
-  u32* my_cnt = s_wcnt + warp * RS_BINS;
+  u32* my_cnt = s_wcnt + warp * (RS_LANES * RS_BINS);
   const u32 lt = lanemask_lt();
+  constexpr int HALF = RS_IPT / RS_LANES;
 #pragma unroll
-  for (int j = 0; j < RS_IPT; ++j) {
-    const u32 d = (u32)(key[j] >> shift) & dmask;
-    const u32 before = my_cnt[d];
+  for (int j = 0; j < HALF; ++j) {
+    u32 d[RS_LANES], before[RS_LANES], same[RS_LANES];
+#pragma unroll
+    for (int h = 0; h < RS_LANES; ++h) {
+      d[h] = (u32)(key[j + h * HALF] >> shift) & dmask;
+      before[h] = my_cnt[h * RS_BINS + d[h]];
+    }
     __syncwarp();
-    atomicAdd(&my_cnt[d], 1u);
+#pragma unroll
+    for (int h = 0; h < RS_LANES; ++h) atomicAdd(&my_cnt[h * RS_BINS + d[h]], 1u);
     __syncwarp();
-    const u32 same = my_cnt[d] - before;  // lanes of this round with digit d (>= 1)
-    u32 r = before;
-    const u32 crowd = __ballot_sync(0xffffffffu, same > 1);
-    if (same > 1) r += __popc(__match_any_sync(crowd, d) & lt);
-    lpos[j] = (u16)r;
+#pragma unroll
+    for (int h = 0; h < RS_LANES; ++h) same[h] = my_cnt[h * RS_BINS + d[h]] - before[h];  // lanes with digit d (>= 1)
+#pragma unroll
+    for (int h = 0; h < RS_LANES; ++h) {
+      u32 r = before[h];
+      const u32 crowd = __ballot_sync(0xffffffffu, same[h] > 1);
+      if (same[h] > 1) r += __popc(__match_any_sync(crowd, d[h]) & lt);
+      lpos[j + h * HALF] = (u16)r;
+    }
   }
   __syncthreads();
 
@@ -236,7 +251,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
   {
     u32 tile_cnt = 0;
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) {
+    for (int w = 0; w < RS_TABLES; ++w) {
       u32 c = s_wcnt[w * RS_BINS + d_own];
       s_wcnt[w * RS_BINS + d_own] = tile_cnt;
       tile_cnt += c;
@@ -268,7 +283,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
 #pragma unroll
   for (int j = 0; j < RS_IPT; ++j) {
     u32 d = (u32)(key[j] >> shift) & dmask;
-    u32 p = s_tbase[d] + my_cnt[d] + lpos[j];
+    u32 p = s_tbase[d] + my_cnt[(j / (RS_IPT / RS_LANES)) * RS_BINS + d] + lpos[j];
     lpos[j] = (u16)p;
     s_keys[p] = key[j];
   }

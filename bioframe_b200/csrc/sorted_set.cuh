@@ -63,10 +63,21 @@ __device__ __forceinline__ u32 tie_scan_tile(u64* __restrict__ keys, u32* __rest
     return e_raw ? e_raw[v1] > e_raw[v2] : false;
   };
   const u32 tid = threadIdx.x;
-  // s_k[i] = keys[base - TIE_HALO + i]
-  for (u32 i = tid; i < rows + 2 * TIE_HALO; i += SC_THREADS) {
-    const i64 p = (i64)base + i - TIE_HALO;
-    s_k[i] = (p >= 0 && (u64)p < n) ? keys[p] : ~0ull;
+  // s_k[i] = keys[base - TIE_HALO + i]; all loads of a thread in flight before its first store
+  {
+    u64 v[SC_IPT], hv = ~0ull;
+#pragma unroll
+    for (int j = 0; j < SC_IPT; ++j) {
+      const u64 p = base + (u64)j * SC_THREADS + tid;
+      v[j] = p < n ? keys[p] : ~0ull;
+    }
+    if (tid < 2 * TIE_HALO) {  // halo: TIE_HALO keys before the tile, TIE_HALO after
+      const i64 p = tid < TIE_HALO ? (i64)base - TIE_HALO + tid : (i64)base + SC_TILE + (tid - TIE_HALO);
+      if (p >= 0 && (u64)p < n) hv = keys[p];
+      s_k[tid < TIE_HALO ? tid : SC_TILE + tid] = hv;
+    }
+#pragma unroll
+    for (int j = 0; j < SC_IPT; ++j) s_k[TIE_HALO + j * SC_THREADS + tid] = v[j];
   }
   __syncthreads();
   u32 mask = 0;
