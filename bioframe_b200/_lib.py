@@ -54,6 +54,7 @@ SIGNATURES = {
          C.POINTER(_i64), C.POINTER(_i64)],
     ),
     "bf_overlap_emit": (C.c_int, [C.POINTER(Plan), _p, _p, _p, _p]),
+    "bf_overlap_set_row_offsets": (C.c_int, [C.POINTER(Plan), _i64, _i64]),
     "bf_closest_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "bf_closest_count": (
         C.c_int,

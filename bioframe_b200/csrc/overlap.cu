@@ -112,6 +112,7 @@ struct OverlapPlan {  // lives in the caller's bf_plan
   i64 n_rows, n_pairs, nU1, nU2;
   i64 totA, totB;
   i32 shift1, shift2;  // log2(rows per search tile) of the two sides
+  i64 row_off1, row_off2;  // added to every reported row number of set 1 / set 2 (query-sharded callers)
   // sorted results (pointers into the workspace)
   u64 *key1, *key2;
   u32 *id1, *id2;
@@ -498,8 +499,8 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
     emit_pairs_kernel(const ScanView scan, const u32* __restrict__ lo, i64 n_owner,
                       const u32* __restrict__ owner_id, const u32* __restrict__ other_id, i64 total,
                       i64 block0, const i64* __restrict__ part, const i32* __restrict__ pgrp,
-                      const i64* __restrict__ cum, const i64* __restrict__ delta, i32 nb, i64* __restrict__ ev1,
-                      i64* __restrict__ ev2) {
+                      const i64* __restrict__ cum, const i64* __restrict__ delta, i32 nb, i64 off1, i64 off2,
+                      i64* __restrict__ ev1, i64* __restrict__ ev2) {
   __shared__ i32 s_rel[EM_TILE + 2];  // scan[first_item + i] - t0, clamped to 32 bits
   __shared__ EmitItem s_item[EM_TILE + 2];
   __shared__ u32 s_owner[EM_TILE + EM_TILE / 8];  // padded: 8 consecutive slots per thread without bank conflicts
@@ -590,7 +591,7 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
     for (int j = 0; j < 4; ++j) {
       const i32 x = (h + j) * EM_THREADS + (i32)tid;
       if (x < nout) {
-        const i64 a = B_SIDE ? (i64)oth[j] : (i64)own[j], b = B_SIDE ? (i64)own[j] : (i64)oth[j];
+        const i64 a = (B_SIDE ? (i64)oth[j] : (i64)own[j]) + off1, b = (B_SIDE ? (i64)own[j] : (i64)oth[j]) + off2;
         if (one_group) {
           out1[x] = a;
           out2[x] = b;
@@ -686,7 +687,7 @@ __global__ void __launch_bounds__(128) unpaired_group_counts_kernel(const u64* _
 template <bool SECOND>
 __global__ void __launch_bounds__(256) emit_unpaired_kernel(const u64* __restrict__ ukeys, i64 nU,
                                                             const i64* __restrict__ ustart,
-                                                            const i64* __restrict__ ubase,
+                                                            const i64* __restrict__ ubase, i64 row_off,
                                                             i64* __restrict__ ev1, i64* __restrict__ ev2) {
   i64 u = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= nU) return;
@@ -694,8 +695,8 @@ __global__ void __launch_bounds__(256) emit_unpaired_kernel(const u64* __restric
   u32 c = (u32)(k >> 32);
   i64 row = (i64)(k & 0xffffffffull);
   i64 out = ubase[c] + (u - ustart[c]);
-  ev1[out] = SECOND ? -1 : row;
-  ev2[out] = SECOND ? row : -1;
+  ev1[out] = SECOND ? -1 : row + row_off;
+  ev2[out] = SECOND ? row + row_off : -1;
 }
 
 template <bool B_SIDE, bool FLAGS, int IPT>
@@ -771,6 +772,7 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   plan->how = how;
   plan->closed = closed;
   plan->ready = 0;
+  plan->row_off1 = plan->row_off2 = 0;
 
   // ---- coordinate extent, group code check, key layout (one small D2H) ----
   const RowSet sets[2] = {{grp1, s1, e1, n1}, {grp2, s2, e2, n2}};
@@ -900,21 +902,23 @@ static int overlap_emit_impl(const OverlapPlan* plan, void* ws_ptr, i64* ev1, i6
       if (side == 0) {
         BF_LAUNCH(PC_EMIT, bytes, st,
                   emit_pairs_kernel<false><<<(unsigned)nb_chunk, EM_THREADS, 0, st>>>(
-                      scan, sw.lo, n_owner, plan->id1, plan->id2, total, b0, part, pgrp, cum, delta, plan->nb, ev1, ev2));
+                      scan, sw.lo, n_owner, plan->id1, plan->id2, total, b0, part, pgrp, cum, delta, plan->nb,
+                      plan->row_off1, plan->row_off2, ev1, ev2));
       } else {
         BF_LAUNCH(PC_EMIT, bytes, st,
                   emit_pairs_kernel<true><<<(unsigned)nb_chunk, EM_THREADS, 0, st>>>(
-                      scan, sw.lo, n_owner, plan->id2, plan->id1, total, b0, part, pgrp, cum, delta, plan->nb, ev1, ev2));
+                      scan, sw.lo, n_owner, plan->id2, plan->id1, total, b0, part, pgrp, cum, delta, plan->nb,
+                      plan->row_off1, plan->row_off2, ev1, ev2));
       }
     }
   }
   if (plan->nU1 > 0) {
     BF_LAUNCH(PC_UNPAIRED, 0, st, emit_unpaired_kernel<false><<<(unsigned)ceil_div(plan->nU1, 256), 256, 0, st>>>(plan->ukeys1, plan->nU1,
-                                                                                    w.ustart1, w.ubase1, ev1, ev2));
+                                                                                    w.ustart1, w.ubase1, plan->row_off1, ev1, ev2));
   }
   if (plan->nU2 > 0) {
     BF_LAUNCH(PC_UNPAIRED, 0, st, emit_unpaired_kernel<true><<<(unsigned)ceil_div(plan->nU2, 256), 256, 0, st>>>(plan->ukeys2, plan->nU2,
-                                                                                   w.ustart2, w.ubase2, ev1, ev2));
+                                                                                   w.ustart2, w.ubase2, plan->row_off2, ev1, ev2));
   }
   return BF_OK;
 }
@@ -944,6 +948,17 @@ int bf_overlap_count(const int32_t* grp1, const int64_t* start1, const int64_t* 
     if (n_pairs_out) *n_pairs_out = p->n_pairs;
   }
   return rc;
+}
+
+int bf_overlap_set_row_offsets(bf_plan* plan, int64_t offset1, int64_t offset2) {
+  bf::OverlapPlan* p = (bf::OverlapPlan*)plan;
+  if (!p || p->magic != bf::OVERLAP_MAGIC || !p->ready) {
+    bf::set_error("bf_overlap_set_row_offsets: plan was not produced by a successful bf_overlap_count");
+    return BF_ERR_STATE;
+  }
+  p->row_off1 = offset1;
+  p->row_off2 = offset2;
+  return BF_OK;
 }
 
 int bf_overlap_emit(const bf_plan* plan, void* ws, int64_t* events1_out, int64_t* events2_out, void* stream) {

@@ -58,8 +58,10 @@ class Workspace:
         cls._cache.clear()
 
 
-def overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how="inner", closed=False, device=None):
-    """All groups of `_overlap_intidxs` in one pass. Returns (events1, events2, n_pairs)."""
+def overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how="inner", closed=False, device=None,
+                    row_offset1=0, row_offset2=0):
+    """All groups of `_overlap_intidxs` in one pass. Returns (events1, events2, n_pairs).
+    row_offset1/2 are added to the reported row numbers (query-sharded callers)."""
     _require_cuda()
     L = _lib.lib()
     device = torch.device(device if device is not None else "cuda")
@@ -81,6 +83,9 @@ def overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how="inner
             int(bool(closed)), _ptr(ws), ws.numel(), C.byref(plan), stream, C.byref(n_rows), C.byref(n_pairs),
         )
         _lib.check(rc, "bf_overlap_count")
+        if row_offset1 or row_offset2:
+            _lib.check(L.bf_overlap_set_row_offsets(C.byref(plan), int(row_offset1), int(row_offset2)),
+                       "bf_overlap_set_row_offsets")
         ev1 = torch.empty(n_rows.value, dtype=torch.int64, device=device)
         ev2 = torch.empty(n_rows.value, dtype=torch.int64, device=device)
         rc = L.bf_overlap_emit(C.byref(plan), _ptr(ws), _ptr(ev1), _ptr(ev2), stream)

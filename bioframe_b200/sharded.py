@@ -52,15 +52,16 @@ def overlap_sharded(grp1, start1, end1, row_offset, grp2, start2, end2, n_groups
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     if world > 1 and broadcast:
         broadcast_targets([grp2, start2, end2], src=src, group=group)
-    ev1, ev2, _ = engine.overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how=how)
+    # the engine adds the shard's position to the query row numbers while it writes them
+    ev1, ev2, _ = engine.overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how=how,
+                                         row_offset1=int(row_offset))
     ev1 = torch.as_tensor(ev1)
     ev2 = torch.as_tensor(ev2)
-    ev1 = torch.where(ev1 >= 0, ev1 + int(row_offset), ev1)
     n_local = torch.tensor([ev1.numel()], dtype=torch.int64, device=ev1.device)
     if world > 1:
         counts = [torch.zeros_like(n_local) for _ in range(world)]
         dist.all_gather(counts, n_local, group=group)
-        counts = [int(c.item()) for c in counts]
+        counts = torch.stack(counts).flatten().tolist()  # one device->host read
     else:
         counts = [int(n_local.item())]
     return ev1, ev2, int(sum(counts[:rank])), int(sum(counts))

@@ -85,6 +85,11 @@ int bf_overlap_count(const int32_t* grp1, const int64_t* start1, const int64_t* 
                      bf_plan* plan, void* stream, int64_t* n_rows_out, int64_t* n_pairs_out);
 int bf_overlap_emit(const bf_plan* plan, void* ws, int64_t* events1_out, int64_t* events2_out,
                     void* stream);
+/* Optional, between _count and _emit: every reported row number of set 1 / set 2 gets this offset
+ * (-1 stays -1).  A query-sharded caller passes the position of its shard in the whole query set, so
+ * that the concatenated per-shard results carry global row numbers without another
+ * pass over the output. */
+int bf_overlap_set_row_offsets(bf_plan* plan, int64_t offset1, int64_t offset2);
 
 /* ---- closest: replaces ops._closest_intidxs (ops.py:919-1040), i.e. the
  * per-group loop around arrops.closest_intervals (arrops.py:601-754) and

@@ -15,10 +15,14 @@ def _i64(x):
     return np.asarray(x, dtype=np.int64) if x is not None else None
 
 
-def overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how="inner", closed=False, device=None):
+def overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how="inner", closed=False, device=None,
+                    row_offset1=0, row_offset2=0):
     s1, e1, s2, e2 = _i64(start1), _i64(end1), _i64(start2), _i64(end2)
     ev1, ev2 = oo.overlap_intidxs_coded(grp1, s1, e1, grp2, s2, e2, n_groups, how=how, closed=closed)
-    return ev1, ev2, int(((ev1 >= 0) & (ev2 >= 0)).sum())
+    n_pairs = int(((ev1 >= 0) & (ev2 >= 0)).sum())
+    ev1 = np.where(ev1 >= 0, ev1 + row_offset1, ev1)
+    ev2 = np.where(ev2 >= 0, ev2 + row_offset2, ev2)
+    return ev1, ev2, n_pairs
 
 
 def closest_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, k=1, ignore_overlaps=False,

@@ -99,3 +99,16 @@ def test_overlap_clamped_tie_order():
         ev1, ev2, _ = engine.overlap_intidxs(None, s1, e1, None, s2, e2, 1, how=how)
         o1, o2 = _oracle_frame(None, s1, e1, None, s2, e2, 1, how)
         assert np.array_equal(ev1.cpu().numpy(), o1) and np.array_equal(ev2.cpu().numpy(), o2)
+
+
+def test_overlap_row_offsets():
+    from bioframe_b200 import engine
+
+    rng = np.random.default_rng(21)
+    g1, s1, e1 = _rand(rng, 3000, 4, 5000, 50)
+    g2, s2, e2 = _rand(rng, 2000, 4, 5000, 50)
+    a0, b0, _ = engine.overlap_intidxs(g1, s1, e1, g2, s2, e2, 4, how="outer")
+    a1, b1, _ = engine.overlap_intidxs(g1, s1, e1, g2, s2, e2, 4, how="outer", row_offset1=10**10, row_offset2=7)
+    a0, b0, a1, b1 = (t.cpu().numpy() for t in (a0, b0, a1, b1))
+    assert np.array_equal(a1, np.where(a0 >= 0, a0 + 10**10, -1))
+    assert np.array_equal(b1, np.where(b0 >= 0, b0 + 7, -1))

@@ -53,9 +53,9 @@ class _TensorEngine:
     def __init__(self, mod):
         self.mod = mod
 
-    def overlap_intidxs(self, g1, s1, e1, g2, s2, e2, nb, how="inner", closed=False):
+    def overlap_intidxs(self, g1, s1, e1, g2, s2, e2, nb, how="inner", closed=False, row_offset1=0, row_offset2=0):
         a, b, n = self.mod.overlap_intidxs(g1.numpy(), s1.numpy(), e1.numpy(), g2.numpy(), s2.numpy(), e2.numpy(), nb,
-                                           how=how, closed=closed)
+                                           how=how, closed=closed, row_offset1=row_offset1, row_offset2=row_offset2)
         return torch.from_numpy(a), torch.from_numpy(b), n
 
 
