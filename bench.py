@@ -68,6 +68,11 @@ def workload(n1, n2, rank, chrom_ids=None):
     return q, t
 
 
+def workload_desc(how, n1, n2):
+    return (f"_overlap_intidxs(how={how!r}) cfg3: {n1} hg38 queries (geom 2kb) per GPU x {n2} peak-like targets, "
+            "unsorted")
+
+
 def cpu_leg(args, steps, warmup):
     """Oracle port on the bounded sample; returns (intervals/s, description, ms/step, rows)."""
     from oracle import ops_oracle as oo
@@ -147,7 +152,8 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "int64",
         "data": "synthetic",
-        "config": {"workload": f"overlap_{args.how}_cfg3_{args.n1:.0e}x{args.n2:.0e}".replace("+", ""), "sample": desc},
+        "config": {"workload": workload_desc(args.how, args.n1, args.n2), "n1_per_gpu": args.n1, "n2": args.n2,
+                   "sample": desc},
         "cpu_baseline": {"value": val, "unit": "intervals/s", "cores": 1, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": "intervals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -411,7 +417,7 @@ def main():
             "dtype": "int64",
             "data": "synthetic",
             "config": {
-                "workload": f"_overlap_intidxs(how={args.how!r}) cfg3: {n1} hg38 queries (geom 2kb) per GPU x {n2} peak-like targets, unsorted",
+                "workload": workload_desc(args.how, n1, n2),
                 "n1_per_gpu": n1,
                 "n2": n2,
                 "rows_out_per_gpu": n_rows,
