@@ -1,0 +1,117 @@
+// bf_sort_pairs: order result pairs by (row of set 1, row of set 2) on the device.
+//
+// bioframe.overlap(how='left') defaults to keep_order=True, i.e.
+// `out_df.sort_values([index1, index2])` over the whole result frame (ops.py:549-550) -- with pandas that
+// one call costs several times the join itself (18.6 s vs 4.0 s at 1e7 x 1e6).  When the frame
+// indexes are monotonic, ordering by labels is ordering by row positions, so the glue can sort the
+// (events1, events2) arrays here before it assembles the frame and skip the pandas sort.
+//   pack (e1, e2) -> one 64-bit key (e1' << bits2 | e2'), -1 mapped to the largest value of its field
+//   (pandas puts NA last) -> stable onesweep radix sort over the used bits -> unpack in place.
+#include "common.cuh"
+#include "keys.cuh"
+#include "radix_sort.cuh"
+#include "../../include/bioframe_b200.h"
+
+namespace bf {
+
+struct PairsWS {
+  u64 *keyA, *keyB;
+  RadixScratch radix;
+};
+static void layout_pairs(Arena& a, i64 n, PairsWS* w) {
+  w->keyA = a.take<u64>(n + 1);
+  w->keyB = a.take<u64>(n + 1);
+  w->radix = take_radix_scratch(a, (u64)n);
+}
+
+__global__ void __launch_bounds__(HIST_THREADS)
+    pack_pairs_kernel(const i64* __restrict__ e1, const i64* __restrict__ e2, u64 n, u64 na1, u64 na2, int bits2,
+                      RadixPlan rp, u64* __restrict__ keys, u64* __restrict__ ghist) {
+  extern __shared__ u32 hist_tabs[];
+  hist_clear(hist_tabs, rp);
+  __syncthreads();
+  const u64 per_block = (u64)HIST_THREADS * 8ull;
+  for (u64 base = (u64)blockIdx.x * per_block; base < n; base += (u64)gridDim.x * per_block) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const u64 i = base + (u64)j * HIST_THREADS + threadIdx.x;
+      const bool ok = i < n;
+      u64 k = 0;
+      if (ok) {
+        const i64 a = e1[i], b = e2[i];
+        k = ((a < 0 ? na1 : (u64)a) << bits2) | (b < 0 ? na2 : (u64)b);
+        keys[i] = k;
+      }
+      hist_add(hist_tabs, rp, k, ok);
+    }
+  }
+  __syncthreads();
+  hist_flush(hist_tabs, rp, ghist);
+}
+__global__ void __launch_bounds__(256)
+    unpack_pairs_kernel(const u64* __restrict__ keys, u64 n, u64 na1, u64 na2, int bits2, i64* __restrict__ e1,
+                        i64* __restrict__ e2) {
+  const u64 mask2 = (1ull << bits2) - 1ull;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u64 k = keys[i];
+    const u64 a = k >> bits2, b = k & mask2;
+    e1[i] = a == na1 ? -1 : (i64)a;
+    e2[i] = b == na2 ? -1 : (i64)b;
+  }
+}
+
+static int sort_pairs_impl(i64* e1, i64* e2, i64 n, i64 max1, i64 max2, void* ws_ptr, size_t ws_bytes, cudaStream_t st) {
+  if (n < 0 || max1 < 0 || max2 < 0) {
+    set_error("bf_sort_pairs: bad argument (n=%lld max1=%lld max2=%lld)", (long long)n, (long long)max1, (long long)max2);
+    return BF_ERR_ARG;
+  }
+  if (n == 0) return BF_OK;
+  if (!e1 || !e2) {
+    set_error("bf_sort_pairs: null pointer");
+    return BF_ERR_ARG;
+  }
+  const u64 na1 = (u64)max1 + 1ull, na2 = (u64)max2 + 1ull;  // the value -1 is packed as
+  const int bits1 = bit_width(na1), bits2 = bit_width(na2);
+  if (bits1 + bits2 > 64) {
+    set_error("bf_sort_pairs: row numbers need %d + %d > 64 bits", bits1, bits2);
+    return BF_ERR_RANGE;
+  }
+  Arena measure(nullptr);
+  PairsWS w;
+  layout_pairs(measure, n, &w);
+  if (!ws_ptr || ws_bytes < measure.off) {
+    set_error("bf_sort_pairs: workspace %zu bytes < required %zu", ws_bytes, measure.off);
+    return BF_ERR_WORKSPACE;
+  }
+  Arena arena(ws_ptr);
+  layout_pairs(arena, n, &w);
+  const RadixPlan rp = make_radix_plan(0, bits1 + bits2);
+  const size_t smem = hist_smem_bytes(rp);
+  BF_CUDA(cudaMemsetAsync(w.radix.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
+  BF_CUDA(cudaFuncSetAttribute(pack_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BF_LAUNCH(PC_GATHER, 24 * n, st,
+            pack_pairs_kernel<<<stream_grid((u64)n, 2048), HIST_THREADS, smem, st>>>(e1, e2, (u64)n, na1, na2, bits2, rp,
+                                                                                    w.keyA, w.radix.hist));
+  SortResult r;
+  BF_TRY(radix_sort_passes<false>(w.keyA, w.keyB, nullptr, nullptr, false, (u64)n, nullptr, rp, w.radix, st, &r,
+                                  PC_SORT_PASS));
+  BF_LAUNCH(PC_GATHER, 24 * n, st,
+            unpack_pairs_kernel<<<stream_grid((u64)n, 1024), 256, 0, st>>>(r.keys, (u64)n, na1, na2, bits2, e1, e2));
+  return BF_OK;
+}
+
+}  // namespace bf
+
+extern "C" {
+size_t bf_sort_pairs_workspace_bytes(int64_t n_rows) {
+  if (n_rows < 0) return 0;
+  bf::Arena a(nullptr);
+  bf::PairsWS w;
+  bf::layout_pairs(a, n_rows, &w);
+  return a.off;
+}
+int bf_sort_pairs(int64_t* events1, int64_t* events2, int64_t n_rows, int64_t max1, int64_t max2, void* ws,
+                  size_t ws_bytes, void* stream) {
+  return bf::sort_pairs_impl((i64*)events1, (i64*)events2, n_rows, max1, max2, ws, ws_bytes, (cudaStream_t)stream);
+}
+}

@@ -93,6 +93,22 @@ def overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how="inner
     return ev1, ev2, n_pairs.value
 
 
+def sort_pairs(ev1, ev2, max1, max2):
+    """Order device-resident result pairs in place by (events1, events2), -1 last (keep_order=True of
+    bioframe.overlap, ops.py:549-550, for monotonic indexes)."""
+    _require_cuda()
+    L = _lib.lib()
+    n = int(ev1.numel())
+    if n == 0:
+        return ev1, ev2
+    device = ev1.device
+    with torch.cuda.device(device):
+        ws = Workspace.get(device, max(L.bf_sort_pairs_workspace_bytes(n), 256))
+        rc = L.bf_sort_pairs(_ptr(ev1), _ptr(ev2), n, int(max1), int(max2), _ptr(ws), ws.numel(), _stream_ptr(device))
+        _lib.check(rc, "bf_sort_pairs")
+    return ev1, ev2
+
+
 def cluster(grp, start, end, n_groups, min_dist=0, want_ids=True, want_table=True, want_row_spans=False, device=None):
     """merge_intervals over all groups (group code order = sorted key order).
 

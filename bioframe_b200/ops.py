@@ -79,7 +79,7 @@ def _to_host(t):
 # --------------------------------------------------------------------------
 # overlap
 # --------------------------------------------------------------------------
-def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _group_order=None):
+def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _group_order=None, _sort_pairs=False):
     """Integer row positions of overlapping pairs, -1 where a kept row has no
     partner.  Mirrors ops._overlap_intidxs (ops.py:242-338): groups are
     (chrom, *on); the group blocks come in the iteration order of
@@ -135,6 +135,8 @@ def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _gro
         n_groups,
         how=how,
     )
+    if _sort_pairs:  # keep_order on the device: rows by (row of df1, row of df2), -1 last
+        ev1, ev2 = _engine.sort_pairs(ev1, ev2, max(len(df1) - 1, 0), max(len(df2) - 1, 0))
     return _to_host(ev1), _to_host(ev2)
 
 
@@ -204,7 +206,13 @@ def overlap(
         _verify_columns(df1, on)
         _verify_columns(df2, on)
 
-    ev1, ev2 = _overlap_intidxs(df1, df2, how=how, cols1=cols1, cols2=cols2, on=on)
+    # keep_order=True sorts the result by (index1, index2) labels (ops.py:549-550).  For strictly
+    # increasing indexes that is the order of the row positions, which the device produces directly
+    # (bf_sort_pairs) -- pandas' sort_values over the assembled frame dominates the reference's run time.
+    device_order = bool(keep_order) and all(
+        ix.is_monotonic_increasing and ix.is_unique for ix in (df1.index, df2.index)
+    )
+    ev1, ev2 = _overlap_intidxs(df1, df2, how=how, cols1=cols1, cols2=cols2, on=on, _sort_pairs=device_order)
 
     stem = return_index if isinstance(return_index, str) else "index"
     icol1, icol2 = stem + suffixes[0], stem + suffixes[1]
@@ -245,7 +253,7 @@ def overlap(
             parts["ov"][miss1 | miss2] = None
 
     out = pd.concat([parts.get(k) for k in ("i1", "in1", "i2", "in2", "ov")], axis=1)
-    if keep_order:
+    if keep_order and not device_order:
         out = out.sort_values([icol1, icol2])
     if not return_index:
         out.drop([icol1, icol2], axis=1, inplace=True)

@@ -91,6 +91,14 @@ int bf_overlap_emit(const bf_plan* plan, void* ws, int64_t* events1_out, int64_t
  * pass over the output. */
 int bf_overlap_set_row_offsets(bf_plan* plan, int64_t offset1, int64_t offset2);
 
+/* ---- keep_order: replaces `out_df.sort_values([index1, index2])` of ops.overlap (ops.py:549-550) for
+ * frames whose indexes are monotonic (labels ordered like row positions).  Sorts the pairs in place by
+ * (events1, events2); -1 sorts after every row number of its column (pandas: NA last).  max1 / max2 are
+ * upper bounds of the row numbers in the two columns (they size the key). */
+size_t bf_sort_pairs_workspace_bytes(int64_t n_rows);
+int bf_sort_pairs(int64_t* events1, int64_t* events2, int64_t n_rows, int64_t max1, int64_t max2, void* ws,
+                  size_t ws_bytes, void* stream);
+
 /* ---- closest: replaces ops._closest_intidxs (ops.py:919-1040), i.e. the
  * per-group loop around arrops.closest_intervals (arrops.py:601-754) and
  * arrops._closest_intervals_nooverlap (arrops.py:506-598), plus the

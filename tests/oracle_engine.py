@@ -59,3 +59,10 @@ def complement(region, start, end, bounds_lo, bounds_hi, device=None):
     region = np.zeros(len(start), np.int32) if region is None else np.asarray(region)
     oc, os_, oe = oo.complement_core(region, _i64(start), _i64(end), list(zip(b0.tolist(), b1.tolist())))
     return oc.astype(np.int32), os_, oe
+
+
+def sort_pairs(ev1, ev2, max1, max2):
+    a = np.where(ev1 < 0, max1 + 1, ev1)
+    b = np.where(ev2 < 0, max2 + 1, ev2)
+    order = np.lexsort([b, a])
+    return ev1[order], ev2[order]

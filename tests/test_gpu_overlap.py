@@ -112,3 +112,18 @@ def test_overlap_row_offsets():
     a0, b0, a1, b1 = (t.cpu().numpy() for t in (a0, b0, a1, b1))
     assert np.array_equal(a1, np.where(a0 >= 0, a0 + 10**10, -1))
     assert np.array_equal(b1, np.where(b0 >= 0, b0 + 7, -1))
+
+
+@pytest.mark.parametrize("n", [0, 1, 5000, 300000])
+def test_sort_pairs(n):
+    from bioframe_b200 import engine
+
+    rng = np.random.default_rng(n)
+    a = rng.integers(-1, 50000, n).astype(np.int64)
+    b = rng.integers(-1, 7000, n).astype(np.int64)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    engine.sort_pairs(ta, tb, 49999, 6999)
+    ka = np.where(a < 0, 50000, a)
+    kb = np.where(b < 0, 7000, b)
+    order = np.lexsort([kb, ka])
+    assert np.array_equal(ta.cpu().numpy(), a[order]) and np.array_equal(tb.cpu().numpy(), b[order])
