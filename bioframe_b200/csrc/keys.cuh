@@ -117,8 +117,7 @@ static __global__ void __launch_bounds__(256) extent_kernel(const i32* __restric
   u64 lhi = 0;
   bool bad = false;
   i32 glo = 0x7fffffff, ghi = (i32)0x80000000;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-    i64 a = s[i], b = e[i];
+  auto take = [&](i64 a, i64 b, i32 g) {
     if (point_adjust && a == b) b += 1;
     const i64 top = max(a, b);
     lo = min(lo, min(a, b));
@@ -127,14 +126,28 @@ static __global__ void __launch_bounds__(256) extent_kernel(const i32* __restric
     bad |= b < a;
     const u64 len = (u64)b - (u64)a;  // exact for b >= a, whatever the magnitudes
     lhi = b < a ? lhi : max(lhi, len);
-    i32 g = 0;
     if (grp) {
-      g = grp[i];
       glo = min(glo, g);
       ghi = max(ghi, g);
     }
     if ((u32)g < (u32)nb && table[g] < top) atomicMax((i64*)&table[g], top);
+  };
+  // four rows per thread and iteration, all twelve loads issued before the first use
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    i64 a[4], b[4];
+    i32 g[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a[u] = s[i + u * stride];
+      b[u] = e[i + u * stride];
+      g[u] = grp ? grp[i + u * stride] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) take(a[u], b[u], g[u]);
   }
+  for (; i < n; i += stride) take(s[i], e[i], grp ? grp[i] : 0);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));

@@ -252,7 +252,7 @@ __device__ __forceinline__ i64 gallop_hi(const u64* __restrict__ other, i64 from
 }
 
 template <bool B_SIDE, bool FLAGS, int IPT>
-__global__ void __launch_bounds__(SC_THREADS)
+__global__ void __launch_bounds__(SC_THREADS, 5)
     search_count_kernel(const u64* __restrict__ mine, const u32* __restrict__ mine_id, i64 n,
                         const u64* __restrict__ other, i64 m, const u64* __restrict__ other_pmax,
                         const i64* __restrict__ bracket, KeyLayout L, int closed, u32* __restrict__ lo_out,

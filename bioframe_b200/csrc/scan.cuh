@@ -98,57 +98,53 @@ __device__ __forceinline__ u64 block_excl_max_u64(u64 v, u64* s_tmp) {
 }
 
 // ---- spine: one block turns per-tile partials into exclusive prefixes ----
-// Coalesced chunks of 1024 entries, block scan per chunk with a carried prefix
-// (a few microseconds for the ~5e4 tiles of a 1e8-row call).
+// Each of the 32 warps owns a contiguous range and walks it 32 entries at a time (coalesced, no block
+// barrier inside the loops): range totals -> scan of the 32 totals -> ranges rewritten as exclusive
+// prefixes with a running carry.
 template <bool IS_MAX>
 static __global__ void __launch_bounds__(1024) spine_scan_kernel(u64* __restrict__ spine, u64 ntiles,
                                                                  u64* __restrict__ total_out) {
   __shared__ u64 s_warp[32];
-  __shared__ u64 s_carry;
   const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid == 0) s_carry = 0;
+  const u64 per = ((ntiles + 31) / 32 + 31) / 32 * 32;  // entries per warp, a multiple of 32
+  const u64 lo = (u64)w * per;
+  const u64 hi = lo + per < ntiles ? lo + per : ntiles;
+  auto op = [](u64 a, u64 b) { return IS_MAX ? (a > b ? a : b) : a + b; };
+  u64 acc = 0;
+  for (u64 i = lo + lane; i < hi; i += 32) acc = op(acc, spine[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc = op(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+  if (lane == 0) s_warp[w] = acc;
   __syncthreads();
-  for (u64 base = 0; base < ntiles; base += 1024) {
-    const u64 i = base + tid;
-    const u64 v = i < ntiles ? spine[i] : 0ull;
+  if (w == 0) {
+    const u64 x = s_warp[lane];
+    u64 y = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u64 t = __shfl_up_sync(0xffffffffu, y, o);
+      if (lane >= (u32)o) y = op(y, t);
+    }
+    u64 ex = __shfl_up_sync(0xffffffffu, y, 1);
+    if (lane == 0) ex = 0;
+    s_warp[lane] = ex;  // exclusive prefix of the warps
+    if (lane == 31 && total_out) *total_out = y;
+  }
+  __syncthreads();
+  u64 carry = s_warp[w];
+  for (u64 base = lo; base < hi; base += 32) {
+    const u64 i = base + lane;
+    const u64 v = i < hi ? spine[i] : 0ull;
     u64 inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const u64 t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= (u32)o) inc = IS_MAX ? (t > inc ? t : inc) : inc + t;
+      if (lane >= (u32)o) inc = op(inc, t);
     }
-    if (lane == 31) s_warp[w] = inc;
-    __syncthreads();
-    if (w == 0) {  // scan of the 32 warp totals
-      const u64 x = s_warp[lane];
-      u64 y = x;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u64 t = __shfl_up_sync(0xffffffffu, y, o);
-        if (lane >= (u32)o) y = IS_MAX ? (t > y ? t : y) : y + t;
-      }
-      // exclusive prefix of the warps
-      u64 ex = __shfl_up_sync(0xffffffffu, y, 1);
-      if (lane == 0) ex = 0;
-      s_warp[lane] = ex;
-    }
-    __syncthreads();
-    const u64 carry = s_carry;
-    u64 before_warp = s_warp[w];
-    // exclusive value for this entry = carry (op) warps before (op) lanes before
     u64 up = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane == 0) up = 0;
-    u64 excl = IS_MAX ? (before_warp > up ? before_warp : up) : before_warp + up;
-    excl = IS_MAX ? (carry > excl ? carry : excl) : carry + excl;
-    if (i < ntiles) spine[i] = excl;
-    __syncthreads();
-    if (tid == 1023) {
-      const u64 incl = IS_MAX ? (excl > v ? excl : v) : excl + v;
-      s_carry = incl;
-    }
-    __syncthreads();
+    if (i < hi) spine[i] = op(carry, up);
+    carry = op(carry, __shfl_sync(0xffffffffu, inc, 31));
   }
-  if (tid == 0 && total_out) *total_out = s_carry;
 }
 
 // ---- per-tile sums of a u32 array (when no producer wrote the spine) ----
