@@ -72,6 +72,8 @@ SIGNATURES = {
     "bf_cluster_emit": (C.c_int, [C.POINTER(Plan), _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "bf_coverage_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "bf_coverage": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _i32, _p, _sz, _p, _p]),
+    "bf_count_overlaps_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "bf_count_overlaps": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _p, _sz, _p, _p]),
     "bf_complement_workspace_bytes": (_sz, [_i64, _i32]),
     "bf_complement_count": (
         C.c_int,

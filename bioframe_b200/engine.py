@@ -168,6 +168,25 @@ def coverage(grp1, start1, end1, grp2, start2, end2, n_groups, device=None):
     return cov
 
 
+def count_overlaps(grp1, start1, end1, grp2, start2, end2, n_groups, closed=False, device=None):
+    """Number of set-2 intervals overlapping every row of set 1 -> int64[n1] (device, input row order)."""
+    _require_cuda()
+    L = _lib.lib()
+    device = torch.device(device if device is not None else "cuda")
+    s1, e1 = _as(start1, torch.int64, device), _as(end1, torch.int64, device)
+    s2, e2 = _as(start2, torch.int64, device), _as(end2, torch.int64, device)
+    g1 = _as(grp1, torch.int32, device) if n_groups > 1 else None
+    g2 = _as(grp2, torch.int32, device) if n_groups > 1 else None
+    n1, n2 = int(s1.numel()), int(s2.numel())
+    with torch.cuda.device(device):
+        ws = Workspace.get(device, max(L.bf_count_overlaps_workspace_bytes(n1, n2, n_groups), 256))
+        counts = torch.empty(n1, dtype=torch.int64, device=device)
+        rc = L.bf_count_overlaps(_ptr(g1), _ptr(s1), _ptr(e1), n1, _ptr(g2), _ptr(s2), _ptr(e2), n2, n_groups,
+                                 int(bool(closed)), _ptr(ws), ws.numel(), _stream_ptr(device), _ptr(counts))
+        _lib.check(rc, "bf_count_overlaps")
+    return counts
+
+
 def complement(region, start, end, bounds_lo, bounds_hi, device=None):
     """Gaps of the (already clipped) intervals inside each view region.
     -> (region int32[G], start int64[G], end int64[G]) on device, regions in code order."""

@@ -25,7 +25,7 @@ from . import engine as _engine
 from .core import checks
 from .core.specs import _get_default_colnames, _verify_columns
 
-__all__ = ["overlap", "closest", "cluster", "merge", "complement", "coverage"]
+__all__ = ["overlap", "closest", "cluster", "merge", "complement", "coverage", "count_overlaps", "setdiff"]
 
 _INT64_MAX = np.iinfo(np.int64).max
 
@@ -608,3 +608,58 @@ def complement(df, view_df=None, view_name_col="name", cols=None, cols_view=None
     return pd.DataFrame(
         {ck: chrom_col, sk: _to_host(gs), ek: _to_host(ge), "view_region": [names[r] for r in reg]}
     ).reset_index(drop=True)
+
+
+# --------------------------------------------------------------------------
+# count_overlaps / setdiff  (SURVEY.md 8f "next" #1: fused, no pair enumeration)
+# --------------------------------------------------------------------------
+def _overlap_counts(df1, df2, cols1, cols2, on):
+    """int64 count of df2 intervals overlapping every df1 row (0 for rows with a null key)."""
+    ck1, sk1, ek1 = _get_default_colnames() if cols1 is None else cols1
+    ck2, sk2, ek2 = _get_default_colnames() if cols2 is None else cols2
+    by1, by2 = [ck1], [ck2]
+    if on is not None:
+        if not isinstance(on, list):
+            raise ValueError("on=[] must be None or list")
+        if (ck1 in on) or (ck2 in on):
+            raise ValueError("on=[] should not contain chromosome colnames")
+        _verify_columns(df1, on)
+        _verify_columns(df2, on)
+        by1, by2 = by1 + on, by2 + on
+    codes1, keys1 = _group_keys(df1, by1)
+    codes2, keys2 = _group_keys(df2, by2)
+    union = sorted(set(keys1) | set(keys2), key=str)
+    rank = {key: r for r, key in enumerate(union)}
+    t1 = np.array([rank[k] for k in keys1], dtype=np.int32)
+    t2 = np.array([rank[k] for k in keys2], dtype=np.int32)
+    v1, v2 = np.flatnonzero(codes1 >= 0), np.flatnonzero(codes2 >= 0)
+    counts = np.zeros(len(df1), dtype=np.int64)
+    if len(v1):
+        got = _engine.count_overlaps(
+            t1[codes1[v1]], _int64_coords(df1, sk1)[v1], _int64_coords(df1, ek1)[v1],
+            t2[codes2[v2]] if len(v2) else np.empty(0, np.int32),
+            _int64_coords(df2, sk2)[v2], _int64_coords(df2, ek2)[v2], max(len(union), 1),
+        )
+        counts[v1] = _to_host(got)
+    return counts
+
+
+def count_overlaps(df1, df2, suffixes=("", "_"), return_input=True, cols1=None, cols2=None, on=None):
+    """Number of df2 intervals overlapping every df1 interval (ops.py:1371-1438).  The reference left-joins
+    and counts the pair list per query; the kernel counts without enumerating pairs.  Like the reference,
+    resets df1's index in place."""
+    ck1, sk1, ek1 = _get_default_colnames() if cols1 is None else cols1
+    ck2, sk2, ek2 = _get_default_colnames() if cols2 is None else cols2
+    df1.reset_index(inplace=True, drop=True)
+    checks.is_bedframe(df1, raise_errors=True, cols=[ck1, sk1, ek1])
+    checks.is_bedframe(df2, raise_errors=True, cols=[ck2, sk2, ek2])
+    # the reference counts a nullable Int64 index column per query, which yields a nullable Int64 column
+    out = pd.DataFrame({"count": pd.array(_overlap_counts(df1, df2, cols1, cols2, on), dtype=pd.Int64Dtype())})
+    if return_input:
+        out = pd.concat([df1, out], axis="columns")
+    return out
+
+
+def setdiff(df1, df2, cols1=None, cols2=None, on=None):
+    """Rows of df1 that overlap no interval of df2 (ops.py:1333-1368), original index kept."""
+    return df1.iloc[np.flatnonzero(_overlap_counts(df1, df2, cols1, cols2, on) == 0)]

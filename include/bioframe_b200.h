@@ -157,6 +157,15 @@ int bf_coverage(const int32_t* grp1, const int64_t* start1, const int64_t* end1,
                 const int32_t* grp2, const int64_t* start2, const int64_t* end2, int64_t n2,
                 int32_t n_groups, void* ws, size_t ws_bytes, void* stream, int64_t* coverage_out);
 
+/* ---- count_overlaps: replaces ops.count_overlaps (ops.py:1371-1438: left overlap + groupby count) and
+ * serves ops.setdiff (ops.py:1333-1368: rows with count 0).  counts_out: int64[n1] in input row order.
+ * No pairs are enumerated (two binary searches per query over the targets sorted by start and by end'). */
+size_t bf_count_overlaps_workspace_bytes(int64_t n1, int64_t n2, int32_t n_groups);
+int bf_count_overlaps(const int32_t* grp1, const int64_t* start1, const int64_t* end1, int64_t n1,
+                      const int32_t* grp2, const int64_t* start2, const int64_t* end2, int64_t n2,
+                      int32_t n_groups, int32_t closed, void* ws, size_t ws_bytes, void* stream,
+                      int64_t* counts_out);
+
 /* ---- complement: replaces the per-view-region loop of ops.complement
  * (ops.py:1644-1685) around arrops.complement_intervals (arrops.py:482-503).
  * `region` = code of the view region each (already clipped) interval belongs

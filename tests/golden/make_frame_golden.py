@@ -80,6 +80,11 @@ def main():
             add(f"cluster_{tag}_on", "cluster", df=df1, on=["strand"])
             add(f"merge_{tag}_on", "merge", df=df1, on=["strand"], min_dist=None)
         add(f"coverage_{tag}", "coverage", df1=df1, df2=df2)
+        add(f"count_overlaps_{tag}", "count_overlaps", df1=df1, df2=df2)
+        add(f"setdiff_{tag}", "setdiff", df1=df1, df2=df2)
+        if tag != "na":
+            add(f"count_overlaps_{tag}_on", "count_overlaps", df1=df1, df2=df2, on=["strand"], return_input=False)
+            add(f"setdiff_{tag}_on", "setdiff", df1=df1, df2=df2, on=["strand"])
         df1, df2 = frames(rng, tie_free=True, **opts)
         add(f"closest_{tag}_k1", "closest", df1=df1, df2=df2)
         add(f"closest_{tag}_k3", "closest", df1=df1, df2=df2, k=3, return_index=True, return_overlap=True)

@@ -66,3 +66,8 @@ def sort_pairs(ev1, ev2, max1, max2):
     b = np.where(ev2 < 0, max2 + 1, ev2)
     order = np.lexsort([b, a])
     return ev1[order], ev2[order]
+
+
+def count_overlaps(grp1, start1, end1, grp2, start2, end2, n_groups, closed=False, device=None):
+    ev1, ev2, _ = overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how="inner", closed=closed)
+    return np.bincount(ev1, minlength=len(start1)).astype(np.int64)

@@ -44,7 +44,7 @@ def _install():
 
         our_ops._engine = oracle_engine
         our_arrops._engine = oracle_engine
-    for name in ("overlap", "closest", "cluster", "merge", "complement", "coverage",
+    for name in ("overlap", "closest", "cluster", "merge", "complement", "coverage", "count_overlaps", "setdiff",
                  "_overlap_intidxs", "_closest_intidxs"):
         setattr(ref_ops, name, getattr(our_ops, name))
         if hasattr(bioframe, name):

@@ -124,3 +124,31 @@ def test_complement_golden(arrops_golden):
             _, gs, ge = engine.complement(None, s1, e1, np.array([b[0]]), np.array([b[1]]))
             assert np.array_equal(gs.cpu().numpy(), g[f"{name}/compl_{tag}_s"]), (name, tag)
             assert np.array_equal(ge.cpu().numpy(), g[f"{name}/compl_{tag}_e"]), (name, tag)
+
+
+@pytest.mark.parametrize("closed", [False, True])
+@pytest.mark.parametrize("n1,n2,nb,span", [(0, 5, 2, 50), (5, 0, 2, 50), (300, 200, 1, 500), (5000, 3000, 7, 4000),
+                                            (20000, 9000, 25, 100000), (9000, 30000, 300, 3000)])
+def test_count_overlaps_matches_oracle(n1, n2, nb, span, closed):
+    from bioframe_b200 import engine
+
+    rng = np.random.default_rng(n1 + 5 * n2 + nb)
+    g1, s1, e1 = _rand(rng, n1, nb, span, 200, neg=(nb == 7))
+    g2, s2, e2 = _rand(rng, n2, nb, span, 60, neg=(nb == 7))
+    got = engine.count_overlaps(g1, s1, e1, g2, s2, e2, nb, closed=closed).cpu().numpy()
+    i, _ = oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, nb, how="inner", closed=closed)
+    assert np.array_equal(got, np.bincount(i, minlength=n1))
+
+
+def test_count_overlaps_int64_max():
+    from bioframe_b200 import engine
+
+    big = np.iinfo(np.int64).max
+    rng = np.random.default_rng(8)
+    g1, s1, e1 = _rand(rng, 3000, 3, 10**8, 4000)
+    g2, s2, e2 = _rand(rng, 2000, 3, 10**8, 4000)
+    e1[::9] = big
+    e2[::13] = big
+    got = engine.count_overlaps(g1, s1, e1, g2, s2, e2, 3).cpu().numpy()
+    i, _ = oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, 3, how="inner")
+    assert np.array_equal(got, np.bincount(i, minlength=3000))
