@@ -401,6 +401,18 @@ def main():
         per_launch_bytes = sp["bytes"] / max(sp["timed"], 1)
         achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         launches = sum(v["launches"] for v in prof.values())
+        # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of a 1e8-row launch,
+        # scaled to this run's mix of launches (passes over n1 and over n2 rows, first pass reads no row id)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tj = json.load(f)
+            npass = max(sp["timed"] // (2 * args.steps), 1)  # passes per set
+            per_row_first, per_row_other = tj["first_pass_bytes"] / tj["rows"], tj["other_pass_bytes"] / tj["rows"]
+            total_bytes = (n1 + n2) * (per_row_first + (npass - 1) * per_row_other)
+            traffic = total_bytes / (2 * npass)
+        except Exception:
+            pass
         a_alg = 256 * (n1 + n2) + 20 * n_rows
         a_io = 20 * (n1 + n2) + 16 * n_rows
         line = {
@@ -437,7 +449,9 @@ def main():
                 "peak_source": peak_src,
                 "unit": "GB/s",
                 "frac": achieved / peak if peak else None,
-                "traffic": None,
+                "traffic": traffic,
+                "traffic_source": "profiles/r1_traffic.json (ncu dram bytes of a 1e8-row launch, scaled per row)",
+                "algorithmic_bytes_per_launch": per_launch_bytes,
                 "launches_timed": sp["timed"],
                 "avg_launch_ms": per_launch_ms,
                 "whole_step": {
