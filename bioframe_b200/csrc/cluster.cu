@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "keys.cuh"
 #include "lookback.cuh"
+#include "lut.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
 #include "sorted_set.cuh"
@@ -306,6 +307,7 @@ struct CoverageWS {
   u64 *slin, *elin;  // [n2+1] merged intervals on the linear (group, coordinate) axis of the key layout
   u64* plen;         // [n2+1] exclusive prefix of merged lengths
   u64* spine;        // [tiles + 1]
+  u32* lut;          // direct-address table over slin
 };
 static void layout_coverage(Arena& a, i64 n2, i32 nb, CoverageWS* w) {
   layout_cluster(a, n2, nb, &w->cl);
@@ -313,6 +315,7 @@ static void layout_coverage(Arena& a, i64 n2, i32 nb, CoverageWS* w) {
   w->elin = a.take<u64>(n2 + 1);
   w->plen = a.take<u64>(n2 + 1);
   w->spine = a.take<u64>(scan_tiles((u64)n2) + 2);
+  w->lut = a.take<u32>(lut_words(n2));
 }
 
 // per-tile sums of the merged lengths (n lives on the device)
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(SC_THREADS)
 // before the group's offset, so they count in full in both F(end) and F(start) and cancel.
 __global__ void __launch_bounds__(256)
     coverage_kernel(const i32* __restrict__ grp1, const i64* __restrict__ s1, const i64* __restrict__ e1, i64 n1,
-                    const i64* __restrict__ n_clusters, KeyLayout L, const u64* __restrict__ slin,
+                    const i64* __restrict__ n_clusters, KeyLayout L, Lut lut, const u64* __restrict__ slin,
                     const u64* __restrict__ elin, const u64* __restrict__ plen, i64* __restrict__ cov) {
   const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n1) return;
@@ -389,7 +392,7 @@ __global__ void __launch_bounds__(256)
     return plen[j - 1] + ((x < E ? x : E) - slin[j - 1]);
   };
   const u64 xs = lin(s1[r]), xe = lin(e1[r]);
-  const i64 js = lower_bound_by(0, C, [&](i64 m) { return slin[m] < xs; });
+  const i64 js = lut_count_below<false>(slin, lut, xs);  // = #{S < xs}: one table sector + a search inside the bucket
   // the end is rarely more than a few merged intervals further on: gallop from js
   i64 lo = js, hi = js, step = 1;
   for (;;) {
@@ -442,9 +445,11 @@ static int coverage_impl(const i32* grp1, const i64* s1, const i64* e1, i64 n1, 
   BF_LAUNCH(PC_COVERAGE, 16 * n2, st, merged_length_tiles_kernel<<<tiles, SC_THREADS, 0, st>>>(tab, w.spine));
   BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.spine, (u64)tiles, nullptr));
   BF_LAUNCH(PC_COVERAGE, 44 * n2, st, merged_table_kernel<<<tiles, SC_THREADS, 0, st>>>(tab, L, w.spine, w.slin, w.elin, w.plen));
+  const Lut lut = make_lut(w.lut, n2, 0, 1ull << L.B, 0);
+  BF_TRY(launch_lut_build(w.slin, 0, tab.n_clusters, lut, w.lut, st, PC_COVERAGE));
   BF_LAUNCH(PC_COVERAGE, 28 * n1, st,
             coverage_kernel<<<(unsigned)ceil_div(n1, 256), 256, 0, st>>>(nb > 1 ? grp1 : nullptr, s1, e1, n1, tab.n_clusters, L,
-                                                                        w.slin, w.elin, w.plen, cov));
+                                                                        lut, w.slin, w.elin, w.plen, cov));
   return BF_OK;
 }
 

@@ -10,6 +10,7 @@
 // Two binary searches per query, any query order.
 #include "common.cuh"
 #include "keys.cuh"
+#include "lut.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
 #include "sorted_set.cuh"
@@ -21,18 +22,21 @@ struct CountWS {
   SortBufs by_start, by_end;
   RadixScratch radix;
   LayoutScratch layout;
+  u32 *lutS, *lutE;  // direct-address tables over the two target orders
 };
 static void layout_count(Arena& a, i64 n2, i32 nb, CountWS* w) {
   take_sort_bufs(a, n2, &w->by_start);
   take_sort_bufs(a, n2, &w->by_end);
   w->radix = take_radix_scratch(a, (u64)n2);
   w->layout = take_layout_scratch(a, nb);
+  w->lutS = a.take<u32>(lut_words(n2));
+  w->lutE = a.take<u32>(lut_words(n2));
 }
 
 __global__ void __launch_bounds__(256)
     count_overlaps_kernel(const i32* __restrict__ grp1, const i64* __restrict__ s1, const i64* __restrict__ e1, i64 n1,
-                          const u64* __restrict__ kS, const u64* __restrict__ kE, i64 n2, KeyLayout L, int closed,
-                          i64* __restrict__ counts) {
+                          const u64* __restrict__ kS, const u64* __restrict__ kE, i64 n2, KeyLayout L, Lut lutS,
+                          Lut lutE, int closed, i64* __restrict__ counts) {
   const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n1) return;
   const u32 g = grp1 ? (u32)grp1[r] : 0u;
@@ -43,10 +47,8 @@ __global__ void __launch_bounds__(256)
   const u64 off = L.goff[g];
   const u64 xs = off + ((u64)a - L.cmin), xe = off + ((u64)b - L.cmin);
   // closed=True also counts intervals that only touch (arrops.py:339,342 with side="right")
-  const i64 started = closed ? lower_bound_by(0, n2, [&](i64 m) { return key_cs(kS[m], L) <= xe; })
-                             : lower_bound_by(0, n2, [&](i64 m) { return key_cs(kS[m], L) < xe; });
-  const i64 ended = closed ? lower_bound_by(0, n2, [&](i64 m) { return key_cs(kE[m], L) < xs; })
-                           : lower_bound_by(0, n2, [&](i64 m) { return key_cs(kE[m], L) <= xs; });
+  const i64 started = closed ? lut_count_below<true>(kS, lutS, xe) : lut_count_below<false>(kS, lutS, xe);
+  const i64 ended = closed ? lut_count_below<false>(kE, lutE, xs) : lut_count_below<true>(kE, lutE, xs);
   counts[r] = started - ended;
 }
 
@@ -86,9 +88,12 @@ static int count_overlaps_impl(const i32* grp1, const i64* s1, const i64* e1, i6
   BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, KEY_POINT_ADJUST | KEY_NO_TIE_FIX, w.by_start, w.radix, st, &rS));
   BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, KEY_POINT_ADJUST | KEY_NO_TIE_FIX | KEY_BY_END, w.by_end,
                    w.radix, st, &rE));
+  const Lut lutS = make_lut(w.lutS, n2, 0, 1ull << L.B, L.LB), lutE = make_lut(w.lutE, n2, 0, 1ull << L.B, L.LB);
+  BF_TRY(launch_lut_build(rS.keys, n2, nullptr, lutS, w.lutS, st, PC_COVERAGE));
+  BF_TRY(launch_lut_build(rE.keys, n2, nullptr, lutE, w.lutE, st, PC_COVERAGE));
   BF_LAUNCH(PC_COVERAGE, 28 * n1, st,
             count_overlaps_kernel<<<(unsigned)ceil_div(n1, 256), 256, 0, st>>>(nb > 1 ? grp1 : nullptr, s1, e1, n1, rS.keys,
-                                                                              rE.keys, n2, L, closed, counts));
+                                                                              rE.keys, n2, L, lutS, lutE, closed, counts));
   return BF_OK;
 }
 
