@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "keys.cuh"
 #include "lookback.cuh"
+#include "lut.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
 #include "sorted_set.cuh"
@@ -47,6 +48,7 @@ struct ClosestWS {
   i64 *obase, *ubase;  // [nb+1] first output row of a group's matched / unmatched block
   i64* header;      // n_rows, n_matched_rows
   u64* nq;          // [1] device count for the query sort
+  u32 *lutS, *lutE; // direct-address tables over the two target orders
 };
 static void layout_closest(Arena& a, i64 n1, i64 n2, i32 nb, ClosestWS* w) {
   take_sort_bufs(a, n2, &w->by_start);
@@ -69,6 +71,8 @@ static void layout_closest(Arena& a, i64 n1, i64 n2, i32 nb, ClosestWS* w) {
   w->ubase = a.take<i64>(nb + 2);
   w->header = a.take<i64>(4);
   w->nq = a.take<u64>(1);
+  w->lutS = a.take<u32>(lut_words(n2));
+  w->lutE = a.take<u32>(lut_words(n2));
 }
 
 struct ClosestArgs {  // everything a query thread needs (kernel parameter)
@@ -81,6 +85,7 @@ struct ClosestArgs {  // everything a query thread needs (kernel parameter)
   const i64 *seg, *qseg;
   const u64* qkey;   // (rank << 32 | row) in (group, row) order; null: identity (one group)
   KeyLayout L;
+  Lut lutS, lutE;
   i64 n1, n2;
   i32 k, self, ignore_overlaps, k_up, k_dn;
 };
@@ -176,10 +181,12 @@ __device__ __forceinline__ void closest_probe(const ClosestArgs& A, i64 t, Probe
   const u64 xe_adj = xe + (a == b);
   P->xs = xs;
   P->xe = xe;
-  P->loA = lower_bound_by(t0, t1, [&](i64 m) { return key_cs(A.kS[m], L) < xs; });
-  P->begin = lower_bound_by(P->loA, t1, [&](i64 m) { return key_cs(A.kS[m], L) < xe; });
-  P->hiA = (a == b) ? lower_bound_by(P->begin, t1, [&](i64 m) { return key_cs(A.kS[m], L) < xe_adj; }) : P->begin;
-  P->stop = lower_bound_by(t0, t1, [&](i64 m) { return key_cs(A.kE[m], L) <= xs; });
+  // positions on the whole sorted arrays: the query's coordinates lie inside its group's stretch of the
+  // linear axis, so targets of other groups fall entirely below or above every probe
+  P->loA = lut_count_below<false>(A.kS, A.lutS, xs);
+  P->begin = lut_count_below<false>(A.kS, A.lutS, xe);
+  P->hiA = (a == b) ? lut_count_below<false>(A.kS, A.lutS, xe_adj) : P->begin;
+  P->stop = lut_count_below<true>(A.kE, A.lutE, xs);
   const bool fwd = A.along ? A.along[row] != 0 : true;
   P->k_left = fwd ? A.k_up : A.k_dn;   // arrops.py:667-706: "-" rows look right for upstream
   P->k_right = fwd ? A.k_dn : A.k_up;
@@ -439,6 +446,10 @@ static int closest_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   A.qseg = w.qseg;
   A.qkey = qkey;
   A.L = L;
+  A.lutS = make_lut(w.lutS, n2, 0, 1ull << L.B, L.LB);
+  A.lutE = make_lut(w.lutE, n2, 0, 1ull << L.B, L.LB);
+  BF_TRY(launch_lut_build(rS.keys, n2, nullptr, A.lutS, w.lutS, st, PC_CLOSEST));
+  BF_TRY(launch_lut_build(rE.keys, n2, nullptr, A.lutE, w.lutE, st, PC_CLOSEST));
   A.n1 = n1;
   A.n2 = n2;
   A.k = k;
