@@ -232,8 +232,10 @@ __device__ __forceinline__ u32 rel32(u64 x, u64 base_cs) {
   return r > 0xffffffffull ? 0xffffffffu : (u32)r;
 }
 
-// hi on the full keys, starting from position `from` (gallop, then bisect)
-__device__ __forceinline__ i64 gallop_hi(const u64* __restrict__ other, i64 from, i64 m, u64 xe, int closed,
+// hi on the full keys, starting from position `from` (gallop, then bisect).  Rare path (a row whose
+// partners run past the staged entries, or a block whose window could not be staged): kept out of line
+// so that the unrolled search loop stays small enough for the instruction cache.
+__device__ __noinline__ i64 gallop_hi(const u64* __restrict__ other, i64 from, i64 m, u64 xe, int closed,
                                          const KeyLayout& L) {
   i64 ga = from, gb = from, gstep = 1;
   for (;;) {
@@ -249,6 +251,12 @@ __device__ __forceinline__ i64 gallop_hi(const u64* __restrict__ other, i64 from
   }
   return closed ? lower_bound_by(ga, gb, [&](i64 q) { return key_cs(other[q], L) <= xe; })
                 : lower_bound_by(ga, gb, [&](i64 q) { return key_cs(other[q], L) < xe; });
+}
+
+template <bool B_SIDE>
+__device__ __noinline__ i64 unstaged_lo(const u64* __restrict__ other, i64 br_lo, i64 br_hi, u64 xs, const KeyLayout& L) {
+  return B_SIDE ? lower_bound_by(br_lo, br_hi, [&](i64 q) { return key_cs(other[q], L) <= xs; })
+                : lower_bound_by(br_lo, br_hi, [&](i64 q) { return key_cs(other[q], L) < xs; });
 }
 
 template <bool B_SIDE, bool FLAGS, int IPT>
@@ -365,8 +373,7 @@ __global__ void __launch_bounds__(SC_THREADS, 5)
         hi = br_lo + h;
         if (h == nst && hi < m) hi = gallop_hi(other, hi, m, xe, closed, L);  // ran off the staged window
       } else {
-        lo = B_SIDE ? lower_bound_by(br_lo, br_hi, [&](i64 q) { return key_cs(other[q], L) <= xs; })
-                    : lower_bound_by(br_lo, br_hi, [&](i64 q) { return key_cs(other[q], L) < xs; });
+        lo = unstaged_lo<B_SIDE>(other, br_lo, br_hi, xs, L);
         hi = gallop_hi(other, lo, m, xe, closed, L);
       }
       cnt[j] = (u32)(hi - lo);
