@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
                       i64* __restrict__ ev1, i64* __restrict__ ev2) {
   __shared__ i32 s_rel[EM_TILE + 2];  // scan[first_item + i] - t0, clamped to 32 bits
   __shared__ EmitItem s_item[EM_TILE + 2];
-  __shared__ u32 s_owner[EM_TILE + EM_TILE / 8];  // padded: 8 consecutive slots per thread without bank conflicts
+  __shared__ __align__(16) u32 s_owner[EM_TILE + EM_TILE / 8];  // padded: 8 consecutive slots per thread without bank conflicts
   __shared__ u32 s_wmax[EM_THREADS / 32];
   const u32 tid = threadIdx.x;
   const i64 W = n_owner + total;
@@ -538,7 +538,10 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
     }
   }
 #define EM_PAD(x) ((x) + ((x) >> 3))
-  for (i32 x = tid; x < EM_TILE; x += EM_THREADS) s_owner[EM_PAD(x)] = 0;
+  {  // clear the owner slots (and their padding) with 16-byte stores
+    uint4* z = reinterpret_cast<uint4*>(s_owner);
+    for (i32 x = tid; x < (EM_TILE + EM_TILE / 8) / 4; x += EM_THREADS) z[x] = make_uint4(0u, 0u, 0u, 0u);
+  }
   __syncthreads();
   for (i32 i = tid; i < nitems; i += EM_THREADS) {
     const i32 r = s_rel[i];
@@ -585,14 +588,12 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
     u32 own[4], oth[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const i32 x = (h + j) * EM_THREADS + (i32)tid;
-      own[j] = 0;
-      oth[j] = 0;
-      if (x < nout) {
-        const EmitItem it = s_item[s_owner[EM_PAD(x)]];
-        own[j] = it.id;
-        oth[j] = other_id[it.src + (u32)x];
-      }
+      // slots past the block's last output read the last valid slot instead (unpredicated loads keep
+      // the shared-memory address arithmetic out of the loop); only the stores are predicated
+      const i32 x = min((h + j) * EM_THREADS + (i32)tid, nout - 1);
+      const EmitItem it = s_item[s_owner[EM_PAD(x)]];
+      own[j] = it.id;
+      oth[j] = other_id[it.src + (u32)x];
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
