@@ -116,6 +116,18 @@ __device__ __forceinline__ void st_relaxed_u64(u64* p, u64 v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Shared-memory reads through an explicit 32-bit shared address.  With array indexing the compiler
+// rebuilds the (cluster-aware) shared window address in front of many accesses -- an S2UR of
+// SR_CgaCtaId plus a ULEA each time, 41 of them in the unrolled search loop -- and the S2UR latency sits
+// on the dependent chain of every search step.  Computing the address once and using ld.shared keeps
+// the loop to one LDS per step.
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ u32 lds_u32(u32 addr) {
+  u32 v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // first index in [lo, hi) with !(a[idx] < x)   (np.searchsorted side="left")
 template <typename F>
 __device__ __forceinline__ i64 lower_bound_by(i64 lo, i64 hi, F less_than_x) {

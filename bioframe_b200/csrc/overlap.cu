@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(SC_THREADS, 5)
 
   u32 cnt[IPT];
   u32 lo32[IPT];
+  const u32 rel_base = smem_addr(s_rel);
   u32 pos = 0;  // lo of the previous row, relative to br_lo (staged path)
 #pragma unroll
   for (int j = 0; j < IPT; ++j) {
@@ -327,18 +328,19 @@ __global__ void __launch_bounds__(SC_THREADS, 5)
       i64 lo, hi;
       if (nst > 0) {
         const u32 xs_rel = rel32(xs, base_cs), xe_rel = rel32(xe, base_cs);
+        auto rel_at = [&](u32 i) { return lds_u32(rel_base + 4u * i); };  // s_rel[i]
         bool searched = false;
         if (j > 0) {  // lo is monotone over consecutive rows: short linear advance
           const u32 lim = pos + 6 < W ? pos + 6 : W;
-          while (pos < lim && (B_SIDE ? (s_rel[pos] <= xs_rel) : (s_rel[pos] < xs_rel))) ++pos;
-          searched = pos < lim || pos == W || !(B_SIDE ? (s_rel[pos] <= xs_rel) : (s_rel[pos] < xs_rel));
+          while (pos < lim && (B_SIDE ? (rel_at(pos) <= xs_rel) : (rel_at(pos) < xs_rel))) ++pos;
+          searched = pos < lim || pos == W || !(B_SIDE ? (rel_at(pos) <= xs_rel) : (rel_at(pos) < xs_rel));
         }
         if (!searched) {  // bit-step lower bound over the W candidates
           u32 q = 0;
           for (u32 step = pow2w; step > 0; step >>= 1) {
             const u32 nx = q + step;
             if (nx <= W) {
-              const u32 v = s_rel[nx - 1];
+              const u32 v = rel_at(nx - 1);
               if (B_SIDE ? (v <= xs_rel) : (v < xs_rel)) q = nx;
             }
           }
@@ -352,20 +354,20 @@ __global__ void __launch_bounds__(SC_THREADS, 5)
         const u32 probe = pos + 64;
         bool near = false;
         if (probe <= nst) {
-          const u32 v = s_rel[probe - 1];
+          const u32 v = rel_at(probe - 1);
           near = !(closed ? (v <= xe_rel) : (v < xe_rel));
         }
         if (near) {
 #pragma unroll
           for (u32 step = 32; step > 0; step >>= 1) {
-            const u32 v = s_rel[h + step - 1];
+            const u32 v = rel_at(h + step - 1);
             if (closed ? (v <= xe_rel) : (v < xe_rel)) h += step;
           }
         } else {
           for (u32 step = pow2n; step > 0; step >>= 1) {
             const u32 nx = h + step;
             if (nx <= nst) {
-              const u32 v = s_rel[nx - 1];
+              const u32 v = rel_at(nx - 1);
               if (closed ? (v <= xe_rel) : (v < xe_rel)) h = nx;
             }
           }
