@@ -380,12 +380,24 @@ __global__ void __launch_bounds__(SC_THREADS, 5)
       }
       cnt[j] = (u32)(hi - lo);
       lo32[j] = (u32)lo;
-      if (FLAGS) {
-        bool partner = cnt[j] > 0;
-        if (!partner && lo > 0) {
-          const u64 pm = other_pmax[lo - 1];
-          partner = closed ? (pm >= xs) : (pm > xs);
-        }
+    }
+  }
+  if (FLAGS) {
+    // rows without a pair of their own still have a partner if an earlier interval of the other set
+    // reaches past their start (running max of end').  Done after the search loop
+    // so that the loads of all IPT rows are in flight together instead of one per dependent iteration.
+    u64 pm[IPT];
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+      const bool ask = base + j < n && cnt[j] == 0 && lo32[j] > 0;
+      pm[j] = ask ? other_pmax[lo32[j] - 1] : 0ull;
+    }
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+      const i64 p = base + j;
+      if (p < n && cnt[j] == 0) {
+        const u64 xs = key_cs(key[j], L);
+        const bool partner = lo32[j] > 0 && (closed ? (pm[j] >= xs) : (pm[j] > xs));
         if (!partner) rowflag[mine_id[p]] = 1;  // per-group counts come later from the compacted list
       }
     }
