@@ -260,7 +260,7 @@ __device__ __noinline__ i64 unstaged_lo(const u64* __restrict__ other, i64 br_lo
 }
 
 template <bool B_SIDE, bool FLAGS, int IPT>
-__global__ void __launch_bounds__(SC_THREADS, 5)
+__global__ void __launch_bounds__(SC_THREADS, 6)
     search_count_kernel(const u64* __restrict__ mine, const u32* __restrict__ mine_id, i64 n,
                         const u64* __restrict__ other, i64 m, const u64* __restrict__ other_pmax,
                         const i64* __restrict__ bracket, KeyLayout L, int closed, u32* __restrict__ lo_out,
