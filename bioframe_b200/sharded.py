@@ -65,3 +65,43 @@ def overlap_sharded(grp1, start1, end1, row_offset, grp2, start2, end2, n_groups
     else:
         counts = [int(n_local.item())]
     return ev1, ev2, int(sum(counts[:rank])), int(sum(counts))
+
+
+def _replicate(targets, broadcast, src, group):
+    if dist.is_initialized() and dist.get_world_size(group) > 1 and broadcast:
+        broadcast_targets(targets, src=src, group=group)
+
+
+def coverage_sharded(grp1, start1, end1, grp2, start2, end2, n_groups, engine=None, group=None, broadcast=True, src=0):
+    """This rank's slice of `coverage`: covered base pairs of its own query rows (ops.py:842-916).  Per-query
+    results: the full answer is the concatenation of the shards in rank order, bit-exact."""
+    if engine is None:
+        from . import engine as engine
+    _replicate([grp2, start2, end2], broadcast, src, group)
+    return engine.coverage(grp1, start1, end1, grp2, start2, end2, n_groups)
+
+
+def count_overlaps_sharded(grp1, start1, end1, grp2, start2, end2, n_groups, engine=None, group=None, broadcast=True,
+                           src=0):
+    """This rank's slice of `count_overlaps` (ops.py:1371-1438); concatenate the shards in rank order."""
+    if engine is None:
+        from . import engine as engine
+    _replicate([grp2, start2, end2], broadcast, src, group)
+    return engine.count_overlaps(grp1, start1, end1, grp2, start2, end2, n_groups)
+
+
+def closest_sharded(grp1, start1, end1, row_offset, grp2, start2, end2, n_groups, engine=None, group=None,
+                    broadcast=True, src=0, **kw):
+    """This rank's slice of `_closest_intidxs` (ops.py:919-1040) with GLOBAL query row numbers.  Every query's
+    rows depend only on the replicated targets.  Order of the concatenation: rank-major, inside a rank per group
+    the matched rows then the unmatched ones; sorting the concatenated rows by (group block, matched-before-
+    unmatched, query row) -- or simply by query row for frames that are assembled per query -- gives the
+    single-GPU order.  Returns (events1, events2, n_matched_rows_of_this_shard)."""
+    if engine is None:
+        from . import engine as engine
+    _replicate([grp2, start2, end2], broadcast, src, group)
+    ev1, ev2, n_matched = engine.closest_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, **kw)
+    ev1 = torch.as_tensor(ev1)
+    if int(row_offset):
+        ev1 = ev1 + int(row_offset)  # every row carries a query (never -1)
+    return ev1, torch.as_tensor(ev2), n_matched

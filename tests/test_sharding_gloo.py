@@ -42,7 +42,13 @@ def _worker(rank, world, port, how, out_dir):
         ev1, ev2, off, total = sharded.overlap_sharded(
             torch.from_numpy(g1[lo:hi]), torch.from_numpy(s1[lo:hi]), torch.from_numpy(e1[lo:hi]), lo,
             t[0], t[1], t[2], 24, how=how, engine=_TensorEngine(oracle_engine))
-        np.savez(os.path.join(out_dir, f"r{rank}.npz"), ev1=ev1.numpy(), ev2=ev2.numpy(), off=off, total=total)
+        eng = _TensorEngine(oracle_engine)
+        q = (torch.from_numpy(g1[lo:hi]), torch.from_numpy(s1[lo:hi]), torch.from_numpy(e1[lo:hi]))
+        cov = sharded.coverage_sharded(*q, t[0], t[1], t[2], 24, engine=eng, broadcast=False)
+        cnt = sharded.count_overlaps_sharded(*q, t[0], t[1], t[2], 24, engine=eng, broadcast=False)
+        c1, c2, _ = sharded.closest_sharded(q[0], q[1], q[2], lo, t[0], t[1], t[2], 24, engine=eng, broadcast=False, k=2)
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), ev1=ev1.numpy(), ev2=ev2.numpy(), off=off, total=total,
+                 cov=np.asarray(cov), cnt=np.asarray(cnt), c1=np.asarray(c1), c2=np.asarray(c2))
     finally:
         dist.destroy_process_group()
 
@@ -52,6 +58,16 @@ class _TensorEngine:
 
     def __init__(self, mod):
         self.mod = mod
+
+    def coverage(self, g1, s1, e1, g2, s2, e2, nb):
+        return self.mod.coverage(g1.numpy(), s1.numpy(), e1.numpy(), g2.numpy(), s2.numpy(), e2.numpy(), nb)
+
+    def count_overlaps(self, g1, s1, e1, g2, s2, e2, nb):
+        return self.mod.count_overlaps(g1.numpy(), s1.numpy(), e1.numpy(), g2.numpy(), s2.numpy(), e2.numpy(), nb)
+
+    def closest_intidxs(self, g1, s1, e1, g2, s2, e2, nb, **kw):
+        a, b, n = self.mod.closest_intidxs(g1.numpy(), s1.numpy(), e1.numpy(), g2.numpy(), s2.numpy(), e2.numpy(), nb, **kw)
+        return torch.from_numpy(a), torch.from_numpy(b), n
 
     def overlap_intidxs(self, g1, s1, e1, g2, s2, e2, nb, how="inner", closed=False, row_offset1=0, row_offset2=0):
         a, b, n = self.mod.overlap_intidxs(g1.numpy(), s1.numpy(), e1.numpy(), g2.numpy(), s2.numpy(), e2.numpy(), nb,
@@ -80,6 +96,16 @@ def test_sharded_overlap_world2(how, tmp_path):
     got = np.lexsort([ev2, ev1])
     want = np.lexsort([o2, o1])
     assert np.array_equal(ev1[got], o1[want]) and np.array_equal(ev2[got], o2[want])
+    # per-query results: concatenation of the shards is the single-process answer
+    assert np.array_equal(np.concatenate([p["cov"] for p in parts]), oo.coverage_coded(g1, s1, e1, g2, s2, e2, 24))
+    i_all, _ = oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, 24, how="inner")
+    assert np.array_equal(np.concatenate([p["cnt"] for p in parts]), np.bincount(i_all, minlength=len(s1)))
+    # closest: same (query, target) rows as the single-process call once both are ordered by query row
+    c1 = np.concatenate([p["c1"] for p in parts])
+    c2 = np.concatenate([p["c2"] for p in parts])
+    w1, w2 = oo.closest_intidxs_coded(g1, s1, e1, g2, s2, e2, 24, k=2)
+    a, b = np.argsort(c1, kind="stable"), np.argsort(w1, kind="stable")
+    assert np.array_equal(c1[a], w1[b]) and np.array_equal(c2[a], w2[b])
 
 
 def test_shard_bounds():
