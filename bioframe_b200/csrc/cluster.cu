@@ -304,16 +304,14 @@ static int cluster_emit_impl(const ClusterPlan* plan, i32* cgrp_out, i64* cstart
 // and coverage = F(end) - F(start): two binary searches per query, no pairs.
 struct CoverageWS {
   ClusterWS cl;
-  u64 *slin, *elin;  // [n2+1] merged intervals on the linear (group, coordinate) axis of the key layout
-  u64* plen;         // [n2+1] exclusive prefix of merged lengths
+  ulonglong4* rec;   // [n2+1] merged intervals as 32-byte records: x = linear start, y = linear end,
+                     // z = exclusive prefix of merged lengths (one sector answers a whole F(x) evaluation)
   u64* spine;        // [tiles + 1]
   u32* lut;          // direct-address table over slin
 };
 static void layout_coverage(Arena& a, i64 n2, i32 nb, CoverageWS* w) {
   layout_cluster(a, n2, nb, &w->cl);
-  w->slin = a.take<u64>(n2 + 1);
-  w->elin = a.take<u64>(n2 + 1);
-  w->plen = a.take<u64>(n2 + 1);
+  w->rec = a.take<ulonglong4>(n2 + 1);
   w->spine = a.take<u64>(scan_tiles((u64)n2) + 2);
   w->lut = a.take<u32>(lut_words(n2));
 }
@@ -334,8 +332,7 @@ __global__ void __launch_bounds__(SC_THREADS) merged_length_tiles_kernel(Cluster
 }
 // linear start / end and exclusive length prefix of every merged interval
 __global__ void __launch_bounds__(SC_THREADS)
-    merged_table_kernel(ClusterTable tab, KeyLayout L, const u64* __restrict__ spine, u64* __restrict__ slin,
-                        u64* __restrict__ elin, u64* __restrict__ plen) {
+    merged_table_kernel(ClusterTable tab, KeyLayout L, const u64* __restrict__ spine, ulonglong4* __restrict__ rec) {
   __shared__ u64 s_tmp[8];
   const u64 n = (u64)*tab.n_clusters;
   const u64 base = (u64)blockIdx.x * SC_TILE + (u64)threadIdx.x * SC_IPT;
@@ -355,10 +352,8 @@ __global__ void __launch_bounds__(SC_THREADS)
     const u64 c = base + j;
     if (c < n) {
       const u64 off = L.goff[tab.cgrp[c]];
-      slin[c] = off + ((u64)tab.cstart[c] - L.cmin);
-      elin[c] = off + ((u64)tab.cend[c] - L.cmin);
+      rec[c] = make_ulonglong4(off + ((u64)tab.cstart[c] - L.cmin), off + ((u64)tab.cend[c] - L.cmin), run, 0ull);
     }
-    if (c <= n) plen[c] = run;  // plen[n] = total
     run += len[j];
   }
 }
@@ -368,8 +363,8 @@ __global__ void __launch_bounds__(SC_THREADS)
 // before the group's offset, so they count in full in both F(end) and F(start) and cancel.
 __global__ void __launch_bounds__(256)
     coverage_kernel(const i32* __restrict__ grp1, const i64* __restrict__ s1, const i64* __restrict__ e1, i64 n1,
-                    const i64* __restrict__ n_clusters, KeyLayout L, Lut lut, const u64* __restrict__ slin,
-                    const u64* __restrict__ elin, const u64* __restrict__ plen, i64* __restrict__ cov) {
+                    const i64* __restrict__ n_clusters, KeyLayout L, Lut lut, const ulonglong4* __restrict__ rec,
+                    i64* __restrict__ cov) {
   const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n1) return;
   const i64 C = *n_clusters;
@@ -386,10 +381,11 @@ __global__ void __launch_bounds__(256)
     const u64 d = (u64)x - L.cmin;
     return g0 + (d < span ? d : span);
   };
+  const u64* slin = reinterpret_cast<const u64*>(rec);  // entry m at word 4 * m (lut.stride == 4)
   auto below = [&](i64 j, u64 x) -> u64 {
     if (j == 0) return 0ull;
-    const u64 E = elin[j - 1];
-    return plen[j - 1] + ((x < E ? x : E) - slin[j - 1]);
+    const ulonglong4 r1 = rec[j - 1];
+    return r1.z + ((x < r1.y ? x : r1.y) - r1.x);
   };
   const u64 xs = lin(s1[r]), xe = lin(e1[r]);
   const i64 js = lut_count_below<false>(slin, lut, xs);  // = #{S < xs}: one table sector + a search inside the bucket
@@ -401,11 +397,11 @@ __global__ void __launch_bounds__(256)
       hi = C;
       break;
     }
-    if (!(slin[hi - 1] < xe)) break;
+    if (!(slin[4 * (hi - 1)] < xe)) break;
     lo = hi;
     step <<= 1;
   }
-  const i64 je = lower_bound_by(lo, hi, [&](i64 m) { return slin[m] < xe; });
+  const i64 je = lower_bound_by(lo, hi, [&](i64 m) { return slin[4 * m] < xe; });
   const u64 fe = below(je, xe), fs = below(js, xs);
   cov[r] = fe > fs ? (i64)(fe - fs) : 0;
 }
@@ -444,12 +440,12 @@ static int coverage_impl(const i32* grp1, const i64* s1, const i64* e1, i64 n1, 
   const unsigned tiles = (unsigned)scan_tiles((u64)n2);
   BF_LAUNCH(PC_COVERAGE, 16 * n2, st, merged_length_tiles_kernel<<<tiles, SC_THREADS, 0, st>>>(tab, w.spine));
   BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.spine, (u64)tiles, nullptr));
-  BF_LAUNCH(PC_COVERAGE, 44 * n2, st, merged_table_kernel<<<tiles, SC_THREADS, 0, st>>>(tab, L, w.spine, w.slin, w.elin, w.plen));
-  const Lut lut = make_lut(w.lut, n2, 0, 1ull << L.B, 0);
-  BF_TRY(launch_lut_build(w.slin, 0, tab.n_clusters, lut, w.lut, st, PC_COVERAGE));
+  BF_LAUNCH(PC_COVERAGE, 44 * n2, st, merged_table_kernel<<<tiles, SC_THREADS, 0, st>>>(tab, L, w.spine, w.rec));
+  const Lut lut = make_lut(w.lut, n2, 0, 1ull << L.B, 0, 4);
+  BF_TRY(launch_lut_build(reinterpret_cast<const u64*>(w.rec), 0, tab.n_clusters, lut, w.lut, st, PC_COVERAGE));
   BF_LAUNCH(PC_COVERAGE, 28 * n1, st,
             coverage_kernel<<<(unsigned)ceil_div(n1, 256), 256, 0, st>>>(nb > 1 ? grp1 : nullptr, s1, e1, n1, tab.n_clusters, L,
-                                                                        lut, w.slin, w.elin, w.plen, cov));
+                                                                        lut, w.rec, cov));
   return BF_OK;
 }
 

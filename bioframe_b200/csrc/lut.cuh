@@ -15,7 +15,8 @@ struct Lut {
   u64 base;        // coordinate of bucket 0
   int shift;       // log2(bucket width)
   u32 nbuckets;
-  int key_shift;   // entries are keys[m] >> key_shift (packed keys: LB; plain coordinates: 0)
+  int key_shift;   // entries are keys[m * stride] >> key_shift (packed keys: LB; plain coordinates: 0)
+  int stride;      // distance between entries in 8-byte words (1: plain array; 4: first word of 32-byte records)
 };
 
 static inline u32 lut_buckets_for(i64 n) {  // power of two, one bucket per 2-4 entries (a 32-byte sector holds
@@ -26,7 +27,7 @@ static inline u32 lut_buckets_for(i64 n) {  // power of two, one bucket per 2-4 
 static inline size_t lut_words(i64 n) { return (size_t)lut_buckets_for(n) + 2; }
 
 // span = number of coordinates covered (probes outside [base, base + span) are clamped to the end buckets)
-static inline Lut make_lut(u32* tab, i64 n, u64 base, u64 span, int key_shift) {
+static inline Lut make_lut(u32* tab, i64 n, u64 base, u64 span, int key_shift, int stride = 1) {
   Lut t;
   t.tab = tab;
   t.base = base;
@@ -36,6 +37,7 @@ static inline Lut make_lut(u32* tab, i64 n, u64 base, u64 span, int key_shift) {
   if (((u64)t.nbuckets << shift) < span) ++shift;
   t.shift = shift;
   t.key_shift = key_shift;
+  t.stride = stride;
   return t;
 }
 
@@ -47,7 +49,7 @@ static __global__ void __launch_bounds__(256) lut_build_kernel(const u64* __rest
   const i64 n = n_dev ? *n_dev : n_host;
   const u64 x = t.base + ((u64)b << t.shift);  // first coordinate of bucket b (b == nbuckets: one past the end)
   const bool past = b > 0 && x <= t.base;      // wrapped around the 64-bit axis
-  tab[b] = past ? (u32)n : (u32)lower_bound_by(0, n, [&](i64 m) { return (keys[m] >> t.key_shift) < x; });
+  tab[b] = past ? (u32)n : (u32)lower_bound_by(0, n, [&](i64 m) { return (keys[m * t.stride] >> t.key_shift) < x; });
 }
 
 // #{entries < x} (strict) or #{entries <= x}
@@ -60,7 +62,7 @@ __device__ __forceinline__ i64 lut_count_below(const u64* __restrict__ keys, con
   if (x < t.base) lo = 0;
   while (lo < hi) {
     const i64 mid = lo + ((hi - lo) >> 1);
-    const u64 v = keys[mid] >> t.key_shift;
+    const u64 v = keys[mid * t.stride] >> t.key_shift;
     if (INCLUSIVE ? (v <= x) : (v < x))
       lo = mid + 1;
     else
