@@ -133,6 +133,25 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def pin_to_gpu_numa_node(index):
+    """Run this rank on the CPU cores next to its GPU, so that the pinned host buffers of the e2e leg
+    (allocated first-touch) sit in that NUMA node's memory: with 8 ranks on one box the host copies
+    otherwise pile up on one memory controller.  Best effort; a no-op when NVML gives no affinity."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -295,6 +314,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    pin_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
@@ -303,6 +323,7 @@ def main():
     (g1, s1, e1), (g2, s2, e2) = workload(args.n1, args.n2, rank)
     host = [torch.from_numpy(a).pin_memory() for a in (g1, s1, e1, g2, s2, e2)]
     n1, n2 = len(s1), len(s2)
+    del g1, s1, e1, g2, s2, e2  # the pinned copies are the host side from here on
     d = [h.to(dev) for h in host]
     if world > 1 and rank != 0:
         for t in d[3:]:
@@ -369,14 +390,30 @@ def main():
     # ---- end to end: pinned host buffers in, pinned host buffers out ----
     e2e = None
     if not args.no_e2e:
-        out1 = torch.empty(n_rows, dtype=torch.int64).pin_memory()
-        out2 = torch.empty(n_rows, dtype=torch.int64).pin_memory()
+        # Host memory: two pinned int64 result columns are 2 x 7 GB per rank (the pinned allocator rounds up to
+        # 8 GB each).  Up to 4 ranks they are kept whole; with more ranks on one box (196 GB of host RAM here)
+        # the result is read back through a ring of two 2-GiB pinned buffers instead -- same bytes over PCIe.
+        ring = world > 4
+        if ring:
+            chunk = 1 << 28
+            bufs = [torch.empty(chunk, dtype=torch.int64).pin_memory() for _ in range(2)]
+        else:
+            out1 = torch.empty(n_rows, dtype=torch.int64).pin_memory()
+            out2 = torch.empty(n_rows, dtype=torch.int64).pin_memory()
 
         def e2e_step():
             dd = [h.to(dev, non_blocking=True) for h in host]
             a, b, _ = engine.overlap_intidxs(dd[0], dd[1], dd[2], dd[3], dd[4], dd[5], N_GROUPS, how=args.how)
-            out1[: a.numel()].copy_(a, non_blocking=True)
-            out2[: b.numel()].copy_(b, non_blocking=True)
+            if ring:
+                k = 0
+                for col in (a, b):
+                    for lo in range(0, col.numel(), chunk):
+                        part = col[lo:lo + chunk]
+                        bufs[k & 1][: part.numel()].copy_(part, non_blocking=True)
+                        k += 1
+            else:
+                out1[: a.numel()].copy_(a, non_blocking=True)
+                out2[: b.numel()].copy_(b, non_blocking=True)
             torch.cuda.synchronize(dev)
 
         e2e_step()
@@ -396,8 +433,12 @@ def main():
             "ms_per_step": e2e_s * 1e3,
             "h2d_bytes_per_step": h2d_bytes,
             "d2h_bytes_per_step": 16 * n_rows,
+            "d2h_mode": "ring of two 2-GiB pinned buffers" if ring else "whole result into pinned host arrays",
         }
-        del out1, out2
+        if ring:
+            del bufs
+        else:
+            del out1, out2
 
     if rank == 0:
         peaks = {}
