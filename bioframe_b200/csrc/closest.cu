@@ -39,6 +39,7 @@ struct ClosestWS {
   RadixScratch radix;
   LayoutScratch layout;
   u64* pmax;        // [n2] running max of linear end' over the start order
+  u64 *bmax1, *bmax2, *bmax3;  // max of linear end' over blocks of 32 / 1024 / 32768 consecutive sorted targets
   i64* seg;         // [nb+1] first sorted target of each group (same for both orders)
   u64 *qkeyA, *qkeyB;  // [n1] (rank << 32 | row) of the queries
   i64* qseg;        // [nb+1] first query of each group in (group, row) order
@@ -56,6 +57,9 @@ static void layout_closest(Arena& a, i64 n1, i64 n2, i32 nb, ClosestWS* w) {
   w->radix = take_radix_scratch(a, (u64)(n1 > n2 ? n1 : n2));
   w->layout = take_layout_scratch(a, nb);
   w->pmax = a.take<u64>(n2 + 1);
+  w->bmax1 = a.take<u64>((n2 >> 5) + 2);
+  w->bmax2 = a.take<u64>((n2 >> 10) + 2);
+  w->bmax3 = a.take<u64>((n2 >> 15) + 2);
   w->seg = a.take<i64>(nb + 2);
   w->qkeyA = a.take<u64>(n1 + 1);
   w->qkeyB = a.take<u64>(n1 + 1);
@@ -82,6 +86,7 @@ struct ClosestArgs {  // everything a query thread needs (kernel parameter)
   const u64 *kS, *kE;  // target keys in start order / end order
   const u32 *idS, *idE;
   const u64* pmax;
+  const u64 *bmax1, *bmax2, *bmax3;
   const i64 *seg, *qseg;
   const u64* qkey;   // (rank << 32 | row) in (group, row) order; null: identity (one group)
   KeyLayout L;
@@ -136,6 +141,28 @@ __global__ void __launch_bounds__(SC_THREADS)
   }
 }
 
+// bmax[b] = max over entries [b << 5, (b << 5) + 32) of the level below (level 0: linear end' of the keys)
+__global__ void __launch_bounds__(256)
+    block_max_kernel(const u64* __restrict__ keys, const u64* __restrict__ below, i64 n_below, KeyLayout L,
+                     u64* __restrict__ out) {
+  const i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((b << 5) >= n_below) return;
+  u64 mx = 0;
+  for (i64 i = b << 5; i < n_below && i < (b << 5) + 32; ++i) {
+    const u64 v = keys ? key_ce_adj(keys[i], L) : below[i];
+    mx = v > mx ? v : mx;
+  }
+  out[b] = mx;
+}
+
+// Walk the targets that start before the query (positions < from, downwards) and still reach past its
+// start xs: fn(m) for every such position.  The running max of end' ends the walk as soon as nothing
+// earlier can reach xs; whole blocks of 32 / 1024 / 32768 targets whose max end' does not reach xs are
+// skipped, so one very long early target does not make every query scan everything in between
+// (cost ~ matches + blocks between them, not the distance to the long target).
+template <typename F>
+__device__ __forceinline__ void walk_stabbing(const ClosestArgs& A, i64 from, u64 xs, F fn);
+
 __global__ void __launch_bounds__(256) query_keys_kernel(const i32* __restrict__ grp, i64 n, u64* __restrict__ qkey) {
   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) qkey[i] = ((u64)(u32)grp[i] << 32) | (u64)i;
@@ -148,6 +175,27 @@ __global__ void query_segments_kernel(const u64* __restrict__ qkey, i64 n, i32 n
     return;
   }
   qseg[c] = lower_bound_by(0, n, [&](i64 m) { return (qkey[m] >> 32) < (u64)c; });
+}
+
+template <typename F>
+__device__ __forceinline__ void walk_stabbing(const ClosestArgs& A, i64 from, u64 xs, F fn) {
+  const KeyLayout& L = A.L;
+  i64 m = from - 1;
+  while (m >= 0 && A.pmax[m] > xs) {
+    if ((m & 31) == 31 && A.bmax1[m >> 5] <= xs) {  // at the top of a block of 32 that holds no match
+      if ((m & 1023) == 1023 && A.bmax2[m >> 10] <= xs) {
+        if ((m & 32767) == 32767 && A.bmax3[m >> 15] <= xs)
+          m -= 32768;
+        else
+          m -= 1024;
+      } else {
+        m -= 32;
+      }
+      continue;
+    }
+    if (key_ce_adj(A.kS[m], L) > xs && !fn(m)) return;
+    --m;
+  }
 }
 
 struct Probe {
@@ -203,8 +251,11 @@ __device__ __forceinline__ i64 count_overlaps_upto(const ClosestArgs& A, const P
         break;
       }
   }
-  for (i64 m = P.loA - 1; m >= P.t0 && c < need && A.pmax[m] > P.xs; --m) {
-    if (key_ce_adj(A.kS[m], L) > P.xs && !(A.self && (i64)A.idS[m] == P.row)) ++c;
+  if (c < need) {
+    walk_stabbing(A, P.loA, P.xs, [&](i64 m) {
+      if (!(A.self && (i64)A.idS[m] == P.row)) ++c;
+      return c < need;  // stop as soon as enough are known
+    });
   }
   return c;
 }
@@ -349,10 +400,11 @@ __global__ void __launch_bounds__(256)
       const i64 j = A.idS[m];
       if (!(A.self && j == row)) slice_insert(dist, tgt, len, cap, 0, j);
     }
-    for (i64 m = loA - 1; m >= t0 && A.pmax[m] > xs; --m) {
+    walk_stabbing(A, loA, xs, [&](i64 m) {
       const i64 j = A.idS[m];
-      if (key_ce_adj(A.kS[m], L) > xs && !(A.self && j == row)) slice_insert(dist, tgt, len, cap, 0, j);
-    }
+      if (!(A.self && j == row)) slice_insert(dist, tgt, len, cap, 0, j);
+      return true;
+    });
   }
   {  // left neighbours: last k_left of the targets ending at or before the start (arrops.py:560-576, 724)
     i64 from = stop - k_left;
@@ -416,6 +468,10 @@ static int closest_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
     const unsigned tiles = (unsigned)scan_tiles((u64)n2);
     BF_TRY(reset_scan_state(w.ss_tmp, tiles, st));
     BF_LAUNCH(PC_RUNMAX, 16 * n2, st, runmax_adj_kernel<<<tiles, SC_THREADS, 0, st>>>(rS.keys, (u64)n2, L, w.ss_tmp, w.pmax));
+    const i64 nb1 = (n2 + 31) >> 5, nb2 = (nb1 + 31) >> 5, nb3 = (nb2 + 31) >> 5;
+    BF_LAUNCH(PC_RUNMAX, 8 * n2, st, block_max_kernel<<<(unsigned)ceil_div(nb1, 256), 256, 0, st>>>(rS.keys, nullptr, n2, L, w.bmax1));
+    BF_LAUNCH(PC_RUNMAX, 0, st, block_max_kernel<<<(unsigned)ceil_div(nb2, 256), 256, 0, st>>>(nullptr, w.bmax1, nb1, L, w.bmax2));
+    BF_LAUNCH(PC_RUNMAX, 0, st, block_max_kernel<<<(unsigned)ceil_div(nb3, 256), 256, 0, st>>>(nullptr, w.bmax2, nb2, L, w.bmax3));
   }
   // queries in (group, row) order
   const u64* qkey = nullptr;
@@ -442,6 +498,9 @@ static int closest_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   A.idS = rS.vals;
   A.idE = rE.vals;
   A.pmax = w.pmax;
+  A.bmax1 = w.bmax1;
+  A.bmax2 = w.bmax2;
+  A.bmax3 = w.bmax3;
   A.seg = w.seg;
   A.qseg = w.qseg;
   A.qkey = qkey;

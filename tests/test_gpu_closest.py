@@ -133,3 +133,23 @@ def test_closest_int64_max_ends():
         got = engine.closest_intidxs(g1, s1, e1, g2, s2, e2, 3, **kw)
         want = oo.closest_intidxs_coded(g1, s1, e1, g2, s2, e2, 3, **kw)
         _check(got, want)
+
+
+def test_closest_one_giant_target_many_short():
+    """a chromosome-long target at the start of the order: the stabbing walk must skip the short
+    targets in between block-wise instead of scanning them for every query"""
+    from bioframe_b200 import engine
+
+    rng = np.random.default_rng(17)
+    n1, n2 = 150_000, 400_000
+    g2 = np.zeros(n2, np.int32)
+    s2 = rng.integers(1000, 50_000_000, n2).astype(np.int64)
+    e2 = s2 + rng.integers(1, 80, n2)
+    s2[0], e2[0] = 0, 60_000_000  # overlaps every query
+    g1 = np.zeros(n1, np.int32)
+    s1 = rng.integers(1000, 50_000_000, n1).astype(np.int64)
+    e1 = s1 + rng.integers(1, 200, n1)
+    for kw in (dict(k=1), dict(k=3)):
+        got = engine.closest_intidxs(g1, s1, e1, g2, s2, e2, 1, **kw)
+        want = oo.closest_intidxs_coded(g1, s1, e1, g2, s2, e2, 1, **kw)
+        _check(got, want)
