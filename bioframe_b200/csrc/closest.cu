@@ -384,8 +384,13 @@ __global__ void __launch_bounds__(256)
     return;
   }
   const i64 out = (i64)rows[t] + obase[rank];
-  i64* dist = ev1 + out;  // the query's slice of ev1 holds distances until the very end
-  i64* tgt = ev2 + out;
+  // working slice: thread-local arrays for the usual small k (the insertion shifts stay in L1 / registers),
+  // otherwise the query's slice of the output itself (ev1 holds the distances until the very end)
+  constexpr int K_LOCAL = 32;
+  i64 loc_d[K_LOCAL], loc_j[K_LOCAL];
+  const bool local = cap <= K_LOCAL;
+  i64* dist = local ? loc_d : ev1 + out;
+  i64* tgt = local ? loc_j : ev2 + out;
   i32 len = 0;
   const uint4 qp = qpos[t];
   const i64 loA = qp.x, hiA = qp.y, stop = qp.z, begin = qp.w;
@@ -418,7 +423,15 @@ __global__ void __launch_bounds__(256)
     for (i64 m = begin; m < to; ++m)
       slice_insert(dist, tgt, len, cap, (i64)(key_cs(A.kS[m], L) - xe) + 1, (i64)A.idS[m]);
   }
-  for (i32 x = 0; x < cap; ++x) dist[x] = row;  // len == cap by construction of the count
+  // len == cap by construction of the count
+  if (local) {
+    for (i32 x = 0; x < cap; ++x) {
+      ev1[out + x] = row;
+      ev2[out + x] = loc_j[x];
+    }
+  } else {
+    for (i32 x = 0; x < cap; ++x) dist[x] = row;
+  }
 }
 
 // ---------------------------------------------------------------- host side

@@ -34,7 +34,6 @@ struct SetWS {
   int shift;     // log2(rows per search tile) of this side (host copy, set by launch_search)
   u64 *spine;    // [tiles]
   i64 *bracket;  // [tiles+1] window of the other set per block of sorted rows
-  ScanState ss;  // = sb.ss
   u64 *pmax;   // [n] running max of ce (only for outer joins on the other side)
   u8 *rowflag; // [n] 1 = row has no partner (row order)
   u64 *ukeyA, *ukeyB;  // [n] (rank << 32 | row) of unpaired rows
@@ -68,7 +67,6 @@ static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS*
     s.loc = s.sb.tmp4b;
     s.tilepre = a.take<u64>(ceil_div(n[k], SEARCH_MIN_ROWS) + 2);
     s.shift = 0;
-    s.ss = s.sb.ss;
     s.spine = a.take<u64>(scan_tiles(n[k]) + 1);
     s.bracket = a.take<i64>(ceil_div(n[k], SEARCH_MIN_ROWS) + 2);
     s.seg = a.take<i64>(nb + 1);

@@ -2,8 +2,8 @@
 // "onesweep" style: one up-front histogram of every digit place, then ONE
 // kernel per digit place that reads each key once and writes it once
 // (12 B in + 12 B out per row with payload).  Per pass and tile:
-//   warp-striped 8-byte loads -> warp-level digit ranking with match.any +
-//   per-warp digit counters in shared memory -> tile digit offsets ->
+//   warp-striped 8-byte loads -> warp-level digit ranking (warp-private shared-memory
+//   counters bumped with atomics, match.any among colliding lanes) -> tile digit offsets ->
 //   decoupled look-back over per-tile digit counts (one 64-bit status word per
 //   (tile, digit): tag | flag | value, so no fence and no per-pass memset) ->
 //   keys/payload staged in shared memory in sorted order -> coalesced runs out.
@@ -70,20 +70,6 @@ static inline RadixScratch take_radix_scratch(Arena& a, u64 n_max) {
   s.status = a.take<u64>(radix_status_words(n_max) + RS_BINS);
   s.tickets = a.take<u32>(RS_MAX_PASSES);
   return s;
-}
-
-// Lanes of the warp whose 8-bit digit equals this lane's. Eight ballots: the
-// hardware match.any instruction serialises over distinct values and was the
-// limiter of the first version of these kernels (profiles/r1_notes.md).
-__device__ __forceinline__ u32 match_digit8(u32 d) {
-  u32 peers = 0xffffffffu;
-#pragma unroll
-  for (int b = 0; b < 8; ++b) {
-    const bool bit = (d >> b) & 1u;
-    const u32 m = __ballot_sync(0xffffffffu, bit);
-    peers &= bit ? m : ~m;
-  }
-  return peers;
 }
 
 // ---- histogram of all digit places, callable from any key-producing kernel ----

@@ -1,10 +1,9 @@
-// Device-wide scans as reduce -> spine scan -> downsweep (no spin-waits):
-//   exclusive sum of u32 counts into u64 offsets (sizes the variable-length
-//   outputs; replaces np.repeat/cumsum in arrops.py:122-127 and np.cumsum in
-//   arrops.py:472), and an inclusive running max of u64 (np.maximum.accumulate,
-//   arrops.py:462).  A tile is 2048 elements; the producer kernel usually
-//   writes the per-tile partials itself, so the inputs are read once more only
-//   by the downsweep.
+// Block-level scan helpers and the spine scan.  Device-wide prefix sums / running maxima are done as
+//   producer kernel: in-tile prefix + per-tile total  ->  spine_scan_kernel (one block)  ->  consumers add
+//   spine[tile] to the in-tile value
+// (sizes the variable-length outputs: np.repeat/cumsum of arrops.py:122-127, np.cumsum of arrops.py:472,
+// np.maximum.accumulate of arrops.py:462).  A tile is 2048 elements.  No kernel spins on another one,
+// except the radix pass (radix_sort.cuh) and two small closest kernels (lookback.cuh).
 #pragma once
 #include "common.cuh"
 
@@ -145,61 +144,6 @@ static __global__ void __launch_bounds__(1024) spine_scan_kernel(u64* __restrict
     if (i < hi) spine[i] = op(carry, up);
     carry = op(carry, __shfl_sync(0xffffffffu, inc, 31));
   }
-}
-
-// ---- per-tile sums of a u32 array (when no producer wrote the spine) ----
-static __global__ void __launch_bounds__(SC_THREADS) tile_sum_u32_kernel(const u32* __restrict__ in, u64 n,
-                                                                  u64* __restrict__ spine) {
-  __shared__ u64 s_tmp[8];
-  const u64 base = (u64)blockIdx.x * SC_TILE;
-  u64 acc = 0;
-#pragma unroll
-  for (int j = 0; j < SC_IPT; ++j) {
-    u64 i = base + (u64)j * SC_THREADS + threadIdx.x;
-    if (i < n) acc += in[i];
-  }
-  acc = block_sum_u64(acc, s_tmp);
-  if (threadIdx.x == 0) spine[blockIdx.x] = acc;
-}
-
-// ---- downsweep: out[i] = spine[tile] + sum(in[tile_start .. i)), out[n] = total ----
-static __global__ void __launch_bounds__(SC_THREADS) excl_sum_u32_kernel(const u32* __restrict__ in, u64 n,
-                                                                  const u64* __restrict__ spine,
-                                                                  u64* __restrict__ out) {
-  __shared__ u64 s_tmp[8];
-  const u64 base = (u64)blockIdx.x * SC_TILE + (u64)threadIdx.x * SC_IPT;
-  u32 v[SC_IPT];
-  u64 mine = 0;
-#pragma unroll
-  for (int j = 0; j < SC_IPT; ++j) {
-    u64 i = base + j;
-    v[j] = i < n ? in[i] : 0u;
-    mine += v[j];
-  }
-  u64 tot;
-  u64 run = spine[blockIdx.x] + block_excl_sum_u64(mine, s_tmp, &tot);
-#pragma unroll
-  for (int j = 0; j < SC_IPT; ++j) {
-    u64 i = base + j;
-    if (i < n) out[i] = run;
-    run += v[j];
-    if (i + 1 == n) out[n] = run;
-  }
-}
-
-static int exclusive_sum_u32(const u32* counts, u64 n, u64* spine, bool spine_ready, u64* out,
-                             cudaStream_t stream) {
-  if (n == 0) {
-    BF_CUDA(cudaMemsetAsync(out, 0, sizeof(u64), stream));
-    return BF_OK;
-  }
-  const u64 tiles = (u64)scan_tiles(n);
-  if (!spine_ready) {
-    BF_LAUNCH(PC_SCAN, 0, stream, tile_sum_u32_kernel<<<(unsigned)tiles, SC_THREADS, 0, stream>>>(counts, n, spine));
-  }
-  BF_LAUNCH(PC_SCAN, 0, stream, spine_scan_kernel<false><<<1, 1024, 0, stream>>>(spine, tiles, nullptr));
-  BF_LAUNCH(PC_SCAN, 0, stream, excl_sum_u32_kernel<<<(unsigned)tiles, SC_THREADS, 0, stream>>>(counts, n, spine, out));
-  return BF_OK;
 }
 
 }  // namespace bf

@@ -20,7 +20,6 @@ struct SortBufs {
   u64 *tmp8;   // [n+1]
   u32 *tmp4a;  // [n]
   u32 *tmp4b;  // [n]
-  ScanState ss;
   u64 *spine;  // [scan tiles + 1] per-tile counts / offsets of rows in long tie runs
   u64 *nT;     // device-side count of rows in long tie runs
 };
@@ -32,7 +31,6 @@ static inline void take_sort_bufs(Arena& a, i64 n, SortBufs* b) {
   b->tmp8 = a.take<u64>(n + 1);
   b->tmp4a = a.take<u32>(n);
   b->tmp4b = a.take<u32>(n);
-  b->ss = take_scan_state(a, (u64)scan_tiles((u64)n));
   b->spine = a.take<u64>(scan_tiles((u64)n) + 2);
   b->nT = a.take<u64>(1);
 }
