@@ -190,6 +190,61 @@ static __global__ void __launch_bounds__(256) tie_scatter_kernel(const u64* __re
 
 // ---------------------------------------------------------------- host side
 
+// ---- clamp mode: (group, start, true end', row) by two stable sorts ----
+static __global__ void __launch_bounds__(256) true_end_keys_kernel(const i64* __restrict__ s, const i64* __restrict__ e,
+                                                                   u64 n, int point_adjust, u64* __restrict__ keys) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    i64 b = e[i];
+    if ((point_adjust & KEY_POINT_ADJUST) && s[i] == b && b != I64_MAX) b += 1;
+    keys[i] = (u64)b ^ 0x8000000000000000ull;  // order-preserving image of the signed value
+  }
+}
+// packed keys of the rows in the order given by `order` (+ histograms of the digit places of the next sort)
+static __global__ void __launch_bounds__(HIST_THREADS)
+    pack_keys_gather_kernel(const i32* __restrict__ grp, const i64* __restrict__ s, const i64* __restrict__ e,
+                            const u32* __restrict__ order, u64 n, KeyLayout L, int point_adjust, RadixPlan rp,
+                            u64* __restrict__ keys, u64* __restrict__ ghist) {
+  extern __shared__ u32 hist_tabs[];
+  hist_clear(hist_tabs, rp);
+  __syncthreads();
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u32 r = order[i];
+    i64 a = s[r], b = e[r];
+    if ((point_adjust & KEY_POINT_ADJUST) && a == b) b += 1;
+    b = min(b, L.endcap);
+    const u64 off = grp ? L.goff[grp[r]] : 0ull;
+    const u64 at = (point_adjust & KEY_BY_END) ? (u64)b : (u64)a;
+    const u64 k = ((off + (at - L.cmin)) << L.LB) | ((u64)b - (u64)a);
+    keys[i] = k;
+    hist_add(hist_tabs, rp, k, true);
+  }
+  __syncthreads();
+  hist_flush(hist_tabs, rp, ghist);
+}
+
+static int sort_rows_two_keys(const i32* grp, const i64* s, const i64* e, i64 n, const KeyLayout& L, int point_adjust,
+                              const SortBufs& ws, const RadixScratch& sc, cudaStream_t st, SortResult* res) {
+  // 1. rows by true end' (64-bit keys, row number as payload)
+  const RadixPlan all64 = make_radix_plan(0, 64);
+  BF_LAUNCH(PC_TIEFIX, 16 * n, st,
+            true_end_keys_kernel<<<stream_grid((u64)n, 1024), 256, 0, st>>>(s, e, (u64)n, point_adjust, ws.keyA));
+  BF_CUDA(cudaMemsetAsync(sc.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
+  BF_TRY(launch_radix_hist(ws.keyA, (u64)n, nullptr, all64, sc.hist, st, PC_TIEFIX));
+  SortResult by_end;
+  BF_TRY(radix_sort_passes<true>(ws.keyA, ws.keyB, ws.idA, ws.idB, true, (u64)n, nullptr, all64, sc, st, &by_end, PC_TIEFIX));
+  // 2. packed keys in that order, stable sort on the (group, start) field, payload = row
+  const RadixPlan rp = make_radix_plan(L.LB, L.total_bits);
+  const size_t smem = hist_smem_bytes(rp);
+  BF_CUDA(cudaMemsetAsync(sc.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
+  BF_CUDA(cudaFuncSetAttribute(pack_keys_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BF_LAUNCH(PC_PACK, 32 * n, st,
+            pack_keys_gather_kernel<<<stream_grid((u64)n, 2048), HIST_THREADS, smem, st>>>(
+                grp, s, e, by_end.vals, (u64)n, L, point_adjust, rp, by_end.keys, sc.hist));
+  BF_TRY(radix_sort_passes<true>(by_end.keys, by_end.keys_alt, by_end.vals, by_end.vals_alt, false, (u64)n, nullptr, rp,
+                                 sc, st, res));
+  return BF_OK;
+}
+
 // Sort rows (grp may be null for a single group) into res->keys / res->vals.
 static int sort_rows(const i32* grp, const i64* s, const i64* e, i64 n, const KeyLayout& L, int point_adjust,
                      const SortBufs& ws, const RadixScratch& sc, cudaStream_t st, SortResult* res) {
@@ -198,6 +253,13 @@ static int sort_rows(const i32* grp, const i64* s, const i64* e, i64 n, const Ke
   res->keys_alt = ws.keyB;
   res->vals_alt = ws.idB;
   if (n == 0) return BF_OK;
+  if (L.endcap != I64_MAX && !(point_adjust & KEY_NO_TIE_FIX)) {
+    // Clamped ends (INT64_MAX-style inputs, keys.cuh measure_layout): the packed length no longer orders
+    // rows that share a start and reach beyond the clamp.  Rare and usually tiny (views, complement
+    // bounds), so do the plain two-key LSD sort instead of start-sort + tie fix: stable sort by the TRUE
+    // end', then stable sort by (group, start) -> (group, start, end', row) exactly.
+    return sort_rows_two_keys(grp, s, e, n, L, point_adjust, ws, sc, st, res);
+  }
   // main sort: stable, on the (group, start) bits only
   const RadixPlan rp = make_radix_plan(L.LB, L.total_bits);
   BF_CUDA(cudaMemsetAsync(sc.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
