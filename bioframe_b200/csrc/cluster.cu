@@ -28,6 +28,7 @@ struct ClusterWS {
   RadixScratch radix;
   LayoutScratch layout;
   u64 *spine_max, *spine_cnt;  // [tiles + 1]
+  u64* cend_true;  // [n+1] clamp mode only: true cluster ends (sign-flipped image, 0 = none)
   i64* header;  // [0] = number of clusters
 };
 static void layout_cluster(Arena& a, i64 n, i32 nb, ClusterWS* w) {
@@ -36,6 +37,7 @@ static void layout_cluster(Arena& a, i64 n, i32 nb, ClusterWS* w) {
   w->layout = take_layout_scratch(a, nb);
   w->spine_max = a.take<u64>(scan_tiles((u64)n) + 2);
   w->spine_cnt = a.take<u64>(scan_tiles((u64)n) + 2);
+  w->cend_true = a.take<u64>(n + 1);
   w->header = a.take<i64>(4);
 }
 
@@ -94,7 +96,8 @@ template <int PHASE>
 __global__ void __launch_bounds__(SC_THREADS)
     cluster_pass_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, KeyLayout L, u64 min_dist,
                         int has_min_dist, const u64* __restrict__ spine_max, u64* __restrict__ spine_cnt,
-                        i64* __restrict__ ids_out, ClusterTable tab) {
+                        i64* __restrict__ ids_out, ClusterTable tab, const i64* __restrict__ e_raw,
+                        u64* __restrict__ cend_true) {
   // [0] row before the tile, [1..rows] tile, [rows+1] row after; one pad slot every 8 entries so that
   // threads reading 8 consecutive rows each do not collide on the shared-memory banks
   __shared__ u64 s_kp[SC_TILE + 2 + (SC_TILE + 2) / 8 + 1];
@@ -175,9 +178,25 @@ __global__ void __launch_bounds__(SC_THREADS)
         closes = advance_rank(rank, ncs, L) != rank || gap_opens_cluster(ncs, run, min_dist, has_min_dist);
       }
       if (closes) tab.cend[id] = (i64)(run - gbase + L.cmin);
+      if (e_raw) {  // clamp mode: the packed end of this row may be cut off; remember the true one
+        const i64 te = e_raw[ids[k]];
+        if (te > L.endcap) atomicMax(&cend_true[id], (u64)te ^ 0x8000000000000000ull);
+      }
     }
   }
 #undef s_k
+}
+
+// clamp mode: cluster ends that were cut off by the clamp get their true value back
+__global__ void __launch_bounds__(256) cluster_fix_ends_kernel(ClusterTable tab, const u64* __restrict__ cend_true) {
+  const i64 C = *tab.n_clusters;
+  for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < C; c += (i64)gridDim.x * blockDim.x) {
+    const u64 t = cend_true[c];
+    if (t) {
+      const i64 te = (i64)(t ^ 0x8000000000000000ull);
+      if (te > tab.cend[c]) tab.cend[c] = te;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -202,10 +221,16 @@ __global__ void __launch_bounds__(256)
 
 // Sort + fused scan; leaves the cluster table in the workspace. No host sync.
 static int cluster_run(const i32* grp, const i64* s, const i64* e, i64 n, i32 nb, i64 min_dist, int has_min_dist,
-                       ClusterWS& w, i64* ids_out, cudaStream_t st, ClusterTable* tab, KeyLayout* L_out) {
+                       ClusterWS& w, i64* ids_out, cudaStream_t st, ClusterTable* tab, KeyLayout* L_out,
+                       int allow_clamp = 1) {
   const RowSet sets[1] = {{grp, s, e, n}};
   KeyLayout L;
-  BF_TRY(measure_layout(sets, 1, nb, 0, 0, w.layout, st, &L, "bf_cluster"));
+  // ends beyond (largest start + 1) may be clamped (INT64_MAX ends, e.g. the last gap of a complement):
+  // the borders do not change (such an end reaches past every start either way) and the true cluster
+  // ends are restored afterwards (cluster_fix_ends_kernel)
+  BF_TRY(measure_layout(sets, 1, nb, 0, allow_clamp, w.layout, st, &L, "bf_cluster"));
+  const bool clamped = L.endcap != I64_MAX;
+  if (clamped) BF_CUDA(cudaMemsetAsync(w.cend_true, 0, (size_t)(n + 1) * sizeof(u64), st));
   if (L.B > 62) {
     set_error("coordinate span too wide for the running-max scan (%d bits)", L.B);
     return BF_ERR_RANGE;
@@ -226,11 +251,14 @@ static int cluster_run(const i32* grp, const i64* s, const i64* e, i64 n, i32 nb
   BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<true><<<1, 1024, 0, st>>>(w.spine_max, (u64)tiles, nullptr));
   BF_LAUNCH(PC_CLUSTER, 8 * n, st,
             cluster_pass_kernel<2><<<tiles, SC_THREADS, 0, st>>>(r.keys, r.vals, (u64)n, L, md, has_min_dist, w.spine_max,
-                                                                 w.spine_cnt, nullptr, *tab));
+                                                                 w.spine_cnt, nullptr, *tab, nullptr, nullptr));
   BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.spine_cnt, (u64)tiles, (u64*)w.header));
   BF_LAUNCH(PC_CLUSTER, (u64)(12 + (ids_out ? 12 : 0)) * (u64)n, st,
             cluster_pass_kernel<3><<<tiles, SC_THREADS, 0, st>>>(r.keys, r.vals, (u64)n, L, md, has_min_dist, w.spine_max,
-                                                                 w.spine_cnt, ids_out, *tab));
+                                                                 w.spine_cnt, ids_out, *tab, clamped ? e : nullptr, w.cend_true));
+  if (clamped) {
+    BF_LAUNCH(PC_CLUSTER, 0, st, cluster_fix_ends_kernel<<<stream_grid((u64)n, 1024), 256, 0, st>>>(*tab, w.cend_true));
+  }
   if (L_out) *L_out = L;
   return BF_OK;
 }
@@ -317,7 +345,8 @@ static void layout_coverage(Arena& a, i64 n2, i32 nb, CoverageWS* w) {
 }
 
 // per-tile sums of the merged lengths (n lives on the device)
-__global__ void __launch_bounds__(SC_THREADS) merged_length_tiles_kernel(ClusterTable tab, u64* __restrict__ spine) {
+__global__ void __launch_bounds__(SC_THREADS) merged_length_tiles_kernel(ClusterTable tab, i64 endcap,
+                                                                          u64* __restrict__ spine) {
   __shared__ u64 s_tmp[8];
   const u64 n = (u64)*tab.n_clusters;
   const u64 base = (u64)blockIdx.x * SC_TILE;
@@ -325,7 +354,7 @@ __global__ void __launch_bounds__(SC_THREADS) merged_length_tiles_kernel(Cluster
 #pragma unroll
   for (int j = 0; j < SC_IPT; ++j) {
     const u64 c = base + (u64)j * SC_THREADS + threadIdx.x;
-    if (c < n) acc += (u64)(tab.cend[c] - tab.cstart[c]);
+    if (c < n) acc += (u64)(min(tab.cend[c], endcap) - tab.cstart[c]);
   }
   acc = block_sum_u64(acc, s_tmp);
   if (threadIdx.x == 0) spine[blockIdx.x] = acc;
@@ -342,7 +371,7 @@ __global__ void __launch_bounds__(SC_THREADS)
 #pragma unroll
   for (int j = 0; j < SC_IPT; ++j) {
     const u64 c = base + j;
-    len[j] = c < n ? (u64)(tab.cend[c] - tab.cstart[c]) : 0ull;
+    len[j] = c < n ? (u64)(min(tab.cend[c], L.endcap) - tab.cstart[c]) : 0ull;
     mine += len[j];
   }
   u64 tot;
@@ -352,7 +381,8 @@ __global__ void __launch_bounds__(SC_THREADS)
     const u64 c = base + j;
     if (c < n) {
       const u64 off = L.goff[tab.cgrp[c]];
-      rec[c] = make_ulonglong4(off + ((u64)tab.cstart[c] - L.cmin), off + ((u64)tab.cend[c] - L.cmin), run, 0ull);
+      rec[c] = make_ulonglong4(off + ((u64)tab.cstart[c] - L.cmin), off + ((u64)min(tab.cend[c], L.endcap) - L.cmin), run,
+                               0ull);
     }
     run += len[j];
   }
@@ -436,9 +466,11 @@ static int coverage_impl(const i32* grp1, const i64* s1, const i64* e1, i64 n1, 
   layout_coverage(arena, n2, nb, &w);
   ClusterTable tab;
   KeyLayout L;
-  BF_TRY(cluster_run(grp2, s2, e2, n2, nb, 0, 1, w.cl, nullptr, st, &tab, &L));
+  // no clamping here: coverage does arithmetic on the ends themselves, so targets whose ends do not fit
+  // the key (INT64_MAX) are refused (BF_ERR_RANGE) rather than answered approximately
+  BF_TRY(cluster_run(grp2, s2, e2, n2, nb, 0, 1, w.cl, nullptr, st, &tab, &L, 0));
   const unsigned tiles = (unsigned)scan_tiles((u64)n2);
-  BF_LAUNCH(PC_COVERAGE, 16 * n2, st, merged_length_tiles_kernel<<<tiles, SC_THREADS, 0, st>>>(tab, w.spine));
+  BF_LAUNCH(PC_COVERAGE, 16 * n2, st, merged_length_tiles_kernel<<<tiles, SC_THREADS, 0, st>>>(tab, L.endcap, w.spine));
   BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.spine, (u64)tiles, nullptr));
   BF_LAUNCH(PC_COVERAGE, 44 * n2, st, merged_table_kernel<<<tiles, SC_THREADS, 0, st>>>(tab, L, w.spine, w.rec));
   const Lut lut = make_lut(w.lut, n2, 0, 1ull << L.B, 0, 4);

@@ -152,3 +152,53 @@ def test_count_overlaps_int64_max():
     got = engine.count_overlaps(g1, s1, e1, g2, s2, e2, 3).cpu().numpy()
     i, _ = oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, 3, how="inner")
     assert np.array_equal(got, np.bincount(i, minlength=3000))
+
+
+@pytest.mark.parametrize("min_dist", [0, None, 30])
+def test_cluster_merge_int64_max_ends(min_dist):
+    """the last gap of a complement ends at INT64_MAX: cluster / merge must take such ends.  With
+    min_dist > 0 the reference computes `running_max + min_dist` in int64, which wraps for such an end and
+    opens a spurious cluster after it; here the end simply reaches past everything, i.e. the
+    answer the reference gives when the huge ends are replaced by a large value that does not overflow."""
+    from bioframe_b200 import engine
+
+    big = np.iinfo(np.int64).max
+    rng = np.random.default_rng(12)
+    g, s, e = _rand(rng, 6000, 4, 10**6, 300)
+    huge = np.zeros(len(e), dtype=bool)
+    huge[::37] = True
+    e[huge] = big
+    e[5] = big - 9
+    huge[5] = True
+    res = engine.cluster(g, s, e, 4, min_dist=min_dist, want_row_spans=True)
+    safe = np.where(huge, 2**61, e)
+    ids, cs, ce, cn = oo.cluster_coded(g, s, safe, 4, min_dist)
+    if not min_dist:  # no overflow in the reference either: identical including the ends
+        ids0, cs0, ce0, cn0 = oo.cluster_coded(g, s, e, 4, min_dist)
+        assert np.array_equal(ids, ids0) and np.array_equal(cn, cn0)
+    true_end = np.full(len(cs), np.iinfo(np.int64).min)
+    np.maximum.at(true_end, ids, e)
+    assert np.array_equal(res["ids"].cpu().numpy(), ids)
+    assert np.array_equal(res["cstart"].cpu().numpy(), cs)
+    assert np.array_equal(res["cend"].cpu().numpy(), true_end)
+    assert np.array_equal(res["ccount"].cpu().numpy(), cn)
+    assert np.array_equal(res["row_end"].cpu().numpy(), true_end[ids])
+
+
+def test_complement_with_int64_max_interval():
+    from bioframe_b200 import engine
+
+    big = np.iinfo(np.int64).max
+    s = np.array([10, 50, 200], dtype=np.int64)
+    e = np.array([20, big, 300], dtype=np.int64)
+    _, gs, ge = engine.complement(None, s, e, np.array([0]), np.array([big]))
+    cs, ce = ao.complement_intervals(s, e, bounds=(0, big))
+    assert np.array_equal(gs.cpu().numpy(), cs) and np.array_equal(ge.cpu().numpy(), ce)
+
+
+def test_coverage_refuses_unpackable_targets():
+    from bioframe_b200 import engine
+
+    big = np.iinfo(np.int64).max
+    with pytest.raises(OverflowError):
+        engine.coverage(None, np.array([5]), np.array([9]), None, np.array([1, 4]), np.array([big, 6]), 1)
