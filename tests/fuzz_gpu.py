@@ -45,7 +45,8 @@ def run(budget=120.0, seed=0, max_rounds=None, sizes1=(0, 1, 7, 300, 2500, 9000,
         nb = int(rng.choice([1, 1, 2, 5, 24, 100, 3000]))
         n1 = int(rng.choice(sizes1))
         n2 = int(rng.choice(sizes2))
-        span = int(rng.choice([5, 60, 1000, 50000, 10**7, 10**12]))
+        # groups are laid end to end on one axis: span x groups (+ length bits) must fit the 64-bit key
+        span = int(rng.choice([5, 60, 1000, 50000, 10**7, 10**12] if nb <= 24 else [5, 60, 1000, 50000, 10**7]))
         maxlen = int(rng.choice([2, 10, 100, 5000]))
         p_point = float(rng.choice([0.0, 0.1, 0.6]))
         neg = bool(rng.random() < 0.3)
