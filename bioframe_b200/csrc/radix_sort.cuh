@@ -20,14 +20,13 @@ namespace bf {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_LANES = 1;  // independent counter tables per warp (rounds ranked RS_LANES at a time; 2 measured slower on B200)
-constexpr int RS_TABLES = RS_WARPS * RS_LANES;
+constexpr int RS_BLOCKS_PER_SM = 3;
 constexpr int RS_IPT = 16;
 constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 keys per tile
 constexpr int RS_BINS = 256;
 constexpr int RS_MAX_PASSES = 8;
 constexpr int RS_LOOK = 4;  // look-back predecessors fetched per round trip
-constexpr u64 RS_PERSISTENT_BLOCKS = 148 * 3;  // one wave of resident blocks, each loops over tiles
+constexpr u64 RS_PERSISTENT_BLOCKS = 148 * RS_BLOCKS_PER_SM;  // one wave of resident blocks, each loops over tiles
 
 struct RadixPlan {
   int passes;
@@ -151,12 +150,12 @@ constexpr u64 RS_FLAG_AGG = 1ull << 56;
 constexpr u64 RS_FLAG_INC = 2ull << 56;
 
 constexpr size_t rs_smem_bytes(bool has_val) {
-  return (size_t)RS_TILE * 8 + (has_val ? (size_t)RS_TILE * 4 : 0) + (size_t)RS_TABLES * RS_BINS * 4 +
+  return (size_t)RS_TILE * 8 + (has_val ? (size_t)RS_TILE * 4 : 0) + (size_t)RS_WARPS * RS_BINS * 4 +
          (size_t)RS_BINS * 4 + (size_t)RS_BINS * 8;
 }
 
 template <bool HAS_VAL>
-__global__ void __launch_bounds__(RS_THREADS, 3)
+__global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM)
     onesweep_pass_kernel(const u64* __restrict__ kin, u64* __restrict__ kout, const u32* __restrict__ vin,
                          u32* __restrict__ vout, u64 n_host, const u64* __restrict__ n_dev, int shift,
                          u32 dmask, u64 tag, const u64* __restrict__ digit_base, u64* __restrict__ status,
@@ -164,26 +163,28 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
   extern __shared__ __align__(16) unsigned char rs_smem[];
   u64* s_keys = (u64*)rs_smem;
   u32* s_vals = (u32*)(s_keys + RS_TILE);
-  u32* s_wcnt = s_vals + (HAS_VAL ? RS_TILE : 0);  // [RS_TABLES][256]: table (warp w, half h) = w * RS_LANES + h
-  u32* s_tbase = s_wcnt + RS_TABLES * RS_BINS;     // [256] exclusive digit offsets inside the tile
+  u32* s_wcnt = s_vals + (HAS_VAL ? RS_TILE : 0);  // [RS_WARPS][256]
+  u32* s_tbase = s_wcnt + RS_WARPS * RS_BINS;      // [256] exclusive digit offsets inside the tile
   u64* s_gofs = (u64*)(s_tbase + RS_BINS);         // [256] global offset minus s_tbase
   __shared__ u32 s_tile;
   __shared__ u32 s_wtot[RS_BINS / 32];
 
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool dthread = tid < RS_BINS;  // threads 0..255 each own one digit in the per-tile bookkeeping
+  const u32 d_own = tid & (RS_BINS - 1);
   const u64 n = n_dev ? *n_dev : n_host;
   // persistent block: take tiles by ticket until the input is exhausted
   for (;;) {
   __syncthreads();  // previous tile fully written out before shared memory is reused
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-  for (int i = tid; i < RS_TABLES * RS_BINS; i += RS_THREADS) s_wcnt[i] = 0;
+  for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) s_wcnt[i] = 0;
   __syncthreads();
   const u64 tile = s_tile;
   const u64 tile_start = tile * RS_TILE;
   if (tile_start >= n) return;
   const u32 valid = (u32)((n - tile_start < (u64)RS_TILE) ? (n - tile_start) : (u64)RS_TILE);
 
-  // ---- load (warp-striped: lane l of warp w owns tile items w*512 + j*32 + l) ----
+  // ---- load (warp-striped: lane l of warp w owns tile items w*(32*IPT) + j*32 + l) ----
   u64 key[RS_IPT];
   const u32 wbase = warp * (RS_IPT * 32) + lane;
 #pragma unroll
@@ -198,69 +199,59 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
   // the same digit.  Alone (the common case for 8-bit digits) its rank is the old count; otherwise the
   // few lanes that collided order themselves by lane with one match.any over just those lanes, which
   // keeps the pass stable.  Replaces 8 ballots + mask logic per key.
-  // The warp's 16 rounds are split in two halves with their own counter tables (rounds 0-7 and 8-15
-  // are consecutive stretches of the tile, so "half" is just a finer warp); one round of each half is
-  // ranked per step, which gives two independent shared-memory dependency chains per warp.
   u16 lpos[RS_IPT];
-  u32* my_cnt = s_wcnt + warp * (RS_LANES * RS_BINS);
+  u32* my_cnt = s_wcnt + warp * RS_BINS;
   const u32 lt = lanemask_lt();
-  constexpr int HALF = RS_IPT / RS_LANES;
 #pragma unroll
-  for (int j = 0; j < HALF; ++j) {
-    u32 d[RS_LANES], before[RS_LANES], same[RS_LANES];
-#pragma unroll
-    for (int h = 0; h < RS_LANES; ++h) {
-      d[h] = (u32)(key[j + h * HALF] >> shift) & dmask;
-      before[h] = my_cnt[h * RS_BINS + d[h]];
-    }
+  for (int j = 0; j < RS_IPT; ++j) {
+    const u32 d = (u32)(key[j] >> shift) & dmask;
+    const u32 before = my_cnt[d];
     __syncwarp();
-#pragma unroll
-    for (int h = 0; h < RS_LANES; ++h) atomicAdd(&my_cnt[h * RS_BINS + d[h]], 1u);
+    atomicAdd(&my_cnt[d], 1u);
     __syncwarp();
-#pragma unroll
-    for (int h = 0; h < RS_LANES; ++h) same[h] = my_cnt[h * RS_BINS + d[h]] - before[h];  // lanes with digit d (>= 1)
-#pragma unroll
-    for (int h = 0; h < RS_LANES; ++h) {
-      u32 r = before[h];
-      const u32 crowd = __ballot_sync(0xffffffffu, same[h] > 1);
-      if (same[h] > 1) r += __popc(__match_any_sync(crowd, d[h]) & lt);
-      lpos[j + h * HALF] = (u16)r;
-    }
+    const u32 same = my_cnt[d] - before;  // lanes of this round with digit d (>= 1)
+    u32 r = before;
+    const u32 crowd = __ballot_sync(0xffffffffu, same > 1);
+    if (same > 1) r += __popc(__match_any_sync(crowd, d) & lt);
+    lpos[j] = (u16)r;
   }
   __syncthreads();
 
   // ---- thread d: exclusive offsets of digit d across warps, tile digit count; publish the tile's
   //      digit counts right away so that later tiles can start summing them ----
-  const u32 d_own = tid & (RS_BINS - 1);  // RS_THREADS == RS_BINS: every thread owns one digit
-  u64 cnt_valid;
-  u32 tbase_own;
+  u64 cnt_valid = 0;
+  u32 tbase_own = 0;
   {
     u32 tile_cnt = 0;
+    if (dthread) {
 #pragma unroll
-    for (int w = 0; w < RS_TABLES; ++w) {
-      u32 c = s_wcnt[w * RS_BINS + d_own];
-      s_wcnt[w * RS_BINS + d_own] = tile_cnt;
-      tile_cnt += c;
+      for (int w = 0; w < RS_WARPS; ++w) {
+        u32 c = s_wcnt[w * RS_BINS + d_own];
+        s_wcnt[w * RS_BINS + d_own] = tile_cnt;
+        tile_cnt += c;
+      }
     }
-    // exclusive scan of tile_cnt over the 256 digits
+    // exclusive scan of tile_cnt over the 256 digits (warps 0..7)
     u32 inc = tile_cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       u32 t = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= (u32)o) inc += t;
     }
-    if (lane == 31) s_wtot[warp] = inc;
+    if (dthread && lane == 31) s_wtot[warp] = inc;
     __syncthreads();
-    u32 pre = 0;
+    if (dthread) {
+      u32 pre = 0;
 #pragma unroll
-    for (int w = 0; w < RS_BINS / 32; ++w)
-      if ((u32)w < warp) pre += s_wtot[w];
-    tbase_own = pre + inc - tile_cnt;
-    s_tbase[d_own] = tbase_own;
-    // pads all carry digit dmask and sit at the very end of the tile
-    cnt_valid = tile_cnt;
-    if (d_own == dmask) cnt_valid -= (u64)(RS_TILE - valid);
-    st_relaxed_u64(status + tile * RS_BINS + d_own, tag | (tile == 0 ? RS_FLAG_INC : RS_FLAG_AGG) | cnt_valid);
+      for (int w = 0; w < RS_BINS / 32; ++w)
+        if ((u32)w < warp) pre += s_wtot[w];
+      tbase_own = pre + inc - tile_cnt;
+      s_tbase[d_own] = tbase_own;
+      // pads all carry digit dmask and sit at the very end of the tile
+      cnt_valid = tile_cnt;
+      if (d_own == dmask) cnt_valid -= (u64)(RS_TILE - valid);
+      st_relaxed_u64(status + tile * RS_BINS + d_own, tag | (tile == 0 ? RS_FLAG_INC : RS_FLAG_AGG) | cnt_valid);
+    }
   }
   __syncthreads();
 
@@ -269,7 +260,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
 #pragma unroll
   for (int j = 0; j < RS_IPT; ++j) {
     u32 d = (u32)(key[j] >> shift) & dmask;
-    u32 p = s_tbase[d] + my_cnt[(j / (RS_IPT / RS_LANES)) * RS_BINS + d] + lpos[j];
+    u32 p = s_tbase[d] + my_cnt[d] + lpos[j];
     lpos[j] = (u16)p;
     s_keys[p] = key[j];
   }
@@ -285,7 +276,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
 
   // ---- decoupled look-back: digits before this tile ----
   // RS_LOOK predecessors are fetched per round trip (independent loads).
-  {
+  if (dthread) {
     u64 excl = 0;
     if (tile > 0) {
       i64 pt = (i64)tile - 1;  // nearest predecessor not yet accounted for
