@@ -23,12 +23,23 @@
 
 namespace bf {
 
+// Cluster ids in input row order.  Two ways, chosen on the host once the cluster count is known:
+//   few clusters (C < n / 16, e.g. deep coverage where everything merges): every row looks its cluster up by
+//   its start -- the last cluster starting at or before it (cluster starts are strictly increasing when
+//   min_dist is a number) -- with coalesced reads and writes and a small, cache-resident table;
+//   otherwise: scatter of the per-sorted-row ids through the sort permutation (one random 8-byte write per row,
+//   the slowest access pattern of the whole library: 4.3 ms per 1e8 rows).
+constexpr i64 CLUSTER_GATHER_RATIO = 16;
+
 struct ClusterWS {
   SortBufs sb;
   RadixScratch radix;
   LayoutScratch layout;
   u64 *spine_max, *spine_cnt;  // [tiles + 1]
   u64* cend_true;  // [n+1] clamp mode only: true cluster ends (sign-flipped image, 0 = none)
+  u32* cid_sorted; // [n] cluster id of every sorted row (input of the two id kernels below)
+  u64* cs_lin;     // [n/16 + 2] linear starts of the clusters (gather path of the ids, few clusters only)
+  u32* id_lut;     // direct-address table over cs_lin
   i64* header;  // [0] = number of clusters
 };
 static void layout_cluster(Arena& a, i64 n, i32 nb, ClusterWS* w) {
@@ -38,6 +49,9 @@ static void layout_cluster(Arena& a, i64 n, i32 nb, ClusterWS* w) {
   w->spine_max = a.take<u64>(scan_tiles((u64)n) + 2);
   w->spine_cnt = a.take<u64>(scan_tiles((u64)n) + 2);
   w->cend_true = a.take<u64>(n + 1);
+  w->cid_sorted = a.take<u32>(n + 1);
+  w->cs_lin = a.take<u64>(n / CLUSTER_GATHER_RATIO + 2);
+  w->id_lut = a.take<u32>(lut_words(n / CLUSTER_GATHER_RATIO + 1));
   w->header = a.take<i64>(4);
 }
 
@@ -96,7 +110,7 @@ template <int PHASE>
 __global__ void __launch_bounds__(SC_THREADS)
     cluster_pass_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, KeyLayout L, u64 min_dist,
                         int has_min_dist, const u64* __restrict__ spine_max, u64* __restrict__ spine_cnt,
-                        i64* __restrict__ ids_out, ClusterTable tab, const i64* __restrict__ e_raw,
+                        u32* __restrict__ cid_sorted, ClusterTable tab, const i64* __restrict__ e_raw,
                         u64* __restrict__ cend_true) {
   // [0] row before the tile, [1..rows] tile, [rows+1] row after; one pad slot every 8 entries so that
   // threads reading 8 consecutive rows each do not collide on the shared-memory banks
@@ -166,7 +180,7 @@ __global__ void __launch_bounds__(SC_THREADS)
       const u32 rank = rk[j + 1];
       const u64 gbase = L.goff[rank];
       const u64 run = rm[j] > before ? rm[j] : before;  // running max including this row
-      if (ids_out) ids_out[ids[k]] = (i64)id;
+      if (cid_sorted) cid_sorted[k] = (u32)id;
       if (bmask & (1u << j)) {
         tab.cstart[id] = (i64)(key_cs(key, L) - gbase + L.cmin);
         tab.cfirst[id] = (u32)k;
@@ -185,6 +199,26 @@ __global__ void __launch_bounds__(SC_THREADS)
     }
   }
 #undef s_k
+}
+
+__global__ void __launch_bounds__(256)
+    cluster_ids_scatter_kernel(const u32* __restrict__ cid_sorted, const u32* __restrict__ ids, i64 n,
+                               i64* __restrict__ ids_out) {
+  for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (i64)gridDim.x * blockDim.x)
+    ids_out[ids[k]] = (i64)cid_sorted[k];
+}
+__global__ void __launch_bounds__(256)
+    cluster_starts_lin_kernel(ClusterTable tab, i64 C, KeyLayout L, u64* __restrict__ cs_lin) {
+  const i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) cs_lin[c] = L.goff[tab.cgrp[c]] + ((u64)tab.cstart[c] - L.cmin);
+}
+__global__ void __launch_bounds__(256)
+    cluster_ids_gather_kernel(const i32* __restrict__ grp, const i64* __restrict__ s, i64 n, KeyLayout L, Lut lut,
+                              const u64* __restrict__ cs_lin, i64* __restrict__ ids_out) {
+  const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const u64 x = (grp ? L.goff[grp[r]] : 0ull) + ((u64)s[r] - L.cmin);
+  ids_out[r] = lut_count_below<true>(cs_lin, lut, x) - 1;  // last cluster starting at or before the row
 }
 
 // clamp mode: cluster ends that were cut off by the clamp get their true value back
@@ -221,8 +255,8 @@ __global__ void __launch_bounds__(256)
 
 // Sort + fused scan; leaves the cluster table in the workspace. No host sync.
 static int cluster_run(const i32* grp, const i64* s, const i64* e, i64 n, i32 nb, i64 min_dist, int has_min_dist,
-                       ClusterWS& w, i64* ids_out, cudaStream_t st, ClusterTable* tab, KeyLayout* L_out,
-                       int allow_clamp = 1) {
+                       ClusterWS& w, bool want_ids, cudaStream_t st, ClusterTable* tab, KeyLayout* L_out,
+                       int allow_clamp = 1, SortResult* sorted_out = nullptr) {
   const RowSet sets[1] = {{grp, s, e, n}};
   KeyLayout L;
   // ends beyond (largest start + 1) may be clamped (INT64_MAX ends, e.g. the last gap of a complement):
@@ -253,13 +287,15 @@ static int cluster_run(const i32* grp, const i64* s, const i64* e, i64 n, i32 nb
             cluster_pass_kernel<2><<<tiles, SC_THREADS, 0, st>>>(r.keys, r.vals, (u64)n, L, md, has_min_dist, w.spine_max,
                                                                  w.spine_cnt, nullptr, *tab, nullptr, nullptr));
   BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.spine_cnt, (u64)tiles, (u64*)w.header));
-  BF_LAUNCH(PC_CLUSTER, (u64)(12 + (ids_out ? 12 : 0)) * (u64)n, st,
+  BF_LAUNCH(PC_CLUSTER, (u64)(12 + (want_ids ? 4 : 0)) * (u64)n, st,
             cluster_pass_kernel<3><<<tiles, SC_THREADS, 0, st>>>(r.keys, r.vals, (u64)n, L, md, has_min_dist, w.spine_max,
-                                                                 w.spine_cnt, ids_out, *tab, clamped ? e : nullptr, w.cend_true));
+                                                                 w.spine_cnt, want_ids ? w.cid_sorted : nullptr, *tab,
+                                                                 clamped ? e : nullptr, w.cend_true));
   if (clamped) {
     BF_LAUNCH(PC_CLUSTER, 0, st, cluster_fix_ends_kernel<<<stream_grid((u64)n, 1024), 256, 0, st>>>(*tab, w.cend_true));
   }
   if (L_out) *L_out = L;
+  if (sorted_out) *sorted_out = r;
   return BF_OK;
 }
 
@@ -293,11 +329,26 @@ static int cluster_count_impl(const i32* grp, const i64* s, const i64* e, i64 n,
   plan->ready = 0;
   plan->n_clusters = 0;
   if (n > 0) {
-    BF_TRY(cluster_run(grp, s, e, n, nb, min_dist, has_min_dist, w, ids_out, st, &plan->tab, nullptr));
+    KeyLayout L;
+    SortResult sorted;
+    BF_TRY(cluster_run(grp, s, e, n, nb, min_dist, has_min_dist, w, ids_out != nullptr, st, &plan->tab, &L, 1, &sorted));
     i64 c = 0;
     BF_CUDA(cudaMemcpyAsync(&c, w.header, sizeof(i64), cudaMemcpyDeviceToHost, st));
     BF_CUDA(cudaStreamSynchronize(st));
     plan->n_clusters = c;
+    if (ids_out) {
+      if (has_min_dist && c * CLUSTER_GATHER_RATIO < n) {
+        const Lut lut = make_lut(w.id_lut, c, 0, 1ull << L.B, 0);
+        BF_LAUNCH(PC_CLUSTER, 0, st, cluster_starts_lin_kernel<<<(unsigned)ceil_div(c, 256), 256, 0, st>>>(plan->tab, c, L, w.cs_lin));
+        BF_TRY(launch_lut_build(w.cs_lin, c, nullptr, lut, w.id_lut, st, PC_CLUSTER));
+        BF_LAUNCH(PC_CLUSTER, 20 * n, st,
+                  cluster_ids_gather_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(nb > 1 ? grp : nullptr, s, n, L, lut,
+                                                                                       w.cs_lin, ids_out));
+      } else {
+        BF_LAUNCH(PC_CLUSTER, 16 * n, st,
+                  cluster_ids_scatter_kernel<<<stream_grid((u64)n, 1024), 256, 0, st>>>(w.cid_sorted, sorted.vals, n, ids_out));
+      }
+    }
   }
   plan->magic = CLUSTER_MAGIC;
   plan->ready = 1;
@@ -468,7 +519,7 @@ static int coverage_impl(const i32* grp1, const i64* s1, const i64* e1, i64 n1, 
   KeyLayout L;
   // no clamping here: coverage does arithmetic on the ends themselves, so targets whose ends do not fit
   // the key (INT64_MAX) are refused (BF_ERR_RANGE) rather than answered approximately
-  BF_TRY(cluster_run(grp2, s2, e2, n2, nb, 0, 1, w.cl, nullptr, st, &tab, &L, 0));
+  BF_TRY(cluster_run(grp2, s2, e2, n2, nb, 0, 1, w.cl, false, st, &tab, &L, 0));
   const unsigned tiles = (unsigned)scan_tiles((u64)n2);
   BF_LAUNCH(PC_COVERAGE, 16 * n2, st, merged_length_tiles_kernel<<<tiles, SC_THREADS, 0, st>>>(tab, L.endcap, w.spine));
   BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.spine, (u64)tiles, nullptr));
@@ -623,7 +674,7 @@ static int complement_count_impl(const i32* region, const i64* s, const i64* e, 
   plan->b0 = b0;
   plan->b1 = b1;
   ClusterTable tab = {};
-  if (n > 0) BF_TRY(cluster_run(region, s, e, n, nr, 0, 1, w.cl, nullptr, st, &tab, nullptr));
+  if (n > 0) BF_TRY(cluster_run(region, s, e, n, nr, 0, 1, w.cl, false, st, &tab, nullptr));
   tab.n_clusters = w.cl.header;
   if (n == 0) BF_CUDA(cudaMemsetAsync(w.cl.header, 0, sizeof(i64), st));
   plan->tab = tab;
