@@ -473,7 +473,7 @@ static int closest_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
     return BF_ERR_RANGE;
   }
   SortResult rS, rE;
-  BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, KEY_NO_TIE_FIX, w.by_start, w.radix, st, &rS));
+  BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, KEY_NO_TIE_FIX | presorted_mode(L, 1), w.by_start, w.radix, st, &rS));
   BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, KEY_NO_TIE_FIX | KEY_BY_END, w.by_end, w.radix, st, &rE));
   BF_LAUNCH(PC_SEGMENT, 0, st,
             segment_table_kernel<<<(unsigned)ceil_div(nb + 1, 128), 128, 0, st>>>(rS.keys, n2, L, nb, w.seg));

@@ -270,7 +270,7 @@ static int cluster_run(const i32* grp, const i64* s, const i64* e, i64 n, i32 nb
     return BF_ERR_RANGE;
   }
   SortResult r;
-  BF_TRY(sort_rows(nb > 1 ? grp : nullptr, s, e, n, L, 0, w.sb, w.radix, st, &r));
+  BF_TRY(sort_rows(nb > 1 ? grp : nullptr, s, e, n, L, presorted_mode(L, 0), w.sb, w.radix, st, &r));
   // table scratch: buffers that are free once the sort is done
   tab->cstart = (i64*)r.keys_alt;
   tab->cend = (i64*)w.sb.tmp8;

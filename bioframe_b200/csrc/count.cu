@@ -85,7 +85,7 @@ static int count_overlaps_impl(const i32* grp1, const i64* s1, const i64* e1, i6
   KeyLayout L;
   BF_TRY(measure_layout(sets, 2, nb, 1, 1, w.layout, st, &L, "bf_count_overlaps"));
   SortResult rS, rE;
-  BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, KEY_POINT_ADJUST | KEY_NO_TIE_FIX, w.by_start, w.radix, st, &rS));
+  BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, KEY_POINT_ADJUST | KEY_NO_TIE_FIX | presorted_mode(L, 1), w.by_start, w.radix, st, &rS));
   BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, KEY_POINT_ADJUST | KEY_NO_TIE_FIX | KEY_BY_END, w.by_end,
                    w.radix, st, &rE));
   const Lut lutS = make_lut(w.lutS, n2, 0, 1ull << L.B, L.LB), lutE = make_lut(w.lutE, n2, 0, 1ull << L.B, L.LB);

@@ -37,6 +37,7 @@ struct KeyLayout {
   u64 cmin;       // coordinate origin (two's complement image of the int64 minimum)
   u64 lmask;      // (1 << LB) - 1
   i64 endcap;     // ends are clamped to this value before packing (I64_MAX: no clamp), see KEY_CLAMP_END
+  u32 presorted;  // bit k: set k of the call already is in (group rank, start) order (no radix passes needed)
   const u64* goff;  // device [nb+1]: linear offset of every group, goff[nb] = total span
 };
 
@@ -62,7 +63,8 @@ struct Extent {  // device-side reduction target
   i64 smax;        // largest start
   u64 lmax;        // largest end' - start (exact in unsigned arithmetic for any int64 pair with end >= start)
   i32 gmin, gmax;
-  i32 bad, pad;    // bad: some row has end < start
+  i32 bad;         // some row has end < start
+  i32 unsorted;    // bit k: set k is NOT in (group code, start) order
   i64 endcap;      // in: clamp for the ends when measuring spans (I64_MAX: none); set by the host wrapper
   u64 total;       // sum of the group spans (written by layout_offsets_kernel)
 };
@@ -90,7 +92,7 @@ static __global__ void extent_init_kernel(Extent* x, i64* gmax, i32 nb) {
     x->smax = I64_MIN;
     x->lmax = 0;
     x->bad = 0;
-    x->pad = 0;
+    x->unsorted = 0;
     x->gmin = 0x7fffffff;
     x->gmax = (i32)0x80000000;
     x->total = 0;
@@ -104,7 +106,8 @@ static __global__ void extent_init_kernel(Extent* x, i64* gmax, i32 nb) {
 // after the first few rows of a block almost never happens.
 static __global__ void __launch_bounds__(256) extent_kernel(const i32* __restrict__ grp, const i64* __restrict__ s,
                                                             const i64* __restrict__ e, u64 n, int point_adjust, i32 nb,
-                                                            Extent* __restrict__ out, i64* __restrict__ gmax_out) {
+                                                            int set_bit, Extent* __restrict__ out,
+                                                            i64* __restrict__ gmax_out) {
   extern __shared__ i64 s_gmax[];
   const bool staged = nb <= EXTENT_SMEM_GROUPS;
   volatile i64* table = staged ? s_gmax : gmax_out;
@@ -117,6 +120,15 @@ static __global__ void __launch_bounds__(256) extent_kernel(const i32* __restric
   u64 lhi = 0;
   bool bad = false;
   i32 glo = 0x7fffffff, ghi = (i32)0x80000000;
+  bool disorder = false;
+  // row i is out of order if (group, start) of row i-1 is larger (sorted input -- BED files usually are --
+  // skips the radix passes altogether); the neighbour's line is in L1 from the previous lane's load
+  auto check_order = [&](u64 i, i64 a, i32 g) {
+    if (i == 0) return;
+    const i64 pa = s[i - 1];
+    const i32 pg = grp ? grp[i - 1] : 0;
+    disorder |= pg > g || (pg == g && pa > a);
+  };
   auto take = [&](i64 a, i64 b, i32 g) {
     if (point_adjust && a == b) b += 1;
     const i64 top = max(a, b);
@@ -144,10 +156,19 @@ static __global__ void __launch_bounds__(256) extent_kernel(const i32* __restric
       b[u] = e[i + u * stride];
       g[u] = grp ? grp[i + u * stride] : 0;
     }
+    // order check on one row in four only: random input fails it at once, and a set that passes is
+    // checked in full by order_check_kernel (measure_layout) -- so unsorted input pays almost nothing
+    check_order(i, a[0], g[0]);
 #pragma unroll
     for (int u = 0; u < 4; ++u) take(a[u], b[u], g[u]);
   }
-  for (; i < n; i += stride) take(s[i], e[i], grp ? grp[i] : 0);
+  for (; i < n; i += stride) {
+    const i64 a = s[i];
+    const i32 g = grp ? grp[i] : 0;
+    check_order(i, a, g);
+    take(a, e[i], g);
+  }
+  if (__any_sync(0xffffffffu, disorder) && lane_id() == 0) atomicOr(&out->unsorted, set_bit);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
@@ -173,6 +194,17 @@ static __global__ void __launch_bounds__(256) extent_kernel(const i32* __restric
     for (i32 i = threadIdx.x; i < nb; i += blockDim.x)
       if (s_gmax[i] != I64_MIN) atomicMax(&gmax_out[i], s_gmax[i]);
   }
+}
+
+// exact order check of one set (only run for sets whose sampled check in extent_kernel found no disorder)
+static __global__ void __launch_bounds__(256) order_check_kernel(const i32* __restrict__ grp, const i64* __restrict__ s,
+                                                                 u64 n, int set_bit, Extent* __restrict__ out) {
+  bool disorder = false;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const i32 g = grp ? grp[i] : 0, pg = grp ? grp[i - 1] : 0;
+    disorder |= pg > g || (pg == g && s[i - 1] > s[i]);
+  }
+  if (__any_sync(0xffffffffu, disorder) && lane_id() == 0) atomicOr(&out->unsorted, set_bit);
 }
 
 // goff[g] = sum of spans of the groups before g; one block, sequential over a
@@ -273,10 +305,11 @@ static int measure_layout(const RowSet* sets, int n_sets, i32 nb, int point_adju
     if (r.n <= 0) continue;
     BF_LAUNCH(PC_EXTENT, 20 * r.n, st,
               extent_kernel<<<stream_grid((u64)r.n, 1024), 256, smem, st>>>(nb > 1 ? r.grp : nullptr, r.s, r.e, (u64)r.n,
-                                                                           point_adjust, nb, sc.extent, sc.gmax));
+                                                                           point_adjust, nb, 1 << k, sc.extent, sc.gmax));
   }
   // first without clamping (the packed lengths then order tied starts exactly as the reference does);
   // only coordinates that do not fit 64 key bits otherwise -- INT64_MAX ends -- get the clamp
+  u32 presorted = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
     BF_LAUNCH(PC_EXTENT, 0, st, layout_offsets_kernel<<<1, 1024, 0, st>>>(sc.extent, sc.gmax, nb, attempt, sc.goff));
     Extent ext;
@@ -294,7 +327,25 @@ static int measure_layout(const RowSet* sets, int n_sets, i32 nb, int point_adju
       set_error("%s: group code outside [0,%d): min %d max %d", who, nb, ext.gmin, ext.gmax);
       return BF_ERR_GROUP;
     }
+    if (attempt == 0) {
+      // sets that passed the sampled order check get the exact one (12 B/row, only for sorted-looking input)
+      const u32 maybe = ~(u32)ext.unsorted & ((1u << n_sets) - 1u);
+      bool asked = false;
+      for (int k = 0; k < n_sets; ++k) {
+        if (!((maybe >> k) & 1u) || sets[k].n < 2) continue;
+        BF_LAUNCH(PC_EXTENT, 12 * sets[k].n, st,
+                  order_check_kernel<<<stream_grid((u64)sets[k].n, 2048), 256, 0, st>>>(
+                      nb > 1 ? sets[k].grp : nullptr, sets[k].s, (u64)sets[k].n, 1 << k, sc.extent));
+        asked = true;
+      }
+      if (asked) {
+        BF_CUDA(cudaMemcpyAsync(&ext, sc.extent, sizeof(Extent), cudaMemcpyDeviceToHost, st));
+        BF_CUDA(cudaStreamSynchronize(st));
+      }
+      presorted = ~(u32)ext.unsorted & ((1u << n_sets) - 1u);
+    }
     const int rc = make_key_layout(ext, nb, sc.goff, L);
+    L->presorted = presorted;
     if (rc != BF_ERR_RANGE || !clamp_ends || attempt == 1) return rc;
   }
   return BF_ERR_RANGE;
@@ -304,6 +355,10 @@ static int measure_layout(const RowSet* sets, int n_sets, i32 nb, int point_adju
 constexpr int KEY_POINT_ADJUST = 1;  // end' = end + (end == start)
 constexpr int KEY_BY_END = 2;        // high field = linear END coordinate (closest: left neighbours)
 constexpr int KEY_NO_TIE_FIX = 4;    // keep rows that share the high field in row order
+constexpr int KEY_PRESORTED = 8;     // the rows already are in (group, start) order: no radix passes
+__host__ __device__ __forceinline__ int presorted_mode(const KeyLayout& L, int set_index) {
+  return (L.presorted >> set_index) & 1u ? KEY_PRESORTED : 0;
+}
 
 // Build keys and, in the same pass over the inputs, the histograms of every
 // radix digit place (so the sort never re-reads the keys to count them).

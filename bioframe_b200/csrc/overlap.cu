@@ -801,8 +801,8 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   plan->L = L;
   // ---- sort both sets ----
   SortResult r1, r2;
-  BF_TRY(sort_rows(nb > 1 ? grp1 : nullptr, s1, e1, n1, L, 1, w.s[0].sb, w.radix, st, &r1));
-  BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, 1, w.s[1].sb, w.radix, st, &r2));
+  BF_TRY(sort_rows(nb > 1 ? grp1 : nullptr, s1, e1, n1, L, KEY_POINT_ADJUST | presorted_mode(L, 0), w.s[0].sb, w.radix, st, &r1));
+  BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, KEY_POINT_ADJUST | presorted_mode(L, 1), w.s[1].sb, w.radix, st, &r2));
   plan->key1 = r1.keys;
   plan->id1 = r1.vals;
   plan->key2 = r2.keys;

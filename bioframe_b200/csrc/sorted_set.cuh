@@ -260,8 +260,10 @@ static int sort_rows(const i32* grp, const i64* s, const i64* e, i64 n, const Ke
     // end', then stable sort by (group, start) -> (group, start, end', row) exactly.
     return sort_rows_two_keys(grp, s, e, n, L, point_adjust, ws, sc, st, res);
   }
-  // main sort: stable, on the (group, start) bits only
-  const RadixPlan rp = make_radix_plan(L.LB, L.total_bits);
+  // main sort: stable, on the (group, start) bits only -- or nothing at all when the extent pass found the
+  // rows already in that order (the tie fix-up below still puts equal starts in (end', row) order)
+  const bool presorted = (point_adjust & KEY_PRESORTED) && !(point_adjust & KEY_BY_END);
+  const RadixPlan rp = presorted ? make_radix_plan(0, 0) : make_radix_plan(L.LB, L.total_bits);
   BF_CUDA(cudaMemsetAsync(sc.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
   BF_TRY(launch_pack_keys(grp, s, e, (u64)n, L, point_adjust, rp, ws.keyA, sc.hist, st));
   BF_TRY(radix_sort_passes<true>(ws.keyA, ws.keyB, ws.idA, ws.idB, true, (u64)n, nullptr, rp, sc, st, res));

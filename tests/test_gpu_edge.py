@@ -105,3 +105,36 @@ def test_coverage_queries_outside_target_extent():
     cov = engine.coverage(g1, s1, e1, g2, s2, e2, 3).cpu().numpy()
     assert np.array_equal(cov, oo.coverage_coded(g1, s1, e1, g2, s2, e2, 3))
     assert list(cov) == [200, 50, 0, 2, 5, 0]
+
+
+@pytest.mark.parametrize("which", ["both", "first", "second"])
+def test_presorted_inputs_skip_the_radix_passes(which):
+    """rows already in (group, start) order (typical BED files): the engine sorts nothing and only
+    fixes ties; results must not change"""
+    from bioframe_b200 import engine
+
+    rng = np.random.default_rng(33)
+
+    def make(n, sort):
+        g = rng.integers(0, 6, n).astype(np.int32)
+        s = rng.integers(0, 3000, n).astype(np.int64)  # dense: plenty of equal starts with unsorted ends
+        e = s + rng.integers(0, 80, n)
+        if sort:
+            o = np.lexsort([s, g])
+            g, s, e = g[o], s[o], e[o]
+        return g, s, e
+
+    g1, s1, e1 = make(30000, which in ("both", "first"))
+    g2, s2, e2 = make(20000, which in ("both", "second"))
+    for how in ("inner", "outer"):
+        _eq(engine.overlap_intidxs(g1, s1, e1, g2, s2, e2, 6, how=how), oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, 6, how))
+    _eq(engine.closest_intidxs(g1, s1, e1, g2, s2, e2, 6, k=3), oo.closest_intidxs_coded(g1, s1, e1, g2, s2, e2, 6, k=3))
+    cnt = engine.count_overlaps(g1, s1, e1, g2, s2, e2, 6).cpu().numpy()
+    i, _ = oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, 6, how="inner")
+    assert np.array_equal(cnt, np.bincount(i, minlength=len(s1)))
+    for md in (0, None):
+        res = engine.cluster(g1, s1, e1, 6, min_dist=md)
+        ids, cs, ce, cn = oo.cluster_coded(g1, s1, e1, 6, md)
+        assert np.array_equal(res["ids"].cpu().numpy(), ids) and np.array_equal(res["cend"].cpu().numpy(), ce)
+    cov = engine.coverage(g1, s1, e1, g2, s2, e2, 6).cpu().numpy()
+    assert np.array_equal(cov, oo.coverage_coded(g1, s1, e1, g2, s2, e2, 6))
