@@ -592,35 +592,64 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
   };
   // outputs of one group (nearly every block): row = t0 + delta[group] + slot
   const bool one_group = c_lo == c_hi;
-  i64* const out1 = ev1 + (t0 + delta[c_lo]);
-  i64* const out2 = ev2 + (t0 + delta[c_lo]);
-  // gathers of 4 outputs in flight before their stores
-#pragma unroll 1
-  for (int h = 0; h < EM_IPT; h += 4) {
-    u32 own[4], oth[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      // slots past the block's last output read the last valid slot instead (unpredicated loads keep
-      // the shared-memory address arithmetic out of the loop); only the stores are predicated
-      const i32 x = min((h + j) * EM_THREADS + (i32)tid, nout - 1);
+  if (one_group) {
+    // Two adjacent output rows per thread and step, written with 16-byte stores.  The pairs are aligned
+    // to even output rows (16-byte aligned addresses): when the block's first row is odd, slot 0 is a
+    // single that thread 0 writes on its own.
+    const i64 row0 = t0 + delta[c_lo];
+    i64* const out1 = ev1 + row0;
+    i64* const out2 = ev2 + row0;
+    const i32 par = (i32)(row0 & 1);
+    auto slot = [&](i32 x, u32& own, u32& oth) {  // x clamped to a valid slot by the caller
       const EmitItem it = s_item[s_owner[EM_PAD(x)]];
-      own[j] = it.id;
-      oth[j] = other_id[it.src + (u32)x];
+      own = it.id;
+      oth = other_id[it.src + (u32)x];
+    };
+    if (par && tid == 0) {
+      u32 own, oth;
+      slot(0, own, oth);
+      out1[0] = (B_SIDE ? (i64)oth : (i64)own) + off1;
+      out2[0] = (B_SIDE ? (i64)own : (i64)oth) + off2;
     }
+    const i32 last = nout - 1;
+#pragma unroll 1
+    for (int h = 0; h < EM_IPT / 2; h += 2) {
+      u32 own[4], oth[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const i32 x = (h + j) * EM_THREADS + (i32)tid;
-      if (x < nout) {
-        const i64 a = (B_SIDE ? (i64)oth[j] : (i64)own[j]) + off1, b = (B_SIDE ? (i64)own[j] : (i64)oth[j]) + off2;
-        if (one_group) {
-          out1[x] = a;
-          out2[x] = b;
+      for (int j = 0; j < 2; ++j) {
+        const i32 x = par + 2 * ((h + j) * EM_THREADS + (i32)tid);
+        slot(min(x, last), own[2 * j], oth[2 * j]);
+        slot(min(x + 1, last), own[2 * j + 1], oth[2 * j + 1]);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const i32 x = par + 2 * ((h + j) * EM_THREADS + (i32)tid);
+        if (x > last) continue;
+        const i64 a0 = (B_SIDE ? (i64)oth[2 * j] : (i64)own[2 * j]) + off1;
+        const i64 b0 = (B_SIDE ? (i64)own[2 * j] : (i64)oth[2 * j]) + off2;
+        if (x + 1 <= last) {
+          const i64 a1 = (B_SIDE ? (i64)oth[2 * j + 1] : (i64)own[2 * j + 1]) + off1;
+          const i64 b1 = (B_SIDE ? (i64)own[2 * j + 1] : (i64)oth[2 * j + 1]) + off2;
+          *reinterpret_cast<longlong2*>(out1 + x) = make_longlong2(a0, a1);
+          *reinterpret_cast<longlong2*>(out2 + x) = make_longlong2(b0, b1);
         } else {
-          const i64 t = t0 + x;
-          const i64 row = t + delta[group_of(t, c_lo, (i64)c_hi + 1)];
-          ev1[row] = a;
-          ev2[row] = b;
+          out1[x] = a0;
+          out2[x] = b0;
         }
+      }
+    }
+  } else {
+    // a block whose outputs span a group boundary: the row offset changes inside the block
+#pragma unroll 1
+    for (int h = 0; h < EM_IPT; ++h) {
+      const i32 x = h * EM_THREADS + (i32)tid;
+      if (x < nout) {
+        const EmitItem it = s_item[s_owner[EM_PAD(x)]];
+        const u32 own = it.id, oth = other_id[it.src + (u32)x];
+        const i64 t = t0 + x;
+        const i64 row = t + delta[group_of(t, c_lo, (i64)c_hi + 1)];
+        ev1[row] = (B_SIDE ? (i64)oth : (i64)own) + off1;
+        ev2[row] = (B_SIDE ? (i64)own : (i64)oth) + off2;
       }
     }
   }
