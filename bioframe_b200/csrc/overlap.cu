@@ -489,6 +489,7 @@ __global__ void offset_table_kernel(OverlapWS w, i64 n1, i64 n2, i32 nb, i32 how
 constexpr int EM_THREADS = 256;
 constexpr int EM_IPT = 8;
 constexpr int EM_TILE = EM_THREADS * EM_IPT;
+constexpr int EM_AHEAD = 148 * 6;  // blocks resident at a time (6 per SM)
 
 // part[b] = owner rows consumed before diagonal b * EM_TILE = #{p : p + scan[p] < D};
 // pgrp[b] = group of the first output of block b.  One thread per block
@@ -533,6 +534,14 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
   const i32 c_lo = pgrp[blockIdx.x], c_hi = pgrp[blockIdx.x + 1];  // c_hi: upper bound of the last output's group
   const i64 t0 = D0 - p0, t1 = D1 - p1;
   const i32 nout = (i32)(t1 - t0);
+  // the block that will take over this SM slot about one wave from now: its partition entries are read
+  // here and its owner rows are pulled into L2 further down, off this block's critical path
+  const bool ahead = blockIdx.x + EM_AHEAD < gridDim.x;
+  i64 q0 = 0, q1 = 0;
+  if (ahead) {
+    q0 = part[blockIdx.x + EM_AHEAD];
+    q1 = part[blockIdx.x + EM_AHEAD + 1];
+  }
   if (nout <= 0) return;
   const i64 first = p0 > 0 ? p0 - 1 : 0;  // owner of the first output may have started earlier
   const i32 nitems = (i32)(p1 - first);
@@ -555,6 +564,15 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
     for (i32 x = tid; x < (EM_TILE + EM_TILE / 8) / 4; x += EM_THREADS) z[x] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
+  if (ahead) {
+    const i64 f = (q0 > 0 ? q0 - 1 : 0) & ~(i64)31;  // 128-byte lines of 32 rows
+    const i64 row = f + (i64)tid * 32;
+    if (row <= q1 && row < n_owner) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(scan.loc + row));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(lo + row));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(owner_id + row));
+    }
+  }
   for (i32 i = tid; i < nitems; i += EM_THREADS) {
     const i32 r = s_rel[i];
     if (s_rel[i + 1] > r && r >= 0 && r < nout) s_owner[EM_PAD(r)] = (u32)i;
