@@ -13,7 +13,7 @@ __version__ = "0.1.0"
 
 from . import core  # noqa: F401
 from .core.specs import update_default_colnames  # noqa: F401
-from .ops import closest, cluster, complement, count_overlaps, coverage, merge, overlap, setdiff  # noqa: F401
+from .ops import closest, cluster, complement, count_overlaps, coverage, merge, overlap, setdiff, subtract  # noqa: F401
 
 __all__ = ["overlap", "closest", "cluster", "merge", "complement", "coverage", "count_overlaps", "setdiff", "core",
            "update_default_colnames"]

@@ -720,7 +720,32 @@ static int complement_emit_impl(const ComplementPlan* plan, void* ws_ptr, i32* r
 
 }  // namespace bf
 
+#include "subtract.cuh"
+
 extern "C" {
+
+size_t bf_subtract_workspace_bytes(int64_t n1, int64_t n2, int32_t n_groups) {
+  if (n1 < 0 || n2 < 0 || n_groups < 1) return 0;
+  bf::Arena a(nullptr);
+  bf::SubtractWS w;
+  bf::layout_subtract(a, n1, n2, n_groups, &w);
+  return a.off;
+}
+int bf_subtract_count(const int32_t* grp1, const int64_t* start1, const int64_t* end1, int64_t n1, const int32_t* grp2,
+                      const int64_t* start2, const int64_t* end2, int64_t n2, int32_t n_groups, void* ws,
+                      size_t ws_bytes, bf_plan* plan, void* stream, int64_t* n_rows_out) {
+  bf::SubtractPlan* p = (bf::SubtractPlan*)plan;
+  int rc = bf::subtract_count_impl((const i32*)grp1, (const i64*)start1, (const i64*)end1, n1, (const i32*)grp2,
+                                   (const i64*)start2, (const i64*)end2, n2, n_groups, ws, ws_bytes, p,
+                                   (cudaStream_t)stream);
+  if (rc == BF_OK && n_rows_out) *n_rows_out = p->n_rows;
+  return rc;
+}
+int bf_subtract_emit(const bf_plan* plan, void* ws, int64_t* row_out, int64_t* start_out, int64_t* end_out,
+                     int64_t* sub_index_out, void* stream) {
+  return bf::subtract_emit_impl((const bf::SubtractPlan*)plan, ws, (i64*)row_out, (i64*)start_out, (i64*)end_out,
+                                (i64*)sub_index_out, (cudaStream_t)stream);
+}
 
 size_t bf_cluster_workspace_bytes(int64_t n, int32_t n_groups) {
   if (n < 0 || n_groups < 1) return 0;

@@ -187,6 +187,35 @@ def count_overlaps(grp1, start1, end1, grp2, start2, end2, n_groups, closed=Fals
     return counts
 
 
+def subtract(grp1, start1, end1, grp2, start2, end2, n_groups, want_sub_index=True, device=None):
+    """Pieces of every row of set 1 that the union of set 2 does not cover (ops.subtract, ops.py:1243-1330).
+    -> (row int64[R], start int64[R], end int64[R], sub_index int64[R] or None) on device: rows of set 1 in
+    ascending order, the pieces of a row left to right."""
+    _require_cuda()
+    L = _lib.lib()
+    device = torch.device(device if device is not None else "cuda")
+    s1, e1 = _as(start1, torch.int64, device), _as(end1, torch.int64, device)
+    s2, e2 = _as(start2, torch.int64, device), _as(end2, torch.int64, device)
+    g1 = _as(grp1, torch.int32, device) if n_groups > 1 else None
+    g2 = _as(grp2, torch.int32, device) if n_groups > 1 else None
+    n1, n2 = int(s1.numel()), int(s2.numel())
+    with torch.cuda.device(device):
+        ws = Workspace.get(device, max(L.bf_subtract_workspace_bytes(n1, n2, n_groups), 256))
+        plan = _lib.Plan()
+        n_rows = C.c_int64(0)
+        stream = _stream_ptr(device)
+        rc = L.bf_subtract_count(_ptr(g1), _ptr(s1), _ptr(e1), n1, _ptr(g2), _ptr(s2), _ptr(e2), n2, n_groups,
+                                 _ptr(ws), ws.numel(), C.byref(plan), stream, C.byref(n_rows))
+        _lib.check(rc, "bf_subtract_count")
+        row = torch.empty(n_rows.value, dtype=torch.int64, device=device)
+        ps = torch.empty(n_rows.value, dtype=torch.int64, device=device)
+        pe = torch.empty(n_rows.value, dtype=torch.int64, device=device)
+        sub = torch.empty(n_rows.value, dtype=torch.int64, device=device) if want_sub_index else None
+        rc = L.bf_subtract_emit(C.byref(plan), _ptr(ws), _ptr(row), _ptr(ps), _ptr(pe), _ptr(sub), stream)
+        _lib.check(rc, "bf_subtract_emit")
+    return row, ps, pe, sub
+
+
 def complement(region, start, end, bounds_lo, bounds_hi, device=None):
     """Gaps of the (already clipped) intervals inside each view region.
     -> (region int32[G], start int64[G], end int64[G]) on device, regions in code order."""

@@ -25,7 +25,7 @@ from . import engine as _engine
 from .core import checks
 from .core.specs import _get_default_colnames, _verify_columns
 
-__all__ = ["overlap", "closest", "cluster", "merge", "complement", "coverage", "count_overlaps", "setdiff"]
+__all__ = ["overlap", "closest", "cluster", "merge", "complement", "coverage", "count_overlaps", "setdiff", "subtract"]
 
 _INT64_MAX = np.iinfo(np.int64).max
 
@@ -663,3 +663,87 @@ def count_overlaps(df1, df2, suffixes=("", "_"), return_input=True, cols1=None, 
 def setdiff(df1, df2, cols1=None, cols2=None, on=None):
     """Rows of df1 that overlap no interval of df2 (ops.py:1333-1368), original index kept."""
     return df1.iloc[np.flatnonzero(_overlap_counts(df1, df2, cols1, cols2, on) == 0)]
+
+
+# --------------------------------------------------------------------------
+# subtract  (SURVEY.md 8f "next" #1: fused -- merged targets + two probes per query, no pair list)
+# --------------------------------------------------------------------------
+def _subtract_composed(df1, df2, return_index, suffixes, cols1, cols2):
+    """ops.subtract exactly as the reference composes it (ops.py:1284-1330): left overlap of df1 with
+    complement(df2).  Used when df1's index does not order like its rows (the result is sorted by index
+    labels, ops.py:549-550)."""
+    ck1, sk1, ek1 = _get_default_colnames() if cols1 is None else cols1
+    ck2, sk2, ek2 = _get_default_colnames() if cols2 is None else cols2
+    name_updates = {ck1 + suffixes[0]: ck1, "overlap_" + sk1: sk1, "overlap_" + ek1: ek1}
+    for c in df1.columns:
+        if c not in (ck1, sk1, ek1):
+            name_updates[c + suffixes[0]] = c
+    if return_index:
+        name_updates["index" + suffixes[0]] = "index" + suffixes[0]
+        name_updates["index" + suffixes[1]] = "complement_index" + suffixes[1]
+    all_chroms = np.unique(list(pd.unique(df1[ck1].dropna())) + list(pd.unique(df2[ck2].dropna())))
+    if len(all_chroms) == 0:
+        raise ValueError("No chromosomes remain after dropping nulls")
+    gaps = complement(df2, view_df={c: _INT64_MAX for c in all_chroms}, cols=cols2).astype(
+        {sk2: pd.Int64Dtype(), ek2: pd.Int64Dtype()}
+    )
+    out = overlap(df1, gaps, how="left", suffixes=suffixes, return_index=return_index, return_overlap=True,
+                  keep_order=True, cols1=cols1, cols2=cols2)[list(name_updates)]
+    out = out.rename(columns=name_updates)
+    out = out.iloc[~pd.isna(out[sk1].values)]
+    out.reset_index(drop=True, inplace=True)
+    if return_index:
+        inds = out["index" + suffixes[0]].values
+        comp = out["complement_index" + suffixes[1]].copy()
+        for i in np.unique(inds):
+            comp[inds == i] -= comp[inds == i].min()
+        out["sub_index" + suffixes[1]] = comp.copy()
+        out.drop(columns=["complement_index" + suffixes[1]], inplace=True)
+    return out
+
+
+def subtract(df1, df2, return_index=False, suffixes=("", "_"), cols1=None, cols2=None):
+    """Intervals of df1 with everything covered by df2 removed (ops.py:1243-1330): an interval comes back
+    as zero, one or several pieces; index reset, coordinates as nullable Int64.  With return_index=True
+    also 'index'+suffixes[0] (label of the source row) and 'sub_index'+suffixes[1] (ordinal of the piece).
+
+    The reference left-joins df1 with complement(df2) and sorts by index labels.  When df1's index is an
+    increasing integer index (e.g. the default RangeIndex) that order is df1's row order and one fused
+    kernel call yields the pieces; otherwise the reference's composition runs on the device overlap."""
+    ck1, sk1, ek1 = _get_default_colnames() if cols1 is None else cols1
+    ck2, sk2, ek2 = _get_default_colnames() if cols2 is None else cols2
+    _verify_columns(df1, [ck1, sk1, ek1])
+    _verify_columns(df2, [ck2, sk2, ek2])
+    ix = df1.index
+    fused = pd.api.types.is_integer_dtype(ix.dtype) and ix.is_monotonic_increasing and ix.is_unique
+    if not fused:
+        return _subtract_composed(df1, df2, return_index, suffixes, cols1, cols2)
+
+    codes1, keys1 = _group_keys(df1, [ck1])
+    codes2, keys2 = _group_keys(df2, [ck2])
+    if len(keys1) + len(keys2) == 0:
+        raise ValueError("No chromosomes remain after dropping nulls")
+    checks.is_bedframe(df2, raise_errors=True, cols=[ck2, sk2, ek2])  # overlap(view, df2) inside complement
+    checks.is_bedframe(df1, raise_errors=True, cols=[ck1, sk1, ek1])  # overlap(df1, gaps)
+    union = sorted(set(keys1) | set(keys2), key=str)
+    rank = {key: r for r, key in enumerate(union)}
+    t1 = np.array([rank[k] for k in keys1], dtype=np.int32)
+    t2 = np.array([rank[k] for k in keys2], dtype=np.int32)
+    v1, v2 = np.flatnonzero(codes1 >= 0), np.flatnonzero(codes2 >= 0)
+    row = ps = pe = sub = np.empty(0, dtype=np.int64)
+    if len(v1):
+        row, ps, pe, sub = _engine.subtract(
+            t1[codes1[v1]], _int64_coords(df1, sk1)[v1], _int64_coords(df1, ek1)[v1],
+            t2[codes2[v2]] if len(v2) else np.empty(0, np.int32),
+            _int64_coords(df2, sk2)[v2], _int64_coords(df2, ek2)[v2], max(len(union), 1),
+            want_sub_index=bool(return_index),
+        )
+        row, ps, pe = v1[_to_host(row)], _to_host(ps), _to_host(pe)
+    others = [c for c in df1.columns if c not in (ck1, sk1, ek1)]
+    out = df1.iloc[row][[ck1, sk1, ek1, *others]].reset_index(drop=True)
+    out[sk1] = pd.array(ps, dtype=pd.Int64Dtype())
+    out[ek1] = pd.array(pe, dtype=pd.Int64Dtype())
+    if return_index:
+        out["index" + suffixes[0]] = pd.array(np.asarray(ix)[row], dtype=pd.Int64Dtype())
+        out["sub_index" + suffixes[1]] = pd.array(_to_host(sub) if len(row) else sub, dtype=pd.Int64Dtype())
+    return out

@@ -179,6 +179,22 @@ int bf_complement_count(const int32_t* region, const int64_t* start, const int64
 int bf_complement_emit(const bf_plan* plan, void* ws, int32_t* region_out, int64_t* start_out,
                        int64_t* end_out, void* stream);
 
+/* ---- subtract: replaces ops.subtract (ops.py:1243-1330), which the reference composes from
+ * complement(df2) over [0, INT64_MAX) per chromosome (ops.py:1305-1309), a left overlap of df1 with those
+ * gaps returning the clipped coordinates (ops.py:1310-1316, 480-497) and a filter of the rows without a
+ * partner (ops.py:1318).  Fused here: merge of the targets + two probes per query, no pair list.
+ * Output rows: for every row of set 1 in ascending row order (keep_order=True on a monotonic index) the
+ * pieces of it not covered by set 2, left to right: row_out = row number in set 1, start/end = the piece,
+ * sub_index_out = ordinal of the piece within its row ('sub_index' of return_index=True,
+ * ops.py:1322-1328).  Rows that are covered entirely produce nothing.  row_out / sub_index_out may be NULL. */
+size_t bf_subtract_workspace_bytes(int64_t n1, int64_t n2, int32_t n_groups);
+int bf_subtract_count(const int32_t* grp1, const int64_t* start1, const int64_t* end1, int64_t n1,
+                      const int32_t* grp2, const int64_t* start2, const int64_t* end2, int64_t n2,
+                      int32_t n_groups, void* ws, size_t ws_bytes, bf_plan* plan, void* stream,
+                      int64_t* n_rows_out);
+int bf_subtract_emit(const bf_plan* plan, void* ws, int64_t* row_out, int64_t* start_out, int64_t* end_out,
+                     int64_t* sub_index_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -281,6 +281,46 @@ def coverage_coded(g1, s1, e1, g2, s2, e2, n_groups):
     return out
 
 
+def subtract_coded(g1, s1, e1, g2, s2, e2, n_groups):
+    """ops.subtract (ops.py:1243-1330) on group-coded arrays, composed the reference's way: per group the
+    targets are clipped to the view [0, INT64_MAX) (inner overlap with the view region, ops.py:1614-1622),
+    complemented (arrops.py:482-503; a group without targets yields the whole view, ops.py:1652-1657), the
+    queries are overlapped with the gaps (arrops.py:290-375) and clipped to them (ops.py:484-492); rows are
+    ordered by (query row, gap) as keep_order=True does (ops.py:549-550) and the gap ordinals are rebased per
+    query (ops.py:1324-1326).  -> (row, start, end, sub_index)."""
+    s1, e1 = np.asarray(s1, dtype=np.int64), np.asarray(e1, dtype=np.int64)
+    s2, e2 = np.asarray(s2, dtype=np.int64), np.asarray(e2, dtype=np.int64)
+    rows1 = _rows_by_code(g1, len(s1), n_groups)
+    rows2 = _rows_by_code(g2, len(s2), n_groups)
+    out = [[], [], [], []]
+    view_s, view_e = np.array([0], dtype=np.int64), np.array([ao.INT64_MAX], dtype=np.int64)
+    for r1, r2 in zip(rows1, rows2):
+        if len(r1) == 0:
+            continue
+        _, inside = ao.overlap_intervals(view_s, view_e, s2[r2], e2[r2])
+        if len(inside):
+            cs = np.maximum(s2[r2][inside], 0)
+            ce = np.minimum(e2[r2][inside], ao.INT64_MAX)
+            gs, ge = ao.complement_intervals(cs, ce, bounds=(0, ao.INT64_MAX))
+            gs, ge = np.asarray(gs, dtype=np.int64), np.asarray(ge, dtype=np.int64)
+        else:
+            gs, ge = view_s, view_e
+        i, j = ao.overlap_intervals(s1[r1], e1[r1], gs, ge)
+        order = np.lexsort([j, r1[i]])
+        i, j = i[order], j[order]
+        row = r1[i]
+        out[0].append(row)
+        out[1].append(np.maximum(s1[row], gs[j]))
+        out[2].append(np.minimum(e1[row], ge[j]))
+        first = np.r_[True, row[1:] != row[:-1]] if len(row) else np.empty(0, dtype=bool)
+        start_of_run = np.maximum.accumulate(np.where(first, np.arange(len(row)), 0)) if len(row) else np.empty(0, dtype=np.int64)
+        out[3].append(j - j[start_of_run] if len(row) else j)
+    cat = lambda xs: np.concatenate(xs).astype(np.int64) if xs else np.empty(0, dtype=np.int64)  # noqa: E731
+    row, ps, pe, sub = (cat(x) for x in out)
+    order = np.argsort(row, kind="stable")  # groups interleave in row order
+    return row[order], ps[order], pe[order], sub[order]
+
+
 def closest_intidxs_coded(g1, s1, e1, g2, s2, e2, n_groups, k=1, ignore_overlaps=False, ignore_upstream=False,
                           ignore_downstream=False, along=None, self_closest=False):
     """`closest_intidxs` on group-coded arrays, groups visited in code order --

@@ -98,6 +98,25 @@ def main():
                              "end": [120, 500, 300, 350, 80], "name": ["p", "q", "chr2", "x", "ten"]})
         add(f"complement_{tag}_view", "complement", df=df1, view_df=view)
         add(f"complement_{tag}_dict", "complement", df=df1, view_df={"chr1": 500, "chr2": 450, "chrX": 10**6, "chr10": 77})
+    # subtract: drawn from a generator of its own so that the cases above keep their inputs
+    rng2 = np.random.default_rng(77)
+    for tag, opts in (("plain", {}), ("na", dict(with_na=True)), ("cat", dict(categorical=True))):
+        df1, df2 = frames(rng2, **opts)
+        add(f"subtract_{tag}", "subtract", df1=df1, df2=df2)
+        add(f"subtract_{tag}_index", "subtract", df1=df1, df2=df2, return_index=True, suffixes=("_a", "_b"))
+        shuffled = df1.copy()
+        shuffled.index = rng2.permutation(len(shuffled))  # labels do not order like rows: composed path
+        add(f"subtract_{tag}_shuffled", "subtract", df1=shuffled, df2=df2, return_index=True)
+        if tag != "na":
+            dense = pd.concat([df2, df2.assign(start=df2["start"] // 2, end=df2["end"] // 2 + 30)], ignore_index=True)
+            add(f"subtract_{tag}_dense", "subtract", df1=df1, df2=dense, return_index=True)
+    edge1 = pd.DataFrame({"chrom": ["chr1"] * 8 + ["chr3"], "start": [0, 0, 5, 5, 10, 12, 30, 3, 7],
+                          "end": [0, 8, 5, 10, 20, 12, 31, 40, 9], "name": list("abcdefghi")})
+    edge2 = pd.DataFrame({"chrom": ["chr1"] * 6 + ["chr2"], "start": [0, 5, 8, 10, 12, 30, 1], "end": [3, 5, 10, 11, 15, 30, 2]})
+    add("subtract_edges", "subtract", df1=edge1, df2=edge2, return_index=True)
+    add("subtract_edges_cols", "subtract", df1=edge1.rename(columns={"chrom": "c", "start": "s", "end": "e"})[["name", "c", "s", "e"]],
+        df2=edge2, cols1=("c", "s", "e"))
+    add("subtract_no_targets", "subtract", df1=edge1, df2=edge2.iloc[:0])
     with open(os.path.join(HERE, "frames.pkl"), "wb") as f:
         pickle.dump(cases, f, protocol=4)
     print(len(cases), "cases ->", os.path.join(HERE, "frames.pkl"))

@@ -51,6 +51,11 @@ def coverage(grp1, start1, end1, grp2, start2, end2, n_groups, device=None):
     return oo.coverage_coded(grp1, _i64(start1), _i64(end1), grp2, _i64(start2), _i64(end2), n_groups)
 
 
+def subtract(grp1, start1, end1, grp2, start2, end2, n_groups, want_sub_index=True, device=None):
+    row, ps, pe, sub = oo.subtract_coded(grp1, _i64(start1), _i64(end1), grp2, _i64(start2), _i64(end2), n_groups)
+    return row, ps, pe, (sub if want_sub_index else None)
+
+
 def complement(region, start, end, bounds_lo, bounds_hi, device=None):
     b0, b1 = _i64(bounds_lo), _i64(bounds_hi)
     if len(b0) == 0:
