@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="overlap", choices=["overlap", "closest", "cluster", "coverage", "count"],
+    ap.add_argument("--workload", default="overlap", choices=["overlap", "closest", "cluster", "coverage", "count", "subtract"],
                     help="overlap = the north-star line (cfg3); the others are the secondary BASELINE.json configs "
                          "(closest: cfg1 1e7 x 1e6 k=1; cluster: cfg2 1e8 heavy-tailed; coverage: cfg3 sets)")
     ap.add_argument("--k", type=int, default=1)
@@ -233,6 +233,18 @@ def run_secondary(args):
         desc = f"count_overlaps cfg3: {n1} hg38 queries (geom 2kb) x {n2} peak-like targets"
         (sq, stt) = workload(n1, n2, 0, chrom_ids=SAMPLE_CHROMS)
         cpu = lambda: np.bincount(oo.overlap_intidxs_coded(*sq, *stt, N_GROUPS, how="inner")[0], minlength=len(sq[1]))  # noqa: E731
+        cpu_units = len(sq[1]) + len(stt[1])
+    elif wl == "subtract":
+        n1, n2 = args.n1, args.n2
+        (q, t) = workload(n1, n2, 0)
+        d = [torch.from_numpy(a).to(dev) for a in (*q, *t)]
+        call = lambda: engine.subtract(d[0], d[1], d[2], d[3], d[4], d[5], N_GROUPS)  # noqa: E731
+        rows_of = lambda r: int(r[0].numel())  # noqa: E731
+        a_alg = lambda R: 256 * n2 + 36 * n1 + 32 * R  # noqa: E731  (merge of the targets, probes, 4 x 8 B per piece)
+        units, name = n1 + n2, "bf.subtract input intervals/s"
+        desc = f"subtract cfg3: {n1} hg38 queries (geom 2kb) minus {n2} peak-like targets"
+        (sq, stt) = workload(n1, n2, 0, chrom_ids=SAMPLE_CHROMS)
+        cpu = lambda: oo.subtract_coded(*sq, *stt, N_GROUPS)  # noqa: E731
         cpu_units = len(sq[1]) + len(stt[1])
     else:  # coverage
         n1, n2 = args.n1, args.n2
