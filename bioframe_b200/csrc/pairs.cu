@@ -100,9 +100,59 @@ static int sort_pairs_impl(i64* e1, i64* e2, i64 n, i64 max1, i64 max2, void* ws
   return BF_OK;
 }
 
+// Coordinates of the reported pairs: the four gathers + max / min of return_overlap=True
+// (ops.py:480-497, closest ops.py:1187-1194) and closest's distance (ops.py:1207-1221), one pass over
+// the pair list while it still is on the device.  Rows with a missing partner (-1) get 0; the frame glue
+// masks them like the reference does (ops.py:541-544, 1205, 1222).
+__global__ void __launch_bounds__(256)
+    pair_coords_kernel(const i64* __restrict__ ev1, const i64* __restrict__ ev2, i64 n, const i64* __restrict__ s1,
+                       const i64* __restrict__ e1, const i64* __restrict__ s2, const i64* __restrict__ e2,
+                       i64* __restrict__ ostart, i64* __restrict__ oend, i64* __restrict__ dist) {
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const i64 a = ev1[i], b = ev2[i];
+    i64 os = 0, oe = 0, d = 0;
+    if (a >= 0 && b >= 0) {
+      const i64 as = s1[a], ae = e1[a], bs = s2[b], be = e2[b];
+      os = as > bs ? as : bs;
+      oe = ae < be ? ae : be;
+      const i64 left = as - be, right = bs - ae;  // gap when the partner lies to the left / right
+      d = left > right ? left : right;
+      if (d < 0) d = 0;
+    }
+    if (ostart) ostart[i] = os;
+    if (oend) oend[i] = oe;
+    if (dist) dist[i] = d;
+  }
+}
+
+static int pair_coords_impl(const i64* ev1, const i64* ev2, i64 n, const i64* s1, const i64* e1, const i64* s2,
+                            const i64* e2, i64* ostart, i64* oend, i64* dist, cudaStream_t st) {
+  if (n < 0) {
+    set_error("bf_pair_coords: bad argument (n_rows=%lld)", (long long)n);
+    return BF_ERR_ARG;
+  }
+  if (n == 0 || (!ostart && !oend && !dist)) return BF_OK;
+  if (!ev1 || !ev2 || !s1 || !e1 || !s2 || !e2) {
+    set_error("bf_pair_coords: null pointer");
+    return BF_ERR_ARG;
+  }
+  const int outs = (ostart != nullptr) + (oend != nullptr) + (dist != nullptr);
+  BF_LAUNCH(PC_GATHER, (16 + 32 + 8 * outs) * n, st,
+            pair_coords_kernel<<<stream_grid((u64)n, 1024), 256, 0, st>>>(ev1, ev2, n, s1, e1, s2, e2, ostart, oend, dist));
+  return BF_OK;
+}
+
 }  // namespace bf
 
 extern "C" {
+int bf_pair_coords(const int64_t* events1, const int64_t* events2, int64_t n_rows, const int64_t* start1,
+                   const int64_t* end1, const int64_t* start2, const int64_t* end2, int64_t* overlap_start_out,
+                   int64_t* overlap_end_out, int64_t* distance_out, void* stream) {
+  return bf::pair_coords_impl((const i64*)events1, (const i64*)events2, n_rows, (const i64*)start1, (const i64*)end1,
+                              (const i64*)start2, (const i64*)end2, (i64*)overlap_start_out, (i64*)overlap_end_out,
+                              (i64*)distance_out, (cudaStream_t)stream);
+}
 size_t bf_sort_pairs_workspace_bytes(int64_t n_rows) {
   if (n_rows < 0) return 0;
   bf::Arena a(nullptr);

@@ -33,6 +33,12 @@ def _as(t, dtype, device):
     return t.to(device=device, dtype=dtype, non_blocking=True).contiguous()
 
 
+def to_device(x, dtype="int64", device=None):
+    """numpy / tensor -> CUDA tensor (the frame glue moves a column once and hands it to several calls)."""
+    _require_cuda()
+    return _as(x, getattr(torch, dtype), torch.device(device if device is not None else "cuda"))
+
+
 def _stream_ptr(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -185,6 +191,27 @@ def count_overlaps(grp1, start1, end1, grp2, start2, end2, n_groups, closed=Fals
                                  int(bool(closed)), _ptr(ws), ws.numel(), _stream_ptr(device), _ptr(counts))
         _lib.check(rc, "bf_count_overlaps")
     return counts
+
+
+def pair_coords(ev1, ev2, start1, end1, start2, end2, want_overlap=True, want_distance=False, device=None):
+    """Clipped coordinates / distances of reported pairs (return_overlap, return_distance of the frame ops).
+    -> (overlap_start, overlap_end, distance) int64 device tensors (None where not wanted); rows with a -1
+    partner hold 0."""
+    _require_cuda()
+    L = _lib.lib()
+    device = torch.device(device if device is not None else "cuda")
+    a, b = _as(ev1, torch.int64, device), _as(ev2, torch.int64, device)
+    s1, e1 = _as(start1, torch.int64, device), _as(end1, torch.int64, device)
+    s2, e2 = _as(start2, torch.int64, device), _as(end2, torch.int64, device)
+    n = int(a.numel())
+    with torch.cuda.device(device):
+        os_ = torch.empty(n, dtype=torch.int64, device=device) if want_overlap else None
+        oe = torch.empty(n, dtype=torch.int64, device=device) if want_overlap else None
+        dist = torch.empty(n, dtype=torch.int64, device=device) if want_distance else None
+        rc = L.bf_pair_coords(_ptr(a), _ptr(b), n, _ptr(s1), _ptr(e1), _ptr(s2), _ptr(e2), _ptr(os_), _ptr(oe),
+                              _ptr(dist), _stream_ptr(device))
+        _lib.check(rc, "bf_pair_coords")
+    return os_, oe, dist
 
 
 def subtract(grp1, start1, end1, grp2, start2, end2, n_groups, want_sub_index=True, device=None):

@@ -79,7 +79,8 @@ def _to_host(t):
 # --------------------------------------------------------------------------
 # overlap
 # --------------------------------------------------------------------------
-def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _group_order=None, _sort_pairs=False):
+def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _group_order=None, _sort_pairs=False,
+                     _coords=False):
     """Integer row positions of overlapping pairs, -1 where a kept row has no
     partner.  Mirrors ops._overlap_intidxs (ops.py:242-338): groups are
     (chrom, *on); the group blocks come in the iteration order of
@@ -125,18 +126,15 @@ def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _gro
 
     g1 = ranks_of(codes1, keys1, rank_na1) if len(df1) else np.empty(0, np.int32)
     g2 = ranks_of(codes2, keys2, rank_na2) if len(df2) else np.empty(0, np.int32)
-    ev1, ev2, _ = _engine.overlap_intidxs(
-        g1,
-        _int64_coords(df1, sk1),
-        _int64_coords(df1, ek1),
-        g2,
-        _int64_coords(df2, sk2),
-        _int64_coords(df2, ek2),
-        n_groups,
-        how=how,
-    )
+    s1, e1, s2, e2 = _int64_coords(df1, sk1), _int64_coords(df1, ek1), _int64_coords(df2, sk2), _int64_coords(df2, ek2)
+    if _coords:  # the coordinates go to the device once: the overlap call and the coordinate gather share them
+        s1, e1, s2, e2 = (_engine.to_device(x) for x in (s1, e1, s2, e2))
+    ev1, ev2, _ = _engine.overlap_intidxs(g1, s1, e1, g2, s2, e2, n_groups, how=how)
     if _sort_pairs:  # keep_order on the device: rows by (row of df1, row of df2), -1 last
         ev1, ev2 = _engine.sort_pairs(ev1, ev2, max(len(df1) - 1, 0), max(len(df2) - 1, 0))
+    if _coords:  # clipped coordinates of every pair (return_overlap, ops.py:480-497) while the list is on the device
+        lo, hi, _ = _engine.pair_coords(ev1, ev2, s1, e1, s2, e2)
+        return _to_host(ev1), _to_host(ev2), (_to_host(lo), _to_host(hi))
     return _to_host(ev1), _to_host(ev2)
 
 
@@ -153,6 +151,10 @@ _NULLABLE_INT = {
         (np.uint64, "UInt64Dtype"),
     )
 }
+
+
+def _is_plain_int(col):
+    return isinstance(col.dtype, np.dtype) and col.dtype.kind in "iu" and col.dtype.itemsize <= 8 and col.dtype != np.uint64
 
 
 def _to_nullable_dtype(dtype):
@@ -212,7 +214,16 @@ def overlap(
     device_order = bool(keep_order) and all(
         ix.is_monotonic_increasing and ix.is_unique for ix in (df1.index, df2.index)
     )
-    ev1, ev2 = _overlap_intidxs(df1, df2, how=how, cols1=cols1, cols2=cols2, on=on, _sort_pairs=device_order)
+    # return_overlap gathers four coordinates per pair (ops.py:484-492): done on the device for plain integer
+    # columns; nullable columns keep the host path (their NA propagation decides the reference's dtypes)
+    device_coords = (
+        bool(return_overlap)
+        and (how == "inner" or ensure_int)
+        and all(_is_plain_int(df[c]) for df, c in ((df1, sk1), (df1, ek1), (df2, sk2), (df2, ek2)))
+    )
+    res = _overlap_intidxs(df1, df2, how=how, cols1=cols1, cols2=cols2, on=on, _sort_pairs=device_order,
+                           _coords=device_coords)
+    ev1, ev2 = res[0], res[1]
 
     stem = return_index if isinstance(return_index, str) else "index"
     icol1, icol2 = stem + suffixes[0], stem + suffixes[1]
@@ -222,12 +233,14 @@ def overlap(
 
     if return_overlap:
         ostem = return_overlap if isinstance(return_overlap, str) else "overlap"
-        parts["ov"] = pd.DataFrame(
-            {
-                ostem + "_" + sk1: np.maximum(df1[sk1].values[ev1], df2[sk2].values[ev2]),
-                ostem + "_" + ek1: np.minimum(df1[ek1].values[ev1], df2[ek2].values[ev2]),
-            }
-        )
+        if device_coords:
+            ov_lo, ov_hi = res[2]
+            dt = np.result_type(df1[sk1].dtype, df2[sk2].dtype), np.result_type(df1[ek1].dtype, df2[ek2].dtype)
+            ov_lo, ov_hi = ov_lo.astype(dt[0], copy=False), ov_hi.astype(dt[1], copy=False)
+        else:
+            ov_lo = np.maximum(df1[sk1].values[ev1], df2[sk2].values[ev2])
+            ov_hi = np.minimum(df1[ek1].values[ev1], df2[ek2].values[ev2])
+        parts["ov"] = pd.DataFrame({ostem + "_" + sk1: ov_lo, ostem + "_" + ek1: ov_hi})
     if return_input:
         parts["in1"] = _suffixed_rows(df1, ev1, suffixes[0])
         parts["in2"] = _suffixed_rows(df2, ev2, suffixes[1])
@@ -276,6 +289,7 @@ def _closest_intidxs(
     cols1=None,
     cols2=None,
     _group_order=None,
+    _coords=None,
 ):
     """Integer row positions of the k closest intervals, -1 where a query has
     none.  Mirrors ops._closest_intidxs (ops.py:919-1040): chromosome blocks in
@@ -308,20 +322,31 @@ def _closest_intidxs(
         return valid, ranks, _int64_coords(df, sk)[valid], _int64_coords(df, ek)[valid]
 
     rows1, g1, s1, e1 = coded(df1, codes1, keys1, sk1, ek1)
+    if _coords:
+        s1, e1 = _engine.to_device(s1), _engine.to_device(e1)
     along = None
     if direction_col is not None:
         along = (df1[direction_col].values != "-")[rows1]
     if self_closest:
-        rows2 = rows1
+        rows2, s2, e2 = rows1, s1, e1
         ev1, ev2, _ = _engine.closest_intidxs(
             g1, s1, e1, None, None, None, n_groups, k=k, ignore_overlaps=ignore_overlaps,
             ignore_upstream=ignore_upstream, ignore_downstream=ignore_downstream, along=along, self_closest=True,
         )
     else:
         rows2, g2, s2, e2 = coded(df2, codes2, keys2, sk2, ek2)
+        if _coords:
+            s2, e2 = _engine.to_device(s2), _engine.to_device(e2)
         ev1, ev2, _ = _engine.closest_intidxs(
             g1, s1, e1, g2, s2, e2, n_groups, k=k, ignore_overlaps=ignore_overlaps,
             ignore_upstream=ignore_upstream, ignore_downstream=ignore_downstream, along=along,
+        )
+    extra = None
+    if _coords:  # (overlap_start, overlap_end, distance) of every reported pair, gathered on the device
+        extra = tuple(
+            None if x is None else _to_host(x)
+            for x in _engine.pair_coords(ev1, ev2, s1, e1, s2, e2, want_overlap="overlap" in _coords,
+                                         want_distance="distance" in _coords)
         )
     ev1, ev2 = _to_host(ev1), _to_host(ev2)
     # kernel rows index the NA-free subsets; map back to frame positions
@@ -329,7 +354,7 @@ def _closest_intidxs(
         ev1 = rows1[ev1]
     if len(rows2) != len(df2):
         ev2 = np.where(ev2 >= 0, rows2[np.maximum(ev2, 0)], -1)
-    return ev1, ev2
+    return (ev1, ev2, extra) if _coords else (ev1, ev2)
 
 
 def closest(
@@ -362,14 +387,14 @@ def closest(
     checks.is_bedframe(df1, raise_errors=True, cols=[ck1, sk1, ek1])
     checks.is_bedframe(df2, raise_errors=True, cols=[ck2, sk2, ek2])
 
-    ev1, ev2 = _closest_intidxs(
+    want = tuple(t for t, on_ in (("overlap", return_overlap), ("distance", return_distance)) if on_)
+    res = _closest_intidxs(
         df1, df2, k=k, ignore_overlaps=ignore_overlaps, ignore_upstream=ignore_upstream,
         ignore_downstream=ignore_downstream, direction_col=direction_col, tie_breaking_col=tie_breaking_col,
-        cols1=cols1, cols2=cols2,
+        cols1=cols1, cols2=cols2, _coords=want or None,
     )
+    ev1, ev2 = res[0], res[1]
     lone = ev2 == -1
-    a1, b1 = df1[sk1].values[ev1], df1[ek1].values[ev1]
-    a2, b2 = df2[sk2].values[ev2], df2[ek2].values[ev2]
 
     pieces = []
     if return_index:
@@ -386,7 +411,7 @@ def closest(
         pieces.append(("in1", _suffixed_rows(df1, ev1, suffixes[0])))
         pieces.append(("in2", in2))
     if return_overlap:
-        lo, hi = np.maximum(a1, a2), np.minimum(b1, b2)
+        lo, hi = res[2][0], res[2][1]
         have = lo < hi
         ov = pd.DataFrame(
             {"have_overlap": have, "overlap_start": np.where(have, lo, None), "overlap_end": np.where(have, hi, None)}
@@ -394,8 +419,7 @@ def closest(
         ov[lone] = pd.NA
         pieces.append(("ov", ov))
     if return_distance:
-        gap = np.maximum(np.maximum(0, a1 - b2), np.maximum(0, a2 - b1))
-        dist = pd.DataFrame({"distance": gap}, dtype=pd.Int64Dtype())
+        dist = pd.DataFrame({"distance": res[2][2]}, dtype=pd.Int64Dtype())
         dist[lone] = pd.NA
         pieces.append(("d", dist))
     by_tag = dict(pieces)

@@ -99,6 +99,18 @@ size_t bf_sort_pairs_workspace_bytes(int64_t n_rows);
 int bf_sort_pairs(int64_t* events1, int64_t* events2, int64_t n_rows, int64_t max1, int64_t max2, void* ws,
                   size_t ws_bytes, void* stream);
 
+/* ---- pair coordinates: replaces the gathers of return_overlap=True -- np.maximum(df1[sk1].values[events1],
+ * df2[sk2].values[events2]) / np.minimum(...) in ops.overlap (ops.py:480-497) and ops.closest
+ * (ops.py:1187-1194) -- and closest's return_distance arithmetic (ops.py:1207-1221), on the pair list
+ * while it still is on the device.  For row i with a = events1[i], b = events2[i], both >= 0:
+ *   overlap_start = max(start1[a], start2[b]), overlap_end = min(end1[a], end2[b]),
+ *   distance = max(0, start1[a] - end2[b], start2[b] - end1[a]);
+ * rows with a missing partner (-1) get 0 (the caller masks them as the reference does).  Any output may be
+ * NULL. */
+int bf_pair_coords(const int64_t* events1, const int64_t* events2, int64_t n_rows, const int64_t* start1,
+                   const int64_t* end1, const int64_t* start2, const int64_t* end2, int64_t* overlap_start_out,
+                   int64_t* overlap_end_out, int64_t* distance_out, void* stream);
+
 /* ---- closest: replaces ops._closest_intidxs (ops.py:919-1040), i.e. the
  * per-group loop around arrops.closest_intervals (arrops.py:601-754) and
  * arrops._closest_intervals_nooverlap (arrops.py:506-598), plus the

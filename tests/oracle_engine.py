@@ -51,6 +51,23 @@ def coverage(grp1, start1, end1, grp2, start2, end2, n_groups, device=None):
     return oo.coverage_coded(grp1, _i64(start1), _i64(end1), grp2, _i64(start2), _i64(end2), n_groups)
 
 
+def to_device(x, dtype="int64", device=None):
+    return np.asarray(x, dtype=dtype)
+
+
+def pair_coords(ev1, ev2, start1, end1, start2, end2, want_overlap=True, want_distance=False, device=None):
+    a, b = _i64(ev1), _i64(ev2)
+    s1, e1, s2, e2 = _i64(start1), _i64(end1), _i64(start2), _i64(end2)
+    ok = (a >= 0) & (b >= 0)
+    if len(s1) == 0 or len(s2) == 0:
+        z = np.zeros(len(a), np.int64)
+        return (z, z.copy(), z.copy() if want_distance else None) if want_overlap else (None, None, z)
+    os_ = np.where(ok, np.maximum(s1[a], s2[b]), 0)
+    oe = np.where(ok, np.minimum(e1[a], e2[b]), 0)
+    dist = np.where(ok, np.maximum(0, np.maximum(s1[a] - e2[b], s2[b] - e1[a])), 0)
+    return (os_ if want_overlap else None, oe if want_overlap else None, dist if want_distance else None)
+
+
 def subtract(grp1, start1, end1, grp2, start2, end2, n_groups, want_sub_index=True, device=None):
     row, ps, pe, sub = oo.subtract_coded(grp1, _i64(start1), _i64(end1), grp2, _i64(start2), _i64(end2), n_groups)
     return row, ps, pe, (sub if want_sub_index else None)

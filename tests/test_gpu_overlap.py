@@ -127,3 +127,27 @@ def test_sort_pairs(n):
     kb = np.where(b < 0, 7000, b)
     order = np.lexsort([kb, ka])
     assert np.array_equal(ta.cpu().numpy(), a[order]) and np.array_equal(tb.cpu().numpy(), b[order])
+
+
+def test_pair_coords_match_numpy():
+    """bf_pair_coords = the gathers of return_overlap / return_distance (ops.py:484-492, 1207-1221)."""
+    from bioframe_b200 import engine
+
+    rng = np.random.default_rng(8)
+    n1, n2, n = 5000, 3000, 200_000
+    s1 = rng.integers(-50, 10**6, n1)
+    e1 = s1 + rng.integers(0, 500, n1)
+    s2 = rng.integers(-50, 10**6, n2)
+    e2 = s2 + rng.integers(0, 500, n2)
+    a = rng.integers(-1, n1, n)
+    b = rng.integers(-1, n2, n)
+    lo, hi, dist = engine.pair_coords(a, b, s1, e1, s2, e2, want_overlap=True, want_distance=True)
+    ok = (a >= 0) & (b >= 0)
+    assert np.array_equal(lo.cpu().numpy(), np.where(ok, np.maximum(s1[a], s2[b]), 0))
+    assert np.array_equal(hi.cpu().numpy(), np.where(ok, np.minimum(e1[a], e2[b]), 0))
+    want = np.maximum(np.maximum(0, s1[a] - e2[b]), np.maximum(0, s2[b] - e1[a]))
+    assert np.array_equal(dist.cpu().numpy(), np.where(ok, want, 0))
+    lo, hi, dist = engine.pair_coords(a[:0], b[:0], s1, e1, s2, e2, want_distance=True)
+    assert lo.numel() == 0 and dist.numel() == 0
+    only = engine.pair_coords(a, b, s1, e1, s2, e2, want_overlap=False, want_distance=True)
+    assert only[0] is None and only[1] is None and only[2].numel() == n
