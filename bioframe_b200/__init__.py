@@ -11,9 +11,12 @@ the arithmetic runs in hand-written sm_100a CUDA kernels behind a C ABI
 """
 __version__ = "0.1.0"
 
-from . import core  # noqa: F401
+from . import core, extras  # noqa: F401
 from .core.specs import update_default_colnames  # noqa: F401
-from .ops import closest, cluster, complement, count_overlaps, coverage, merge, overlap, setdiff, subtract  # noqa: F401
+from .extras import pair_by_distance  # noqa: F401
+from .ops import (  # noqa: F401
+    assign_view, closest, cluster, complement, count_overlaps, coverage, merge, overlap, setdiff, subtract, trim,
+)
 
-__all__ = ["overlap", "closest", "cluster", "merge", "complement", "coverage", "count_overlaps", "setdiff", "core",
-           "update_default_colnames"]
+__all__ = ["overlap", "closest", "cluster", "merge", "complement", "coverage", "count_overlaps", "setdiff", "subtract",
+           "assign_view", "trim", "pair_by_distance", "core", "extras", "update_default_colnames"]

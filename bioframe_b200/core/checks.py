@@ -6,7 +6,7 @@ import pandas as pd
 
 from .specs import _get_default_colnames, _verify_column_dtypes, _verify_columns
 
-__all__ = ["is_bedframe"]
+__all__ = ["is_bedframe", "is_cataloged"]
 
 
 def is_bedframe(df, raise_errors=False, cols=None):
@@ -38,4 +38,24 @@ def is_bedframe(df, raise_errors=False, cols=None):
         return fail(
             ValueError(f"Invalid bedframe: starts exceed ends for {sum(backwards)} intervals")
         )
+    return True
+
+
+def is_cataloged(df, view_df, raise_errors=False, df_view_col="view_region", view_name_col="name"):
+    """Every (non-null) region name in df[df_view_col] is a name of the view (checks.py:88-142)."""
+
+    def fail(message):
+        if raise_errors:
+            raise ValueError(message)
+        return False
+
+    if not _verify_columns(df, [df_view_col], return_as_bool=True):
+        return fail(f"Could not find `{df_view_col}` column in df")
+    if not _verify_columns(view_df, [view_name_col], return_as_bool=True):
+        return fail(f"Could not find `{view_name_col}` column in view_df")
+    known = set(view_df[view_name_col].values)
+    used = set(df[df_view_col].dropna().values)
+    if not used.issubset(known):
+        missing = set(df[df_view_col].values).difference(known)
+        return fail(f"The following regions in df[df_view_col] not in view_df[view_name_col]: \n{missing}")
     return True

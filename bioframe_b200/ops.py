@@ -25,7 +25,7 @@ from . import engine as _engine
 from .core import checks
 from .core.specs import _get_default_colnames, _verify_columns
 
-__all__ = ["overlap", "closest", "cluster", "merge", "complement", "coverage", "count_overlaps", "setdiff", "subtract"]
+__all__ = ["overlap", "closest", "cluster", "merge", "complement", "coverage", "count_overlaps", "setdiff", "subtract", "assign_view", "trim"]
 
 _INT64_MAX = np.iinfo(np.int64).max
 
@@ -771,3 +771,69 @@ def subtract(df1, df2, return_index=False, suffixes=("", "_"), cols1=None, cols2
         out["index" + suffixes[0]] = pd.array(np.asarray(ix)[row], dtype=pd.Int64Dtype())
         out["sub_index" + suffixes[1]] = pd.array(_to_host(sub) if len(row) else sub, dtype=pd.Int64Dtype())
     return out
+
+
+# --------------------------------------------------------------------------
+# assign_view / trim  (SURVEY.md 8f "next" #1): frame glue over the device overlap
+# --------------------------------------------------------------------------
+def assign_view(df, view_df, drop_unassigned=False, df_view_col="view_region", view_name_col="name", cols=None,
+                cols_view=None):
+    """Name of the view region every interval overlaps most (ops.py:1807-1901).  The pair list and the
+    clipped coordinates come from the device (left overlap + bf_pair_coords); picking the longest overlap
+    per row is the reference's sort / drop_duplicates on the assembled frame.  Resets the index."""
+    from . import _viewframe
+
+    _ck, sk, ek = _get_default_colnames() if cols is None else cols
+    df = df.copy()
+    df.reset_index(inplace=True, drop=True)
+    checks.is_bedframe(df, raise_errors=True, cols=cols)
+    view_df = _viewframe.make_viewframe(view_df, view_name_col=view_name_col, cols=cols_view)
+    hits = overlap(df, view_df, how="left", suffixes=("", "_view"), return_overlap=True, keep_order=False,
+                   return_index=True, cols1=cols, cols2=cols_view)
+    hits["overlap_length"] = hits["overlap_" + ek] - hits["overlap_" + sk]
+    best = hits.sort_values("overlap_length", ascending=False).drop_duplicates("index", keep="first").sort_values("index")
+    best.rename(columns={view_name_col + "_view": df_view_col}, inplace=True)
+    if drop_unassigned:
+        best = best.iloc[pd.isna(best).any(axis=1).values == 0, :]
+    best.reset_index(inplace=True, drop=True)
+    return best[[*df.columns, df_view_col]]
+
+
+def trim(df, view_df=None, df_view_col=None, view_name_col="name", return_view_columns=False, cols=None,
+         cols_view=None):
+    """Clip every interval to its view region; intervals outside every region become null (ops.py:1441-1557).
+    Without a view the intervals are only cut at zero.  Regions come from `df_view_col` when given, else
+    from `assign_view` (device overlap)."""
+    from . import _viewframe
+
+    ck, sk, ek = _get_default_colnames() if cols is None else cols
+    _verify_columns(df, [ck, sk, ek])
+    keep_cols = list(df.columns)
+    out = df.copy()
+    inferred = view_df is None
+    if inferred:
+        df_view_col = ck
+        view_df = {c: _INT64_MAX for c in set(df[ck].copy().dropna().values)}
+    ckv, skv, ekv = _get_default_colnames() if cols_view is None else cols_view
+    view_df = _viewframe.make_viewframe(view_df, view_name_col=view_name_col, cols=[ckv, skv, ekv]).rename(
+        columns=dict(zip([ckv, skv, ekv], [ck, sk, ek]))
+    )
+    if inferred:
+        view_name_col = ck
+    elif df_view_col is None:
+        if _verify_columns(out, ["view_region"], return_as_bool=True):
+            raise ValueError("column view_region already exists in input df")
+        df_view_col = "view_region"
+        out = assign_view(out, view_df, drop_unassigned=False, df_view_col=df_view_col, view_name_col=view_name_col,
+                          cols=cols, cols_view=cols)
+    else:
+        _verify_columns(out, [df_view_col])
+        checks.is_cataloged(out, view_df, raise_errors=True, df_view_col=df_view_col, view_name_col=view_name_col)
+    out = out.merge(view_df, how="left", left_on=df_view_col, right_on=view_name_col, suffixes=("", "_view"))
+    outside = pd.isnull(out[df_view_col].values)
+    if outside.any():
+        out.loc[outside, [ck, sk, ek]] = pd.NA
+    lower, upper = out[sk + "_view"].values, out[ek + "_view"].values
+    out[sk] = out[sk].clip(lower=lower, upper=upper)
+    out[ek] = out[ek].clip(lower=lower, upper=upper)
+    return out if return_view_columns else out[keep_cols]

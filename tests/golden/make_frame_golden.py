@@ -117,6 +117,23 @@ def main():
     add("subtract_edges_cols", "subtract", df1=edge1.rename(columns={"chrom": "c", "start": "s", "end": "e"})[["name", "c", "s", "e"]],
         df2=edge2, cols1=("c", "s", "e"))
     add("subtract_no_targets", "subtract", df1=edge1, df2=edge2.iloc[:0])
+    # assign_view / trim / pair_by_distance: frame glue over the device overlap
+    view3 = pd.DataFrame({"chrom": ["chr1", "chr1", "chr2", "chrX"], "start": [0, 160, 20, 0], "end": [150, 333, 410, 90],
+                          "name": ["left", "right", "two", "x"]})
+    for tag, opts in (("plain", {}), ("cat", dict(categorical=True))):
+        df1, _ = frames(rng2, **opts)
+        add(f"assign_view_{tag}", "assign_view", df=df1, view_df=view3)
+        add(f"assign_view_{tag}_drop", "assign_view", df=df1, view_df=view3, drop_unassigned=True, df_view_col="reg")
+        add(f"trim_{tag}_view", "trim", df=df1, view_df=view3)
+        add(f"trim_{tag}_noview", "trim", df=df1.assign(start=df1["start"] - 30))
+        named = df1.assign(region=np.where(df1["chrom"].astype(str) == "chr2", "two", None))
+        add(f"trim_{tag}_col", "trim", df=named, view_df=view3, df_view_col="region", return_view_columns=True)
+        one = df1[df1["chrom"].astype(str) == "chr1"].copy()
+        add(f"pair_by_distance_{tag}", "pair_by_distance", df=one, min_sep=5, max_sep=90)
+        add(f"pair_by_distance_{tag}_mid", "pair_by_distance", df=df1, min_sep=0, max_sep=60, min_intervening=1,
+            max_intervening=6, return_index=True, keep_order=True)
+        add(f"pair_by_distance_{tag}_ends", "pair_by_distance", df=df1, min_sep=10, max_sep=200, relative_to="endpoints",
+            suffixes=("_a", "_b"))
     with open(os.path.join(HERE, "frames.pkl"), "wb") as f:
         pickle.dump(cases, f, protocol=4)
     print(len(cases), "cases ->", os.path.join(HERE, "frames.pkl"))

@@ -1,7 +1,8 @@
-"""Frame-level parity: `bioframe_b200.{overlap,closest,cluster,merge,coverage,complement}` against
+"""Frame-level parity: `bioframe_b200.{overlap,closest,cluster,merge,coverage,complement,count_overlaps,setdiff,
+subtract,assign_view,trim,pair_by_distance}` against
 outputs of the reference itself (tests/golden/frames.pkl, made by tests/golden/make_frame_golden.py).
 
-Two legs over the same 64 cases:
+Two legs over the same cases:
   * not gpu : the pandas glue on top of the oracle-backed test double (tests/oracle_engine.py) -- checks
               group encoding, NA handling, dtypes and frame assembly in the build container;
   * gpu     : the same calls on the real CUDA engine (B200 box).
@@ -25,6 +26,8 @@ def _order_free(name, case):
     kw = case["kwargs"]
     if case["fn"] == "closest":
         return True
+    if case["fn"] == "pair_by_distance":
+        return not kw.get("keep_order", False)
     if case["fn"] == "overlap":
         return kw.get("how", "left") != "left" or kw.get("keep_order") is False
     return False
