@@ -45,10 +45,16 @@ def _install():
         our_ops._engine = oracle_engine
         our_arrops._engine = oracle_engine
     for name in ("overlap", "closest", "cluster", "merge", "complement", "coverage", "count_overlaps", "setdiff",
-                 "_overlap_intidxs", "_closest_intidxs"):
+                 "subtract", "assign_view", "trim", "_overlap_intidxs", "_closest_intidxs"):
         setattr(ref_ops, name, getattr(our_ops, name))
         if hasattr(bioframe, name):
             setattr(bioframe, name, getattr(our_ops, name))
+    import bioframe.extras as ref_extras
+
+    import bioframe_b200.extras as our_extras
+
+    ref_extras.pair_by_distance = our_extras.pair_by_distance
+    bioframe.pair_by_distance = our_extras.pair_by_distance
     print(f"[refsuite] reference ops patched with bioframe_b200 ({'CUDA engine' if use_gpu else 'oracle test double'})")
 
 
