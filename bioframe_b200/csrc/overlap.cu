@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
                       i64* __restrict__ ev1, i64* __restrict__ ev2) {
   __shared__ i32 s_rel[EM_TILE + 2];  // scan[first_item + i] - t0, clamped to 32 bits
   __shared__ EmitItem s_item[EM_TILE + 2];
-  __shared__ __align__(16) u32 s_owner[EM_TILE + EM_TILE / 8];  // padded: 8 consecutive slots per thread without bank conflicts
+  __shared__ __align__(16) u16 s_owner[EM_TILE];  // owner (index into s_item) of every output slot
   __shared__ u32 s_wmax[EM_THREADS / 32];
   const u32 tid = threadIdx.x;
   const i64 W = n_owner + total;
@@ -532,6 +532,7 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
   // every thread reads the block's partition entries itself (broadcast loads, no barrier)
   const i64 p0 = part[blockIdx.x], p1 = part[blockIdx.x + 1];
   const i32 c_lo = pgrp[blockIdx.x], c_hi = pgrp[blockIdx.x + 1];  // c_hi: upper bound of the last output's group
+  const i64 delta_lo = delta[c_lo];
   const i64 t0 = D0 - p0, t1 = D1 - p1;
   const i32 nout = (i32)(t1 - t0);
   // the block that will take over this SM slot about one wave from now: its partition entries are read
@@ -558,11 +559,8 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
       s_item[i] = it;
     }
   }
-#define EM_PAD(x) ((x) + ((x) >> 3))
-  {  // clear the owner slots (and their padding) with 16-byte stores
-    uint4* z = reinterpret_cast<uint4*>(s_owner);
-    for (i32 x = tid; x < (EM_TILE + EM_TILE / 8) / 4; x += EM_THREADS) z[x] = make_uint4(0u, 0u, 0u, 0u);
-  }
+#define EM_PAD(x) (x)
+  reinterpret_cast<uint4*>(s_owner)[tid] = make_uint4(0u, 0u, 0u, 0u);  // 8 slots per thread
   __syncthreads();
   if (ahead) {
     const i64 f = (q0 > 0 ? q0 - 1 : 0) & ~(i64)31;  // 128-byte lines of 32 rows
@@ -575,16 +573,18 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
   }
   for (i32 i = tid; i < nitems; i += EM_THREADS) {
     const i32 r = s_rel[i];
-    if (s_rel[i + 1] > r && r >= 0 && r < nout) s_owner[EM_PAD(r)] = (u32)i;
+    if (s_rel[i + 1] > r && r >= 0 && r < nout) s_owner[r] = (u16)i;
   }
   __syncthreads();
-  {  // inclusive running max over the 2048 slots, 8 consecutive slots per thread
+  {  // inclusive running max over the 2048 slots, 8 consecutive slots (one 16-byte word) per thread
+    const uint4 q = reinterpret_cast<const uint4*>(s_owner)[tid];
+    const u32 word[4] = {q.x, q.y, q.z, q.w};
     u32 v[EM_IPT];
     u32 run = 0;
 #pragma unroll
     for (int j = 0; j < EM_IPT; ++j) {
-      v[j] = s_owner[tid * (EM_IPT + 1) + j];
-      run = v[j] > run ? v[j] : run;
+      const u32 x = (word[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+      run = x > run ? x : run;
       v[j] = run;
     }
     u32 inc = run;
@@ -601,8 +601,13 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
 #pragma unroll
     for (int i = 0; i < EM_THREADS / 32; ++i)
       if ((u32)i < w) before = s_wmax[i] > before ? s_wmax[i] : before;
+    u32 out[4];
 #pragma unroll
-    for (int j = 0; j < EM_IPT; ++j) s_owner[tid * (EM_IPT + 1) + j] = v[j] > before ? v[j] : before;
+    for (int j = 0; j < EM_IPT; j += 2) {
+      const u32 a = v[j] > before ? v[j] : before, b = v[j + 1] > before ? v[j + 1] : before;
+      out[j >> 1] = a | (b << 16);
+    }
+    reinterpret_cast<uint4*>(s_owner)[tid] = make_uint4(out[0], out[1], out[2], out[3]);
   }
   __syncthreads();
   auto group_of = [&](i64 t, i64 a, i64 b) {  // last c with cum[c] <= t
@@ -614,7 +619,7 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
     // Two adjacent output rows per thread and step, written with 16-byte stores.  The pairs are aligned
     // to even output rows (16-byte aligned addresses): when the block's first row is odd, slot 0 is a
     // single that thread 0 writes on its own.
-    const i64 row0 = t0 + delta[c_lo];
+    const i64 row0 = t0 + delta_lo;
     i64* const out1 = ev1 + row0;
     i64* const out2 = ev2 + row0;
     const i32 par = (i32)(row0 & 1);
