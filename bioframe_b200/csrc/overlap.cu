@@ -489,7 +489,7 @@ __global__ void offset_table_kernel(OverlapWS w, i64 n1, i64 n2, i32 nb, i32 how
 constexpr int EM_THREADS = 256;
 constexpr int EM_IPT = 8;
 constexpr int EM_TILE = EM_THREADS * EM_IPT;
-constexpr int EM_AHEAD = 148 * 6;  // blocks resident at a time (6 per SM)
+constexpr int EM_AHEAD = 148 * 8;  // blocks resident at a time (8 per SM)
 
 // part[b] = owner rows consumed before diagonal b * EM_TILE = #{p : p + scan[p] < D};
 // pgrp[b] = group of the first output of block b.  One thread per block
@@ -515,13 +515,12 @@ struct EmitItem {  // one owner row staged in shared memory
 };
 
 template <bool B_SIDE>
-__global__ void __launch_bounds__(EM_THREADS, 6)
+__global__ void __launch_bounds__(EM_THREADS, 8)
     emit_pairs_kernel(const ScanView scan, const u32* __restrict__ lo, i64 n_owner,
                       const u32* __restrict__ owner_id, const u32* __restrict__ other_id, i64 total,
                       i64 block0, const i64* __restrict__ part, const i32* __restrict__ pgrp,
                       const i64* __restrict__ cum, const i64* __restrict__ delta, i32 nb, i64 off1, i64 off2,
                       i64* __restrict__ ev1, i64* __restrict__ ev2) {
-  __shared__ i32 s_rel[EM_TILE + 2];  // scan[first_item + i] - t0, clamped to 32 bits
   __shared__ EmitItem s_item[EM_TILE + 2];
   __shared__ __align__(16) u16 s_owner[EM_TILE];  // owner (index into s_item) of every output slot
   __shared__ u32 s_wmax[EM_THREADS / 32];
@@ -546,19 +545,26 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
   if (nout <= 0) return;
   const i64 first = p0 > 0 ? p0 - 1 : 0;  // owner of the first output may have started earlier
   const i32 nitems = (i32)(p1 - first);
-  for (i32 i = tid; i <= nitems; i += EM_THREADS) {
-    // only offsets in [0, nout] are ever used exactly; the first owner may have started up to
-    // 2^31 - 1 outputs earlier (a row has < 2^31 partners), later owners may start far ahead
-    const i64 rel64 = scan.at(first + i) - t0;
-    const i32 rel = rel64 > 0x7fffffffLL ? 0x7fffffff : (i32)rel64;
-    s_rel[i] = rel;
-    if (i < nitems) {
-      EmitItem it;
-      it.src = lo[first + i] - (u32)rel;
-      it.id = owner_id[first + i];
-      s_item[i] = it;
-    }
-  }
+  // scan[row] - t0 clamped to 32 bits: only offsets in [0, nout] are ever used exactly; the first owner
+  // may have started up to 2^31 - 1 outputs earlier (a row has < 2^31 partners), later owners may start
+  // far ahead
+  auto rel_at = [&](i64 p) -> i32 {
+    const i64 rel64 = scan.at(p) - t0;
+    return rel64 > 0x7fffffffLL ? 0x7fffffff : (i32)rel64;
+  };
+  // An owner row marks the slot of its first output; its successor's offset (same cache line, read by
+  // the thread itself) tells whether it has any.  The first round of loads is in flight across the barrier
+  // that separates the clearing of the slots from the marks.
+  i32 i = (i32)tid;
+  i32 r = 0, r_next = 0;
+  EmitItem it = {0u, 0u};
+  auto load_row = [&]() {
+    r = rel_at(first + i);
+    r_next = rel_at(first + i + 1);
+    it.src = lo[first + i] - (u32)r;
+    it.id = owner_id[first + i];
+  };
+  if (i < nitems) load_row();
 #define EM_PAD(x) (x)
   reinterpret_cast<uint4*>(s_owner)[tid] = make_uint4(0u, 0u, 0u, 0u);  // 8 slots per thread
   __syncthreads();
@@ -571,9 +577,11 @@ __global__ void __launch_bounds__(EM_THREADS, 6)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(owner_id + row));
     }
   }
-  for (i32 i = tid; i < nitems; i += EM_THREADS) {
-    const i32 r = s_rel[i];
-    if (s_rel[i + 1] > r && r >= 0 && r < nout) s_owner[r] = (u16)i;
+  while (i < nitems) {
+    s_item[i] = it;
+    if (r_next > r && r >= 0 && r < nout) s_owner[r] = (u16)i;
+    i += EM_THREADS;
+    if (i < nitems) load_row();
   }
   __syncthreads();
   {  // inclusive running max over the 2048 slots, 8 consecutive slots (one 16-byte word) per thread
