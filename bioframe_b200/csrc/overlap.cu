@@ -22,7 +22,7 @@
 
 namespace bf {
 
-constexpr i64 EMIT_CHUNK_BLOCKS = 1 << 18;  // emit blocks per partition chunk (fixed-size scratch)
+constexpr i64 EMIT_CHUNK_BLOCKS = 1 << 20;  // emit blocks per partition chunk (fixed-size scratch)
 constexpr i64 SEARCH_MIN_ROWS = 256;        // == SR_MIN_ROWS (smallest block of rows of the search kernels)
 
 // ---------------------------------------------------------------- workspace
