@@ -143,33 +143,34 @@ __global__ void __launch_bounds__(SC_THREADS)
                           u32* __restrict__ loc_out, u64* __restrict__ tile_tot, i64* __restrict__ overflow) {
   __shared__ u64 s_tmp[8];
   const i64 base = (i64)blockIdx.x * SC_TILE + (i64)threadIdx.x * SC_IPT;
-  u32 cnt[SC_IPT], jl[SC_IPT];
   u64 mine = 0;
-#pragma unroll
+  // one row at a time (the probe code is not replicated SC_IPT times: registers, and with them occupancy,
+  // decide the speed of these random probes); counts go straight to memory and are read back below
+#pragma unroll 1
   for (int j = 0; j < SC_IPT; ++j) {
     const i64 r = base + j;
-    cnt[j] = 0;
-    jl[j] = 0;
-    if (r < n1) {
-      const i32 g = grp1 ? grp1[r] : 0;
-      if (g >= 0 && g < v.nb) {
-        const GapRange q = subtract_range(v, (u32)g, s1[r], e1[r]);
-        i64 c = q.jhi - q.jlo;
-        if (c > 0) {
-          // only the outermost gaps of a group can be empty: before a merged interval starting at 0,
-          // after one reaching INT64_MAX
-          if (q.C > 0 && q.jlo == 0 && sub_raw(v.rec[q.c0].x, q.g0, v.L) <= 0) --c;
-          if (q.C > 0 && q.jhi - 1 == q.C && sub_raw(v.rec[q.c0 + q.C - 1].y, q.g0, v.L) == I64_MAX) --c;
-          if (c >> 31) {
-            *overflow = 1;
-            c = 0;
-          }
-          cnt[j] = (u32)c;
-          jl[j] = (u32)q.jlo;
+    if (r >= n1) break;
+    u32 cnt = 0, jl = 0;
+    const i32 g = grp1 ? grp1[r] : 0;
+    if (g >= 0 && g < v.nb) {
+      const GapRange q = subtract_range(v, (u32)g, s1[r], e1[r]);
+      i64 c = q.jhi - q.jlo;
+      if (c > 0) {
+        // only the outermost gaps of a group can be empty: before a merged interval starting at 0,
+        // after one reaching INT64_MAX
+        if (q.C > 0 && q.jlo == 0 && sub_raw(v.rec[q.c0].x, q.g0, v.L) <= 0) --c;
+        if (q.C > 0 && q.jhi - 1 == q.C && sub_raw(v.rec[q.c0 + q.C - 1].y, q.g0, v.L) == I64_MAX) --c;
+        if (c >> 31) {
+          *overflow = 1;
+          c = 0;
         }
+        cnt = (u32)c;
+        jl = (u32)q.jlo;
       }
     }
-    mine += cnt[j];
+    jlo_out[r] = jl;
+    cnt_out[r] = cnt;
+    mine += cnt;
   }
   u64 tot;
   u64 run = block_excl_sum_u64(mine, s_tmp, &tot);
@@ -181,11 +182,9 @@ __global__ void __launch_bounds__(SC_THREADS)
   for (int j = 0; j < SC_IPT; ++j) {
     const i64 r = base + j;
     if (r < n1) {
-      jlo_out[r] = jl[j];
-      cnt_out[r] = cnt[j];
       loc_out[r] = (u32)run;
+      run += cnt_out[r];  // written by this thread above
     }
-    run += cnt[j];
   }
 }
 
