@@ -80,6 +80,16 @@ def run(budget=120.0, seed=0, max_rounds=None, sizes1=(0, 1, 7, 300, 2500, 9000,
             same((res["ids"], res["cstart"], res["cend"], res["ccount"]), (ids, cs, ce, cn), f"cluster {md}", cfg)
             cov = engine.coverage(g1, s1, e1, g2, s2, e2, nb)
             same((cov,), (oo.coverage_coded(g1, s1, e1, g2, s2, e2, nb),), "coverage", cfg)
+            got = engine.subtract(g1, s1, e1, g2, s2, e2, nb)
+            same(got, oo.subtract_coded(g1, s1, e1, g2, s2, e2, nb), "subtract", cfg)
+        if n1 and n2 and len(ev1):
+            lo, hi, dist = engine.pair_coords(ev1, ev2, s1, e1, s2, e2, want_distance=True)
+            a, b = ev1.cpu().numpy(), ev2.cpu().numpy()
+            ok = (a >= 0) & (b >= 0)
+            with np.errstate(over="ignore"):
+                want = (np.where(ok, np.maximum(s1[a], s2[b]), 0), np.where(ok, np.minimum(e1[a], e2[b]), 0),
+                        np.where(ok, np.maximum(0, np.maximum(s1[a] - e2[b], s2[b] - e1[a])), 0))
+            same((lo, hi, dist), want, "pair_coords", cfg)
     return it
 
 
