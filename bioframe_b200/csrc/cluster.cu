@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(SC_THREADS)
 }
 
 template <int PHASE>
-__global__ void __launch_bounds__(SC_THREADS)
+__global__ void __launch_bounds__(SC_THREADS, 6)
     cluster_pass_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, KeyLayout L, u64 min_dist,
                         int has_min_dist, const u64* __restrict__ spine_max, u64* __restrict__ spine_cnt,
                         u32* __restrict__ cid_sorted, ClusterTable tab, const i64* __restrict__ e_raw,
