@@ -33,6 +33,60 @@ def _as(t, dtype, device):
     return t.to(device=device, dtype=dtype, non_blocking=True).contiguous()
 
 
+class _DownloadStage:
+    """Device + pinned staging of `download_rows`, one per device, kept across calls."""
+
+    CHUNK_ROWS = 1 << 23  # 32 MB of int32 per chunk (profiles/download_bench.py: best with 8 threads)
+    _cache = {}
+
+    @classmethod
+    def get(cls, device):
+        key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+        if key not in cls._cache:
+            nbytes = _lib.lib().bf_download_stage_bytes(cls.CHUNK_ROWS)
+            dev = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            pinned = torch.empty(8 * cls.CHUNK_ROWS, dtype=torch.uint8).pin_memory()
+            cls._cache[key] = (dev, pinned)
+        return cls._cache[key]
+
+
+def host_threads():
+    """Host threads a download may use: the cores this process may run on, minus a little headroom."""
+    import os
+
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(8, n - 2))  # the widening is bound by host memory bandwidth well before 8 threads
+
+
+def download_rows(t, out=None, n_threads=None):
+    """int64 CUDA tensor of row numbers (values in [-1, 2^31 - 1)) -> int64 numpy array on the host, crossing PCIe
+    as 4 bytes per value (bf_download_rows).  `out`: optional preallocated contiguous int64 numpy array."""
+    import numpy as np
+
+    _require_cuda()
+    if t.dtype != torch.int64 or not t.is_cuda or not t.is_contiguous():
+        raise ValueError("download_rows: contiguous int64 CUDA tensor expected")
+    n = int(t.numel())
+    if out is None:
+        out = np.empty(n, dtype=np.int64)
+    if out.dtype != np.int64 or not out.flags.c_contiguous or out.size < n:
+        raise ValueError("download_rows: out must be a contiguous int64 array of at least t.numel() values")
+    if n == 0:
+        return out[:0]
+    device = t.device
+    with torch.cuda.device(device):
+        dev, pinned = _DownloadStage.get(device)
+        rc = _lib.lib().bf_download_rows(
+            _ptr(t), n, C.c_void_p(out.ctypes.data), _ptr(dev), dev.numel(), C.c_void_p(pinned.data_ptr()),
+            pinned.numel(), int(n_threads or host_threads()), _stream_ptr(device),
+        )
+        _lib.check(rc, "bf_download_rows")
+    return out[:n]
+
+
 def to_device(x, dtype="int64", device=None):
     """numpy / tensor -> CUDA tensor (the frame glue moves a column once and hands it to several calls)."""
     _require_cuda()

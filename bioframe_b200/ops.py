@@ -76,6 +76,14 @@ def _to_host(t):
     return t.cpu().numpy() if hasattr(t, "cpu") else np.asarray(t)
 
 
+def _rows_to_host(t):
+    """Row-number results (int64, -1 = none): large ones cross PCIe as 4 bytes per value and are widened on
+    the host (bf_download_rows); small ones take the plain copy."""
+    if hasattr(t, "is_cuda") and t.is_cuda and t.numel() >= (1 << 22):
+        return _engine.download_rows(t)
+    return _to_host(t)
+
+
 # --------------------------------------------------------------------------
 # overlap
 # --------------------------------------------------------------------------
@@ -134,8 +142,8 @@ def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _gro
         ev1, ev2 = _engine.sort_pairs(ev1, ev2, max(len(df1) - 1, 0), max(len(df2) - 1, 0))
     if _coords:  # clipped coordinates of every pair (return_overlap, ops.py:480-497) while the list is on the device
         lo, hi, _ = _engine.pair_coords(ev1, ev2, s1, e1, s2, e2)
-        return _to_host(ev1), _to_host(ev2), (_to_host(lo), _to_host(hi))
-    return _to_host(ev1), _to_host(ev2)
+        return _rows_to_host(ev1), _rows_to_host(ev2), (_to_host(lo), _to_host(hi))
+    return _rows_to_host(ev1), _rows_to_host(ev2)
 
 
 _NULLABLE_INT = {
@@ -348,7 +356,7 @@ def _closest_intidxs(
             for x in _engine.pair_coords(ev1, ev2, s1, e1, s2, e2, want_overlap="overlap" in _coords,
                                          want_distance="distance" in _coords)
         )
-    ev1, ev2 = _to_host(ev1), _to_host(ev2)
+    ev1, ev2 = _rows_to_host(ev1), _rows_to_host(ev2)
     # kernel rows index the NA-free subsets; map back to frame positions
     if len(rows1) != len(df1):
         ev1 = rows1[ev1]

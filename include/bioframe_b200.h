@@ -207,6 +207,19 @@ int bf_subtract_count(const int32_t* grp1, const int64_t* start1, const int64_t*
 int bf_subtract_emit(const bf_plan* plan, void* ws, int64_t* row_out, int64_t* start_out, int64_t* end_out,
                      int64_t* sub_index_out, void* stream);
 
+/* ---- host download of row numbers: the last step of ops._overlap_intidxs / ops._closest_intidxs as the
+ * reference's callers see it -- int64 numpy arrays of row positions on the HOST (ops.py:338, 1040).  A call
+ * through host buffers is bound by PCIe, and row numbers of sets below 2^31 rows carry 4 bytes: they cross the
+ * bus as int32 and are widened into `host_dst` by `n_threads` host threads (streaming stores) while the next
+ * chunk is in flight.  dev_src: device int64[n] with every value in [-1, 2^31 - 1), 16-byte aligned (else
+ * BF_ERR_RANGE / BF_ERR_ARG); host_dst: ordinary (pageable) host int64[n]; dev_stage: device scratch of
+ * bf_download_stage_bytes(chunk_rows) bytes; pinned_stage: page-locked host scratch of at least
+ * 8 * chunk_rows bytes.  Synchronises `stream`; returns when host_dst is complete. */
+size_t bf_download_stage_bytes(int64_t chunk_rows);
+int bf_download_rows(const int64_t* dev_src, int64_t n, int64_t* host_dst, void* dev_stage,
+                     size_t dev_stage_bytes, void* pinned_stage, size_t pinned_bytes, int32_t n_threads,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,14 @@ def coverage(grp1, start1, end1, grp2, start2, end2, n_groups, device=None):
     return oo.coverage_coded(grp1, _i64(start1), _i64(end1), grp2, _i64(start2), _i64(end2), n_groups)
 
 
+def download_rows(t, out=None, n_threads=None):
+    t = np.asarray(t, dtype=np.int64)
+    if out is None:
+        return t.copy()
+    out[: len(t)] = t
+    return out[: len(t)]
+
+
 def to_device(x, dtype="int64", device=None):
     return np.asarray(x, dtype=dtype)
 

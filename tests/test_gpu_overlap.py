@@ -151,3 +151,32 @@ def test_pair_coords_match_numpy():
     assert lo.numel() == 0 and dist.numel() == 0
     only = engine.pair_coords(a, b, s1, e1, s2, e2, want_overlap=False, want_distance=True)
     assert only[0] is None and only[1] is None and only[2].numel() == n
+
+
+@pytest.mark.parametrize("n", [0, 1, 63, 64, 5000, (1 << 24) + 777, 40_000_001])
+def test_download_rows_matches_plain_copy(n):
+    """bf_download_rows: int32 over PCIe + host widening gives the same int64 host array as a plain copy."""
+    from bioframe_b200 import engine
+
+    g = torch.Generator(device="cuda").manual_seed(n)
+    t = torch.randint(-1, 2**31 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+    if n > 2:
+        t[0], t[1], t[-1] = -1, 2**31 - 2, -1
+    got = engine.download_rows(t)
+    assert got.dtype == np.int64 and np.array_equal(got, t.cpu().numpy())
+    out = np.full(n + 5, 7, dtype=np.int64)
+    view = engine.download_rows(t, out=out, n_threads=3)
+    assert np.array_equal(view, t.cpu().numpy()) and (out[n:] == 7).all()
+
+
+def test_download_rows_rejects_values_outside_int32():
+    from bioframe_b200 import _lib, engine
+
+    t = torch.arange(100_000, dtype=torch.int64, device="cuda")
+    t[777] = 2**31 - 1
+    with pytest.raises(OverflowError):
+        engine.download_rows(t)
+    t[777] = -2
+    with pytest.raises(OverflowError):
+        engine.download_rows(t)
+    assert _lib is not None
