@@ -405,16 +405,18 @@ def main():
         # Host memory: two pinned int64 result columns are 2 x 7 GB per rank (the pinned allocator rounds up to
         # 8 GB each).  Up to 4 ranks they are kept whole; with more ranks on one box (196 GB of host RAM here)
         # the result is read back through a ring of two 2-GiB pinned buffers instead -- same bytes over PCIe.
-        # With enough host cores per rank the result crosses PCIe as 4 bytes per row number and is widened into
+        # With one or two ranks on the box the result crosses PCIe as 4 bytes per row number and is widened into
         # ordinary int64 host arrays by host threads while the next chunk is in flight (bf_download_rows): half
-        # the bus traffic for the same int64 result.  Otherwise (many ranks sharing few cores) it is copied as
-        # int64 into pinned host arrays.
+        # the bus traffic for the same int64 result (315 -> 198 ms at one GPU).  The widening doubles the host
+        # memory traffic, though, and with more ranks sharing one host the memory controllers, not PCIe, are
+        # the limit (440 vs 467 ms at two GPUs: already a tie): from four ranks on the int64 columns are
+        # copied as they are into pinned host arrays.
         try:
             cores = len(os.sched_getaffinity(0))
         except AttributeError:
             cores = os.cpu_count() or 1
         threads = max(1, min(8, cores // world - 1))
-        narrow = threads >= 4
+        narrow = threads >= 4 and world <= 2
         ring = (not narrow) and world > 4
         if narrow:
             res1 = np.zeros(n_rows, dtype=np.int64)  # pageable, touched once here
