@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--n1", type=int, default=100_000_000)
     ap.add_argument("--n2", type=int, default=10_000_000)
     ap.add_argument("--how", default="left", choices=["inner", "left", "right", "outer"])
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="overlap", choices=["overlap", "closest", "cluster", "coverage", "count", "subtract"],
