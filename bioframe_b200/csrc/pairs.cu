@@ -126,6 +126,43 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Column gather: out[i] = src[idx[i]] for a fixed-width column (4- or 8-byte values), 0 where idx[i] is -1.
+// The df.iloc[events] of the frame assembly (ops.py:499-508, 1224-1234) for numeric columns, done where the
+// pair list lives; `valid` (optional) is the Arrow-style validity byte per row.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    gather_rows_kernel(const T* __restrict__ src, const i64* __restrict__ idx, i64 n, T* __restrict__ out,
+                       u8* __restrict__ valid) {
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const i64 r = idx[i];
+    out[i] = r >= 0 ? src[r] : T(0);
+    if (valid) valid[i] = r >= 0;
+  }
+}
+
+static int gather_rows_impl(const void* src, i32 itemsize, const i64* idx, i64 n, void* out, u8* valid, cudaStream_t st) {
+  if (n < 0 || (itemsize != 4 && itemsize != 8)) {
+    set_error("bf_gather_rows: bad argument (n_rows=%lld itemsize=%d; 4- and 8-byte columns are supported)", (long long)n,
+              itemsize);
+    return BF_ERR_ARG;
+  }
+  if (n == 0) return BF_OK;
+  if (!src || !idx || !out) {
+    set_error("bf_gather_rows: null pointer");
+    return BF_ERR_ARG;
+  }
+  const unsigned grid = stream_grid((u64)n, 1024);
+  if (itemsize == 8) {
+    BF_LAUNCH(PC_GATHER, 24 * n, st,
+              gather_rows_kernel<u64><<<grid, 256, 0, st>>>((const u64*)src, idx, n, (u64*)out, valid));
+  } else {
+    BF_LAUNCH(PC_GATHER, 16 * n, st,
+              gather_rows_kernel<u32><<<grid, 256, 0, st>>>((const u32*)src, idx, n, (u32*)out, valid));
+  }
+  return BF_OK;
+}
+
 static int pair_coords_impl(const i64* ev1, const i64* ev2, i64 n, const i64* s1, const i64* e1, const i64* s2,
                             const i64* e2, i64* ostart, i64* oend, i64* dist, cudaStream_t st) {
   if (n < 0) {
@@ -146,6 +183,10 @@ static int pair_coords_impl(const i64* ev1, const i64* ev2, i64 n, const i64* s1
 }  // namespace bf
 
 extern "C" {
+int bf_gather_rows(const void* src, int32_t itemsize, const int64_t* row_idx, int64_t n_rows, void* out,
+                   uint8_t* valid_out, void* stream) {
+  return bf::gather_rows_impl(src, itemsize, (const i64*)row_idx, n_rows, out, (u8*)valid_out, (cudaStream_t)stream);
+}
 int bf_pair_coords(const int64_t* events1, const int64_t* events2, int64_t n_rows, const int64_t* start1,
                    const int64_t* end1, const int64_t* start2, const int64_t* end2, int64_t* overlap_start_out,
                    int64_t* overlap_end_out, int64_t* distance_out, void* stream) {

@@ -247,6 +247,26 @@ def count_overlaps(grp1, start1, end1, grp2, start2, end2, n_groups, closed=Fals
     return counts
 
 
+def gather_rows(column, idx, want_valid=False, device=None):
+    """column[idx] for a 4- or 8-byte numeric column (numpy array or tensor) and device row numbers `idx`
+    (-1 -> 0) -> device tensor of the column's dtype (and the validity bytes when asked)."""
+    _require_cuda()
+    device = torch.device(device if device is not None else "cuda")
+    col = column if isinstance(column, torch.Tensor) else torch.as_tensor(column)
+    if col.element_size() not in (4, 8) or col.dtype in (torch.complex64,):
+        raise ValueError("gather_rows: 4- or 8-byte numeric column expected")
+    col = col.to(device=device, non_blocking=True).contiguous()
+    ix = _as(idx, torch.int64, device)
+    n = int(ix.numel())
+    with torch.cuda.device(device):
+        out = torch.empty(n, dtype=col.dtype, device=device)
+        valid = torch.empty(n, dtype=torch.uint8, device=device) if want_valid else None
+        rc = _lib.lib().bf_gather_rows(_ptr(col), col.element_size(), _ptr(ix), n, _ptr(out), _ptr(valid),
+                                       _stream_ptr(device))
+        _lib.check(rc, "bf_gather_rows")
+    return (out, valid) if want_valid else out
+
+
 def pair_coords(ev1, ev2, start1, end1, start2, end2, want_overlap=True, want_distance=False, device=None):
     """Clipped coordinates / distances of reported pairs (return_overlap, return_distance of the frame ops).
     -> (overlap_start, overlap_end, distance) int64 device tensors (None where not wanted); rows with a -1

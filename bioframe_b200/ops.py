@@ -88,7 +88,7 @@ def _rows_to_host(t):
 # overlap
 # --------------------------------------------------------------------------
 def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _group_order=None, _sort_pairs=False,
-                     _coords=False):
+                     _coords=False, _device_rows=None):
     """Integer row positions of overlapping pairs, -1 where a kept row has no
     partner.  Mirrors ops._overlap_intidxs (ops.py:242-338): groups are
     (chrom, *on); the group blocks come in the iteration order of
@@ -140,6 +140,8 @@ def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _gro
     ev1, ev2, _ = _engine.overlap_intidxs(g1, s1, e1, g2, s2, e2, n_groups, how=how)
     if _sort_pairs:  # keep_order on the device: rows by (row of df1, row of df2), -1 last
         ev1, ev2 = _engine.sort_pairs(ev1, ev2, max(len(df1) - 1, 0), max(len(df2) - 1, 0))
+    if _device_rows is not None:  # the caller goes on working with the pair list where it is
+        _device_rows.extend([ev1, ev2])
     if _coords:  # clipped coordinates of every pair (return_overlap, ops.py:480-497) while the list is on the device
         lo, hi, _ = _engine.pair_coords(ev1, ev2, s1, e1, s2, e2)
         return _rows_to_host(ev1), _rows_to_host(ev2), (_to_host(lo), _to_host(hi))
@@ -176,6 +178,34 @@ def _suffixed_rows(df, positions, suffix):
     part = df.iloc[positions].reset_index(drop=True)
     part.columns = [c + suffix for c in part.columns]
     return part
+
+
+# Results of this many rows and more are assembled with device-side column gathers (bf_gather_rows): taking
+# 1e8+ rows of a column with numpy costs seconds per column; the device does it at PCIe speed.
+_DEVICE_GATHER_MIN_ROWS = 1 << 22
+_GATHER_DTYPES = (np.dtype(np.int64), np.dtype(np.int32), np.dtype(np.float64), np.dtype(np.float32))
+
+
+def _taken_rows(df, positions, device_positions, suffix):
+    """`df.iloc[positions]` with suffixed column names (ops.py:499-508).  For large results the fixed-width
+    numeric columns are gathered on the device from the pair list that still lives there (-1 -> 0: such rows
+    are blanked afterwards, as the reference blanks the rows it took from position -1); the other columns
+    (strings, categoricals, nullable dtypes) go through pandas."""
+    if device_positions is None or len(positions) < _DEVICE_GATHER_MIN_ROWS or not df.columns.is_unique:
+        return _suffixed_rows(df, positions, suffix)
+    on_device = [c for c in df.columns if isinstance(df[c].dtype, np.dtype) and df[c].dtype in _GATHER_DTYPES]
+    others = [c for c in df.columns if c not in on_device]
+    rest = df[others].iloc[positions].reset_index(drop=True) if others else None
+    data = {}
+    for c in df.columns:
+        if c in on_device:
+            col = df[c].to_numpy()
+            taken = _engine.gather_rows(col, device_positions)
+            small = col.dtype == np.int64 and len(col) and col.min() >= -1 and col.max() < 2**31 - 1
+            data[c + suffix] = _rows_to_host(taken) if small else _to_host(taken)
+        else:
+            data[c + suffix] = rest[c].array
+    return pd.DataFrame(data, columns=[c + suffix for c in df.columns])
 
 
 def overlap(
@@ -229,9 +259,11 @@ def overlap(
         and (how == "inner" or ensure_int)
         and all(_is_plain_int(df[c]) for df, c in ((df1, sk1), (df1, ek1), (df2, sk2), (df2, ek2)))
     )
+    dev_rows = []
     res = _overlap_intidxs(df1, df2, how=how, cols1=cols1, cols2=cols2, on=on, _sort_pairs=device_order,
-                           _coords=device_coords)
+                           _coords=device_coords, _device_rows=dev_rows)
     ev1, ev2 = res[0], res[1]
+    dev1, dev2 = dev_rows if dev_rows else (None, None)
 
     stem = return_index if isinstance(return_index, str) else "index"
     icol1, icol2 = stem + suffixes[0], stem + suffixes[1]
@@ -250,8 +282,9 @@ def overlap(
             ov_hi = np.minimum(df1[ek1].values[ev1], df2[ek2].values[ev2])
         parts["ov"] = pd.DataFrame({ostem + "_" + sk1: ov_lo, ostem + "_" + ek1: ov_hi})
     if return_input:
-        parts["in1"] = _suffixed_rows(df1, ev1, suffixes[0])
-        parts["in2"] = _suffixed_rows(df2, ev2, suffixes[1])
+        parts["in1"] = _taken_rows(df1, ev1, dev1, suffixes[0])
+        parts["in2"] = _taken_rows(df2, ev2, dev2, suffixes[1])
+    del dev_rows, dev1, dev2
 
     if how != "inner":  # blank the side that has no partner (ops.py:511-544)
         miss1, miss2 = ev1 == -1, ev2 == -1

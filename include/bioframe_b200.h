@@ -111,6 +111,13 @@ int bf_pair_coords(const int64_t* events1, const int64_t* events2, int64_t n_row
                    const int64_t* end1, const int64_t* start2, const int64_t* end2, int64_t* overlap_start_out,
                    int64_t* overlap_end_out, int64_t* distance_out, void* stream);
 
+/* ---- column gather: replaces `df.iloc[events]` of the frame assembly (ops.py:499-508, 1224-1234) for
+ * fixed-width numeric columns: out[i] = src[row_idx[i]] (itemsize 4 or 8 bytes, any numeric type of that
+ * width), 0 where row_idx[i] is -1; valid_out (optional, uint8[n_rows]) = 1 where a row was taken -- value
+ * buffer + validity, the Arrow layout of a nullable column. */
+int bf_gather_rows(const void* src, int32_t itemsize, const int64_t* row_idx, int64_t n_rows, void* out,
+                   uint8_t* valid_out, void* stream);
+
 /* ---- closest: replaces ops._closest_intidxs (ops.py:919-1040), i.e. the
  * per-group loop around arrops.closest_intervals (arrops.py:601-754) and
  * arrops._closest_intervals_nooverlap (arrops.py:506-598), plus the

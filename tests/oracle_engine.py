@@ -63,6 +63,13 @@ def to_device(x, dtype="int64", device=None):
     return np.asarray(x, dtype=dtype)
 
 
+def gather_rows(column, idx, want_valid=False, device=None):
+    column, idx = np.asarray(column), _i64(idx)
+    out = np.where(idx >= 0, column[np.maximum(idx, 0)], column.dtype.type(0)) if len(column) else np.zeros(len(idx), column.dtype)
+    out = out.astype(column.dtype, copy=False)
+    return (out, (idx >= 0).astype(np.uint8)) if want_valid else out
+
+
 def pair_coords(ev1, ev2, start1, end1, start2, end2, want_overlap=True, want_distance=False, device=None):
     a, b = _i64(ev1), _i64(ev2)
     s1, e1, s2, e2 = _i64(start1), _i64(end1), _i64(start2), _i64(end2)

@@ -75,7 +75,30 @@ def test_frame_glue_on_oracle_double(name, oracle_double):
     _check(name)
 
 
+# cases that assemble an `overlap` frame: run them once more with the large-result assembly forced on
+# (numeric columns gathered through bf_gather_rows instead of pandas iloc)
+GATHER_CASES = sorted(n for n, c in CASES.items() if c["fn"] in ("overlap", "subtract", "assign_view", "trim", "complement"))
+
+
+@pytest.fixture
+def device_assembly(monkeypatch):
+    import bioframe_b200.ops as ops
+
+    monkeypatch.setattr(ops, "_DEVICE_GATHER_MIN_ROWS", 0)
+
+
+@pytest.mark.parametrize("name", GATHER_CASES)
+def test_frame_glue_with_column_gathers_on_oracle_double(name, oracle_double, device_assembly):
+    _check(name)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_frame_on_cuda_engine(name):
+    _check(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GATHER_CASES)
+def test_frame_with_column_gathers_on_cuda_engine(name, device_assembly):
     _check(name)

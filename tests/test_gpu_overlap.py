@@ -180,3 +180,19 @@ def test_download_rows_rejects_values_outside_int32():
     with pytest.raises(OverflowError):
         engine.download_rows(t)
     assert _lib is not None
+
+
+@pytest.mark.parametrize("dtype", [np.int64, np.int32, np.float64, np.float32])
+def test_gather_rows_matches_numpy_take(dtype):
+    """bf_gather_rows = df.iloc[events] for one fixed-width column (ops.py:499-508); -1 gives 0 / invalid."""
+    from bioframe_b200 import engine
+
+    rng = np.random.default_rng(3)
+    col = (rng.normal(0, 1e6, 70_001)).astype(dtype)
+    idx = rng.integers(-1, len(col), 300_000)
+    got, valid = engine.gather_rows(col, idx, want_valid=True)
+    want = np.where(idx >= 0, col[np.maximum(idx, 0)], dtype(0)).astype(dtype)
+    assert got.cpu().numpy().dtype == np.dtype(dtype)
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(valid.cpu().numpy(), (idx >= 0).astype(np.uint8))
+    assert engine.gather_rows(col, idx[:0]).numel() == 0
