@@ -227,6 +227,29 @@ int bf_download_rows(const int64_t* dev_src, int64_t n, int64_t* host_dst, void*
                      size_t dev_stage_bytes, void* pinned_stage, size_t pinned_bytes, int32_t n_threads,
                      void* stream);
 
+/* ---- BED ingest: replaces `read_table(path, schema="bed3" ...)` (io/fileops.py:42-84: pandas.read_csv with
+ * sep="\t", header=None) plus the host-side encoding of the chromosome column (ops.py:287-289) for the three
+ * columns the path consumes: tab-separated text on the device -> chromosome code, start, end.  Every
+ * non-blank line is a record `<name> TAB <int> TAB <int> [TAB anything]`, lines end in "\n" or "\r\n" (the last
+ * one may be unterminated); anything else is an error naming the line.  text: device uint8[n_bytes], 16-byte
+ * aligned.
+ *   bf_bed_scan   -> number of lines.
+ *   bf_bed_parse  -> number of records (n_rows_out) and the distinct names: for name k (k < *n_names_out <=
+ *                    32768) the byte offset of an occurrence (HOST name_first_out[k]), its length (HOST
+ *                    name_len_out[k]) and its table slot (HOST name_slot_out[k]); the three arrays must hold
+ *                    32768 entries.
+ *   bf_bed_emit   -> rows in file order; slot_code: HOST int32[65536], the code the caller assigns to every
+ *                    slot reported by bf_bed_parse (e.g. the rank of the name in sorted order).  Outputs may
+ *                    be NULL. */
+size_t bf_bed_scan_workspace_bytes(int64_t n_bytes);
+int bf_bed_scan(const uint8_t* text, int64_t n_bytes, void* ws, size_t ws_bytes, void* stream, int64_t* n_lines_out);
+size_t bf_bed_parse_workspace_bytes(int64_t n_bytes, int64_t n_lines);
+int bf_bed_parse(const uint8_t* text, int64_t n_bytes, int64_t n_lines, void* ws, size_t ws_bytes, bf_plan* plan,
+                 void* stream, int64_t* n_rows_out, int32_t* n_names_out, int64_t* name_first_out,
+                 int32_t* name_len_out, int32_t* name_slot_out);
+int bf_bed_emit(const bf_plan* plan, void* ws, const int32_t* slot_code, int32_t* chrom_code_out,
+                int64_t* start_out, int64_t* end_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
