@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="overlap", choices=["overlap", "closest", "cluster", "coverage", "count", "subtract"],
+    ap.add_argument("--workload", default="overlap", choices=["overlap", "closest", "cluster", "coverage", "count", "subtract", "ingest"],
                     help="overlap = the north-star line (cfg3); the others are the secondary BASELINE.json configs "
                          "(closest: cfg1 1e7 x 1e6 k=1; cluster: cfg2 1e8 heavy-tailed; coverage: cfg3 sets)")
     ap.add_argument("--k", type=int, default=1)
@@ -238,6 +238,41 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _ingest_device(text, raw, dev):
+    """The device part of bioframe_b200.io.read_bed_device on text that already is on the GPU; returns the row count."""
+    import ctypes as C
+
+    import torch
+
+    from bioframe_b200 import _lib
+    from bioframe_b200.engine import Workspace, _ptr, _stream_ptr
+
+    L = _lib.lib()
+    n_bytes = int(text.numel())
+    stream = _stream_ptr(dev)
+    ws = Workspace.get(dev, max(L.bf_bed_scan_workspace_bytes(n_bytes), 256))
+    n_lines = C.c_int64(0)
+    _lib.check(L.bf_bed_scan(_ptr(text), n_bytes, _ptr(ws), ws.numel(), stream, C.byref(n_lines)), "bf_bed_scan")
+    ws = Workspace.get(dev, max(L.bf_bed_parse_workspace_bytes(n_bytes, n_lines.value), 256))
+    plan = _lib.Plan()
+    n_rows, n_names = C.c_int64(0), C.c_int32(0)
+    first, length, slot = np.zeros(1 << 15, np.int64), np.zeros(1 << 15, np.int32), np.zeros(1 << 15, np.int32)
+    _lib.check(L.bf_bed_parse(_ptr(text), n_bytes, n_lines.value, _ptr(ws), ws.numel(), C.byref(plan), stream, C.byref(n_rows),
+                              C.byref(n_names), C.c_void_p(first.ctypes.data), C.c_void_p(length.ctypes.data),
+                              C.c_void_p(slot.ctypes.data)), "bf_bed_parse")
+    k = n_names.value
+    found = [bytes(raw[first[i]: first[i] + length[i]]) for i in range(k)]
+    slot_code = np.full(1 << 16, -1, dtype=np.int32)
+    for code, i in enumerate(sorted(range(k), key=lambda i: found[i])):
+        slot_code[slot[i]] = code
+    chrom = torch.empty(n_rows.value, dtype=torch.int32, device=dev)
+    start = torch.empty(n_rows.value, dtype=torch.int64, device=dev)
+    end = torch.empty(n_rows.value, dtype=torch.int64, device=dev)
+    _lib.check(L.bf_bed_emit(C.byref(plan), _ptr(ws), C.c_void_p(slot_code.ctypes.data), _ptr(chrom), _ptr(start), _ptr(end),
+                             stream), "bf_bed_emit")
+    return n_rows.value
+
+
 def run_secondary(args):
     """closest / cluster / coverage at their BASELINE.json sizes, single GPU: device-resident inputs,
     CUDA-event timing of the whole call, whole-call algorithmic bytes against the measured
@@ -252,6 +287,7 @@ def run_secondary(args):
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     wl = args.workload
+    cpu_sample = None
     if wl == "closest":
         n1, n2 = (args.n1 if args.n1 != 100_000_000 else 10_000_000), (args.n2 if args.n2 != 10_000_000 else 1_000_000)
         q = synth.make_intervals(n1, 1, "geom1k")
@@ -292,6 +328,31 @@ def run_secondary(args):
         (sq, stt) = workload(n1, n2, 0, chrom_ids=SAMPLE_CHROMS)
         cpu = lambda: np.bincount(oo.overlap_intidxs_coded(*sq, *stt, N_GROUPS, how="inner")[0], minlength=len(sq[1]))  # noqa: E731
         cpu_units = len(sq[1]) + len(stt[1])
+    elif wl == "ingest":
+        import io as _io
+
+        import pandas as pd
+
+        n1 = args.n1 if args.n1 != 100_000_000 else 10_000_000
+        q = synth.make_intervals(n1, 1, "geom2k")
+        names = np.array(synth.HG38_CHROMS, dtype=object)
+        buf = _io.BytesIO()
+        pd.DataFrame({"c": names[q[0]], "s": q[1], "e": q[2]}).to_csv(buf, sep="\t", header=False, index=False)
+        raw = np.frombuffer(buf.getvalue(), dtype=np.uint8)
+        text = torch.from_numpy(raw.copy()).to(dev)
+        nbytes = int(raw.size)
+
+        def call():
+            # device-resident text -> device columns (the H2D of the text is the e2e part, not timed here)
+            return _ingest_device(text, raw, dev)
+
+        rows_of = lambda r: int(r)  # noqa: E731
+        a_alg = lambda R: 3 * nbytes + 52 * R  # noqa: E731  (text read three times; line table, parsed fields, outputs)
+        units, name = n1, "BED ingest rows/s"
+        desc = f"bed3 ingest: {n1} lines, {nbytes} bytes of tab-separated text (hg38 names, geom 2kb intervals)"
+        cpu = lambda: pd.read_csv(_io.BytesIO(buf.getvalue()), sep="\t", header=None, names=["chrom", "start", "end"])  # noqa: E731
+        cpu_units = n1
+        cpu_sample = "the same text through pandas.read_csv(sep=TAB, header=None), which is what the reference's read_table calls"
     elif wl == "subtract":
         n1, n2 = args.n1, args.n2
         (q, t) = workload(n1, n2, 0)
@@ -357,8 +418,9 @@ def run_secondary(args):
             w0 = time.perf_counter()
             cpu()
             times.append(time.perf_counter() - w0)
-        line["cpu_baseline"] = {"value": cpu_units / min(times), "unit": "intervals/s", "cores": 1, "kind": "port",
-                                "sample": f"chr21+chr22 share of the workload at full density ({cpu_units} intervals), numpy oracle port",
+        line["cpu_baseline"] = {"value": cpu_units / min(times), "unit": "intervals/s", "cores": 1,
+                                "kind": "reference" if wl == "ingest" else "port",
+                                "sample": cpu_sample or f"chr21+chr22 share of the workload at full density ({cpu_units} intervals), numpy oracle port",
                                 "ms_per_step": min(times) * 1e3}
     print(json.dumps(line), flush=True)
 

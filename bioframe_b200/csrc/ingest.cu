@@ -195,10 +195,14 @@ __global__ void __launch_bounds__(SC_THREADS)
           u64 seen = table[s].hash;
           if (seen == 0) seen = atomicCAS(reinterpret_cast<unsigned long long*>(&table[s].hash), 0ull, h);
           if (seen == 0 || seen == h) {
-            const u32 other = atomicCAS(&table[s].check, 0u, h2);
+            // a genome has a few dozen names and every line lands on one of them: once a slot is set up,
+            // plain loads see that nothing is left to do (no atomics on the hot addresses)
+            u32 other = *reinterpret_cast<volatile u32*>(&table[s].check);
+            if (other == 0) other = atomicCAS(&table[s].check, 0u, h2);
             if (other != 0 && other != h2) atomicMin(reinterpret_cast<unsigned long long*>(hdr + 2), (unsigned long long)(ln + 1));
-            atomicMin(reinterpret_cast<unsigned long long*>(&table[s].first), (unsigned long long)name0);
-            table[s].len = len;
+            if (*reinterpret_cast<volatile u64*>(&table[s].first) > (u64)name0)
+              atomicMin(reinterpret_cast<unsigned long long*>(&table[s].first), (unsigned long long)name0);
+            if (*reinterpret_cast<volatile u32*>(&table[s].len) != len) table[s].len = len;
             slot = s;
             break;
           }
