@@ -13,10 +13,10 @@ __version__ = "0.1.0"
 
 from . import core, extras  # noqa: F401
 from .core.specs import update_default_colnames  # noqa: F401
-from .extras import pair_by_distance  # noqa: F401
+from .extras import mark_runs, merge_runs, pair_by_distance  # noqa: F401
 from .ops import (  # noqa: F401
     assign_view, closest, cluster, complement, count_overlaps, coverage, merge, overlap, setdiff, subtract, trim,
 )
 
 __all__ = ["overlap", "closest", "cluster", "merge", "complement", "coverage", "count_overlaps", "setdiff", "subtract",
-           "assign_view", "trim", "pair_by_distance", "core", "extras", "update_default_colnames"]
+           "assign_view", "trim", "pair_by_distance", "mark_runs", "merge_runs", "core", "extras", "update_default_colnames"]

@@ -1,5 +1,6 @@
-"""Operations the reference layers on top of `overlap` (src/bioframe/extras.py) -- SURVEY.md 8f "next" #3.
-Only the layer whose cost is the pair enumeration is here: `pair_by_distance` (extras.py:389-543)."""
+"""Operations the reference layers on top of `overlap` and the running-max scan (src/bioframe/extras.py) --
+SURVEY.md 8f "next" #3: `pair_by_distance` (extras.py:389-543), `mark_runs` (extras.py:546-652) and
+`merge_runs` (extras.py:655-735)."""
 from __future__ import annotations
 
 import numpy as np
@@ -8,7 +9,7 @@ import pandas as pd
 from . import ops
 from .core.specs import _get_default_colnames
 
-__all__ = ["pair_by_distance"]
+__all__ = ["pair_by_distance", "mark_runs", "merge_runs"]
 
 
 def pair_by_distance(df, min_sep, max_sep, min_intervening=None, max_intervening=None, relative_to="midpoints",
@@ -66,3 +67,56 @@ def pair_by_distance(df, min_sep, max_sep, min_intervening=None, max_intervening
         out = out.drop([icol1, icol2], axis=1)
     out.reset_index(drop=True, inplace=True)
     return out
+
+
+def mark_runs(df, col, *, allow_overlaps=False, reset_counter=True, run_col="run", cols=None):
+    """Number the runs of spatially consecutive intervals that share the value of `col` (extras.py:546-652).
+    Returns a reordered copy of `df`: chromosomes in order of first appearance, rows by (start, end), plus
+    `run_col`.
+
+    The reference loops over chromosomes: sort, running max of the ends, a border wherever an interval starts
+    past everything before it or the value changes, cumulative sum.  Here the spatial borders of all
+    chromosomes come from one device call (the cluster kernel: same sort, running max and border rule,
+    arrops.py:459-470 with min_dist=0), the overlap check counts partners without listing pairs
+    (bf_count_overlaps), and the value borders and the numbering are array operations over the whole frame."""
+    ck, sk, ek = _get_default_colnames() if cols is None else cols
+    if not allow_overlaps and int(ops._overlap_counts(df, df, cols, cols, None).sum()) > len(df):
+        raise ValueError("Not a proper bedGraph: found overlapping intervals.")
+
+    codes, _ = pd.factorize(df[ck])  # order of first appearance, -1 for null chromosomes (dropped, as groupby does)
+    rows = np.flatnonzero(codes >= 0)
+    starts, ends = df[sk].to_numpy()[rows], df[ek].to_numpy()[rows]
+    groups = codes[rows].astype(np.int32)
+    order = np.lexsort((ends, starts, groups))  # stable, like sort_values([start, end]) inside every group
+    n_groups = int(groups.max()) + 1 if len(rows) else 1
+    spatial = np.empty(0, dtype=np.int64)
+    if len(rows):
+        res = ops._engine.cluster(groups, starts.astype(np.int64), ends.astype(np.int64), n_groups, min_dist=0,
+                              want_ids=True, want_table=False)
+        spatial = ops._to_host(res["ids"])[order]  # cluster of every row, in sorted order
+
+    values = df[col].to_numpy()[rows][order]
+    g = groups[order]
+    border = np.ones(len(order), dtype=bool)
+    if len(order) > 1:
+        if values.dtype.kind == "f":
+            changed = ~np.isclose(values[1:], values[:-1], equal_nan=True)
+        else:
+            changed = np.asarray(values[1:] != values[:-1], dtype=bool)
+        border[1:] = (spatial[1:] != spatial[:-1]) | changed | (g[1:] != g[:-1])
+    run = np.cumsum(border) - 1
+    if reset_counter and len(order):  # numbering restarts with every chromosome
+        first_of_group = np.r_[True, g[1:] != g[:-1]]
+        run = run - np.maximum.accumulate(np.where(first_of_group, run, 0))
+    out = df.iloc[rows[order]].copy()
+    out[run_col] = run
+    return out
+
+
+def merge_runs(df, col, *, allow_overlaps=False, agg=None, cols=None):
+    """Merge every run of spatially consecutive intervals sharing the value of `col` into one interval
+    (extras.py:655-735); `agg` adds named aggregations over the rows of a run."""
+    ck, sk, ek = _get_default_colnames() if cols is None else cols
+    marked = mark_runs(df, col, allow_overlaps=allow_overlaps, reset_counter=False, run_col="_run")
+    spec = {ck: (ck, "first"), sk: (sk, "min"), ek: (ek, "max"), col: (col, "first"), **(agg or {})}
+    return marked.groupby("_run").agg(**spec).reset_index(drop=True)

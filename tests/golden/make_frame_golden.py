@@ -134,6 +134,23 @@ def main():
             max_intervening=6, return_index=True, keep_order=True)
         add(f"pair_by_distance_{tag}_ends", "pair_by_distance", df=df1, min_sep=10, max_sep=200, relative_to="endpoints",
             suffixes=("_a", "_b"))
+    # mark_runs / merge_runs: bedGraph-like input (non-overlapping bins with a value column)
+    rng3 = np.random.default_rng(5)
+    bins = []
+    for chrom in ("chr2", "chr1", "chrX"):
+        pos = 0
+        for _ in range(40):
+            pos += int(rng3.integers(0, 3)) * 5  # some gaps
+            width = int(rng3.integers(1, 20))
+            bins.append((chrom, pos, pos + width, int(rng3.integers(0, 3)), float(rng3.integers(0, 2)) / 2))
+            pos += width
+    graph = pd.DataFrame(bins, columns=["chrom", "start", "end", "state", "signal"])
+    graph = graph.sample(frac=1.0, random_state=3)  # shuffled rows, labels kept
+    add("mark_runs_int", "mark_runs", df=graph, col="state")
+    add("mark_runs_float_continue", "mark_runs", df=graph, col="signal", reset_counter=False, run_col="r")
+    add("merge_runs_int", "merge_runs", df=graph, col="state")
+    add("merge_runs_agg", "merge_runs", df=graph, col="signal", agg={"n": ("state", "count"), "top": ("state", "max")})
+    add("mark_runs_overlapping", "mark_runs", df=frames(rng3)[0], col="score", allow_overlaps=True)
     with open(os.path.join(HERE, "frames.pkl"), "wb") as f:
         pickle.dump(cases, f, protocol=4)
     print(len(cases), "cases ->", os.path.join(HERE, "frames.pkl"))

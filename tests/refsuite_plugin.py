@@ -53,8 +53,10 @@ def _install():
 
     import bioframe_b200.extras as our_extras
 
-    ref_extras.pair_by_distance = our_extras.pair_by_distance
-    bioframe.pair_by_distance = our_extras.pair_by_distance
+    for name in ("pair_by_distance", "mark_runs", "merge_runs"):
+        setattr(ref_extras, name, getattr(our_extras, name))
+        if hasattr(bioframe, name):
+            setattr(bioframe, name, getattr(our_extras, name))
     print(f"[refsuite] reference ops patched with bioframe_b200 ({'CUDA engine' if use_gpu else 'oracle test double'})")
 
 
