@@ -55,6 +55,12 @@ SIGNATURES = {
     ),
     "bf_overlap_emit": (C.c_int, [C.POINTER(Plan), _p, _p, _p, _p]),
     "bf_overlap_set_row_offsets": (C.c_int, [C.POINTER(Plan), _i64, _i64]),
+    "bf_overlap_ordered_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "bf_overlap_ordered_count": (
+        C.c_int,
+        [_p, _p, _p, _i64, _p, _p, _p, _i64, _i32, _p, _sz, C.POINTER(Plan), _p, C.POINTER(_i64), C.POINTER(_i64)],
+    ),
+    "bf_overlap_ordered_emit": (C.c_int, [C.POINTER(Plan), _p, _p, _p, _p]),
     "bf_sort_pairs_workspace_bytes": (_sz, [_i64]),
     "bf_sort_pairs": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _sz, _p]),
     "bf_gather_rows": (C.c_int, [_p, _i32, _p, _i64, _p, _p, _p]),

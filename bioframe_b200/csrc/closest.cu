@@ -571,9 +571,323 @@ static int closest_emit_impl(const ClosestPlan* plan, void* ws_ptr, i64* ev1, i6
   return BF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// bf_overlap_ordered_*: overlap(how='left') with the rows in (row of set 1, row of set 2) order -- what
+// bioframe.overlap(how='left') returns by default (keep_order=True, ops.py:455-456, 549-550) when the indexes
+// order like the rows.  The reference sorts the assembled frame; sorting 8.76e8 pairs on the device costs 4x
+// the overlap itself (profiles/NOTES.md).  Here the pairs are BORN in that order: the queries are visited in
+// row order and never sorted, only the targets are (twice, like count_overlaps):
+//   count:  partners = #{start_t < end'_q} - #{end'_t <= start_q}        (two table-assisted probes)
+//   emit:   targets starting inside the query are a contiguous range of the start order; those that started
+//           earlier and still reach the query are found by the running-max walk of closest (walk_stabbing);
+//           the query's few partner rows are sorted by row number in registers and written at its offset
+//           (a query without partner writes (row, -1)).
+struct OrderedWS {
+  SortBufs by_start, by_end;
+  RadixScratch radix;
+  LayoutScratch layout;
+  u64* pmax;
+  u64 *bmax1, *bmax2, *bmax3;
+  u32 *lutS, *lutE;
+  u32 *cnt, *loc;  // [n1] partners of every query, output offset inside its tile
+  u64* spine;      // [tiles(n1) + 2]
+  ScanState ss_tmp;
+  i64* hdr;        // [0] rows, [1] overflow flag, [2] largest partner count
+};
+static void layout_ordered(Arena& a, i64 n1, i64 n2, i32 nb, OrderedWS* w) {
+  take_sort_bufs(a, n2, &w->by_start);
+  take_sort_bufs(a, n2, &w->by_end);
+  w->radix = take_radix_scratch(a, (u64)n2);
+  w->layout = take_layout_scratch(a, nb);
+  w->pmax = a.take<u64>(n2 + 1);
+  w->bmax1 = a.take<u64>((n2 >> 5) + 2);
+  w->bmax2 = a.take<u64>((n2 >> 10) + 2);
+  w->bmax3 = a.take<u64>((n2 >> 15) + 2);
+  w->lutS = a.take<u32>(lut_words(n2));
+  w->lutE = a.take<u32>(lut_words(n2));
+  w->cnt = a.take<u32>(n1 + 1);
+  w->loc = a.take<u32>(n1 + 1);
+  w->spine = a.take<u64>(scan_tiles((u64)(n1 > 0 ? n1 : 1)) + 2);
+  w->ss_tmp = take_scan_state(a, (u64)scan_tiles((u64)(n2 > 0 ? n2 : 1)));
+  w->hdr = a.take<i64>(4);
+}
+struct OrderedPlan {
+  u64 magic;
+  i32 ready, pad;
+  i64 n_rows, n_pairs, max_partners;
+  ClosestArgs args;
+};
+static_assert(sizeof(OrderedPlan) <= sizeof(bf_plan), "bf_plan too small");
+constexpr u64 ORDERED_MAGIC = 0x62664f7264657265ull;
+constexpr int ORDERED_SMALL = 32;  // partner lists up to this size are sorted in registers / local memory
+
+// linear start and end' of query r (a point behaves as [x, x + 1), arrops.py:271-287; ends clamped like the packed ones)
+__device__ __forceinline__ void ordered_query(const ClosestArgs& A, i64 r, u64* xs, u64* xe) {
+  const u32 g = A.grp1 ? (u32)A.grp1[r] : 0u;
+  const i64 a = A.s1[r];
+  i64 b = A.e1[r];
+  if (a == b) b += 1;
+  b = min(b, A.L.endcap);
+  const u64 off = A.L.goff[g];
+  *xs = off + ((u64)a - A.L.cmin);
+  *xe = off + ((u64)b - A.L.cmin);
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+    ordered_count_kernel(ClosestArgs A, u32* __restrict__ cnt_out, u32* __restrict__ loc_out, u64* __restrict__ tile_tot,
+                         i64* __restrict__ hdr) {
+  __shared__ u64 s_tmp[8];
+  const i64 base = (i64)blockIdx.x * SC_TILE + (i64)threadIdx.x * SC_IPT;
+  u64 mine = 0;
+  u32 biggest = 0;
+#pragma unroll 1
+  for (int j = 0; j < SC_IPT; ++j) {
+    const i64 r = base + j;
+    if (r >= A.n1) break;
+    u32 c = 0;
+    if (A.n2 > 0) {
+      u64 xs, xe;
+      ordered_query(A, r, &xs, &xe);
+      const i64 started = lut_count_below<false>(A.kS, A.lutS, xe);
+      const i64 ended = lut_count_below<true>(A.kE, A.lutE, xs);
+      c = started > ended ? (u32)(started - ended) : 0u;
+    }
+    cnt_out[r] = c;
+    mine += c > 0 ? c : 1;  // how='left': a query without partner still yields one row
+    biggest = c > biggest ? c : biggest;
+  }
+  u64 tot;
+  u64 run = block_excl_sum_u64(mine, s_tmp, &tot);
+  if (threadIdx.x == 0) {
+    tile_tot[blockIdx.x] = tot;
+    if (tot >> 32) hdr[1] = 1;  // in-tile offsets are 32-bit
+  }
+  if (biggest > 0) atomicMax(reinterpret_cast<unsigned long long*>(hdr + 2), (unsigned long long)biggest);
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    const i64 r = base + j;
+    if (r < A.n1) {
+      loc_out[r] = (u32)run;
+      const u32 c = cnt_out[r];  // written by this thread above
+      run += c > 0 ? c : 1;
+    }
+  }
+}
+
+// in-place heap sort of a long partner list (one thread; lists this long are rare)
+__device__ void ordered_heapsort(i64* v, i64 n) {
+  auto sift = [&](i64 root, i64 end) {
+    for (;;) {
+      i64 child = 2 * root + 1;
+      if (child >= end) return;
+      if (child + 1 < end && v[child] < v[child + 1]) ++child;
+      if (v[root] >= v[child]) return;
+      const i64 t = v[root];
+      v[root] = v[child];
+      v[child] = t;
+      root = child;
+    }
+  };
+  for (i64 i = n / 2 - 1; i >= 0; --i) sift(i, n);
+  for (i64 end = n - 1; end > 0; --end) {
+    const i64 t = v[0];
+    v[0] = v[end];
+    v[end] = t;
+    sift(0, end);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    ordered_emit_kernel(ClosestArgs A, const u32* __restrict__ cnt_in, const u32* __restrict__ loc_in,
+                        const u64* __restrict__ spine, i64* __restrict__ ev1, i64* __restrict__ ev2) {
+  const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= A.n1) return;
+  const u32 c = cnt_in[r];
+  const i64 at = (i64)spine[r / SC_TILE] + loc_in[r];
+  if (c == 0) {
+    ev1[at] = r;
+    ev2[at] = -1;
+    return;
+  }
+  u64 xs, xe;
+  ordered_query(A, r, &xs, &xe);
+  const i64 lo = lut_count_below<false>(A.kS, A.lutS, xs);
+  const i64 hi = lut_count_below<false>(A.kS, A.lutS, xe);
+  const u32 n_inside = (u32)(hi - lo);  // targets starting inside the query
+  if (c <= ORDERED_SMALL) {
+    u32 ids[ORDERED_SMALL];
+    u32 k = 0;
+    auto put = [&](u32 id) {  // insertion keeps the list sorted by row number
+      u32 y = k++;
+      while (y > 0 && ids[y - 1] > id) {
+        ids[y] = ids[y - 1];
+        --y;
+      }
+      ids[y] = id;
+    };
+    for (u32 i = 0; i < n_inside && k < c; ++i) put(A.idS[lo + i]);
+    if (k < c)
+      walk_stabbing(A, lo, xs, [&](i64 m) {
+        put(A.idS[m]);
+        return k < c;
+      });
+    for (u32 i = 0; i < k; ++i) {
+      ev1[at + i] = r;
+      ev2[at + i] = ids[i];
+    }
+  } else {
+    u32 k = 0;
+    for (u32 i = 0; i < n_inside && k < c; ++i) ev2[at + k++] = A.idS[lo + i];
+    if (k < c)
+      walk_stabbing(A, lo, xs, [&](i64 m) {
+        ev2[at + k++] = A.idS[m];
+        return k < c;
+      });
+    ordered_heapsort(ev2 + at, (i64)k);
+    for (u32 i = 0; i < k; ++i) ev1[at + i] = r;
+  }
+}
+
+static int ordered_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64 n1, const i32* grp2, const i64* s2,
+                              const i64* e2, i64 n2, i32 nb, void* ws_ptr, size_t ws_bytes, OrderedPlan* plan,
+                              cudaStream_t st) {
+  if (n1 < 0 || n2 < 0 || nb < 1 || !plan) {
+    set_error("bf_overlap_ordered_count: bad argument (n1=%lld n2=%lld n_groups=%d)", (long long)n1, (long long)n2, nb);
+    return BF_ERR_ARG;
+  }
+  if (n1 >= (1ll << 31) || n2 >= (1ll << 31)) {
+    set_error("bf_overlap_ordered_count: more than 2^31-1 rows in one set");
+    return BF_ERR_RANGE;
+  }
+  plan->magic = 0;
+  plan->ready = 0;
+  plan->n_rows = plan->n_pairs = plan->max_partners = 0;
+  if (n1 == 0) {
+    plan->args = ClosestArgs{};
+    plan->magic = ORDERED_MAGIC;
+    plan->ready = 1;
+    return BF_OK;
+  }
+  if (!s1 || !e1 || (n2 > 0 && (!s2 || !e2)) || (nb > 1 && (!grp1 || (n2 > 0 && !grp2)))) {
+    set_error("bf_overlap_ordered_count: null input pointer");
+    return BF_ERR_ARG;
+  }
+  Arena measure(nullptr);
+  OrderedWS w;
+  layout_ordered(measure, n1, n2, nb, &w);
+  if (!ws_ptr || ws_bytes < measure.off) {
+    set_error("bf_overlap_ordered_count: workspace %zu bytes < required %zu", ws_bytes, measure.off);
+    return BF_ERR_WORKSPACE;
+  }
+  Arena arena(ws_ptr);
+  layout_ordered(arena, n1, n2, nb, &w);
+  const RowSet sets[2] = {{grp1, s1, e1, n1}, {grp2, s2, e2, n2}};
+  KeyLayout L;
+  BF_TRY(measure_layout(sets, 2, nb, 1, 1, w.layout, st, &L, "bf_overlap_ordered_count"));
+  if (L.B > 62) {
+    set_error("bf_overlap_ordered_count: coordinate span too wide (%d bits)", L.B);
+    return BF_ERR_RANGE;
+  }
+  ClosestArgs A = {};
+  A.grp1 = nb > 1 ? grp1 : nullptr;
+  A.s1 = s1;
+  A.e1 = e1;
+  A.L = L;
+  A.n1 = n1;
+  A.n2 = n2;
+  if (n2 > 0) {
+    SortResult rS, rE;
+    BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, KEY_POINT_ADJUST | KEY_NO_TIE_FIX | presorted_mode(L, 1), w.by_start,
+                     w.radix, st, &rS));
+    BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, KEY_POINT_ADJUST | KEY_NO_TIE_FIX | KEY_BY_END, w.by_end, w.radix,
+                     st, &rE));
+    const unsigned tiles = (unsigned)scan_tiles((u64)n2);
+    BF_TRY(reset_scan_state(w.ss_tmp, tiles, st));
+    BF_LAUNCH(PC_RUNMAX, 16 * n2, st, runmax_adj_kernel<<<tiles, SC_THREADS, 0, st>>>(rS.keys, (u64)n2, L, w.ss_tmp, w.pmax));
+    const i64 nb1 = (n2 + 31) >> 5, nb2 = (nb1 + 31) >> 5, nb3 = (nb2 + 31) >> 5;
+    BF_LAUNCH(PC_RUNMAX, 8 * n2, st, block_max_kernel<<<(unsigned)ceil_div(nb1, 256), 256, 0, st>>>(rS.keys, nullptr, n2, L, w.bmax1));
+    BF_LAUNCH(PC_RUNMAX, 0, st, block_max_kernel<<<(unsigned)ceil_div(nb2, 256), 256, 0, st>>>(nullptr, w.bmax1, nb1, L, w.bmax2));
+    BF_LAUNCH(PC_RUNMAX, 0, st, block_max_kernel<<<(unsigned)ceil_div(nb3, 256), 256, 0, st>>>(nullptr, w.bmax2, nb2, L, w.bmax3));
+    A.kS = rS.keys;
+    A.kE = rE.keys;
+    A.idS = rS.vals;
+    A.idE = rE.vals;
+    A.pmax = w.pmax;
+    A.bmax1 = w.bmax1;
+    A.bmax2 = w.bmax2;
+    A.bmax3 = w.bmax3;
+    A.lutS = make_lut(w.lutS, n2, 0, 1ull << L.B, L.LB);
+    A.lutE = make_lut(w.lutE, n2, 0, 1ull << L.B, L.LB);
+    BF_TRY(launch_lut_build(rS.keys, n2, nullptr, A.lutS, w.lutS, st, PC_COVERAGE));
+    BF_TRY(launch_lut_build(rE.keys, n2, nullptr, A.lutE, w.lutE, st, PC_COVERAGE));
+  }
+  BF_CUDA(cudaMemsetAsync(w.hdr, 0, 4 * sizeof(i64), st));
+  const unsigned qtiles = (unsigned)scan_tiles((u64)n1);
+  BF_LAUNCH(PC_SEARCH, 36 * n1, st, ordered_count_kernel<<<qtiles, SC_THREADS, 0, st>>>(A, w.cnt, w.loc, w.spine, w.hdr));
+  BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.spine, (u64)qtiles, reinterpret_cast<u64*>(w.hdr)));
+  i64 hdr[3];
+  BF_CUDA(cudaMemcpyAsync(hdr, w.hdr, sizeof(hdr), cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaStreamSynchronize(st));
+  if (hdr[1]) {
+    set_error("bf_overlap_ordered_count: more than 2^32-1 output rows for 2048 consecutive queries");
+    return BF_ERR_RANGE;
+  }
+  plan->n_rows = hdr[0];
+  plan->max_partners = hdr[2];
+  plan->args = A;
+  plan->magic = ORDERED_MAGIC;
+  plan->ready = 1;
+  return BF_OK;
+}
+
+static int ordered_emit_impl(const OrderedPlan* plan, void* ws_ptr, i64* ev1, i64* ev2, cudaStream_t st) {
+  if (!plan || plan->magic != ORDERED_MAGIC || !plan->ready) {
+    set_error("bf_overlap_ordered_emit: plan was not produced by a successful bf_overlap_ordered_count");
+    return BF_ERR_STATE;
+  }
+  if (plan->n_rows == 0) return BF_OK;
+  if (!ev1 || !ev2) {
+    set_error("bf_overlap_ordered_emit: null output pointer");
+    return BF_ERR_ARG;
+  }
+  const ClosestArgs& A = plan->args;
+  Arena arena(ws_ptr);
+  OrderedWS w;
+  layout_ordered(arena, A.n1, A.n2, A.L.nb, &w);
+  BF_LAUNCH(PC_EMIT, 28 * A.n1 + 20 * plan->n_rows, st,
+            ordered_emit_kernel<<<(unsigned)ceil_div(A.n1, 256), 256, 0, st>>>(A, w.cnt, w.loc, w.spine, ev1, ev2));
+  return BF_OK;
+}
+
 }  // namespace bf
 
 extern "C" {
+
+size_t bf_overlap_ordered_workspace_bytes(int64_t n1, int64_t n2, int32_t n_groups) {
+  if (n1 < 0 || n2 < 0 || n_groups < 1) return 0;
+  bf::Arena a(nullptr);
+  bf::OrderedWS w;
+  bf::layout_ordered(a, n1, n2, n_groups, &w);
+  return a.off;
+}
+int bf_overlap_ordered_count(const int32_t* grp1, const int64_t* start1, const int64_t* end1, int64_t n1,
+                             const int32_t* grp2, const int64_t* start2, const int64_t* end2, int64_t n2,
+                             int32_t n_groups, void* ws, size_t ws_bytes, bf_plan* plan, void* stream,
+                             int64_t* n_rows_out, int64_t* max_partners_out) {
+  bf::OrderedPlan* p = (bf::OrderedPlan*)plan;
+  int rc = bf::ordered_count_impl((const i32*)grp1, (const i64*)start1, (const i64*)end1, n1, (const i32*)grp2,
+                                  (const i64*)start2, (const i64*)end2, n2, n_groups, ws, ws_bytes, p,
+                                  (cudaStream_t)stream);
+  if (rc == BF_OK) {
+    if (n_rows_out) *n_rows_out = p->n_rows;
+    if (max_partners_out) *max_partners_out = p->max_partners;
+  }
+  return rc;
+}
+int bf_overlap_ordered_emit(const bf_plan* plan, void* ws, int64_t* events1_out, int64_t* events2_out, void* stream) {
+  return bf::ordered_emit_impl((const bf::OrderedPlan*)plan, ws, (i64*)events1_out, (i64*)events2_out,
+                               (cudaStream_t)stream);
+}
 
 size_t bf_closest_workspace_bytes(int64_t n1, int64_t n2, int32_t n_groups) {
   if (n1 < 0 || n2 < 0 || n_groups < 1) return 0;

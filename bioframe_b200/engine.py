@@ -247,6 +247,32 @@ def count_overlaps(grp1, start1, end1, grp2, start2, end2, n_groups, closed=Fals
     return counts
 
 
+def overlap_ordered(grp1, start1, end1, grp2, start2, end2, n_groups, device=None):
+    """overlap(how='left') with the rows already in (row of set 1, row of set 2) order, -1 = no partner
+    (bf_overlap_ordered_*).  -> (events1, events2, largest partner count of one row)."""
+    _require_cuda()
+    L = _lib.lib()
+    device = torch.device(device if device is not None else "cuda")
+    s1, e1 = _as(start1, torch.int64, device), _as(end1, torch.int64, device)
+    s2, e2 = _as(start2, torch.int64, device), _as(end2, torch.int64, device)
+    g1 = _as(grp1, torch.int32, device) if n_groups > 1 else None
+    g2 = _as(grp2, torch.int32, device) if n_groups > 1 else None
+    n1, n2 = int(s1.numel()), int(s2.numel())
+    with torch.cuda.device(device):
+        ws = Workspace.get(device, max(L.bf_overlap_ordered_workspace_bytes(n1, n2, n_groups), 256))
+        plan = _lib.Plan()
+        n_rows, biggest = C.c_int64(0), C.c_int64(0)
+        stream = _stream_ptr(device)
+        rc = L.bf_overlap_ordered_count(_ptr(g1), _ptr(s1), _ptr(e1), n1, _ptr(g2), _ptr(s2), _ptr(e2), n2, n_groups,
+                                        _ptr(ws), ws.numel(), C.byref(plan), stream, C.byref(n_rows), C.byref(biggest))
+        _lib.check(rc, "bf_overlap_ordered_count")
+        ev1 = torch.empty(n_rows.value, dtype=torch.int64, device=device)
+        ev2 = torch.empty(n_rows.value, dtype=torch.int64, device=device)
+        rc = L.bf_overlap_ordered_emit(C.byref(plan), _ptr(ws), _ptr(ev1), _ptr(ev2), stream)
+        _lib.check(rc, "bf_overlap_ordered_emit")
+    return ev1, ev2, biggest.value
+
+
 def gather_rows(column, idx, want_valid=False, device=None):
     """column[idx] for a 4- or 8-byte numeric column (numpy array or tensor) and device row numbers `idx`
     (-1 -> 0) -> device tensor of the column's dtype (and the validity bytes when asked)."""

@@ -28,6 +28,7 @@ from .core.specs import _get_default_colnames, _verify_columns
 __all__ = ["overlap", "closest", "cluster", "merge", "complement", "coverage", "count_overlaps", "setdiff", "subtract", "assign_view", "trim"]
 
 _INT64_MAX = np.iinfo(np.int64).max
+_ORDERED_MAX_PARTNERS = 1 << 14  # longest partner list of one row the row-order overlap kernel is used for
 
 
 # --------------------------------------------------------------------------
@@ -137,9 +138,18 @@ def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _gro
     s1, e1, s2, e2 = _int64_coords(df1, sk1), _int64_coords(df1, ek1), _int64_coords(df2, sk2), _int64_coords(df2, ek2)
     if _coords:  # the coordinates go to the device once: the overlap call and the coordinate gather share them
         s1, e1, s2, e2 = (_engine.to_device(x) for x in (s1, e1, s2, e2))
-    ev1, ev2, _ = _engine.overlap_intidxs(g1, s1, e1, g2, s2, e2, n_groups, how=how)
-    if _sort_pairs:  # keep_order on the device: rows by (row of df1, row of df2), -1 last
-        ev1, ev2 = _engine.sort_pairs(ev1, ev2, max(len(df1) - 1, 0), max(len(df2) - 1, 0))
+    ev1 = None
+    if _sort_pairs and how == "left":
+        # keep_order: the pairs are produced in (row of df1, row of df2) order directly, queries visited in row
+        # order (bf_overlap_ordered_*).  A row with a huge partner list is sorted by one thread there: such
+        # inputs take the general path below (all pairs, then a radix sort of the pair list).
+        ev1, ev2, biggest = _engine.overlap_ordered(g1, s1, e1, g2, s2, e2, n_groups)
+        if biggest > _ORDERED_MAX_PARTNERS:
+            ev1 = None
+    if ev1 is None:
+        ev1, ev2, _ = _engine.overlap_intidxs(g1, s1, e1, g2, s2, e2, n_groups, how=how)
+        if _sort_pairs:  # keep_order on the device: rows by (row of df1, row of df2), -1 last
+            ev1, ev2 = _engine.sort_pairs(ev1, ev2, max(len(df1) - 1, 0), max(len(df2) - 1, 0))
     if _device_rows is not None:  # the caller goes on working with the pair list where it is
         _device_rows.extend([ev1, ev2])
     if _coords:  # clipped coordinates of every pair (return_overlap, ops.py:480-497) while the list is on the device

@@ -91,6 +91,21 @@ int bf_overlap_emit(const bf_plan* plan, void* ws, int64_t* events1_out, int64_t
  * pass over the output. */
 int bf_overlap_set_row_offsets(bf_plan* plan, int64_t offset1, int64_t offset2);
 
+/* ---- overlap(how='left') with the rows in (row of set 1, row of set 2) order: what bioframe.overlap returns by
+ * default for how='left' (keep_order=True, ops.py:455-456 and the sort_values of ops.py:549-550) when the frame
+ * indexes order like the rows; -1 marks a row of set 1 without partner.  The pairs are produced in that order
+ * directly -- the queries are visited in row order and never sorted, only the targets are -- instead of
+ * sorting the pair list afterwards (bf_sort_pairs).  max_partners_out: the largest number of partners of one
+ * row (lists above 32 are sorted by a single thread: a caller may prefer bf_overlap_* + bf_sort_pairs when it
+ * is huge). */
+size_t bf_overlap_ordered_workspace_bytes(int64_t n1, int64_t n2, int32_t n_groups);
+int bf_overlap_ordered_count(const int32_t* grp1, const int64_t* start1, const int64_t* end1, int64_t n1,
+                             const int32_t* grp2, const int64_t* start2, const int64_t* end2, int64_t n2,
+                             int32_t n_groups, void* ws, size_t ws_bytes, bf_plan* plan, void* stream,
+                             int64_t* n_rows_out, int64_t* max_partners_out);
+int bf_overlap_ordered_emit(const bf_plan* plan, void* ws, int64_t* events1_out, int64_t* events2_out,
+                            void* stream);
+
 /* ---- keep_order: replaces `out_df.sort_values([index1, index2])` of ops.overlap (ops.py:549-550) for
  * frames whose indexes are monotonic (labels ordered like row positions).  Sorts the pairs in place by
  * (events1, events2); -1 sorts after every row number of its column (pandas: NA last).  max1 / max2 are

@@ -98,6 +98,13 @@ def complement(region, start, end, bounds_lo, bounds_hi, device=None):
     return oc.astype(np.int32), os_, oe
 
 
+def overlap_ordered(grp1, start1, end1, grp2, start2, end2, n_groups, device=None):
+    ev1, ev2, _ = overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how="left")
+    ev1, ev2 = sort_pairs(ev1, ev2, len(start1), len(start2))
+    biggest = int(np.bincount(ev1[ev2 >= 0], minlength=1).max()) if len(ev1) else 0
+    return ev1, ev2, biggest
+
+
 def sort_pairs(ev1, ev2, max1, max2):
     a = np.where(ev1 < 0, max1 + 1, ev1)
     b = np.where(ev2 < 0, max2 + 1, ev2)

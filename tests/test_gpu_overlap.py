@@ -196,3 +196,42 @@ def test_gather_rows_matches_numpy_take(dtype):
     assert np.array_equal(got.cpu().numpy(), want)
     assert np.array_equal(valid.cpu().numpy(), (idx >= 0).astype(np.uint8))
     assert engine.gather_rows(col, idx[:0]).numel() == 0
+
+
+def _ordered_reference(g1, s1, e1, g2, s2, e2, nb):
+    ev1, ev2 = oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, nb, how="left")
+    key2 = np.where(ev2 < 0, len(s2) + 1, ev2)
+    order = np.lexsort([key2, ev1])
+    return ev1[order], ev2[order]
+
+
+@pytest.mark.parametrize("n1,n2,nb,span,maxlen,big", [
+    (0, 10, 2, 100, 10, 0.0), (10, 0, 2, 100, 10, 0.0), (1, 1, 1, 10, 5, 0.0), (300, 200, 1, 500, 30, 0.0),
+    (5000, 3000, 7, 4000, 60, 0.0), (20000, 9000, 25, 100000, 400, 0.0), (9000, 30000, 300, 3000, 20, 0.0),
+    (4000, 2500, 3, 800, 400, 0.0), (3000, 2000, 4, 5000, 50, 0.02), (2000, 60000, 2, 300, 40, 0.0),
+])
+def test_overlap_ordered_matches_sorted_left_join(n1, n2, nb, span, maxlen, big):
+    """bf_overlap_ordered_*: how='left' rows in (row1, row2) order = the reference's keep_order=True result
+    (ops.py:549-550) at the index level; includes lists above 32 partners (heap-sorted) and INT64_MAX ends."""
+    from bioframe_b200 import engine
+
+    rng = np.random.default_rng(n1 + 7 * n2 + nb)
+
+    def make(n):
+        g = rng.integers(0, nb, n).astype(np.int32)
+        s = rng.integers(0, span, n).astype(np.int64)
+        ln = rng.integers(1, maxlen, n).astype(np.int64)
+        ln[rng.random(n) < 0.1] = 0
+        e = s + ln
+        if big:
+            e[rng.random(n) < big] = np.iinfo(np.int64).max
+        return g, s, e
+
+    g1, s1, e1 = make(n1)
+    g2, s2, e2 = make(n2)
+    ev1, ev2, biggest = engine.overlap_ordered(g1, s1, e1, g2, s2, e2, nb)
+    want1, want2 = _ordered_reference(g1, s1, e1, g2, s2, e2, nb)
+    assert np.array_equal(ev1.cpu().numpy(), want1)
+    assert np.array_equal(ev2.cpu().numpy(), want2)
+    paired = want1[want2 >= 0]
+    assert biggest == (int(np.bincount(paired).max()) if len(paired) else 0)
