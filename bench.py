@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="overlap", choices=["overlap", "closest", "cluster", "coverage", "count", "subtract", "ingest"],
+    ap.add_argument("--workload", default="overlap", choices=["overlap", "closest", "cluster", "coverage", "count", "subtract", "ingest", "ordered"],
                     help="overlap = the north-star line (cfg3); the others are the secondary BASELINE.json configs "
                          "(closest: cfg1 1e7 x 1e6 k=1; cluster: cfg2 1e8 heavy-tailed; coverage: cfg3 sets)")
     ap.add_argument("--k", type=int, default=1)
@@ -353,6 +353,22 @@ def run_secondary(args):
         cpu = lambda: pd.read_csv(_io.BytesIO(buf.getvalue()), sep="\t", header=None, names=["chrom", "start", "end"])  # noqa: E731
         cpu_units = n1
         cpu_sample = "the same text through pandas.read_csv(sep=TAB, header=None), which is what the reference's read_table calls"
+    elif wl == "ordered":
+        n1, n2 = args.n1, args.n2
+        (q, t) = workload(n1, n2, 0)
+        d = [torch.from_numpy(a).to(dev) for a in (*q, *t)]
+        call = lambda: engine.overlap_ordered(d[0], d[1], d[2], d[3], d[4], d[5], N_GROUPS)  # noqa: E731
+        rows_of = lambda r: int(r[0].numel())  # noqa: E731
+        a_alg = lambda R: 2 * 256 * n2 + 36 * n1 + 20 * R  # noqa: E731  (targets sorted twice, probes, pairs)
+        units, name = n1 + n2, "bf.overlap(how='left', keep_order=True) input intervals/s"
+        desc = f"left overlap in row order (keep_order) cfg3: {n1} hg38 queries (geom 2kb) x {n2} peak-like targets"
+        (sq, stt) = workload(n1, n2, 0, chrom_ids=SAMPLE_CHROMS)
+
+        def cpu():
+            a, b = oo.overlap_intidxs_coded(*sq, *stt, N_GROUPS, how="left")
+            return np.lexsort([np.where(b < 0, len(stt[1]) + 1, b), a])
+
+        cpu_units = len(sq[1]) + len(stt[1])
     elif wl == "subtract":
         n1, n2 = args.n1, args.n2
         (q, t) = workload(n1, n2, 0)

@@ -136,3 +136,18 @@ def test_closest_k1_brute_force_sample():
         t = by_chrom[g1[q]]
         best = np.maximum(0, np.maximum(s1[q] - e2[t], s2[t] - e1[q])).min()
         assert dist[r] == best
+
+
+def test_ordered_left_overlap_equals_sorted_pair_list_at_full_size(sets):
+    """Two independent routes to the keep_order result at 1e8 x 1e7: pairs born in row order
+    (bf_overlap_ordered_*: per-query probes + running-max walk) against all pairs + radix sort of the pair
+    list (bf_overlap_* + bf_sort_pairs).  They share the sort of the targets and nothing else."""
+    from bioframe_b200 import engine
+
+    g1, s1, e1, g2, s2, e2 = sets
+    a, b, biggest = engine.overlap_ordered(g1, s1, e1, g2, s2, e2, NB)
+    ev1, ev2, _ = engine.overlap_intidxs(g1, s1, e1, g2, s2, e2, NB, how="left")
+    ev1, ev2 = engine.sort_pairs(ev1, ev2, N1 - 1, N2 - 1)
+    assert a.numel() == ev1.numel()
+    assert torch.equal(a, ev1) and torch.equal(b, ev2)
+    assert 0 < biggest < 100_000
