@@ -590,6 +590,10 @@ struct OrderedWS {
   u64 *bmax1, *bmax2, *bmax3;
   u32 *lutS, *lutE;
   u32 *cnt, *loc;  // [n1] partners of every query, output offset inside its tile
+  u32* started;    // [n1] #{targets starting before the query's end'} (end of its range in the start order)
+  // axes up to 2^32 (any real genome): everything a query touches per target packed next to each other
+  uint4* rec;      // [n2] start order: x = linear start, y = linear end', z = row number
+  u32* ends32;     // [n2] end order: linear end'
   u64* spine;      // [tiles(n1) + 2]
   ScanState ss_tmp;
   i64* hdr;        // [0] rows, [1] overflow flag, [2] largest partner count
@@ -607,6 +611,9 @@ static void layout_ordered(Arena& a, i64 n1, i64 n2, i32 nb, OrderedWS* w) {
   w->lutE = a.take<u32>(lut_words(n2));
   w->cnt = a.take<u32>(n1 + 1);
   w->loc = a.take<u32>(n1 + 1);
+  w->started = a.take<u32>(n1 + 1);
+  w->rec = a.take<uint4>(n2 + 1);
+  w->ends32 = a.take<u32>(n2 + 1);
   w->spine = a.take<u64>(scan_tiles((u64)(n1 > 0 ? n1 : 1)) + 2);
   w->ss_tmp = take_scan_state(a, (u64)scan_tiles((u64)(n2 > 0 ? n2 : 1)));
   w->hdr = a.take<i64>(4);
@@ -633,56 +640,115 @@ __device__ __forceinline__ void ordered_query(const ClosestArgs& A, i64 r, u64* 
   *xe = off + ((u64)b - A.L.cmin);
 }
 
+// Queries arrive in arbitrary order, so every array they touch is a random DRAM access (the target arrays of
+// the benchmark, 180 MB as 64-bit keys + ids + ends, do not fit the L2).  On axes up to 2^32 the targets are
+// repacked: 16-byte records in start order (start, end', row: a query's whole neighbourhood is a few adjacent
+// cache lines) and a 4-byte array of the ends in end order.
+struct Ordered32 {
+  const uint4* rec;   // null: the axis needs more than 32 bits, use the 64-bit arrays
+  const u32* ends32;
+};
+__global__ void __launch_bounds__(256)
+    ordered_pack32_kernel(const u64* __restrict__ kS, const u32* __restrict__ idS, const u64* __restrict__ kE, i64 n,
+                          KeyLayout L, uint4* __restrict__ rec, u32* __restrict__ ends32) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64 k = kS[i];
+  rec[i] = make_uint4((u32)key_cs(k, L), (u32)key_ce_adj(k, L), idS[i], 0u);
+  ends32[i] = (u32)(kE[i] >> L.LB);
+}
+// #{records with start < x} / #{ends <= x}: one table sector, then a search inside the bucket
+__device__ __forceinline__ i64 ordered_starts_below(const uint4* __restrict__ rec, const Lut& t, u64 x) {
+  u64 b = x < t.base ? 0ull : (x - t.base) >> t.shift;
+  if (b >= t.nbuckets) b = t.nbuckets - 1;
+  i64 lo = t.tab[b], hi = t.tab[b + 1];
+  if (x < t.base) lo = 0;
+  while (lo < hi) {
+    const i64 mid = lo + ((hi - lo) >> 1);
+    if ((u64)rec[mid].x < x)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ i64 ordered_ends_upto(const u32* __restrict__ ends32, const Lut& t, u64 x) {
+  u64 b = x < t.base ? 0ull : (x - t.base) >> t.shift;
+  if (b >= t.nbuckets) b = t.nbuckets - 1;
+  i64 lo = t.tab[b], hi = t.tab[b + 1];
+  if (x < t.base) lo = 0;
+  while (lo < hi) {
+    const i64 mid = lo + ((hi - lo) >> 1);
+    if ((u64)ends32[mid] <= x)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(SC_THREADS)
-    ordered_count_kernel(ClosestArgs A, u32* __restrict__ cnt_out, u32* __restrict__ loc_out, u64* __restrict__ tile_tot,
-                         i64* __restrict__ hdr) {
+    ordered_count_kernel(ClosestArgs A, Ordered32 P, u32* __restrict__ cnt_out, u32* __restrict__ started_out,
+                         u32* __restrict__ loc_out, u64* __restrict__ tile_tot, i64* __restrict__ hdr) {
   __shared__ u64 s_tmp[8];
-  const i64 base = (i64)blockIdx.x * SC_TILE + (i64)threadIdx.x * SC_IPT;
-  u64 mine = 0;
+  const i64 tile0 = (i64)blockIdx.x * SC_TILE;
   u32 biggest = 0;
+  // probes: rows strided over the block (coalesced reads of the query columns, coalesced writes of the counts)
 #pragma unroll 1
   for (int j = 0; j < SC_IPT; ++j) {
-    const i64 r = base + j;
+    const i64 r = tile0 + (i64)j * SC_THREADS + threadIdx.x;
     if (r >= A.n1) break;
-    u32 c = 0;
+    u32 c = 0, st = 0;
     if (A.n2 > 0) {
       u64 xs, xe;
       ordered_query(A, r, &xs, &xe);
-      const i64 started = lut_count_below<false>(A.kS, A.lutS, xe);
-      const i64 ended = lut_count_below<true>(A.kE, A.lutE, xs);
+      const i64 started = P.rec ? ordered_starts_below(P.rec, A.lutS, xe) : lut_count_below<false>(A.kS, A.lutS, xe);
+      const i64 ended = P.rec ? ordered_ends_upto(P.ends32, A.lutE, xs) : lut_count_below<true>(A.kE, A.lutE, xs);
       c = started > ended ? (u32)(started - ended) : 0u;
+      st = (u32)started;
     }
     cnt_out[r] = c;
-    mine += c > 0 ? c : 1;  // how='left': a query without partner still yields one row
+    started_out[r] = st;
     biggest = c > biggest ? c : biggest;
   }
-  u64 tot;
-  u64 run = block_excl_sum_u64(mine, s_tmp, &tot);
-  if (threadIdx.x == 0) {
-    tile_tot[blockIdx.x] = tot;
-    if (tot >> 32) hdr[1] = 1;  // in-tile offsets are 32-bit
-  }
-  if (biggest > 0) atomicMax(reinterpret_cast<unsigned long long*>(hdr + 2), (unsigned long long)biggest);
+  __syncthreads();  // the counts of the whole tile are visible to the block
+  // offsets: every thread scans 8 consecutive rows (how='left': a query without partner still yields one row)
+  const i64 base = tile0 + (i64)threadIdx.x * SC_IPT;
+  u32 rows[SC_IPT];
+  u64 mine = 0;
 #pragma unroll
   for (int j = 0; j < SC_IPT; ++j) {
     const i64 r = base + j;
-    if (r < A.n1) {
-      loc_out[r] = (u32)run;
-      const u32 c = cnt_out[r];  // written by this thread above
-      run += c > 0 ? c : 1;
-    }
+    const u32 c = r < A.n1 ? cnt_out[r] : 0u;
+    rows[j] = r < A.n1 ? (c > 0 ? c : 1u) : 0u;
+    mine += rows[j];
+  }
+  u64 tot;
+  u64 run = block_excl_sum_u64(mine, s_tmp, &tot);
+  const u64 block_biggest = block_max_u64((u64)biggest, s_tmp);
+  if (threadIdx.x == 0) {
+    tile_tot[blockIdx.x] = tot;
+    if (tot >> 32) hdr[1] = 1;  // in-tile offsets are 32-bit
+    if (block_biggest > 0) atomicMax(reinterpret_cast<unsigned long long*>(hdr + 2), (unsigned long long)block_biggest);
+  }
+#pragma unroll
+  for (int j = 0; j < SC_IPT; ++j) {
+    const i64 r = base + j;
+    if (r < A.n1) loc_out[r] = (u32)run;
+    run += rows[j];
   }
 }
 
 // in-place heap sort of a long partner list (one thread; lists this long are rare)
-__device__ void ordered_heapsort(i64* v, i64 n) {
+template <typename T>
+__device__ void ordered_heapsort(T* v, i64 n) {
   auto sift = [&](i64 root, i64 end) {
     for (;;) {
       i64 child = 2 * root + 1;
       if (child >= end) return;
       if (child + 1 < end && v[child] < v[child + 1]) ++child;
       if (v[root] >= v[child]) return;
-      const i64 t = v[root];
+      const T t = v[root];
       v[root] = v[child];
       v[child] = t;
       root = child;
@@ -690,61 +756,123 @@ __device__ void ordered_heapsort(i64* v, i64 n) {
   };
   for (i64 i = n / 2 - 1; i >= 0; --i) sift(i, n);
   for (i64 end = n - 1; end > 0; --end) {
-    const i64 t = v[0];
+    const T t = v[0];
     v[0] = v[end];
     v[end] = t;
     sift(0, end);
   }
 }
 
-__global__ void __launch_bounds__(256)
-    ordered_emit_kernel(ClosestArgs A, const u32* __restrict__ cnt_in, const u32* __restrict__ loc_in,
+// One block = 256 consecutive queries, one per thread.  Every thread collects its partners -- the range of
+// the start order inside the query, then the walk over earlier targets that still reach it -- into its
+// stretch of a shared-memory staging area, sorted by row number; the block then writes its output rows
+// coalesced (a thread's own rows are only ~9 x 8 bytes: written from the threads directly, every 32-byte
+// sector of the result would be touched by four different store instructions).  A block whose queries have
+// more rows than the staging area holds writes from the threads.
+constexpr int OE_THREADS = 256;
+constexpr int OE_CAP = 4096;          // staged output rows per block (avg 2240 for the benchmark workload)
+constexpr u32 OE_NEAR_STEPS = 192;    // plain backward scan before the block-skipping walk takes over
+
+// One block = 256 consecutive queries.
+//   gather: one query per thread collects its partners UNSORTED into its stretch of a shared staging area --
+//           the range of the start order inside the query, then a backward scan over earlier targets that
+//           still reach it (their number is known, so the scan ends when all are found; a query whose
+//           partners lie far back hands over to the block-skipping walk of closest);
+//   rank:   every staged row, one per thread and step, counts the smaller rows of its own query: its rank is
+//           its place.  The work of ordering, sum of c^2, is the same as an insertion sort per query, but
+//           it is spread evenly over the block instead of leaving 255 threads waiting for the one query
+//           with 40 partners (36 % of the stall samples at the barrier, 30 % in the insertion loop before);
+//   write:  the block's rows leave coalesced.
+// A block whose queries have more rows than the staging area holds writes and sorts per thread in global memory.
+__global__ void __launch_bounds__(OE_THREADS)
+    ordered_emit_kernel(ClosestArgs A, Ordered32 P, const u32* __restrict__ cnt_in,
+                        const u32* __restrict__ started_in, const u32* __restrict__ loc_in,
                         const u64* __restrict__ spine, i64* __restrict__ ev1, i64* __restrict__ ev2) {
-  const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= A.n1) return;
-  const u32 c = cnt_in[r];
-  const i64 at = (i64)spine[r / SC_TILE] + loc_in[r];
-  if (c == 0) {
-    ev1[at] = r;
-    ev2[at] = -1;
-    return;
-  }
-  u64 xs, xe;
-  ordered_query(A, r, &xs, &xe);
-  const i64 lo = lut_count_below<false>(A.kS, A.lutS, xs);
-  const i64 hi = lut_count_below<false>(A.kS, A.lutS, xe);
-  const u32 n_inside = (u32)(hi - lo);  // targets starting inside the query
-  if (c <= ORDERED_SMALL) {
-    u32 ids[ORDERED_SMALL];
-    u32 k = 0;
-    auto put = [&](u32 id) {  // insertion keeps the list sorted by row number
-      u32 y = k++;
-      while (y > 0 && ids[y - 1] > id) {
-        ids[y] = ids[y - 1];
-        --y;
+  __shared__ u32 s_raw[OE_CAP];             // partner rows as gathered, 0xffffffff = none
+  __shared__ u32 s_sorted[OE_CAP];          // ... in row order within every query
+  __shared__ u8 s_own[OE_CAP];              // query of the row, relative to the block's first query
+  __shared__ u32 s_rel[OE_THREADS + 1];     // first staged row of every query
+  const u32 tid = threadIdx.x;
+  const i64 r0 = (i64)blockIdx.x * OE_THREADS;
+  const i64 r = r0 + tid;
+  const i64 r_last = min(r0 + OE_THREADS, A.n1) - 1;
+  // 256 consecutive queries lie inside one scan tile (2048 rows): offsets relative to the block's first row
+  const u32 loc0 = loc_in[r0];
+  const u32 c_last = cnt_in[r_last];
+  const u32 block_rows = loc_in[r_last] + (c_last > 0 ? c_last : 1u) - loc0;
+  const i64 out0 = (i64)spine[r0 / SC_TILE] + loc0;
+  const bool staged = block_rows <= (u32)OE_CAP;
+  s_rel[tid] = block_rows;  // queries past the end of the input
+  if (tid == 0) s_rel[OE_THREADS] = block_rows;
+  if (r < A.n1) {
+    const u32 c = cnt_in[r];
+    const u32 rel = loc_in[r] - loc0;
+    const i64 at = out0 + rel;
+    s_rel[tid] = rel;
+    if (c == 0) {
+      if (staged) {
+        s_raw[rel] = 0xffffffffu;
+        s_own[rel] = (u8)tid;
+      } else {
+        ev1[at] = r;
+        ev2[at] = -1;
       }
-      ids[y] = id;
-    };
-    for (u32 i = 0; i < n_inside && k < c; ++i) put(A.idS[lo + i]);
-    if (k < c)
-      walk_stabbing(A, lo, xs, [&](i64 m) {
-        put(A.idS[m]);
-        return k < c;
-      });
-    for (u32 i = 0; i < k; ++i) {
-      ev1[at + i] = r;
-      ev2[at + i] = ids[i];
+    } else {
+      u64 xs, xe;
+      ordered_query(A, r, &xs, &xe);
+      const i64 lo = P.rec ? ordered_starts_below(P.rec, A.lutS, xs) : lut_count_below<false>(A.kS, A.lutS, xs);
+      const i64 hi = (i64)started_in[r];
+      const u32 n_inside = hi > lo ? (u32)(hi - lo) : 0u;
+      u32 k = 0;
+      auto gather = [&](auto put) {
+        i64 from = lo;
+        if (P.rec) {
+          for (u32 i = 0; i < n_inside && k < c; ++i) put(P.rec[lo + i].z);
+          const u32 xs32 = (u32)xs;
+          i64 m = lo - 1;
+          for (u32 step = 0; k < c && m >= 0 && step < OE_NEAR_STEPS; step += 4, m -= 4) {
+            uint4 t[4];  // four records in flight: the loop is a chain of dependent round trips otherwise
+#pragma unroll
+            for (int q = 0; q < 4; ++q) t[q] = P.rec[m - q >= 0 ? m - q : 0];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (m - q >= 0 && k < c && t[q].y > xs32) put(t[q].z);
+          }
+          from = m + 1 > 0 ? m + 1 : 0;
+        } else {
+          for (u32 i = 0; i < n_inside && k < c; ++i) put(A.idS[lo + i]);
+        }
+        if (k < c)
+          walk_stabbing(A, from, xs, [&](i64 mm) {
+            put(A.idS[mm]);
+            return k < c;
+          });
+      };
+      if (staged) {
+        gather([&](u32 id) { s_raw[rel + k++] = id; });
+        for (u32 i = 0; i < c; ++i) s_own[rel + i] = (u8)tid;
+      } else {
+        gather([&](u32 id) { ev2[at + k++] = id; });
+        ordered_heapsort(ev2 + at, (i64)k);
+        for (u32 i = 0; i < k; ++i) ev1[at + i] = r;
+      }
     }
-  } else {
-    u32 k = 0;
-    for (u32 i = 0; i < n_inside && k < c; ++i) ev2[at + k++] = A.idS[lo + i];
-    if (k < c)
-      walk_stabbing(A, lo, xs, [&](i64 m) {
-        ev2[at + k++] = A.idS[m];
-        return k < c;
-      });
-    ordered_heapsort(ev2 + at, (i64)k);
-    for (u32 i = 0; i < k; ++i) ev1[at + i] = r;
+  }
+  if (!staged) return;  // block-uniform
+  __syncthreads();
+  for (u32 x = tid; x < block_rows; x += OE_THREADS) {
+    const u32 o = s_own[x];
+    const u32 a = s_rel[o], b = a + (s_rel[o + 1] - a);  // the query's rows: [a, b)
+    const u32 v = s_raw[x];
+    u32 rank = 0;
+    for (u32 j = a; j < b; ++j) rank += s_raw[j] < v;
+    s_sorted[a + rank] = v;
+  }
+  __syncthreads();
+  for (u32 x = tid; x < block_rows; x += OE_THREADS) {
+    const u32 id = s_sorted[x];
+    ev1[out0 + x] = r0 + s_own[x];
+    ev2[out0 + x] = id == 0xffffffffu ? -1ll : (i64)id;
   }
 }
 
@@ -820,10 +948,14 @@ static int ordered_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
     A.lutE = make_lut(w.lutE, n2, 0, 1ull << L.B, L.LB);
     BF_TRY(launch_lut_build(rS.keys, n2, nullptr, A.lutS, w.lutS, st, PC_COVERAGE));
     BF_TRY(launch_lut_build(rE.keys, n2, nullptr, A.lutE, w.lutE, st, PC_COVERAGE));
+    if (L.B <= 32)
+      BF_LAUNCH(PC_RUNMAX, 40 * n2, st,
+                ordered_pack32_kernel<<<(unsigned)ceil_div(n2, 256), 256, 0, st>>>(rS.keys, rS.vals, rE.keys, n2, L, w.rec, w.ends32));
   }
   BF_CUDA(cudaMemsetAsync(w.hdr, 0, 4 * sizeof(i64), st));
+  const Ordered32 P32 = {(n2 > 0 && L.B <= 32) ? w.rec : nullptr, w.ends32};
   const unsigned qtiles = (unsigned)scan_tiles((u64)n1);
-  BF_LAUNCH(PC_SEARCH, 36 * n1, st, ordered_count_kernel<<<qtiles, SC_THREADS, 0, st>>>(A, w.cnt, w.loc, w.spine, w.hdr));
+  BF_LAUNCH(PC_SEARCH, 36 * n1, st, ordered_count_kernel<<<qtiles, SC_THREADS, 0, st>>>(A, P32, w.cnt, w.started, w.loc, w.spine, w.hdr));
   BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.spine, (u64)qtiles, reinterpret_cast<u64*>(w.hdr)));
   i64 hdr[3];
   BF_CUDA(cudaMemcpyAsync(hdr, w.hdr, sizeof(hdr), cudaMemcpyDeviceToHost, st));
@@ -855,7 +987,8 @@ static int ordered_emit_impl(const OrderedPlan* plan, void* ws_ptr, i64* ev1, i6
   OrderedWS w;
   layout_ordered(arena, A.n1, A.n2, A.L.nb, &w);
   BF_LAUNCH(PC_EMIT, 28 * A.n1 + 20 * plan->n_rows, st,
-            ordered_emit_kernel<<<(unsigned)ceil_div(A.n1, 256), 256, 0, st>>>(A, w.cnt, w.loc, w.spine, ev1, ev2));
+            ordered_emit_kernel<<<(unsigned)ceil_div(A.n1, OE_THREADS), OE_THREADS, 0, st>>>(
+                A, Ordered32{(A.n2 > 0 && A.L.B <= 32) ? w.rec : nullptr, w.ends32}, w.cnt, w.started, w.loc, w.spine, ev1, ev2));
   return BF_OK;
 }
 
