@@ -592,7 +592,8 @@ struct OrderedWS {
   u32 *cnt, *loc;  // [n1] partners of every query, output offset inside its tile
   u32* started;    // [n1] #{targets starting before the query's end'} (end of its range in the start order)
   // axes up to 2^32 (any real genome): everything a query touches per target packed next to each other
-  uint4* rec;      // [n2] start order: x = linear start, y = linear end', z = row number
+  uint2* rec;      // [n2] start order: x = linear end', y = row number
+  u32* starts32;   // [n2] start order: linear start
   u32* ends32;     // [n2] end order: linear end'
   u64* spine;      // [tiles(n1) + 2]
   ScanState ss_tmp;
@@ -612,7 +613,8 @@ static void layout_ordered(Arena& a, i64 n1, i64 n2, i32 nb, OrderedWS* w) {
   w->cnt = a.take<u32>(n1 + 1);
   w->loc = a.take<u32>(n1 + 1);
   w->started = a.take<u32>(n1 + 1);
-  w->rec = a.take<uint4>(n2 + 1);
+  w->rec = a.take<uint2>(n2 + 1);
+  w->starts32 = a.take<u32>(n2 + 1);
   w->ends32 = a.take<u32>(n2 + 1);
   w->spine = a.take<u64>(scan_tiles((u64)(n1 > 0 ? n1 : 1)) + 2);
   w->ss_tmp = take_scan_state(a, (u64)scan_tiles((u64)(n2 > 0 ? n2 : 1)));
@@ -642,30 +644,33 @@ __device__ __forceinline__ void ordered_query(const ClosestArgs& A, i64 r, u64* 
 
 // Queries arrive in arbitrary order, so every array they touch is a random DRAM access (the target arrays of
 // the benchmark, 180 MB as 64-bit keys + ids + ends, do not fit the L2).  On axes up to 2^32 the targets are
-// repacked: 16-byte records in start order (start, end', row: a query's whole neighbourhood is a few adjacent
-// cache lines) and a 4-byte array of the ends in end order.
+// repacked: 8-byte records in start order (end', row: what the scan over a query's neighbourhood reads, a few
+// adjacent cache lines; 16-byte records with the start included read 26 GB per 1e8 queries, twice this) and
+// 4-byte arrays of the starts (start order) and the ends (end order) for the probes.
 struct Ordered32 {
-  const uint4* rec;   // null: the axis needs more than 32 bits, use the 64-bit arrays
+  const uint2* rec;   // null: the axis needs more than 32 bits, use the 64-bit arrays
+  const u32* starts32;
   const u32* ends32;
 };
 __global__ void __launch_bounds__(256)
     ordered_pack32_kernel(const u64* __restrict__ kS, const u32* __restrict__ idS, const u64* __restrict__ kE, i64 n,
-                          KeyLayout L, uint4* __restrict__ rec, u32* __restrict__ ends32) {
+                          KeyLayout L, uint2* __restrict__ rec, u32* __restrict__ starts32, u32* __restrict__ ends32) {
   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const u64 k = kS[i];
-  rec[i] = make_uint4((u32)key_cs(k, L), (u32)key_ce_adj(k, L), idS[i], 0u);
+  rec[i] = make_uint2((u32)key_ce_adj(k, L), idS[i]);
+  starts32[i] = (u32)key_cs(k, L);
   ends32[i] = (u32)(kE[i] >> L.LB);
 }
 // #{records with start < x} / #{ends <= x}: one table sector, then a search inside the bucket
-__device__ __forceinline__ i64 ordered_starts_below(const uint4* __restrict__ rec, const Lut& t, u64 x) {
+__device__ __forceinline__ i64 ordered_starts_below(const u32* __restrict__ starts32, const Lut& t, u64 x) {
   u64 b = x < t.base ? 0ull : (x - t.base) >> t.shift;
   if (b >= t.nbuckets) b = t.nbuckets - 1;
   i64 lo = t.tab[b], hi = t.tab[b + 1];
   if (x < t.base) lo = 0;
   while (lo < hi) {
     const i64 mid = lo + ((hi - lo) >> 1);
-    if ((u64)rec[mid].x < x)
+    if ((u64)starts32[mid] < x)
       lo = mid + 1;
     else
       hi = mid;
@@ -702,7 +707,7 @@ __global__ void __launch_bounds__(SC_THREADS)
     if (A.n2 > 0) {
       u64 xs, xe;
       ordered_query(A, r, &xs, &xe);
-      const i64 started = P.rec ? ordered_starts_below(P.rec, A.lutS, xe) : lut_count_below<false>(A.kS, A.lutS, xe);
+      const i64 started = P.rec ? ordered_starts_below(P.starts32, A.lutS, xe) : lut_count_below<false>(A.kS, A.lutS, xe);
       const i64 ended = P.rec ? ordered_ends_upto(P.ends32, A.lutE, xs) : lut_count_below<true>(A.kE, A.lutE, xs);
       c = started > ended ? (u32)(started - ended) : 0u;
       st = (u32)started;
@@ -820,23 +825,23 @@ __global__ void __launch_bounds__(OE_THREADS)
     } else {
       u64 xs, xe;
       ordered_query(A, r, &xs, &xe);
-      const i64 lo = P.rec ? ordered_starts_below(P.rec, A.lutS, xs) : lut_count_below<false>(A.kS, A.lutS, xs);
+      const i64 lo = P.rec ? ordered_starts_below(P.starts32, A.lutS, xs) : lut_count_below<false>(A.kS, A.lutS, xs);
       const i64 hi = (i64)started_in[r];
       const u32 n_inside = hi > lo ? (u32)(hi - lo) : 0u;
       u32 k = 0;
       auto gather = [&](auto put) {
         i64 from = lo;
         if (P.rec) {
-          for (u32 i = 0; i < n_inside && k < c; ++i) put(P.rec[lo + i].z);
+          for (u32 i = 0; i < n_inside && k < c; ++i) put(P.rec[lo + i].y);
           const u32 xs32 = (u32)xs;
           i64 m = lo - 1;
           for (u32 step = 0; k < c && m >= 0 && step < OE_NEAR_STEPS; step += 4, m -= 4) {
-            uint4 t[4];  // four records in flight: the loop is a chain of dependent round trips otherwise
+            uint2 t[4];  // four records in flight: the loop is a chain of dependent round trips otherwise
 #pragma unroll
             for (int q = 0; q < 4; ++q) t[q] = P.rec[m - q >= 0 ? m - q : 0];
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              if (m - q >= 0 && k < c && t[q].y > xs32) put(t[q].z);
+              if (m - q >= 0 && k < c && t[q].x > xs32) put(t[q].y);
           }
           from = m + 1 > 0 ? m + 1 : 0;
         } else {
@@ -950,10 +955,10 @@ static int ordered_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
     BF_TRY(launch_lut_build(rE.keys, n2, nullptr, A.lutE, w.lutE, st, PC_COVERAGE));
     if (L.B <= 32)
       BF_LAUNCH(PC_RUNMAX, 40 * n2, st,
-                ordered_pack32_kernel<<<(unsigned)ceil_div(n2, 256), 256, 0, st>>>(rS.keys, rS.vals, rE.keys, n2, L, w.rec, w.ends32));
+                ordered_pack32_kernel<<<(unsigned)ceil_div(n2, 256), 256, 0, st>>>(rS.keys, rS.vals, rE.keys, n2, L, w.rec, w.starts32, w.ends32));
   }
   BF_CUDA(cudaMemsetAsync(w.hdr, 0, 4 * sizeof(i64), st));
-  const Ordered32 P32 = {(n2 > 0 && L.B <= 32) ? w.rec : nullptr, w.ends32};
+  const Ordered32 P32 = {(n2 > 0 && L.B <= 32) ? w.rec : nullptr, w.starts32, w.ends32};
   const unsigned qtiles = (unsigned)scan_tiles((u64)n1);
   BF_LAUNCH(PC_SEARCH, 36 * n1, st, ordered_count_kernel<<<qtiles, SC_THREADS, 0, st>>>(A, P32, w.cnt, w.started, w.loc, w.spine, w.hdr));
   BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.spine, (u64)qtiles, reinterpret_cast<u64*>(w.hdr)));
@@ -988,7 +993,7 @@ static int ordered_emit_impl(const OrderedPlan* plan, void* ws_ptr, i64* ev1, i6
   layout_ordered(arena, A.n1, A.n2, A.L.nb, &w);
   BF_LAUNCH(PC_EMIT, 28 * A.n1 + 20 * plan->n_rows, st,
             ordered_emit_kernel<<<(unsigned)ceil_div(A.n1, OE_THREADS), OE_THREADS, 0, st>>>(
-                A, Ordered32{(A.n2 > 0 && A.L.B <= 32) ? w.rec : nullptr, w.ends32}, w.cnt, w.started, w.loc, w.spine, ev1, ev2));
+                A, Ordered32{(A.n2 > 0 && A.L.B <= 32) ? w.rec : nullptr, w.starts32, w.ends32}, w.cnt, w.started, w.loc, w.spine, ev1, ev2));
   return BF_OK;
 }
 

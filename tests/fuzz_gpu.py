@@ -60,6 +60,11 @@ def run(budget=120.0, seed=0, max_rounds=None, sizes1=(0, 1, 7, 300, 2500, 9000,
         closed = bool(rng.random() < 0.3)
         ev1, ev2, _ = engine.overlap_intidxs(g1, s1, e1, g2, s2, e2, nb, how=how, closed=closed)
         same((ev1, ev2), oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, nb, how=how, closed=closed), f"overlap {how} closed={closed}", cfg)
+        if how == "left" and not closed:  # the same left join born in (row1, row2) order
+            a, b, _ = engine.overlap_ordered(g1, s1, e1, g2, s2, e2, nb)
+            w1, w2 = oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, nb, how="left")
+            o = np.lexsort([np.where(w2 < 0, n2 + 1, w2), w1])
+            same((a, b), (w1[o], w2[o]), "overlap_ordered", cfg)
         cnt = engine.count_overlaps(g1, s1, e1, g2, s2, e2, nb, closed=closed)
         i, _ = oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, nb, how="inner", closed=closed)
         same((cnt,), (np.bincount(i, minlength=n1),), "count_overlaps", cfg)
