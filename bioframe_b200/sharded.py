@@ -10,10 +10,12 @@ queries is valid because every query-side quantity depends only on the
 replicated targets.
 
 Row order of the concatenated result: rank-major, inside a rank the reference's
-order for that shard.  For how='left' the frame-level `keep_order=True` sort
-(by query row, then target row) makes the final frame identical to the
-single-GPU one; for the other joins the pair SET is identical and the order is
-(shard, group, A-block, B-block)."""
+order for that shard.  For how='left' with keep_order=True (the default of
+`bioframe.overlap`) `overlap_ordered_sharded` yields every shard in (query row,
+target row) order, so the concatenation is the single-GPU result bit for bit; the
+same holds for the other per-query results (coverage, count_overlaps, subtract,
+closest per query).  For the block order of how='inner' the pair SET is identical
+and the order is (shard, group, A-block, B-block)."""
 from __future__ import annotations
 
 import numpy as np
@@ -88,6 +90,36 @@ def count_overlaps_sharded(grp1, start1, end1, grp2, start2, end2, n_groups, eng
         from . import engine as engine
     _replicate([grp2, start2, end2], broadcast, src, group)
     return engine.count_overlaps(grp1, start1, end1, grp2, start2, end2, n_groups)
+
+
+def overlap_ordered_sharded(grp1, start1, end1, row_offset, grp2, start2, end2, n_groups, engine=None, group=None,
+                            broadcast=True, src=0):
+    """This rank's slice of `overlap(how='left', keep_order=True)` at the index level (ops.py:455-456, 549-550):
+    rows in (query row, target row) order with GLOBAL query row numbers.  The result is per query, so the
+    concatenation of the shards in rank order IS the single-GPU result, bit for bit, with the one broadcast
+    (first bullet).  Returns (events1, events2)."""
+    if engine is None:
+        from . import engine as engine
+    _replicate([grp2, start2, end2], broadcast, src, group)
+    ev1, ev2, _ = engine.overlap_ordered(grp1, start1, end1, grp2, start2, end2, n_groups)
+    ev1 = torch.as_tensor(ev1)
+    if int(row_offset):
+        ev1 = ev1 + int(row_offset)  # every row carries a query (never -1)
+    return ev1, torch.as_tensor(ev2)
+
+
+def subtract_sharded(grp1, start1, end1, row_offset, grp2, start2, end2, n_groups, engine=None, group=None,
+                     broadcast=True, src=0):
+    """This rank's slice of `subtract` (ops.py:1243-1330): the pieces of its own query rows, rows numbered
+    globally; concatenate the shards in rank order.  Returns (row, start, end, sub_index)."""
+    if engine is None:
+        from . import engine as engine
+    _replicate([grp2, start2, end2], broadcast, src, group)
+    row, ps, pe, sub = engine.subtract(grp1, start1, end1, grp2, start2, end2, n_groups)
+    row = torch.as_tensor(row)
+    if int(row_offset):
+        row = row + int(row_offset)
+    return row, torch.as_tensor(ps), torch.as_tensor(pe), torch.as_tensor(sub)
 
 
 def closest_sharded(grp1, start1, end1, row_offset, grp2, start2, end2, n_groups, engine=None, group=None,

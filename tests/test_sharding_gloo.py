@@ -47,8 +47,11 @@ def _worker(rank, world, port, how, out_dir):
         cov = sharded.coverage_sharded(*q, t[0], t[1], t[2], 24, engine=eng, broadcast=False)
         cnt = sharded.count_overlaps_sharded(*q, t[0], t[1], t[2], 24, engine=eng, broadcast=False)
         c1, c2, _ = sharded.closest_sharded(q[0], q[1], q[2], lo, t[0], t[1], t[2], 24, engine=eng, broadcast=False, k=2)
+        o1, o2 = sharded.overlap_ordered_sharded(q[0], q[1], q[2], lo, t[0], t[1], t[2], 24, engine=eng, broadcast=False)
+        sub = sharded.subtract_sharded(q[0], q[1], q[2], lo, t[0], t[1], t[2], 24, engine=eng, broadcast=False)
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), ev1=ev1.numpy(), ev2=ev2.numpy(), off=off, total=total,
-                 cov=np.asarray(cov), cnt=np.asarray(cnt), c1=np.asarray(c1), c2=np.asarray(c2))
+                 cov=np.asarray(cov), cnt=np.asarray(cnt), c1=np.asarray(c1), c2=np.asarray(c2),
+                 o1=np.asarray(o1), o2=np.asarray(o2), sub=np.stack([np.asarray(x) for x in sub]))
     finally:
         dist.destroy_process_group()
 
@@ -68,6 +71,14 @@ class _TensorEngine:
     def closest_intidxs(self, g1, s1, e1, g2, s2, e2, nb, **kw):
         a, b, n = self.mod.closest_intidxs(g1.numpy(), s1.numpy(), e1.numpy(), g2.numpy(), s2.numpy(), e2.numpy(), nb, **kw)
         return torch.from_numpy(a), torch.from_numpy(b), n
+
+    def overlap_ordered(self, g1, s1, e1, g2, s2, e2, nb):
+        a, b, n = self.mod.overlap_ordered(g1.numpy(), s1.numpy(), e1.numpy(), g2.numpy(), s2.numpy(), e2.numpy(), nb)
+        return torch.from_numpy(a), torch.from_numpy(b), n
+
+    def subtract(self, g1, s1, e1, g2, s2, e2, nb):
+        return tuple(torch.from_numpy(np.asarray(x)) for x in
+                     self.mod.subtract(g1.numpy(), s1.numpy(), e1.numpy(), g2.numpy(), s2.numpy(), e2.numpy(), nb))
 
     def overlap_intidxs(self, g1, s1, e1, g2, s2, e2, nb, how="inner", closed=False, row_offset1=0, row_offset2=0):
         a, b, n = self.mod.overlap_intidxs(g1.numpy(), s1.numpy(), e1.numpy(), g2.numpy(), s2.numpy(), e2.numpy(), nb,
@@ -106,6 +117,13 @@ def test_sharded_overlap_world2(how, tmp_path):
     w1, w2 = oo.closest_intidxs_coded(g1, s1, e1, g2, s2, e2, 24, k=2)
     a, b = np.argsort(c1, kind="stable"), np.argsort(w1, kind="stable")
     assert np.array_equal(c1[a], w1[b]) and np.array_equal(c2[a], w2[b])
+    # keep_order left join and subtract: per query, so the plain concatenation is the single-process result
+    l1, l2 = oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, 24, how="left")
+    order = np.lexsort([np.where(l2 < 0, len(s2) + 1, l2), l1])
+    assert np.array_equal(np.concatenate([p["o1"] for p in parts]), l1[order])
+    assert np.array_equal(np.concatenate([p["o2"] for p in parts]), l2[order])
+    want_sub = np.stack(oo.subtract_coded(g1, s1, e1, g2, s2, e2, 24))
+    assert np.array_equal(np.concatenate([p["sub"] for p in parts], axis=1), want_sub)
 
 
 def test_shard_bounds():
