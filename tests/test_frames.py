@@ -92,9 +92,35 @@ def test_frame_glue_with_column_gathers_on_oracle_double(name, oracle_double, de
     _check(name)
 
 
+# keep_order left joins take the row-order kernel (bf_overlap_ordered_*); a row with a huge partner list sends the
+# glue to the general path (all pairs + bf_sort_pairs): force that path and expect the same frames
+KEEP_ORDER_CASES = sorted(n for n, c in CASES.items()
+                          if c["fn"] in ("subtract", "trim", "assign_view")
+                          or (c["fn"] == "overlap" and c["kwargs"].get("how", "left") == "left"
+                              and c["kwargs"].get("keep_order") is not False))
+
+
+@pytest.fixture
+def general_keep_order_path(monkeypatch):
+    import bioframe_b200.ops as ops
+
+    monkeypatch.setattr(ops, "_ORDERED_MAX_PARTNERS", -1)
+
+
+@pytest.mark.parametrize("name", KEEP_ORDER_CASES)
+def test_frame_glue_keep_order_general_path_on_oracle_double(name, oracle_double, general_keep_order_path):
+    _check(name)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_frame_on_cuda_engine(name):
+    _check(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", KEEP_ORDER_CASES)
+def test_frame_keep_order_general_path_on_cuda_engine(name, general_keep_order_path):
     _check(name)
 
 
