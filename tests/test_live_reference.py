@@ -1,0 +1,103 @@
+"""Live differential test against the reference itself (build container only: /root/reference is not on the GPU
+box, where this module skips).  Random frames go through the reference's public functions and through this
+repo's frame-level functions -- on the oracle-backed test double here, so what is compared is the reference's
+pandas/numpy pipeline against oracle + glue.  Complements the frozen goldens of tests/golden/ with fresh draws."""
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import GOLDEN
+
+REF = "/root/reference/src"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    sys.path.insert(0, GOLDEN)
+    from make_golden import import_reference
+
+    return import_reference()
+
+
+@pytest.fixture
+def ours(monkeypatch):
+    import oracle_engine
+
+    import bioframe_b200 as bf
+    import bioframe_b200.core.arrops as arrops
+    import bioframe_b200.ops as ops
+
+    monkeypatch.setattr(ops, "_engine", oracle_engine)
+    monkeypatch.setattr(arrops, "_engine", oracle_engine)
+    old = pd.get_option("future.infer_string")
+    pd.set_option("future.infer_string", False)
+    yield bf
+    pd.set_option("future.infer_string", old)
+
+
+def _frame(rng, n, chroms=("chr1", "chr2", "chrX"), span=600, maxlen=50, p_point=0.1):
+    s = rng.integers(0, span, n)
+    ln = rng.integers(1, maxlen, n)
+    ln[rng.random(n) < p_point] = 0
+    return pd.DataFrame({"chrom": rng.choice(np.array(chroms, dtype=object), n), "start": s, "end": s + ln,
+                         "score": rng.integers(0, 5, n)})
+
+
+def _canon(df):
+    key = df.astype(str).apply(lambda r: "\x1f".join(r.values), axis=1) if len(df) else pd.Series([], dtype=str)
+    return df.iloc[np.argsort(key.values, kind="stable")].reset_index(drop=True)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_live_overlap_family(ref, ours, seed):
+    rng = np.random.default_rng(1000 + seed)
+    df1, df2 = _frame(rng, int(rng.integers(1, 120))), _frame(rng, int(rng.integers(1, 90)), chroms=("chr2", "chrX", "chr9"))
+    # row order pinned by the reference: left join with keep_order, and everything per-query
+    for kw in (dict(how="left"), dict(how="left", return_index=True, return_overlap=True, suffixes=("_q", "_t"))):
+        pd.testing.assert_frame_equal(ours.overlap(df1, df2, **kw), ref.overlap(df1, df2, **kw))
+    for how in ("inner", "right", "outer"):  # chromosome blocks come in set order: compare as row sets
+        got, want = ours.overlap(df1, df2, how=how, return_index=True), ref.overlap(df1, df2, how=how, return_index=True)
+        pd.testing.assert_frame_equal(_canon(got), _canon(want))
+    pd.testing.assert_frame_equal(ours.coverage(df1.copy(), df2), ref.coverage(df1.copy(), df2))
+    pd.testing.assert_frame_equal(ours.count_overlaps(df1.copy(), df2), ref.count_overlaps(df1.copy(), df2))
+    pd.testing.assert_frame_equal(ours.setdiff(df1, df2), ref.setdiff(df1, df2))
+    pd.testing.assert_frame_equal(ours.subtract(df1, df2, return_index=True), ref.subtract(df1, df2, return_index=True))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_live_cluster_family(ref, ours, seed):
+    rng = np.random.default_rng(2000 + seed)
+    df = _frame(rng, int(rng.integers(1, 150)))
+    for md in (0, None, 3, 40):
+        pd.testing.assert_frame_equal(ours.cluster(df, min_dist=md), ref.cluster(df, min_dist=md))
+        pd.testing.assert_frame_equal(ours.merge(df, min_dist=md), ref.merge(df, min_dist=md))
+    pd.testing.assert_frame_equal(ours.complement(df), ref.complement(df))
+    view = {"chr1": 700, "chr2": 650, "chrX": 900}
+    pd.testing.assert_frame_equal(ours.complement(df, view_df=view), ref.complement(df, view_df=view))
+    pd.testing.assert_frame_equal(ours.trim(df, view_df={"chr1": 300, "chr2": 400, "chrX": 200}),
+                                  ref.trim(df, view_df={"chr1": 300, "chr2": 400, "chrX": 200}))
+    pd.testing.assert_frame_equal(ours.mark_runs(df, "score", allow_overlaps=True), ref.mark_runs(df, "score", allow_overlaps=True))
+    pd.testing.assert_frame_equal(ours.merge_runs(df, "score", allow_overlaps=True), ref.merge_runs(df, "score", allow_overlaps=True))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_live_closest_tie_free(ref, ours, seed):
+    """closest picks among equal ends / starts through an unstable argsort in the reference: tie-free draws."""
+    rng = np.random.default_rng(3000 + seed)
+
+    def tie_free(n, chroms):
+        s = rng.choice(np.arange(0, 5000, 7), n, replace=False)
+        e = s + 1 + 7 * rng.integers(0, 5, n) + rng.integers(0, 6, n)
+        while len(set(e)) < n:
+            dup = pd.Series(e).duplicated().values
+            e[dup] = s[dup] + 1 + rng.integers(0, 80, dup.sum())
+        return pd.DataFrame({"chrom": rng.choice(np.array(chroms, dtype=object), n), "start": s, "end": e})
+
+    df1, df2 = tie_free(60, ("chr1", "chr2")), tie_free(45, ("chr2", "chr1", "chr3"))
+    for kw in (dict(k=1), dict(k=3, return_overlap=True, return_index=True), dict(k=2, ignore_overlaps=True),
+               dict(k=2, ignore_upstream=True), dict(k=1, ignore_downstream=True)):
+        pd.testing.assert_frame_equal(_canon(ours.closest(df1, df2, **kw)), _canon(ref.closest(df1, df2, **kw)))
