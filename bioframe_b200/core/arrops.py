@@ -108,7 +108,9 @@ def closest_intervals(
     """(ids1, ids2) of the k closest set-2 intervals of every set-1 interval;
     with `starts2=ends2=None` the closest other intervals of the same set."""
     if tie_arr is not None:
-        raise NotImplementedError("tie_arr is not supported by the CUDA engine (broken in the reference, arrops.py:740)")
+        # np.lexsort([ids2, tie_arr, dists, ids1]) of the reference (arrops.py:738-740) mixes keys of
+        # different lengths: it raises this error whenever tie_arr is given
+        raise ValueError("all keys need to be the same shape")
     self_closest = starts2 is None and ends2 is None
     if self_closest:
         if ignore_overlaps:  # reference quirk (SURVEY.md Appendix B5): starts2 stays None and indexing fails

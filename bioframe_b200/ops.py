@@ -352,7 +352,9 @@ def _closest_intidxs(
     ck1, sk1, ek1 = _get_default_colnames() if cols1 is None else cols1
     ck2, sk2, ek2 = _get_default_colnames() if cols2 is None else cols2
     if tie_breaking_col is not None:
-        raise NotImplementedError("tie_breaking_col is not supported by the CUDA engine")
+        # the reference hands the column to np.lexsort next to keys of another length (arrops.py:738-740)
+        # and fails with exactly this error whenever the argument is used
+        raise ValueError("all keys need to be the same shape")
     self_closest = (df2 is None) or (df2 is df1)
     if self_closest:
         if len(df1) == 1:

@@ -1,16 +1,15 @@
 """pytest plugin (loaded with `-p refsuite_plugin`) that runs the REFERENCE's own test files
-against this repo's implementation: the reference package is imported from /root/reference/src (with a
-stub matplotlib) and its six hot-path operations plus the two `_intidxs` helpers are replaced by
+against this repo's implementation: the reference package is imported from /root/reference/src -- on the GPU
+box from the vendored, git-ignored baseline/_ref (oracle/make_ref.py) -- with a stub matplotlib, and its six
+hot-path operations plus the two `_intidxs` helpers are replaced by
 `bioframe_b200.ops`, so `bioframe.overlap(...)` in a reference test calls our glue -> our engine.
 Derived reference ops (subtract, setdiff, count_overlaps, trim, ...) then run on top of ours too.
-Without a GPU the engine is the oracle-backed test double (tests/oracle_engine.py): that checks the
-pandas glue; with a GPU it is the CUDA engine."""
+REFSUITE_ENGINE=oracle: the engine is the oracle-backed test double (tests/oracle_engine.py): that checks the
+pandas glue.  REFSUITE_ENGINE=cuda: the CUDA engine (fails loudly without a GPU).  Unset: cuda when available."""
 import os
 import sys
-import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF_SRC = "/root/reference/src"
 
 
 def _install():
@@ -20,18 +19,16 @@ def _install():
         import pandas as pd
 
         pd.set_option("future.infer_string", False)
-    stub = tempfile.mkdtemp(prefix="mplstub")
-    os.makedirs(os.path.join(stub, "matplotlib"))
-    for name, body in (("__init__", ""), ("pyplot", ""), ("colors", "def to_rgb(c):\n    return (0.0, 0.0, 0.0)\n")):
-        with open(os.path.join(stub, "matplotlib", name + ".py"), "w") as f:
-            f.write(body)
-    sys.path[:0] = [stub, REF_SRC, ROOT, os.path.join(ROOT, "tests")]
-    import bioframe
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    from conftest import import_reference
+
+    bioframe = import_reference()
     import bioframe.ops as ref_ops
 
     import bioframe_b200.core.arrops as our_arrops
     import bioframe_b200.ops as our_ops
 
+    want = os.environ.get("REFSUITE_ENGINE", "")
     use_gpu = False
     try:
         import torch
@@ -39,6 +36,10 @@ def _install():
         use_gpu = torch.cuda.is_available()
     except Exception:
         pass
+    if want == "cuda" and not use_gpu:
+        raise RuntimeError("REFSUITE_ENGINE=cuda but no CUDA device")
+    if want == "oracle":
+        use_gpu = False
     if not use_gpu:
         import oracle_engine
 

@@ -1,7 +1,8 @@
-"""Live differential test against the reference itself (build container only: /root/reference is not on the GPU
-box, where this module skips).  Random frames go through the reference's public functions and through this
-repo's frame-level functions -- on the oracle-backed test double here, so what is compared is the reference's
-pandas/numpy pipeline against oracle + glue.  Complements the frozen goldens of tests/golden/ with fresh draws."""
+"""Live differential test against the reference itself.  Random frames go through the reference's public
+functions and through this repo's frame-level functions -- every case twice: on the oracle-backed test double
+(CPU: the reference's pandas/numpy pipeline against oracle + glue) and, marked gpu, on the CUDA engine (GPU box,
+reference = the vendored git-ignored copy of oracle/make_ref.py).  Complements the frozen goldens of
+tests/golden/ with fresh draws."""
 import os
 import sys
 
@@ -9,30 +10,31 @@ import numpy as np
 import pandas as pd
 import pytest
 
-from conftest import GOLDEN
+from conftest import has_cuda, import_reference, reference_paths
 
-REF = "/root/reference/src"
-pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+pytestmark = pytest.mark.skipif(reference_paths()[0] is None, reason="reference checkout / vendored copy not present")
 
 
 @pytest.fixture(scope="module")
 def ref():
-    sys.path.insert(0, GOLDEN)
-    from make_golden import import_reference
-
     return import_reference()
 
 
-@pytest.fixture
-def ours(monkeypatch):
-    import oracle_engine
-
+@pytest.fixture(params=["oracle", pytest.param("cuda", marks=pytest.mark.gpu)])
+def ours(monkeypatch, request):
     import bioframe_b200 as bf
     import bioframe_b200.core.arrops as arrops
     import bioframe_b200.ops as ops
 
-    monkeypatch.setattr(ops, "_engine", oracle_engine)
-    monkeypatch.setattr(arrops, "_engine", oracle_engine)
+    if request.param == "oracle":
+        import oracle_engine
+
+        monkeypatch.setattr(ops, "_engine", oracle_engine)
+        monkeypatch.setattr(arrops, "_engine", oracle_engine)
+    else:
+        from bioframe_b200 import engine
+
+        assert has_cuda() and ops._engine is engine and arrops._engine is engine
     old = pd.get_option("future.infer_string")
     pd.set_option("future.infer_string", False)
     yield bf
