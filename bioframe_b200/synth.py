@@ -104,3 +104,27 @@ def to_frame(codes, starts, ends, categorical=False):
     else:
         chrom = names[codes]
     return pd.DataFrame({"chrom": chrom, "start": starts, "end": ends})
+
+
+def make_tie_free(n, seed, kind="geom1k", chrom_ids=None):
+    """`make_intervals` with (chrom, start) and (chrom, end) both unique: rows that collide are drawn again.
+    For `closest`, whose choice among targets with equal ends / equal starts is undefined in the reference
+    (unstable argsort, arrops.py:562, 580; SURVEY.md §8c ii)."""
+    codes, starts, ends = make_intervals(n, seed, kind, chrom_ids)
+    rng = np.random.default_rng(seed + 7919)
+    for _ in range(64):
+        ks = codes.astype(np.int64) << 40 | starts
+        ke = codes.astype(np.int64) << 40 | ends
+        bad = np.zeros(n, dtype=bool)
+        for key in (ks, ke):
+            order = np.argsort(key, kind="stable")
+            dup = np.zeros(n, dtype=bool)
+            dup[order[1:]] = key[order[1:]] == key[order[:-1]]
+            bad |= dup
+        m = int(bad.sum())
+        if m == 0:
+            return codes, starts, ends
+        lens = ends[bad] - starts[bad]
+        s, e = _place(rng, codes[bad], lens)
+        starts[bad], ends[bad] = s, e
+    raise RuntimeError("could not draw a tie-free set")
