@@ -29,6 +29,10 @@ class Plan(C.Structure):
     _fields_ = [("opaque", C.c_int64 * 96)]
 
 
+class SortedSetStruct(C.Structure):
+    _fields_ = [("opaque", C.c_int64 * 32)]
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -55,6 +59,21 @@ SIGNATURES = {
     ),
     "bf_overlap_emit": (C.c_int, [C.POINTER(Plan), _p, _p, _p, _p]),
     "bf_overlap_set_row_offsets": (C.c_int, [C.POINTER(Plan), _i64, _i64]),
+    "bf_extent_words": (_sz, [_i32]),
+    "bf_extent_workspace_bytes": (_sz, [_i32]),
+    "bf_extent_measure": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _sz, _p, _p, C.POINTER(_i32)]),
+    "bf_sorted_set_bytes": (_sz, [_i64, _i32, _i32]),
+    "bf_overlap_prepare_set": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _p, _sz, _p, C.POINTER(SortedSetStruct)]),
+    "bf_overlap_adopt_set": (C.c_int, [_p, _i64, _i32, _p, _sz, _p, C.POINTER(SortedSetStruct)]),
+    "bf_sorted_set_buffers": (C.c_int, [C.POINTER(SortedSetStruct), C.POINTER(_p), C.POINTER(_p), C.POINTER(_i64)]),
+    "bf_overlap_prepared_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "bf_overlap_count_prepared": (
+        C.c_int,
+        [C.POINTER(SortedSetStruct), C.POINTER(SortedSetStruct), _p, _p, _i32, _i32, _p, _p, _sz, C.POINTER(Plan), _p,
+         C.POINTER(_i64), C.POINTER(_i64)],
+    ),
+    "bf_overlap_set_halo_rows": (C.c_int, [C.POINTER(Plan), _i64, _p]),
+    "bf_overlap_group_counts": (C.c_int, [C.POINTER(Plan), _p, _p, _p]),
     "bf_overlap_ordered_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "bf_overlap_ordered_count": (
         C.c_int,

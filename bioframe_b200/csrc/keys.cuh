@@ -351,6 +351,53 @@ static int measure_layout(const RowSet* sets, int n_sets, i32 nb, int point_adju
   return BF_ERR_RANGE;
 }
 
+// ---- extent as a host-side record that merges across sets and ranks ----
+// Sets that are sorted apart from each other -- the targets on rank 0, the query shard of every rank
+//  -- must still be packed with ONE key layout.  The extent of a set is therefore also
+// available as a small host array of int64 words that merges by elementwise MAX (np.maximum on the
+// host, all_reduce(MAX) across ranks):
+//   w[0] = ~cmin   w[1] = cmax   w[2] = largest start   w[3] = largest end' - start   w[4..7] = 0
+//   w[8 + g] = largest coordinate of group g (INT64_MIN: the group has no rows)
+constexpr int EXT_HDR = 8;
+static inline void extent_to_words(const Extent& x, const i64* gmax_host, i32 nb, bool empty, i64* w) {
+  for (int i = 0; i < EXT_HDR; ++i) w[i] = 0;
+  w[0] = empty ? I64_MIN : ~x.cmin;
+  w[1] = empty ? I64_MIN : x.cmax;
+  w[2] = empty ? I64_MIN : x.smax;
+  w[3] = empty ? 0 : (x.lmax > (u64)I64_MAX ? I64_MAX : (i64)x.lmax);
+  for (i32 g = 0; g < nb; ++g) w[EXT_HDR + g] = empty ? I64_MIN : gmax_host[g];
+}
+// Layout from merged words; the same arithmetic as layout_offsets_kernel + make_key_layout.  goff_host gets
+// nb + 1 entries (the caller uploads them and sets L->goff).
+static inline int layout_from_words(const i64* w, i32 nb, int clamp_ends, KeyLayout* L, u64* goff_host) {
+  Extent x;
+  const bool empty = w[1] == I64_MIN;
+  x.cmin = empty ? 0 : ~w[0];
+  x.cmax = empty ? 0 : w[1];
+  x.smax = empty ? 0 : w[2];
+  x.lmax = (u64)w[3];
+  x.bad = 0;
+  x.unsorted = 0;
+  x.gmin = 0;
+  x.gmax = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const i64 cap = (attempt && !empty && x.smax < I64_MAX) ? x.smax + 1 : I64_MAX;
+    u64 run = 0;
+    for (i32 g = 0; g < nb; ++g) {
+      goff_host[g] = run;
+      const i64 gm = w[EXT_HDR + g];
+      if (!empty && gm != I64_MIN) run += (u64)(gm < cap ? gm : cap) - (u64)x.cmin + 1ull;
+    }
+    goff_host[nb] = run;
+    x.total = run;
+    x.endcap = cap;
+    const int rc = make_key_layout(x, nb, nullptr, L);
+    L->presorted = 0;
+    if (rc != BF_ERR_RANGE || !clamp_ends || attempt == 1) return rc;
+  }
+  return BF_ERR_RANGE;
+}
+
 // key modes (the `point_adjust` argument of pack_keys / sort_rows is a bit set)
 constexpr int KEY_POINT_ADJUST = 1;  // end' = end + (end == start)
 constexpr int KEY_BY_END = 2;        // high field = linear END coordinate (closest: left neighbours)

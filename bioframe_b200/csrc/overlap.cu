@@ -19,6 +19,7 @@
 #include "lookback.cuh"
 #include "sorted_set.cuh"
 #include "../../include/bioframe_b200.h"
+#include <vector>
 
 namespace bf {
 
@@ -27,9 +28,8 @@ constexpr i64 SEARCH_MIN_ROWS = 256;        // == SR_MIN_ROWS (smallest block of
 
 // ---------------------------------------------------------------- workspace
 struct SetWS {
-  SortBufs sb;   // sort double buffers + per-row temporaries + look-back state
-  u32 *lo;       // = sb.tmp4a after the sort: first partner position per sorted row
-  u32 *loc;      // = sb.tmp4b after the sort: [n] exclusive output offset inside the row's search tile
+  u32 *lo;       // [n] first partner position per sorted row
+  u32 *loc;      // [n] exclusive output offset inside the row's search tile
   u64 *tilepre;  // [search tiles + 1] exclusive output offset of every search tile; last = total
   int shift;     // log2(rows per search tile) of this side (host copy, set by launch_search)
   u64 *spine;    // [tiles]
@@ -43,6 +43,7 @@ struct SetWS {
 };
 
 struct OverlapWS {
+  SortBufs sb[2];  // sort double buffers + per-row temporaries (one-shot calls only: prepared sets bring their own)
   SetWS s[2];
   RadixScratch radix;
   LayoutScratch layout;
@@ -55,16 +56,17 @@ struct OverlapWS {
   i32 *pgrpA, *pgrpB;    // group of the first output of every emit block
   i64 *header;           // n_rows, n_pairs, nU1, nU2
   u64 *nU;               // [2] device-side unpaired totals (sort sizes)
+  i64 *ownpos;           // [4] owned sorted-position ranges of a query-sharded call: set 1 [0,1), set 2 [2,3)
 };
 
-static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS* w) {
+// Everything the count / emit stages need besides the sorted sets themselves.
+static void layout_count(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS* w) {
   const i64 n[2] = {n1, n2};
   const bool need[2] = {(how & 1) != 0, (how & 2) != 0};
   for (int k = 0; k < 2; ++k) {
     SetWS& s = w->s[k];
-    take_sort_bufs(a, n[k], &s.sb);
-    s.lo = s.sb.tmp4a;
-    s.loc = s.sb.tmp4b;
+    s.lo = a.take<u32>(n[k]);
+    s.loc = a.take<u32>(n[k]);
     s.tilepre = a.take<u64>(ceil_div(n[k], SEARCH_MIN_ROWS) + 2);
     s.shift = 0;
     s.spine = a.take<u64>(scan_tiles(n[k]) + 1);
@@ -85,7 +87,6 @@ static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS*
     }
   }
   w->radix = take_radix_scratch(a, (u64)(n1 > n2 ? n1 : n2));
-  w->layout = take_layout_scratch(a, nb);
   w->cumA = a.take<i64>(nb + 1);
   w->cumB = a.take<i64>(nb + 1);
   w->deltaA = a.take<i64>(nb + 1);
@@ -100,6 +101,15 @@ static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS*
   w->pgrpB = a.take<i32>(EMIT_CHUNK_BLOCKS + 1);
   w->header = a.take<i64>(8);
   w->nU = a.take<u64>(2);
+  w->ownpos = a.take<i64>(4);
+}
+
+// One-shot call (bf_overlap_count): the sort buffers of both sets live in the same workspace.
+static void layout_overlap(Arena& a, i64 n1, i64 n2, i32 nb, i32 how, OverlapWS* w) {
+  take_sort_bufs(a, n1, &w->sb[0]);
+  take_sort_bufs(a, n2, &w->sb[1]);
+  w->layout = take_layout_scratch(a, nb);
+  layout_count(a, n1, n2, nb, how, w);
 }
 
 struct OverlapPlan {  // lives in the caller's bf_plan
@@ -111,6 +121,9 @@ struct OverlapPlan {  // lives in the caller's bf_plan
   i64 totA, totB;
   i32 shift1, shift2;  // log2(rows per search tile) of the two sides
   i64 row_off1, row_off2;  // added to every reported row number of set 1 / set 2 (query-sharded callers)
+  i32 prepared;            // 1: produced by bf_overlap_count_prepared (workspace without sort buffers)
+  u32 n_own1;              // rows of set 1 at and above this local row number are halo rows ...
+  const i64* halo_ids;     // ... whose global row numbers are halo_ids[row - n_own1] (device; query-sharded callers)
   // sorted results (pointers into the workspace)
   u64 *key1, *key2;
   u32 *id1, *id2;
@@ -263,7 +276,7 @@ __global__ void __launch_bounds__(SC_THREADS, 6)
                         const u64* __restrict__ other, i64 m, const u64* __restrict__ other_pmax,
                         const i64* __restrict__ bracket, KeyLayout L, int closed, u32* __restrict__ lo_out,
                         u32* __restrict__ loc_out, u64* __restrict__ tile_tot, i64* __restrict__ overflow,
-                        u8* __restrict__ rowflag) {
+                        u8* __restrict__ rowflag, const i64* __restrict__ ownpos) {
   constexpr int TILE = SC_THREADS * IPT;
   __shared__ u32 s_rel[SR_STAGE];
   __shared__ u64 s_tmp[8];
@@ -380,6 +393,18 @@ __global__ void __launch_bounds__(SC_THREADS, 6)
       lo32[j] = (u32)lo;
     }
   }
+  if (ownpos) {
+    // query-sharded call: only rows inside this shard's owned range of sorted positions produce output --
+    // queries outside it are halo rows (they only serve as partners in the B block), targets outside it
+    // have their B block written by the shard that owns them
+    const i64 own_lo = ownpos[B_SIDE ? 2 : 0], own_hi = ownpos[B_SIDE ? 3 : 1];
+#pragma unroll
+    for (int j = 0; j < IPT; ++j)
+      if (base + j < own_lo || base + j >= own_hi) {
+        cnt[j] = 0;
+        lo32[j] = 0xffffffffu;  // marks "not owned" for the unpaired-row check below
+      }
+  }
   if (FLAGS) {
     // rows without a pair of their own still have a partner if an earlier interval of the other set
     // reaches past their start (running max of end').  Done after the search loop
@@ -387,13 +412,13 @@ __global__ void __launch_bounds__(SC_THREADS, 6)
     u64 pm[IPT];
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
-      const bool ask = base + j < n && cnt[j] == 0 && lo32[j] > 0;
+      const bool ask = base + j < n && cnt[j] == 0 && lo32[j] > 0 && lo32[j] != 0xffffffffu;
       pm[j] = ask ? other_pmax[lo32[j] - 1] : 0ull;
     }
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
       const i64 p = base + j;
-      if (p < n && cnt[j] == 0) {
+      if (p < n && cnt[j] == 0 && lo32[j] != 0xffffffffu) {
         const u64 xs = key_cs(key[j], L);
         const bool partner = lo32[j] > 0 && (closed ? (pm[j] >= xs) : (pm[j] > xs));
         if (!partner) rowflag[mine_id[p]] = 1;  // per-group counts come later from the compacted list
@@ -520,8 +545,10 @@ __global__ void __launch_bounds__(EM_THREADS, 8)
                       const u32* __restrict__ owner_id, const u32* __restrict__ other_id, i64 total,
                       i64 block0, const i64* __restrict__ part, const i32* __restrict__ pgrp,
                       const i64* __restrict__ cum, const i64* __restrict__ delta, i32 nb, i64 off1, i64 off2,
-                      i64* __restrict__ ev1, i64* __restrict__ ev2) {
+                      u32 n_own1, const i64* __restrict__ halo_ids, i64* __restrict__ ev1, i64* __restrict__ ev2) {
   __shared__ EmitItem s_item[EM_TILE + 2];
+  // global row number of a set-1 row listed as a partner (B side only: owners of the A side are never halo rows)
+  auto row1 = [&](u32 id) -> i64 { return id < n_own1 ? (i64)id + off1 : halo_ids[id - n_own1]; };
   __shared__ __align__(16) u16 s_owner[EM_TILE];  // owner (index into s_item) of every output slot
   __shared__ u32 s_wmax[EM_THREADS / 32];
   const u32 tid = threadIdx.x;
@@ -639,7 +666,7 @@ __global__ void __launch_bounds__(EM_THREADS, 8)
     if (par && tid == 0) {
       u32 own, oth;
       slot(0, own, oth);
-      out1[0] = (B_SIDE ? (i64)oth : (i64)own) + off1;
+      out1[0] = B_SIDE ? row1(oth) : (i64)own + off1;
       out2[0] = (B_SIDE ? (i64)own : (i64)oth) + off2;
     }
     const i32 last = nout - 1;
@@ -656,10 +683,10 @@ __global__ void __launch_bounds__(EM_THREADS, 8)
       for (int j = 0; j < 2; ++j) {
         const i32 x = par + 2 * ((h + j) * EM_THREADS + (i32)tid);
         if (x > last) continue;
-        const i64 a0 = (B_SIDE ? (i64)oth[2 * j] : (i64)own[2 * j]) + off1;
+        const i64 a0 = B_SIDE ? row1(oth[2 * j]) : (i64)own[2 * j] + off1;
         const i64 b0 = (B_SIDE ? (i64)own[2 * j] : (i64)oth[2 * j]) + off2;
         if (x + 1 <= last) {
-          const i64 a1 = (B_SIDE ? (i64)oth[2 * j + 1] : (i64)own[2 * j + 1]) + off1;
+          const i64 a1 = B_SIDE ? row1(oth[2 * j + 1]) : (i64)own[2 * j + 1] + off1;
           const i64 b1 = (B_SIDE ? (i64)own[2 * j + 1] : (i64)oth[2 * j + 1]) + off2;
           *reinterpret_cast<longlong2*>(out1 + x) = make_longlong2(a0, a1);
           *reinterpret_cast<longlong2*>(out2 + x) = make_longlong2(b0, b1);
@@ -679,7 +706,7 @@ __global__ void __launch_bounds__(EM_THREADS, 8)
         const u32 own = it.id, oth = other_id[it.src + (u32)x];
         const i64 t = t0 + x;
         const i64 row = t + delta[group_of(t, c_lo, (i64)c_hi + 1)];
-        ev1[row] = (B_SIDE ? (i64)oth : (i64)own) + off1;
+        ev1[row] = B_SIDE ? row1(oth) : (i64)own + off1;
         ev2[row] = (B_SIDE ? (i64)own : (i64)oth) + off2;
       }
     }
@@ -781,13 +808,14 @@ __global__ void __launch_bounds__(256) emit_unpaired_kernel(const u64* __restric
 
 template <bool B_SIDE, bool FLAGS, int IPT>
 static int launch_search_ipt(const SortResult& mine, i64 n, const SortResult& other, i64 m, SetWS& sw,
-                             const u64* other_pmax, const KeyLayout& L, int closed, i64* overflow, cudaStream_t st) {
+                             const u64* other_pmax, const KeyLayout& L, int closed, i64* overflow, const i64* ownpos,
+                             cudaStream_t st) {
   const i64 tiles = search_tiles(n, IPT);
   BF_LAUNCH(PC_SEARCH, 0, st, search_partition_kernel<B_SIDE><<<(unsigned)ceil_div(tiles + 1, 256), 256, 0, st>>>(
       mine.keys, n, other.keys, m, L, (i64)SC_THREADS * IPT, tiles, sw.bracket));
   BF_LAUNCH(PC_SEARCH, 16 * n, st, (search_count_kernel<B_SIDE, FLAGS, IPT><<<(unsigned)tiles, SC_THREADS, 0, st>>>(
       mine.keys, mine.vals, n, other.keys, m, other_pmax, sw.bracket, L, closed, sw.lo, sw.loc, sw.tilepre, overflow,
-      FLAGS ? sw.rowflag : nullptr)));
+      FLAGS ? sw.rowflag : nullptr, ownpos)));
   // tile totals -> exclusive tile offsets, grand total in tilepre[tiles]
   BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(sw.tilepre, (u64)tiles, sw.tilepre + tiles));
   int shift = 0;
@@ -797,7 +825,8 @@ static int launch_search_ipt(const SortResult& mine, i64 n, const SortResult& ot
 }
 template <bool B_SIDE>
 static int launch_search(const SortResult& mine, i64 n, const SortResult& other, i64 m, bool flags, SetWS& sw,
-                         const u64* other_pmax, const KeyLayout& L, int closed, i64* overflow, cudaStream_t st) {
+                         const u64* other_pmax, const KeyLayout& L, int closed, i64* overflow, const i64* ownpos,
+                         cudaStream_t st) {
   if (n == 0) {
     BF_CUDA(cudaMemsetAsync(sw.tilepre, 0, 2 * sizeof(u64), st));
     sw.shift = 8;
@@ -806,8 +835,8 @@ static int launch_search(const SortResult& mine, i64 n, const SortResult& other,
   const int ipt = pick_search_ipt(n, m);
 #define BF_SEARCH_CASE(I)                                                                                          \
   case I:                                                                                                          \
-    return flags ? launch_search_ipt<B_SIDE, true, I>(mine, n, other, m, sw, other_pmax, L, closed, overflow, st)  \
-                 : launch_search_ipt<B_SIDE, false, I>(mine, n, other, m, sw, other_pmax, L, closed, overflow, st);
+    return flags ? launch_search_ipt<B_SIDE, true, I>(mine, n, other, m, sw, other_pmax, L, closed, overflow, ownpos, st)  \
+                 : launch_search_ipt<B_SIDE, false, I>(mine, n, other, m, sw, other_pmax, L, closed, overflow, ownpos, st);
   switch (ipt) {
     BF_SEARCH_CASE(8)
     BF_SEARCH_CASE(4)
@@ -818,51 +847,34 @@ static int launch_search(const SortResult& mine, i64 n, const SortResult& other,
 #undef BF_SEARCH_CASE
 }
 
-static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64 n1, const i32* grp2,
-                              const i64* s2, const i64* e2, i64 n2, i32 nb, i32 how, i32 closed,
-                              void* ws_ptr, size_t ws_bytes, OverlapPlan* plan, cudaStream_t st) {
-  if (n1 < 0 || n2 < 0 || nb < 1 || how < 0 || how > 3 || !plan) {
-    set_error("bf_overlap_count: bad argument (n1=%lld n2=%lld n_groups=%d how=%d)", (long long)n1,
-              (long long)n2, nb, how);
-    return BF_ERR_ARG;
-  }
-  if (n1 >= (1ll << 31) || n2 >= (1ll << 31)) {
-    set_error("bf_overlap_count: more than 2^31-1 rows in one set");
-    return BF_ERR_RANGE;
-  }
-  if ((n1 > 0 && (!s1 || !e1)) || (n2 > 0 && (!s2 || !e2)) || (nb > 1 && ((n1 > 0 && !grp1) || (n2 > 0 && !grp2)))) {
-    set_error("bf_overlap_count: null input pointer");
-    return BF_ERR_ARG;
-  }
-  Arena measure(nullptr);
-  OverlapWS w;
-  layout_overlap(measure, n1, n2, nb, how, &w);
-  if (!ws_ptr || ws_bytes < measure.off) {
-    set_error("bf_overlap_count: workspace %zu bytes < required %zu", ws_bytes, measure.off);
-    return BF_ERR_WORKSPACE;
-  }
-  Arena arena(ws_ptr);
-  layout_overlap(arena, n1, n2, nb, how, &w);
+// Sorted-position ranges a query-sharded call owns: rows whose (group, start) lies in
+// [(g_lo, s_lo), (g_hi, s_hi)) in lexicographic order.  One thread; the groups lie end to end on the linear
+// axis, so the bounds become two linear coordinates and four binary searches.
+__global__ void own_positions_kernel(const u64* __restrict__ key1, i64 n1, const u64* __restrict__ key2, i64 n2,
+                                     KeyLayout L, i64 g_lo, i64 s_lo, i64 g_hi, i64 s_hi, i64* __restrict__ ownpos) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  auto linear = [&](i64 g, i64 s) -> u64 {
+    if (g >= L.nb) return L.goff[L.nb];
+    if (g < 0) return 0ull;
+    const u64 lo = L.goff[g], hi = L.goff[g + 1];
+    if (s <= (i64)L.cmin) return lo;
+    const u64 off = (u64)s - L.cmin;
+    return off >= hi - lo ? hi : lo + off;
+  };
+  const u64 c_lo = linear(g_lo, s_lo), c_hi = linear(g_hi, s_hi);
+  ownpos[0] = lower_bound_by(0, n1, [&](i64 q) { return key_cs(key1[q], L) < c_lo; });
+  ownpos[1] = lower_bound_by(0, n1, [&](i64 q) { return key_cs(key1[q], L) < c_hi; });
+  ownpos[2] = lower_bound_by(0, n2, [&](i64 q) { return key_cs(key2[q], L) < c_lo; });
+  ownpos[3] = lower_bound_by(0, n2, [&](i64 q) { return key_cs(key2[q], L) < c_hi; });
+}
+
+// Everything after the two sorts: segments, running maxima, search + count, unpaired lists, offset table.
+// `own` (host, 4 words or null): (g_lo, s_lo, g_hi, s_hi) of a query-sharded call.
+static int count_sorted(OverlapWS& w, const KeyLayout& L, const SortResult& r1, i64 n1, const SortResult& r2, i64 n2,
+                        const i32* grp1, const i32* grp2, i32 nb, i32 how, i32 closed, const i64* own,
+                        OverlapPlan* plan, cudaStream_t st) {
   const bool need1 = how & 1, need2 = how & 2;
-
-  plan->magic = 0;
-  plan->n1 = n1;
-  plan->n2 = n2;
-  plan->nb = nb;
-  plan->how = how;
-  plan->closed = closed;
-  plan->ready = 0;
-  plan->row_off1 = plan->row_off2 = 0;
-
-  // ---- coordinate extent, group code check, key layout (one small D2H) ----
-  const RowSet sets[2] = {{grp1, s1, e1, n1}, {grp2, s2, e2, n2}};
-  KeyLayout L;
-  BF_TRY(measure_layout(sets, 2, nb, 1, 1, w.layout, st, &L, "bf_overlap_count"));
   plan->L = L;
-  // ---- sort both sets ----
-  SortResult r1, r2;
-  BF_TRY(sort_rows(nb > 1 ? grp1 : nullptr, s1, e1, n1, L, KEY_POINT_ADJUST | presorted_mode(L, 0), w.s[0].sb, w.radix, st, &r1));
-  BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, KEY_POINT_ADJUST | presorted_mode(L, 1), w.s[1].sb, w.radix, st, &r2));
   plan->key1 = r1.keys;
   plan->id1 = r1.vals;
   plan->key2 = r2.keys;
@@ -872,6 +884,12 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   const unsigned seg_grid = (unsigned)ceil_div(nb + 1, 128);
   BF_LAUNCH(PC_SEGMENT, 0, st, segment_table_kernel<<<seg_grid, 128, 0, st>>>(r1.keys, n1, L, nb, w.s[0].seg));
   BF_LAUNCH(PC_SEGMENT, 0, st, segment_table_kernel<<<seg_grid, 128, 0, st>>>(r2.keys, n2, L, nb, w.s[1].seg));
+  const i64* ownpos = nullptr;
+  if (own) {
+    BF_LAUNCH(PC_SEGMENT, 0, st, own_positions_kernel<<<1, 32, 0, st>>>(r1.keys, n1, r2.keys, n2, L, own[0], own[1], own[2],
+                                                                       own[3], w.ownpos));
+    ownpos = w.ownpos;
+  }
 
   // ---- running max of end' (only where an outer side needs it) ----
   const SortResult* rs[2] = {&r1, &r2};
@@ -896,8 +914,8 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   }
   // algorithmic bytes: key read (8) + lo (4) + scan offset (8) written per row
   BF_CUDA(cudaMemsetAsync(w.header, 0, 8 * sizeof(i64), st));
-  BF_TRY((launch_search<false>(r1, n1, r2, n2, need1, w.s[0], w.s[1].pmax, L, closed, w.header + 6, st)));
-  BF_TRY((launch_search<true>(r2, n2, r1, n1, need2, w.s[1], w.s[0].pmax, L, closed, w.header + 6, st)));
+  BF_TRY((launch_search<false>(r1, n1, r2, n2, need1, w.s[0], w.s[1].pmax, L, closed, w.header + 6, ownpos, st)));
+  BF_TRY((launch_search<true>(r2, n2, r1, n1, need2, w.s[1], w.s[0].pmax, L, closed, w.header + 6, ownpos, st)));
   plan->shift1 = w.s[0].shift;
   plan->shift2 = w.s[1].shift;
 
@@ -949,6 +967,344 @@ static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64
   return BF_OK;
 }
 
+static int check_count_args(const char* who, i64 n1, i64 n2, i32 nb, i32 how, const OverlapPlan* plan) {
+  if (n1 < 0 || n2 < 0 || nb < 1 || how < 0 || how > 3 || !plan) {
+    set_error("%s: bad argument (n1=%lld n2=%lld n_groups=%d how=%d)", who, (long long)n1, (long long)n2, nb, how);
+    return BF_ERR_ARG;
+  }
+  if (n1 >= (1ll << 31) || n2 >= (1ll << 31)) {
+    set_error("%s: more than 2^31-1 rows in one set", who);
+    return BF_ERR_RANGE;
+  }
+  return BF_OK;
+}
+static void init_plan(OverlapPlan* plan, i64 n1, i64 n2, i32 nb, i32 how, i32 closed, i32 prepared) {
+  plan->magic = 0;
+  plan->n1 = n1;
+  plan->n2 = n2;
+  plan->nb = nb;
+  plan->how = how;
+  plan->closed = closed;
+  plan->ready = 0;
+  plan->row_off1 = plan->row_off2 = 0;
+  plan->prepared = prepared;
+  plan->n_own1 = 0xffffffffu;
+  plan->halo_ids = nullptr;
+}
+
+static int overlap_count_impl(const i32* grp1, const i64* s1, const i64* e1, i64 n1, const i32* grp2,
+                              const i64* s2, const i64* e2, i64 n2, i32 nb, i32 how, i32 closed,
+                              void* ws_ptr, size_t ws_bytes, OverlapPlan* plan, cudaStream_t st) {
+  BF_TRY(check_count_args("bf_overlap_count", n1, n2, nb, how, plan));
+  if ((n1 > 0 && (!s1 || !e1)) || (n2 > 0 && (!s2 || !e2)) || (nb > 1 && ((n1 > 0 && !grp1) || (n2 > 0 && !grp2)))) {
+    set_error("bf_overlap_count: null input pointer");
+    return BF_ERR_ARG;
+  }
+  Arena measure(nullptr);
+  OverlapWS w;
+  layout_overlap(measure, n1, n2, nb, how, &w);
+  if (!ws_ptr || ws_bytes < measure.off) {
+    set_error("bf_overlap_count: workspace %zu bytes < required %zu", ws_bytes, measure.off);
+    return BF_ERR_WORKSPACE;
+  }
+  Arena arena(ws_ptr);
+  layout_overlap(arena, n1, n2, nb, how, &w);
+  init_plan(plan, n1, n2, nb, how, closed, 0);
+
+  // ---- coordinate extent, group code check, key layout (one small D2H) ----
+  const RowSet sets[2] = {{grp1, s1, e1, n1}, {grp2, s2, e2, n2}};
+  KeyLayout L;
+  BF_TRY(measure_layout(sets, 2, nb, 1, 1, w.layout, st, &L, "bf_overlap_count"));
+  // ---- sort both sets ----
+  SortResult r1, r2;
+  BF_TRY(sort_rows(nb > 1 ? grp1 : nullptr, s1, e1, n1, L, KEY_POINT_ADJUST | presorted_mode(L, 0), w.sb[0], w.radix, st, &r1));
+  BF_TRY(sort_rows(nb > 1 ? grp2 : nullptr, s2, e2, n2, L, KEY_POINT_ADJUST | presorted_mode(L, 1), w.sb[1], w.radix, st, &r2));
+  return count_sorted(w, L, r1, n1, r2, n2, grp1, grp2, nb, how, closed, nullptr, plan, st);
+}
+
+// ---------------------------------------------------------------- prepared (pre-sorted) sets
+// A set sorted once and used by several count/emit calls, or sorted on one rank and adopted on the
+// others after a broadcast of its 8-byte keys and 4-byte row ids.
+struct SetStore {
+  SortBufs sb;
+  RadixScratch radix;
+  LayoutScratch layout;
+};
+static void layout_set_store(Arena& a, i64 n, i32 nb, bool adopt, SetStore* s) {
+  if (adopt) {
+    s->sb.keyA = a.take<u64>(n);
+    s->sb.idA = a.take<u32>(n);
+    s->sb.keyB = nullptr;
+    s->sb.idB = nullptr;
+    s->sb.tmp8 = nullptr;
+    s->sb.tmp4a = s->sb.tmp4b = nullptr;
+    s->sb.spine = s->sb.nT = nullptr;
+    s->layout = take_layout_scratch(a, nb);
+    return;
+  }
+  take_sort_bufs(a, n, &s->sb);
+  s->radix = take_radix_scratch(a, (u64)n);
+  s->layout = take_layout_scratch(a, nb);
+}
+struct SortedSet {  // lives in the caller's bf_sorted_set
+  u64 magic;
+  i64 n;
+  i32 nb, adopted;
+  KeyLayout L;  // goff points into the set's own store
+  u64* keys;
+  u32* ids;
+};
+static_assert(sizeof(SortedSet) <= sizeof(bf_sorted_set), "bf_sorted_set too small");
+constexpr u64 SET_MAGIC = 0x6266536f72746564ull;
+
+// layout from the merged extent words, goff uploaded into the store
+static int set_layout(const i64* words, i32 nb, const SetStore& store, cudaStream_t st, KeyLayout* L) {
+  std::vector<u64> goff((size_t)nb + 2);
+  BF_TRY(layout_from_words(words, nb, 1, L, goff.data()));
+  BF_CUDA(cudaMemcpyAsync(store.layout.goff, goff.data(), ((size_t)nb + 1) * sizeof(u64), cudaMemcpyHostToDevice, st));
+  BF_CUDA(cudaStreamSynchronize(st));  // the host vector goes out of scope
+  L->goff = store.layout.goff;
+  return BF_OK;
+}
+
+}  // namespace bf
+
+extern "C" {
+
+size_t bf_extent_words(int32_t n_groups) { return n_groups < 1 ? 0 : (size_t)bf::EXT_HDR + (size_t)n_groups; }
+size_t bf_extent_workspace_bytes(int32_t n_groups) {
+  if (n_groups < 1) return 0;
+  bf::Arena a(nullptr);
+  bf::take_layout_scratch(a, n_groups);
+  return a.off;
+}
+int bf_extent_measure(const int32_t* grp, const int64_t* start, const int64_t* end, int64_t n, int32_t n_groups,
+                      void* ws, size_t ws_bytes, void* stream, int64_t* words_out, int32_t* presorted_out) {
+  using namespace bf;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n < 0 || n_groups < 1 || !words_out || (n > 0 && (!start || !end)) || (n > 0 && n_groups > 1 && !grp)) {
+    set_error("bf_extent_measure: bad argument");
+    return BF_ERR_ARG;
+  }
+  if (!ws || ws_bytes < bf_extent_workspace_bytes(n_groups)) {
+    set_error("bf_extent_measure: workspace too small");
+    return BF_ERR_WORKSPACE;
+  }
+  Arena a(ws);
+  LayoutScratch sc = take_layout_scratch(a, n_groups);
+  const i32 nb = n_groups;
+  BF_LAUNCH(PC_EXTENT, 0, st, extent_init_kernel<<<(unsigned)ceil_div(nb + 1, 256), 256, 0, st>>>(sc.extent, sc.gmax, nb));
+  const size_t smem = nb <= EXTENT_SMEM_GROUPS ? (size_t)nb * sizeof(i64) : 0;
+  if (n > 0)
+    BF_LAUNCH(PC_EXTENT, 20 * n, st,
+              extent_kernel<<<stream_grid((u64)n, 1024), 256, smem, st>>>(nb > 1 ? (const i32*)grp : nullptr, (const i64*)start,
+                                                                         (const i64*)end, (u64)n, 1, nb, 1, sc.extent, sc.gmax));
+  Extent ext;
+  BF_CUDA(cudaMemcpyAsync(&ext, sc.extent, sizeof(Extent), cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaStreamSynchronize(st));
+  if (n > 1 && !ext.unsorted) {  // the sampled check found no disorder: exact check
+    BF_LAUNCH(PC_EXTENT, 12 * n, st,
+              order_check_kernel<<<stream_grid((u64)n, 2048), 256, 0, st>>>(nb > 1 ? (const i32*)grp : nullptr, (const i64*)start,
+                                                                           (u64)n, 1, sc.extent));
+    BF_CUDA(cudaMemcpyAsync(&ext, sc.extent, sizeof(Extent), cudaMemcpyDeviceToHost, st));
+    BF_CUDA(cudaStreamSynchronize(st));
+  }
+  if (n > 0 && ext.bad) {
+    set_error("interval with end < start: not a valid bedframe interval");
+    return BF_ERR_ARG;
+  }
+  if (n > 0 && nb > 1 && (ext.gmin < 0 || ext.gmax >= nb)) {
+    set_error("bf_extent_measure: group code outside [0,%d): min %d max %d", nb, ext.gmin, ext.gmax);
+    return BF_ERR_GROUP;
+  }
+  std::vector<i64> gmax((size_t)nb);
+  BF_CUDA(cudaMemcpyAsync(gmax.data(), sc.gmax, (size_t)nb * sizeof(i64), cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaStreamSynchronize(st));
+  extent_to_words(ext, gmax.data(), nb, n == 0, (i64*)words_out);
+  if (presorted_out) *presorted_out = (n > 0 && !ext.unsorted) ? 1 : 0;
+  return BF_OK;
+}
+
+size_t bf_sorted_set_bytes(int64_t n, int32_t n_groups, int32_t adopt) {
+  if (n < 0 || n_groups < 1) return 0;
+  bf::Arena a(nullptr);
+  bf::SetStore s;
+  bf::layout_set_store(a, n, n_groups, adopt != 0, &s);
+  return a.off;
+}
+
+int bf_overlap_prepare_set(const int64_t* extent_words, const int32_t* grp, const int64_t* start, const int64_t* end,
+                           int64_t n, int32_t n_groups, int32_t presorted, void* store, size_t store_bytes,
+                           void* stream, bf_sorted_set* set_out) {
+  using namespace bf;
+  cudaStream_t st = (cudaStream_t)stream;
+  SortedSet* set = (SortedSet*)set_out;
+  if (!extent_words || !set || n < 0 || n_groups < 1 || n >= (1ll << 31) || (n > 0 && (!start || !end)) ||
+      (n > 0 && n_groups > 1 && !grp)) {
+    set_error("bf_overlap_prepare_set: bad argument");
+    return BF_ERR_ARG;
+  }
+  if (!store || store_bytes < bf_sorted_set_bytes(n, n_groups, 0)) {
+    set_error("bf_overlap_prepare_set: set storage too small");
+    return BF_ERR_WORKSPACE;
+  }
+  Arena a(store);
+  SetStore ss;
+  layout_set_store(a, n, n_groups, false, &ss);
+  set->magic = 0;
+  BF_TRY(set_layout((const i64*)extent_words, n_groups, ss, st, &set->L));
+  SortResult r;
+  BF_TRY(sort_rows(n_groups > 1 ? (const i32*)grp : nullptr, (const i64*)start, (const i64*)end, n, set->L,
+                   KEY_POINT_ADJUST | (presorted ? KEY_PRESORTED : 0), ss.sb, ss.radix, st, &r));
+  set->n = n;
+  set->nb = n_groups;
+  set->adopted = 0;
+  set->keys = r.keys;
+  set->ids = r.vals;
+  set->magic = SET_MAGIC;
+  return BF_OK;
+}
+
+int bf_overlap_adopt_set(const int64_t* extent_words, int64_t n, int32_t n_groups, void* store, size_t store_bytes,
+                         void* stream, bf_sorted_set* set_out) {
+  using namespace bf;
+  SortedSet* set = (SortedSet*)set_out;
+  if (!extent_words || !set || n < 0 || n_groups < 1 || n >= (1ll << 31)) {
+    set_error("bf_overlap_adopt_set: bad argument");
+    return BF_ERR_ARG;
+  }
+  if (!store || store_bytes < bf_sorted_set_bytes(n, n_groups, 1)) {
+    set_error("bf_overlap_adopt_set: set storage too small");
+    return BF_ERR_WORKSPACE;
+  }
+  Arena a(store);
+  SetStore ss;
+  layout_set_store(a, n, n_groups, true, &ss);
+  set->magic = 0;
+  BF_TRY(set_layout((const i64*)extent_words, n_groups, ss, (cudaStream_t)stream, &set->L));
+  set->n = n;
+  set->nb = n_groups;
+  set->adopted = 1;
+  set->keys = ss.sb.keyA;
+  set->ids = ss.sb.idA;
+  set->magic = SET_MAGIC;
+  return BF_OK;
+}
+
+int bf_sorted_set_buffers(const bf_sorted_set* set_in, void** keys_out, void** ids_out, int64_t* n_out) {
+  const bf::SortedSet* set = (const bf::SortedSet*)set_in;
+  if (!set || set->magic != bf::SET_MAGIC) {
+    bf::set_error("bf_sorted_set_buffers: not a prepared set");
+    return BF_ERR_STATE;
+  }
+  if (keys_out) *keys_out = set->keys;
+  if (ids_out) *ids_out = set->ids;
+  if (n_out) *n_out = set->n;
+  return BF_OK;
+}
+
+size_t bf_overlap_prepared_workspace_bytes(int64_t n1, int64_t n2, int32_t n_groups, int32_t how) {
+  if (n1 < 0 || n2 < 0 || n_groups < 1) return 0;
+  bf::Arena a(nullptr);
+  bf::OverlapWS w;
+  bf::layout_count(a, n1, n2, n_groups, how, &w);
+  return a.off;
+}
+
+int bf_overlap_count_prepared(const bf_sorted_set* set1_in, const bf_sorted_set* set2_in, const int32_t* grp1,
+                              const int32_t* grp2, int32_t how, int32_t closed, const int64_t* own_range, void* ws,
+                              size_t ws_bytes, bf_plan* plan_out, void* stream, int64_t* n_rows_out,
+                              int64_t* n_pairs_out) {
+  using namespace bf;
+  const SortedSet* a = (const SortedSet*)set1_in;
+  const SortedSet* b = (const SortedSet*)set2_in;
+  OverlapPlan* plan = (OverlapPlan*)plan_out;
+  if (!a || !b || a->magic != SET_MAGIC || b->magic != SET_MAGIC) {
+    set_error("bf_overlap_count_prepared: sets were not produced by bf_overlap_prepare_set / bf_overlap_adopt_set");
+    return BF_ERR_STATE;
+  }
+  if (a->nb != b->nb || a->L.B != b->L.B || a->L.LB != b->L.LB || a->L.cmin != b->L.cmin || a->L.endcap != b->L.endcap) {
+    set_error("bf_overlap_count_prepared: the two sets were prepared with different extents");
+    return BF_ERR_STATE;
+  }
+  const i32 nb = a->nb;
+  BF_TRY(check_count_args("bf_overlap_count_prepared", a->n, b->n, nb, how, plan));
+  if (nb > 1 && (((how & 1) && a->n > 0 && !grp1) || ((how & 2) && b->n > 0 && !grp2))) {
+    set_error("bf_overlap_count_prepared: the group codes of a kept side are needed for its unpaired rows");
+    return BF_ERR_ARG;
+  }
+  if (own_range && (how & 2)) {
+    set_error("bf_overlap_count_prepared: a query-sharded call supports how=inner/left (unpaired targets need a reduction)");
+    return BF_ERR_ARG;
+  }
+  if (!ws || ws_bytes < bf_overlap_prepared_workspace_bytes(a->n, b->n, nb, how)) {
+    set_error("bf_overlap_count_prepared: workspace too small");
+    return BF_ERR_WORKSPACE;
+  }
+  Arena arena(ws);
+  OverlapWS w;
+  layout_count(arena, a->n, b->n, nb, how, &w);
+  init_plan(plan, a->n, b->n, nb, how, closed, 1);
+  SortResult r1 = {a->keys, a->ids, nullptr, nullptr}, r2 = {b->keys, b->ids, nullptr, nullptr};
+  int rc = count_sorted(w, a->L, r1, a->n, r2, b->n, (const i32*)grp1, (const i32*)grp2, nb, how, closed,
+                        (const i64*)own_range, plan, (cudaStream_t)stream);
+  if (rc == BF_OK) {
+    if (n_rows_out) *n_rows_out = plan->n_rows;
+    if (n_pairs_out) *n_pairs_out = plan->n_pairs;
+  }
+  return rc;
+}
+
+int bf_overlap_set_halo_rows(bf_plan* plan_in, int64_t n_own1, const int64_t* halo_ids) {
+  bf::OverlapPlan* p = (bf::OverlapPlan*)plan_in;
+  if (!p || p->magic != bf::OVERLAP_MAGIC || !p->ready) {
+    bf::set_error("bf_overlap_set_halo_rows: plan was not produced by a successful count call");
+    return BF_ERR_STATE;
+  }
+  if (n_own1 < 0 || n_own1 > p->n1 || (n_own1 < p->n1 && !halo_ids)) {
+    bf::set_error("bf_overlap_set_halo_rows: bad argument");
+    return BF_ERR_ARG;
+  }
+  p->n_own1 = (u32)n_own1;
+  p->halo_ids = (const i64*)halo_ids;
+  return BF_OK;
+}
+
+int bf_overlap_group_counts(const bf_plan* plan_in, void* ws, int64_t* counts_out, void* stream) {
+  using namespace bf;
+  const OverlapPlan* p = (const OverlapPlan*)plan_in;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!p || p->magic != OVERLAP_MAGIC || !p->ready || !counts_out) {
+    set_error("bf_overlap_group_counts: plan was not produced by a successful count call");
+    return BF_ERR_STATE;
+  }
+  Arena arena(ws);
+  OverlapWS w;
+  if (p->prepared)
+    layout_count(arena, p->n1, p->n2, p->nb, p->how, &w);
+  else
+    layout_overlap(arena, p->n1, p->n2, p->nb, p->how, &w);
+  const i32 nb = p->nb;
+  std::vector<i64> cum((size_t)2 * (nb + 1));
+  std::vector<u64> uc((size_t)2 * (nb + 1), 0ull);
+  BF_CUDA(cudaMemcpyAsync(cum.data(), w.cumA, (size_t)(nb + 1) * sizeof(i64), cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaMemcpyAsync(cum.data() + nb + 1, w.cumB, (size_t)(nb + 1) * sizeof(i64), cudaMemcpyDeviceToHost, st));
+  if (p->how & 1) BF_CUDA(cudaMemcpyAsync(uc.data(), w.s[0].ucnt, (size_t)(nb + 1) * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  if (p->how & 2) BF_CUDA(cudaMemcpyAsync(uc.data() + nb + 1, w.s[1].ucnt, (size_t)(nb + 1) * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaStreamSynchronize(st));
+  for (i32 c = 0; c < nb; ++c) {
+    counts_out[4 * c + 0] = cum[c + 1] - cum[c];
+    counts_out[4 * c + 1] = cum[nb + 1 + c + 1] - cum[nb + 1 + c];
+    counts_out[4 * c + 2] = (i64)uc[c];
+    counts_out[4 * c + 3] = (i64)uc[nb + 1 + c];
+  }
+  return BF_OK;
+}
+
+}  // extern "C"
+
+namespace bf {
+
 static int overlap_emit_impl(const OverlapPlan* plan, void* ws_ptr, i64* ev1, i64* ev2, cudaStream_t st) {
   if (!plan || plan->magic != OVERLAP_MAGIC || !plan->ready) {
     set_error("bf_overlap_emit: plan was not produced by a successful bf_overlap_count");
@@ -960,7 +1316,10 @@ static int overlap_emit_impl(const OverlapPlan* plan, void* ws_ptr, i64* ev1, i6
   }
   Arena arena(ws_ptr);
   OverlapWS w;
-  layout_overlap(arena, plan->n1, plan->n2, plan->nb, plan->how, &w);
+  if (plan->prepared)
+    layout_count(arena, plan->n1, plan->n2, plan->nb, plan->how, &w);
+  else
+    layout_overlap(arena, plan->n1, plan->n2, plan->nb, plan->how, &w);
   // pairs: chunks of EMIT_CHUNK_BLOCKS blocks, each preceded by its partition kernel
   for (int side = 0; side < 2; ++side) {
     const i64 total = side ? plan->totB : plan->totA;
@@ -983,12 +1342,13 @@ static int overlap_emit_impl(const OverlapPlan* plan, void* ws_ptr, i64* ev1, i6
         BF_LAUNCH(PC_EMIT, bytes, st,
                   emit_pairs_kernel<false><<<(unsigned)nb_chunk, EM_THREADS, 0, st>>>(
                       scan, sw.lo, n_owner, plan->id1, plan->id2, total, b0, part, pgrp, cum, delta, plan->nb,
-                      plan->row_off1, plan->row_off2, ev1, ev2));
+                      plan->row_off1, plan->row_off2, 0xffffffffu, nullptr, ev1, ev2));
       } else {
         BF_LAUNCH(PC_EMIT, bytes, st,
                   emit_pairs_kernel<true><<<(unsigned)nb_chunk, EM_THREADS, 0, st>>>(
                       scan, sw.lo, n_owner, plan->id2, plan->id1, total, b0, part, pgrp, cum, delta, plan->nb,
-                      plan->row_off1, plan->row_off2, ev1, ev2));
+                      plan->row_off1, plan->row_off2, plan->halo_ids ? plan->n_own1 : 0xffffffffu, plan->halo_ids,
+                      ev1, ev2));
       }
     }
   }

@@ -153,6 +153,132 @@ def overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how="inner
     return ev1, ev2, n_pairs.value
 
 
+class SortedSet:
+    """A set sorted once on the device (bf_overlap_prepare_set) or adopted from another rank
+    (bf_overlap_adopt_set): `keys` (int64 view of the uint64 sort keys) and `ids` (int32 view of the uint32 row
+    ids) are the two buffers a broadcast moves; `store` owns the memory."""
+
+    def __init__(self, struct, store, n, n_groups, grp, device):
+        self.struct, self.store, self.n, self.n_groups, self.grp, self.device = struct, store, int(n), int(n_groups), grp, device
+        kp, ip, nn = C.c_void_p(0), C.c_void_p(0), C.c_int64(0)
+        _lib.check(_lib.lib().bf_sorted_set_buffers(C.byref(struct), C.byref(kp), C.byref(ip), C.byref(nn)),
+                   "bf_sorted_set_buffers")
+        base = store.data_ptr()
+        if self.n:
+            ko, io = kp.value - base, ip.value - base
+            self.keys = store[ko:ko + 8 * self.n].view(torch.int64)
+            self.ids = store[io:io + 4 * self.n].view(torch.int32)
+        else:
+            self.keys = torch.empty(0, dtype=torch.int64, device=device)
+            self.ids = torch.empty(0, dtype=torch.int32, device=device)
+
+
+def measure_extent(grp, start, end, n_groups, device=None):
+    """Extent of one set as the mergeable host record of the C ABI (bf_extent_measure).
+    -> (int64 numpy words, presorted flag).  Merge records with `np.maximum` / all_reduce(MAX)."""
+    import numpy as np
+
+    _require_cuda()
+    L = _lib.lib()
+    device = torch.device(device if device is not None else "cuda")
+    s, e = _as(start, torch.int64, device), _as(end, torch.int64, device)
+    g = _as(grp, torch.int32, device) if n_groups > 1 else None
+    n = int(s.numel())
+    words = np.zeros(int(L.bf_extent_words(n_groups)), dtype=np.int64)
+    pres = C.c_int32(0)
+    with torch.cuda.device(device):
+        ws = torch.empty(max(int(L.bf_extent_workspace_bytes(n_groups)), 256), dtype=torch.uint8, device=device)
+        rc = L.bf_extent_measure(_ptr(g), _ptr(s), _ptr(e), n, n_groups, _ptr(ws), ws.numel(), _stream_ptr(device),
+                                 C.c_void_p(words.ctypes.data), C.byref(pres))
+        _lib.check(rc, "bf_extent_measure")
+    return words, bool(pres.value)
+
+
+def prepare_set(words, grp, start, end, n_groups, presorted=False, device=None):
+    """Sort one set for `overlap_prepared` with the key layout the merged extent `words` fix."""
+    import numpy as np
+
+    _require_cuda()
+    L = _lib.lib()
+    device = torch.device(device if device is not None else "cuda")
+    s, e = _as(start, torch.int64, device), _as(end, torch.int64, device)
+    g = _as(grp, torch.int32, device) if n_groups > 1 else None
+    n = int(s.numel())
+    words = np.ascontiguousarray(words, dtype=np.int64)
+    struct = _lib.SortedSetStruct()
+    with torch.cuda.device(device):
+        store = torch.empty(max(int(L.bf_sorted_set_bytes(n, n_groups, 0)), 256), dtype=torch.uint8, device=device)
+        rc = L.bf_overlap_prepare_set(C.c_void_p(words.ctypes.data), _ptr(g), _ptr(s), _ptr(e), n, n_groups,
+                                      int(bool(presorted)), _ptr(store), store.numel(), _stream_ptr(device),
+                                      C.byref(struct))
+        _lib.check(rc, "bf_overlap_prepare_set")
+    return SortedSet(struct, store, n, n_groups, g, device)
+
+
+def adopt_set(words, n, n_groups, grp=None, device=None):
+    """An empty prepared set of `n` rows whose `keys` / `ids` the caller fills (e.g. by a broadcast of another
+    rank's `SortedSet.keys` / `.ids`) before it is used."""
+    import numpy as np
+
+    _require_cuda()
+    L = _lib.lib()
+    device = torch.device(device if device is not None else "cuda")
+    words = np.ascontiguousarray(words, dtype=np.int64)
+    struct = _lib.SortedSetStruct()
+    with torch.cuda.device(device):
+        store = torch.empty(max(int(L.bf_sorted_set_bytes(int(n), n_groups, 1)), 256), dtype=torch.uint8, device=device)
+        rc = L.bf_overlap_adopt_set(C.c_void_p(words.ctypes.data), int(n), n_groups, _ptr(store), store.numel(),
+                                    _stream_ptr(device), C.byref(struct))
+        _lib.check(rc, "bf_overlap_adopt_set")
+    g = _as(grp, torch.int32, device) if (grp is not None and n_groups > 1) else None
+    return SortedSet(struct, store, n, n_groups, g, device)
+
+
+def overlap_prepared(set1, set2, how="inner", closed=False, own_range=None, row_offset1=0, row_offset2=0,
+                     n_own1=None, halo_ids=None, want_group_counts=False):
+    """`_overlap_intidxs` on two prepared sets (bf_overlap_count_prepared + bf_overlap_emit).
+    own_range = (g_lo, start_lo, g_hi, start_hi): produce only the part of the result this query shard owns;
+    n_own1 / halo_ids: set-1 rows from n_own1 on are halo rows with these global row numbers.
+    -> (events1, events2, n_pairs[, per-group counts int64[n_groups, 4] = A, B, unpaired 1, unpaired 2])."""
+    import numpy as np
+
+    _require_cuda()
+    L = _lib.lib()
+    device = set1.device
+    how_code = _lib.HOW[how]
+    own = None if own_range is None else np.ascontiguousarray(own_range, dtype=np.int64)
+    with torch.cuda.device(device):
+        ws = Workspace.get(device, max(L.bf_overlap_prepared_workspace_bytes(set1.n, set2.n, set1.n_groups, how_code), 256))
+        plan = _lib.Plan()
+        n_rows, n_pairs = C.c_int64(0), C.c_int64(0)
+        stream = _stream_ptr(device)
+        rc = L.bf_overlap_count_prepared(C.byref(set1.struct), C.byref(set2.struct), _ptr(set1.grp), _ptr(set2.grp),
+                                         how_code, int(bool(closed)), C.c_void_p(own.ctypes.data) if own is not None else None,
+                                         _ptr(ws), ws.numel(), C.byref(plan), stream, C.byref(n_rows), C.byref(n_pairs))
+        _lib.check(rc, "bf_overlap_count_prepared")
+        if row_offset1 or row_offset2:
+            _lib.check(L.bf_overlap_set_row_offsets(C.byref(plan), int(row_offset1), int(row_offset2)),
+                       "bf_overlap_set_row_offsets")
+        halo = None
+        if n_own1 is not None and int(n_own1) < set1.n:
+            halo = _as(halo_ids, torch.int64, device)
+            if int(halo.numel()) != set1.n - int(n_own1):
+                raise ValueError("halo_ids must hold one global row number per halo row")
+            _lib.check(L.bf_overlap_set_halo_rows(C.byref(plan), int(n_own1), _ptr(halo)), "bf_overlap_set_halo_rows")
+        counts = None
+        if want_group_counts:
+            counts = np.zeros((set1.n_groups, 4), dtype=np.int64)
+            _lib.check(L.bf_overlap_group_counts(C.byref(plan), _ptr(ws), C.c_void_p(counts.ctypes.data), stream),
+                       "bf_overlap_group_counts")
+        ev1 = torch.empty(n_rows.value, dtype=torch.int64, device=device)
+        ev2 = torch.empty(n_rows.value, dtype=torch.int64, device=device)
+        rc = L.bf_overlap_emit(C.byref(plan), _ptr(ws), _ptr(ev1), _ptr(ev2), stream)
+        _lib.check(rc, "bf_overlap_emit")
+    if want_group_counts:
+        return ev1, ev2, n_pairs.value, counts
+    return ev1, ev2, n_pairs.value
+
+
 def sort_pairs(ev1, ev2, max1, max2):
     """Order device-resident result pairs in place by (events1, events2), -1 last (keep_order=True of
     bioframe.overlap, ops.py:549-550, for monotonic indexes)."""

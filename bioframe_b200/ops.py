@@ -147,7 +147,10 @@ def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _gro
         if biggest > _ORDERED_MAX_PARTNERS:
             ev1 = None
     if ev1 is None:
-        ev1, ev2, _ = _engine.overlap_intidxs(g1, s1, e1, g2, s2, e2, n_groups, how=how)
+        # any other string joins like 'inner' in the reference (its `how in {...}` tests all fail, ops.py:229-234,
+        # 327-331; its own test suite passes how="innter")
+        join = how if how in ("left", "right", "outer") else "inner"
+        ev1, ev2, _ = _engine.overlap_intidxs(g1, s1, e1, g2, s2, e2, n_groups, how=join)
         if _sort_pairs:  # keep_order on the device: rows by (row of df1, row of df2), -1 last
             ev1, ev2 = _engine.sort_pairs(ev1, ev2, max(len(df1) - 1, 0), max(len(df2) - 1, 0))
     if _device_rows is not None:  # the caller goes on working with the pair list where it is

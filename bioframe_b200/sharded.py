@@ -14,8 +14,16 @@ order for that shard.  For how='left' with keep_order=True (the default of
 `bioframe.overlap`) `overlap_ordered_sharded` yields every shard in (query row,
 target row) order, so the concatenation is the single-GPU result bit for bit; the
 same holds for the other per-query results (coverage, count_overlaps, subtract,
-closest per query).  For the block order of how='inner' the pair SET is identical
-and the order is (shard, group, A-block, B-block)."""
+closest per query).  `overlap_sharded` (row-range shards of unsorted queries) yields the pair SET in
+(shard, group, A-block, B-block) order.
+
+`overlap_range_sharded` is the exact form: the shards are contiguous (group, start) RANGES of the queries
+(what the north star asks for), every rank gets the queries of its range plus the few halo queries a target
+of its range can still reach, the targets are sorted ONCE on `src` and their sorted keys + row ids are
+broadcast (12 B/row) while every rank sorts its own queries, and each rank produces only the rows it owns.
+Per group the reference's rows (arrops.py:357-368, ops.py:319-326) then are: the A segments of the shards in
+shard order, their B segments, their unpaired segments -- `assemble_offsets` turns the per-(shard, group)
+segment sizes into the position of every segment in the reference's result, bit for bit."""
 from __future__ import annotations
 
 import numpy as np
@@ -137,3 +145,180 @@ def closest_sharded(grp1, start1, end1, row_offset, grp2, start2, end2, n_groups
     if int(row_offset):
         ev1 = ev1 + int(row_offset)  # every row carries a query (never -1)
     return ev1, torch.as_tensor(ev2), n_matched
+
+
+# ---------------------------------------------------------------------------------------------------------
+# exact reference row order with (group, start)-range shards
+
+
+def merge_extent_words(words, device=None, group=None):
+    """all_reduce(MAX) of the mergeable extent record (bf_extent_measure) over the ranks -> numpy int64."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return np.asarray(words, dtype=np.int64)
+    t = torch.from_numpy(np.ascontiguousarray(words, dtype=np.int64))
+    if device is not None and torch.device(device).type == "cuda":
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return t.cpu().numpy()
+
+
+def halo_reach(grp2, start2, end2, own_hi, n_groups):
+    """How far beyond the upper bound `own_hi` = (g_hi, start_hi) of a shard its halo has to reach: the
+    largest end' of a target that starts below the bound in the bound's own group (a target never leaves its
+    group).  Queries of group g_hi with start in [start_hi, reach) are the shard's halo rows.  numpy, host."""
+    g_hi, s_hi = int(own_hi[0]), int(own_hi[1])
+    if g_hi >= n_groups:
+        return s_hi
+    g2, s2, e2 = np.asarray(grp2), np.asarray(start2), np.asarray(end2)
+    m = (g2 == g_hi) & (s2 < s_hi) if n_groups > 1 else (s2 < s_hi)
+    if not m.any():
+        return s_hi
+    e = e2[m] + (e2[m] == s2[m])
+    return max(int(e.max()), s_hi)
+
+
+def overlap_range_sharded(grp1, start1, end1, n_own, own_range, grp2, start2, end2, n_groups, how="left",
+                          row_offset=0, halo_ids=None, engine=None, group=None, src=0, n2=None, device=None):
+    """This rank's part of `_overlap_intidxs(df1, df2, how)` in the reference's row order.
+
+    grp1/start1/end1: the queries of this rank's (group, start) range `own_range` = (g_lo, start_lo, g_hi,
+    start_hi) -- rows [0, n_own), global row numbers row_offset + i -- followed by its halo rows (global row
+    numbers `halo_ids`).  grp2/start2/end2: the targets, needed on `src` only (pass None elsewhere, with n2).
+    Returns (events1, events2, n_pairs, counts[n_groups, 4]); `assemble_offsets(all ranks' counts)` places the
+    per-group segments of events1/events2 in the whole result."""
+    if engine is None:
+        from . import engine as engine
+    if how not in ("inner", "left"):
+        raise ValueError("query-sharded overlap supports how='inner' and how='left' (unpaired targets need a reduction)")
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    have_targets = world == 1 or rank == src
+    use_cuda = torch.is_tensor(start1) and start1.is_cuda
+    dev = start1.device if use_cuda else device
+
+    # 1. one key layout for every set on every rank: local extents, MAX-merged (a few hundred bytes)
+    words, presorted1 = engine.measure_extent(grp1, start1, end1, n_groups)
+    presorted2 = False
+    if have_targets:
+        w2, presorted2 = engine.measure_extent(grp2, start2, end2, n_groups)
+        words = np.maximum(words, w2)
+        n2 = int(len(start2))
+    words = merge_extent_words(words, device=dev, group=group)
+
+    # 2. targets: sorted once on `src`, keys + row ids broadcast on a side stream; queries sorted meanwhile
+    side = torch.cuda.Stream(device=dev) if use_cuda else None
+    main = torch.cuda.current_stream(dev) if use_cuda else None
+    if side is not None:
+        side.wait_stream(main)
+    ctx = torch.cuda.stream(side) if side is not None else _NullContext()
+    handles = []
+    with ctx:
+        if have_targets:
+            set2 = engine.prepare_set(words, grp2, start2, end2, n_groups, presorted=presorted2)
+        else:
+            set2 = engine.adopt_set(words, n2, n_groups)
+        if world > 1:
+            handles.append(dist.broadcast(set2.keys, src=src, group=group, async_op=True))
+            handles.append(dist.broadcast(set2.ids, src=src, group=group, async_op=True))
+    set1 = engine.prepare_set(words, grp1, start1, end1, n_groups, presorted=presorted1)
+    for h in handles:
+        h.wait()
+    if side is not None:
+        main.wait_stream(side)
+        set2.store.record_stream(main)
+
+    # 3. search + count + emit, only what this shard owns
+    sharded_call = world > 1 or own_range is not None
+    ev1, ev2, n_pairs, counts = engine.overlap_prepared(
+        set1, set2, how=how, own_range=own_range if sharded_call else None, row_offset1=int(row_offset),
+        n_own1=int(n_own), halo_ids=halo_ids, want_group_counts=True)
+    return ev1, ev2, n_pairs, counts
+
+
+def _first_row_at_or_after(grp, start, g, s):
+    lo, hi = np.searchsorted(grp, g, "left"), np.searchsorted(grp, g, "right")
+    return int(lo + np.searchsorted(start[lo:hi], s, "left"))
+
+
+def plan_range_shards(grp1, start1, world, grp2, start2, end2, n_groups):
+    """Split queries that are sorted by (group rank, start) into `world` contiguous (group, start) ranges of
+    about equal row counts, with the halo rows each shard needs.  Host side, numpy (the partition of df1 is the
+    host's job).  -> list of dict(lo, hi: owned rows [lo, hi); halo: row numbers of the halo
+    rows; own_range: (g_lo, start_lo, g_hi, start_hi))."""
+    g1 = np.zeros(len(start1), np.int64) if grp1 is None else np.asarray(grp1)
+    s1 = np.asarray(start1)
+    n = len(s1)
+    if n > 1 and not bool(np.all((g1[1:] > g1[:-1]) | ((g1[1:] == g1[:-1]) & (s1[1:] >= s1[:-1])))):
+        raise ValueError("range shards need queries sorted by (group, start): their rows must be contiguous per shard")
+    int_min = np.iinfo(np.int64).min
+    cuts = [(0, int_min)]
+    for r in range(1, world):
+        p = min(r * n // world, max(n - 1, 0))
+        cuts.append((int(g1[p]), int(s1[p])) if n else (n_groups, int_min))
+    cuts.append((n_groups, int_min))
+    shards = []
+    for r in range(world):
+        (g_lo, s_lo), (g_hi, s_hi) = cuts[r], cuts[r + 1]
+        lo = _first_row_at_or_after(g1, s1, g_lo, s_lo) if r else 0
+        hi = _first_row_at_or_after(g1, s1, g_hi, s_hi) if r + 1 < world else n
+        hi = max(hi, lo)
+        reach = halo_reach(grp2, start2, end2, (g_hi, s_hi), n_groups)
+        h_hi = _first_row_at_or_after(g1, s1, g_hi, reach) if g_hi < n_groups else hi
+        shards.append(dict(lo=lo, hi=hi, halo=np.arange(hi, max(h_hi, hi), dtype=np.int64),
+                           own_range=(g_lo, s_lo, g_hi, s_hi)))
+    return shards
+
+
+class _NullContext:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def gather_group_counts(counts, device=None, group=None):
+    """all_gather of the per-rank (n_groups, 4) segment sizes -> numpy [world, n_groups, 4]."""
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return counts[None]
+    t = torch.from_numpy(counts)
+    if device is not None and torch.device(device).type == "cuda":
+        t = t.to(device)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(out, t, group=group)
+    return torch.stack(out).cpu().numpy()
+
+
+def assemble_offsets(counts_all):
+    """counts_all [world, n_groups, 4] (A, B, unpaired 1, unpaired 2 rows per shard and group) ->
+    (dst [world, n_groups, 3], src [world, n_groups, 3], total): rows src[r, c, t] ... + counts of shard r's
+    result are rows dst[r, c, t] ... of the whole result, t = A / B / unpaired-1 segment of group c.  The
+    reference's order per group: all A pairs (shards in (group, start) order), all B pairs, the unpaired rows
+    (arrops.py:357-368, ops.py:319-326)."""
+    c = np.asarray(counts_all, dtype=np.int64)[:, :, :3]
+    world, nb, _ = c.shape
+    # destination: group-major, then segment kind, then shard
+    per = c.transpose(1, 2, 0).reshape(-1)  # [nb, 3, world]
+    dst = (np.cumsum(per) - per).reshape(nb, 3, world).transpose(2, 0, 1)
+    # source: inside a shard the rows are group-major, then A, B, unpaired (bf_overlap_emit)
+    flat = c.reshape(world, -1)
+    src = (np.cumsum(flat, axis=1) - flat).reshape(world, nb, 3)
+    return dst, src, int(c.sum())
+
+
+def assemble_host(parts, counts_all):
+    """Concatenate-by-offset on the host: parts[r] = (events1, events2) numpy arrays of shard r -> the whole
+    result in the reference's row order."""
+    dst, src, total = assemble_offsets(counts_all)
+    c = np.asarray(counts_all, dtype=np.int64)
+    out1 = np.empty(total, dtype=np.int64)
+    out2 = np.empty(total, dtype=np.int64)
+    for r, (a, b) in enumerate(parts):
+        for g in range(c.shape[1]):
+            for t in range(3):
+                k = int(c[r, g, t])
+                if k:
+                    out1[dst[r, g, t]:dst[r, g, t] + k] = a[src[r, g, t]:src[r, g, t] + k]
+                    out2[dst[r, g, t]:dst[r, g, t] + k] = b[src[r, g, t]:src[r, g, t] + k]
+    return out1, out2

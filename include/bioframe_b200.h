@@ -91,6 +91,56 @@ int bf_overlap_emit(const bf_plan* plan, void* ws, int64_t* events1_out, int64_t
  * pass over the output. */
 int bf_overlap_set_row_offsets(bf_plan* plan, int64_t offset1, int64_t offset2);
 
+/* ---- prepared sets: the query-sharded, multi-GPU form of ops._overlap_intidxs (the group loop
+ * of ops.py:301-338 split over ranks).  The reference sorts both sets inside every call (np.lexsort,
+ * arrops.py:332-335); here a set is sorted ONCE into a caller-owned store and then used by any number of
+ * count/emit calls, or sorted on one rank and adopted by the others after a broadcast of its 8-byte keys and
+ * 4-byte row ids (12 B/row instead of the 20 B/row of the raw columns, and no second sort).
+ *
+ *  1. bf_extent_measure per set and rank -> a small HOST array of bf_extent_words(n_groups) int64 words that
+ *     merges by elementwise MAX (np.maximum between sets, all_reduce(MAX) across ranks).  Every set of one
+ *     join must be prepared from the SAME merged words: they fix the key layout.
+ *  2. bf_overlap_prepare_set (sorts; `presorted` = what bf_extent_measure reported for this very set), or
+ *     bf_overlap_adopt_set + a copy of another rank's buffers into bf_sorted_set_buffers().
+ *  3. bf_overlap_count_prepared -> caller allocates -> bf_overlap_emit (the same emit as above).
+ *
+ * own_range (host, 4 words or NULL) = (g_lo, start_lo, g_hi, start_hi): the call then only produces the part
+ * of the result its shard owns -- A-block pairs and unpaired rows of the set-1 rows whose (group, start) lies
+ * in [lo, hi) lexicographically, B-block pairs of the set-2 rows in that range.  Set-1 rows outside the range
+ * are halo rows: they only appear as partners in the B block (a target's partners may start beyond the shard
+ * boundary, arrops.py:341-342, 360-366).  With contiguous (group, start) ranges per shard, the reference's
+ * row order of the whole join is, per group, the shards' A segments in shard order, then their B segments,
+ * then their unpaired segments: bf_overlap_group_counts gives the segment sizes, bf_overlap_set_halo_rows the
+ * global row numbers of the halo rows.  how=right/outer is refused with own_range (an unpaired target needs a
+ * reduction over all shards). */
+typedef struct bf_sorted_set {
+  int64_t opaque[32];
+} bf_sorted_set;
+size_t bf_extent_words(int32_t n_groups);
+size_t bf_extent_workspace_bytes(int32_t n_groups);
+int bf_extent_measure(const int32_t* grp, const int64_t* start, const int64_t* end, int64_t n, int32_t n_groups,
+                      void* ws, size_t ws_bytes, void* stream, int64_t* words_out, int32_t* presorted_out);
+size_t bf_sorted_set_bytes(int64_t n, int32_t n_groups, int32_t adopt);
+int bf_overlap_prepare_set(const int64_t* extent_words, const int32_t* grp, const int64_t* start, const int64_t* end,
+                           int64_t n, int32_t n_groups, int32_t presorted, void* store, size_t store_bytes,
+                           void* stream, bf_sorted_set* set_out);
+int bf_overlap_adopt_set(const int64_t* extent_words, int64_t n, int32_t n_groups, void* store, size_t store_bytes,
+                         void* stream, bf_sorted_set* set_out);
+/* device pointers of the set's sorted keys (uint64[n]) and row ids (uint32[n]): what a broadcast moves */
+int bf_sorted_set_buffers(const bf_sorted_set* set, void** keys_out, void** ids_out, int64_t* n_out);
+size_t bf_overlap_prepared_workspace_bytes(int64_t n1, int64_t n2, int32_t n_groups, int32_t how);
+/* grp1 / grp2: the group codes of the kept side(s) (how left: grp1), NULL otherwise or when n_groups == 1 */
+int bf_overlap_count_prepared(const bf_sorted_set* set1, const bf_sorted_set* set2, const int32_t* grp1,
+                              const int32_t* grp2, int32_t how, int32_t closed, const int64_t* own_range, void* ws,
+                              size_t ws_bytes, bf_plan* plan, void* stream, int64_t* n_rows_out,
+                              int64_t* n_pairs_out);
+/* between _count and _emit: set-1 rows [n_own1, n1) are halo rows whose global row numbers are
+ * halo_ids[row - n_own1] (device int64); rows below n_own1 get the row offset of bf_overlap_set_row_offsets */
+int bf_overlap_set_halo_rows(bf_plan* plan, int64_t n_own1, const int64_t* halo_ids);
+/* after a count call: counts_out (HOST, int64[4 * n_groups]) = per group the rows of its A block, B block,
+ * unpaired set-1 rows, unpaired set-2 rows */
+int bf_overlap_group_counts(const bf_plan* plan, void* ws, int64_t* counts_out, void* stream);
+
 /* ---- overlap(how='left') with the rows in (row of set 1, row of set 2) order: what bioframe.overlap returns by
  * default for how='left' (keep_order=True, ops.py:455-456 and the sort_values of ops.py:549-550) when the frame
  * indexes order like the rows; -1 marks a row of set 1 without partner.  The pairs are produced in that order

@@ -115,3 +115,76 @@ def sort_pairs(ev1, ev2, max1, max2):
 def count_overlaps(grp1, start1, end1, grp2, start2, end2, n_groups, closed=False, device=None):
     ev1, ev2, _ = overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how="inner", closed=closed)
     return np.bincount(ev1, minlength=len(start1)).astype(np.int64)
+
+
+# ---- prepared sets / range-sharded overlap (engine.measure_extent, prepare_set, adopt_set, overlap_prepared) ----
+# An independent model of the shard-ownership rule: the whole local result from the oracle, then rows are
+# dropped by classifying every pair as A-block (target starts at or after the query: arrops.py:338-339, 359-360)
+# or B-block (query starts after the target: arrops.py:341-342, 365-366).
+class _DoubleSet:
+    def __init__(self, rows, n_groups):
+        import torch
+
+        self.n, self.n_groups = len(rows), n_groups
+        self.keys = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.int64))  # [n, 3] = (group, start, end)
+        self.ids = torch.arange(self.n, dtype=torch.int32)
+        self.store = self.keys
+
+
+def measure_extent(grp, start, end, n_groups, device=None):
+    s, e = _i64(start), _i64(end)
+    w = np.full(8 + n_groups, np.iinfo(np.int64).min, dtype=np.int64)
+    w[3:8] = 0
+    if len(s):
+        ee = e + (e == s)
+        w[0], w[1], w[2], w[3] = ~min(s.min(), ee.min()), max(s.max(), ee.max()), s.max(), (ee - s).max()
+        g = np.zeros(len(s), np.int64) if grp is None else np.asarray(grp)
+        np.maximum.at(w, 8 + g, np.maximum(s, ee))
+    return w, False
+
+
+def prepare_set(words, grp, start, end, n_groups, presorted=False, device=None):
+    s, e = _i64(start), _i64(end)
+    g = np.zeros(len(s), np.int64) if grp is None else np.asarray(grp, dtype=np.int64)
+    return _DoubleSet(np.stack([g, s, e], axis=1) if len(s) else np.zeros((0, 3), np.int64), n_groups)
+
+
+def adopt_set(words, n, n_groups, grp=None, device=None):
+    return _DoubleSet(np.zeros((int(n), 3), np.int64), n_groups)
+
+
+def overlap_prepared(set1, set2, how="inner", closed=False, own_range=None, row_offset1=0, row_offset2=0,
+                     n_own1=None, halo_ids=None, want_group_counts=False):
+    import torch
+
+    r1, r2 = set1.keys.numpy(), set2.keys.numpy()
+    g1, s1, e1 = r1[:, 0], r1[:, 1], r1[:, 2]
+    g2, s2, e2 = r2[:, 0], r2[:, 1], r2[:, 2]
+    nb = set1.n_groups
+    ev1, ev2 = oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, nb, how=how, closed=closed)
+    grp_of = np.where(ev1 >= 0, g1[np.maximum(ev1, 0)], g2[np.maximum(ev2, 0)]) if len(ev1) else np.zeros(0, np.int64)
+    paired = (ev1 >= 0) & (ev2 >= 0)
+    is_a = paired & (s2[np.maximum(ev2, 0)] >= s1[np.maximum(ev1, 0)])
+    is_b = paired & ~is_a
+    keep = np.ones(len(ev1), dtype=bool)
+    if own_range is not None:
+        g_lo, s_lo, g_hi, s_hi = (int(x) for x in own_range)
+
+        def owned(g, s):
+            return ((g > g_lo) | ((g == g_lo) & (s >= s_lo))) & ((g < g_hi) | ((g == g_hi) & (s < s_hi)))
+
+        own1 = owned(g1, s1)[np.maximum(ev1, 0)]
+        own2 = owned(g2, s2)[np.maximum(ev2, 0)]
+        keep = np.where(is_a, own1, np.where(is_b, own2, own1))
+    ev1, ev2, grp_of, is_a, is_b = ev1[keep], ev2[keep], grp_of[keep], is_a[keep], is_b[keep]
+    counts = np.zeros((nb, 4), dtype=np.int64)
+    np.add.at(counts[:, 0], grp_of[is_a], 1)
+    np.add.at(counts[:, 1], grp_of[is_b], 1)
+    np.add.at(counts[:, 2], grp_of[(ev2 < 0)], 1)
+    n_own = set1.n if n_own1 is None else int(n_own1)
+    out1 = ev1 + row_offset1
+    if n_own < set1.n:
+        halo = np.asarray(halo_ids, dtype=np.int64)
+        out1 = np.where(ev1 >= n_own, halo[np.maximum(ev1 - n_own, 0)], out1)
+    res = (torch.from_numpy(out1), torch.from_numpy(np.where(ev2 >= 0, ev2 + row_offset2, -1)), int(paired[keep].sum()))
+    return (*res, counts) if want_group_counts else res

@@ -31,10 +31,17 @@ def arrops(monkeypatch, request):
     return mod
 
 
-def test_overlap_merge_complement_cases(arrops, arrops_golden):
+def test_overlap_merge_complement_cases(arrops, arrops_golden, request):
     g = arrops_golden
+    on_cuda = "cuda" in request.node.name
     for name in g["names"]:
         s1, e1, s2, e2 = (g[f"{name}/{k}"] for k in ("s1", "e1", "s2", "e2"))
+        if name == "wide" and on_cuda:
+            # one group whose STARTS span -100 .. 2^63-6: no 64-bit (position, length) key holds it; the CUDA
+            # engine refuses loudly instead of answering wrongly
+            with pytest.raises(OverflowError):
+                arrops.overlap_intervals(s1, e1, s2, e2)
+            continue
         for closed in (0, 1):
             i, j = arrops.overlap_intervals(s1, e1, s2, e2, closed=bool(closed))
             assert i.dtype == np.int64 and j.dtype == np.int64
