@@ -5,20 +5,34 @@ One "step" = one pass of `_overlap_intidxs(how='left')` over
 the cfg3 workload of BASELINE.json: 1e8 synthetic hg38 queries (Geometric mean
 2 kb) against 1e7 peak-like targets, ~9 overlaps per query, ~9e8 output rows.
 
-  value       (N1*n_gpus + N2) / t, inputs resident in HBM, CUDA-event timed
-  e2e         same call with HOST (pinned) buffers: H2D of the three columns of
-              both sets and D2H of both int64 result columns inside the timed region
-  roofline    dominant kernel = one onesweep radix pass over the query keys:
-              24 B/row algorithmic (8 B key + 4 B row id, read and written)
-  cpu_baseline the numpy oracle port of the reference algorithm on a bounded,
-              same-density sample (chr21+chr22 share of both sets), 1 core
+  value        (N1*n_gpus + N2) / t, inputs resident in HBM, CUDA-event timed
+  e2e          same call with HOST (pinned) buffers: H2D of the three columns of
+               both sets and D2H of both int64 result columns inside the timed region
+  roofline     dominant kernel = one onesweep radix pass over the query keys
+  cpu_baseline the REFERENCE itself (`bioframe.ops._overlap_intidxs` from the vendored
+               baseline/_ref, oracle/make_ref.py; the numpy port only if that copy is
+               missing) on a bounded, same-density sample (chr21+chr22), 1 core
+  parity_checked  the GPU rows of that sample equal the reference's rows, in order
+  frame_e2e    DataFrames in, DataFrames out through `bioframe_b200.overlap` /
+               `ops._overlap_intidxs`, the reference's `bioframe.overlap` beside it,
+               and where the call spends its time (encode / H2D / kernels / D2H / frame)
+  secondary    the other BASELINE.json configs (cfg0 overlap inner 1e6 x 1e6, cfg1
+               closest, cfg2 cluster, cfg3 coverage) at 3 steps each
 
-`--impl reference` times only that CPU port (there is no other reference
-implementation of this path: the reference is pure numpy/pandas).
+`--impl reference` times the reference's `_overlap_intidxs` on DataFrames with a
+categorical chromosome column, all 24 chromosomes of the workload at full density
+spread over every host core (one process per core, chromosomes bin-packed).
 
-N > 1 (torchrun): queries are sharded (each rank owns 1e8 of them, weak
-scaling), the target columns are broadcast from rank 0 over NCCL inside every
-step, no other collective.
+N > 1 (torchrun): the queries are sharded by contiguous (chrom, start) ranges (rank r
+owns the r-th slice of the end-to-end genome axis and 1e8 queries in it: weak
+scaling; `--scaling strong`: 1e8 queries in total), the targets are sorted once on
+rank 0 and their sorted keys + row ids are broadcast over NCCL on a side stream
+while every rank sorts its own queries; the only other collective is one MAX
+all-reduce of a few hundred bytes (the shared key layout).  Every rank produces its
+part of the reference's row order (bioframe_b200/sharded.py); after the timed region
+the result of every rank is checked against the single-GPU engine
+(`sharded_verified`).  `--workload cfg4`: BASELINE.json configs[4], 1e9 sorted
+queries x 1e8 targets over the ranks.
 """
 from __future__ import annotations
 
@@ -48,24 +62,48 @@ def parse():
     ap.add_argument("--n2", type=int, default=10_000_000)
     ap.add_argument("--how", default="left", choices=["inner", "left", "right", "outer"])
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--chunks", type=int, default=4, help="cfg4: query chunks (virtual shards) per rank")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="overlap", choices=["overlap", "closest", "cluster", "coverage", "count", "subtract", "ingest", "ordered"],
-                    help="overlap = the north-star line (cfg3); the others are the secondary BASELINE.json configs "
-                         "(closest: cfg1 1e7 x 1e6 k=1; cluster: cfg2 1e8 heavy-tailed; coverage: cfg3 sets)")
+    ap.add_argument("--no-frame", action="store_true", help="skip the DataFrame-level leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE.json configs")
+    ap.add_argument("--no-verify", action="store_true", help="N>1: skip the check against the single-GPU engine")
+    ap.add_argument("--workload", default="overlap",
+                    choices=["overlap", "cfg4", "cfg0", "closest", "cluster", "coverage", "count", "subtract", "ingest", "ordered"],
+                    help="overlap = the north-star line (cfg3); cfg4 = 1e9 x 1e8 over the ranks; the others are the "
+                         "secondary configs (cfg0: overlap inner 1e6 x 1e6; closest: cfg1 1e7 x 1e6 k=1; cluster: cfg2 1e8 "
+                         "heavy-tailed; coverage: cfg3 sets)")
     ap.add_argument("--k", type=int, default=1)
     return ap.parse_args()
 
 
+_WL_CACHE = {}
+
+
 def workload(n1, n2, rank, chrom_ids=None):
+    """cfg3 sets (host numpy); the full-size draw is kept for the legs of one run that share it."""
+    from bioframe_b200 import synth
+
+    key = (n1, n2, rank, tuple(chrom_ids) if chrom_ids is not None else None)
+    if key in _WL_CACHE:
+        return _WL_CACHE[key]
+    frac = synth.subset_fraction(chrom_ids) if chrom_ids is not None else 1.0
+    m1 = max(int(n1 * frac), 1)
+    q = synth.make_intervals(m1, 1 + 1000 * rank, "geom2k", chrom_ids=chrom_ids)
+    t = targets(n2, chrom_ids)
+    if chrom_ids is None:
+        _WL_CACHE.clear()
+        _WL_CACHE[key] = (q, t)
+    return q, t
+
+
+def targets(n2, chrom_ids=None):
     from bioframe_b200 import synth
 
     frac = synth.subset_fraction(chrom_ids) if chrom_ids is not None else 1.0
-    m1, m2 = max(int(n1 * frac), 1), max(int(n2 * frac), 1)
-    q = synth.make_intervals(m1, 1 + 1000 * rank, "geom2k", chrom_ids=chrom_ids)
     hot = max(int(200_000 * frac * (n2 / 1e7)), 1)
-    t = synth.make_peak_targets(m2, 2, n_hotspots=hot, chrom_ids=chrom_ids)
-    return q, t
+    return synth.make_peak_targets(max(int(n2 * frac), 1), 2, n_hotspots=hot, chrom_ids=chrom_ids)
 
 
 def workload_desc(how, n1, n2):
@@ -73,27 +111,88 @@ def workload_desc(how, n1, n2):
             "unsorted")
 
 
-def cpu_leg(args, steps, warmup):
-    """Oracle port on the bounded sample; returns (intervals/s, description, ms/step, rows)."""
+def cores_available():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+        if "hbm_gbs" in peaks:
+            return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ reference / oracle
+def reference_module():
+    """The vendored reference (baseline/_ref, oracle/make_ref.py) or None.  /root/reference is never read."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import make_ref
+
+        return make_ref.import_reference()
+    except Exception:
+        return None
+
+
+def reference_frame(g, s, e, categorical=True):
+    """hg38 interval frame the way a bioframe user holds it: chrom as names (categorical: the fast case of
+    docs/guide-performance.ipynb:497-498)."""
+    import pandas as pd
+
+    from bioframe_b200 import synth
+
+    if categorical:
+        chrom = pd.Categorical.from_codes(np.asarray(g), categories=synth.HG38_CHROMS)
+    else:
+        chrom = np.array(synth.HG38_CHROMS, dtype=object)[np.asarray(g)]
+    return pd.DataFrame({"chrom": chrom, "start": s, "end": e})
+
+
+def cpu_overlap(q, t, how, order_by_code=False):
+    """One pass of the reference path on the host.  -> (events1, events2, kind).  With order_by_code the chromosome
+    column holds the integer group codes, which makes the reference visit its groups in code order (the C ABI's
+    order) instead of the process's string-hash order: used where the rows are compared."""
+    bf = reference_module()
+    if bf is not None:
+        import pandas as pd
+
+        if order_by_code:
+            df1 = pd.DataFrame({"chrom": q[0].astype(np.int64), "start": q[1], "end": q[2]})
+            df2 = pd.DataFrame({"chrom": t[0].astype(np.int64), "start": t[1], "end": t[2]})
+        else:
+            df1, df2 = reference_frame(*q), reference_frame(*t)
+        a, b = bf.ops._overlap_intidxs(df1, df2, how=how)
+        return np.asarray(a, dtype=np.int64), np.asarray(b, dtype=np.int64), "reference"
     from oracle import ops_oracle as oo
 
-    (g1, s1, e1), (g2, s2, e2) = workload(args.n1, args.n2, 0, chrom_ids=SAMPLE_CHROMS)
-    times = []
-    rows = 0
+    a, b = oo.overlap_intidxs_coded(*q, *t, N_GROUPS, how=how)
+    return a, b, "port"
+
+
+def cpu_leg(args, steps, warmup):
+    """The reference on the bounded sample, 1 core; returns a dict with the rate, the sample and its rows."""
+    q, t = workload(args.n1, args.n2, 0, chrom_ids=SAMPLE_CHROMS)
+    times, rows, kind = [], 0, "port"
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        ev1, _ = oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, N_GROUPS, how=args.how)
+        ev1, ev2, kind = cpu_overlap(q, t, args.how, order_by_code=True)
         dt = time.perf_counter() - t0
         rows = int(ev1.shape[0])
         if it >= warmup:
             times.append(dt)
-    t = float(np.mean(times))
-    n = len(s1) + len(s2)
-    desc = (
-        f"chr21+chr22 share of the workload at full density: {len(s1)} x {len(s2)} intervals -> "
-        f"{rows} rows per step, numpy oracle port of ops._overlap_intidxs(how={args.how!r})"
-    )
-    return n / t, desc, t * 1e3, rows
+    tm = float(np.mean(times))
+    n = len(q[1]) + len(t[1])
+    what = "bioframe.ops._overlap_intidxs (reference v0.8.0, baseline/_ref)" if kind == "reference" else "numpy oracle port of ops._overlap_intidxs"
+    desc = (f"chr21+chr22 share of the workload at full density: {len(q[1])} x {len(t[1])} intervals -> {rows} rows per step, "
+            f"{what}(how={args.how!r})")
+    return dict(value=n / tm, desc=desc, ms=tm * 1e3, rows=rows, kind=kind, q=q, t=t, ev1=ev1, ev2=ev2)
 
 
 class ClockSampler(threading.Thread):
@@ -152,41 +251,58 @@ def pin_to_gpu_numa_node(index):
         pass
 
 
-def _reference_worker(conn, n1, n2, how, chrom):
-    """One process of the reference arm: the per-chromosome body of the reference's loop (ops.py:301-336) on one
-    chromosome of the workload at full density, run whenever the parent says go."""
-    from oracle import ops_oracle as oo
+# ------------------------------------------------------------------------------------------ --impl reference
+def _reference_worker(conn, n1, n2, how, chroms):
+    """One process of the reference arm: the reference's `_overlap_intidxs` (ops.py:242-338) on DataFrames that
+    hold this worker's chromosomes of the workload at full density, run whenever the parent says go."""
+    q, t = workload(n1, n2, 0, chrom_ids=tuple(chroms))
+    bf = reference_module()
+    if bf is not None:
+        df1, df2 = reference_frame(*q), reference_frame(*t)
+        call = lambda: bf.ops._overlap_intidxs(df1, df2, how=how)  # noqa: E731
+        kind = "reference"
+    else:
+        from oracle import ops_oracle as oo
 
-    (g1, s1, e1), (g2, s2, e2) = workload(n1, n2, 0, chrom_ids=(chrom,))
-    conn.send((len(s1), len(s2)))
+        call = lambda: oo.overlap_intidxs_coded(*q, *t, N_GROUPS, how=how)  # noqa: E731
+        kind = "port"
+    conn.send((len(q[1]), len(t[1]), kind))
     while conn.recv():
-        ev1, _ = oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, N_GROUPS, how=how)
-        conn.send(int(ev1.shape[0]))
+        ev1, _ = call()
+        conn.send(int(len(ev1)))
+
+
+def pack_chromosomes(n_bins):
+    """All 24 chromosomes over n_bins workers, longest first into the lightest bin (the work is ~linear in length)."""
+    from bioframe_b200 import synth
+
+    bins = [[] for _ in range(n_bins)]
+    load = [0] * n_bins
+    for c in np.argsort(-synth.HG38_SIZES):
+        b = int(np.argmin(load))
+        bins[b].append(int(c))
+        load[b] += int(synth.HG38_SIZES[c])
+    return [sorted(b) for b in bins if b]
 
 
 def reference_leg_all_cores(args, steps, warmup):
-    """The reference's algorithm on every host core: its chromosome groups are independent, so one process per
-    chromosome is how its user spreads it over a machine.  The `cores` smallest chromosomes of the workload at
-    full density, one per process, all started together; a step ends when the slowest process is done.
-    Returns (intervals/s, description, ms/step, rows, cores)."""
+    """The reference on every host core: its chromosome groups are independent (ops.py:301-338), so one process
+    per core, each holding a share of the chromosomes, is how its user spreads it over a machine.  ALL 24
+    chromosomes of the workload at full density; a step ends when the slowest process is done.
+    Returns (intervals/s, description, ms/step, rows, cores, kind)."""
     import multiprocessing as mp
 
-    from bioframe_b200 import synth
-
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        cores = os.cpu_count() or 1
-    cores = max(1, min(cores, N_GROUPS))
-    chroms = [int(c) for c in np.argsort(synth.HG38_SIZES)[:cores]]
+    cores = max(1, min(cores_available(), N_GROUPS))
+    bins = pack_chromosomes(cores)
     ctx = mp.get_context("spawn")  # the parent may hold a CUDA context: never fork it
     procs = []
-    for c in chroms:
+    for chroms in bins:
         parent, child = ctx.Pipe()
-        pr = ctx.Process(target=_reference_worker, args=(child, args.n1, args.n2, args.how, c), daemon=True)
+        pr = ctx.Process(target=_reference_worker, args=(child, args.n1, args.n2, args.how, chroms), daemon=True)
         pr.start()
         procs.append((pr, parent))
     sizes = [conn.recv() for _, conn in procs]
+    kind = sizes[0][2]
     times, rows = [], 0
     for it in range(warmup + steps):
         t0 = time.perf_counter()
@@ -199,22 +315,20 @@ def reference_leg_all_cores(args, steps, warmup):
     for pr, conn in procs:
         conn.send(False)
         pr.join(timeout=10)
-    t = float(np.mean(times))
-    n = sum(a + b for a, b in sizes)
-    names = ",".join(synth.HG38_CHROMS[c] for c in chroms)
-    desc = (
-        f"{cores} processes, one chromosome each ({names}) of the workload at full density: "
-        f"{sum(a for a, _ in sizes)} x {sum(b for _, b in sizes)} intervals -> {rows} rows per step, numpy oracle port "
-        f"of the per-chromosome body of ops._overlap_intidxs(how={args.how!r})"
-    )
-    return n / t, desc, t * 1e3, rows, cores
+    tm = float(np.mean(times))
+    n = sum(a + b for a, b, _ in sizes)
+    what = ("bioframe.ops._overlap_intidxs of the reference (v0.8.0, baseline/_ref) on DataFrames with a categorical chrom column"
+            if kind == "reference" else "numpy oracle port of ops._overlap_intidxs (baseline/_ref missing)")
+    desc = (f"{len(bins)} processes sharing all 24 chromosomes of the workload at full density: "
+            f"{sum(a for a, _, _ in sizes)} x {sum(b for _, b, _ in sizes)} intervals -> {rows} rows per step, {what}, how={args.how!r}")
+    return n / tm, desc, tm * 1e3, rows, len(bins), kind
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, desc, ms, rows, cores = reference_leg_all_cores(args, args.steps, args.warmup)
+    val, desc, ms, rows, cores, kind = reference_leg_all_cores(args, args.steps, args.warmup)
     line = {
         "impl": "reference",
         "metric": "bf.overlap input intervals/s",
@@ -225,19 +339,20 @@ def run_reference(args):
         "warmup": args.warmup,
         "ms_per_step": ms,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": args.scaling,
         "vs_baseline": None,
         "dtype": "int64",
         "data": "synthetic",
         "config": {"workload": workload_desc(args.how, args.n1, args.n2), "n1_per_gpu": args.n1, "n2": args.n2,
-                   "sample": desc},
-        "cpu_baseline": {"value": val, "unit": "intervals/s", "cores": cores, "kind": "port", "sample": desc},
+                   "rows_out": rows, "sample": desc},
+        "cpu_baseline": {"value": val, "unit": "intervals/s", "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": val, "unit": "intervals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ secondary configs
 def _ingest_device(text, raw, dev):
     """The device part of bioframe_b200.io.read_bed_device on text that already is on the GPU; returns the row count."""
     import ctypes as C
@@ -273,22 +388,41 @@ def _ingest_device(text, raw, dev):
     return n_rows.value
 
 
-def run_secondary(args):
-    """closest / cluster / coverage at their BASELINE.json sizes, single GPU: device-resident inputs,
-    CUDA-event timing of the whole call, whole-call algorithmic bytes against the measured
-    HBM peak, and the oracle port on a bounded sample beside it."""
+def _named_frame(g, s, e):
+    """frame with string chromosome names whose sorted order is the code order (what cluster / merge / coverage of
+    the reference need: they validate the chrom dtype, ops.py:758)"""
+    import pandas as pd
+
+    names = np.array([f"c{c:02d}" for c in range(N_GROUPS)], dtype=object)
+    return pd.DataFrame({"chrom": names[np.asarray(g)], "start": s, "end": e})
+
+
+def secondary_line(args, wl, steps, warmup, with_cpu=True):
+    """One secondary config: device-resident inputs, CUDA-event timing of the whole call, whole-call algorithmic
+    bytes against the measured HBM peak, and the reference on a bounded sample beside it."""
     import torch
 
     from bioframe_b200 import _lib, engine, synth
     from oracle import ops_oracle as oo
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(dev)
-    wl = args.workload
+    dev = torch.device("cuda", torch.cuda.current_device())
+    bf = reference_module() if with_cpu else None
+    cpu_kind = "reference" if bf is not None else "port"
     cpu_sample = None
-    if wl == "closest":
+    frac = synth.subset_fraction(SAMPLE_CHROMS)
+    if wl == "cfg0":
+        n1, n2 = 1_000_000, 1_000_000
+        q, t = synth.make_intervals(n1, 1, "geom1k"), synth.make_intervals(n2, 2, "geom1k")
+        d = [torch.from_numpy(a).to(dev) for a in (*q, *t)]
+        call = lambda: engine.overlap_intidxs(d[0], d[1], d[2], d[3], d[4], d[5], N_GROUPS, how="inner")  # noqa: E731
+        rows_of = lambda r: int(r[0].numel())  # noqa: E731
+        a_alg = lambda R: 256 * (n1 + n2) + 20 * R  # noqa: E731
+        units, name = n1 + n2, "bf.overlap(how='inner') input intervals/s"
+        desc = f"_overlap_intidxs(how='inner') cfg0: {n1} x {n2} hg38 intervals (geom 1kb), unsorted"
+        cpu = lambda: cpu_overlap(q, t, "inner")  # noqa: E731  (the WHOLE config: it is the reference's own CPU-runnable case)
+        cpu_units = n1 + n2
+        cpu_sample = f"the whole cfg0 workload ({n1} x {n2}), bioframe.ops._overlap_intidxs on categorical-chrom DataFrames" if bf is not None else None
+    elif wl == "closest":
         n1, n2 = (args.n1 if args.n1 != 100_000_000 else 10_000_000), (args.n2 if args.n2 != 10_000_000 else 1_000_000)
         q = synth.make_intervals(n1, 1, "geom1k")
         t = synth.make_intervals(n2, 2, "geom1k")
@@ -298,10 +432,13 @@ def run_secondary(args):
         a_alg = lambda R: 2 * 256 * n2 + 36 * n1 + 20 * R  # noqa: E731
         units, name = n1 + n2, f"bf.closest(k={args.k}) input intervals/s"
         desc = f"_closest_intidxs cfg1: {n1} hg38 queries x {n2} targets (geom 1kb), k={args.k}, unsorted"
-        frac = synth.subset_fraction(SAMPLE_CHROMS)
         sq = synth.make_intervals(int(n1 * frac), 1, "geom1k", chrom_ids=SAMPLE_CHROMS)
         stt = synth.make_intervals(int(n2 * frac), 2, "geom1k", chrom_ids=SAMPLE_CHROMS)
-        cpu = lambda: oo.closest_intidxs_coded(*sq, *stt, N_GROUPS, k=args.k)  # noqa: E731
+        if bf is not None:
+            f1, f2 = reference_frame(*sq), reference_frame(*stt)
+            cpu = lambda: bf.ops._closest_intidxs(f1, f2, k=args.k)  # noqa: E731
+        else:
+            cpu = lambda: oo.closest_intidxs_coded(*sq, *stt, N_GROUPS, k=args.k)  # noqa: E731
         cpu_units = len(sq[1]) + len(stt[1])
     elif wl == "cluster":
         n1 = args.n1
@@ -312,9 +449,12 @@ def run_secondary(args):
         a_alg = lambda C: 256 * n1 + 12 * n1 + 28 * C  # noqa: E731
         units, name = n1, "bf.cluster input intervals/s"
         desc = f"cluster+merge table cfg2: {n1} hg38 intervals, Pareto(1.2) lengths capped 5 Mb, unsorted"
-        frac = synth.subset_fraction(SAMPLE_CHROMS)
         sq = synth.make_intervals(int(n1 * frac), 1, "pareto", chrom_ids=SAMPLE_CHROMS)
-        cpu = lambda: oo.cluster_coded(*sq, N_GROUPS, 0)  # noqa: E731
+        if bf is not None:
+            f1 = _named_frame(*sq)
+            cpu = lambda: bf.cluster(f1, min_dist=0)  # noqa: E731
+        else:
+            cpu = lambda: oo.cluster_coded(*sq, N_GROUPS, 0)  # noqa: E731
         cpu_units = len(sq[1])
     elif wl == "count":
         n1, n2 = args.n1, args.n2
@@ -326,7 +466,11 @@ def run_secondary(args):
         units, name = n1 + n2, "bf.count_overlaps input intervals/s"
         desc = f"count_overlaps cfg3: {n1} hg38 queries (geom 2kb) x {n2} peak-like targets"
         (sq, stt) = workload(n1, n2, 0, chrom_ids=SAMPLE_CHROMS)
-        cpu = lambda: np.bincount(oo.overlap_intidxs_coded(*sq, *stt, N_GROUPS, how="inner")[0], minlength=len(sq[1]))  # noqa: E731
+        if bf is not None:
+            f1, f2 = _named_frame(*sq), _named_frame(*stt)
+            cpu = lambda: bf.count_overlaps(f1, f2)  # noqa: E731
+        else:
+            cpu = lambda: np.bincount(oo.overlap_intidxs_coded(*sq, *stt, N_GROUPS, how="inner")[0], minlength=len(sq[1]))  # noqa: E731
         cpu_units = len(sq[1]) + len(stt[1])
     elif wl == "ingest":
         import io as _io
@@ -352,6 +496,7 @@ def run_secondary(args):
         desc = f"bed3 ingest: {n1} lines, {nbytes} bytes of tab-separated text (hg38 names, geom 2kb intervals)"
         cpu = lambda: pd.read_csv(_io.BytesIO(buf.getvalue()), sep="\t", header=None, names=["chrom", "start", "end"])  # noqa: E731
         cpu_units = n1
+        cpu_kind = "reference"
         cpu_sample = "the same text through pandas.read_csv(sep=TAB, header=None), which is what the reference's read_table calls"
     elif wl == "ordered":
         n1, n2 = args.n1, args.n2
@@ -365,7 +510,7 @@ def run_secondary(args):
         (sq, stt) = workload(n1, n2, 0, chrom_ids=SAMPLE_CHROMS)
 
         def cpu():
-            a, b = oo.overlap_intidxs_coded(*sq, *stt, N_GROUPS, how="left")
+            a, b, _ = cpu_overlap(sq, stt, "left")
             return np.lexsort([np.where(b < 0, len(stt[1]) + 1, b), a])
 
         cpu_units = len(sq[1]) + len(stt[1])
@@ -379,7 +524,11 @@ def run_secondary(args):
         units, name = n1 + n2, "bf.subtract input intervals/s"
         desc = f"subtract cfg3: {n1} hg38 queries (geom 2kb) minus {n2} peak-like targets"
         (sq, stt) = workload(n1, n2, 0, chrom_ids=SAMPLE_CHROMS)
-        cpu = lambda: oo.subtract_coded(*sq, *stt, N_GROUPS)  # noqa: E731
+        if bf is not None:
+            f1, f2 = _named_frame(*sq), _named_frame(*stt)
+            cpu = lambda: bf.subtract(f1, f2)  # noqa: E731
+        else:
+            cpu = lambda: oo.subtract_coded(*sq, *stt, N_GROUPS)  # noqa: E731
         cpu_units = len(sq[1]) + len(stt[1])
     else:  # coverage
         n1, n2 = args.n1, args.n2
@@ -391,10 +540,14 @@ def run_secondary(args):
         units, name = n1 + n2, "bf.coverage input intervals/s"
         desc = f"coverage cfg3: {n1} hg38 queries (geom 2kb) x {n2} peak-like targets"
         (sq, stt) = workload(n1, n2, 0, chrom_ids=SAMPLE_CHROMS)
-        cpu = lambda: oo.coverage_coded(*sq, *stt, N_GROUPS)  # noqa: E731
+        if bf is not None:
+            f1, f2 = _named_frame(*sq), _named_frame(*stt)
+            cpu = lambda: bf.coverage(f1, f2)  # noqa: E731
+        else:
+            cpu = lambda: oo.coverage_coded(*sq, *stt, N_GROUPS)  # noqa: E731
         cpu_units = len(sq[1]) + len(stt[1])
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         r = call()
     R = rows_of(r)
     del r
@@ -403,42 +556,184 @@ def run_secondary(args):
     torch.cuda.synchronize(dev)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         r = call()
         del r
     t1.record()
     torch.cuda.synchronize(dev)
-    ms = t0.elapsed_time(t1) / args.steps
+    ms = t0.elapsed_time(t1) / steps
     prof = _lib.prof_read()
     _lib.prof_enable(False)
-    peak = 6554.6
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peak = float(json.load(f).get("hbm_gbs", peak))
-    except Exception:
-        pass
+    peak, _src = hbm_peak()
     alg = a_alg(R)
     line = {
-        "metric": name, "value": units / (ms * 1e-3), "unit": "intervals/s", "n_gpus": 1, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "metric": name, "value": units / (ms * 1e-3), "unit": "intervals/s", "n_gpus": 1, "steps": steps,
+        "warmup": max(warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": desc, "rows_out": R, "l2": "inputs and intermediates exceed the 126 MB L2"},
+        "config": {"workload": desc, "rows_out": R, "l2": "inputs and intermediates exceed the 126 MB L2" if units > 5e6 else
+                   "inputs fit the 126 MB L2: launch-latency bound (SURVEY.md 8d), reported, not tuned for"},
         "gpu_launches": sum(v["launches"] for v in prof.values()),
         "roofline": {"bound": "hbm", "kernel": "whole call (A_alg of SURVEY.md 8d)", "achieved": alg / (ms * 1e-3) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
-                     "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}},
+                     "kernel_ms_per_step": {k: v["ms"] / steps for k, v in prof.items()}},
     }
-    if not args.no_cpu:
+    if with_cpu:
         times = []
         for it in range(2):
             w0 = time.perf_counter()
             cpu()
             times.append(time.perf_counter() - w0)
-        line["cpu_baseline"] = {"value": cpu_units / min(times), "unit": "intervals/s", "cores": 1,
-                                "kind": "reference" if wl == "ingest" else "port",
-                                "sample": cpu_sample or f"chr21+chr22 share of the workload at full density ({cpu_units} intervals), numpy oracle port",
+        what = "the reference (bioframe v0.8.0, baseline/_ref)" if cpu_kind == "reference" else "numpy oracle port"
+        line["cpu_baseline"] = {"value": cpu_units / min(times), "unit": "intervals/s", "cores": 1, "kind": cpu_kind,
+                                "sample": cpu_sample or f"chr21+chr22 share of the workload at full density ({cpu_units} intervals), {what}",
                                 "ms_per_step": min(times) * 1e3}
-    print(json.dumps(line), flush=True)
+    del d
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_secondary(args):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(0)
+    print(json.dumps(secondary_line(args, args.workload, args.steps, args.warmup, with_cpu=not args.no_cpu)), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ DataFrame-level leg
+def frame_leg(args):
+    """DataFrames in, DataFrames out (VERDICT r1 Missing #7): the public `bioframe_b200.overlap` and the seam
+    `ops._overlap_intidxs` on pandas frames (categorical chrom + a string `name` column), wall clock around the
+    whole call -- validation, group encoding, H2D, kernels, D2H, frame assembly -- with the reference's own call
+    timed beside it on the same frames, and the equality of the two results."""
+    import pandas as pd
+
+    import bioframe_b200 as ours
+    from bioframe_b200 import ops as our_ops
+    from bioframe_b200 import synth
+
+    bf = reference_module()
+    out = {}
+
+    def frames(n1, n2, kind1, kind2):
+        q, t = synth.make_intervals(n1, 1, kind1), synth.make_intervals(n2, 2, kind2)
+        df1, df2 = reference_frame(*q), reference_frame(*t)
+        df1["name"] = np.array([f"q{i}" for i in range(1000)], dtype=object)[np.arange(n1) % 1000]
+        df2["score"] = (np.arange(n2) % 97).astype(np.float64)
+        return df1, df2
+
+    def wall(fn, reps):
+        best, res = None, None
+        for _ in range(reps):
+            w0 = time.perf_counter()
+            res = fn()
+            dt = time.perf_counter() - w0
+            best = dt if best is None else min(best, dt)
+        return best, res
+
+    for tag, n1, n2 in (("cfg0_1e6x1e6", 1_000_000, 1_000_000), ("1e7x1e6", 10_000_000, 1_000_000)):
+        df1, df2 = frames(n1, n2, "geom1k", "geom1k")
+        entry = {"n1": n1, "n2": n2, "columns": "chrom (categorical), start, end, name (str) | chrom, start, end, score (f64)"}
+        ours.overlap(df1.iloc[:1000], df2.iloc[:1000], how="inner")  # warm the library
+        t_idx, idx = wall(lambda: our_ops._overlap_intidxs(df1, df2, how="inner"), 2)
+        t_all, got = wall(lambda: ours.overlap(df1, df2, how="inner"), 2)
+        with our_ops.profile() as prof:
+            ours.overlap(df1, df2, how="inner")
+        stages = {k: round(v * 1e3, 2) for k, v in prof.items()}
+        pandas_ms = stages.get("validate", 0) + stages.get("encode_groups", 0) + stages.get("assemble_frame", 0)
+        entry["bioframe_b200"] = {"_overlap_intidxs_ms": t_idx * 1e3, "overlap_inner_ms": t_all * 1e3, "rows": int(len(got)),
+                                  "intervals_per_s": (n1 + n2) / t_all, "stages_ms_profiled": stages,
+                                  "pandas_share_profiled": pandas_ms / max(sum(stages.values()), 1e-9)}
+        if bf is not None:
+            r_idx, ridx = wall(lambda: bf.ops._overlap_intidxs(df1, df2, how="inner"), 1)
+            r_all, want = wall(lambda: bf.overlap(df1, df2, how="inner"), 1)
+            key = [c for c in got.columns if c not in ("chrom", "chrom_")]
+            same_pairs = bool(np.array_equal(np.sort(idx[0] * (n2 + 1) + idx[1]), np.sort(ridx[0] * (n2 + 1) + ridx[1])))
+            a = got.sort_values(key, kind="stable").reset_index(drop=True)
+            b = want.sort_values(key, kind="stable").reset_index(drop=True)
+            try:
+                pd.testing.assert_frame_equal(a, b)
+                same_frame = True
+            except AssertionError:
+                same_frame = False
+            entry["reference"] = {"_overlap_intidxs_ms": r_idx * 1e3, "overlap_inner_ms": r_all * 1e3, "cores": 1,
+                                  "intervals_per_s": (n1 + n2) / r_all}
+            entry["speedup_overlap_inner"] = r_all / t_all
+            entry["speedup_overlap_intidxs"] = r_idx / t_idx
+            entry["frames_equal_to_reference"] = same_frame and same_pairs
+            entry["note"] = "rows compared after sorting both frames: the reference's chromosome-block order follows the string hash seed"
+        out[tag] = entry
+        del df1, df2, got
+    # the seam at the benchmark size: DataFrames (categorical chrom) -> int64 numpy index arrays on the host
+    q, t = workload(args.n1, args.n2, 0)
+    df1, df2 = reference_frame(*q), reference_frame(*t)
+    del q, t
+    t_idx, idx = wall(lambda: our_ops._overlap_intidxs(df1, df2, how=args.how), 1)
+    with our_ops.profile() as prof:
+        our_ops._overlap_intidxs(df1, df2, how=args.how)
+    out["cfg3_intidxs_frames"] = {
+        "what": f"bioframe_b200.ops._overlap_intidxs(df1, df2, how={args.how!r}) on DataFrames of {len(df1)} / {len(df2)} rows",
+        "ms": t_idx * 1e3, "rows": int(len(idx[0])), "intervals_per_s": (len(df1) + len(df2)) / t_idx,
+        "stages_ms_profiled": {k: round(v * 1e3, 1) for k, v in prof.items()},
+    }
+    return out
+
+
+# ------------------------------------------------------------------------------------------ N > 1: range shards
+def exchange_halo(q_local, rank, world, reach_of, dev):
+    """Setup, outside the timed region (the partition of df1 into shards + halo rows is the host's job, SURVEY.md
+    8e): every rank receives the queries of later ranks that a target of its own range can still reach --
+    queries of its upper bound's chromosome with start below reach_of[r].  -> (grp, start, end, global row ids)
+    of this rank's halo rows."""
+    import torch.distributed as dist
+
+    from bioframe_b200 import synth
+
+    g, s, e = q_local
+    n = len(s)
+    send = {}
+    for r in range(rank):  # earlier shards whose reach extends into this rank's rows
+        g_hi, s_hi = synth.range_bounds(r, world)[2:]
+        if g_hi >= N_GROUPS:
+            continue
+        m = np.flatnonzero((g == g_hi) & (s < reach_of[r]))
+        if len(m):
+            send[r] = (g[m], s[m], e[m], m.astype(np.int64) + rank * n)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, send)
+    parts = [gathered[r][rank] for r in range(world) if rank in gathered[r]]
+    if not parts:
+        z = np.empty(0, np.int64)
+        return np.empty(0, np.int32), z, z.copy(), z.copy()
+    return tuple(np.concatenate([p[i] for p in parts]) for i in range(4))
+
+
+def verify_shard(engine, dq, n_own, own_range, halo_ids, row_offset, dt, how, got):
+    """The rows this rank produced against the single-GPU engine: bf_overlap_count/emit (its own sort, its own
+    key layout) on the same local queries (own + halo) and all targets, with the rows another shard owns dropped
+    -- an A-block pair (target starts at or after the query, arrops.py:338-339) belongs to the query's shard,
+    a B-block pair (query starts after the target, arrops.py:341-342) to the target's, an unpaired row to the
+    query's.  Dropping rows keeps the order, so the two must be equal row for row."""
+    import torch
+
+    ev1, ev2, _ = engine.overlap_intidxs(*dq, *dt, N_GROUPS, how=how)
+    g1, s1 = dq[0], dq[1]
+    g2, s2 = dt[0], dt[1]
+    g_lo, s_lo, g_hi, s_hi = own_range
+
+    def owned(g, s):
+        return ((g > g_lo) | ((g == g_lo) & (s >= s_lo))) & ((g < g_hi) | ((g == g_hi) & (s < s_hi)))
+
+    a, b = ev1.clamp(min=0), ev2.clamp(min=0)
+    paired = ev2 >= 0
+    is_a = paired & (s2[b] >= s1[a])
+    own1 = owned(g1[a], s1[a])
+    own2 = owned(g2[b], s2[b])
+    keep = torch.where(is_a, own1, torch.where(paired, own2, own1))
+    ev1, ev2 = ev1[keep], ev2[keep]
+    want1 = torch.where(ev1 < n_own, ev1 + row_offset, halo_ids[(ev1 - n_own).clamp(min=0)] if halo_ids.numel() else ev1)
+    return bool(torch.equal(want1, got[0]) and torch.equal(ev2, got[1]))
 
 
 def main():
@@ -446,14 +741,14 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
-    if args.workload != "overlap":
+    if args.workload not in ("overlap", "cfg4"):
         run_secondary(args)
         return
 
     import torch
     import torch.distributed as dist
 
-    from bioframe_b200 import _lib, engine, sharded
+    from bioframe_b200 import _lib, engine, sharded, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -466,35 +761,124 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
+    cfg4 = args.workload == "cfg4"
+    ranged = world > 1 or cfg4
+    chunks = max(args.chunks, 1) if cfg4 else 1
 
     # ---- synthetic workload, host side (pinned: the e2e leg copies from here) ----
-    (g1, s1, e1), (g2, s2, e2) = workload(args.n1, args.n2, rank)
-    host = [torch.from_numpy(a).pin_memory() for a in (g1, s1, e1, g2, s2, e2)]
-    n1, n2 = len(s1), len(s2)
-    del g1, s1, e1, g2, s2, e2  # the pinned copies are the host side from here on
-    d = [h.to(dev) for h in host]
-    if world > 1 and rank != 0:
-        for t in d[3:]:
-            t.zero_()  # targets arrive by broadcast
-    h2d_bytes = sum(h.numel() * h.element_size() for h in host)
+    if cfg4:
+        n1_total = args.n1 if args.n1 != 100_000_000 else 1_000_000_000
+        n2 = args.n2 if args.n2 != 10_000_000 else 100_000_000
+        n1 = n1_total // world
+        q = synth.make_intervals_in_range(n1, 1 + 1000 * rank, "geom1k", rank, world, sort=True)
+        t = synth.make_intervals(n2, 2, "geom1k") if rank == 0 else None
+        desc = (f"_overlap_intidxs(how={args.how!r}) cfg4: {n1_total} hg38 queries (geom 1kb) pre-sorted by (chrom, start), "
+                f"{n1} per GPU in {chunks} chunks, x {n2} targets (geom 1kb), sorted once on rank 0 and broadcast")
+    elif ranged:
+        n1 = args.n1 if args.scaling == "weak" else args.n1 // world
+        n2 = args.n2
+        q = synth.make_intervals_in_range(n1, 1 + 1000 * rank, "geom2k", rank, world)
+        t = targets(n2)  # every rank draws them (the halo reach is computed from them); only rank 0's copy is used
+        desc = workload_desc(args.how, n1, n2) + f"; queries of rank r inside the r-th of {world} (chrom, start) ranges"
+    else:
+        n1, n2 = args.n1, args.n2
+        q, t = workload(n1, n2, rank)
+        desc = workload_desc(args.how, n1, n2)
+    row_offset = rank * n1
+    own_range = synth.range_bounds(rank, world) if ranged else None
 
-    row_offset = rank * n1  # weak scaling: rank r owns query rows [r*n1, (r+1)*n1) of the whole job
+    halo = (np.empty(0, np.int32), np.empty(0, np.int64), np.empty(0, np.int64), np.empty(0, np.int64))
+    lmax = 0
+    if cfg4:  # the longest interval of either set bounds how far a target reaches beyond a range bound
+        w, _ = engine.measure_extent(*[torch.from_numpy(a).to(dev) for a in (t if rank == 0 else q)], N_GROUPS)
+        lmax = int(sharded.merge_extent_words(w, device=dev)[3])
+        torch.cuda.empty_cache()
+    if world > 1:
+        if cfg4:  # the other ranks never hold the targets: reach = bound + longest interval (a superset)
+            reach_of = [synth.range_bounds(r, world)[3] + lmax for r in range(world)]
+        else:
+            reach_of = [sharded.halo_reach(*t, synth.range_bounds(r, world)[2:], N_GROUPS) for r in range(world)]
+        halo = exchange_halo(q, rank, world, reach_of, dev)
+    n_halo = len(halo[1])
+    q_all = tuple(np.concatenate([a, h]) for a, h in zip(q, halo[:3]))
+    host_q = [torch.from_numpy(a).pin_memory() for a in q_all]
+    have_targets = t is not None and (rank == 0 or not ranged)
+    host_t = [torch.from_numpy(a).pin_memory() for a in t] if have_targets else None
+    del q, q_all
+    dq = [h.to(dev) for h in host_q]
+    dt = [h.to(dev) for h in host_t] if have_targets else [None, None, None]
+    halo_ids = torch.from_numpy(halo[3]).to(dev)
+    h2d_bytes = sum(h.numel() * h.element_size() for h in host_q) + (sum(h.numel() * h.element_size() for h in host_t) if have_targets else 0)
 
-    def step():
-        if world > 1:
-            # targets broadcast from rank 0 over NCCL/NVLink inside the step, queries stay local,
-            # one all-gather of the per-rank row counts (bioframe_b200/sharded.py)
-            ev1, ev2, _off, _tot = sharded.overlap_sharded(d[0], d[1], d[2], row_offset, d[3], d[4], d[5], N_GROUPS,
-                                                           how=args.how)
-            return ev1, ev2, last_pairs[0]
-        a, b, npairs = engine.overlap_intidxs(d[0], d[1], d[2], d[3], d[4], d[5], N_GROUPS, how=args.how)
-        last_pairs[0] = npairs
-        return a, b, npairs
+    # cfg4: the rank's sorted queries in `chunks` contiguous sub-ranges (virtual shards); the halo of a chunk is
+    # the head of the next one (local rows), the halo of the last chunk the rank's halo rows
+    chunk_plan = None
+    if cfg4 and chunks > 1:
+        gq, sq = dq[0][:n1].cpu().numpy(), dq[1][:n1].cpu().numpy()
+        chunk_plan = []
+        cuts = [0] + [sharded._first_row_at_or_after(gq, sq, int(gq[n1 * c // chunks]), int(sq[n1 * c // chunks])) for c in range(1, chunks)] + [n1]
+        for c in range(chunks):
+            lo, hi = cuts[c], cuts[c + 1]
+            g_lo, s_lo = (own_range[0], own_range[1]) if c == 0 else (int(gq[lo]), int(sq[lo]))
+            g_hi, s_hi = (own_range[2], own_range[3]) if c == chunks - 1 else (int(gq[hi]), int(sq[hi]))
+            if c == chunks - 1:
+                h_hi = n1 + n_halo
+            else:
+                h_hi = sharded._first_row_at_or_after(gq, sq, g_hi, s_hi + lmax)
+                h_hi = min(max(h_hi, hi), n1)
+            chunk_plan.append(dict(lo=lo, hi=hi, h_hi=h_hi, own=(g_lo, s_lo, g_hi, s_hi)))
+        del gq, sq
 
-    last_pairs = [0]
-    if world > 1:  # pair count of this rank's shard (for pairs/s), measured once outside the timed region
-        _a, _b, last_pairs[0] = engine.overlap_intidxs(d[0], d[1], d[2], d[3], d[4], d[5], N_GROUPS, how=args.how)
-        del _a, _b
+    last = {"pairs": 0, "rows": 0, "counts": None}
+
+    def step(keep=False):
+        if not ranged:
+            a, b, npairs = engine.overlap_intidxs(dq[0], dq[1], dq[2], dt[0], dt[1], dt[2], N_GROUPS, how=args.how)
+            last["pairs"], last["rows"] = npairs, int(a.numel())
+            return a, b
+        if chunk_plan is None:
+            a, b, npairs, counts = sharded.overlap_range_sharded(
+                dq[0], dq[1], dq[2], n1, own_range, dt[0], dt[1], dt[2], N_GROUPS, how=args.how, row_offset=row_offset,
+                halo_ids=halo_ids, n2=n2, device=dev)
+            last["pairs"], last["rows"], last["counts"] = npairs, int(a.numel()), counts
+            return a, b
+        # cfg4: targets prepared once per step, then one count/emit per chunk; the chunk results are released as
+        # they are produced (130 GB of pairs per rank would not fit next to each other)
+        words, pres = engine.measure_extent(dq[0], dq[1], dq[2], N_GROUPS)
+        if rank == 0:
+            w2, pres2 = engine.measure_extent(dt[0], dt[1], dt[2], N_GROUPS)
+            words = np.maximum(words, w2)
+        words = sharded.merge_extent_words(words, device=dev)
+        side, main_s = torch.cuda.Stream(device=dev), torch.cuda.current_stream(dev)
+        side.wait_stream(main_s)
+        handles = []
+        with torch.cuda.stream(side):
+            set2 = engine.prepare_set(words, dt[0], dt[1], dt[2], N_GROUPS, presorted=pres2) if rank == 0 else engine.adopt_set(words, n2, N_GROUPS)
+            if world > 1:
+                handles = [dist.broadcast(set2.keys, src=0, async_op=True), dist.broadcast(set2.ids, src=0, async_op=True)]
+        pairs = rows = 0
+        for c, ch in enumerate(chunk_plan):
+            sl = slice(ch["lo"], ch["h_hi"])
+            set1 = engine.prepare_set(words, dq[0][sl], dq[1][sl], dq[2][sl], N_GROUPS, presorted=pres)
+            if c == 0:
+                for h in handles:
+                    h.wait()
+                main_s.wait_stream(side)
+                set2.store.record_stream(main_s)
+            n_own = ch["hi"] - ch["lo"]
+            local_halo = ch["h_hi"] - ch["hi"]
+            hid = None
+            if local_halo:
+                hid = halo_ids if c == len(chunk_plan) - 1 else torch.arange(row_offset + ch["hi"], row_offset + ch["h_hi"], device=dev)
+            a, b, npairs = engine.overlap_prepared(set1, set2, how=args.how, own_range=ch["own"], row_offset1=row_offset + ch["lo"],
+                                                   n_own1=n_own, halo_ids=hid)
+            pairs += npairs
+            rows += int(a.numel())
+            if not (keep and c == len(chunk_plan) - 1):
+                del a, b
+            del set1
+        last["pairs"], last["rows"] = pairs, rows
+        return (a, b) if keep else (None, None)
 
     def fence():
         if world > 1:
@@ -502,9 +886,8 @@ def main():
         torch.cuda.synchronize(dev)
 
     for _ in range(max(args.warmup, 3)):
-        ev1, ev2, n_pairs = step()
-    n_rows = int(ev1.numel())
-    del ev1, ev2
+        ev1, ev2 = step()
+        del ev1, ev2
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -514,7 +897,7 @@ def main():
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
-        ev1, ev2, n_pairs = step()
+        ev1, ev2 = step()
         del ev1, ev2
     t1.record()
     fence()
@@ -527,66 +910,72 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total = float(tt.item())
     ms_step = ms_total / args.steps
-    total_pairs, total_rows = int(n_pairs), n_rows
+    n_pairs, n_rows = int(last["pairs"]), int(last["rows"])
+    total_pairs, total_rows = n_pairs, n_rows
     if world > 1:
-        tt = torch.tensor([int(n_pairs), n_rows], device=dev, dtype=torch.int64)
+        tt = torch.tensor([n_pairs, n_rows], device=dev, dtype=torch.int64)
         dist.all_reduce(tt, op=dist.ReduceOp.SUM)
         total_pairs, total_rows = int(tt[0].item()), int(tt[1].item())
     units = n1 * world + n2
     value = units / (ms_step * 1e-3)
 
-    # ---- end to end: pinned host buffers in, pinned host buffers out ----
+    # ---- N > 1: every rank checks its rows against the single-GPU engine; the segment sizes of all ranks are
+    #      exchanged once, after the last step (they place the segments in the whole result) ----
+    sharded_verified = None
+    if ranged and world > 1 and not args.no_verify and chunk_plan is None:
+        got = step()
+        counts_all = sharded.gather_group_counts(last["counts"], device=dev)
+        _dst, _src, total = sharded.assemble_offsets(counts_all)
+        full_t = [torch.from_numpy(a).to(dev) for a in t]  # regenerated from the seed on this rank, not the broadcast copy
+        ok = verify_shard(engine, dq, n1, own_range, halo_ids, row_offset, full_t, args.how, got) and total == total_rows
+        del got, full_t
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        sharded_verified = bool(flag.item())
+
+    # ---- end to end: pinned host buffers in, host arrays out ----
     e2e = None
-    if not args.no_e2e:
-        # Host memory: two pinned int64 result columns are 2 x 7 GB per rank (the pinned allocator rounds up to
-        # 8 GB each).  Up to 4 ranks they are kept whole; with more ranks on one box (196 GB of host RAM here)
-        # the result is read back through a ring of two 2-GiB pinned buffers instead -- same bytes over PCIe.
-        # With one or two ranks on the box the result crosses PCIe as 4 bytes per row number and is widened into
-        # ordinary int64 host arrays by host threads while the next chunk is in flight (bf_download_rows): half
-        # the bus traffic for the same int64 result (315 -> 198 ms at one GPU).  The widening doubles the host
-        # memory traffic, though, and with more ranks sharing one host the memory controllers, not PCIe, are
-        # the limit (440 vs 467 ms at two GPUs: already a tie): from four ranks on the int64 columns are
-        # copied as they are into pinned host arrays.
-        try:
-            cores = len(os.sched_getaffinity(0))
-        except AttributeError:
-            cores = os.cpu_count() or 1
-        threads = max(1, min(8, cores // world - 1))
-        narrow = threads >= 4 and world <= 2
-        ring = (not narrow) and world > 4
+    if not args.no_e2e and not cfg4:
+        # The result crosses PCIe as 4 bytes per row number and is widened into ordinary int64 host arrays by host
+        # threads while the next chunk is in flight (bf_download_rows): half the bus traffic for the same int64
+        # result.  With many ranks on one host the widening threads are scaled down to the cores each rank has;
+        # below two threads the int64 columns are copied as they are (ring of two pinned 2-GiB buffers).
+        threads = max(1, min(8, cores_available() // world - 1))
+        narrow = threads >= 2
         if narrow:
             res1 = np.zeros(n_rows, dtype=np.int64)  # pageable, touched once here
             res2 = np.zeros(n_rows, dtype=np.int64)
-        elif ring:
+        else:
             chunk = 1 << 28
             bufs = [torch.empty(chunk, dtype=torch.int64).pin_memory() for _ in range(2)]
-        else:
-            out1 = torch.empty(n_rows, dtype=torch.int64).pin_memory()
-            out2 = torch.empty(n_rows, dtype=torch.int64).pin_memory()
 
         def e2e_step():
-            dd = [h.to(dev, non_blocking=True) for h in host]
-            a, b, _ = engine.overlap_intidxs(dd[0], dd[1], dd[2], dd[3], dd[4], dd[5], N_GROUPS, how=args.how)
+            for i, h in enumerate(host_q):
+                dq[i].copy_(h, non_blocking=True)
+            if have_targets:
+                for i, h in enumerate(host_t):
+                    dt[i].copy_(h, non_blocking=True)
+            a, b = step()
             if narrow:
                 engine.download_rows(a, out=res1, n_threads=threads)
                 engine.download_rows(b, out=res2, n_threads=threads)
-            elif ring:
+            else:
                 k = 0
                 for col in (a, b):
                     for lo in range(0, col.numel(), chunk):
                         part = col[lo:lo + chunk]
                         bufs[k & 1][: part.numel()].copy_(part, non_blocking=True)
                         k += 1
-            else:
-                out1[: a.numel()].copy_(a, non_blocking=True)
-                out2[: b.numel()].copy_(b, non_blocking=True)
             torch.cuda.synchronize(dev)
+            return a, b
 
-        e2e_step()
+        a, b = e2e_step()
+        del a, b
         fence()
         w0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            e2e_step()
+            a, b = e2e_step()
+            del a, b
         fence()
         e2e_s = (time.perf_counter() - w0) / args.e2e_steps
         if world > 1:
@@ -600,29 +989,20 @@ def main():
             "h2d_bytes_per_step": h2d_bytes,
             "d2h_bytes_per_step": (8 if narrow else 16) * n_rows,
             "result_bytes_per_step": 16 * n_rows,
+            "api": "engine.overlap_intidxs / sharded.overlap_range_sharded on host columns (pre-encoded group codes); the "
+                   "DataFrame-level call is timed in frame_e2e",
             "d2h_mode": (f"row numbers cross PCIe as int32 and are widened into int64 host arrays by {threads} host threads "
-                         "(bf_download_rows)") if narrow
-            else ("ring of two 2-GiB pinned buffers" if ring else "whole result into pinned host arrays"),
+                         "(bf_download_rows)") if narrow else "int64 columns through a ring of two 2-GiB pinned buffers",
         }
         if narrow:
-            # the widened host arrays hold exactly what the device produced
-            a, b, _ = engine.overlap_intidxs(*[h.to(dev) for h in host], N_GROUPS, how=args.how)
+            a, b = step()  # the widened host arrays hold exactly what the device produced
             e2e["verified"] = bool(torch.equal(torch.from_numpy(res1), a.cpu()) and torch.equal(torch.from_numpy(res2), b.cpu()))
             del res1, res2, a, b
-        elif ring:
-            del bufs
         else:
-            del out1, out2
+            del bufs
 
     if rank == 0:
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        peak, peak_src = hbm_peak()
         sp = prof.get("sort_pass", {"ms": 0.0, "timed": 0, "bytes": 0})
         per_launch_ms = sp["ms"] / max(sp["timed"], 1)
         per_launch_bytes = sp["bytes"] / max(sp["timed"], 1)
@@ -630,18 +1010,24 @@ def main():
         launches = sum(v["launches"] for v in prof.values())
         # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of a 1e8-row launch,
         # scaled to this run's mix of launches (passes over n1 and over n2 rows, first pass reads no row id)
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-                tj = json.load(f)
-            npass = max(sp["timed"] // (2 * args.steps), 1)  # passes per set
-            per_row_first, per_row_other = tj["first_pass_bytes"] / tj["rows"], tj["other_pass_bytes"] / tj["rows"]
-            total_bytes = (n1 + n2) * (per_row_first + (npass - 1) * per_row_other)
-            traffic = total_bytes / (2 * npass)
-        except Exception:
-            pass
-        a_alg = 256 * (n1 + n2) + 20 * n_rows
-        a_io = 20 * (n1 + n2) + 16 * n_rows
+        traffic, traffic_src = None, None
+        for name in ("r2_traffic.json", "r1_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", name)) as f:
+                    tj = json.load(f)
+                npass = max(sp["timed"] // (2 * args.steps), 1)  # passes per set
+                per_row_first, per_row_other = tj["first_pass_bytes"] / tj["rows"], tj["other_pass_bytes"] / tj["rows"]
+                total_bytes = (n1 + n2) * (per_row_first + (npass - 1) * per_row_other)
+                traffic = total_bytes / (2 * npass)
+                traffic_src = f"profiles/{name} (ncu dram bytes of a 1e8-row launch, scaled per row)"
+                break
+            except Exception:
+                continue
+        n_sorted = n1 + n_halo + (n2 if (rank == 0 or not ranged) else 0)
+        a_alg = 256 * n_sorted + 20 * n_rows
+        a_alg_p4 = 160 * n_sorted + 20 * n_rows
+        a_io = 20 * n_sorted + 16 * n_rows
+        sec = ms_step * 1e-3
         line = {
             "metric": "bf.overlap input intervals/s",
             "value": value,
@@ -651,20 +1037,22 @@ def main():
             "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step,
             "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": args.scaling,
             "vs_baseline": None,
             "dtype": "int64",
             "data": "synthetic",
             "config": {
-                "workload": workload_desc(args.how, n1, n2),
+                "workload": desc,
                 "n1_per_gpu": n1,
                 "n2": n2,
+                "halo_rows_rank0": n_halo,
                 "rows_out_per_gpu": n_rows,
-                "pairs_out_per_gpu": int(n_pairs),
-                "pairs_per_s": total_pairs / (ms_step * 1e-3),
+                "pairs_out_per_gpu": n_pairs,
+                "pairs_per_s": total_pairs / sec,
                 "rows_out_total": total_rows,
                 "l2": "inputs (2.2 GB) and every intermediate exceed the 126 MB L2; no flush needed",
-                "parallelism": f"query-sharded x{world}, targets NCCL-broadcast" if world > 1 else "single GPU",
+                "parallelism": (f"queries sharded by (chrom, start) range x{world}, targets sorted on rank 0, sorted keys + ids "
+                                "NCCL-broadcast on a side stream; row order = the reference's") if ranged else "single GPU",
             },
             "gpu_launches": launches // max(args.steps, 1) * args.steps,
             "clocks": sampler.summary(),
@@ -677,30 +1065,71 @@ def main():
                 "unit": "GB/s",
                 "frac": achieved / peak if peak else None,
                 "traffic": traffic,
-                "traffic_source": "profiles/r1_traffic.json (ncu dram bytes of a 1e8-row launch, scaled per row)",
+                "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": per_launch_bytes,
                 "launches_timed": sp["timed"],
                 "avg_launch_ms": per_launch_ms,
                 "whole_step": {
+                    "note": "A_alg is SURVEY.md 8d's stage model with p=8 radix passes; the code runs 4 (32-bit linear genome "
+                            "axis), so A_alg_p4 = 160 N + 20 R is the model of what actually runs; A_io is the I/O floor",
                     "A_alg_GB": a_alg / 1e9,
+                    "A_alg_p4_GB": a_alg_p4 / 1e9,
                     "A_io_GB": a_io / 1e9,
-                    "achieved_alg_GBps": a_alg / (ms_step * 1e-3) / 1e9,
-                    "achieved_io_GBps": a_io / (ms_step * 1e-3) / 1e9,
-                    "frac_alg": a_alg / (ms_step * 1e-3) / 1e9 / peak,
-                    "frac_io": a_io / (ms_step * 1e-3) / 1e9 / peak,
+                    "achieved_alg_GBps": a_alg / sec / 1e9,
+                    "frac_alg": a_alg / sec / 1e9 / peak,
+                    "frac_alg_p4": a_alg_p4 / sec / 1e9 / peak,
+                    "frac_io": a_io / sec / 1e9 / peak,
                 },
                 "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
             },
             "e2e": e2e,
         }
-        if world == 1 and not args.no_cpu:
-            val, desc, ms, _ = cpu_leg(args, 2, 1)
-            line["cpu_baseline"] = {"value": val, "unit": "intervals/s", "cores": 1, "kind": "port", "sample": desc, "ms_per_step": ms}
-            # the same port spread over every host core, one chromosome per process (what `--impl reference` times)
-            val_all, desc_all, ms_all, _, cores_all = reference_leg_all_cores(args, 2, 1)
-            line["cpu_baseline"]["all_cores"] = {"value": val_all, "cores": cores_all, "sample": desc_all, "ms_per_step": ms_all}
-        print(json.dumps(line), flush=True)
+        if sharded_verified is not None:
+            line["sharded_verified"] = sharded_verified
+        print_line = True
+        if world == 1 and not cfg4 and not args.no_cpu:
+            leg = cpu_leg(args, 2, 1)
+            line["cpu_baseline"] = {"value": leg["value"], "unit": "intervals/s", "cores": 1, "kind": leg["kind"],
+                                    "sample": leg["desc"], "ms_per_step": leg["ms"]}
+            # the GPU on the very same sample, row for row against the reference's result
+            ds = [torch.from_numpy(a).to(dev) for a in (*leg["q"], *leg["t"])]
+            g1_, g2_, _ = engine.overlap_intidxs(*ds, N_GROUPS, how=args.how)
+            line["parity_checked"] = bool(np.array_equal(g1_.cpu().numpy(), leg["ev1"]) and np.array_equal(g2_.cpu().numpy(), leg["ev2"]))
+            line["parity_sample"] = f"{leg['rows']} rows of the chr21+chr22 sample, array-equal with the {leg['kind']}, in its row order"
+            del ds, g1_, g2_, leg
+            # the same reference spread over every host core (what `--impl reference` times)
+            val_all, desc_all, ms_all, _, cores_all, kind_all = reference_leg_all_cores(args, 1, 1)
+            line["cpu_baseline"]["all_cores"] = {"value": val_all, "cores": cores_all, "kind": kind_all, "sample": desc_all,
+                                                 "ms_per_step": ms_all}
+        # release the benchmark's tensors before the other legs
+        del dq, dt, host_q, host_t
+        engine.Workspace.release()
+        torch.cuda.empty_cache()
+        if world == 1 and not cfg4 and not args.no_frame:
+            try:
+                line["frame_e2e"] = frame_leg(args)
+            except Exception as exc:  # a reported leg, never the reason the headline is lost
+                line["frame_e2e"] = {"error": f"{type(exc).__name__}: {exc}"}
+            engine.Workspace.release()
+            torch.cuda.empty_cache()
+        if world == 1 and not cfg4 and not args.no_secondary:
+            sec_out = {}
+            for wl in ("cfg0", "closest", "cluster", "coverage", "ordered"):
+                try:
+                    s_line = secondary_line(args, wl, 3, 3, with_cpu=not args.no_cpu)
+                    sec_out[wl] = {"metric": s_line["metric"], "workload": s_line["config"]["workload"], "ms_per_step": s_line["ms_per_step"],
+                                   "value": s_line["value"], "rows_out": s_line["config"]["rows_out"],
+                                   "roofline_frac": s_line["roofline"]["frac"], "gpu_launches": s_line["gpu_launches"],
+                                   "cpu_baseline": s_line.get("cpu_baseline")}
+                except Exception as exc:
+                    sec_out[wl] = {"error": f"{type(exc).__name__}: {exc}"}
+                engine.Workspace.release()
+                torch.cuda.empty_cache()
+            line["secondary"] = sec_out
+        if print_line:
+            print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -28,6 +28,48 @@ from .core.specs import _get_default_colnames, _verify_columns
 __all__ = ["overlap", "closest", "cluster", "merge", "complement", "coverage", "count_overlaps", "setdiff", "subtract", "assign_view", "trim"]
 
 _INT64_MAX = np.iinfo(np.int64).max
+
+# ---- where a frame-level call spends its time (bench.py's frame_e2e leg): stage -> seconds while a
+# `profile()` context is open.  Stage boundaries synchronise the device, so the context is for measuring only.
+_PROFILE = None
+
+
+class profile:
+    def __enter__(self):
+        global _PROFILE
+        _PROFILE = {}
+        return _PROFILE
+
+    def __exit__(self, *exc):
+        global _PROFILE
+        _PROFILE = None
+        return False
+
+
+def _tick(stage, t0):
+    """Charge the time since t0 to `stage`; -> now.  A no-op (returns t0) outside a profile() context."""
+    if _PROFILE is None:
+        return t0
+    import time
+
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+    except ImportError:
+        pass
+    now = time.perf_counter()
+    _PROFILE[stage] = _PROFILE.get(stage, 0.0) + (now - t0)
+    return now
+
+
+def _now():
+    if _PROFILE is None:
+        return 0.0
+    import time
+
+    return time.perf_counter()
 _ORDERED_MAX_PARTNERS = 1 << 14  # longest partner list of one row the row-order overlap kernel is used for
 
 
@@ -99,6 +141,7 @@ def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _gro
     ck2, sk2, ek2 = _get_default_colnames() if cols2 is None else cols2
     _verify_columns(df1, [ck1, sk1, ek1])
     _verify_columns(df2, [ck2, sk2, ek2])
+    t0 = _now()
     by1, by2 = [ck1], [ck2]
     if on is not None:
         by1 = by1 + list(on)
@@ -136,8 +179,12 @@ def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _gro
     g1 = ranks_of(codes1, keys1, rank_na1) if len(df1) else np.empty(0, np.int32)
     g2 = ranks_of(codes2, keys2, rank_na2) if len(df2) else np.empty(0, np.int32)
     s1, e1, s2, e2 = _int64_coords(df1, sk1), _int64_coords(df1, ek1), _int64_coords(df2, sk2), _int64_coords(df2, ek2)
-    if _coords:  # the coordinates go to the device once: the overlap call and the coordinate gather share them
+    t0 = _tick("encode_groups", t0)
+    if _coords or _PROFILE is not None:
+        # the coordinates go to the device once: the overlap call and the coordinate gather share them
         s1, e1, s2, e2 = (_engine.to_device(x) for x in (s1, e1, s2, e2))
+        g1, g2 = _engine.to_device(g1, "int32"), _engine.to_device(g2, "int32")
+    t0 = _tick("h2d", t0)
     ev1 = None
     if _sort_pairs and how == "left":
         # keep_order: the pairs are produced in (row of df1, row of df2) order directly, queries visited in row
@@ -157,8 +204,14 @@ def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _gro
         _device_rows.extend([ev1, ev2])
     if _coords:  # clipped coordinates of every pair (return_overlap, ops.py:480-497) while the list is on the device
         lo, hi, _ = _engine.pair_coords(ev1, ev2, s1, e1, s2, e2)
-        return _rows_to_host(ev1), _rows_to_host(ev2), (_to_host(lo), _to_host(hi))
-    return _rows_to_host(ev1), _rows_to_host(ev2)
+        t0 = _tick("kernels", t0)
+        out = _rows_to_host(ev1), _rows_to_host(ev2), (_to_host(lo), _to_host(hi))
+        _tick("d2h", t0)
+        return out
+    t0 = _tick("kernels", t0)
+    out = _rows_to_host(ev1), _rows_to_host(ev2)
+    _tick("d2h", t0)
+    return out
 
 
 _NULLABLE_INT = {
@@ -244,8 +297,10 @@ def overlap(
     rows go missing."""
     ck1, sk1, ek1 = _get_default_colnames() if cols1 is None else cols1
     ck2, sk2, ek2 = _get_default_colnames() if cols2 is None else cols2
+    t0 = _now()
     checks.is_bedframe(df1, raise_errors=True, cols=[ck1, sk1, ek1])
     checks.is_bedframe(df2, raise_errors=True, cols=[ck2, sk2, ek2])
+    _tick("validate", t0)
 
     if how == "left" and keep_order is None:
         keep_order = True
@@ -277,6 +332,7 @@ def overlap(
                            _coords=device_coords, _device_rows=dev_rows)
     ev1, ev2 = res[0], res[1]
     dev1, dev2 = dev_rows if dev_rows else (None, None)
+    t0 = _now()
 
     stem = return_index if isinstance(return_index, str) else "index"
     icol1, icol2 = stem + suffixes[0], stem + suffixes[1]
@@ -325,6 +381,7 @@ def overlap(
     if not return_index:
         out.drop([icol1, icol2], axis=1, inplace=True)
     out.reset_index(drop=True, inplace=True)
+    _tick("assemble_frame", t0)
     return out
 
 

@@ -128,3 +128,41 @@ def make_tie_free(n, seed, kind="geom1k", chrom_ids=None):
         s, e = _place(rng, codes[bad], lens)
         starts[bad], ends[bad] = s, e
     raise RuntimeError("could not draw a tie-free set")
+
+
+HG38_OFFSETS = np.concatenate([[0], np.cumsum(HG38_SIZES)]).astype(np.int64)  # chromosomes laid end to end
+HG38_TOTAL = int(HG38_OFFSETS[-1])
+
+
+def linear_to_chrom(pos):
+    """position on the end-to-end axis -> (chromosome code, coordinate on it); HG38_TOTAL -> (24, 0)."""
+    pos = np.asarray(pos, dtype=np.int64)
+    code = np.searchsorted(HG38_OFFSETS, pos, side="right") - 1
+    code = np.minimum(code, len(HG38_SIZES))
+    return code.astype(np.int32), pos - HG38_OFFSETS[np.minimum(code, len(HG38_SIZES) - 1)] * (code < len(HG38_SIZES))
+
+
+def range_bounds(rank, world):
+    """(g_lo, start_lo, g_hi, start_hi) of shard `rank` when the end-to-end genome axis is cut into `world`
+    equal (chrom, start) ranges (the query sharding of SURVEY.md 8e)."""
+    lo, hi = HG38_TOTAL * rank // world, HG38_TOTAL * (rank + 1) // world
+    (g_lo,), (s_lo,) = (x.reshape(1) for x in linear_to_chrom(lo))
+    if rank + 1 >= world:
+        return int(g_lo), int(s_lo), len(HG38_SIZES), 0
+    (g_hi,), (s_hi,) = (x.reshape(1) for x in linear_to_chrom(hi))
+    return int(g_lo), int(s_lo), int(g_hi), int(s_hi)
+
+
+def make_intervals_in_range(n, seed, kind, rank, world, sort=False):
+    """n intervals whose (chrom, start) lies in shard `rank`'s range of `range_bounds`: starts uniform on that
+    stretch of the end-to-end axis, lengths of `kind`, ends clipped to the chromosome.  sort=True orders the rows
+    by (chrom, start) (cfg4: "queries pre-sorted by (chrom, start) on the host")."""
+    rng = np.random.default_rng(seed)
+    lo, hi = HG38_TOTAL * rank // world, HG38_TOTAL * (rank + 1) // world
+    pos = lo + np.floor(rng.random(n) * (hi - lo)).astype(np.int64)
+    if sort:
+        pos.sort()
+    lens = lengths(rng, n, kind)
+    codes, starts = linear_to_chrom(pos)
+    ends = np.minimum(starts + lens, HG38_SIZES[codes])
+    return codes, starts, ends
