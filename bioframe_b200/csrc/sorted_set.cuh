@@ -35,127 +35,108 @@ static inline void take_sort_bufs(Arena& a, i64 n, SortBufs* b) {
   b->nT = a.take<u64>(1);
 }
 
-// ---- tie fix-up: rows sharing (group, start) into (end', row) order ----
-// After the stable sort on cs the rows of a tie run are in row order; the
-// reference wants them by (end', row).  One pass over the sorted keys: a tile's
-// keys (+ TIE_HALO keys each side) are staged in shared memory and every tied
-// row measures its run.  Runs of up to TIE_SMALL rows (nearly all of them: two
-// or three intervals that happen to start at the same base) are insertion-
-// sorted in place by the thread that owns the run's first row -- stable, so
-// equal keys keep row order.  Rows of longer runs (heavily duplicated input)
-// are compacted as (key, id, slot), sorted by the FULL key with the stable
-// radix sort and written back into the same slots in order.
-constexpr int TIE_SMALL = 32;
-constexpr int TIE_HALO = TIE_SMALL + 1;
+// ---- finishing pass: local order inside runs of rows that share their high key bits ----
+// The radix passes only sort the key bits from `run_shift` up (a stable LSD sort): all of the (group, start)
+// field when rows are sparse, but for dense sets -- 1e8 rows on a 2^32 axis are 30 positions apart -- its
+// lowest bits are left out, which saves a whole pass over the data (24 B/row).  Afterwards the rows of a
+// "run" (equal key >> run_shift) sit next to each other in input order, a handful at a time, and this one pass
+// finishes the job: every row counts the rows of its run that must precede it -- smaller (key >> cmp_shift),
+// or equal and earlier -- and is written to that place in the other buffer.  cmp_shift = 0 orders by the full
+// key, i.e. (group, start, end', row) = np.lexsort([ends, starts]) of the reference (arrops.py:332-335,
+// 459-460); cmp_shift = LB orders by (group, start) and keeps equal starts in row order (KEY_NO_TIE_FIX).
+// With run_shift = LB it is the former tie fix-up (rows sharing (group, start) into (end', row) order).
+// A tile's keys (+ RUN_MAX keys each side) are staged in shared memory; one thread per row, no owner thread,
+// no atomics, no dependence between blocks.  Rows of runs longer than RUN_MAX (heavily duplicated or
+// clustered input) are copied through unchanged, compacted as (key, id, slot), sorted by the remaining
+// key bits with the stable radix sort and written back into the same slots.
+constexpr int RUN_MAX = 64;
+constexpr int RUN_HALO = RUN_MAX;
 
-// Stage a tile's keys (+ halo), measure the run of every tied row; with FIX,
-// sort short runs in place.  Returns the mask of this thread's rows that belong
-// to long runs.
-// `e_raw` is null unless the layout clamps ends (keys.cuh measure_layout): then rows whose keys are
-// equal may still differ in their original ends, which decide their order.
-template <bool FIX>
-__device__ __forceinline__ u32 tie_scan_tile(u64* __restrict__ keys, u32* __restrict__ ids, u64 n, const KeyLayout& L,
-                                             u64 base, u64 rows, u64* s_k, const i64* __restrict__ e_raw) {
-  auto after = [&](u64 k1, u32 v1, u64 k2, u32 v2) {  // (k1, row v1) sorts strictly after (k2, row v2)
-    if (k1 != k2) return k1 > k2;
-    return e_raw ? e_raw[v1] > e_raw[v2] : false;
-  };
+// Stage a tile and classify / place its rows.  PLACE: write every row of a short run to its final position in
+// (kout, vout), copy rows of long runs through.  Returns the mask of this thread's rows that belong to long
+// runs; row j of the mask is tile row  j * SC_THREADS + tid  (PLACE)  or  tid * SC_IPT + j  (!PLACE: the
+// compaction needs consecutive rows per thread).
+template <bool PLACE>
+__device__ __forceinline__ u32 run_scan_tile(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n,
+                                             int run_shift, int cmp_shift, u64 base, u64 rows, u64* s_k,
+                                             u64* __restrict__ kout, u32* __restrict__ vout) {
   const u32 tid = threadIdx.x;
-  // s_k[i] = keys[base - TIE_HALO + i]; all loads of a thread in flight before its first store
-  {
+  u32 idv[SC_IPT];
+  {  // s_k[i] = keys[base - RUN_HALO + i]; all loads of a thread in flight before its first store
     u64 v[SC_IPT], hv = ~0ull;
 #pragma unroll
     for (int j = 0; j < SC_IPT; ++j) {
       const u64 p = base + (u64)j * SC_THREADS + tid;
       v[j] = p < n ? keys[p] : ~0ull;
+      if (PLACE) idv[j] = p < n ? ids[p] : 0u;
     }
-    if (tid < 2 * TIE_HALO) {  // halo: TIE_HALO keys before the tile, TIE_HALO after
-      const i64 p = tid < TIE_HALO ? (i64)base - TIE_HALO + tid : (i64)base + SC_TILE + (tid - TIE_HALO);
+    if (tid < 2 * RUN_HALO) {
+      const i64 p = tid < RUN_HALO ? (i64)base - RUN_HALO + tid : (i64)base + SC_TILE + (tid - RUN_HALO);
       if (p >= 0 && (u64)p < n) hv = keys[p];
-      s_k[tid < TIE_HALO ? tid : SC_TILE + tid] = hv;
+      s_k[tid < RUN_HALO ? tid : SC_TILE + tid] = hv;
     }
 #pragma unroll
-    for (int j = 0; j < SC_IPT; ++j) s_k[TIE_HALO + j * SC_THREADS + tid] = v[j];
+    for (int j = 0; j < SC_IPT; ++j) s_k[RUN_HALO + j * SC_THREADS + tid] = v[j];
   }
   __syncthreads();
   u32 mask = 0;
-#pragma unroll 1
+#pragma unroll
   for (int j = 0; j < SC_IPT; ++j) {
-    // row inside the tile (s_k index r + TIE_HALO).  The fix pass only counts, so its threads take
-    // strided rows (conflict-free shared-memory reads); the gather pass needs consecutive rows per
-    // thread for the ordered compaction.
-    const u32 r = FIX ? (u32)j * SC_THREADS + tid : tid * SC_IPT + j;
-    if (r >= rows) {
-      if (FIX) continue;
-      break;
+    const u32 r = PLACE ? (u32)j * SC_THREADS + tid : tid * SC_IPT + j;
+    if (r >= rows) continue;
+    const u32 at = r + RUN_HALO;
+    const u64 pos = base + r;
+    const u64 k = s_k[at];
+    // run_shift can be 64 (no bit sorted: a tiny set is one run); cmp_shift < 64 always
+    const u64 run = run_shift < 64 ? k >> run_shift : 0ull, mine = k >> cmp_shift;
+    // rows of my run before me: all of them count if they compare <= me (equal ones are earlier rows);
+    // rows after me count if they compare < me
+    u32 back = 0, fwd = 0, rank = 0;
+    while (back < RUN_MAX && pos > back) {
+      const u64 o = s_k[at - back - 1];
+      if ((run_shift < 64 ? o >> run_shift : 0ull) != run) break;
+      rank += (o >> cmp_shift) <= mine;
+      ++back;
     }
-    const u32 at = r + TIE_HALO;
-    const u64 c = key_cs(s_k[at], L);
-    const bool prev_same = (base + r > 0) && key_cs(s_k[at - 1], L) == c;
-    const bool next_same = (base + r + 1 < n) && key_cs(s_k[at + 1], L) == c;
-    if (!prev_same && !next_same) continue;
-    u32 back = 0, fwd = 0;
-    while (back < TIE_SMALL && base + r > back && key_cs(s_k[at - back - 1], L) == c) ++back;
-    while (fwd < TIE_SMALL && base + r + fwd + 1 < n && key_cs(s_k[at + fwd + 1], L) == c) ++fwd;
-    const u32 m = back + fwd + 1;
-    if (m > TIE_SMALL) {
-      mask |= 1u << j;  // long run: general path
-    } else if (FIX && back == 0) {
-      // owner of a short run: stable insertion sort of (key, id) by key, in place
-      const u64 p0 = base + r;
-      if (m == 2) {
-        bool swap = s_k[at] > s_k[at + 1];
-        if (e_raw && s_k[at] == s_k[at + 1]) swap = after(s_k[at], ids[p0], s_k[at + 1], ids[p0 + 1]);
-        if (swap) {
-          const u32 v0 = ids[p0], v1 = ids[p0 + 1];
-          keys[p0] = s_k[at + 1];
-          keys[p0 + 1] = s_k[at];
-          ids[p0] = v1;
-          ids[p0 + 1] = v0;
-        }
-      } else {
-        u64 k[TIE_SMALL];
-        u32 v[TIE_SMALL];
-        for (u32 x = 0; x < m; ++x) {
-          const u64 kx = s_k[at + x];
-          const u32 vx = ids[p0 + x];
-          u32 y = x;
-          while (y > 0 && after(k[y - 1], v[y - 1], kx, vx)) {
-            k[y] = k[y - 1];
-            v[y] = v[y - 1];
-            --y;
-          }
-          k[y] = kx;
-          v[y] = vx;
-        }
-        for (u32 x = 0; x < m; ++x) {
-          if (k[x] != s_k[at + x]) keys[p0 + x] = k[x];
-          ids[p0 + x] = v[x];  // equal keys may still have traded places with each other's neighbours
-        }
+    while (fwd < RUN_MAX && pos + fwd + 1 < n) {
+      const u64 o = s_k[at + fwd + 1];
+      if ((run_shift < 64 ? o >> run_shift : 0ull) != run) break;
+      rank += (o >> cmp_shift) < mine;
+      ++fwd;
+    }
+    if (back + fwd + 1 > RUN_MAX) {
+      mask |= 1u << j;
+      if (PLACE) {
+        kout[pos] = k;
+        vout[pos] = idv[j];
       }
+    } else if (PLACE) {
+      const u64 dst = pos - back + rank;
+      kout[dst] = k;
+      vout[dst] = idv[j];
     }
   }
   return mask;
 }
 
-// pass 1: fix short runs in place, count rows of long runs per tile
+// pass 1: place the rows of short runs, count rows of long runs per tile
 static __global__ void __launch_bounds__(SC_THREADS)
-    tie_fix_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u64 n, KeyLayout L, const i64* __restrict__ e_raw,
-                   u64* __restrict__ spine) {
-  __shared__ u64 s_k[SC_TILE + 2 * TIE_HALO];
+    local_order_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, int run_shift, int cmp_shift,
+                       u64* __restrict__ kout, u32* __restrict__ vout, u64* __restrict__ spine) {
+  __shared__ u64 s_k[SC_TILE + 2 * RUN_HALO];
   __shared__ u64 s_tmp[8];
   const u64 base = (u64)blockIdx.x * SC_TILE;
   const u64 rows = n - base < (u64)SC_TILE ? n - base : (u64)SC_TILE;
-  const u32 mask = tie_scan_tile<true>(keys, ids, n, L, base, rows, s_k, e_raw);
+  const u32 mask = run_scan_tile<true>(keys, ids, n, run_shift, cmp_shift, base, rows, s_k, kout, vout);
   const u64 c = block_sum_u64((u64)__popc(mask), s_tmp);
   if (threadIdx.x == 0) spine[blockIdx.x] = c;
 }
 // pass 2 (after the spine scan): tiles that hold rows of long runs compact them as (key, id, slot)
 static __global__ void __launch_bounds__(SC_THREADS)
-    tie_gather_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u64 n, KeyLayout L, const u64* __restrict__ spine,
-                      u64 ntiles, const u64* __restrict__ nT, u64* __restrict__ tkeys, u32* __restrict__ tids,
-                      u32* __restrict__ tpos) {
-  __shared__ u64 s_k[SC_TILE + 2 * TIE_HALO];
+    long_run_gather_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, int run_shift,
+                           const u64* __restrict__ spine, u64 ntiles, const u64* __restrict__ nT,
+                           u64* __restrict__ tkeys, u32* __restrict__ tids, u32* __restrict__ tpos) {
+  __shared__ u64 s_k[SC_TILE + 2 * RUN_HALO];
   __shared__ u64 s_tmp[8];
   const u64 tile = blockIdx.x;
   const u64 first = spine[tile];
@@ -163,14 +144,14 @@ static __global__ void __launch_bounds__(SC_THREADS)
   if (next == first) return;  // nearly every tile of real data
   const u64 base = tile * SC_TILE;
   const u64 rows = n - base < (u64)SC_TILE ? n - base : (u64)SC_TILE;
-  const u32 mask = tie_scan_tile<false>(keys, ids, n, L, base, rows, s_k, nullptr);
+  const u32 mask = run_scan_tile<false>(keys, nullptr, n, run_shift, 0, base, rows, s_k, nullptr, nullptr);
   u64 tot;
   u64 at_out = first + block_excl_sum_u64((u64)__popc(mask), s_tmp, &tot);
 #pragma unroll
   for (int j = 0; j < SC_IPT; ++j) {
     if (mask & (1u << j)) {
       const u32 r = threadIdx.x * SC_IPT + j;
-      tkeys[at_out] = s_k[r + TIE_HALO];
+      tkeys[at_out] = s_k[r + RUN_HALO];
       tids[at_out] = ids[base + r];
       tpos[at_out] = (u32)(base + r);
       ++at_out;
@@ -189,6 +170,19 @@ static __global__ void __launch_bounds__(256) tie_scatter_kernel(const u64* __re
 }
 
 // ---------------------------------------------------------------- host side
+
+// How many low bits of the B-bit (group, start) field the radix passes may leave to the finishing pass: a run
+// of 2^drop positions should hold about 8-16 rows of evenly spread input, and the sorted bits fill whole 8-bit
+// passes.  1e8 rows on the 32-bit hg38 axis: drop = 8, three passes instead of four.
+static inline int choose_drop_bits(int B, i64 n) {
+  if (n <= 0) return 0;
+  int drop = B - bit_width((u64)n) + 3;
+  if (drop <= 0) return 0;
+  if (drop > B) drop = B;
+  const int passes = (B - drop + 7) / 8;
+  const int sorted_bits = passes * 8 < B ? passes * 8 : B;
+  return B - sorted_bits;
+}
 
 // ---- clamp mode: (group, start, true end', row) by two stable sorts ----
 static __global__ void __launch_bounds__(256) true_end_keys_kernel(const i64* __restrict__ s, const i64* __restrict__ e,
@@ -260,29 +254,44 @@ static int sort_rows(const i32* grp, const i64* s, const i64* e, i64 n, const Ke
     // end', then stable sort by (group, start) -> (group, start, end', row) exactly.
     return sort_rows_two_keys(grp, s, e, n, L, point_adjust, ws, sc, st, res);
   }
-  // main sort: stable, on the (group, start) bits only -- or nothing at all when the extent pass found the
-  // rows already in that order (the tie fix-up below still puts equal starts in (end', row) order)
+  // main sort: stable LSD passes on the upper bits of the (group, start) field -- or none at all when the
+  // extent pass found the rows already in that order -- then one finishing pass that orders the rows inside
+  // every run of equal sorted bits (local_order_kernel)
   const bool presorted = (point_adjust & KEY_PRESORTED) && !(point_adjust & KEY_BY_END);
-  const RadixPlan rp = presorted ? make_radix_plan(0, 0) : make_radix_plan(L.LB, L.total_bits);
+  const bool keep_row_order = (point_adjust & KEY_NO_TIE_FIX) != 0;  // equal (group, start): rows stay in row order
+  const int drop = presorted ? 0 : choose_drop_bits(L.B, n);
+  const int run_shift = L.LB + drop;
+  const int cmp_shift = keep_row_order ? L.LB : 0;
+  const RadixPlan rp = presorted ? make_radix_plan(0, 0) : make_radix_plan(run_shift, L.total_bits);
   BF_CUDA(cudaMemsetAsync(sc.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
   BF_TRY(launch_pack_keys(grp, s, e, (u64)n, L, point_adjust, rp, ws.keyA, sc.hist, st));
   BF_TRY(radix_sort_passes<true>(ws.keyA, ws.keyB, ws.idA, ws.idB, true, (u64)n, nullptr, rp, sc, st, res));
-  if (point_adjust & KEY_NO_TIE_FIX) return BF_OK;
-  // tie fix-up on the subset of rows that share (group, start); scratch = the
-  // sort's spare buffers and the per-row temporaries
+  if (keep_row_order && drop == 0) return BF_OK;  // runs = equal (group, start), already in row order
   const unsigned tiles = (unsigned)scan_tiles((u64)n);
+  BF_LAUNCH(PC_TIEFIX, 24 * n, st,
+            local_order_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, run_shift, cmp_shift, res->keys_alt,
+                                                            res->vals_alt, ws.spine));
+  {  // the ordered rows are in the other buffer pair now
+    u64* tk = res->keys;
+    res->keys = res->keys_alt;
+    res->keys_alt = tk;
+    u32* tv = res->vals;
+    res->vals = res->vals_alt;
+    res->vals_alt = tv;
+  }
+  // rows of long runs (rare): compact, sort by the bits below the run prefix, write back into their slots
   u64* tkeyA = res->keys_alt;
   u32* tidA = res->vals_alt;
   u64* tkeyB = ws.tmp8;
   u32* tidB = ws.tmp4a;
   u32* tpos = ws.tmp4b;
-  BF_LAUNCH(PC_TIEFIX, 8 * n, st, tie_fix_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, L,
-                                                                             L.endcap != I64_MAX ? e : nullptr, ws.spine));
   BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(ws.spine, (u64)tiles, ws.nT));
   BF_LAUNCH(PC_TIEFIX, 0, st,
-            tie_gather_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, L, ws.spine, (u64)tiles, ws.nT,
-                                                            tkeyA, tidA, tpos));
-  const RadixPlan full = make_radix_plan(0, L.total_bits);
+            long_run_gather_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, run_shift, ws.spine, (u64)tiles,
+                                                                 ws.nT, tkeyA, tidA, tpos));
+  // the compacted rows are still in run order and, inside a run, in input order: a stable sort on ALL compared
+  // bits puts them into the order of the whole array restricted to those slots
+  const RadixPlan full = make_radix_plan(cmp_shift, L.total_bits);
   BF_CUDA(cudaMemsetAsync(sc.hist, 0, RS_MAX_PASSES * RS_BINS * sizeof(u64), st));
   BF_TRY(launch_radix_hist(tkeyA, (u64)n, ws.nT, full, sc.hist, st, PC_TIEFIX));
   SortResult tr;
