@@ -51,32 +51,62 @@ static inline void take_sort_bufs(Arena& a, i64 n, SortBufs* b) {
 // key bits with the stable radix sort and written back into the same slots.
 constexpr int RUN_MAX = 64;
 constexpr int RUN_HALO = RUN_MAX;
+constexpr int RUN_STAGED = SC_TILE + 2 * RUN_HALO;  // 2176 staged rows = 68 words of run-head bits
+constexpr int RUN_WORDS = RUN_STAGED / 32;
+static_assert(RUN_STAGED % 32 == 0 && RUN_HALO % 32 == 0, "head bit words must tile the staged rows");
 
 // Stage a tile and classify / place its rows.  PLACE: write every row of a short run to its final position in
 // (kout, vout), copy rows of long runs through.  Returns the mask of this thread's rows that belong to long
-// runs; row j of the mask is tile row  j * SC_THREADS + tid  (PLACE)  or  tid * SC_IPT + j  (!PLACE: the
+// runs; bit j of the mask is tile row  j * SC_THREADS + tid  (PLACE)  or  tid * SC_IPT + j  (!PLACE: the
 // compaction needs consecutive rows per thread).
-template <bool PLACE>
+//   s_c[i]   = keys[base - RUN_HALO + i] >> cmp_shift   (what rows are compared by)
+//   s_head   = one bit per staged row: the row starts a run (its key >> run_shift differs from its
+//              predecessor's).  A row finds its run as [last head at or before it, next head after it) with a
+//              few bit operations on at most three words either way -- no walk, no divergence; a run whose
+//              bounds are not inside that reach is longer than RUN_MAX.
+//   SUB32: run_shift - cmp_shift <= 32, so rows of one run differ only in the low 32 bits of s_c: the rank
+//              loop then reads 4-byte words (s_lo).
+template <bool PLACE, bool SUB32>
 __device__ __forceinline__ u32 run_scan_tile(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n,
-                                             int run_shift, int cmp_shift, u64 base, u64 rows, u64* s_k,
-                                             u64* __restrict__ kout, u32* __restrict__ vout) {
-  const u32 tid = threadIdx.x;
+                                             int run_shift, int cmp_shift, u64 base, u64 rows, u64* s_c, u32* s_lo,
+                                             u32* s_head, u64* __restrict__ kout, u32* __restrict__ vout) {
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  u64 kv[SC_IPT];
   u32 idv[SC_IPT];
-  {  // s_k[i] = keys[base - RUN_HALO + i]; all loads of a thread in flight before its first store
-    u64 v[SC_IPT], hv = ~0ull;
+  {  // all loads of a thread in flight before its first store
+    u64 hv = ~0ull;
 #pragma unroll
     for (int j = 0; j < SC_IPT; ++j) {
       const u64 p = base + (u64)j * SC_THREADS + tid;
-      v[j] = p < n ? keys[p] : ~0ull;
+      kv[j] = p < n ? keys[p] : ~0ull;
       if (PLACE) idv[j] = p < n ? ids[p] : 0u;
     }
     if (tid < 2 * RUN_HALO) {
       const i64 p = tid < RUN_HALO ? (i64)base - RUN_HALO + tid : (i64)base + SC_TILE + (tid - RUN_HALO);
       if (p >= 0 && (u64)p < n) hv = keys[p];
-      s_k[tid < RUN_HALO ? tid : SC_TILE + tid] = hv;
+      const u32 i = tid < RUN_HALO ? tid : SC_TILE + tid;
+      s_c[i] = hv >> cmp_shift;
+      if (SUB32) s_lo[i] = (u32)(hv >> cmp_shift);
     }
 #pragma unroll
-    for (int j = 0; j < SC_IPT; ++j) s_k[RUN_HALO + j * SC_THREADS + tid] = v[j];
+    for (int j = 0; j < SC_IPT; ++j) {
+      const u32 i = RUN_HALO + j * SC_THREADS + tid;
+      s_c[i] = kv[j] >> cmp_shift;
+      if (SUB32) s_lo[i] = (u32)(kv[j] >> cmp_shift);
+    }
+  }
+  __syncthreads();
+  const int pshift = run_shift - cmp_shift;  // run prefix of a staged value; 64 = every row in one run
+  for (u32 c = warp; c < RUN_WORDS; c += SC_THREADS / 32) {
+    const u32 i = c * 32 + lane;
+    const i64 p = (i64)base - RUN_HALO + (i64)i;
+    bool head = true;  // rows outside the array and the first staged row close / open a run
+    if (p > 0 && (u64)p < n && i > 0) {
+      const u64 a = s_c[i], b = s_c[i - 1];
+      head = pshift < 64 && (a >> pshift) != (b >> pshift);
+    }
+    const u32 m = __ballot_sync(0xffffffffu, head);
+    if (lane == 0) s_head[c] = m;
   }
   __syncthreads();
   u32 mask = 0;
@@ -84,35 +114,61 @@ __device__ __forceinline__ u32 run_scan_tile(const u64* __restrict__ keys, const
   for (int j = 0; j < SC_IPT; ++j) {
     const u32 r = PLACE ? (u32)j * SC_THREADS + tid : tid * SC_IPT + j;
     if (r >= rows) continue;
-    const u32 at = r + RUN_HALO;
+    const u32 i = r + RUN_HALO, c = i >> 5, l = i & 31;
+    // first row of my run: the last head at or before me
+    i32 start = -1;
+    {
+      const u32 w0 = s_head[c] & (0xffffffffu >> (31 - l));
+      if (w0) {
+        start = (i32)(c << 5) + 31 - __clz(w0);
+      } else {
+        const u32 w1 = s_head[c - 1];
+        if (w1) {
+          start = (i32)((c - 1) << 5) + 31 - __clz(w1);
+        } else {
+          const u32 w2 = s_head[c - 2];
+          if (w2) start = (i32)((c - 2) << 5) + 31 - __clz(w2);
+        }
+      }
+    }
+    // one past its last row: the next head after me
+    i32 end = -1;
+    {
+      const u32 w0 = l == 31 ? 0u : s_head[c] & (0xffffffffu << (l + 1));
+      if (w0) {
+        end = (i32)(c << 5) + __ffs(w0) - 1;
+      } else {
+        const u32 w1 = s_head[c + 1];
+        if (w1) {
+          end = (i32)((c + 1) << 5) + __ffs(w1) - 1;
+        } else {
+          const u32 w2 = c + 2 < RUN_WORDS ? s_head[c + 2] : 0u;
+          if (w2) end = (i32)((c + 2) << 5) + __ffs(w2) - 1;
+        }
+      }
+    }
     const u64 pos = base + r;
-    const u64 k = s_k[at];
-    // run_shift can be 64 (no bit sorted: a tiny set is one run); cmp_shift < 64 always
-    const u64 run = run_shift < 64 ? k >> run_shift : 0ull, mine = k >> cmp_shift;
-    // rows of my run before me: all of them count if they compare <= me (equal ones are earlier rows);
-    // rows after me count if they compare < me
-    u32 back = 0, fwd = 0, rank = 0;
-    while (back < RUN_MAX && pos > back) {
-      const u64 o = s_k[at - back - 1];
-      if ((run_shift < 64 ? o >> run_shift : 0ull) != run) break;
-      rank += (o >> cmp_shift) <= mine;
-      ++back;
-    }
-    while (fwd < RUN_MAX && pos + fwd + 1 < n) {
-      const u64 o = s_k[at + fwd + 1];
-      if ((run_shift < 64 ? o >> run_shift : 0ull) != run) break;
-      rank += (o >> cmp_shift) < mine;
-      ++fwd;
-    }
-    if (back + fwd + 1 > RUN_MAX) {
+    const bool is_long = start < 0 || end < 0 || end - start > RUN_MAX || start == 0;  // staged row 0: bound unknown
+    if (is_long) {
       mask |= 1u << j;
       if (PLACE) {
-        kout[pos] = k;
+        kout[pos] = kv[j];
         vout[pos] = idv[j];
       }
     } else if (PLACE) {
-      const u64 dst = pos - back + rank;
-      kout[dst] = k;
+      // rows of my run that precede me: earlier ones that compare <= me, later ones that compare < me
+      u32 rank = 0;
+      if (SUB32) {
+        const u32 mine = s_lo[i];
+        for (i32 x = start; x < (i32)i; ++x) rank += s_lo[x] <= mine;
+        for (i32 x = (i32)i + 1; x < end; ++x) rank += s_lo[x] < mine;
+      } else {
+        const u64 mine = s_c[i];
+        for (i32 x = start; x < (i32)i; ++x) rank += s_c[x] <= mine;
+        for (i32 x = (i32)i + 1; x < end; ++x) rank += s_c[x] < mine;
+      }
+      const u64 dst = pos - (u64)((i32)i - start) + rank;
+      kout[dst] = kv[j];
       vout[dst] = idv[j];
     }
   }
@@ -120,14 +176,17 @@ __device__ __forceinline__ u32 run_scan_tile(const u64* __restrict__ keys, const
 }
 
 // pass 1: place the rows of short runs, count rows of long runs per tile
+template <bool SUB32>
 static __global__ void __launch_bounds__(SC_THREADS)
     local_order_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, int run_shift, int cmp_shift,
                        u64* __restrict__ kout, u32* __restrict__ vout, u64* __restrict__ spine) {
-  __shared__ u64 s_k[SC_TILE + 2 * RUN_HALO];
+  __shared__ u64 s_c[RUN_STAGED];
+  __shared__ u32 s_lo[SUB32 ? RUN_STAGED : 1];
+  __shared__ u32 s_head[RUN_WORDS];
   __shared__ u64 s_tmp[8];
   const u64 base = (u64)blockIdx.x * SC_TILE;
   const u64 rows = n - base < (u64)SC_TILE ? n - base : (u64)SC_TILE;
-  const u32 mask = run_scan_tile<true>(keys, ids, n, run_shift, cmp_shift, base, rows, s_k, kout, vout);
+  const u32 mask = run_scan_tile<true, SUB32>(keys, ids, n, run_shift, cmp_shift, base, rows, s_c, s_lo, s_head, kout, vout);
   const u64 c = block_sum_u64((u64)__popc(mask), s_tmp);
   if (threadIdx.x == 0) spine[blockIdx.x] = c;
 }
@@ -136,7 +195,8 @@ static __global__ void __launch_bounds__(SC_THREADS)
     long_run_gather_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, int run_shift,
                            const u64* __restrict__ spine, u64 ntiles, const u64* __restrict__ nT,
                            u64* __restrict__ tkeys, u32* __restrict__ tids, u32* __restrict__ tpos) {
-  __shared__ u64 s_k[SC_TILE + 2 * RUN_HALO];
+  __shared__ u64 s_c[RUN_STAGED];
+  __shared__ u32 s_head[RUN_WORDS];
   __shared__ u64 s_tmp[8];
   const u64 tile = blockIdx.x;
   const u64 first = spine[tile];
@@ -144,14 +204,14 @@ static __global__ void __launch_bounds__(SC_THREADS)
   if (next == first) return;  // nearly every tile of real data
   const u64 base = tile * SC_TILE;
   const u64 rows = n - base < (u64)SC_TILE ? n - base : (u64)SC_TILE;
-  const u32 mask = run_scan_tile<false>(keys, nullptr, n, run_shift, 0, base, rows, s_k, nullptr, nullptr);
+  const u32 mask = run_scan_tile<false, false>(keys, nullptr, n, run_shift, 0, base, rows, s_c, nullptr, s_head, nullptr, nullptr);
   u64 tot;
   u64 at_out = first + block_excl_sum_u64((u64)__popc(mask), s_tmp, &tot);
 #pragma unroll
   for (int j = 0; j < SC_IPT; ++j) {
     if (mask & (1u << j)) {
       const u32 r = threadIdx.x * SC_IPT + j;
-      tkeys[at_out] = s_k[r + RUN_HALO];
+      tkeys[at_out] = s_c[r + RUN_HALO];  // cmp_shift = 0 here: the staged value is the key itself
       tids[at_out] = ids[base + r];
       tpos[at_out] = (u32)(base + r);
       ++at_out;
@@ -171,17 +231,24 @@ static __global__ void __launch_bounds__(256) tie_scatter_kernel(const u64* __re
 
 // ---------------------------------------------------------------- host side
 
-// How many low bits of the B-bit (group, start) field the radix passes may leave to the finishing pass: a run
-// of 2^drop positions should hold about 8-16 rows of evenly spread input, and the sorted bits fill whole 8-bit
-// passes.  1e8 rows on the 32-bit hg38 axis: drop = 8, three passes instead of four.
+// How many low bits of the B-bit (group, start) field the radix passes may leave to the finishing pass.
+// Every dropped byte saves a pass over the data (24 B/row), but the finishing pass pays ~6 instructions per
+// pair of rows that share a run: measured at 1e8 rows on the 32-bit hg38 axis (profiles/NOTES.md, r2), three
+// passes + runs of ~8 rows cost 2.31 + 1.47 ms against 3.08 + 0.53 ms for four passes + runs of ~1 row -- a
+// loss -- while sets whose runs stay around one row (1e7 rows: 0.8 per 256 positions) just lose a pass.  So
+// bits are dropped only while the expected run of evenly spread rows, n * 2^drop / 2^B, stays below 1.5.
 static inline int choose_drop_bits(int B, i64 n) {
   if (n <= 0) return 0;
-  int drop = B - bit_width((u64)n) + 3;
-  if (drop <= 0) return 0;
-  if (drop > B) drop = B;
-  const int passes = (B - drop + 7) / 8;
-  const int sorted_bits = passes * 8 < B ? passes * 8 : B;
-  return B - sorted_bits;
+  int best = 0;
+  for (int passes = (B + 7) / 8; passes >= 0; --passes) {
+    const int sorted_bits = passes * 8 < B ? passes * 8 : B;
+    const int drop = B - sorted_bits;
+    // expected rows per run = n / 2^(B - drop) <= 1.5
+    const double buckets = sorted_bits >= 63 ? 9.2e18 : (double)(1ull << sorted_bits);
+    if ((double)n > 1.5 * buckets) break;
+    best = drop;
+  }
+  return best;
 }
 
 // ---- clamp mode: (group, start, true end', row) by two stable sorts ----
@@ -268,9 +335,15 @@ static int sort_rows(const i32* grp, const i64* s, const i64* e, i64 n, const Ke
   BF_TRY(radix_sort_passes<true>(ws.keyA, ws.keyB, ws.idA, ws.idB, true, (u64)n, nullptr, rp, sc, st, res));
   if (keep_row_order && drop == 0) return BF_OK;  // runs = equal (group, start), already in row order
   const unsigned tiles = (unsigned)scan_tiles((u64)n);
-  BF_LAUNCH(PC_TIEFIX, 24 * n, st,
-            local_order_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, run_shift, cmp_shift, res->keys_alt,
-                                                            res->vals_alt, ws.spine));
+  if (run_shift - cmp_shift <= 32) {
+    BF_LAUNCH(PC_TIEFIX, 24 * n, st,
+              local_order_kernel<true><<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, run_shift, cmp_shift,
+                                                                    res->keys_alt, res->vals_alt, ws.spine));
+  } else {
+    BF_LAUNCH(PC_TIEFIX, 24 * n, st,
+              local_order_kernel<false><<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, run_shift, cmp_shift,
+                                                                     res->keys_alt, res->vals_alt, ws.spine));
+  }
   {  // the ordered rows are in the other buffer pair now
     u64* tk = res->keys;
     res->keys = res->keys_alt;

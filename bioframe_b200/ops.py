@@ -106,6 +106,33 @@ def _group_keys(df, by):
     return codes, keys
 
 
+def _is_na(x):
+    return x is None or x is pd.NA or x is pd.NaT or (isinstance(x, float) and x != x)
+
+
+def _chrom_is_na(key):
+    """Does a group key (scalar, or tuple with the chromosome first) have a null chromosome?"""
+    return _is_na(key[0]) if isinstance(key, tuple) else _is_na(key)
+
+
+def _group_keys_shared_na(df, by):
+    """Group code per row (always >= 0) and the keys in sorted-groupby order with NA as a key value of its
+    own, the way `df.groupby(by, dropna=False).indices` of the reference sees them (ops.py:287-288): every
+    null is the np.nan singleton, so a key such as ('chr1', nan) -- a null in an `on` column -- is ONE key
+    shared by both frames.  Keys whose chromosome is null belong to all-null rows (checks.is_bedframe): the
+    callers keep those from pairing."""
+    if len(by) == 1:
+        codes, keys = _factorize_column(df[by[0]])
+        if (codes < 0).any():
+            codes = np.where(codes < 0, len(keys), codes)
+            keys = keys + [np.nan]
+        return codes, keys
+    gb = df.groupby(by, observed=True, sort=True, dropna=False)
+    codes = gb.ngroup().to_numpy(dtype=np.int64)
+    keys = [tuple(np.nan if _is_na(x) else x for x in key) for key in gb.size().index]
+    return codes, keys
+
+
 def _int64_coords(df, col):
     """Coordinate column as int64 numpy; NA (nullable dtypes) -> 0 (such rows
     never reach a kernel as pairable: they sit in their own NA group)."""
@@ -147,37 +174,33 @@ def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _gro
         by1 = by1 + list(on)
         by2 = by2 + list(on)
 
-    codes1, keys1 = _group_keys(df1, by1)
-    codes2, keys2 = _group_keys(df2, by2)
-    # dropna=False in the reference: NA-keyed rows form one more group per frame,
-    # visited where the NaN key falls in the set order; they can never pair.
-    na1 = bool((codes1 < 0).any())
-    na2 = bool((codes2 < 0).any())
-    nan_key = float("nan")
-    k1 = keys1 + ([nan_key] if na1 else [])
-    k2 = keys2 + ([nan_key] if na2 else [])
-    order = list(set.union(set(k1), set(k2))) if _group_order is None else list(_group_order)
+    codes1, keys1 = _group_keys_shared_na(df1, by1)
+    codes2, keys2 = _group_keys_shared_na(df2, by2)
+    # dropna=False in the reference (ops.py:287-288): a null in an `on` column is a key value like any other,
+    # shared by both frames; the groups are visited in the order of the union set (ops.py:289, 301)
+    order = list(set.union(set(keys1), set(keys2))) if _group_order is None else [
+        np.nan if _is_na(k) else k for k in _group_order]
 
-    # rank of every group in the visiting order; the NA groups of the two frames
-    # get two adjacent ranks so that they stay unpaired
-    rank = {}
+    # rank of every group in the visiting order.  A key with a null CHROMOSOME holds all-null rows
+    # (checks.is_bedframe): their coordinates are NaN in the reference and never overlap anything, so the two
+    # frames' rows of such a key get two adjacent ranks -- same block position, never paired.
+    rank1, rank2 = {}, {}
     next_rank = 0
-    rank_na1 = rank_na2 = -1
     for key in order:
-        if isinstance(key, float) and key != key:
-            rank_na1, rank_na2 = next_rank, next_rank + 1
+        if _chrom_is_na(key):
+            rank1[key], rank2[key] = next_rank, next_rank + 1
             next_rank += 2
         else:
-            rank[key] = next_rank
+            rank1[key] = rank2[key] = next_rank
             next_rank += 1
     n_groups = max(next_rank, 1)
 
-    def ranks_of(codes, keys, rank_na):
-        table = np.array([rank[k] for k in keys] + [rank_na], dtype=np.int32)
-        return table[codes]  # code -1 picks the last entry
+    def ranks_of(codes, keys, rank):
+        table = np.array([rank[k] for k in keys], dtype=np.int32)
+        return table[codes]
 
-    g1 = ranks_of(codes1, keys1, rank_na1) if len(df1) else np.empty(0, np.int32)
-    g2 = ranks_of(codes2, keys2, rank_na2) if len(df2) else np.empty(0, np.int32)
+    g1 = ranks_of(codes1, keys1, rank1) if len(df1) else np.empty(0, np.int32)
+    g2 = ranks_of(codes2, keys2, rank2) if len(df2) else np.empty(0, np.int32)
     s1, e1, s2, e2 = _int64_coords(df1, sk1), _int64_coords(df1, ek1), _int64_coords(df2, sk2), _int64_coords(df2, ek2)
     t0 = _tick("encode_groups", t0)
     if _coords or _PROFILE is not None:
@@ -763,13 +786,18 @@ def _overlap_counts(df1, df2, cols1, cols2, on):
         _verify_columns(df1, on)
         _verify_columns(df2, on)
         by1, by2 = by1 + on, by2 + on
-    codes1, keys1 = _group_keys(df1, by1)
-    codes2, keys2 = _group_keys(df2, by2)
+    codes1, keys1 = _group_keys_shared_na(df1, by1)
+    codes2, keys2 = _group_keys_shared_na(df2, by2)
+    # a null in an `on` column is an ordinary key shared by both frames (groupby(dropna=False), ops.py:287-288);
+    # rows with a null chromosome are all-null rows and overlap nothing
     union = sorted(set(keys1) | set(keys2), key=str)
     rank = {key: r for r, key in enumerate(union)}
     t1 = np.array([rank[k] for k in keys1], dtype=np.int32)
     t2 = np.array([rank[k] for k in keys2], dtype=np.int32)
-    v1, v2 = np.flatnonzero(codes1 >= 0), np.flatnonzero(codes2 >= 0)
+    ok1 = np.array([not _chrom_is_na(k) for k in keys1], dtype=bool)
+    ok2 = np.array([not _chrom_is_na(k) for k in keys2], dtype=bool)
+    v1 = np.flatnonzero(ok1[codes1]) if len(df1) else np.empty(0, np.int64)
+    v2 = np.flatnonzero(ok2[codes2]) if len(df2) else np.empty(0, np.int64)
     counts = np.zeros(len(df1), dtype=np.int64)
     if len(v1):
         got = _engine.count_overlaps(

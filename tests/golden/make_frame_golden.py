@@ -151,6 +151,18 @@ def main():
     add("merge_runs_int", "merge_runs", df=graph, col="state")
     add("merge_runs_agg", "merge_runs", df=graph, col="signal", agg={"n": ("state", "count"), "top": ("state", "max")})
     add("mark_runs_overlapping", "mark_runs", df=frames(rng3)[0], col="score", allow_overlaps=True)
+    # nulls inside an `on` column: groupby(dropna=False) of the reference makes ('chr1', nan) ONE key
+    # shared by both frames (ops.py:287-288), so such rows are overlapped with each other; all-null rows
+    # (null chromosome) still never pair.  Own generator: the cases above keep their inputs.
+    rng4 = np.random.default_rng(404)
+    for tag, opts in (("na", dict(with_na=True)), ("plain", {})):
+        df1, df2 = frames(rng4, n1=70, n2=55, **opts)
+        for df in (df1, df2):
+            df.loc[df.index[3::5], "strand"] = None
+        for how in ("inner", "left", "outer", "right"):
+            add(f"overlap_{tag}_on_null_{how}", "overlap", df1=df1, df2=df2, how=how, on=["strand"], return_index=True)
+        add(f"count_overlaps_{tag}_on_null", "count_overlaps", df1=df1, df2=df2, on=["strand"])
+        add(f"setdiff_{tag}_on_null", "setdiff", df1=df1, df2=df2, on=["strand"])
     with open(os.path.join(HERE, "frames.pkl"), "wb") as f:
         pickle.dump(cases, f, protocol=4)
     print(len(cases), "cases ->", os.path.join(HERE, "frames.pkl"))

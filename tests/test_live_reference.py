@@ -103,3 +103,21 @@ def test_live_closest_tie_free(ref, ours, seed):
     for kw in (dict(k=1), dict(k=3, return_overlap=True, return_index=True), dict(k=2, ignore_overlaps=True),
                dict(k=2, ignore_upstream=True), dict(k=1, ignore_downstream=True)):
         pd.testing.assert_frame_equal(_canon(ours.closest(df1, df2, **kw)), _canon(ref.closest(df1, df2, **kw)))
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_live_nulls_in_on_column(ref, ours, seed):
+    """A null in an `on` column is a key value shared by both frames (groupby(dropna=False), ops.py:287-288);
+    all-null rows never pair.  Same process, same hash seed: the block order must match too."""
+    rng = np.random.default_rng(4000 + seed)
+    df1, df2 = _frame(rng, 80), _frame(rng, 60, chroms=("chr2", "chrX", "chr1"))
+    for df in (df1, df2):
+        df["strand"] = rng.choice(np.array(["+", "-", None], dtype=object), len(df))
+        df["start"] = df["start"].astype(pd.Int64Dtype())
+        df["end"] = df["end"].astype(pd.Int64Dtype())
+        df.loc[df.index[::13], ["chrom", "start", "end"]] = pd.NA
+    for how in ("inner", "left", "outer", "right"):
+        kw = dict(how=how, on=["strand"], return_index=True)
+        pd.testing.assert_frame_equal(ours.overlap(df1, df2, **kw), ref.overlap(df1, df2, **kw))
+    pd.testing.assert_frame_equal(ours.count_overlaps(df1, df2, on=["strand"]), ref.count_overlaps(df1, df2, on=["strand"]))
+    pd.testing.assert_frame_equal(ours.setdiff(df1, df2, on=["strand"]), ref.setdiff(df1, df2, on=["strand"]))
