@@ -142,9 +142,9 @@ __global__ void __launch_bounds__(256)
 }
 
 static int gather_rows_impl(const void* src, i32 itemsize, const i64* idx, i64 n, void* out, u8* valid, cudaStream_t st) {
-  if (n < 0 || (itemsize != 4 && itemsize != 8)) {
-    set_error("bf_gather_rows: bad argument (n_rows=%lld itemsize=%d; 4- and 8-byte columns are supported)", (long long)n,
-              itemsize);
+  if (n < 0 || (itemsize != 1 && itemsize != 2 && itemsize != 4 && itemsize != 8)) {
+    set_error("bf_gather_rows: bad argument (n_rows=%lld itemsize=%d; 1-, 2-, 4- and 8-byte columns are supported)",
+              (long long)n, itemsize);
     return BF_ERR_ARG;
   }
   if (n == 0) return BF_OK;
@@ -156,9 +156,15 @@ static int gather_rows_impl(const void* src, i32 itemsize, const i64* idx, i64 n
   if (itemsize == 8) {
     BF_LAUNCH(PC_GATHER, 24 * n, st,
               gather_rows_kernel<u64><<<grid, 256, 0, st>>>((const u64*)src, idx, n, (u64*)out, valid));
-  } else {
+  } else if (itemsize == 4) {
     BF_LAUNCH(PC_GATHER, 16 * n, st,
               gather_rows_kernel<u32><<<grid, 256, 0, st>>>((const u32*)src, idx, n, (u32*)out, valid));
+  } else if (itemsize == 2) {  // categorical codes of up to 32767 categories
+    BF_LAUNCH(PC_GATHER, 12 * n, st,
+              gather_rows_kernel<u16><<<grid, 256, 0, st>>>((const u16*)src, idx, n, (u16*)out, valid));
+  } else {  // int8 categorical codes (chromosomes), bool columns, the mask bytes of nullable columns
+    BF_LAUNCH(PC_GATHER, 10 * n, st,
+              gather_rows_kernel<u8><<<grid, 256, 0, st>>>((const u8*)src, idx, n, (u8*)out, valid));
   }
   return BF_OK;
 }

@@ -400,13 +400,13 @@ def overlap_ordered(grp1, start1, end1, grp2, start2, end2, n_groups, device=Non
 
 
 def gather_rows(column, idx, want_valid=False, device=None):
-    """column[idx] for a 4- or 8-byte numeric column (numpy array or tensor) and device row numbers `idx`
+    """column[idx] for a 1-, 2-, 4- or 8-byte column (numpy array or tensor) and device row numbers `idx`
     (-1 -> 0) -> device tensor of the column's dtype (and the validity bytes when asked)."""
     _require_cuda()
     device = torch.device(device if device is not None else "cuda")
     col = column if isinstance(column, torch.Tensor) else torch.as_tensor(column)
-    if col.element_size() not in (4, 8) or col.dtype in (torch.complex64,):
-        raise ValueError("gather_rows: 4- or 8-byte numeric column expected")
+    if col.element_size() not in (1, 2, 4, 8) or col.dtype in (torch.complex64,):
+        raise ValueError("gather_rows: 1-, 2-, 4- or 8-byte column expected")
     col = col.to(device=device, non_blocking=True).contiguous()
     ix = _as(idx, torch.int64, device)
     n = int(ix.numel())

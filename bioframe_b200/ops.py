@@ -272,29 +272,52 @@ def _suffixed_rows(df, positions, suffix):
 # Results of this many rows and more are assembled with device-side column gathers (bf_gather_rows): taking
 # 1e8+ rows of a column with numpy costs seconds per column; the device does it at PCIe speed.
 _DEVICE_GATHER_MIN_ROWS = 1 << 22
-_GATHER_DTYPES = (np.dtype(np.int64), np.dtype(np.int32), np.dtype(np.float64), np.dtype(np.float32))
+_SAME_WIDTH_INT = {1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}
+
+
+def _device_take(values, device_positions):
+    """values[positions] for a fixed-width numpy array (1, 2, 4 or 8 bytes per item, any dtype of that width)
+    through bf_gather_rows; position -1 yields 0.  -> numpy array of the same dtype."""
+    values = np.ascontiguousarray(values)
+    as_int = _SAME_WIDTH_INT[values.dtype.itemsize]
+    taken = _engine.gather_rows(values.view(as_int), device_positions)
+    small = values.dtype == np.int64 and len(values) and values.min() >= -1 and values.max() < 2**31 - 1
+    host = _rows_to_host(taken) if small else _to_host(taken)
+    return host.view(values.dtype)
+
+
+def _fixed_width(dtype):
+    return isinstance(dtype, np.dtype) and dtype.kind in "iufbmM" and dtype.itemsize in _SAME_WIDTH_INT
+
+
+def _taken_column(col, positions, device_positions):
+    """One column of `df.iloc[positions]` (ops.py:499-508) as a pandas array, built from device gathers where
+    the column has a fixed-width representation -- plain numeric / bool / datetime values, the integer codes of
+    a categorical (chromosome names!), the value + mask pair of a nullable column (the Arrow layout) -- and
+    with pandas' take otherwise (object / string columns).  Position -1 picks an arbitrary valid value: the
+    caller blanks those rows, as the reference blanks what it took from position -1."""
+    dtype = col.dtype
+    if _fixed_width(dtype):
+        return _device_take(col.to_numpy(), device_positions)
+    if isinstance(dtype, pd.CategoricalDtype) and len(dtype.categories):
+        codes = _device_take(np.asarray(col.cat.codes), device_positions)
+        return pd.Categorical.from_codes(codes, dtype=dtype)
+    arr = col.array
+    if isinstance(arr, (pd.arrays.IntegerArray, pd.arrays.FloatingArray, pd.arrays.BooleanArray)) and _fixed_width(arr._data.dtype):
+        values = _device_take(arr._data, device_positions)
+        mask = _device_take(arr._mask, device_positions)
+        return type(arr)(values, mask)
+    return col.iloc[positions].array
 
 
 def _taken_rows(df, positions, device_positions, suffix):
-    """`df.iloc[positions]` with suffixed column names (ops.py:499-508).  For large results the fixed-width
-    numeric columns are gathered on the device from the pair list that still lives there (-1 -> 0: such rows
-    are blanked afterwards, as the reference blanks the rows it took from position -1); the other columns
-    (strings, categoricals, nullable dtypes) go through pandas."""
+    """`df.iloc[positions]` with suffixed column names (ops.py:499-508).  For large results the pair list still
+    lives on the device and every column with a fixed-width representation is gathered there
+    (`_taken_column`); only object / string columns go through pandas."""
     if device_positions is None or len(positions) < _DEVICE_GATHER_MIN_ROWS or not df.columns.is_unique:
         return _suffixed_rows(df, positions, suffix)
-    on_device = [c for c in df.columns if isinstance(df[c].dtype, np.dtype) and df[c].dtype in _GATHER_DTYPES]
-    others = [c for c in df.columns if c not in on_device]
-    rest = df[others].iloc[positions].reset_index(drop=True) if others else None
-    data = {}
-    for c in df.columns:
-        if c in on_device:
-            col = df[c].to_numpy()
-            taken = _engine.gather_rows(col, device_positions)
-            small = col.dtype == np.int64 and len(col) and col.min() >= -1 and col.max() < 2**31 - 1
-            data[c + suffix] = _rows_to_host(taken) if small else _to_host(taken)
-        else:
-            data[c + suffix] = rest[c].array
-    return pd.DataFrame(data, columns=[c + suffix for c in df.columns])
+    data = {c + suffix: _taken_column(df[c], positions, device_positions) for c in df.columns}
+    return pd.DataFrame(data, columns=[c + suffix for c in df.columns], copy=False)
 
 
 def overlap(
@@ -360,8 +383,12 @@ def overlap(
     stem = return_index if isinstance(return_index, str) else "index"
     icol1, icol2 = stem + suffixes[0], stem + suffixes[1]
     parts = {}
-    parts["i1"] = pd.DataFrame({icol1: df1.index[ev1]}, dtype=pd.Int64Dtype())
-    parts["i2"] = pd.DataFrame({icol2: df2.index[ev2]}, dtype=pd.Int64Dtype())
+    # the index columns are only built when they are returned or needed to order the rows (the reference always
+    # builds them, ops.py:464-478, and drops them at the end when return_index is False, ops.py:552-553)
+    need_index = bool(return_index) or (bool(keep_order) and not device_order)
+    if need_index:
+        parts["i1"] = pd.DataFrame({icol1: df1.index[ev1]}, dtype=pd.Int64Dtype())
+        parts["i2"] = pd.DataFrame({icol2: df2.index[ev2]}, dtype=pd.Int64Dtype())
 
     if return_overlap:
         ostem = return_overlap if isinstance(return_overlap, str) else "overlap"
@@ -381,8 +408,9 @@ def overlap(
     if how != "inner":  # blank the side that has no partner (ops.py:511-544)
         miss1, miss2 = ev1 == -1, ev2 == -1
         any1, any2 = bool(miss1.any()), bool(miss2.any())
-        parts["i1"][miss1] = None
-        parts["i2"][miss2] = None
+        if need_index:
+            parts["i1"][miss1] = None
+            parts["i2"][miss2] = None
         for tag, miss, any_miss, df, sk, ek, suf in (
             ("in1", miss1, any1, df1, sk1, ek1, suffixes[0]),
             ("in2", miss2, any2, df2, sk2, ek2, suffixes[1]),
@@ -398,10 +426,11 @@ def overlap(
             parts["ov"] = parts["ov"].convert_dtypes()
             parts["ov"][miss1 | miss2] = None
 
-    out = pd.concat([parts.get(k) for k in ("i1", "in1", "i2", "in2", "ov")], axis=1)
+    kept = [parts[k] for k in ("i1", "in1", "i2", "in2", "ov") if k in parts]
+    out = pd.concat(kept, axis=1) if kept else pd.DataFrame(index=pd.RangeIndex(len(ev1)))
     if keep_order and not device_order:
         out = out.sort_values([icol1, icol2])
-    if not return_index:
+    if need_index and not return_index:
         out.drop([icol1, icol2], axis=1, inplace=True)
     out.reset_index(drop=True, inplace=True)
     _tick("assemble_frame", t0)

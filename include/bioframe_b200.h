@@ -177,8 +177,9 @@ int bf_pair_coords(const int64_t* events1, const int64_t* events2, int64_t n_row
                    int64_t* overlap_end_out, int64_t* distance_out, void* stream);
 
 /* ---- column gather: replaces `df.iloc[events]` of the frame assembly (ops.py:499-508, 1224-1234) for
- * fixed-width numeric columns: out[i] = src[row_idx[i]] (itemsize 4 or 8 bytes, any numeric type of that
- * width), 0 where row_idx[i] is -1; valid_out (optional, uint8[n_rows]) = 1 where a row was taken -- value
+ * fixed-width columns: out[i] = src[row_idx[i]] (itemsize 1, 2, 4 or 8 bytes, any type of that width:
+ * numeric values, the integer codes of a categorical column, the mask bytes of a nullable column), 0 where
+ * row_idx[i] is -1; valid_out (optional, uint8[n_rows]) = 1 where a row was taken -- value
  * buffer + validity, the Arrow layout of a nullable column. */
 int bf_gather_rows(const void* src, int32_t itemsize, const int64_t* row_idx, int64_t n_rows, void* out,
                    uint8_t* valid_out, void* stream);
