@@ -51,152 +51,145 @@ static inline void take_sort_bufs(Arena& a, i64 n, SortBufs* b) {
 // key bits with the stable radix sort and written back into the same slots.
 constexpr int RUN_MAX = 64;
 constexpr int RUN_HALO = RUN_MAX;
-constexpr int RUN_STAGED = SC_TILE + 2 * RUN_HALO;  // 2176 staged rows = 68 words of run-head bits
-constexpr int RUN_WORDS = RUN_STAGED / 32;
-static_assert(RUN_STAGED % 32 == 0 && RUN_HALO % 32 == 0, "head bit words must tile the staged rows");
+constexpr int RUN_STAGED = SC_TILE + 2 * RUN_HALO;  // rows a tile stages: its own and RUN_HALO either side
 
-// Stage a tile and classify / place its rows.  PLACE: write every row of a short run to its final position in
-// (kout, vout), copy rows of long runs through.  Returns the mask of this thread's rows that belong to long
-// runs; bit j of the mask is tile row  j * SC_THREADS + tid  (PLACE)  or  tid * SC_IPT + j  (!PLACE: the
-// compaction needs consecutive rows per thread).
-//   s_c[i]   = keys[base - RUN_HALO + i] >> cmp_shift   (what rows are compared by)
-//   s_head   = one bit per staged row: the row starts a run (its key >> run_shift differs from its
-//              predecessor's).  A row finds its run as [last head at or before it, next head after it) with a
-//              few bit operations on at most three words either way -- no walk, no divergence; a run whose
-//              bounds are not inside that reach is longer than RUN_MAX.
-//   SUB32: run_shift - cmp_shift <= 32, so rows of one run differ only in the low 32 bits of s_c: the rank
-//              loop then reads 4-byte words (s_lo).
-template <bool PLACE, bool SUB32>
-__device__ __forceinline__ u32 run_scan_tile(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n,
-                                             int run_shift, int cmp_shift, u64 base, u64 rows, u64* s_c, u32* s_lo,
-                                             u32* s_head, u64* __restrict__ kout, u32* __restrict__ vout) {
-  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  u64 kv[SC_IPT];
-  u32 idv[SC_IPT];
+// Stage a tile and classify / place its rows, IN PLACE.
+//   s_k[i] = keys[base - RUN_HALO + i]; rows are compared by s_k >> cmp_shift; two neighbours belong to one
+//   run when they agree at and above bit run_shift, i.e. (a ^ b) < 2^run_shift.
+// Nearly every row of sparse data is a run of its own: two comparisons with its neighbours and it is done.  A
+// row with an equal neighbour walks to both ends of its run (at most RUN_MAX rows, else the run is "long") and
+// counts on the way the rows that must precede it.
+// PLACE: every short run is put in order by the ONE tile that holds its first row -- so the rows of a run are
+// read (from the staged snapshot) and written by a single block: in place without a race; the rows of the run
+// may reach up to RUN_MAX - 1 rows into the next tile's range, which skips them.  A row that already is where it
+// belongs is not written at all, so the pass reads 8 B per row and writes next to nothing.  Rows that move
+// are parked in a list in shared memory (slot, destination, row id) and written after a barrier, when every
+// row id that moves has been read.  Another tile may stage rows of a run while its owner rewrites them: it
+// only looks at their run prefix, which every version of the row shares.
+// Returns the mask of this thread's OWN tile rows that belong to long runs; bit j is tile row
+// j * SC_THREADS + tid (PLACE) or tid * SC_IPT + j (!PLACE: the compaction needs consecutive rows per thread).
+struct RunMove {
+  u32 id;
+  u16 from, to;  // staged indices
+};
+constexpr int RUN_MOVES = SC_TILE + RUN_HALO;  // every row a tile can own
+
+template <bool PLACE>
+__device__ __forceinline__ u32 run_scan_tile(u64* __restrict__ keys, u32* __restrict__ ids, u64 n, int run_shift,
+                                             int cmp_shift, u64 base, u64 rows, u64* s_k, RunMove* s_move,
+                                             u32* s_nmove) {
+  const u32 tid = threadIdx.x;
+  // staged indices [v_lo, v_hi) hold rows of the array (32-bit from here on: the kernel is bound by its
+  // instruction count, and 64-bit index arithmetic doubles it)
+  const u32 v_lo = base >= (u64)RUN_HALO ? 0u : (u32)(RUN_HALO - base);
+  const u64 left = n - (base + v_lo - RUN_HALO);  // rows from staged index v_lo to the end of the array
+  const u32 v_hi = left >= (u64)(RUN_STAGED - v_lo) ? (u32)RUN_STAGED : v_lo + (u32)left;
+  const u64* kp = keys + base - RUN_HALO;  // kp[i] = staged row i (only dereferenced for v_lo <= i < v_hi)
   {  // all loads of a thread in flight before its first store
-    u64 hv = ~0ull;
-#pragma unroll
-    for (int j = 0; j < SC_IPT; ++j) {
-      const u64 p = base + (u64)j * SC_THREADS + tid;
-      kv[j] = p < n ? keys[p] : ~0ull;
-      if (PLACE) idv[j] = p < n ? ids[p] : 0u;
-    }
-    if (tid < 2 * RUN_HALO) {
-      const i64 p = tid < RUN_HALO ? (i64)base - RUN_HALO + tid : (i64)base + SC_TILE + (tid - RUN_HALO);
-      if (p >= 0 && (u64)p < n) hv = keys[p];
-      const u32 i = tid < RUN_HALO ? tid : SC_TILE + tid;
-      s_c[i] = hv >> cmp_shift;
-      if (SUB32) s_lo[i] = (u32)(hv >> cmp_shift);
-    }
+    u64 v[SC_IPT], hv = ~0ull;
+    const u32 hi = tid < RUN_HALO ? tid : SC_TILE + tid;  // this thread's halo row (threads 0 .. 2 * RUN_HALO - 1)
 #pragma unroll
     for (int j = 0; j < SC_IPT; ++j) {
       const u32 i = RUN_HALO + j * SC_THREADS + tid;
-      s_c[i] = kv[j] >> cmp_shift;
-      if (SUB32) s_lo[i] = (u32)(kv[j] >> cmp_shift);
+      v[j] = i < v_hi ? kp[i] : ~0ull;  // tile rows are never below v_lo
     }
-  }
-  __syncthreads();
-  const int pshift = run_shift - cmp_shift;  // run prefix of a staged value; 64 = every row in one run
-  for (u32 c = warp; c < RUN_WORDS; c += SC_THREADS / 32) {
-    const u32 i = c * 32 + lane;
-    const i64 p = (i64)base - RUN_HALO + (i64)i;
-    bool head = true;  // rows outside the array and the first staged row close / open a run
-    if (p > 0 && (u64)p < n && i > 0) {
-      const u64 a = s_c[i], b = s_c[i - 1];
-      head = pshift < 64 && (a >> pshift) != (b >> pshift);
+    if (tid < 2 * RUN_HALO) {
+      if (hi >= v_lo && hi < v_hi) hv = kp[hi];
+      s_k[hi] = hv;
     }
-    const u32 m = __ballot_sync(0xffffffffu, head);
-    if (lane == 0) s_head[c] = m;
-  }
-  __syncthreads();
-  u32 mask = 0;
 #pragma unroll
-  for (int j = 0; j < SC_IPT; ++j) {
-    const u32 r = PLACE ? (u32)j * SC_THREADS + tid : tid * SC_IPT + j;
-    if (r >= rows) continue;
-    const u32 i = r + RUN_HALO, c = i >> 5, l = i & 31;
-    // first row of my run: the last head at or before me
-    i32 start = -1;
-    {
-      const u32 w0 = s_head[c] & (0xffffffffu >> (31 - l));
-      if (w0) {
-        start = (i32)(c << 5) + 31 - __clz(w0);
-      } else {
-        const u32 w1 = s_head[c - 1];
-        if (w1) {
-          start = (i32)((c - 1) << 5) + 31 - __clz(w1);
-        } else {
-          const u32 w2 = s_head[c - 2];
-          if (w2) start = (i32)((c - 2) << 5) + 31 - __clz(w2);
-        }
-      }
+    for (int j = 0; j < SC_IPT; ++j) s_k[RUN_HALO + j * SC_THREADS + tid] = v[j];
+    if (PLACE && tid == 0) *s_nmove = 0;
+  }
+  __syncthreads();
+  // run_shift = 64: the whole set is one run (a tiny set sorted by this pass alone)
+  const u64 run_lim = run_shift < 64 ? 1ull << run_shift : ~0ull;
+  const bool one_run = run_shift >= 64;
+  auto same_run = [&](u64 a, u64 b) { return one_run || (a ^ b) < run_lim; };
+  u32 mask = 0;
+  const u32 nrows = (u32)rows;
+  // rows of this thread: SC_IPT tile rows, and for RUN_HALO threads one row of the forward halo (a run that
+  // starts in this tile may end there)
+#pragma unroll 1
+  for (int j = 0; j <= SC_IPT; ++j) {
+    u32 r;
+    if (j < SC_IPT) {
+      r = PLACE ? (u32)j * SC_THREADS + tid : tid * SC_IPT + j;
+      if (r >= nrows) continue;
+    } else {
+      if (!PLACE || tid >= RUN_HALO) break;
+      r = SC_TILE + tid;
+      if (r + RUN_HALO >= v_hi) break;
     }
-    // one past its last row: the next head after me
-    i32 end = -1;
-    {
-      const u32 w0 = l == 31 ? 0u : s_head[c] & (0xffffffffu << (l + 1));
-      if (w0) {
-        end = (i32)(c << 5) + __ffs(w0) - 1;
-      } else {
-        const u32 w1 = s_head[c + 1];
-        if (w1) {
-          end = (i32)((c + 1) << 5) + __ffs(w1) - 1;
-        } else {
-          const u32 w2 = c + 2 < RUN_WORDS ? s_head[c + 2] : 0u;
-          if (w2) end = (i32)((c + 2) << 5) + __ffs(w2) - 1;
-        }
-      }
+    const u32 i = r + RUN_HALO;
+    const u64 k = s_k[i];
+    const bool prev_same = i > v_lo && same_run(k, s_k[i - 1]);
+    const bool next_same = i + 1 < v_hi && same_run(k, s_k[i + 1]);
+    if (!prev_same && !next_same) continue;  // a run of its own
+    // walk to both ends of the run; rows before me count when they compare <= me, rows after me when < me
+    const u64 mine = k >> cmp_shift;
+    u32 back = 0, fwd = 0, rank = 0;
+    while (back < RUN_MAX && i - back > v_lo) {
+      const u64 o = s_k[i - back - 1];
+      if (!same_run(k, o)) break;
+      rank += (o >> cmp_shift) <= mine;
+      ++back;
     }
-    const u64 pos = base + r;
-    const bool is_long = start < 0 || end < 0 || end - start > RUN_MAX || start == 0;  // staged row 0: bound unknown
-    if (is_long) {
-      mask |= 1u << j;
-      if (PLACE) {
-        kout[pos] = kv[j];
-        vout[pos] = idv[j];
-      }
-    } else if (PLACE) {
-      // rows of my run that precede me: earlier ones that compare <= me, later ones that compare < me
-      u32 rank = 0;
-      if (SUB32) {
-        const u32 mine = s_lo[i];
-        for (i32 x = start; x < (i32)i; ++x) rank += s_lo[x] <= mine;
-        for (i32 x = (i32)i + 1; x < end; ++x) rank += s_lo[x] < mine;
-      } else {
-        const u64 mine = s_c[i];
-        for (i32 x = start; x < (i32)i; ++x) rank += s_c[x] <= mine;
-        for (i32 x = (i32)i + 1; x < end; ++x) rank += s_c[x] < mine;
-      }
-      const u64 dst = pos - (u64)((i32)i - start) + rank;
-      kout[dst] = kv[j];
-      vout[dst] = idv[j];
+    while (fwd < RUN_MAX && i + fwd + 1 < v_hi) {
+      const u64 o = s_k[i + fwd + 1];
+      if (!same_run(k, o)) break;
+      rank += (o >> cmp_shift) < mine;
+      ++fwd;
+    }
+    if (back + fwd + 1 > RUN_MAX) {  // also when the walk ran into the edge of the staged rows
+      if (j < SC_IPT) mask |= 1u << j;
+      continue;
+    }
+    if (!PLACE) continue;  // classification only
+    const u32 start = i - back;
+    if (start < RUN_HALO || start >= RUN_HALO + SC_TILE) continue;  // the run belongs to another tile
+    if (rank != back) {  // the row moves
+      const u32 slot = atomicAdd(s_nmove, 1u);
+      RunMove m;
+      m.id = ids[base + r];
+      m.from = (u16)i;
+      m.to = (u16)(start + rank);
+      s_move[slot] = m;
+    }
+  }
+  if (PLACE) {
+    __syncthreads();  // every row id that moves has been read before the first one is overwritten
+    const u32 nm = *s_nmove;
+    for (u32 x = tid; x < nm; x += SC_THREADS) {
+      const RunMove m = s_move[x];
+      const u64 at = base + m.to - RUN_HALO;  // >= base: the run starts in this tile
+      keys[at] = s_k[m.from];
+      ids[at] = m.id;
     }
   }
   return mask;
 }
 
-// pass 1: place the rows of short runs, count rows of long runs per tile
-template <bool SUB32>
+// pass 1: order the short runs in place, count rows of long runs per tile
 static __global__ void __launch_bounds__(SC_THREADS)
-    local_order_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, int run_shift, int cmp_shift,
-                       u64* __restrict__ kout, u32* __restrict__ vout, u64* __restrict__ spine) {
-  __shared__ u64 s_c[RUN_STAGED];
-  __shared__ u32 s_lo[SUB32 ? RUN_STAGED : 1];
-  __shared__ u32 s_head[RUN_WORDS];
+    local_order_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u64 n, int run_shift, int cmp_shift,
+                       u64* __restrict__ spine) {
+  __shared__ u64 s_k[RUN_STAGED];
+  __shared__ RunMove s_move[RUN_MOVES];
+  __shared__ u32 s_nmove;
   __shared__ u64 s_tmp[8];
   const u64 base = (u64)blockIdx.x * SC_TILE;
   const u64 rows = n - base < (u64)SC_TILE ? n - base : (u64)SC_TILE;
-  const u32 mask = run_scan_tile<true, SUB32>(keys, ids, n, run_shift, cmp_shift, base, rows, s_c, s_lo, s_head, kout, vout);
+  const u32 mask = run_scan_tile<true>(keys, ids, n, run_shift, cmp_shift, base, rows, s_k, s_move, &s_nmove);
   const u64 c = block_sum_u64((u64)__popc(mask), s_tmp);
   if (threadIdx.x == 0) spine[blockIdx.x] = c;
 }
 // pass 2 (after the spine scan): tiles that hold rows of long runs compact them as (key, id, slot)
 static __global__ void __launch_bounds__(SC_THREADS)
-    long_run_gather_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids, u64 n, int run_shift,
+    long_run_gather_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u64 n, int run_shift,
                            const u64* __restrict__ spine, u64 ntiles, const u64* __restrict__ nT,
                            u64* __restrict__ tkeys, u32* __restrict__ tids, u32* __restrict__ tpos) {
-  __shared__ u64 s_c[RUN_STAGED];
-  __shared__ u32 s_head[RUN_WORDS];
+  __shared__ u64 s_k[RUN_STAGED];
   __shared__ u64 s_tmp[8];
   const u64 tile = blockIdx.x;
   const u64 first = spine[tile];
@@ -204,14 +197,14 @@ static __global__ void __launch_bounds__(SC_THREADS)
   if (next == first) return;  // nearly every tile of real data
   const u64 base = tile * SC_TILE;
   const u64 rows = n - base < (u64)SC_TILE ? n - base : (u64)SC_TILE;
-  const u32 mask = run_scan_tile<false, false>(keys, nullptr, n, run_shift, 0, base, rows, s_c, nullptr, s_head, nullptr, nullptr);
+  const u32 mask = run_scan_tile<false>(keys, ids, n, run_shift, 0, base, rows, s_k, nullptr, nullptr);
   u64 tot;
   u64 at_out = first + block_excl_sum_u64((u64)__popc(mask), s_tmp, &tot);
 #pragma unroll
   for (int j = 0; j < SC_IPT; ++j) {
     if (mask & (1u << j)) {
       const u32 r = threadIdx.x * SC_IPT + j;
-      tkeys[at_out] = s_c[r + RUN_HALO];  // cmp_shift = 0 here: the staged value is the key itself
+      tkeys[at_out] = s_k[r + RUN_HALO];
       tids[at_out] = ids[base + r];
       tpos[at_out] = (u32)(base + r);
       ++at_out;
@@ -335,23 +328,8 @@ static int sort_rows(const i32* grp, const i64* s, const i64* e, i64 n, const Ke
   BF_TRY(radix_sort_passes<true>(ws.keyA, ws.keyB, ws.idA, ws.idB, true, (u64)n, nullptr, rp, sc, st, res));
   if (keep_row_order && drop == 0) return BF_OK;  // runs = equal (group, start), already in row order
   const unsigned tiles = (unsigned)scan_tiles((u64)n);
-  if (run_shift - cmp_shift <= 32) {
-    BF_LAUNCH(PC_TIEFIX, 24 * n, st,
-              local_order_kernel<true><<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, run_shift, cmp_shift,
-                                                                    res->keys_alt, res->vals_alt, ws.spine));
-  } else {
-    BF_LAUNCH(PC_TIEFIX, 24 * n, st,
-              local_order_kernel<false><<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, run_shift, cmp_shift,
-                                                                     res->keys_alt, res->vals_alt, ws.spine));
-  }
-  {  // the ordered rows are in the other buffer pair now
-    u64* tk = res->keys;
-    res->keys = res->keys_alt;
-    res->keys_alt = tk;
-    u32* tv = res->vals;
-    res->vals = res->vals_alt;
-    res->vals_alt = tv;
-  }
+  BF_LAUNCH(PC_TIEFIX, 8 * n, st,
+            local_order_kernel<<<tiles, SC_THREADS, 0, st>>>(res->keys, res->vals, (u64)n, run_shift, cmp_shift, ws.spine));
   // rows of long runs (rare): compact, sort by the bits below the run prefix, write back into their slots
   u64* tkeyA = res->keys_alt;
   u32* tidA = res->vals_alt;
