@@ -69,6 +69,7 @@ def parse():
     ap.add_argument("--no-frame", action="store_true", help="skip the DataFrame-level leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE.json configs")
     ap.add_argument("--no-verify", action="store_true", help="N>1: skip the check against the single-GPU engine")
+    ap.add_argument("--force-ranged", action="store_true", help="run the range-sharded path even on one GPU (diagnostic)")
     ap.add_argument("--workload", default="overlap",
                     choices=["overlap", "cfg4", "cfg0", "closest", "cluster", "coverage", "count", "subtract", "ingest", "ordered"],
                     help="overlap = the north-star line (cfg3); cfg4 = 1e9 x 1e8 over the ranks; the others are the "
@@ -762,7 +763,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
     cfg4 = args.workload == "cfg4"
-    ranged = world > 1 or cfg4
+    ranged = world > 1 or cfg4 or args.force_ranged
     chunks = max(args.chunks, 1) if cfg4 else 1
 
     # ---- synthetic workload, host side (pinned: the e2e leg copies from here) ----

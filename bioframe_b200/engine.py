@@ -153,6 +153,30 @@ def overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how="inner
     return ev1, ev2, n_pairs.value
 
 
+class SetStores:
+    """Grow-only device buffers for prepared sets, one per (device, slot), kept across calls: a caller that
+    prepares the same two sets step after step (sharded.overlap_range_sharded) names its slots and never goes
+    back to the allocator -- a buffer used on two streams would otherwise be handed back through
+    record_stream and re-allocated.  The caller orders the streams itself."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, device, slot, nbytes):
+        key = (torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device(), slot)
+        buf = cls._cache.get(key)
+        if buf is None or buf.numel() < nbytes:
+            cls._cache.pop(key, None)
+            buf = None
+            buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            cls._cache[key] = buf
+        return buf
+
+    @classmethod
+    def release(cls):
+        cls._cache.clear()
+
+
 class SortedSet:
     """A set sorted once on the device (bf_overlap_prepare_set) or adopted from another rank
     (bf_overlap_adopt_set): `keys` (int64 view of the uint64 sort keys) and `ids` (int32 view of the uint32 row
@@ -194,8 +218,10 @@ def measure_extent(grp, start, end, n_groups, device=None):
     return words, bool(pres.value)
 
 
-def prepare_set(words, grp, start, end, n_groups, presorted=False, device=None):
-    """Sort one set for `overlap_prepared` with the key layout the merged extent `words` fix."""
+def prepare_set(words, grp, start, end, n_groups, presorted=False, device=None, slot=None):
+    """Sort one set for `overlap_prepared` with the key layout the merged extent `words` fix.
+    slot: name of a persistent store (SetStores) to sort into instead of a fresh allocation; the set then is
+    valid until the slot is prepared again."""
     import numpy as np
 
     _require_cuda()
@@ -207,7 +233,8 @@ def prepare_set(words, grp, start, end, n_groups, presorted=False, device=None):
     words = np.ascontiguousarray(words, dtype=np.int64)
     struct = _lib.SortedSetStruct()
     with torch.cuda.device(device):
-        store = torch.empty(max(int(L.bf_sorted_set_bytes(n, n_groups, 0)), 256), dtype=torch.uint8, device=device)
+        nbytes = max(int(L.bf_sorted_set_bytes(n, n_groups, 0)), 256)
+        store = SetStores.get(device, slot, nbytes) if slot else torch.empty(nbytes, dtype=torch.uint8, device=device)
         rc = L.bf_overlap_prepare_set(C.c_void_p(words.ctypes.data), _ptr(g), _ptr(s), _ptr(e), n, n_groups,
                                       int(bool(presorted)), _ptr(store), store.numel(), _stream_ptr(device),
                                       C.byref(struct))
@@ -215,7 +242,7 @@ def prepare_set(words, grp, start, end, n_groups, presorted=False, device=None):
     return SortedSet(struct, store, n, n_groups, g, device)
 
 
-def adopt_set(words, n, n_groups, grp=None, device=None):
+def adopt_set(words, n, n_groups, grp=None, device=None, slot=None):
     """An empty prepared set of `n` rows whose `keys` / `ids` the caller fills (e.g. by a broadcast of another
     rank's `SortedSet.keys` / `.ids`) before it is used."""
     import numpy as np
@@ -226,7 +253,8 @@ def adopt_set(words, n, n_groups, grp=None, device=None):
     words = np.ascontiguousarray(words, dtype=np.int64)
     struct = _lib.SortedSetStruct()
     with torch.cuda.device(device):
-        store = torch.empty(max(int(L.bf_sorted_set_bytes(int(n), n_groups, 1)), 256), dtype=torch.uint8, device=device)
+        nbytes = max(int(L.bf_sorted_set_bytes(int(n), n_groups, 1)), 256)
+        store = SetStores.get(device, slot, nbytes) if slot else torch.empty(nbytes, dtype=torch.uint8, device=device)
         rc = L.bf_overlap_adopt_set(C.c_void_p(words.ctypes.data), int(n), n_groups, _ptr(store), store.numel(),
                                     _stream_ptr(device), C.byref(struct))
         _lib.check(rc, "bf_overlap_adopt_set")

@@ -196,6 +196,17 @@ def overlap_range_sharded(grp1, start1, end1, n_own, own_range, grp2, start2, en
     use_cuda = torch.is_tensor(start1) and start1.is_cuda
     dev = start1.device if use_cuda else device
 
+    import os
+    import time
+
+    trace = [] if os.environ.get("BF_PHASE_TIMES") and use_cuda else None
+
+    def mark(name):
+        if trace is not None:
+            torch.cuda.synchronize(dev)
+            trace.append((name, time.perf_counter()))
+
+    mark("begin")
     # 1. one key layout for every set on every rank: local extents, MAX-merged (a few hundred bytes)
     words, presorted1 = engine.measure_extent(grp1, start1, end1, n_groups)
     presorted2 = False
@@ -203,35 +214,46 @@ def overlap_range_sharded(grp1, start1, end1, n_own, own_range, grp2, start2, en
         w2, presorted2 = engine.measure_extent(grp2, start2, end2, n_groups)
         words = np.maximum(words, w2)
         n2 = int(len(start2))
+    mark("extent")
     words = merge_extent_words(words, device=dev, group=group)
+    mark("allreduce")
 
-    # 2. targets: sorted once on `src`, keys + row ids broadcast on a side stream; queries sorted meanwhile
+    # 2. queries first: their sort is the long part (ms of GPU work), and once it is enqueued the host has all
+    #    that time to enqueue the many small kernels of the target side behind it on a side stream.  Targets:
+    #    sorted once on `src`, keys + row ids broadcast on the side stream while the queries sort.
     side = torch.cuda.Stream(device=dev) if use_cuda else None
     main = torch.cuda.current_stream(dev) if use_cuda else None
-    if side is not None:
-        side.wait_stream(main)
+    if side is not None:  # the side stream may start once the inputs exist, not only after the query sort
+        inputs_ready = torch.cuda.Event()
+        inputs_ready.record(main)
+        side.wait_event(inputs_ready)
+    set1 = engine.prepare_set(words, grp1, start1, end1, n_groups, presorted=presorted1, slot="sharded.queries")
+    mark("queries_sorted")
     ctx = torch.cuda.stream(side) if side is not None else _NullContext()
     handles = []
     with ctx:
         if have_targets:
-            set2 = engine.prepare_set(words, grp2, start2, end2, n_groups, presorted=presorted2)
+            set2 = engine.prepare_set(words, grp2, start2, end2, n_groups, presorted=presorted2, slot="sharded.targets")
         else:
-            set2 = engine.adopt_set(words, n2, n_groups)
+            set2 = engine.adopt_set(words, n2, n_groups, slot="sharded.targets")
         if world > 1:
             handles.append(dist.broadcast(set2.keys, src=src, group=group, async_op=True))
             handles.append(dist.broadcast(set2.ids, src=src, group=group, async_op=True))
-    set1 = engine.prepare_set(words, grp1, start1, end1, n_groups, presorted=presorted1)
     for h in handles:
         h.wait()
     if side is not None:
-        main.wait_stream(side)
-        set2.store.record_stream(main)
+        main.wait_stream(side)  # the target store is persistent (SetStores): the streams are ordered here and by
+        #                         `inputs_ready` of the next call, the allocator is not involved
+    mark("targets_ready")
 
     # 3. search + count + emit, only what this shard owns
     sharded_call = world > 1 or own_range is not None
     ev1, ev2, n_pairs, counts = engine.overlap_prepared(
         set1, set2, how=how, own_range=own_range if sharded_call else None, row_offset1=int(row_offset),
         n_own1=int(n_own), halo_ids=halo_ids, want_group_counts=True)
+    mark("count+emit")
+    if trace is not None:
+        print("[phases ms] " + "  ".join(f"{b[0]}={1e3 * (b[1] - a[1]):.2f}" for a, b in zip(trace, trace[1:])), flush=True)
     return ev1, ev2, n_pairs, counts
 
 

@@ -143,13 +143,13 @@ def measure_extent(grp, start, end, n_groups, device=None):
     return w, False
 
 
-def prepare_set(words, grp, start, end, n_groups, presorted=False, device=None):
+def prepare_set(words, grp, start, end, n_groups, presorted=False, device=None, slot=None):
     s, e = _i64(start), _i64(end)
     g = np.zeros(len(s), np.int64) if grp is None else np.asarray(grp, dtype=np.int64)
     return _DoubleSet(np.stack([g, s, e], axis=1) if len(s) else np.zeros((0, 3), np.int64), n_groups)
 
 
-def adopt_set(words, n, n_groups, grp=None, device=None):
+def adopt_set(words, n, n_groups, grp=None, device=None, slot=None):
     return _DoubleSet(np.zeros((int(n), 3), np.int64), n_groups)
 
 
