@@ -934,6 +934,39 @@ def main():
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         sharded_verified = bool(flag.item())
 
+    # cfg4: the same check on a virtual shard -- the first ~5e6 queries of this rank with their halo -- against the
+    # single-GPU engine on all targets (sent to every rank once, after the timed region), and the row total of
+    # the whole job against the independent count kernel
+    if cfg4 and not args.no_verify:
+        full_t = [torch.empty(n2, dtype=dt_, device=dev) for dt_ in (torch.int32, torch.int64, torch.int64)]
+        if rank == 0:
+            for dst_, src_ in zip(full_t, dt):
+                dst_.copy_(src_)
+        if world > 1:
+            for x in full_t:
+                dist.broadcast(x, src=0)
+        gq, sq = dq[0][:n1].cpu().numpy(), dq[1][:n1].cpu().numpy()
+        nv = min(5_000_000, n1 - 1)
+        g_hi, s_hi = int(gq[nv]), int(sq[nv])
+        nv = sharded._first_row_at_or_after(gq, sq, g_hi, s_hi)
+        hv = min(max(sharded._first_row_at_or_after(gq, sq, g_hi, s_hi + lmax), nv), n1)
+        own_v = (own_range[0], own_range[1], g_hi, s_hi)
+        qv = [x[:hv] for x in dq]
+        hid = torch.arange(row_offset + nv, row_offset + hv, device=dev)
+        got = sharded.overlap_range_sharded(*qv, nv, own_v, *full_t, N_GROUPS, how=args.how, row_offset=row_offset,
+                                            halo_ids=hid, n2=n2, device=dev, collective=False)[:2]
+        ok = verify_shard(engine, qv, nv, own_v, hid, row_offset, full_t, args.how, got)
+        del got
+        cnt = engine.count_overlaps(dq[0][:n1], dq[1][:n1], dq[2][:n1], *full_t, N_GROUPS)
+        want_rows = int(cnt.sum().item()) + (int((cnt == 0).sum().item()) if args.how == "left" else 0)
+        del cnt, full_t
+        tot = torch.tensor([want_rows, 1 if ok else 0], device=dev, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        sharded_verified = bool(int(tot[1].item()) == world and int(tot[0].item()) == total_rows)
+        engine.SetStores.release()
+        torch.cuda.empty_cache()
+
     # ---- end to end: pinned host buffers in, host arrays out ----
     e2e = None
     if not args.no_e2e and not cfg4:

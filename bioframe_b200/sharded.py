@@ -178,20 +178,22 @@ def halo_reach(grp2, start2, end2, own_hi, n_groups):
 
 
 def overlap_range_sharded(grp1, start1, end1, n_own, own_range, grp2, start2, end2, n_groups, how="left",
-                          row_offset=0, halo_ids=None, engine=None, group=None, src=0, n2=None, device=None):
+                          row_offset=0, halo_ids=None, engine=None, group=None, src=0, n2=None, device=None,
+                          collective=True):
     """This rank's part of `_overlap_intidxs(df1, df2, how)` in the reference's row order.
 
     grp1/start1/end1: the queries of this rank's (group, start) range `own_range` = (g_lo, start_lo, g_hi,
     start_hi) -- rows [0, n_own), global row numbers row_offset + i -- followed by its halo rows (global row
     numbers `halo_ids`).  grp2/start2/end2: the targets, needed on `src` only (pass None elsewhere, with n2).
     Returns (events1, events2, n_pairs, counts[n_groups, 4]); `assemble_offsets(all ranks' counts)` places the
-    per-group segments of events1/events2 in the whole result."""
+    per-group segments of events1/events2 in the whole result.  collective=False: no communication at all -- the
+    caller holds the targets itself (one process walking over several shards, or a check)."""
     if engine is None:
         from . import engine as engine
     if how not in ("inner", "left"):
         raise ValueError("query-sharded overlap supports how='inner' and how='left' (unpaired targets need a reduction)")
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if (dist.is_initialized() and collective) else 1
+    rank = dist.get_rank(group) if (dist.is_initialized() and collective) else 0
     have_targets = world == 1 or rank == src
     use_cuda = torch.is_tensor(start1) and start1.is_cuda
     dev = start1.device if use_cuda else device
@@ -215,7 +217,8 @@ def overlap_range_sharded(grp1, start1, end1, n_own, own_range, grp2, start2, en
         words = np.maximum(words, w2)
         n2 = int(len(start2))
     mark("extent")
-    words = merge_extent_words(words, device=dev, group=group)
+    if world > 1:
+        words = merge_extent_words(words, device=dev, group=group)
     mark("allreduce")
 
     # 2. queries first: their sort is the long part (ms of GPU work), and once it is enqueued the host has all
