@@ -83,6 +83,8 @@ SIGNATURES = {
     "bf_sort_pairs_workspace_bytes": (_sz, [_i64]),
     "bf_sort_pairs": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _sz, _p]),
     "bf_gather_rows": (C.c_int, [_p, _i32, _p, _i64, _p, _p, _p]),
+    "bf_group_codes_present": (C.c_int, [_p, _i32, _i64, _i32, _p, _p]),
+    "bf_group_codes_apply": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p]),
     "bf_pair_coords": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
     "bf_closest_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "bf_closest_count": (

@@ -118,8 +118,67 @@ class Workspace:
         cls._cache.clear()
 
 
+# ---- group batches: the wide path for key layouts that do not fit 64 bits ------------------------------------
+# Every call lays all groups end to end on one linear axis (csrc/keys.cuh); with very many groups -- on=[...]
+# columns multiply the chromosomes -- times long intervals the (position, length) key can need more than 64
+# bits and the library answers BF_ERR_RANGE (OverflowError here).  Groups never interact, so the call is then
+# repeated over contiguous ranges of groups, halving a range until its layout fits; results of the ranges are
+# stitched in group order, which is the order of the whole call.  Only a SINGLE group whose own coordinates do not
+# fit (spread over more than ~2^63) still raises.
+def _rows_of_groups(g, lo, hi):
+    return torch.nonzero((g >= lo) & (g < hi)).flatten()
+
+
+def _global_rows(ev, rows):
+    """row numbers inside a batch -> row numbers of the whole set (-1 stays -1)"""
+    if rows.numel() == 0:
+        return ev
+    return torch.where(ev >= 0, rows[ev.clamp(min=0)], ev)
+
+
+def _over_group_ranges(run, lo, hi):
+    """[run(a, b) for consecutive group ranges [a, b) covering [lo, hi)], ranges halved on OverflowError"""
+    try:
+        return [run(lo, hi)]
+    except OverflowError:
+        if hi - lo <= 1:
+            raise
+        mid = (lo + hi) // 2
+        return _over_group_ranges(run, lo, mid) + _over_group_ranges(run, mid, hi)
+
+
 def overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how="inner", closed=False, device=None,
                     row_offset1=0, row_offset2=0):
+    """`_overlap_intidxs` for all groups (see _overlap_intidxs_once); falls back to group batches when the key
+    layout of all groups together does not fit."""
+    try:
+        return _overlap_intidxs_once(grp1, start1, end1, grp2, start2, end2, n_groups, how, closed, device,
+                                     row_offset1, row_offset2)
+    except OverflowError:
+        if n_groups <= 1:
+            raise
+    device = torch.device(device if device is not None else "cuda")
+    s1, e1 = _as(start1, torch.int64, device), _as(end1, torch.int64, device)
+    s2, e2 = _as(start2, torch.int64, device), _as(end2, torch.int64, device)
+    g1, g2 = _as(grp1, torch.int32, device), _as(grp2, torch.int32, device)
+
+    def run(lo, hi):
+        r1, r2 = _rows_of_groups(g1, lo, hi), _rows_of_groups(g2, lo, hi)
+        a, b, n_pairs = _overlap_intidxs_once(g1[r1] - lo, s1[r1], e1[r1], g2[r2] - lo, s2[r2], e2[r2], hi - lo, how,
+                                              closed, device, 0, 0)
+        a, b = _global_rows(a, r1), _global_rows(b, r2)
+        if row_offset1:
+            a = torch.where(a >= 0, a + int(row_offset1), a)
+        if row_offset2:
+            b = torch.where(b >= 0, b + int(row_offset2), b)
+        return a, b, n_pairs
+
+    parts = _over_group_ranges(run, 0, int(n_groups))
+    return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts]), sum(p[2] for p in parts)
+
+
+def _overlap_intidxs_once(grp1, start1, end1, grp2, start2, end2, n_groups, how="inner", closed=False, device=None,
+                          row_offset1=0, row_offset2=0):
     """All groups of `_overlap_intidxs` in one pass. Returns (events1, events2, n_pairs).
     row_offset1/2 are added to the reported row numbers (query-sharded callers)."""
     _require_cuda()
@@ -324,6 +383,43 @@ def sort_pairs(ev1, ev2, max1, max2):
 
 
 def cluster(grp, start, end, n_groups, min_dist=0, want_ids=True, want_table=True, want_row_spans=False, device=None):
+    """merge_intervals over all groups (see _cluster_once); group batches when the key layout does not fit."""
+    try:
+        return _cluster_once(grp, start, end, n_groups, min_dist, want_ids, want_table, want_row_spans, device)
+    except OverflowError:
+        if n_groups <= 1:
+            raise
+    device = torch.device(device if device is not None else "cuda")
+    s, e, g = _as(start, torch.int64, device), _as(end, torch.int64, device), _as(grp, torch.int32, device)
+
+    def run(lo, hi):
+        rows = _rows_of_groups(g, lo, hi)
+        return rows, lo, _cluster_once(g[rows] - lo, s[rows], e[rows], hi - lo, min_dist, want_ids, want_table,
+                                       want_row_spans, device)
+
+    parts = _over_group_ranges(run, 0, int(n_groups))
+    n = int(s.numel())
+    out = dict(ids=None, n_clusters=sum(p[2]["n_clusters"] for p in parts), cgrp=None, cstart=None, cend=None,
+               ccount=None, row_start=None, row_end=None)
+    for name in ("ids", "row_start", "row_end"):
+        if parts[0][2][name] is not None:
+            out[name] = torch.empty(n, dtype=torch.int64, device=device)
+    base = 0
+    for rows, lo, res in parts:  # cluster ids count on from range to range (ops.py:653-655)
+        if out["ids"] is not None:
+            out["ids"][rows] = res["ids"] + base
+        for name in ("row_start", "row_end"):
+            if out[name] is not None:
+                out[name][rows] = res[name]
+        base += res["n_clusters"]
+    if want_table:
+        out["cgrp"] = torch.cat([res["cgrp"] + lo for _, lo, res in parts])
+        for name in ("cstart", "cend", "ccount"):
+            out[name] = torch.cat([res[name] for _, _, res in parts])
+    return out
+
+
+def _cluster_once(grp, start, end, n_groups, min_dist=0, want_ids=True, want_table=True, want_row_spans=False, device=None):
     """merge_intervals over all groups (group code order = sorted key order).
 
     Returns dict(ids=int64[n] | None, n_clusters, cgrp=int32[C], cstart, cend,
@@ -363,7 +459,52 @@ def cluster(grp, start, end, n_groups, min_dist=0, want_ids=True, want_table=Tru
     return out
 
 
+def _per_query_batched(once, grp1, start1, end1, grp2, start2, end2, n_groups, device, **kw):
+    """a per-query result (coverage, counts) over group batches: out[rows of the batch] = result of the batch"""
+    device = torch.device(device if device is not None else "cuda")
+    s1, e1 = _as(start1, torch.int64, device), _as(end1, torch.int64, device)
+    s2, e2 = _as(start2, torch.int64, device), _as(end2, torch.int64, device)
+    g1, g2 = _as(grp1, torch.int32, device), _as(grp2, torch.int32, device)
+    out = torch.zeros(int(s1.numel()), dtype=torch.int64, device=device)
+
+    def run(lo, hi):
+        r1, r2 = _rows_of_groups(g1, lo, hi), _rows_of_groups(g2, lo, hi)
+        if r1.numel():
+            out[r1] = once(g1[r1] - lo, s1[r1], e1[r1], g2[r2] - lo, s2[r2], e2[r2], hi - lo, device=device, **kw)
+        return None
+
+    _over_group_ranges(run, 0, int(n_groups))
+    return out
+
+
 def coverage(grp1, start1, end1, grp2, start2, end2, n_groups, device=None):
+    """Covered base pairs of every row of set 1 by the union of set 2 -> int64[n1] (device).
+    The kernel does arithmetic on the ends themselves, so ends of INT64_MAX (what `complement` / `subtract` /
+    `trim` put at the end of a chromosome, ops.py:1309, 1499, 1604) do not fit its key layout as they are: such
+    calls are repeated with every coordinate clipped to the window in which both sets have intervals --
+    outside it nothing of set 1 meets anything of set 2, so no covered base pair is lost -- and, if the groups
+    together still need more than 64 key bits, over group batches."""
+    try:
+        return _coverage_once(grp1, start1, end1, grp2, start2, end2, n_groups, device)
+    except OverflowError:
+        pass
+    device = torch.device(device if device is not None else "cuda")
+    s1, e1 = _as(start1, torch.int64, device), _as(end1, torch.int64, device)
+    s2, e2 = _as(start2, torch.int64, device), _as(end2, torch.int64, device)
+    if s1.numel() and s2.numel():
+        lo = max(int(s1.min().item()), int(s2.min().item()))
+        hi = min(int(e1.max().item()), int(e2.max().item()))
+        hi = max(hi, lo)
+        s1, e1, s2, e2 = (x.clamp(min=lo, max=hi) for x in (s1, e1, s2, e2))
+    try:
+        return _coverage_once(grp1, s1, e1, grp2, s2, e2, n_groups, device)
+    except OverflowError:
+        if n_groups <= 1:
+            raise
+    return _per_query_batched(_coverage_once, grp1, s1, e1, grp2, s2, e2, n_groups, device)
+
+
+def _coverage_once(grp1, start1, end1, grp2, start2, end2, n_groups, device=None):
     """Covered base pairs of every row of set 1 by the union of set 2 -> int64[n1] (device)."""
     _require_cuda()
     L = _lib.lib()
@@ -383,6 +524,17 @@ def coverage(grp1, start1, end1, grp2, start2, end2, n_groups, device=None):
 
 
 def count_overlaps(grp1, start1, end1, grp2, start2, end2, n_groups, closed=False, device=None):
+    """Number of set-2 intervals overlapping every row of set 1 -> int64[n1] (device, input row order);
+    group batches when the key layout of all groups together does not fit."""
+    try:
+        return _count_overlaps_once(grp1, start1, end1, grp2, start2, end2, n_groups, closed, device)
+    except OverflowError:
+        if n_groups <= 1:
+            raise
+    return _per_query_batched(_count_overlaps_once, grp1, start1, end1, grp2, start2, end2, n_groups, device, closed=closed)
+
+
+def _count_overlaps_once(grp1, start1, end1, grp2, start2, end2, n_groups, closed=False, device=None):
     """Number of set-2 intervals overlapping every row of set 1 -> int64[n1] (device, input row order)."""
     _require_cuda()
     L = _lib.lib()
@@ -447,6 +599,43 @@ def gather_rows(column, idx, want_valid=False, device=None):
     return (out, valid) if want_valid else out
 
 
+def codes_present(codes, n_categories, device=None):
+    """Which dictionary codes of a categorical key column occur (bf_group_codes_present).
+    codes: int8 / int16 numpy array or CUDA tensor (-1 = null).  -> (device codes, bool numpy [n_categories + 1]:
+    slot 0 = a null occurs, slot c + 1 = category c occurs)."""
+    import numpy as np
+
+    _require_cuda()
+    device = torch.device(device if device is not None else "cuda")
+    t = codes if isinstance(codes, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(codes))
+    t = t.to(device=device, non_blocking=True).contiguous()
+    with torch.cuda.device(device):
+        present = torch.empty(int(n_categories) + 2, dtype=torch.int32, device=device)
+        rc = _lib.lib().bf_group_codes_present(_ptr(t), t.element_size(), int(t.numel()), int(n_categories), _ptr(present),
+                                               _stream_ptr(device))
+        _lib.check(rc, "bf_group_codes_present")
+    flags = present.cpu().numpy().astype(bool)
+    if flags[-1]:
+        raise ValueError("categorical codes outside [-1, n_categories)")
+    return t, flags[:-1]
+
+
+def codes_apply(codes_dev, lut, device=None):
+    """group rank per row = lut[code + 1] (bf_group_codes_apply).  codes_dev: what `codes_present` returned;
+    lut: int32 numpy [n_categories + 1].  -> int32 CUDA tensor."""
+    import numpy as np
+
+    _require_cuda()
+    device = codes_dev.device
+    lut_t = torch.from_numpy(np.ascontiguousarray(lut, dtype=np.int32)).to(device)
+    with torch.cuda.device(device):
+        out = torch.empty(int(codes_dev.numel()), dtype=torch.int32, device=device)
+        rc = _lib.lib().bf_group_codes_apply(_ptr(codes_dev), codes_dev.element_size(), int(codes_dev.numel()), _ptr(lut_t),
+                                             int(lut_t.numel()) - 1, _ptr(out), _stream_ptr(device))
+        _lib.check(rc, "bf_group_codes_apply")
+    return out
+
+
 def pair_coords(ev1, ev2, start1, end1, start2, end2, want_overlap=True, want_distance=False, device=None):
     """Clipped coordinates / distances of reported pairs (return_overlap, return_distance of the frame ops).
     -> (overlap_start, overlap_end, distance) int64 device tensors (None where not wanted); rows with a -1
@@ -469,6 +658,31 @@ def pair_coords(ev1, ev2, start1, end1, start2, end2, want_overlap=True, want_di
 
 
 def subtract(grp1, start1, end1, grp2, start2, end2, n_groups, want_sub_index=True, device=None):
+    """ops.subtract pieces for all groups (see _subtract_once); group batches when the key layout of all groups
+    together does not fit (the pieces of the batches are merged back into ascending row order)."""
+    try:
+        return _subtract_once(grp1, start1, end1, grp2, start2, end2, n_groups, want_sub_index, device)
+    except OverflowError:
+        if n_groups <= 1:
+            raise
+    device = torch.device(device if device is not None else "cuda")
+    s1, e1, g1 = _as(start1, torch.int64, device), _as(end1, torch.int64, device), _as(grp1, torch.int32, device)
+    s2, e2, g2 = _as(start2, torch.int64, device), _as(end2, torch.int64, device), _as(grp2, torch.int32, device)
+
+    def run(lo, hi):
+        r1, r2 = _rows_of_groups(g1, lo, hi), _rows_of_groups(g2, lo, hi)
+        row, ps, pe, sub = _subtract_once(g1[r1] - lo, s1[r1], e1[r1], g2[r2] - lo, s2[r2], e2[r2], hi - lo,
+                                          want_sub_index, device)
+        return _global_rows(row, r1), ps, pe, sub
+
+    parts = _over_group_ranges(run, 0, int(n_groups))
+    row = torch.cat([p[0] for p in parts])
+    order = torch.sort(row, stable=True).indices  # the pieces of a row stay left to right
+    cat = lambda i: torch.cat([p[i] for p in parts])[order]  # noqa: E731
+    return row[order], cat(1), cat(2), (cat(3) if want_sub_index else None)
+
+
+def _subtract_once(grp1, start1, end1, grp2, start2, end2, n_groups, want_sub_index=True, device=None):
     """Pieces of every row of set 1 that the union of set 2 does not cover (ops.subtract, ops.py:1243-1330).
     -> (row int64[R], start int64[R], end int64[R], sub_index int64[R] or None) on device: rows of set 1 in
     ascending order, the pieces of a row left to right."""
@@ -529,6 +743,36 @@ def complement(region, start, end, bounds_lo, bounds_hi, device=None):
 
 def closest_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, k=1, ignore_overlaps=False,
                     ignore_upstream=False, ignore_downstream=False, along=None, self_closest=False, device=None):
+    """`_closest_intidxs` for all groups (see _closest_intidxs_once); group batches when the key layout of all
+    groups together does not fit."""
+    kw = dict(k=k, ignore_overlaps=ignore_overlaps, ignore_upstream=ignore_upstream, ignore_downstream=ignore_downstream,
+              self_closest=self_closest)
+    try:
+        return _closest_intidxs_once(grp1, start1, end1, grp2, start2, end2, n_groups, along=along, device=device, **kw)
+    except OverflowError:
+        if n_groups <= 1:
+            raise
+    device = torch.device(device if device is not None else "cuda")
+    s1, e1, g1 = _as(start1, torch.int64, device), _as(end1, torch.int64, device), _as(grp1, torch.int32, device)
+    if self_closest:
+        s2, e2, g2 = s1, e1, g1
+    else:
+        s2, e2, g2 = _as(start2, torch.int64, device), _as(end2, torch.int64, device), _as(grp2, torch.int32, device)
+    al = _as(along, torch.uint8, device) if along is not None else None
+
+    def run(lo, hi):
+        r1 = _rows_of_groups(g1, lo, hi)
+        r2 = r1 if self_closest else _rows_of_groups(g2, lo, hi)
+        a, b, n_matched = _closest_intidxs_once(g1[r1] - lo, s1[r1], e1[r1], g2[r2] - lo, s2[r2], e2[r2], hi - lo,
+                                                along=al[r1] if al is not None else None, device=device, **kw)
+        return _global_rows(a, r1), _global_rows(b, r2), n_matched
+
+    parts = _over_group_ranges(run, 0, int(n_groups))
+    return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts]), sum(p[2] for p in parts)
+
+
+def _closest_intidxs_once(grp1, start1, end1, grp2, start2, end2, n_groups, k=1, ignore_overlaps=False,
+                          ignore_upstream=False, ignore_downstream=False, along=None, self_closest=False, device=None):
     """All groups of `_closest_intidxs` (ops.py:919-1040) in one pass.
     `self_closest`: set 2 is set 1 (grp2/start2/end2 are ignored).  `along`: bool per
     query, False = "-" strand.  Returns (events1, events2, n_matched_rows) on device."""

@@ -213,8 +213,11 @@ def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _gro
         # keep_order: the pairs are produced in (row of df1, row of df2) order directly, queries visited in row
         # order (bf_overlap_ordered_*).  A row with a huge partner list is sorted by one thread there: such
         # inputs take the general path below (all pairs, then a radix sort of the pair list).
-        ev1, ev2, biggest = _engine.overlap_ordered(g1, s1, e1, g2, s2, e2, n_groups)
-        if biggest > _ORDERED_MAX_PARTNERS:
+        try:
+            ev1, ev2, biggest = _engine.overlap_ordered(g1, s1, e1, g2, s2, e2, n_groups)
+            if biggest > _ORDERED_MAX_PARTNERS:
+                ev1 = None
+        except OverflowError:  # the key layout of all groups together does not fit: the general path batches them
             ev1 = None
     if ev1 is None:
         # any other string joins like 'inner' in the reference (its `how in {...}` tests all fail, ops.py:229-234,

@@ -184,6 +184,18 @@ int bf_pair_coords(const int64_t* events1, const int64_t* events2, int64_t n_row
 int bf_gather_rows(const void* src, int32_t itemsize, const int64_t* row_idx, int64_t n_rows, void* out,
                    uint8_t* valid_out, void* stream);
 
+/* ---- group encoding: replaces the hash groupby that finds the (chromosome) groups of a frame --
+ * df.groupby(by, observed=True).indices / .groups (ops.py:287-289, 631, 772, 983-985) -- for a categorical key
+ * column, whose dictionary codes (int8 / int16 per row, -1 = null) go to the device as they are.
+ * bf_group_codes_present: present_out (device int32[n_categories + 2]) gets 1 in slot 0 if a null occurs, in slot
+ * c + 1 if category c occurs (the observed keys), in the last slot if any code lies outside [-1, n_categories).
+ * bf_group_codes_apply: grp_out[i] = lut[codes[i] + 1] (lut: device int32[n_categories + 1], slot 0 = the rank of
+ * null rows), i.e. the group rank every other entry point of this header takes. */
+int bf_group_codes_present(const void* codes, int32_t itemsize, int64_t n, int32_t n_categories, int32_t* present_out,
+                           void* stream);
+int bf_group_codes_apply(const void* codes, int32_t itemsize, int64_t n, const int32_t* lut, int32_t n_categories,
+                         int32_t* grp_out, void* stream);
+
 /* ---- closest: replaces ops._closest_intidxs (ops.py:919-1040), i.e. the
  * per-group loop around arrops.closest_intervals (arrops.py:601-754) and
  * arrops._closest_intervals_nooverlap (arrops.py:506-598), plus the

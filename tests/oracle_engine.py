@@ -188,3 +188,14 @@ def overlap_prepared(set1, set2, how="inner", closed=False, own_range=None, row_
         out1 = np.where(ev1 >= n_own, halo[np.maximum(ev1 - n_own, 0)], out1)
     res = (torch.from_numpy(out1), torch.from_numpy(np.where(ev2 >= 0, ev2 + row_offset2, -1)), int(paired[keep].sum()))
     return (*res, counts) if want_group_counts else res
+
+
+def codes_present(codes, n_categories, device=None):
+    codes = np.asarray(codes)
+    flags = np.zeros(int(n_categories) + 1, dtype=bool)
+    flags[np.unique(codes).astype(np.int64) + 1] = True
+    return codes, flags
+
+
+def codes_apply(codes_dev, lut, device=None):
+    return np.asarray(lut, dtype=np.int32)[np.asarray(codes_dev).astype(np.int64) + 1]

@@ -138,3 +138,67 @@ def test_presorted_inputs_skip_the_radix_passes(which):
         assert np.array_equal(res["ids"].cpu().numpy(), ids) and np.array_equal(res["cend"].cpu().numpy(), ce)
     cov = engine.coverage(g1, s1, e1, g2, s2, e2, 6).cpu().numpy()
     assert np.array_equal(cov, oo.coverage_coded(g1, s1, e1, g2, s2, e2, 6))
+
+
+def test_many_groups_times_long_intervals_take_group_batches():
+    """~1000 (chrom, on) groups of hg38-sized spans need ~38 position bits, one chromosome-long interval
+    28 length bits more: no single 64-bit key layout holds all groups, so the engine walks over group batches --
+    same rows as the oracle, for every op."""
+    from bioframe_b200 import engine
+    from oracle import ops_oracle as oo
+
+    rng = np.random.default_rng(5)
+    nb, span = 1000, 250_000_000
+    n1, n2 = 6000, 5000
+    g1, g2 = rng.integers(0, nb, n1).astype(np.int32), rng.integers(0, nb, n2).astype(np.int32)
+    s1, s2 = rng.integers(0, span, n1), rng.integers(0, span, n2)
+    e1 = s1 + rng.integers(0, 3_000_000, n1)
+    e2 = s2 + rng.integers(0, 3_000_000, n2)
+    e1[::50] = s1[::50] + span  # chromosome-long intervals: 28 length bits
+    e2[::70] = s2[::70] + span
+    d = [torch.from_numpy(x).cuda() for x in (g1, s1, e1, g2, s2, e2)]
+    for how in ("inner", "outer"):
+        a, b, _ = engine.overlap_intidxs(*d, nb, how=how)
+        w1, w2 = oo.overlap_intidxs_coded(g1, s1, e1, g2, s2, e2, nb, how=how)
+        assert np.array_equal(a.cpu().numpy(), w1) and np.array_equal(b.cpu().numpy(), w2)
+    cnt = engine.count_overlaps(*d, nb).cpu().numpy()
+    assert np.array_equal(cnt, np.bincount(w1[(w1 >= 0) & (w2 >= 0)], minlength=n1))
+    assert np.array_equal(engine.coverage(*d, nb).cpu().numpy(), oo.coverage_coded(g1, s1, e1, g2, s2, e2, nb))
+    res = engine.cluster(d[0], d[1], d[2], nb, min_dist=0)
+    ids, cs, ce, cn = oo.cluster_coded(g1, s1, e1, nb, 0)
+    assert np.array_equal(res["ids"].cpu().numpy(), ids) and np.array_equal(res["cstart"].cpu().numpy(), cs)
+    assert np.array_equal(res["cend"].cpu().numpy(), ce) and np.array_equal(res["ccount"].cpu().numpy(), cn)
+    row, ps, pe, sub = engine.subtract(*d, nb)
+    wr, wps, wpe, wsub = oo.subtract_coded(g1, s1, e1, g2, s2, e2, nb)
+    assert np.array_equal(row.cpu().numpy(), wr) and np.array_equal(ps.cpu().numpy(), wps)
+    assert np.array_equal(pe.cpu().numpy(), wpe) and np.array_equal(sub.cpu().numpy(), wsub)
+
+
+def test_coverage_of_complement_output():
+    """`coverage(df1, complement(df2))` -- the complement ends every chromosome at INT64_MAX
+    (ops.py:1604), which the coverage key layout cannot hold as it is."""
+    import pandas as pd
+
+    import bioframe_b200 as bf
+    from oracle import ops_oracle as oo
+
+    rng = np.random.default_rng(9)
+    chroms = np.array(["chr1", "chr2", "chr3"], dtype=object)
+
+    def frame(n):
+        s = rng.integers(0, 100_000, n)
+        return pd.DataFrame({"chrom": rng.choice(chroms, n), "start": s, "end": s + rng.integers(1, 3000, n)})
+
+    df1, df2 = frame(4000), frame(500)
+    gaps = bf.complement(df2)
+    assert int(gaps["end"].max()) == np.iinfo(np.int64).max
+    got = bf.coverage(df1, gaps)
+    code = {c: i for i, c in enumerate(chroms)}
+    g1 = df1["chrom"].map(code).to_numpy().astype(np.int32)
+    g2 = gaps["chrom"].map(code).to_numpy().astype(np.int32)
+    want = oo.coverage_coded(g1, df1["start"].to_numpy(), df1["end"].to_numpy(), g2, gaps["start"].to_numpy(),
+                             gaps["end"].to_numpy(), 3)
+    assert np.array_equal(got["coverage"].to_numpy(), want)
+    # and the two coverages of a query add up to its length where the view covers it
+    both = bf.coverage(df1, df2)["coverage"].to_numpy() + got["coverage"].to_numpy()
+    assert np.array_equal(both, (df1["end"] - df1["start"]).to_numpy())
