@@ -553,9 +553,11 @@ def _count_overlaps_once(grp1, start1, end1, grp2, start2, end2, n_groups, close
     return counts
 
 
-def overlap_ordered(grp1, start1, end1, grp2, start2, end2, n_groups, device=None):
+def overlap_ordered(grp1, start1, end1, grp2, start2, end2, n_groups, device=None, max_partners=None):
     """overlap(how='left') with the rows already in (row of set 1, row of set 2) order, -1 = no partner
-    (bf_overlap_ordered_*).  -> (events1, events2, largest partner count of one row)."""
+    (bf_overlap_ordered_*).  -> (events1, events2, largest partner count of one row).
+    max_partners: give up right after the count phase -- before any output is allocated or written -- when one
+    row has more partners than that (the emit orders a row's partners inside one block); -> (None, None, largest)."""
     _require_cuda()
     L = _lib.lib()
     device = torch.device(device if device is not None else "cuda")
@@ -572,6 +574,8 @@ def overlap_ordered(grp1, start1, end1, grp2, start2, end2, n_groups, device=Non
         rc = L.bf_overlap_ordered_count(_ptr(g1), _ptr(s1), _ptr(e1), n1, _ptr(g2), _ptr(s2), _ptr(e2), n2, n_groups,
                                         _ptr(ws), ws.numel(), C.byref(plan), stream, C.byref(n_rows), C.byref(biggest))
         _lib.check(rc, "bf_overlap_ordered_count")
+        if max_partners is not None and biggest.value > int(max_partners):
+            return None, None, biggest.value
         ev1 = torch.empty(n_rows.value, dtype=torch.int64, device=device)
         ev2 = torch.empty(n_rows.value, dtype=torch.int64, device=device)
         rc = L.bf_overlap_ordered_emit(C.byref(plan), _ptr(ws), _ptr(ev1), _ptr(ev2), stream)

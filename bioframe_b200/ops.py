@@ -133,10 +133,43 @@ def _group_keys_shared_na(df, by):
     return codes, keys
 
 
+_DEVICE_ENCODE_MIN_ROWS = 1 << 20
+
+
+def _categorical_keys_on_device(df1, by1, df2, by2):
+    """Group encoding of two frames keyed by ONE categorical column each (the usual chromosome column) without
+    a pass over the rows on the host: the dictionary codes (int8 / int16) go to the device as they are,
+    bf_group_codes_present reports the observed categories -- the keys `groupby(observed=True)` of the reference
+    would find (ops.py:287-288), nulls as the np.nan key -- and the caller maps codes to group ranks there too.
+    -> ((device codes, keys, lookup slots) per frame) or None when the frames are keyed otherwise / are small."""
+    if len(by1) != 1 or len(by2) != 1 or not hasattr(_engine, "codes_present"):
+        return None
+    if max(len(df1), len(df2)) < _DEVICE_ENCODE_MIN_ROWS or min(len(df1), len(df2)) == 0:
+        return None
+    out = []
+    for df, col in ((df1, by1[0]), (df2, by2[0])):
+        dtype = df[col].dtype
+        if not isinstance(dtype, pd.CategoricalDtype):
+            return None
+        raw = df[col].cat.codes.to_numpy()
+        if raw.dtype.itemsize > 2:
+            return None
+        dev, present = _engine.codes_present(raw, len(dtype.categories))
+        slots = np.flatnonzero(present[1:]) + 1  # observed categories, in category order like the sorted groupby
+        keys = [dtype.categories[i - 1] for i in slots]
+        if present[0]:  # nulls: one more key, after the others (_group_keys_shared_na)
+            keys.append(np.nan)
+            slots = np.append(slots, 0)
+        out.append((dev, keys, slots))
+    return out
+
+
 def _int64_coords(df, col):
     """Coordinate column as int64 numpy; NA (nullable dtypes) -> 0 (such rows
     never reach a kernel as pairable: they sit in their own NA group)."""
     values = df[col]
+    if isinstance(values.dtype, np.dtype) and values.dtype.kind in "iu":
+        return np.asarray(values, dtype=np.int64)  # a plain integer column cannot hold a null
     if values.isna().any():
         values = values.fillna(0)
     return np.asarray(values, dtype=np.int64)
@@ -174,8 +207,12 @@ def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _gro
         by1 = by1 + list(on)
         by2 = by2 + list(on)
 
-    codes1, keys1 = _group_keys_shared_na(df1, by1)
-    codes2, keys2 = _group_keys_shared_na(df2, by2)
+    fast = _categorical_keys_on_device(df1, by1, df2, by2)
+    if fast is not None:
+        (dev1, keys1, slots1), (dev2, keys2, slots2) = fast
+    else:
+        codes1, keys1 = _group_keys_shared_na(df1, by1)
+        codes2, keys2 = _group_keys_shared_na(df2, by2)
     # dropna=False in the reference (ops.py:287-288): a null in an `on` column is a key value like any other,
     # shared by both frames; the groups are visited in the order of the union set (ops.py:289, 301)
     order = list(set.union(set(keys1), set(keys2))) if _group_order is None else [
@@ -199,8 +236,17 @@ def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _gro
         table = np.array([rank[k] for k in keys], dtype=np.int32)
         return table[codes]
 
-    g1 = ranks_of(codes1, keys1, rank1) if len(df1) else np.empty(0, np.int32)
-    g2 = ranks_of(codes2, keys2, rank2) if len(df2) else np.empty(0, np.int32)
+    if fast is not None:  # dictionary codes -> group ranks on the device (bf_group_codes_apply)
+        def lut_of(keys, slots, rank, n_slots):
+            lut = np.full(n_slots, -1, dtype=np.int32)
+            lut[slots] = [rank[k] for k in keys]
+            return lut
+
+        g1 = _engine.codes_apply(dev1, lut_of(keys1, slots1, rank1, len(df1[by1[0]].cat.categories) + 1))
+        g2 = _engine.codes_apply(dev2, lut_of(keys2, slots2, rank2, len(df2[by2[0]].cat.categories) + 1))
+    else:
+        g1 = ranks_of(codes1, keys1, rank1) if len(df1) else np.empty(0, np.int32)
+        g2 = ranks_of(codes2, keys2, rank2) if len(df2) else np.empty(0, np.int32)
     s1, e1, s2, e2 = _int64_coords(df1, sk1), _int64_coords(df1, ek1), _int64_coords(df2, sk2), _int64_coords(df2, ek2)
     t0 = _tick("encode_groups", t0)
     if _coords or _PROFILE is not None:
@@ -214,9 +260,8 @@ def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _gro
         # order (bf_overlap_ordered_*).  A row with a huge partner list is sorted by one thread there: such
         # inputs take the general path below (all pairs, then a radix sort of the pair list).
         try:
-            ev1, ev2, biggest = _engine.overlap_ordered(g1, s1, e1, g2, s2, e2, n_groups)
-            if biggest > _ORDERED_MAX_PARTNERS:
-                ev1 = None
+            ev1, ev2, _biggest = _engine.overlap_ordered(g1, s1, e1, g2, s2, e2, n_groups,
+                                                         max_partners=_ORDERED_MAX_PARTNERS)
         except OverflowError:  # the key layout of all groups together does not fit: the general path batches them
             ev1 = None
     if ev1 is None:

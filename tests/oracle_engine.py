@@ -98,10 +98,12 @@ def complement(region, start, end, bounds_lo, bounds_hi, device=None):
     return oc.astype(np.int32), os_, oe
 
 
-def overlap_ordered(grp1, start1, end1, grp2, start2, end2, n_groups, device=None):
+def overlap_ordered(grp1, start1, end1, grp2, start2, end2, n_groups, device=None, max_partners=None):
     ev1, ev2, _ = overlap_intidxs(grp1, start1, end1, grp2, start2, end2, n_groups, how="left")
     ev1, ev2 = sort_pairs(ev1, ev2, len(start1), len(start2))
     biggest = int(np.bincount(ev1[ev2 >= 0], minlength=1).max()) if len(ev1) else 0
+    if max_partners is not None and biggest > max_partners:
+        return None, None, biggest
     return ev1, ev2, biggest
 
 

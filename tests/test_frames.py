@@ -85,6 +85,7 @@ def device_assembly(monkeypatch):
     import bioframe_b200.ops as ops
 
     monkeypatch.setattr(ops, "_DEVICE_GATHER_MIN_ROWS", 0)
+    monkeypatch.setattr(ops, "_DEVICE_ENCODE_MIN_ROWS", 0)  # and the categorical keys encoded on the device
 
 
 @pytest.mark.parametrize("name", GATHER_CASES)
