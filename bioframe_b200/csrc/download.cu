@@ -8,6 +8,7 @@
 //               event;  host: wait for the previous chunk's event, widen it into the destination
 //   two device and two pinned staging chunks: the bus carries chunk k + 1 while the host widens chunk k.
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <vector>
 #if defined(__x86_64__)
@@ -96,11 +97,17 @@ struct WidenPool {
   void work(int k) {
     i64 seen = 0;
     for (;;) {
-      while (posted.load(std::memory_order_acquire) == seen) {
+      // a short spin (the next chunk usually is a few microseconds away), then yield the core: while the
+      // PCIe copy is the bottleneck the workers must not fight the copy / driver threads for cores
+      for (unsigned spins = 0; posted.load(std::memory_order_acquire) == seen; ++spins) {
         if (stop.load(std::memory_order_acquire)) return;
+        if (spins < 2000) {
 #if defined(__x86_64__)
-        _mm_pause();
+          _mm_pause();
 #endif
+        } else {
+          std::this_thread::sleep_for(std::chrono::microseconds(50));
+        }
       }
       ++seen;
       slice(k);
@@ -115,10 +122,14 @@ struct WidenPool {
     const i64 target = finished.load(std::memory_order_relaxed) + (i64)threads.size();
     posted.fetch_add(1, std::memory_order_release);
     slice(0);
-    while (finished.load(std::memory_order_acquire) != target) {
+    for (unsigned spins = 0; finished.load(std::memory_order_acquire) != target; ++spins) {
+      if (spins < 20000) {
 #if defined(__x86_64__)
-      _mm_pause();
+        _mm_pause();
 #endif
+      } else {
+        std::this_thread::yield();
+      }
     }
   }
 };
@@ -150,7 +161,14 @@ static int download_rows_impl(const i64* dev_src, i64 n, i64* host_dst, void* de
   i32* hstage[2] = {reinterpret_cast<i32*>(pinned), reinterpret_cast<i32*>(pinned) + chunk};
   cudaEvent_t ev[2];
   BF_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-  BF_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  {
+    const cudaError_t e = cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+    if (e != cudaSuccess) {  // do not leave the first event behind
+      cudaEventDestroy(ev[0]);
+      set_error("bf_download_rows: cudaEventCreate: %s", cudaGetErrorString(e));
+      return BF_ERR_CUDA;
+    }
+  }
   int rc = BF_OK;
   auto fail = [&](cudaError_t e, const char* what) {
     if (e != cudaSuccess && rc == BF_OK) {

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(SC_THREADS)
             // plain loads see that nothing is left to do (no atomics on the hot addresses)
             u32 other = *reinterpret_cast<volatile u32*>(&table[s].check);
             if (other == 0) other = atomicCAS(&table[s].check, 0u, h2);
-            if (other != 0 && other != h2) atomicMin(reinterpret_cast<unsigned long long*>(hdr + 2), (unsigned long long)(ln + 1));
+            if (other != 0 && other != h2) continue;  // same 64-bit hash, another name: that one owns the slot, probe on
             if (*reinterpret_cast<volatile u64*>(&table[s].first) > (u64)name0)
               atomicMin(reinterpret_cast<unsigned long long*>(&table[s].first), (unsigned long long)name0);
             if (*reinterpret_cast<volatile u32*>(&table[s].len) != len) table[s].len = len;
@@ -227,6 +227,27 @@ __global__ void __launch_bounds__(SC_THREADS)
     if (ln < n_lines) loc[ln] = (u32)run;
     run += (keep >> j) & 1u;
   }
+}
+
+// pass 4: the names, byte for byte.  A slot is identified by a 64-bit + 32-bit fingerprint of the name; two
+// different names with the same 96 bits would silently become one chromosome.  Every line compares its name with
+// the first occurrence recorded in its slot (a handful of bytes per line, the same cache lines the parse
+// just read); a mismatch is reported as what it is, a fingerprint collision, with the line.
+__global__ void __launch_bounds__(256)
+    bed_verify_names_kernel(const u8* __restrict__ text, const i64* __restrict__ line_start, i64 n_lines,
+                            const BedSlot* __restrict__ table, const u32* __restrict__ t_slot, i64* __restrict__ hdr) {
+  const i64 ln = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ln >= n_lines) return;
+  const u32 slot = t_slot[ln];
+  if (slot == 0xffffffffu) return;
+  const u64 first = table[slot].first;
+  const u32 len = table[slot].len;
+  const i64 p = line_start[ln];
+  if ((u64)p == first) return;
+  bool same = true;
+  for (u32 i = 0; i < len && same; ++i) same = text[p + i] == text[first + i];
+  same = same && text[p + len] == '\t';
+  if (!same) atomicMin(reinterpret_cast<unsigned long long*>(hdr + 3), (unsigned long long)(ln + 1));
 }
 
 __global__ void bed_table_init_kernel(BedSlot* table) {
@@ -331,7 +352,7 @@ int bf_bed_parse(const uint8_t* text, int64_t n_bytes, int64_t n_lines, void* ws
   const i64 tiles = bed_tiles(n_bytes);
   const unsigned ltiles = (unsigned)scan_tiles((u64)n_lines);
   BF_CUDA(cudaMemsetAsync(w.hdr, 0, 8 * sizeof(i64), st));
-  BF_CUDA(cudaMemsetAsync(w.hdr + 2, 0xff, sizeof(i64), st));  // first bad line: none
+  BF_CUDA(cudaMemsetAsync(w.hdr + 2, 0xff, 2 * sizeof(i64), st));  // first bad line, first colliding line: none
   BF_LAUNCH(PC_GATHER, 0, st, bed_table_init_kernel<<<BED_SLOTS / 256, 256, 0, st>>>(w.table));
   // the census again (the workspace of bf_bed_scan is not kept), now followed by the line starts
   BF_LAUNCH(PC_GATHER, n_bytes, st, bed_census_kernel<<<(unsigned)tiles, SC_THREADS, 0, st>>>(text, n_bytes, w.spine));
@@ -342,6 +363,9 @@ int bf_bed_parse(const uint8_t* text, int64_t n_bytes, int64_t n_lines, void* ws
             bed_parse_kernel<<<ltiles, SC_THREADS, 0, st>>>(text, n_bytes, w.line_start, n_lines, w.table, w.t_start, w.t_end,
                                                             w.t_slot, w.loc, w.row_spine, w.hdr));
   BF_LAUNCH(PC_SCAN, 0, st, spine_scan_kernel<false><<<1, 1024, 0, st>>>(w.row_spine, (u64)ltiles, reinterpret_cast<u64*>(w.hdr + 1)));
+  BF_LAUNCH(PC_GATHER, 16 * n_lines, st,
+            bed_verify_names_kernel<<<(unsigned)ceil_div(n_lines, 256), 256, 0, st>>>(text, w.line_start, n_lines, w.table,
+                                                                                     w.t_slot, w.hdr));
   BF_CUDA(cudaStreamSynchronize(st));
   i64 hdr[4];
   BF_CUDA(cudaMemcpy(hdr, w.hdr, sizeof(hdr), cudaMemcpyDeviceToHost));
@@ -354,6 +378,11 @@ int bf_bed_parse(const uint8_t* text, int64_t n_bytes, int64_t n_lines, void* ws
     set_error("bf_bed_parse: line %lld is not <name> TAB <integer> TAB <integer> [TAB ...] (or more than %u distinct names)",
               (long long)hdr[2], BED_MAX_NAMES);
     return BF_ERR_ARG;
+  }
+  if (hdr[3] != -1) {
+    set_error("bf_bed_parse: the chromosome name of line %lld has the same 96-bit fingerprint as a different name "
+              "(hash collision; the names are compared byte for byte, nothing was merged)", (long long)hdr[3]);
+    return BF_ERR_RANGE;
   }
   // host copy of the table: BED_SLOTS x 24 bytes = 1.5 MB
   std::vector<BedSlot> h_table(BED_SLOTS);

@@ -21,6 +21,28 @@ def _require_cuda():
         raise _lib.EngineError("bioframe_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
 
 
+# The scratch of every op -- Workspace, the prepared-set stores, the download staging -- is ONE grow-only buffer
+# per device that carries state from a _count call to its _emit call.  ctypes releases the GIL inside the library,
+# so two Python threads on one device would overwrite each other's scratch: every op holds the device's lock
+# from its first library call to its last (calls on different devices run side by side).
+import contextlib
+import threading
+
+_DEVICE_LOCKS = {}
+_LOCKS_LOCK = threading.Lock()
+
+
+@contextlib.contextmanager
+def _on(device):
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    with _LOCKS_LOCK:
+        lock = _DEVICE_LOCKS.setdefault(idx, threading.RLock())
+    with lock, torch.cuda.device(device):
+        yield
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr() if t is not None and t.numel() > 0 else 0)
 
@@ -77,7 +99,7 @@ def download_rows(t, out=None, n_threads=None):
     if n == 0:
         return out[:0]
     device = t.device
-    with torch.cuda.device(device):
+    with _on(device):
         dev, pinned = _DownloadStage.get(device)
         rc = _lib.lib().bf_download_rows(
             _ptr(t), n, C.c_void_p(out.ctypes.data), _ptr(dev), dev.numel(), C.c_void_p(pinned.data_ptr()),
@@ -190,7 +212,7 @@ def _overlap_intidxs_once(grp1, start1, end1, grp2, start2, end2, n_groups, how=
     g2 = _as(grp2, torch.int32, device) if n_groups > 1 else None
     n1, n2 = int(s1.numel()), int(s2.numel())
     how_code = _lib.HOW[how]
-    with torch.cuda.device(device):
+    with _on(device):
         nbytes = L.bf_overlap_workspace_bytes(n1, n2, n_groups, how_code)
         ws = Workspace.get(device, max(nbytes, 256))
         plan = _lib.Plan()
@@ -269,7 +291,7 @@ def measure_extent(grp, start, end, n_groups, device=None):
     n = int(s.numel())
     words = np.zeros(int(L.bf_extent_words(n_groups)), dtype=np.int64)
     pres = C.c_int32(0)
-    with torch.cuda.device(device):
+    with _on(device):
         ws = torch.empty(max(int(L.bf_extent_workspace_bytes(n_groups)), 256), dtype=torch.uint8, device=device)
         rc = L.bf_extent_measure(_ptr(g), _ptr(s), _ptr(e), n, n_groups, _ptr(ws), ws.numel(), _stream_ptr(device),
                                  C.c_void_p(words.ctypes.data), C.byref(pres))
@@ -291,7 +313,7 @@ def prepare_set(words, grp, start, end, n_groups, presorted=False, device=None, 
     n = int(s.numel())
     words = np.ascontiguousarray(words, dtype=np.int64)
     struct = _lib.SortedSetStruct()
-    with torch.cuda.device(device):
+    with _on(device):
         nbytes = max(int(L.bf_sorted_set_bytes(n, n_groups, 0)), 256)
         store = SetStores.get(device, slot, nbytes) if slot else torch.empty(nbytes, dtype=torch.uint8, device=device)
         rc = L.bf_overlap_prepare_set(C.c_void_p(words.ctypes.data), _ptr(g), _ptr(s), _ptr(e), n, n_groups,
@@ -311,7 +333,7 @@ def adopt_set(words, n, n_groups, grp=None, device=None, slot=None):
     device = torch.device(device if device is not None else "cuda")
     words = np.ascontiguousarray(words, dtype=np.int64)
     struct = _lib.SortedSetStruct()
-    with torch.cuda.device(device):
+    with _on(device):
         nbytes = max(int(L.bf_sorted_set_bytes(int(n), n_groups, 1)), 256)
         store = SetStores.get(device, slot, nbytes) if slot else torch.empty(nbytes, dtype=torch.uint8, device=device)
         rc = L.bf_overlap_adopt_set(C.c_void_p(words.ctypes.data), int(n), n_groups, _ptr(store), store.numel(),
@@ -334,7 +356,7 @@ def overlap_prepared(set1, set2, how="inner", closed=False, own_range=None, row_
     device = set1.device
     how_code = _lib.HOW[how]
     own = None if own_range is None else np.ascontiguousarray(own_range, dtype=np.int64)
-    with torch.cuda.device(device):
+    with _on(device):
         ws = Workspace.get(device, max(L.bf_overlap_prepared_workspace_bytes(set1.n, set2.n, set1.n_groups, how_code), 256))
         plan = _lib.Plan()
         n_rows, n_pairs = C.c_int64(0), C.c_int64(0)
@@ -375,7 +397,7 @@ def sort_pairs(ev1, ev2, max1, max2):
     if n == 0:
         return ev1, ev2
     device = ev1.device
-    with torch.cuda.device(device):
+    with _on(device):
         ws = Workspace.get(device, max(L.bf_sort_pairs_workspace_bytes(n), 256))
         rc = L.bf_sort_pairs(_ptr(ev1), _ptr(ev2), n, int(max1), int(max2), _ptr(ws), ws.numel(), _stream_ptr(device))
         _lib.check(rc, "bf_sort_pairs")
@@ -433,7 +455,7 @@ def _cluster_once(grp, start, end, n_groups, min_dist=0, want_ids=True, want_tab
     has_md = 0 if min_dist is None else 1
     md = 0 if min_dist is None else int(min_dist)
     need_ids = want_ids or want_row_spans
-    with torch.cuda.device(device):
+    with _on(device):
         ws = Workspace.get(device, max(L.bf_cluster_workspace_bytes(n, n_groups), 256))
         plan = _lib.Plan()
         nc = C.c_int64(0)
@@ -514,7 +536,7 @@ def _coverage_once(grp1, start1, end1, grp2, start2, end2, n_groups, device=None
     g1 = _as(grp1, torch.int32, device) if n_groups > 1 else None
     g2 = _as(grp2, torch.int32, device) if n_groups > 1 else None
     n1, n2 = int(s1.numel()), int(s2.numel())
-    with torch.cuda.device(device):
+    with _on(device):
         ws = Workspace.get(device, max(L.bf_coverage_workspace_bytes(n1, n2, n_groups), 256))
         cov = torch.empty(n1, dtype=torch.int64, device=device)
         rc = L.bf_coverage(_ptr(g1), _ptr(s1), _ptr(e1), n1, _ptr(g2), _ptr(s2), _ptr(e2), n2, n_groups,
@@ -544,7 +566,7 @@ def _count_overlaps_once(grp1, start1, end1, grp2, start2, end2, n_groups, close
     g1 = _as(grp1, torch.int32, device) if n_groups > 1 else None
     g2 = _as(grp2, torch.int32, device) if n_groups > 1 else None
     n1, n2 = int(s1.numel()), int(s2.numel())
-    with torch.cuda.device(device):
+    with _on(device):
         ws = Workspace.get(device, max(L.bf_count_overlaps_workspace_bytes(n1, n2, n_groups), 256))
         counts = torch.empty(n1, dtype=torch.int64, device=device)
         rc = L.bf_count_overlaps(_ptr(g1), _ptr(s1), _ptr(e1), n1, _ptr(g2), _ptr(s2), _ptr(e2), n2, n_groups,
@@ -566,7 +588,7 @@ def overlap_ordered(grp1, start1, end1, grp2, start2, end2, n_groups, device=Non
     g1 = _as(grp1, torch.int32, device) if n_groups > 1 else None
     g2 = _as(grp2, torch.int32, device) if n_groups > 1 else None
     n1, n2 = int(s1.numel()), int(s2.numel())
-    with torch.cuda.device(device):
+    with _on(device):
         ws = Workspace.get(device, max(L.bf_overlap_ordered_workspace_bytes(n1, n2, n_groups), 256))
         plan = _lib.Plan()
         n_rows, biggest = C.c_int64(0), C.c_int64(0)
@@ -594,7 +616,7 @@ def gather_rows(column, idx, want_valid=False, device=None):
     col = col.to(device=device, non_blocking=True).contiguous()
     ix = _as(idx, torch.int64, device)
     n = int(ix.numel())
-    with torch.cuda.device(device):
+    with _on(device):
         out = torch.empty(n, dtype=col.dtype, device=device)
         valid = torch.empty(n, dtype=torch.uint8, device=device) if want_valid else None
         rc = _lib.lib().bf_gather_rows(_ptr(col), col.element_size(), _ptr(ix), n, _ptr(out), _ptr(valid),
@@ -613,7 +635,7 @@ def codes_present(codes, n_categories, device=None):
     device = torch.device(device if device is not None else "cuda")
     t = codes if isinstance(codes, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(codes))
     t = t.to(device=device, non_blocking=True).contiguous()
-    with torch.cuda.device(device):
+    with _on(device):
         present = torch.empty(int(n_categories) + 2, dtype=torch.int32, device=device)
         rc = _lib.lib().bf_group_codes_present(_ptr(t), t.element_size(), int(t.numel()), int(n_categories), _ptr(present),
                                                _stream_ptr(device))
@@ -632,7 +654,7 @@ def codes_apply(codes_dev, lut, device=None):
     _require_cuda()
     device = codes_dev.device
     lut_t = torch.from_numpy(np.ascontiguousarray(lut, dtype=np.int32)).to(device)
-    with torch.cuda.device(device):
+    with _on(device):
         out = torch.empty(int(codes_dev.numel()), dtype=torch.int32, device=device)
         rc = _lib.lib().bf_group_codes_apply(_ptr(codes_dev), codes_dev.element_size(), int(codes_dev.numel()), _ptr(lut_t),
                                              int(lut_t.numel()) - 1, _ptr(out), _stream_ptr(device))
@@ -651,7 +673,7 @@ def pair_coords(ev1, ev2, start1, end1, start2, end2, want_overlap=True, want_di
     s1, e1 = _as(start1, torch.int64, device), _as(end1, torch.int64, device)
     s2, e2 = _as(start2, torch.int64, device), _as(end2, torch.int64, device)
     n = int(a.numel())
-    with torch.cuda.device(device):
+    with _on(device):
         os_ = torch.empty(n, dtype=torch.int64, device=device) if want_overlap else None
         oe = torch.empty(n, dtype=torch.int64, device=device) if want_overlap else None
         dist = torch.empty(n, dtype=torch.int64, device=device) if want_distance else None
@@ -698,7 +720,7 @@ def _subtract_once(grp1, start1, end1, grp2, start2, end2, n_groups, want_sub_in
     g1 = _as(grp1, torch.int32, device) if n_groups > 1 else None
     g2 = _as(grp2, torch.int32, device) if n_groups > 1 else None
     n1, n2 = int(s1.numel()), int(s2.numel())
-    with torch.cuda.device(device):
+    with _on(device):
         ws = Workspace.get(device, max(L.bf_subtract_workspace_bytes(n1, n2, n_groups), 256))
         plan = _lib.Plan()
         n_rows = C.c_int64(0)
@@ -729,7 +751,7 @@ def complement(region, start, end, bounds_lo, bounds_hi, device=None):
         return torch.empty(0, dtype=torch.int32, device=device), z, z.clone()
     g = _as(region, torch.int32, device) if nr > 1 else None
     n = int(s.numel())
-    with torch.cuda.device(device):
+    with _on(device):
         ws = Workspace.get(device, max(L.bf_complement_workspace_bytes(n, nr), 256))
         plan = _lib.Plan()
         ng = C.c_int64(0)
@@ -800,7 +822,7 @@ def _closest_intidxs_once(grp1, start1, end1, grp2, start2, end2, n_groups, k=1,
         | (_lib.CLOSEST_IGNORE_DOWNSTREAM if ignore_downstream else 0)
         | (_lib.CLOSEST_SELF if self_closest else 0)
     )
-    with torch.cuda.device(device):
+    with _on(device):
         ws = Workspace.get(device, max(L.bf_closest_workspace_bytes(n1, n2, n_groups), 256))
         plan = _lib.Plan()
         n_rows, n_matched = C.c_int64(0), C.c_int64(0)
