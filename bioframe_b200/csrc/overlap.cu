@@ -317,11 +317,10 @@ __global__ void __launch_bounds__(SC_THREADS, 6)
   }
 #pragma unroll 4
   for (u32 i = tid; i < nst; i += SC_THREADS) s_rel[i] = (u32)(key_cs(other[br_lo + i], L) - base_cs + 1);
-  u32 pow2w = 1, pow2n = 1;
-  while (pow2w <= W) pow2w <<= 1;
-  pow2w >>= 1;  // largest power of two <= W (0 if W == 0)
-  while (pow2n <= nst) pow2n <<= 1;
-  pow2n >>= 1;
+  // largest powers of two <= W and <= nst (0 for 0); the shift loops these replace were 13 % of the kernel's
+  // executed instructions (ncu source page, r1 capture)
+  const u32 pow2w = W ? 1u << (31 - __clz(W)) : 0u;
+  const u32 pow2n = nst ? 1u << (31 - __clz(nst)) : 0u;
   __syncthreads();
 
   u32 cnt[IPT];

@@ -5,7 +5,7 @@
 set -u
 TAG=${1:-r1}; shift
 KERNELS=${@:-onesweep_pass_kernel emit_pairs_kernel search_count_kernel pack_keys_kernel}
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --no-frame --no-secondary"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
