@@ -678,6 +678,29 @@ def frame_leg(args):
         "ms": t_idx * 1e3, "rows": int(len(idx[0])), "intervals_per_s": (len(df1) + len(df2)) / t_idx,
         "stages_ms_profiled": {k: round(v * 1e3, 1) for k, v in prof.items()},
     }
+    del idx
+    # the public call at the benchmark size: the whole result FRAME (8.76e8 rows x 6 columns, ~40 GB on the host).  The
+    # reference materialises every input column per pair through numpy and needs > 60 GB and minutes for it (SURVEY.md
+    # 8d); only attempted where the host has the memory
+    try:
+        import psutil
+
+        room = psutil.virtual_memory().available
+    except Exception:
+        room = 0
+    if room > 150e9:
+        w0 = time.perf_counter()
+        res = ours.overlap(df1, df2, how="inner")
+        dt = time.perf_counter() - w0
+        out["cfg3_overlap_inner_frames"] = {
+            "what": f"bioframe_b200.overlap(df1, df2, how='inner') on DataFrames of {len(df1)} / {len(df2)} rows -> frame of "
+                    f"{len(res)} rows x {res.shape[1]} columns",
+            "ms": dt * 1e3, "intervals_per_s": (len(df1) + len(df2)) / dt, "rows": int(len(res)),
+            "frame_bytes": int(res.memory_usage(index=False).sum()),
+        }
+        del res
+    else:
+        out["cfg3_overlap_inner_frames"] = {"skipped": f"needs ~150 GB of free host memory, {room / 1e9:.0f} GB available"}
     return out
 
 

@@ -796,88 +796,123 @@ __global__ void __launch_bounds__(OE_THREADS)
   __shared__ u32 s_raw[OE_CAP];             // partner rows as gathered, 0xffffffff = none
   __shared__ u32 s_sorted[OE_CAP];          // ... in row order within every query
   __shared__ u8 s_own[OE_CAP];              // query of the row, relative to the block's first query
-  __shared__ u32 s_rel[OE_THREADS + 1];     // first staged row of every query
+  __shared__ u32 s_rel[OE_THREADS + 1];     // first output row of every query, relative to the block's first
   const u32 tid = threadIdx.x;
   const i64 r0 = (i64)blockIdx.x * OE_THREADS;
   const i64 r = r0 + tid;
   const i64 r_last = min(r0 + OE_THREADS, A.n1) - 1;
+  const u32 nq = (u32)(r_last - r0 + 1);
   // 256 consecutive queries lie inside one scan tile (2048 rows): offsets relative to the block's first row
   const u32 loc0 = loc_in[r0];
   const u32 c_last = cnt_in[r_last];
   const u32 block_rows = loc_in[r_last] + (c_last > 0 ? c_last : 1u) - loc0;
   const i64 out0 = (i64)spine[r0 / SC_TILE] + loc0;
-  const bool staged = block_rows <= (u32)OE_CAP;
-  s_rel[tid] = block_rows;  // queries past the end of the input
-  if (tid == 0) s_rel[OE_THREADS] = block_rows;
+  // this thread's query: partner count, place, and where its partners are in the start order
+  u32 c = 0, rel = block_rows;
+  u64 xs = 0;
+  i64 lo = 0;
+  u32 n_inside = 0;
   if (r < A.n1) {
-    const u32 c = cnt_in[r];
-    const u32 rel = loc_in[r] - loc0;
-    const i64 at = out0 + rel;
-    s_rel[tid] = rel;
-    if (c == 0) {
-      if (staged) {
-        s_raw[rel] = 0xffffffffu;
-        s_own[rel] = (u8)tid;
-      } else {
-        ev1[at] = r;
-        ev2[at] = -1;
-      }
-    } else {
-      u64 xs, xe;
+    c = cnt_in[r];
+    rel = loc_in[r] - loc0;
+    if (c > 0) {
+      u64 xe;
       ordered_query(A, r, &xs, &xe);
-      const i64 lo = P.rec ? ordered_starts_below(P.starts32, A.lutS, xs) : lut_count_below<false>(A.kS, A.lutS, xs);
+      lo = P.rec ? ordered_starts_below(P.starts32, A.lutS, xs) : lut_count_below<false>(A.kS, A.lutS, xs);
       const i64 hi = (i64)started_in[r];
-      const u32 n_inside = hi > lo ? (u32)(hi - lo) : 0u;
-      u32 k = 0;
-      auto gather = [&](auto put) {
-        i64 from = lo;
-        if (P.rec) {
-          for (u32 i = 0; i < n_inside && k < c; ++i) put(P.rec[lo + i].y);
-          const u32 xs32 = (u32)xs;
-          i64 m = lo - 1;
-          for (u32 step = 0; k < c && m >= 0 && step < OE_NEAR_STEPS; step += 4, m -= 4) {
-            uint2 t[4];  // four records in flight: the loop is a chain of dependent round trips otherwise
+      n_inside = hi > lo ? (u32)(hi - lo) : 0u;
+    }
+  }
+  s_rel[tid] = rel;
+  if (tid == 0) s_rel[OE_THREADS] = block_rows;
+  __syncthreads();
+  // all partners of this thread's query, unsorted, handed to `put` one by one
+  auto gather = [&](auto put, u32& k) {
+    i64 from = lo;
+    if (P.rec) {
+      for (u32 i = 0; i < n_inside && k < c; ++i) put(P.rec[lo + i].y);
+      const u32 xs32 = (u32)xs;
+      i64 m = lo - 1;
+      for (u32 step = 0; k < c && m >= 0 && step < OE_NEAR_STEPS; step += 4, m -= 4) {
+        uint2 t[4];  // four records in flight: the loop is a chain of dependent round trips otherwise
 #pragma unroll
-            for (int q = 0; q < 4; ++q) t[q] = P.rec[m - q >= 0 ? m - q : 0];
+        for (int q = 0; q < 4; ++q) t[q] = P.rec[m - q >= 0 ? m - q : 0];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (m - q >= 0 && k < c && t[q].x > xs32) put(t[q].y);
-          }
-          from = m + 1 > 0 ? m + 1 : 0;
-        } else {
-          for (u32 i = 0; i < n_inside && k < c; ++i) put(A.idS[lo + i]);
-        }
-        if (k < c)
-          walk_stabbing(A, from, xs, [&](i64 mm) {
-            put(A.idS[mm]);
-            return k < c;
-          });
-      };
-      if (staged) {
-        gather([&](u32 id) { s_raw[rel + k++] = id; });
-        for (u32 i = 0; i < c; ++i) s_own[rel + i] = (u8)tid;
-      } else {
-        gather([&](u32 id) { ev2[at + k++] = id; });
+        for (int q = 0; q < 4; ++q)
+          if (m - q >= 0 && k < c && t[q].x > xs32) put(t[q].y);
+      }
+      from = m + 1 > 0 ? m + 1 : 0;
+    } else {
+      for (u32 i = 0; i < n_inside && k < c; ++i) put(A.idS[lo + i]);
+    }
+    if (k < c)
+      walk_stabbing(A, from, xs, [&](i64 mm) {
+        put(A.idS[mm]);
+        return k < c;
+      });
+  };
+  // The block's queries are taken in stretches whose rows fit the staging area.  Queries in arbitrary order
+  // average 9 partners (2240 rows per block: one stretch); queries that arrive SORTED put a whole hotspot of
+  // targets into one block (256 neighbours with 30+ partners each), which used to push the block onto the
+  // per-thread path below -- 24 ms for sorted input against 18.7 ms for shuffled input (profiles/NOTES.md, r2).
+  u32 qb = 0;
+  while (qb < nq) {  // block-uniform
+    const u32 first_row = s_rel[qb];
+    u32 qe = qb + 1;
+    {  // largest qe with rows(qb .. qe) <= OE_CAP (s_rel is non-decreasing; s_rel[nq .. 256] = block_rows)
+      u32 a = qb + 1, b = nq;
+      while (a < b) {
+        const u32 mid = (a + b + 1) >> 1;
+        if (s_rel[mid] - first_row <= (u32)OE_CAP)
+          a = mid;
+        else
+          b = mid - 1;
+      }
+      qe = a;
+    }
+    const u32 seg_rows = s_rel[qe] - first_row;
+    if (seg_rows > (u32)OE_CAP) {
+      // one query with more rows than the staging area holds: written and sorted in global memory by its thread
+      if (tid == qb) {
+        const i64 at = out0 + rel;
+        u32 k = 0;
+        gather([&](u32 id) { ev2[at + k++] = id; }, k);
         ordered_heapsort(ev2 + at, (i64)k);
         for (u32 i = 0; i < k; ++i) ev1[at + i] = r;
       }
+      qb = qe;
+      continue;
     }
-  }
-  if (!staged) return;  // block-uniform
-  __syncthreads();
-  for (u32 x = tid; x < block_rows; x += OE_THREADS) {
-    const u32 o = s_own[x];
-    const u32 a = s_rel[o], b = a + (s_rel[o + 1] - a);  // the query's rows: [a, b)
-    const u32 v = s_raw[x];
-    u32 rank = 0;
-    for (u32 j = a; j < b; ++j) rank += s_raw[j] < v;
-    s_sorted[a + rank] = v;
-  }
-  __syncthreads();
-  for (u32 x = tid; x < block_rows; x += OE_THREADS) {
-    const u32 id = s_sorted[x];
-    ev1[out0 + x] = r0 + s_own[x];
-    ev2[out0 + x] = id == 0xffffffffu ? -1ll : (i64)id;
+    if (tid >= qb && tid < qe) {
+      const u32 at = rel - first_row;
+      if (c == 0) {
+        s_raw[at] = 0xffffffffu;
+        s_own[at] = (u8)tid;
+      } else {
+        u32 k = 0;
+        gather([&](u32 id) { s_raw[at + k++] = id; }, k);
+        for (u32 i = 0; i < c; ++i) s_own[at + i] = (u8)tid;
+      }
+    }
+    __syncthreads();
+    // rank: every staged row counts the smaller rows of its own query; its rank is its place
+    for (u32 x = tid; x < seg_rows; x += OE_THREADS) {
+      const u32 o = s_own[x];
+      const u32 a = s_rel[o] - first_row, b = s_rel[o + 1] - first_row;  // the query's rows: [a, b)
+      const u32 v = s_raw[x];
+      u32 rank = 0;
+      for (u32 j = a; j < b; ++j) rank += s_raw[j] < v;
+      s_sorted[a + rank] = v;
+    }
+    __syncthreads();
+    const i64 seg0 = out0 + first_row;
+    for (u32 x = tid; x < seg_rows; x += OE_THREADS) {
+      const u32 id = s_sorted[x];
+      ev1[seg0 + x] = r0 + s_own[x];
+      ev2[seg0 + x] = id == 0xffffffffu ? -1ll : (i64)id;
+    }
+    __syncthreads();  // the staging area is reused by the next stretch
+    qb = qe;
   }
 }
 

@@ -27,4 +27,11 @@ for name, (qq, tt) in (("unsorted", (q, t)), ("sorted", (srt(q), srt(t)))):
         r = engine.cluster(d[0], d[1], d[2], bench.N_GROUPS); del r
     b.record(); torch.cuda.synchronize()
     print(name, "cluster 1e8:", round(a.elapsed_time(b) / 3, 2), "ms")
+    for _ in range(2):
+        r = engine.overlap_ordered(*d, bench.N_GROUPS); del r
+    a.record()
+    for _ in range(3):
+        r = engine.overlap_ordered(*d, bench.N_GROUPS); del r
+    b.record(); torch.cuda.synchronize()
+    print(name, "left join in row order (keep_order) 1e8 x 1e7:", round(a.elapsed_time(b) / 3, 2), "ms")
     del d
