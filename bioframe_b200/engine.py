@@ -83,31 +83,6 @@ def host_threads():
     return max(1, min(8, n - 2))  # the widening is bound by host memory bandwidth well before 8 threads
 
 
-_LIBC = None
-
-
-def _big_host_array(n):
-    """Fresh int64 host array for a result.  A 7 GB result is 1.7 M first-touch page faults of 4 KB -- more time
-    than the PCIe copy itself -- so large arrays ask for transparent huge pages (madvise(MADV_HUGEPAGE) on the
-    2 MB-aligned interior of numpy's mmap'ed block; a no-op where the kernel does not offer them)."""
-    import numpy as np
-
-    global _LIBC
-    out = np.empty(n, dtype=np.int64)
-    if out.nbytes >= (64 << 20):
-        try:
-            if _LIBC is None:
-                _LIBC = C.CDLL(None, use_errno=True)
-            huge = 2 << 20
-            lo = (out.ctypes.data + huge - 1) // huge * huge
-            hi = (out.ctypes.data + out.nbytes) // huge * huge
-            if hi > lo:
-                _LIBC.madvise(C.c_void_p(lo), C.c_size_t(hi - lo), 14)  # MADV_HUGEPAGE
-        except Exception:
-            pass
-    return out
-
-
 def download_rows(t, out=None, n_threads=None):
     """int64 CUDA tensor of row numbers (values in [-1, 2^31 - 1)) -> int64 numpy array on the host, crossing PCIe
     as 4 bytes per value (bf_download_rows).  `out`: optional preallocated contiguous int64 numpy array."""
@@ -118,7 +93,7 @@ def download_rows(t, out=None, n_threads=None):
         raise ValueError("download_rows: contiguous int64 CUDA tensor expected")
     n = int(t.numel())
     if out is None:
-        out = _big_host_array(n)
+        out = np.empty(n, dtype=np.int64)
     if out.dtype != np.int64 or not out.flags.c_contiguous or out.size < n:
         raise ValueError("download_rows: out must be a contiguous int64 array of at least t.numel() values")
     if n == 0:
