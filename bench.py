@@ -880,13 +880,15 @@ def main():
             set2 = engine.prepare_set(words, dt[0], dt[1], dt[2], N_GROUPS, presorted=pres2) if rank == 0 else engine.adopt_set(words, n2, N_GROUPS)
             if world > 1:
                 handles = [dist.broadcast(set2.keys, src=0, async_op=True), dist.broadcast(set2.ids, src=0, async_op=True)]
+            for h in handles:
+                h.wait()  # the side stream waits for the sorted targets; the main stream sorts the first chunk meanwhile
+            if args.how == "left":
+                engine.set_runmax(set2)  # running max of the targets' ends: once per step, not once per chunk
         pairs = rows = 0
         for c, ch in enumerate(chunk_plan):
             sl = slice(ch["lo"], ch["h_hi"])
             set1 = engine.prepare_set(words, dq[0][sl], dq[1][sl], dq[2][sl], N_GROUPS, presorted=pres)
             if c == 0:
-                for h in handles:
-                    h.wait()
                 main_s.wait_stream(side)
                 set2.store.record_stream(main_s)
             n_own = ch["hi"] - ch["lo"]

@@ -66,6 +66,7 @@ SIGNATURES = {
     "bf_overlap_prepare_set": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _p, _sz, _p, C.POINTER(SortedSetStruct)]),
     "bf_overlap_adopt_set": (C.c_int, [_p, _i64, _i32, _p, _sz, _p, C.POINTER(SortedSetStruct)]),
     "bf_sorted_set_buffers": (C.c_int, [C.POINTER(SortedSetStruct), C.POINTER(_p), C.POINTER(_p), C.POINTER(_i64)]),
+    "bf_sorted_set_runmax": (C.c_int, [C.POINTER(SortedSetStruct), _p]),
     "bf_overlap_prepared_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "bf_overlap_count_prepared": (
         C.c_int,

@@ -282,6 +282,12 @@ __global__ void __launch_bounds__(SC_THREADS, 6)
   __shared__ u64 s_tmp[8];
   const u32 tid = threadIdx.x;
   const i64 tile = blockIdx.x;
+  if (ownpos) {
+    // query-sharded call: a tile without a single owned row has nothing to count (its offsets and its tile
+    // total were zeroed by the host wrapper) -- 7 of 8 tiles of the target side on 8 ranks
+    const i64 own_lo = ownpos[B_SIDE ? 2 : 0], own_hi = ownpos[B_SIDE ? 3 : 1];
+    if (tile * TILE >= own_hi || (tile + 1) * TILE <= own_lo) return;
+  }
   const i64 base = tile * TILE + (i64)tid * IPT;  // this thread's first row
   // own rows: IPT consecutive keys per thread, 16-byte loads
   u64 key[IPT];
@@ -810,6 +816,10 @@ static int launch_search_ipt(const SortResult& mine, i64 n, const SortResult& ot
                              const u64* other_pmax, const KeyLayout& L, int closed, i64* overflow, const i64* ownpos,
                              cudaStream_t st) {
   const i64 tiles = search_tiles(n, IPT);
+  if (ownpos) {  // tiles outside the owned range return at once: their outputs are these zeros
+    BF_CUDA(cudaMemsetAsync(sw.loc, 0, (size_t)n * sizeof(u32), st));
+    BF_CUDA(cudaMemsetAsync(sw.tilepre, 0, ((size_t)tiles + 1) * sizeof(u64), st));
+  }
   BF_LAUNCH(PC_SEARCH, 0, st, search_partition_kernel<B_SIDE><<<(unsigned)ceil_div(tiles + 1, 256), 256, 0, st>>>(
       mine.keys, n, other.keys, m, L, (i64)SC_THREADS * IPT, tiles, sw.bracket));
   BF_LAUNCH(PC_SEARCH, 16 * n, st, (search_count_kernel<B_SIDE, FLAGS, IPT><<<(unsigned)tiles, SC_THREADS, 0, st>>>(
@@ -871,7 +881,8 @@ __global__ void own_positions_kernel(const u64* __restrict__ key1, i64 n1, const
 // `own` (host, 4 words or null): (g_lo, s_lo, g_hi, s_hi) of a query-sharded call.
 static int count_sorted(OverlapWS& w, const KeyLayout& L, const SortResult& r1, i64 n1, const SortResult& r2, i64 n2,
                         const i32* grp1, const i32* grp2, i32 nb, i32 how, i32 closed, const i64* own,
-                        OverlapPlan* plan, cudaStream_t st) {
+                        OverlapPlan* plan, cudaStream_t st, const u64* pmax1_ready = nullptr,
+                        const u64* pmax2_ready = nullptr) {
   const bool need1 = how & 1, need2 = how & 2;
   plan->L = L;
   plan->key1 = r1.keys;
@@ -893,8 +904,11 @@ static int count_sorted(OverlapWS& w, const KeyLayout& L, const SortResult& r1, 
   // ---- running max of end' (only where an outer side needs it) ----
   const SortResult* rs[2] = {&r1, &r2};
   const i64 nn[2] = {n1, n2};
+  const u64* pmax_ready[2] = {pmax1_ready, pmax2_ready};
   for (int k = 0; k < 2; ++k) {
-    if (w.s[k].pmax && nn[k] > 0) {
+    if (w.s[k].pmax && pmax_ready[k]) {  // a prepared set brought its running maximum along (bf_sorted_set_runmax)
+      w.s[k].pmax = const_cast<u64*>(pmax_ready[k]);
+    } else if (w.s[k].pmax && nn[k] > 0) {
       const unsigned tiles = (unsigned)scan_tiles((u64)nn[k]);
       BF_LAUNCH(PC_RUNMAX, 0, st, tile_max_ce_kernel<<<tiles, SC_THREADS, 0, st>>>(rs[k]->keys, (u64)nn[k], L, w.s[k].spine));
       BF_LAUNCH(PC_RUNMAX, 0, st, spine_scan_kernel<true><<<1, 1024, 0, st>>>(w.s[k].spine, tiles, nullptr));
@@ -1028,6 +1042,7 @@ struct SetStore {
   SortBufs sb;
   RadixScratch radix;
   LayoutScratch layout;
+  u64 *pmax, *pmax_spine;
 };
 static void layout_set_store(Arena& a, i64 n, i32 nb, bool adopt, SetStore* s) {
   if (adopt) {
@@ -1039,11 +1054,15 @@ static void layout_set_store(Arena& a, i64 n, i32 nb, bool adopt, SetStore* s) {
     s->sb.tmp4a = s->sb.tmp4b = nullptr;
     s->sb.spine = s->sb.nT = nullptr;
     s->layout = take_layout_scratch(a, nb);
+    s->pmax = a.take<u64>(n);
+    s->pmax_spine = a.take<u64>(scan_tiles((u64)n) + 1);
     return;
   }
   take_sort_bufs(a, n, &s->sb);
   s->radix = take_radix_scratch(a, (u64)n);
   s->layout = take_layout_scratch(a, nb);
+  s->pmax = a.take<u64>(n);
+  s->pmax_spine = a.take<u64>(scan_tiles((u64)n) + 1);
 }
 struct SortedSet {  // lives in the caller's bf_sorted_set
   u64 magic;
@@ -1052,6 +1071,9 @@ struct SortedSet {  // lives in the caller's bf_sorted_set
   KeyLayout L;  // goff points into the set's own store
   u64* keys;
   u32* ids;
+  u64* pmax;        // [n] running max of end' in sorted order, valid once pmax_ready (bf_sorted_set_runmax)
+  u64* pmax_spine;  // [scan tiles + 1]
+  i32 pmax_ready, pad;
 };
 static_assert(sizeof(SortedSet) <= sizeof(bf_sorted_set), "bf_sorted_set too small");
 constexpr u64 SET_MAGIC = 0x6266536f72746564ull;
@@ -1160,6 +1182,9 @@ int bf_overlap_prepare_set(const int64_t* extent_words, const int32_t* grp, cons
   set->adopted = 0;
   set->keys = r.keys;
   set->ids = r.vals;
+  set->pmax = ss.pmax;
+  set->pmax_spine = ss.pmax_spine;
+  set->pmax_ready = 0;
   set->magic = SET_MAGIC;
   return BF_OK;
 }
@@ -1186,6 +1211,9 @@ int bf_overlap_adopt_set(const int64_t* extent_words, int64_t n, int32_t n_group
   set->adopted = 1;
   set->keys = ss.sb.keyA;
   set->ids = ss.sb.idA;
+  set->pmax = ss.pmax;
+  set->pmax_spine = ss.pmax_spine;
+  set->pmax_ready = 0;
   set->magic = SET_MAGIC;
   return BF_OK;
 }
@@ -1199,6 +1227,25 @@ int bf_sorted_set_buffers(const bf_sorted_set* set_in, void** keys_out, void** i
   if (keys_out) *keys_out = set->keys;
   if (ids_out) *ids_out = set->ids;
   if (n_out) *n_out = set->n;
+  return BF_OK;
+}
+
+int bf_sorted_set_runmax(bf_sorted_set* set_io, void* stream) {
+  using namespace bf;
+  SortedSet* set = (SortedSet*)set_io;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!set || set->magic != SET_MAGIC) {
+    set_error("bf_sorted_set_runmax: not a prepared set");
+    return BF_ERR_STATE;
+  }
+  if (set->n > 0) {
+    const unsigned tiles = (unsigned)scan_tiles((u64)set->n);
+    BF_LAUNCH(PC_RUNMAX, 0, st, tile_max_ce_kernel<<<tiles, SC_THREADS, 0, st>>>(set->keys, (u64)set->n, set->L, set->pmax_spine));
+    BF_LAUNCH(PC_RUNMAX, 0, st, spine_scan_kernel<true><<<1, 1024, 0, st>>>(set->pmax_spine, tiles, nullptr));
+    BF_LAUNCH(PC_RUNMAX, 16 * set->n, st,
+              running_max_ce_kernel<<<tiles, SC_THREADS, 0, st>>>(set->keys, (u64)set->n, set->L, set->pmax_spine, set->pmax));
+  }
+  set->pmax_ready = 1;
   return BF_OK;
 }
 
@@ -1246,7 +1293,8 @@ int bf_overlap_count_prepared(const bf_sorted_set* set1_in, const bf_sorted_set*
   init_plan(plan, a->n, b->n, nb, how, closed, 1);
   SortResult r1 = {a->keys, a->ids, nullptr, nullptr}, r2 = {b->keys, b->ids, nullptr, nullptr};
   int rc = count_sorted(w, a->L, r1, a->n, r2, b->n, (const i32*)grp1, (const i32*)grp2, nb, how, closed,
-                        (const i64*)own_range, plan, (cudaStream_t)stream);
+                        (const i64*)own_range, plan, (cudaStream_t)stream, a->pmax_ready ? a->pmax : nullptr,
+                        b->pmax_ready ? b->pmax : nullptr);
   if (rc == BF_OK) {
     if (n_rows_out) *n_rows_out = plan->n_rows;
     if (n_pairs_out) *n_pairs_out = plan->n_pairs;

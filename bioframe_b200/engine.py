@@ -278,6 +278,16 @@ class SortedSet:
             self.ids = torch.empty(0, dtype=torch.int32, device=device)
 
 
+def set_runmax(sorted_set):
+    """Running maximum of end' of a prepared set, computed once into the set's own store (bf_sorted_set_runmax)
+    and reused by every `overlap_prepared` that needs it (left / outer joins: the unpaired-row test)."""
+    _require_cuda()
+    with _on(sorted_set.device):
+        _lib.check(_lib.lib().bf_sorted_set_runmax(C.byref(sorted_set.struct), _stream_ptr(sorted_set.device)),
+                   "bf_sorted_set_runmax")
+    return sorted_set
+
+
 def measure_extent(grp, start, end, n_groups, device=None):
     """Extent of one set as the mergeable host record of the C ABI (bf_extent_measure).
     -> (int64 numpy words, presorted flag).  Merge records with `np.maximum` / all_reduce(MAX)."""

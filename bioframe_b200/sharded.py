@@ -242,8 +242,10 @@ def overlap_range_sharded(grp1, start1, end1, n_own, own_range, grp2, start2, en
         if world > 1:
             handles.append(dist.broadcast(set2.keys, src=src, group=group, async_op=True))
             handles.append(dist.broadcast(set2.ids, src=src, group=group, async_op=True))
-    for h in handles:
-        h.wait()
+        for h in handles:
+            h.wait()  # the SIDE stream waits for the sorted targets to arrive; the main stream keeps sorting queries
+        if how == "left" and hasattr(engine, "set_runmax"):
+            engine.set_runmax(set2)  # the unpaired-row test reads the running maximum of the targets' ends: once per set
     if side is not None:
         main.wait_stream(side)  # the target store is persistent (SetStores): the streams are ordered here and by
         #                         `inputs_ready` of the next call, the allocator is not involved

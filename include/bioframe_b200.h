@@ -128,6 +128,10 @@ int bf_overlap_adopt_set(const int64_t* extent_words, int64_t n, int32_t n_group
                          void* stream, bf_sorted_set* set_out);
 /* device pointers of the set's sorted keys (uint64[n]) and row ids (uint32[n]): what a broadcast moves */
 int bf_sorted_set_buffers(const bf_sorted_set* set, void** keys_out, void** ids_out, int64_t* n_out);
+/* optional, once per prepared set (after its buffers hold the sorted rows): the running maximum of end' in sorted
+ * order (np.maximum.accumulate of the unpaired-row test) is computed into the set's own
+ * store and reused by every bf_overlap_count_prepared that needs it, instead of once per call */
+int bf_sorted_set_runmax(bf_sorted_set* set, void* stream);
 size_t bf_overlap_prepared_workspace_bytes(int64_t n1, int64_t n2, int32_t n_groups, int32_t how);
 /* grp1 / grp2: the group codes of the kept side(s) (how left: grp1), NULL otherwise or when n_groups == 1 */
 int bf_overlap_count_prepared(const bf_sorted_set* set1, const bf_sorted_set* set2, const int32_t* grp1,

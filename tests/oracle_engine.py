@@ -155,6 +155,10 @@ def adopt_set(words, n, n_groups, grp=None, device=None, slot=None):
     return _DoubleSet(np.zeros((int(n), 3), np.int64), n_groups)
 
 
+def set_runmax(sorted_set):
+    return sorted_set
+
+
 def overlap_prepared(set1, set2, how="inner", closed=False, own_range=None, row_offset1=0, row_offset2=0,
                      n_own1=None, halo_ids=None, want_group_counts=False):
     import torch
