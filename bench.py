@@ -877,7 +877,10 @@ def main():
         side.wait_stream(main_s)
         handles = []
         with torch.cuda.stream(side):
-            set2 = engine.prepare_set(words, dt[0], dt[1], dt[2], N_GROUPS, presorted=pres2) if rank == 0 else engine.adopt_set(words, n2, N_GROUPS)
+            # persistent stores (engine.SetStores): a fresh multi-GB allocation per step that is used on two streams
+            # goes back to the allocator through record_stream and costs a cudaMalloc every step
+            set2 = (engine.prepare_set(words, dt[0], dt[1], dt[2], N_GROUPS, presorted=pres2, slot="cfg4.targets") if rank == 0
+                    else engine.adopt_set(words, n2, N_GROUPS, slot="cfg4.targets"))
             if world > 1:
                 handles = [dist.broadcast(set2.keys, src=0, async_op=True), dist.broadcast(set2.ids, src=0, async_op=True)]
             for h in handles:
@@ -887,10 +890,9 @@ def main():
         pairs = rows = 0
         for c, ch in enumerate(chunk_plan):
             sl = slice(ch["lo"], ch["h_hi"])
-            set1 = engine.prepare_set(words, dq[0][sl], dq[1][sl], dq[2][sl], N_GROUPS, presorted=pres)
+            set1 = engine.prepare_set(words, dq[0][sl], dq[1][sl], dq[2][sl], N_GROUPS, presorted=pres, slot="cfg4.queries")
             if c == 0:
                 main_s.wait_stream(side)
-                set2.store.record_stream(main_s)
             n_own = ch["hi"] - ch["lo"]
             local_halo = ch["h_hi"] - ch["hi"]
             hid = None
