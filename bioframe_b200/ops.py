@@ -190,24 +190,22 @@ def _rows_to_host(t):
 # --------------------------------------------------------------------------
 # overlap
 # --------------------------------------------------------------------------
-def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _group_order=None, _sort_pairs=False,
-                     _coords=False, _device_rows=None):
-    """Integer row positions of overlapping pairs, -1 where a kept row has no
-    partner.  Mirrors ops._overlap_intidxs (ops.py:242-338): groups are
-    (chrom, *on); the group blocks come in the iteration order of
-    `set.union(set(groups1), set(groups2))` exactly as in the reference
-    (ops.py:289,301), each block = pairs, unpaired-left, unpaired-right."""
+def _encode_frames(df1, df2, cols1=None, cols2=None, on=None, _group_order=None, _device=True):
+    """The two frames as the arrays the engine takes: group rank per row (int32; position of the row's
+    (chrom, *on) group in the reference's visiting order, ops.py:287-301) and int64 coordinates.
+    -> (g1, s1, e1, g2, s2, e2, n_groups, order); `order` is the list of group keys in visiting order (the order
+    of the union set, which follows the process's hash seed for strings: a multi-process caller fixes it by
+    passing one rank's `order` to the others as _group_order).  _device=False keeps the ranks on the host."""
     ck1, sk1, ek1 = _get_default_colnames() if cols1 is None else cols1
     ck2, sk2, ek2 = _get_default_colnames() if cols2 is None else cols2
     _verify_columns(df1, [ck1, sk1, ek1])
     _verify_columns(df2, [ck2, sk2, ek2])
-    t0 = _now()
     by1, by2 = [ck1], [ck2]
     if on is not None:
         by1 = by1 + list(on)
         by2 = by2 + list(on)
 
-    fast = _categorical_keys_on_device(df1, by1, df2, by2)
+    fast = _categorical_keys_on_device(df1, by1, df2, by2) if _device else None
     if fast is not None:
         (dev1, keys1, slots1), (dev2, keys2, slots2) = fast
     else:
@@ -248,6 +246,18 @@ def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _gro
         g1 = ranks_of(codes1, keys1, rank1) if len(df1) else np.empty(0, np.int32)
         g2 = ranks_of(codes2, keys2, rank2) if len(df2) else np.empty(0, np.int32)
     s1, e1, s2, e2 = _int64_coords(df1, sk1), _int64_coords(df1, ek1), _int64_coords(df2, sk2), _int64_coords(df2, ek2)
+    return g1, s1, e1, g2, s2, e2, n_groups, order
+
+
+def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _group_order=None, _sort_pairs=False,
+                     _coords=False, _device_rows=None):
+    """Integer row positions of overlapping pairs, -1 where a kept row has no
+    partner.  Mirrors ops._overlap_intidxs (ops.py:242-338): groups are
+    (chrom, *on); the group blocks come in the iteration order of
+    `set.union(set(groups1), set(groups2))` exactly as in the reference
+    (ops.py:289,301), each block = pairs, unpaired-left, unpaired-right."""
+    t0 = _now()
+    g1, s1, e1, g2, s2, e2, n_groups, _order = _encode_frames(df1, df2, cols1, cols2, on, _group_order)
     t0 = _tick("encode_groups", t0)
     if _coords or _PROFILE is not None:
         # the coordinates go to the device once: the overlap call and the coordinate gather share them

@@ -349,3 +349,61 @@ def assemble_host(parts, counts_all):
                     out1[dst[r, g, t]:dst[r, g, t] + k] = a[src[r, g, t]:src[r, g, t] + k]
                     out2[dst[r, g, t]:dst[r, g, t] + k] = b[src[r, g, t]:src[r, g, t] + k]
     return out1, out2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# frame level
+
+
+def overlap_intidxs_frames(df1, df2, how="left", cols1=None, cols2=None, on=None, group=None, engine=None, gather=True):
+    """`bioframe.ops._overlap_intidxs(df1, df2, how)` (ops.py:242-338) over the ranks of a process group: every
+    rank holds the same two frames (df2 is only read on rank 0: its sorted keys reach the others by broadcast),
+    takes the queries of its (chrom, start) range + halo, and -- with gather=True -- every rank returns the whole
+    result in the reference's row order (events1, events2 as int64 numpy arrays); with gather=False only this
+    rank's rows, their per-group segment sizes and the sizes of all ranks, for a caller that keeps the result
+    distributed.  how='inner' / 'left'.
+
+    The frames must be the same on every rank, and inside every (chrom, *on) group the starts of df1 must ascend in
+    row order -- any frame sorted by chromosome and start, whatever the chromosome order -- because the unpaired rows
+    of a group come in row order (ops.py:319-322) and shard order has to be row order for that (ValueError
+    otherwise).  The visiting order of the groups follows the string hash seed of the process (set.union,
+    ops.py:289): rank 0 fixes it for everyone."""
+    from . import ops
+
+    if engine is None:
+        from . import engine as engine
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    # group ranks on the host (the shard planner reads them); rank 0's visiting order for everyone
+    enc = ops._encode_frames(df1, df2, cols1, cols2, on, _device=False)
+    if world > 1:
+        box = [enc[7] if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        if rank != 0:
+            enc = ops._encode_frames(df1, df2, cols1, cols2, on, _group_order=box[0], _device=False)
+    g1, s1, e1, g2, s2, e2, n_groups, _ = enc
+    # the queries in (group rank, start) order: a stable sort by rank is enough when the starts of every group
+    # already ascend in row order (plan_range_shards checks it)
+    perm = np.argsort(g1, kind="stable")
+    shards = plan_range_shards(g1[perm], s1[perm], world, g2, s2, e2, n_groups)
+    sh = shards[rank]
+    n_own = sh["hi"] - sh["lo"]
+    rows = perm[np.concatenate([np.arange(sh["lo"], sh["hi"]), sh["halo"]])]  # frame rows of this shard, halo last
+    use_cuda = torch.cuda.is_available() and getattr(engine, "__name__", "").endswith("engine") and hasattr(engine, "Workspace")
+    put = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()) if use_cuda else (lambda a: a)
+    targets = (put(g2), put(s2), put(e2)) if rank == 0 else (None, None, None)
+    ev1, ev2, _n_pairs, counts = overlap_range_sharded(
+        put(g1[rows]), put(s1[rows]), put(e1[rows]), n_own, sh["own_range"], *targets, n_groups, how=how,
+        halo_ids=put(np.arange(n_own, len(rows), dtype=np.int64)), engine=engine, group=group, n2=len(s2))
+    host = lambda t: t.cpu().numpy() if hasattr(t, "cpu") else np.asarray(t)  # noqa: E731
+    ev1, ev2 = host(ev1), host(ev2)
+    ev1 = np.where(ev1 >= 0, rows[np.maximum(ev1, 0)], -1) if len(rows) else ev1  # shard-local -> frame row numbers
+    counts_all = gather_group_counts(counts, device=("cuda" if use_cuda else None), group=group)
+    if not gather:
+        return ev1, ev2, counts, counts_all
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, (ev1, ev2), group=group)
+    else:
+        parts = [(ev1, ev2)]
+    return assemble_host(parts, counts_all)

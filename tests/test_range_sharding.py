@@ -113,3 +113,56 @@ def test_world2_gloo_broadcast_of_sorted_targets(tmp_path):
     q, t = _sets(5)
     w1, w2 = oo.overlap_intidxs_coded(*q, *t, NB, how="left")
     assert np.array_equal(a, w1) and np.array_equal(b, w2)
+
+
+def _frame_worker(rank, world, port, out_dir):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    import pandas as pd
+
+    import oracle_engine
+    from bioframe_b200 import sharded
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        df1, df2 = _frames()
+        a, b = sharded.overlap_intidxs_frames(df1, df2, how="left", engine=oracle_engine)
+        np.savez(os.path.join(out_dir, f"f{rank}.npz"), a=a, b=b)
+    finally:
+        dist.destroy_process_group()
+
+
+def _frames():
+    import pandas as pd
+
+    q, t = _sets(8, n1=2500, n2=600)
+    names = np.array(["chr1", "chr10", "chr2", "chrX", "chrY"], dtype=object)  # sorted like the chromosome column
+    df1 = pd.DataFrame({"chrom": names[q[0]], "start": q[1], "end": q[2]})
+    df2 = pd.DataFrame({"chrom": names[t[0]], "start": t[1], "end": t[2]})
+    return df1, df2
+
+
+def test_frame_level_sharded_overlap_world2_gloo(tmp_path):
+    """DataFrames in, the reference's `_overlap_intidxs` rows out, from two ranks: every rank returns the whole
+    result; it must be a valid reference result for SOME visiting order of the chromosome blocks (the order follows
+    the hash seed of rank 0's process), so the rows are compared block by block with the single-process glue."""
+    import oracle_engine
+    from bioframe_b200 import ops
+
+    world = 2
+    mp.spawn(_frame_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [np.load(os.path.join(tmp_path, f"f{r}.npz")) for r in range(world)]
+    assert np.array_equal(res[0]["a"], res[1]["a"]) and np.array_equal(res[0]["b"], res[1]["b"])
+    df1, df2 = _frames()
+    saved = ops._engine
+    ops._engine = oracle_engine
+    try:
+        w1, w2 = ops._overlap_intidxs(df1, df2, how="left")
+    finally:
+        ops._engine = saved
+    a, b = res[0]["a"], res[0]["b"]
+    assert len(a) == len(w1)
+    chrom = df1["chrom"].to_numpy()
+    for c in np.unique(chrom):  # the block of every chromosome, rows in the same order
+        m_got, m_want = chrom[a] == c, chrom[w1] == c
+        assert np.array_equal(a[m_got], w1[m_want]) and np.array_equal(b[m_got], w2[m_want]), c
