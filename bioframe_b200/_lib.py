@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libbioframe_b200.so")
+# BIOFRAME_B200_LIB: another build of the same sources (the range-checked one, build.py --checked); never a fallback
+LIB_PATH = os.environ.get("BIOFRAME_B200_LIB") or os.path.join(_PKG, "libbioframe_b200.so")
 
 BF_OK = 0
 ERRORS = {

@@ -30,9 +30,13 @@ def sources():
 
 
 def stale():
-    if not os.path.exists(LIB):
+    return _stale(LIB)
+
+
+def _stale(lib):
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -45,15 +49,26 @@ def _run(cmd):
     return proc.stderr
 
 
-def build(force=False, verbose=False):
-    """One nvcc -c per translation unit (in parallel), then one link."""
-    if not force and not stale():
+LIB_CHECKED = os.path.join(PKG, "libbioframe_b200_checked.so")
+
+
+def build(force=False, verbose=False, checked=False):
+    """One nvcc -c per translation unit (in parallel), then one link.
+    checked=True: the same sources with -DBF_CHECKED (device-side range checks that trap, common.cuh) into
+    libbioframe_b200_checked.so; loaded instead of the product library when BIOFRAME_B200_LIB points to it."""
+    if checked:
+        return _build(LIB_CHECKED, os.path.join(PKG, "build_checked"), ["-DBF_CHECKED"], force, verbose)
+    return _build(LIB, OBJ_DIR, [], force, verbose)
+
+
+def _build(LIB, OBJ_DIR, defines, force, verbose):
+    if not force and os.path.exists(LIB) and not _stale(LIB):
         return LIB
     from concurrent.futures import ThreadPoolExecutor
 
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(OBJ_DIR, exist_ok=True)
-    extra = ["-Xptxas=-v"] if verbose else []
+    extra = (["-Xptxas=-v"] if verbose else []) + list(defines)
     jobs = []
     for src in sources():
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
@@ -67,4 +82,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, checked="--checked" in sys.argv))

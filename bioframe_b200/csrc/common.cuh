@@ -21,6 +21,22 @@ typedef unsigned char u8;
 #define BF_ERR_GROUP -5     // group code outside [0, n_groups)
 #define BF_ERR_STATE -6     // emit called on a plan that did not complete count
 
+// Checked build (python -m bioframe_b200.build --checked -> libbioframe_b200_checked.so): every index the kernels
+// compute for a global load or store outside plain "i < n" loops is range-checked on the device and the kernel
+// traps on a violation (the launch then fails with a CUDA error and the test with it).  compute-sanitizer is
+// closed on the GPU pool; tests/test_gpu_checked_build.py runs the fuzz / edge / sharding cases on this build.
+#ifdef BF_CHECKED
+#define BF_DEVICE_CHECK(cond)              \
+  do {                                     \
+    if (!(cond)) {                         \
+      printf("BF_DEVICE_CHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); \
+      __trap();                            \
+    }                                      \
+  } while (0)
+#else
+#define BF_DEVICE_CHECK(cond) ((void)0)
+#endif
+
 namespace bf {
 
 void set_error(const char* fmt, ...);

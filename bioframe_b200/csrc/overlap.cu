@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(SC_THREADS, 6)
         lo = unstaged_lo<B_SIDE>(other, br_lo, br_hi, xs, L);
         hi = gallop_hi(other, lo, m, xe, closed, L);
       }
+      BF_DEVICE_CHECK(lo >= 0 && lo <= hi && hi <= m);
       cnt[j] = (u32)(hi - lo);
       lo32[j] = (u32)lo;
     }
@@ -550,7 +551,8 @@ __global__ void __launch_bounds__(EM_THREADS, 8)
                       const u32* __restrict__ owner_id, const u32* __restrict__ other_id, i64 total,
                       i64 block0, const i64* __restrict__ part, const i32* __restrict__ pgrp,
                       const i64* __restrict__ cum, const i64* __restrict__ delta, i32 nb, i64 off1, i64 off2,
-                      u32 n_own1, const i64* __restrict__ halo_ids, i64* __restrict__ ev1, i64* __restrict__ ev2) {
+                      u32 n_own1, const i64* __restrict__ halo_ids, i64 n_other, i64 n_rows, i64* __restrict__ ev1,
+                      i64* __restrict__ ev2) {
   __shared__ EmitItem s_item[EM_TILE + 2];
   // global row number of a set-1 row listed as a partner (B side only: owners of the A side are never halo rows)
   auto row1 = [&](u32 id) -> i64 { return id < n_own1 ? (i64)id + off1 : halo_ids[id - n_own1]; };
@@ -660,12 +662,14 @@ __global__ void __launch_bounds__(EM_THREADS, 8)
     // to even output rows (16-byte aligned addresses): when the block's first row is odd, slot 0 is a
     // single that thread 0 writes on its own.
     const i64 row0 = t0 + delta_lo;
+    BF_DEVICE_CHECK(row0 >= 0 && row0 + nout <= n_rows);
     i64* const out1 = ev1 + row0;
     i64* const out2 = ev2 + row0;
     const i32 par = (i32)(row0 & 1);
     auto slot = [&](i32 x, u32& own, u32& oth) {  // x clamped to a valid slot by the caller
       const EmitItem it = s_item[s_owner[EM_PAD(x)]];
       own = it.id;
+      BF_DEVICE_CHECK((i64)(u32)(it.src + (u32)x) < n_other && (i64)s_owner[EM_PAD(x)] < nitems);
       oth = other_id[it.src + (u32)x];
     };
     if (par && tid == 0) {
@@ -708,9 +712,11 @@ __global__ void __launch_bounds__(EM_THREADS, 8)
       const i32 x = h * EM_THREADS + (i32)tid;
       if (x < nout) {
         const EmitItem it = s_item[s_owner[EM_PAD(x)]];
+        BF_DEVICE_CHECK((i64)(u32)(it.src + (u32)x) < n_other);
         const u32 own = it.id, oth = other_id[it.src + (u32)x];
         const i64 t = t0 + x;
         const i64 row = t + delta[group_of(t, c_lo, (i64)c_hi + 1)];
+        BF_DEVICE_CHECK(row >= 0 && row < n_rows);
         ev1[row] = B_SIDE ? row1(oth) : (i64)own + off1;
         ev2[row] = (B_SIDE ? (i64)own : (i64)oth) + off2;
       }
@@ -807,6 +813,7 @@ __global__ void __launch_bounds__(256) emit_unpaired_kernel(const u64* __restric
   u32 c = (u32)(k >> 32);
   i64 row = (i64)(k & 0xffffffffull);
   i64 out = ubase[c] + (u - ustart[c]);
+  BF_DEVICE_CHECK(out >= 0);
   ev1[out] = SECOND ? -1 : row + row_off;
   ev2[out] = SECOND ? row + row_off : -1;
 }
@@ -1389,13 +1396,13 @@ static int overlap_emit_impl(const OverlapPlan* plan, void* ws_ptr, i64* ev1, i6
         BF_LAUNCH(PC_EMIT, bytes, st,
                   emit_pairs_kernel<false><<<(unsigned)nb_chunk, EM_THREADS, 0, st>>>(
                       scan, sw.lo, n_owner, plan->id1, plan->id2, total, b0, part, pgrp, cum, delta, plan->nb,
-                      plan->row_off1, plan->row_off2, 0xffffffffu, nullptr, ev1, ev2));
+                      plan->row_off1, plan->row_off2, 0xffffffffu, nullptr, plan->n2, plan->n_rows, ev1, ev2));
       } else {
         BF_LAUNCH(PC_EMIT, bytes, st,
                   emit_pairs_kernel<true><<<(unsigned)nb_chunk, EM_THREADS, 0, st>>>(
                       scan, sw.lo, n_owner, plan->id2, plan->id1, total, b0, part, pgrp, cum, delta, plan->nb,
                       plan->row_off1, plan->row_off2, plan->halo_ids ? plan->n_own1 : 0xffffffffu, plan->halo_ids,
-                      ev1, ev2));
+                      plan->n1, plan->n_rows, ev1, ev2));
       }
     }
   }

@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM)
   for (int j = 0; j < RS_IPT; ++j) {
     u32 d = (u32)(key[j] >> shift) & dmask;
     u32 p = s_tbase[d] + my_cnt[d] + lpos[j];
+    BF_DEVICE_CHECK(p < (u32)RS_TILE);
     lpos[j] = (u16)p;
     s_keys[p] = key[j];
   }
@@ -319,6 +320,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM)
       u64 k = s_keys[idx];
       u32 d = (u32)(k >> shift) & dmask;
       u64 dst = s_gofs[d] + idx;
+      BF_DEVICE_CHECK(dst < n);
       kout[dst] = k;
       if (HAS_VAL) vout[dst] = s_vals[idx];
     }

@@ -150,6 +150,7 @@ __device__ __forceinline__ u32 run_scan_tile(u64* __restrict__ keys, u32* __rest
     if (start < RUN_HALO || start >= RUN_HALO + SC_TILE) continue;  // the run belongs to another tile
     if (rank != back) {  // the row moves
       const u32 slot = atomicAdd(s_nmove, 1u);
+      BF_DEVICE_CHECK(slot < (u32)RUN_MOVES && start + rank < (u32)RUN_STAGED);
       RunMove m;
       m.id = ids[base + r];
       m.from = (u16)i;
@@ -163,6 +164,7 @@ __device__ __forceinline__ u32 run_scan_tile(u64* __restrict__ keys, u32* __rest
     for (u32 x = tid; x < nm; x += SC_THREADS) {
       const RunMove m = s_move[x];
       const u64 at = base + m.to - RUN_HALO;  // >= base: the run starts in this tile
+      BF_DEVICE_CHECK(at >= base && at < n && m.from < RUN_STAGED);
       keys[at] = s_k[m.from];
       ids[at] = m.id;
     }
@@ -217,7 +219,7 @@ static __global__ void __launch_bounds__(256) tie_scatter_kernel(const u64* __re
   const u64 n = *nT;
   for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (u64)gridDim.x * blockDim.x) {
     const u32 p = tpos[t];
-    keys[p] = tkeys[t];
+    keys[p] = tkeys[t];  // p was recorded from a valid slot by long_run_gather_kernel
     ids[p] = tids[t];
   }
 }
