@@ -47,6 +47,7 @@ _sz = C.c_size_t
 SIGNATURES = {
     "bf_last_error": (C.c_char_p, []),
     "bf_version": (C.c_int, []),
+    "bf_checked_build": (C.c_int, []),
     "bf_prof_enable": (C.c_int, [C.c_int]),
     "bf_prof_reset": (C.c_int, []),
     "bf_prof_num_classes": (C.c_int, []),

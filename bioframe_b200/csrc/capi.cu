@@ -79,7 +79,14 @@ static void drain() {
 
 extern "C" {
 const char* bf_last_error(void) { return bf::g_error; }
-int bf_version(void) { return 100; }
+int bf_version(void) { return 200; }
+int bf_checked_build(void) {
+#ifdef BF_CHECKED
+  return 1;
+#else
+  return 0;
+#endif
+}
 
 int bf_prof_enable(int on) {
   bf::drain();

@@ -60,6 +60,8 @@ typedef struct bf_plan {
 
 const char* bf_last_error(void);
 int bf_version(void);
+/* 1 for the range-checked build (-DBF_CHECKED: device-side index checks that trap), 0 for the product build */
+int bf_checked_build(void);
 
 /* ---- launch counter and CUDA-event profiler (measurement only; used by
  * bench.py for `gpu_launches` and the per-kernel roofline).  Launches are

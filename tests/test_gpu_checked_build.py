@@ -24,6 +24,9 @@ def test_suites_pass_on_the_range_checked_build(tmp_path):
 
         build.build(checked=True)
     env = dict(os.environ, BIOFRAME_B200_LIB=lib, PYTHONDONTWRITEBYTECODE="1")
+    which = subprocess.run([sys.executable, "-c", "from bioframe_b200 import _lib; print(_lib.lib().bf_checked_build())"],
+                           cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert which.stdout.strip().endswith("1"), which.stdout + which.stderr  # the subprocesses really load the checked build
     cmd = [sys.executable, "-m", "pytest", *[os.path.join(ROOT, "tests", f) for f in FILES], "-m", "gpu", "-q", "-x",
            "-p", "no:cacheprovider", "--no-header"]
     proc = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
