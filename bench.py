@@ -666,6 +666,42 @@ def frame_leg(args):
             entry["note"] = "rows compared after sorting both frames: the reference's chromosome-block order follows the string hash seed"
         out[tag] = entry
         del df1, df2, got
+    # the other public calls of BASELINE.json's configs at a size the reference finishes in seconds (its closest needs
+    # 21 s at 1e7 x 1e6, its coverage 17 s: SURVEY.md 6): frames in, frames out, results compared
+    if bf is not None:
+        n1, n2 = 3_000_000, 300_000
+        q = synth.make_intervals(n1, 1, "geom1k")
+        t = synth.make_tie_free(n2, 2, "geom1k")  # closest among equal ends / starts is undefined in the reference
+        df1, df2 = reference_frame(*q), reference_frame(*t)
+        heavy = reference_frame(*synth.make_intervals(n1, 3, "pareto"))
+        other = {}
+
+        def same(a, b, canon=False):
+            try:
+                if canon:
+                    key = list(a.columns)
+                    a = a.sort_values(key, kind="stable").reset_index(drop=True)
+                    b = b.sort_values(key, kind="stable").reset_index(drop=True)
+                pd.testing.assert_frame_equal(a, b)
+                return True
+            except AssertionError:
+                return False
+
+        for name, ours_fn, ref_fn, canon in (
+            ("closest_k1", lambda: ours.closest(df1, df2, k=1), lambda: bf.closest(df1, df2, k=1), True),
+            ("cluster", lambda: ours.cluster(heavy), lambda: bf.cluster(heavy), False),
+            ("merge", lambda: ours.merge(heavy), lambda: bf.merge(heavy), False),
+            ("coverage", lambda: ours.coverage(df1, df2), lambda: bf.coverage(df1, df2), False),
+        ):
+            ours_fn()
+            t_ours, got = wall(ours_fn, 2)
+            t_ref, want = wall(ref_fn, 1)
+            other[name] = {"bioframe_b200_ms": t_ours * 1e3, "reference_ms": t_ref * 1e3, "speedup": t_ref / t_ours,
+                           "frames_equal_to_reference": same(got, want, canon)}
+            del got, want
+        out["other_ops_3e6x3e5"] = {"sizes": f"{n1} queries (geom 1kb; cluster / merge: Pareto lengths) x {n2} tie-free targets, "
+                                             "categorical chrom", **other}
+        del df1, df2, heavy
     # the seam at the benchmark size: DataFrames (categorical chrom) -> int64 numpy index arrays on the host
     q, t = workload(args.n1, args.n2, 0)
     df1, df2 = reference_frame(*q), reference_frame(*t)
