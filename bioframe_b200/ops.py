@@ -691,11 +691,18 @@ def _cluster_table(df, res, keys, group_list, sk, ek):
     cgrp = _to_host(res["cgrp"]).astype(np.int64)
     out = {}
     for pos, col in enumerate(group_list):
-        if len(group_list) == 1:
-            values = [keys[g] for g in cgrp]
+        # the key of every cluster's group, vectorised: the few distinct keys are looked up by group code (a Python
+        # loop over a million clusters cost more than the clustering itself -- "storing chromosome names causes a
+        # 2x slowdown", ops.py:660)
+        per_group = [k if len(group_list) == 1 else k[pos] for k in keys]
+        dtype = df[col].dtype
+        if isinstance(dtype, pd.CategoricalDtype) and len(per_group):
+            codes = dtype.categories.get_indexer(per_group)
+            out[col] = pd.Series(pd.Categorical.from_codes(codes[cgrp], dtype=dtype))
         else:
-            values = [keys[g][pos] for g in cgrp]
-        out[col] = pd.Series(values, dtype=df[col].dtype)
+            table = np.empty(len(per_group), dtype=object)
+            table[:] = per_group
+            out[col] = pd.Series(table[cgrp] if len(per_group) else [], dtype=dtype)
     out[sk] = _to_host(res["cstart"])
     out[ek] = _to_host(res["cend"])
     out["n_intervals"] = _to_host(res["ccount"])
