@@ -176,3 +176,61 @@ def test_cfg3_coverage_1e8_x_1e7_chromosomes(cfg3):
         w1, _, _ = refcheck.overlap(None, s1[r1], e1[r1], None, s2[r2], e2[r2], 1, "inner")
         same(cnt[r1], np.bincount(w1, minlength=len(r1)).astype(np.int64))
     print(f"cfg3 coverage checked against: {kind}")
+
+
+def test_closest_variants_1e6_row_order():
+    """the closest options of the north star (k, ignore_overlaps / upstream / downstream, direction_col) at 1e6 x
+    2e5 on tie-free targets, whole result against the reference's `_closest_intidxs`"""
+    import pandas as pd
+
+    from bioframe_b200 import engine, synth
+
+    q = synth.make_intervals(1_000_000, 11, "geom1k")
+    t = synth.make_tie_free(200_000, 12, "geom1k")
+    d = up(*q, *t)
+    rng = np.random.default_rng(3)
+    strand = rng.choice(np.array(["+", "-"], dtype=object), len(q[1]))
+    along = strand != "-"
+    for kw in (dict(k=2), dict(k=1, ignore_overlaps=True), dict(k=2, ignore_upstream=True), dict(k=3, ignore_downstream=True)):
+        ev1, ev2, _ = engine.closest_intidxs(*d, NB, **kw)
+        w1, w2, kind = refcheck.closest(*q, *t, NB, **kw)
+        same(ev1, w1), same(ev2, w2)
+    if refcheck.have_reference():  # direction_col: upstream / downstream follow the query's strand (ops.py:983-1013)
+        from conftest import import_reference
+
+        bf = import_reference()
+        df1 = pd.DataFrame({"chrom": q[0].astype(np.int64), "start": q[1], "end": q[2], "strand": strand})
+        df2 = pd.DataFrame({"chrom": t[0].astype(np.int64), "start": t[1], "end": t[2]})
+        for kw in (dict(k=2, ignore_upstream=True), dict(k=1, ignore_downstream=True, ignore_overlaps=True)):
+            w1, w2 = bf.ops._closest_intidxs(df1, df2, direction_col="strand", **kw)
+            ev1, ev2, _ = engine.closest_intidxs(*d, NB, along=torch.from_numpy(along).to(dev()), **kw)
+            same(ev1, np.asarray(w1, dtype=np.int64)), same(ev2, np.asarray(w2, dtype=np.int64))
+
+
+def test_count_subtract_complement_1e7_against_reference():
+    """count_overlaps, subtract and complement at 1e7 x 1e6: chr1 and chr21 against the reference's
+    public functions on those chromosomes"""
+    import pandas as pd
+
+    from bioframe_b200 import engine, synth
+
+    if not refcheck.have_reference():
+        pytest.skip("needs the reference")
+    from conftest import import_reference
+
+    bf = import_reference()
+    q = synth.make_intervals(10_000_000, 21, "geom2k")
+    t = synth.make_peak_targets(1_000_000, 22, n_hotspots=20_000)
+    d = up(*q, *t)
+    cnt = engine.count_overlaps(*d, NB).cpu().numpy()
+    row, ps, pe, sub = (x.cpu().numpy() for x in engine.subtract(*d, NB))
+    for c in CHECK_CHROMS:
+        r1, r2 = np.flatnonzero(q[0] == c), np.flatnonzero(t[0] == c)
+        df1 = pd.DataFrame({"chrom": "c", "start": q[1][r1], "end": q[2][r1]})
+        df2 = pd.DataFrame({"chrom": "c", "start": t[1][r2], "end": t[2][r2]})
+        same(cnt[r1], bf.count_overlaps(df1, df2)["count"].to_numpy().astype(np.int64))
+        want = bf.subtract(df1, df2, return_index=True)  # rows by (query row, piece), ops.py:1318-1330
+        m = q[0][row] == c
+        same(row[m], r1[want["index"].to_numpy().astype(np.int64)])
+        same(ps[m], want["start"].to_numpy().astype(np.int64)), same(pe[m], want["end"].to_numpy().astype(np.int64))
+        same(sub[m], want["sub_index_"].to_numpy().astype(np.int64))
