@@ -891,6 +891,7 @@ __global__ void __launch_bounds__(OE_THREADS)
       } else {
         u32 k = 0;
         gather([&](u32 id) { s_raw[at + k++] = id; }, k);
+        BF_DEVICE_CHECK(k == c && at + c <= (u32)OE_CAP);  // the walk found exactly the partners the count phase counted
         for (u32 i = 0; i < c; ++i) s_own[at + i] = (u8)tid;
       }
     }
@@ -899,6 +900,7 @@ __global__ void __launch_bounds__(OE_THREADS)
     for (u32 x = tid; x < seg_rows; x += OE_THREADS) {
       const u32 o = s_own[x];
       const u32 a = s_rel[o] - first_row, b = s_rel[o + 1] - first_row;  // the query's rows: [a, b)
+      BF_DEVICE_CHECK(o >= qb && o < qe && a <= x && x < b && b <= seg_rows);
       const u32 v = s_raw[x];
       u32 rank = 0;
       for (u32 j = a; j < b; ++j) rank += s_raw[j] < v;

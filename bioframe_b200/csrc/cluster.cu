@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(SC_THREADS, 6)
       const u64 key = s_k(r + 1);
       if (bmask & (1u << j)) ++seen;
       const u64 id = seen - 1;
+      BF_DEVICE_CHECK(seen >= 1 && id <= k);  // a row's cluster ordinal never exceeds its sorted position
       const u32 rank = rk[j + 1];
       const u64 gbase = L.goff[rank];
       const u64 run = rm[j] > before ? rm[j] : before;  // running max including this row

@@ -14,7 +14,8 @@ from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
 
-FILES = ["test_gpu_fuzz.py", "test_gpu_edge.py", "test_gpu_prepared.py", "test_gpu_stress.py", "test_gpu_overlap.py"]
+FILES = ["test_gpu_fuzz.py", "test_gpu_edge.py", "test_gpu_prepared.py", "test_gpu_stress.py", "test_gpu_overlap.py",
+         "test_gpu_cluster.py", "test_gpu_closest.py"]
 
 
 def test_suites_pass_on_the_range_checked_build(tmp_path):
