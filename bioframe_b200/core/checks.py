@@ -2,6 +2,7 @@
 `bioframe.core.checks.is_bedframe` (reference src/bioframe/core/checks.py:20-87)."""
 from __future__ import annotations
 
+import numpy as np
 import pandas as pd
 
 from .specs import _get_default_colnames, _verify_column_dtypes, _verify_columns
@@ -24,8 +25,14 @@ def is_bedframe(df, raise_errors=False, cols=None):
         return fail(TypeError("Invalid bedFrame: Invalid column names"))
     if not _verify_column_dtypes(df, cols=[ck, sk, ek], return_as_bool=True):
         return fail(TypeError("Invalid bedFrame: Invalid column dtypes"))
-    nulls = pd.isnull(df[[ck, sk, ek]])
-    partial = nulls.any(axis=1) & ~nulls.all(axis=1)
+    plain_coords = all(isinstance(df[c].dtype, np.dtype) and df[c].dtype.kind in "iu" for c in (sk, ek))
+    if plain_coords:
+        # plain integer coordinates cannot be null: a null chromosome then IS a partially null row (same verdict as
+        # the row-wise test below, without building a 3-column boolean frame: 50 ms per 1e7 rows)
+        partial = df[ck].isna()
+    else:
+        nulls = pd.isnull(df[[ck, sk, ek]])
+        partial = nulls.any(axis=1) & ~nulls.all(axis=1)
     if partial.any():
         return fail(
             ValueError(
@@ -33,7 +40,7 @@ def is_bedframe(df, raise_errors=False, cols=None):
                 "(if any of chrom, start, end are null, then all must be null)"
             )
         )
-    backwards = (df[ek] - df[sk]) < 0
+    backwards = (df[ek].to_numpy() < df[sk].to_numpy()) if plain_coords else ((df[ek] - df[sk]) < 0)
     if backwards.any():
         return fail(
             ValueError(f"Invalid bedframe: starts exceed ends for {sum(backwards)} intervals")
