@@ -129,3 +129,24 @@ def test_frame_keep_order_general_path_on_cuda_engine(name, general_keep_order_p
 @pytest.mark.parametrize("name", GATHER_CASES)
 def test_frame_with_column_gathers_on_cuda_engine(name, device_assembly):
     _check(name)
+
+
+def test_arrow_string_take_matches_iloc(monkeypatch):
+    """String columns of a large result are taken with pyarrow on several host threads (`_arrow_string_take`):
+    same values and dtype as `iloc` (ops.py:499-508), missing where the position is -1."""
+    import bioframe_b200.ops as ops
+
+    monkeypatch.setattr(ops, "_ARROW_TAKE_THREADS", 3)
+    rng = np.random.default_rng(5)
+    col = pd.Series([f"peak{i:07d}" if i % 11 else None for i in range(50_000)])
+    if not isinstance(col.array, pd.arrays.ArrowStringArray):
+        pytest.skip("string columns are not Arrow-backed in this pandas")
+    for n in (0, 5, (1 << 19) + 77, 3 << 18):
+        positions = rng.integers(-1, len(col), n)
+        got = ops._arrow_string_take(col.array, positions)
+        assert got.dtype == col.dtype and len(got) == n
+        want = col.iloc[np.where(positions < 0, 0, positions)].array
+        want[positions < 0] = None
+        pd.testing.assert_extension_array_equal(got, want)
+    empty = ops._arrow_string_take(col.iloc[:0].array, np.array([-1, -1]))
+    assert empty.isna().all() and len(empty) == 2
