@@ -135,7 +135,9 @@ def _group_keys_shared_na(df, by):
     return codes, keys
 
 
-_DEVICE_ENCODE_MIN_ROWS = 1 << 20
+# measured on the B200 box (profiles/threshold_sweep.py): the device encoding wins from 1e5 rows up (3.4 vs 3.9 ms for a
+# whole 1e5 x 1e5 inner join, 37 vs 52 ms at 1e6 x 1e6)
+_DEVICE_ENCODE_MIN_ROWS = 1 << 16
 
 
 def _categorical_keys_on_device(df1, by1, df2, by2):
@@ -330,8 +332,11 @@ def _suffixed_rows(df, positions, suffix):
 
 
 # Results of this many rows and more are assembled with device-side column gathers (bf_gather_rows): taking
-# 1e8+ rows of a column with numpy costs seconds per column; the device does it at PCIe speed.
-_DEVICE_GATHER_MIN_ROWS = 1 << 22
+# 1e8+ rows of a column with numpy costs seconds per column; the device does it at PCIe speed.  The source columns
+# have to cross PCIe first, so small results stay with pandas: measured (profiles/threshold_sweep.py) a loss at
+# 5.8e4 result rows of 3e5-row frames (4.6 vs 2.5 ms), a gain from 5.8e5 result rows up (27 vs 33 ms; 1e6 x 1e6:
+# 15 vs 31 ms; 1e7 x 1e6: 118 vs 459 ms).
+_DEVICE_GATHER_MIN_ROWS = 1 << 19
 _SAME_WIDTH_INT = {1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}
 
 
