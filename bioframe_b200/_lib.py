@@ -114,6 +114,7 @@ SIGNATURES = {
     "bf_complement_emit": (C.c_int, [C.POINTER(Plan), _p, _p, _p, _p, _p]),
     "bf_download_stage_bytes": (_sz, [_i64]),
     "bf_download_rows": (C.c_int, [_p, _i64, _p, _p, _sz, _p, _sz, _i32, _p]),
+    "bf_download_direct_rows": (_i64, []),
     "bf_bed_scan_workspace_bytes": (_sz, [_i64]),
     "bf_bed_scan": (C.c_int, [_p, _i64, _p, _sz, _p, C.POINTER(_i64)]),
     "bf_bed_parse_workspace_bytes": (_sz, [_i64, _i64]),

@@ -7,8 +7,15 @@
 //   per chunk:  narrow kernel (int64 -> int32, checks the range)  ->  cudaMemcpyAsync to pinned staging  ->
 //               event;  host: wait for the previous chunk's event, widen it into the destination
 //   two device and two pinned staging chunks: the bus carries chunk k + 1 while the host widens chunk k.
+//
+// Hosts differ: on the boxes of the pool the widening of a chunk takes between 1.1x and 5x the time of its copy
+// (profiles/NOTES.md: 191 ... 699 ms for the same 1.75e9 row numbers).  When the destination is page-locked the
+// call therefore measures both on its first chunks and, if the host threads are the slower side, hands the TAIL of
+// the array to a second lane: plain int64 copies straight into the destination on a second stream (8 bytes per
+// row over the bus, no host work), sized so that both lanes end together.
 #include <atomic>
 #include <chrono>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 #if defined(__x86_64__)
@@ -134,6 +141,24 @@ struct WidenPool {
   }
 };
 
+// BF_DOWNLOAD_DIRECT=0: never use the direct lane; =1: always split (tests); unset: decide from the measured times
+enum DirectMode { DIRECT_ADAPTIVE, DIRECT_OFF, DIRECT_FORCE };
+static DirectMode direct_mode() {
+  const char* e = std::getenv("BF_DOWNLOAD_DIRECT");
+  if (!e || !*e) return DIRECT_ADAPTIVE;
+  return e[0] == '0' ? DIRECT_OFF : e[0] == '1' ? DIRECT_FORCE : DIRECT_ADAPTIVE;
+}
+
+static bool page_locked(const void* p, size_t bytes) {
+  cudaPointerAttributes first{}, last{};
+  const bool ok = cudaPointerGetAttributes(&first, p) == cudaSuccess &&
+                  cudaPointerGetAttributes(&last, static_cast<const char*>(p) + bytes - 1) == cudaSuccess;
+  if (!ok) cudaGetLastError();  // an unknown pointer is reported as an error by older drivers: not sticky
+  return ok && first.type == cudaMemoryTypeHost && last.type == cudaMemoryTypeHost;
+}
+
+static thread_local i64 g_direct_rows = 0;  // rows of this thread's last call that took the direct lane
+
 static int download_rows_impl(const i64* dev_src, i64 n, i64* host_dst, void* dev_stage, size_t dev_bytes, void* pinned,
                               size_t pinned_bytes, int threads, cudaStream_t st) {
   if (n < 0 || threads < 1) {
@@ -159,12 +184,17 @@ static int download_rows_impl(const i64* dev_src, i64 n, i64* host_dst, void* de
   i64* bad = reinterpret_cast<i64*>(dev_stage);
   i32* dstage[2] = {reinterpret_cast<i32*>((char*)dev_stage + 256), reinterpret_cast<i32*>((char*)dev_stage + 256) + chunk};
   i32* hstage[2] = {reinterpret_cast<i32*>(pinned), reinterpret_cast<i32*>(pinned) + chunk};
-  cudaEvent_t ev[2];
-  BF_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-  {
-    const cudaError_t e = cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
-    if (e != cudaSuccess) {  // do not leave the first event behind
-      cudaEventDestroy(ev[0]);
+  // ev[]: chunk landed in the pinned stage; tb[]: recorded in front of the chunk's kernel, so that
+  // elapsed(tb, ev) = what the chunk costs on the device + bus side
+  cudaEvent_t ev[2] = {nullptr, nullptr}, tb[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t e = cudaEventCreate(&ev[i]);
+    if (e == cudaSuccess) e = cudaEventCreate(&tb[i]);
+    if (e != cudaSuccess) {  // leave no event behind
+      for (int j = 0; j < 2; ++j) {
+        if (ev[j]) cudaEventDestroy(ev[j]);
+        if (tb[j]) cudaEventDestroy(tb[j]);
+      }
       set_error("bf_download_rows: cudaEventCreate: %s", cudaGetErrorString(e));
       return BF_ERR_CUDA;
     }
@@ -177,29 +207,87 @@ static int download_rows_impl(const i64* dev_src, i64 n, i64* host_dst, void* de
     }
   };
   fail(cudaMemsetAsync(bad, 0, sizeof(i64), st), "memset");
-  const i64 nchunks = ceil_div(n, chunk);
-  auto enqueue = [&](i64 k) {
-    const i64 a = k * chunk, m = n - a < chunk ? n - a : chunk;
+  // Rows [0, next) have been handed to the narrow lane, rows [tail, n) to the direct lane; the lanes meet somewhere.
+  i64 next = 0, tail = n;
+  i64 first_row[2] = {0, 0}, rows_in[2] = {0, 0};
+  auto enqueue = [&](int slot) {
+    const i64 a = next, m = tail - a < chunk ? tail - a : chunk;
+    first_row[slot] = a;
+    rows_in[slot] = m;
+    next = a + m;
+    fail(cudaEventRecord(tb[slot], st), "event");
     prof_pre(PC_GATHER, st);
-    narrow_rows_kernel<<<(unsigned)ceil_div(m, 256 * 4 * 4), 256, 0, st>>>(dev_src + a, m, dstage[k & 1], bad);
+    narrow_rows_kernel<<<(unsigned)ceil_div(m, 256 * 4 * 4), 256, 0, st>>>(dev_src + a, m, dstage[slot], bad);
     fail(cudaGetLastError(), "narrow kernel");
     prof_post(PC_GATHER, st, (u64)(12 * m));
-    fail(cudaMemcpyAsync(hstage[k & 1], dstage[k & 1], (size_t)m * sizeof(i32), cudaMemcpyDeviceToHost, st), "copy");
-    fail(cudaEventRecord(ev[k & 1], st), "event");
+    fail(cudaMemcpyAsync(hstage[slot], dstage[slot], (size_t)m * sizeof(i32), cudaMemcpyDeviceToHost, st), "copy");
+    fail(cudaEventRecord(ev[slot], st), "event");
   };
+  // The direct lane: needs a page-locked destination and enough chunks to measure on.  Per narrow chunk the host
+  // needs widen_ms and the bus copy_ms; what the narrow lane leaves of the bus carries direct slices of `chunk` rows
+  // at 8 instead of 4 bytes per row: (widen / copy - 1) / 2 slices per narrow chunk.  The slices are handed out a
+  // few per chunk, not all at once, so that the lanes share the bus whichever way the copy engines order them.
+  const DirectMode mode = direct_mode();
+  constexpr int kFirstSample = 1, kSamples = 3, kMinChunks = 8;
+  bool undecided = mode != DIRECT_OFF && ceil_div(n, chunk) >= kMinChunks && page_locked(host_dst, (size_t)n * sizeof(i64));
+  cudaStream_t st2 = nullptr;
+  double widen_ms = 0, copy_ms = 0, quota = 0;
+  auto claim_direct = [&](double slices) {
+    quota += slices;
+    while (quota >= 1.0 && tail > next && rc == BF_OK) {
+      const i64 lo = tail - chunk > next ? tail - chunk : next;
+      fail(cudaMemcpyAsync(host_dst + lo, dev_src + lo, (size_t)(tail - lo) * sizeof(i64), cudaMemcpyDeviceToHost, st2),
+           "direct copy");
+      tail = lo;
+      quota -= 1.0;
+    }
+  };
+
   WidenPool pool(n < (1 << 16) ? 1 : threads);
   enqueue(0);
-  for (i64 k = 0; k < nchunks && rc == BF_OK; ++k) {
-    if (k + 1 < nchunks) enqueue(k + 1);  // in flight while chunk k is widened
-    fail(cudaEventSynchronize(ev[k & 1]), "wait");
-    const i64 a = k * chunk, m = n - a < chunk ? n - a : chunk;
-    if (rc == BF_OK) pool.run(hstage[k & 1], host_dst + a, (size_t)m);
+  for (i64 k = 0; rc == BF_OK; ++k) {
+    const int slot = (int)(k & 1);
+    const bool more = next < tail;
+    if (more) enqueue(slot ^ 1);  // in flight while chunk k is widened
+    fail(cudaEventSynchronize(ev[slot]), "wait");
+    if (rc != BF_OK) break;
+    float on_device = 0.f;
+    if (undecided && k >= kFirstSample) fail(cudaEventElapsedTime(&on_device, tb[slot], ev[slot]), "elapsed");
+    const auto w0 = std::chrono::steady_clock::now();
+    pool.run(hstage[slot], host_dst + first_row[slot], (size_t)rows_in[slot]);
+    const double widened = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    if (st2) {
+      // the share of the bus the narrow lane leaves, from its latest widening time
+      const double spare = copy_ms > 0 ? 0.5 * (widened / copy_ms - 1.0) : 1.0;
+      claim_direct(spare < 0 ? 0.0 : spare > 8 ? 8.0 : spare);
+    } else if (undecided && k >= kFirstSample && rc == BF_OK) {
+      widen_ms += widened;
+      copy_ms += on_device;
+      if (k + 1 == kFirstSample + kSamples) {
+        undecided = false;
+        widen_ms /= kSamples;
+        copy_ms /= kSamples;
+        // dev_src is complete: this thread has synchronised with events recorded on `st` behind its producer
+        if (mode == DIRECT_FORCE || widen_ms > 1.25 * copy_ms) {
+          fail(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking), "stream");
+          if (mode == DIRECT_FORCE && widen_ms <= 1.25 * copy_ms) copy_ms = 0;  // tests: one slice per chunk
+        }
+      }
+    }
+    if (!more) break;
   }
+  if (st2) {
+    fail(cudaStreamSynchronize(st2), "direct lane");
+    cudaStreamDestroy(st2);
+  }
+  g_direct_rows = n - tail;
   i64 flag = 0;
   fail(cudaMemcpyAsync(&flag, bad, sizeof(i64), cudaMemcpyDeviceToHost, st), "flag");
   fail(cudaStreamSynchronize(st), "sync");
-  cudaEventDestroy(ev[0]);
-  cudaEventDestroy(ev[1]);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(ev[i]);
+    cudaEventDestroy(tb[i]);
+  }
   if (rc == BF_OK && flag) {
     set_error("bf_download_rows: a value lies outside [-1, 2^31 - 1): not a row number of a set below 2^31 rows");
     return BF_ERR_RANGE;
@@ -214,6 +302,7 @@ size_t bf_download_stage_bytes(int64_t chunk_rows) {
   if (chunk_rows < 64) chunk_rows = 64;
   return 256 + 2 * (size_t)chunk_rows * sizeof(int32_t);
 }
+int64_t bf_download_direct_rows(void) { return bf::g_direct_rows; }
 int bf_download_rows(const int64_t* dev_src, int64_t n, int64_t* host_dst, void* dev_stage, size_t dev_stage_bytes,
                      void* pinned_stage, size_t pinned_bytes, int32_t n_threads, void* stream) {
   return bf::download_rows_impl((const i64*)dev_src, n, (i64*)host_dst, dev_stage, dev_stage_bytes, pinned_stage,

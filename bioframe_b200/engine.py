@@ -83,9 +83,23 @@ def host_threads():
     return max(1, min(8, n - 2))  # the widening is bound by host memory bandwidth well before 8 threads
 
 
+def pinned_rows(n):
+    """A page-locked int64 host array of n values (a numpy view of a pinned torch tensor), for results that are
+    downloaded again and again into the same buffer: `download_rows(t, out=...)` into such an array may use its
+    second, direct lane on hosts whose threads cannot keep up with the bus."""
+    return torch.empty(int(n), dtype=torch.int64, pin_memory=True).numpy()
+
+
+def download_direct_rows():
+    """Rows of this thread's last `download_rows` call that crossed the bus as plain int64 copies (8 instead of 4
+    bytes per row) because the host threads were the slower side."""
+    return int(_lib.lib().bf_download_direct_rows())
+
+
 def download_rows(t, out=None, n_threads=None):
     """int64 CUDA tensor of row numbers (values in [-1, 2^31 - 1)) -> int64 numpy array on the host, crossing PCIe
-    as 4 bytes per value (bf_download_rows).  `out`: optional preallocated contiguous int64 numpy array."""
+    as 4 bytes per value (bf_download_rows).  `out`: optional preallocated contiguous int64 numpy array; when it
+    is page-locked (`pinned_rows`) the library may send the tail of a large result straight into it."""
     import numpy as np
 
     _require_cuda()

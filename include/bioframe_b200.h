@@ -305,8 +305,15 @@ int bf_subtract_emit(const bf_plan* plan, void* ws, int64_t* row_out, int64_t* s
  * chunk is in flight.  dev_src: device int64[n] with every value in [-1, 2^31 - 1), 16-byte aligned (else
  * BF_ERR_RANGE / BF_ERR_ARG); host_dst: ordinary (pageable) host int64[n]; dev_stage: device scratch of
  * bf_download_stage_bytes(chunk_rows) bytes; pinned_stage: page-locked host scratch of at least
- * 8 * chunk_rows bytes.  Synchronises `stream`; returns when host_dst is complete. */
+ * 8 * chunk_rows bytes.  Synchronises `stream`; returns when host_dst is complete.
+ *   When host_dst itself is page-locked and the call spans at least 8 chunks, the call times the widening and the
+ * copy of its first chunks; on a host whose threads are the slower side (the boxes differ by 5x) the tail of the
+ * array then travels as plain int64 copies straight into host_dst on a second stream, a few slices per narrow
+ * chunk, until the two lanes meet -- same result, 8 instead of 4 bytes per row over the bus for that part, no host
+ * work.  Environment BF_DOWNLOAD_DIRECT=0 disables the second lane, =1 forces it (tests).
+ * bf_download_direct_rows(): rows of the calling thread's last bf_download_rows call that took it. */
 size_t bf_download_stage_bytes(int64_t chunk_rows);
+int64_t bf_download_direct_rows(void);
 int bf_download_rows(const int64_t* dev_src, int64_t n, int64_t* host_dst, void* dev_stage,
                      size_t dev_stage_bytes, void* pinned_stage, size_t pinned_bytes, int32_t n_threads,
                      void* stream);

@@ -169,6 +169,40 @@ def test_download_rows_matches_plain_copy(n):
     assert np.array_equal(view, t.cpu().numpy()) and (out[n:] == 7).all()
 
 
+@pytest.mark.parametrize("mode", ["1", "0", None])
+@pytest.mark.parametrize("n", [8 * 4096 + 1, 100_003, 1_000_000])
+def test_download_rows_direct_lane_into_pinned_destination(n, mode, monkeypatch):
+    """A page-locked destination lets bf_download_rows send the tail of the array as plain int64 copies on a second
+    stream while the host threads widen the front (include/bioframe_b200.h).  Forced here (BF_DOWNLOAD_DIRECT=1)
+    with small chunks so that the lanes meet many times in different places; =0 / unset must give the same array."""
+    from bioframe_b200 import engine
+
+    monkeypatch.setattr(engine._DownloadStage, "CHUNK_ROWS", 4096)
+    monkeypatch.setattr(engine._DownloadStage, "_cache", {})
+    if mode is None:
+        monkeypatch.delenv("BF_DOWNLOAD_DIRECT", raising=False)
+    else:
+        monkeypatch.setenv("BF_DOWNLOAD_DIRECT", mode)
+    g = torch.Generator(device="cuda").manual_seed(n)
+    t = torch.randint(-1, 2**31 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+    want = t.cpu().numpy()
+    out = engine.pinned_rows(n + 3)
+    for threads in (1, 3):
+        out[:] = 7
+        got = engine.download_rows(t, out=out, n_threads=threads)
+        assert np.array_equal(got, want) and (out[n:] == 7).all()
+        direct = engine.download_direct_rows()
+        if mode == "1":
+            assert 0 < direct < n  # both lanes carried rows
+        elif mode == "0":
+            assert direct == 0
+        else:
+            assert 0 <= direct < n
+    # a pageable destination never takes the second lane
+    plain = np.empty(n, dtype=np.int64)
+    assert np.array_equal(engine.download_rows(t, out=plain), want) and engine.download_direct_rows() == 0
+
+
 def test_download_rows_rejects_values_outside_int32():
     from bioframe_b200 import _lib, engine
 
