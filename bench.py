@@ -45,6 +45,8 @@ import time
 
 import numpy as np
 
+_T_START = time.perf_counter()
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -68,6 +70,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-frame", action="store_true", help="skip the DataFrame-level leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE.json configs")
+    ap.add_argument("--time-budget", type=float, default=240.0,
+                    help="seconds since process start after which the reported extra legs (all-core reference, frames, "
+                         "secondary configs) are skipped, so that a slow host cannot cost the headline line")
     ap.add_argument("--no-verify", action="store_true", help="N>1: skip the check against the single-GPU engine")
     ap.add_argument("--force-ranged", action="store_true", help="run the range-sharded path even on one GPU (diagnostic)")
     ap.add_argument("--workload", default="overlap",
@@ -1197,6 +1202,10 @@ def main():
         if sharded_verified is not None:
             line["sharded_verified"] = sharded_verified
         print_line = True
+
+        def over_budget():
+            return time.perf_counter() - _T_START > args.time_budget
+
         if world == 1 and not cfg4 and not args.no_cpu:
             leg = cpu_leg(args, 2, 1)
             line["cpu_baseline"] = {"value": leg["value"], "unit": "intervals/s", "cores": 1, "kind": leg["kind"],
@@ -1208,16 +1217,19 @@ def main():
             line["parity_sample"] = f"{leg['rows']} rows of the chr21+chr22 sample, array-equal with the {leg['kind']}, in its row order"
             del ds, g1_, g2_, leg
             # the same reference spread over every host core (what `--impl reference` times)
-            val_all, desc_all, ms_all, _, cores_all, kind_all = reference_leg_all_cores(args, 1, 1)
-            line["cpu_baseline"]["all_cores"] = {"value": val_all, "cores": cores_all, "kind": kind_all, "sample": desc_all,
-                                                 "ms_per_step": ms_all}
+            if over_budget():
+                line["cpu_baseline"]["all_cores"] = {"skipped": f"time budget ({args.time_budget:.0f} s)"}
+            else:
+                val_all, desc_all, ms_all, _, cores_all, kind_all = reference_leg_all_cores(args, 1, 1)
+                line["cpu_baseline"]["all_cores"] = {"value": val_all, "cores": cores_all, "kind": kind_all, "sample": desc_all,
+                                                     "ms_per_step": ms_all}
         # release the benchmark's tensors before the other legs
         del dq, dt, host_q, host_t
         engine.Workspace.release()
         torch.cuda.empty_cache()
         if world == 1 and not cfg4 and not args.no_frame:
             try:
-                line["frame_e2e"] = frame_leg(args)
+                line["frame_e2e"] = {"skipped": f"time budget ({args.time_budget:.0f} s)"} if over_budget() else frame_leg(args)
             except Exception as exc:  # a reported leg, never the reason the headline is lost
                 line["frame_e2e"] = {"error": f"{type(exc).__name__}: {exc}"}
             engine.Workspace.release()
@@ -1225,6 +1237,9 @@ def main():
         if world == 1 and not cfg4 and not args.no_secondary:
             sec_out = {}
             for wl in ("cfg0", "closest", "cluster", "coverage", "ordered"):
+                if over_budget():
+                    sec_out[wl] = {"skipped": f"time budget ({args.time_budget:.0f} s)"}
+                    continue
                 try:
                     s_line = secondary_line(args, wl, 3, 3, with_cpu=not args.no_cpu)
                     sec_out[wl] = {"metric": s_line["metric"], "workload": s_line["config"]["workload"], "ms_per_step": s_line["ms_per_step"],
