@@ -86,8 +86,8 @@ def complement_intervals(starts, ends, bounds=(0, INT64_MAX)):
     """(starts, ends) of the gaps between the merged intervals inside `bounds`."""
     s, e = _arrays(starts, ends)
     if len(s) == 0:
-        # the reference merges first and fails on empty input (np.r_ of an empty cumsum); an empty
-        # set has the whole bounds as its complement
+        # an empty set has the whole bounds as its complement; the reference (arrops.py:482-503 on the numpy of
+        # this image) answers the same, ([bounds[0]], [bounds[1]])
         return np.array([bounds[0]], dtype=np.int64), np.array([bounds[1]], dtype=np.int64)
     _, gs, ge = _engine.complement(None, s, e, np.array([bounds[0]], np.int64), np.array([bounds[1]], np.int64))
     return _host(gs), _host(ge)
