@@ -112,6 +112,16 @@ def _is_na(x):
     return x is None or x is pd.NA or x is pd.NaT or (isinstance(x, float) and x != x)
 
 
+def _visiting_order(keys1, keys2):
+    """Group keys of both frames in the order the reference's loop visits them: the iteration order of
+    `set.union(set(df1_groups), set(df2_groups))` (ops.py:289, 301; 985-986).  The reference builds its two sets
+    from DICTS (`groupby(...).indices`), and CPython sizes a set built from a dict once, up front, while a set built
+    from a list grows step by step and re-inserts its entries at every growth: with colliding hashes the two end up
+    in different iteration orders.  So the keys go through dicts here too (same keys, same insertion order, same
+    hashes -> the same table layout)."""
+    return list(set.union(set(dict.fromkeys(keys1)), set(dict.fromkeys(keys2))))
+
+
 def _chrom_is_na(key):
     """Does a group key (scalar, or tuple with the chromosome first) have a null chromosome?"""
     return _is_na(key[0]) if isinstance(key, tuple) else _is_na(key)
@@ -217,7 +227,7 @@ def _encode_frames(df1, df2, cols1=None, cols2=None, on=None, _group_order=None,
         codes2, keys2 = _group_keys_shared_na(df2, by2)
     # dropna=False in the reference (ops.py:287-288): a null in an `on` column is a key value like any other,
     # shared by both frames; the groups are visited in the order of the union set (ops.py:289, 301)
-    order = list(set.union(set(keys1), set(keys2))) if _group_order is None else [
+    order = _visiting_order(keys1, keys2) if _group_order is None else [
         np.nan if _is_na(k) else k for k in _group_order]
 
     # rank of every group in the visiting order.  A key with a null CHROMOSOME holds all-null rows
@@ -582,7 +592,7 @@ def _closest_intidxs(
 
     codes1, keys1 = _group_keys(df1, [ck1])
     codes2, keys2 = (codes1, keys1) if self_closest else _group_keys(df2, [ck2])
-    order = list(set.union(set(keys1), set(keys2))) if _group_order is None else list(_group_order)
+    order = _visiting_order(keys1, keys2) if _group_order is None else list(_group_order)
     rank = {key: r for r, key in enumerate(order)}
     n_groups = max(len(order), 1)
 

@@ -121,3 +121,28 @@ def test_live_nulls_in_on_column(ref, ours, seed):
         pd.testing.assert_frame_equal(ours.overlap(df1, df2, **kw), ref.overlap(df1, df2, **kw))
     pd.testing.assert_frame_equal(ours.count_overlaps(df1, df2, on=["strand"]), ref.count_overlaps(df1, df2, on=["strand"]))
     pd.testing.assert_frame_equal(ours.setdiff(df1, df2, on=["strand"]), ref.setdiff(df1, df2, on=["strand"]))
+
+
+def test_block_order_when_key_hashes_collide(ref, ours):
+    """The reference visits its groups in the iteration order of `set.union(set(df1_groups), set(df2_groups))`
+    (ops.py:289, 301) where the two operands are built from DICTS; a set built from a list of the same keys can
+    iterate differently when hashes collide in the table (CPython sizes a set from a dict once, a set from a list
+    grows and re-inserts).  Integer group keys whose two constructions differ -- independent of the string hash
+    seed -- must still give the reference's row order."""
+    keys1, keys2 = [58, 68, 114, 178, 184], [5, 6, 7, 81, 138, 166]
+    assert list(set.union(set(keys1), set(keys2))) != list(set.union(set(dict.fromkeys(keys1)), set(dict.fromkeys(keys2))))
+    rng = np.random.default_rng(11)
+
+    def frame(keys, n):
+        s = rng.integers(0, 300, n)
+        return pd.DataFrame({"chrom": rng.choice(np.array(keys + [58, 5]), n), "start": s, "end": s + rng.integers(1, 60, n)})
+
+    df1, df2 = frame(keys1, 300), frame(keys2, 200)
+    for how in ("inner", "left", "outer", "right"):
+        a, b = ours.ops._overlap_intidxs(df1, df2, how=how)
+        ra, rb = ref.ops._overlap_intidxs(df1, df2, how=how)
+        assert np.array_equal(np.asarray(a), np.asarray(ra, dtype=np.int64)), how
+        assert np.array_equal(np.asarray(b), np.asarray(rb, dtype=np.int64)), how
+    a, b = ours.ops._closest_intidxs(df1, df2, k=2)
+    ra, rb = ref.ops._closest_intidxs(df1, df2, k=2)
+    assert np.array_equal(np.asarray(a), np.asarray(ra, dtype=np.int64)) and np.array_equal(np.asarray(b), np.asarray(rb, dtype=np.int64))
