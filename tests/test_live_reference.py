@@ -61,9 +61,13 @@ def test_live_overlap_family(ref, ours, seed):
     # row order pinned by the reference: left join with keep_order, and everything per-query
     for kw in (dict(how="left"), dict(how="left", return_index=True, return_overlap=True, suffixes=("_q", "_t"))):
         pd.testing.assert_frame_equal(ours.overlap(df1, df2, **kw), ref.overlap(df1, df2, **kw))
-    for how in ("inner", "right", "outer"):  # chromosome blocks come in set order: compare as row sets
+    # chromosome blocks come in set order (ops.py:289, 301): the same process builds the same sets, so even the
+    # joins without keep_order must agree row for row
+    for how in ("inner", "right", "outer"):
         got, want = ours.overlap(df1, df2, how=how, return_index=True), ref.overlap(df1, df2, how=how, return_index=True)
-        pd.testing.assert_frame_equal(_canon(got), _canon(want))
+        pd.testing.assert_frame_equal(got, want)
+    got, want = ours.ops._overlap_intidxs(df1, df2, how="outer"), ref.ops._overlap_intidxs(df1, df2, how="outer")
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
     pd.testing.assert_frame_equal(ours.coverage(df1.copy(), df2), ref.coverage(df1.copy(), df2))
     pd.testing.assert_frame_equal(ours.count_overlaps(df1.copy(), df2), ref.count_overlaps(df1.copy(), df2))
     pd.testing.assert_frame_equal(ours.setdiff(df1, df2), ref.setdiff(df1, df2))
