@@ -83,8 +83,22 @@ def _factorize_column(col):
     sorted groupby visits them: lexical for strings, category order (observed
     only) for categoricals."""
     if isinstance(col.dtype, pd.CategoricalDtype):
-        raw = np.asarray(col.cat.codes, dtype=np.int64)
+        raw = np.asarray(col.cat.codes)
         n_cat = len(col.cat.categories)
+        if raw.dtype.itemsize <= 2 and len(raw):
+            # 1- or 2-byte dictionary codes (the usual chromosome column): which categories occur comes from one
+            # histogram over the unsigned view (-1 = NA lands in the last bin, never a category: n_cat <= 32767),
+            # and when the observed categories are the first ones -- nearly always all of them -- the group codes
+            # ARE the dictionary codes
+            bins = np.bincount(raw.view(np.uint8 if raw.dtype.itemsize == 1 else np.uint16), minlength=n_cat)
+            present = np.flatnonzero(bins[:n_cat])
+            keys = [col.cat.categories[i] for i in present]
+            if len(present) == 0 or present[-1] == len(present) - 1:
+                return raw.astype(np.int64), keys
+            remap = np.full(n_cat + 1, -1, dtype=np.int64)
+            remap[present + 1] = np.arange(len(present))
+            return remap[raw.astype(np.int64) + 1], keys
+        raw = raw.astype(np.int64)
         seen = np.zeros(n_cat + 1, dtype=bool)
         seen[raw + 1] = True
         present = np.flatnonzero(seen[1:])
@@ -187,6 +201,33 @@ def _int64_coords(df, col):
     if values.isna().any():
         values = values.fillna(0)
     return np.asarray(values, dtype=np.int64)
+
+
+def _ranked_rows(df, codes, table, sk, ek, keep=None):
+    """The rows of a frame that take part in a kernel call: those with a group code (>= 0), or, with `keep` (a
+    flag per group key), those of a kept group.  `table` maps group codes to group ranks (int32).
+    -> (row positions, or None when that is every row; group ranks; starts; ends).  The usual frame has no null
+    and its codes already are the ranks: then nothing is indexed or copied per row beyond the int32 cast."""
+    n = len(codes)
+    if keep is not None:
+        rows = None if bool(keep.all()) else np.flatnonzero(keep[codes])
+    else:
+        rows = None if (n == 0 or codes.min() >= 0) else np.flatnonzero(codes >= 0)
+    identity = np.array_equal(table, np.arange(len(table)))
+    starts, ends = _int64_coords(df, sk), _int64_coords(df, ek)
+    if rows is None:
+        return None, (codes.astype(np.int32) if identity else table[codes]), starts, ends
+    picked = codes[rows]
+    return rows, (picked.astype(np.int32) if identity else table[picked]), starts[rows], ends[rows]
+
+
+def _spread(values, rows, n, fill=0):
+    """values of the participating rows -> one value per frame row (`fill` elsewhere)."""
+    if rows is None:
+        return values
+    out = np.full(n, fill, dtype=values.dtype)
+    out[rows] = values
+    return out
 
 
 def _to_host(t):
@@ -335,9 +376,15 @@ def _to_nullable_dtype(dtype):
         return dtype
 
 
+def _int64_array(values):
+    """A nullable Int64 column without a null over `values` (int64 numpy, not copied)."""
+    return pd.arrays.IntegerArray(np.ascontiguousarray(values, dtype=np.int64), np.zeros(len(values), dtype=bool))
+
+
 def _suffixed_rows(df, positions, suffix):
     part = df.iloc[positions].reset_index(drop=True)
-    part.columns = [c + suffix for c in part.columns]
+    if suffix != "":
+        part.columns = [c + suffix for c in part.columns]
     return part
 
 
@@ -570,6 +617,7 @@ def _closest_intidxs(
     cols2=None,
     _group_order=None,
     _coords=None,
+    _device_rows=None,
 ):
     """Integer row positions of the k closest intervals, -1 where a query has
     none.  Mirrors ops._closest_intidxs (ops.py:919-1040): chromosome blocks in
@@ -597,18 +645,17 @@ def _closest_intidxs(
     n_groups = max(len(order), 1)
 
     def coded(df, codes, keys, sk, ek):
-        """rows with a valid chromosome: (positions, group ranks, starts, ends)"""
-        valid = np.flatnonzero(codes >= 0)
-        table = np.array([rank[key] for key in keys], dtype=np.int32)
-        ranks = table[codes[valid]] if len(valid) else np.empty(0, np.int32)
-        return valid, ranks, _int64_coords(df, sk)[valid], _int64_coords(df, ek)[valid]
+        """rows with a valid chromosome: (positions or None for every row, group ranks, starts, ends)"""
+        return _ranked_rows(df, codes, np.array([rank[key] for key in keys], dtype=np.int32), sk, ek)
 
     rows1, g1, s1, e1 = coded(df1, codes1, keys1, sk1, ek1)
     if _coords:
         s1, e1 = _engine.to_device(s1), _engine.to_device(e1)
     along = None
     if direction_col is not None:
-        along = (df1[direction_col].values != "-")[rows1]
+        along = df1[direction_col].values != "-"
+        if rows1 is not None:
+            along = along[rows1]
     if self_closest:
         rows2, s2, e2 = rows1, s1, e1
         ev1, ev2, _ = _engine.closest_intidxs(
@@ -630,11 +677,13 @@ def _closest_intidxs(
             for x in _engine.pair_coords(ev1, ev2, s1, e1, s2, e2, want_overlap="overlap" in _coords,
                                          want_distance="distance" in _coords)
         )
+    if _device_rows is not None and rows1 is None and rows2 is None:
+        _device_rows.extend([ev1, ev2])  # frame positions as they are: the caller gathers its columns with them
     ev1, ev2 = _rows_to_host(ev1), _rows_to_host(ev2)
     # kernel rows index the NA-free subsets; map back to frame positions
-    if len(rows1) != len(df1):
+    if rows1 is not None:
         ev1 = rows1[ev1]
-    if len(rows2) != len(df2):
+    if rows2 is not None:
         ev2 = np.where(ev2 >= 0, rows2[np.maximum(ev2, 0)], -1)
     return (ev1, ev2, extra) if _coords else (ev1, ev2)
 
@@ -670,12 +719,15 @@ def closest(
     checks.is_bedframe(df2, raise_errors=True, cols=[ck2, sk2, ek2])
 
     want = tuple(t for t, on_ in (("overlap", return_overlap), ("distance", return_distance)) if on_)
+    dev_rows = []  # the pair list where the kernel left it: large results gather their columns there (_taken_rows)
     res = _closest_intidxs(
         df1, df2, k=k, ignore_overlaps=ignore_overlaps, ignore_upstream=ignore_upstream,
         ignore_downstream=ignore_downstream, direction_col=direction_col, tie_breaking_col=tie_breaking_col,
-        cols1=cols1, cols2=cols2, _coords=want or None,
+        cols1=cols1, cols2=cols2, _coords=want or None, _device_rows=dev_rows,
     )
     ev1, ev2 = res[0], res[1]
+    dev1, dev2 = dev_rows if dev_rows else (None, None)
+    del dev_rows
     lone = ev2 == -1
 
     pieces = []
@@ -686,12 +738,13 @@ def closest(
         pieces.append(("i1", pd.DataFrame({stem + suffixes[0]: df1.index[ev1]})))
         pieces.append(("i2", idx2))
     if return_input:
-        in2 = _suffixed_rows(df2, ev2, suffixes[1]).astype(
+        in2 = _taken_rows(df2, ev2, dev2, suffixes[1]).astype(
             {sk2 + suffixes[1]: pd.Int64Dtype(), ek2 + suffixes[1]: pd.Int64Dtype()}
         )
         in2[lone] = pd.NA
-        pieces.append(("in1", _suffixed_rows(df1, ev1, suffixes[0])))
+        pieces.append(("in1", _taken_rows(df1, ev1, dev1, suffixes[0])))
         pieces.append(("in2", in2))
+    del dev1, dev2
     if return_overlap:
         lo, hi = res[2][0], res[2][1]
         have = lo < hi
@@ -725,24 +778,43 @@ def _check_min_dist_and_on(df, min_dist, ck, on):
     return group_list
 
 
-def _merge_groups(df, group_list, sk, ek, min_dist, want_ids):
+def _cannot_hold_null(dtype):
+    """Plain integer / bool numpy columns have no null: no pass over the rows is needed to know it."""
+    return isinstance(dtype, np.dtype) and dtype.kind in "iub"
+
+
+def _null_rows(df, cols):
+    """Boolean mask of the rows with a null in any of `cols` (pd.isnull(df[cols]).any(axis=1), ops.py:676), or
+    None when there is none; columns that cannot hold a null are not scanned."""
+    mask = None
+    for c in cols:
+        col = df[c]
+        if _cannot_hold_null(col.dtype):
+            continue
+        if isinstance(col.dtype, pd.CategoricalDtype):
+            m = np.asarray(col.cat.codes) < 0
+        else:
+            m = np.asarray(pd.isnull(col))
+        if m.any():
+            mask = m if mask is None else (mask | m)
+    return mask
+
+
+def _merge_groups(df, group_list, sk, ek, min_dist, want_ids, want_row_spans=False):
     """One kernel call for all (chrom, *on) groups in sorted key order
     (`df.groupby(group_list, observed=True).groups`, ops.py:631/772).
-    -> (valid row positions, engine result, group keys)."""
+    -> (valid row positions or None for "every row", engine result, group keys, mask of null rows or None)."""
     codes, keys = _group_keys(df, group_list)
-    has_coords = ~np.asarray(pd.isnull(df[[sk, ek]]).any(axis=1))
-    valid = np.flatnonzero((codes >= 0) & has_coords)
+    null_rows = _null_rows(df, [sk, ek, *group_list])
     md = None if min_dist is None else int(np.floor(min_dist))  # integer coordinates: s > r + d <=> s > r + floor(d)
-    res = _engine.cluster(
-        codes[valid].astype(np.int32),
-        _int64_coords(df, sk)[valid],
-        _int64_coords(df, ek)[valid],
-        max(len(keys), 1),
-        min_dist=md,
-        want_ids=want_ids,
-        want_table=True,
-    )
-    return valid, res, keys
+    grp, starts, ends = codes.astype(np.int32), _int64_coords(df, sk), _int64_coords(df, ek)
+    valid = None
+    if null_rows is not None:  # rows with a null key or coordinate take no part (ops.py:631, 641-644)
+        valid = np.flatnonzero(~null_rows)
+        grp, starts, ends = grp[valid], starts[valid], ends[valid]
+    res = _engine.cluster(grp, starts, ends, max(len(keys), 1), min_dist=md, want_ids=want_ids, want_table=True,
+                          want_row_spans=want_row_spans)
+    return valid, res, keys, null_rows
 
 
 def _cluster_table(df, res, keys, group_list, sk, ek):
@@ -787,31 +859,36 @@ def cluster(
     df = df.reset_index(drop=True)
     group_list = _check_min_dist_and_on(df, min_dist, ck, on)
 
-    valid, res, keys = _merge_groups(df, group_list, sk, ek, min_dist, want_ids=True)
+    # every row's cluster span comes straight from the device (row_start / row_end of bf_cluster_emit) unless
+    # null rows, which are clusters of their own, have to be spliced in
+    valid, res, keys, null_rows = _merge_groups(df, group_list, sk, ek, min_dist, want_ids=True,
+                                                want_row_spans=bool(return_cluster_intervals))
     n_clusters = res["n_clusters"]
-    ids = np.full(len(df), -1)
-    ids[valid] = _to_host(res["ids"])
-    null_rows = np.asarray(pd.isnull(df[[sk, ek, *group_list]]).any(axis=1))
-    n_null = int(null_rows.sum())
-    if n_null:
-        ids[null_rows] = n_clusters + np.arange(n_null)
-    assert np.all(ids >= 0)
-
     out = {}
-    if return_cluster_ids:
-        out["cluster"] = ids
-    if return_cluster_intervals:
-        cs, ce = _to_host(res["cstart"]), _to_host(res["cend"])
-        if n_null:  # null rows are their own "cluster" with their own (null) coordinates
+    if null_rows is None:
+        if return_cluster_ids:
+            out["cluster"] = _to_host(res["ids"])
+        if return_cluster_intervals:
+            out["cluster_start"] = _to_host(res["row_start"])
+            out["cluster_end"] = _to_host(res["row_end"])
+    else:
+        ids = np.full(len(df), -1)
+        ids[valid] = _to_host(res["ids"])
+        n_null = int(null_rows.sum())
+        ids[null_rows] = n_clusters + np.arange(n_null)
+        assert np.all(ids >= 0)
+        if return_cluster_ids:
+            out["cluster"] = ids
+        if return_cluster_intervals:
+            # null rows are their own "cluster" with their own (null) coordinates
+            cs, ce = _to_host(res["cstart"]), _to_host(res["cend"])
             cs = pd.array(np.concatenate([cs, np.zeros(n_null, np.int64)]), dtype=pd.Int64Dtype())
             ce = pd.array(np.concatenate([ce, np.zeros(n_null, np.int64)]), dtype=pd.Int64Dtype())
-            null_s = df.loc[null_rows, sk].astype(pd.Int64Dtype()).values
-            null_e = df.loc[null_rows, ek].astype(pd.Int64Dtype()).values
-            cs[n_clusters:] = null_s
-            ce[n_clusters:] = null_e
-        out["cluster_start"] = cs[ids]
-        out["cluster_end"] = ce[ids]
-    out = pd.DataFrame(out)
+            cs[n_clusters:] = df.loc[null_rows, sk].astype(pd.Int64Dtype()).values
+            ce[n_clusters:] = df.loc[null_rows, ek].astype(pd.Int64Dtype()).values
+            out["cluster_start"] = cs[ids]
+            out["cluster_end"] = ce[ids]
+    out = pd.DataFrame(out, copy=False)
     if return_input:
         out = pd.concat([df, out], axis="columns")
     return out
@@ -824,14 +901,12 @@ def merge(df, min_dist=0, cols=None, on=None):
         raise ValueError("min_dist>=0 currently required")
     ck, sk, ek = _get_default_colnames() if cols is None else cols
     checks.is_bedframe(df, raise_errors=True, cols=[ck, sk, ek])
-    df = df.copy()
-    df.reset_index(inplace=True, drop=True)
+    df = df.reset_index(drop=True)  # the frame itself is only read here: no copy of its columns is needed
     group_list = _check_min_dist_and_on(df, min_dist, ck, on)
 
-    _, res, keys = _merge_groups(df, group_list, sk, ek, min_dist, want_ids=False)
+    _, res, keys, null_rows = _merge_groups(df, group_list, sk, ek, min_dist, want_ids=False)
     parts = [_cluster_table(df, res, keys, group_list, sk, ek)] if res["n_clusters"] else []
-    null_rows = pd.isnull(df[[sk, ek, *group_list]]).any(axis=1)
-    n_null = int(null_rows.sum())
+    n_null = 0 if null_rows is None else int(null_rows.sum())
     if n_null:
         extra = pd.DataFrame([pd.NA] * n_null, columns=["n_intervals"], index=df.loc[null_rows].index)
         parts.append(pd.concat([df.loc[null_rows], extra], axis=1))
@@ -863,19 +938,14 @@ def coverage(df1, df2, suffixes=("", "_"), return_input=True, cols1=None, cols2=
     union = sorted(set(keys1) | set(keys2), key=str)
     rank = {key: r for r, key in enumerate(union)}
     n_groups = max(len(union), 1)
-    v1 = np.flatnonzero(codes1 >= 0)
-    v2 = np.flatnonzero(codes2 >= 0)
     t1 = np.array([rank[k] for k in keys1], dtype=np.int32)
     t2 = np.array([rank[k] for k in keys2], dtype=np.int32)
+    rows1, g1, s1, e1 = _ranked_rows(df1, codes1, t1, sk1, ek1)
+    _, g2, s2, e2 = _ranked_rows(df2, codes2, t2, sk2, ek2)
     cov = np.zeros(len(df1), dtype=np.int64)
-    if len(v1):
-        got = _engine.coverage(
-            t1[codes1[v1]], _int64_coords(df1, sk1)[v1], _int64_coords(df1, ek1)[v1],
-            t2[codes2[v2]] if len(v2) else np.empty(0, np.int32),
-            _int64_coords(df2, sk2)[v2], _int64_coords(df2, ek2)[v2], n_groups,
-        )
-        cov[v1] = _to_host(got)
-    out = pd.DataFrame({"coverage": pd.Series(cov).astype(df1[sk1].dtype)})
+    if len(g1):
+        cov = _spread(_to_host(_engine.coverage(g1, s1, e1, g2, s2, e2, n_groups)), rows1, len(df1))
+    out = pd.DataFrame({"coverage": pd.Series(cov).astype(df1[sk1].dtype, copy=False)}, copy=False)
     if return_input:
         out = pd.concat([df1, out], axis="columns")
     return out
@@ -949,16 +1019,11 @@ def _overlap_counts(df1, df2, cols1, cols2, on):
     t2 = np.array([rank[k] for k in keys2], dtype=np.int32)
     ok1 = np.array([not _chrom_is_na(k) for k in keys1], dtype=bool)
     ok2 = np.array([not _chrom_is_na(k) for k in keys2], dtype=bool)
-    v1 = np.flatnonzero(ok1[codes1]) if len(df1) else np.empty(0, np.int64)
-    v2 = np.flatnonzero(ok2[codes2]) if len(df2) else np.empty(0, np.int64)
+    rows1, g1, s1, e1 = _ranked_rows(df1, codes1, t1, sk1, ek1, keep=ok1)
+    _, g2, s2, e2 = _ranked_rows(df2, codes2, t2, sk2, ek2, keep=ok2)
     counts = np.zeros(len(df1), dtype=np.int64)
-    if len(v1):
-        got = _engine.count_overlaps(
-            t1[codes1[v1]], _int64_coords(df1, sk1)[v1], _int64_coords(df1, ek1)[v1],
-            t2[codes2[v2]] if len(v2) else np.empty(0, np.int32),
-            _int64_coords(df2, sk2)[v2], _int64_coords(df2, ek2)[v2], max(len(union), 1),
-        )
-        counts[v1] = _to_host(got)
+    if len(g1):
+        counts = _spread(_to_host(_engine.count_overlaps(g1, s1, e1, g2, s2, e2, max(len(union), 1))), rows1, len(df1))
     return counts
 
 
@@ -1047,20 +1112,27 @@ def subtract(df1, df2, return_index=False, suffixes=("", "_"), cols1=None, cols2
     rank = {key: r for r, key in enumerate(union)}
     t1 = np.array([rank[k] for k in keys1], dtype=np.int32)
     t2 = np.array([rank[k] for k in keys2], dtype=np.int32)
-    v1, v2 = np.flatnonzero(codes1 >= 0), np.flatnonzero(codes2 >= 0)
+    rows1, g1, s1, e1 = _ranked_rows(df1, codes1, t1, sk1, ek1)
+    _, g2, s2, e2 = _ranked_rows(df2, codes2, t2, sk2, ek2)
     row = ps = pe = sub = np.empty(0, dtype=np.int64)
-    if len(v1):
-        row, ps, pe, sub = _engine.subtract(
-            t1[codes1[v1]], _int64_coords(df1, sk1)[v1], _int64_coords(df1, ek1)[v1],
-            t2[codes2[v2]] if len(v2) else np.empty(0, np.int32),
-            _int64_coords(df2, sk2)[v2], _int64_coords(df2, ek2)[v2], max(len(union), 1),
-            want_sub_index=bool(return_index),
-        )
-        row, ps, pe = v1[_to_host(row)], _to_host(ps), _to_host(pe)
+    row_dev = None
+    if len(g1):
+        row_dev, ps, pe, sub = _engine.subtract(g1, s1, e1, g2, s2, e2, max(len(union), 1),
+                                                want_sub_index=bool(return_index))
+        row, ps, pe = _to_host(row_dev), _to_host(ps), _to_host(pe)
+        if rows1 is not None:
+            row, row_dev = rows1[row], None
+    # the pieces' coordinates replace the source rows' own: only the other columns are taken per piece
     others = [c for c in df1.columns if c not in (ck1, sk1, ek1)]
-    out = df1.iloc[row][[ck1, sk1, ek1, *others]].reset_index(drop=True)
-    out[sk1] = pd.array(ps, dtype=pd.Int64Dtype())
-    out[ek1] = pd.array(pe, dtype=pd.Int64Dtype())
+    if df1.columns.is_unique:
+        out = _taken_rows(df1[[ck1, *others]], row, row_dev, "")
+        out.insert(1, sk1, _int64_array(ps))
+        out.insert(2, ek1, _int64_array(pe))
+    else:
+        out = df1.iloc[row][[ck1, sk1, ek1, *others]].reset_index(drop=True)
+        out[sk1] = _int64_array(ps)
+        out[ek1] = _int64_array(pe)
+    del row_dev
     if return_index:
         out["index" + suffixes[0]] = pd.array(np.asarray(ix)[row], dtype=pd.Int64Dtype())
         out["sub_index" + suffixes[1]] = pd.array(_to_host(sub) if len(row) else sub, dtype=pd.Int64Dtype())

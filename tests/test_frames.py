@@ -75,9 +75,10 @@ def test_frame_glue_on_oracle_double(name, oracle_double):
     _check(name)
 
 
-# cases that assemble an `overlap` frame: run them once more with the large-result assembly forced on
+# cases that assemble an `overlap` / `closest` frame: run them once more with the large-result assembly forced on
 # (numeric columns gathered through bf_gather_rows instead of pandas iloc)
-GATHER_CASES = sorted(n for n, c in CASES.items() if c["fn"] in ("overlap", "subtract", "assign_view", "trim", "complement"))
+GATHER_CASES = sorted(n for n, c in CASES.items()
+                      if c["fn"] in ("overlap", "closest", "subtract", "assign_view", "trim", "complement"))
 
 
 @pytest.fixture
