@@ -243,6 +243,43 @@ def _rows_to_host(t):
 
 
 # --------------------------------------------------------------------------
+# rows the reference's grouping leaves out
+# --------------------------------------------------------------------------
+_PANDAS_DROPS_NULL_CATEGORY = None
+
+
+def _pandas_drops_null_category():
+    """Does `groupby([one categorical column], observed=True, dropna=False).indices` of this pandas leave the
+    null rows out?  (It does in pandas 1.x-3.x: the single-categorical fast path of `.indices` knows no NaN
+    group, although `dropna=False` -- with two key columns, or an object column, the NaN key is there.)  The
+    reference builds its groups with exactly that call (ops.py:287-288), so where pandas drops them, all-null
+    rows of a frame with a categorical chromosome column appear nowhere in its `_overlap_intidxs` result -- not
+    even as unpaired rows of a left / outer join.  Probed once instead of assumed."""
+    global _PANDAS_DROPS_NULL_CATEGORY
+    if _PANDAS_DROPS_NULL_CATEGORY is None:
+        probe = pd.DataFrame({"k": pd.Categorical(["a", None])})
+        _PANDAS_DROPS_NULL_CATEGORY = len(probe.groupby(["k"], observed=True, dropna=False).indices) == 1
+    return _PANDAS_DROPS_NULL_CATEGORY
+
+
+def _ungrouped_rows(df, ck, on):
+    """Mask of the rows `_overlap_intidxs` of the reference never sees (see above), or None."""
+    if on or not isinstance(df[ck].dtype, pd.CategoricalDtype):
+        return None
+    missing = np.asarray(df[ck].cat.codes) < 0
+    if not missing.any() or not _pandas_drops_null_category():
+        return None
+    return missing
+
+
+def _frame_positions(ev, rows):
+    """Row numbers of a filtered frame -> row numbers of the frame it was taken from (-1 stays)."""
+    if rows is None:
+        return ev
+    return np.where(ev >= 0, rows[np.maximum(ev, 0)], -1) if len(rows) else ev
+
+
+# --------------------------------------------------------------------------
 # overlap
 # --------------------------------------------------------------------------
 def _encode_frames(df1, df2, cols1=None, cols2=None, on=None, _group_order=None, _device=True):
@@ -312,6 +349,17 @@ def _overlap_intidxs(df1, df2, how="left", cols1=None, cols2=None, on=None, _gro
     `set.union(set(groups1), set(groups2))` exactly as in the reference
     (ops.py:289,301), each block = pairs, unpaired-left, unpaired-right."""
     t0 = _now()
+    gone1 = _ungrouped_rows(df1, (cols1 or _get_default_colnames())[0], on)
+    gone2 = _ungrouped_rows(df2, (cols2 or _get_default_colnames())[0], on)
+    if gone1 is not None or gone2 is not None:
+        # all-null rows under a categorical chromosome column: the reference's grouping has no group for them
+        # (_pandas_drops_null_category), so they are not even unpaired rows.  The join runs on the other rows.
+        rows1 = None if gone1 is None else np.flatnonzero(~gone1)
+        rows2 = None if gone2 is None else np.flatnonzero(~gone2)
+        res = _overlap_intidxs(df1 if rows1 is None else df1.iloc[rows1], df2 if rows2 is None else df2.iloc[rows2],
+                               how=how, cols1=cols1, cols2=cols2, on=on, _group_order=_group_order,
+                               _sort_pairs=_sort_pairs, _coords=_coords)
+        return (_frame_positions(res[0], rows1), _frame_positions(res[1], rows2), *res[2:])
     g1, s1, e1, g2, s2, e2, n_groups, _order = _encode_frames(df1, df2, cols1, cols2, on, _group_order)
     t0 = _tick("encode_groups", t0)
     if _coords or _PROFILE is not None:
@@ -945,7 +993,12 @@ def coverage(df1, df2, suffixes=("", "_"), return_input=True, cols1=None, cols2=
     cov = np.zeros(len(df1), dtype=np.int64)
     if len(g1):
         cov = _spread(_to_host(_engine.coverage(g1, s1, e1, g2, s2, e2, n_groups)), rows1, len(df1))
-    out = pd.DataFrame({"coverage": pd.Series(cov).astype(df1[sk1].dtype, copy=False)}, copy=False)
+    gone = _ungrouped_rows(df1, ck1, None)
+    if gone is not None:
+        # the reference's left join has no rows for these (`_ungrouped_rows`), and it attaches the per-row sums of
+        # the others by POSITION (ops.py:903-915): they move up and the tail of the column is null.  Reproduced.
+        cov = cov[~gone]
+    out = pd.DataFrame({"coverage": pd.Series(cov).astype(df1[sk1].dtype)}, copy=False)
     if return_input:
         out = pd.concat([df1, out], axis="columns")
     return out
@@ -1037,7 +1090,11 @@ def count_overlaps(df1, df2, suffixes=("", "_"), return_input=True, cols1=None, 
     checks.is_bedframe(df1, raise_errors=True, cols=[ck1, sk1, ek1])
     checks.is_bedframe(df2, raise_errors=True, cols=[ck2, sk2, ek2])
     # the reference counts a nullable Int64 index column per query, which yields a nullable Int64 column
-    out = pd.DataFrame({"count": pd.array(_overlap_counts(df1, df2, cols1, cols2, on), dtype=pd.Int64Dtype())})
+    counts = _overlap_counts(df1, df2, cols1, cols2, on)
+    gone = _ungrouped_rows(df1, ck1, on)
+    if gone is not None:  # as in coverage: the reference counts the rows its join has and attaches them by position
+        counts = counts[~gone]
+    out = pd.DataFrame({"count": pd.array(counts, dtype=pd.Int64Dtype())})
     if return_input:
         out = pd.concat([df1, out], axis="columns")
     return out

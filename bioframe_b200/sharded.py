@@ -372,6 +372,15 @@ def overlap_intidxs_frames(df1, df2, how="left", cols1=None, cols2=None, on=None
 
     if engine is None:
         from . import engine as engine
+    # all-null rows under a categorical chromosome column are in no group of the reference (ops._ungrouped_rows)
+    gone1 = ops._ungrouped_rows(df1, (cols1 or ops._get_default_colnames())[0], on)
+    gone2 = ops._ungrouped_rows(df2, (cols2 or ops._get_default_colnames())[0], on)
+    if gone1 is not None or gone2 is not None:
+        rows1 = None if gone1 is None else np.flatnonzero(~gone1)
+        rows2 = None if gone2 is None else np.flatnonzero(~gone2)
+        res = overlap_intidxs_frames(df1 if rows1 is None else df1.iloc[rows1], df2 if rows2 is None else df2.iloc[rows2],
+                                     how=how, cols1=cols1, cols2=cols2, on=on, group=group, engine=engine, gather=gather)
+        return (ops._frame_positions(res[0], rows1), ops._frame_positions(res[1], rows2), *res[2:])
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     # group ranks on the host (the shard planner reads them); rank 0's visiting order for everyone

@@ -85,6 +85,90 @@ def test_live_cluster_family(ref, ours, seed):
     pd.testing.assert_frame_equal(ours.merge_runs(df, "score", allow_overlaps=True), ref.merge_runs(df, "score", allow_overlaps=True))
 
 
+@pytest.mark.parametrize("forced_device_assembly", [False, True])
+@pytest.mark.parametrize("seed", range(4))
+def test_live_categorical_family(ref, ours, seed, forced_device_assembly, monkeypatch):
+    """Categorical chromosome columns: dictionary codes become group codes without a per-row remap when the
+    observed categories are the first ones (ops._factorize_column), categories out of lexical order, categories
+    that never occur, whole-null rows; once more with the large-result paths (device encode + column gathers)
+    forced on for these small frames."""
+    import bioframe_b200.ops as ops
+
+    if forced_device_assembly:
+        monkeypatch.setattr(ops, "_DEVICE_GATHER_MIN_ROWS", 0)
+        monkeypatch.setattr(ops, "_DEVICE_ENCODE_MIN_ROWS", 0)
+    rng = np.random.default_rng(5000 + seed)
+    cats = [["chrX", "chr2", "chr10", "chr1", "chrUn"], ["chr1", "chr2", "chrX"], ["chr9", "chrX", "chr2", "chr1"],
+            ["chr2", "chr1"]][seed]
+    used1, used2 = cats[: max(2, len(cats) - 1)], cats[1:]
+
+    def cat_frame(n, used, nulls):
+        df = _frame(rng, n, chroms=tuple(used))
+        df["chrom"] = pd.Categorical(df["chrom"], categories=cats)
+        if nulls:
+            df["start"] = df["start"].astype(pd.Int64Dtype())
+            df["end"] = df["end"].astype(pd.Int64Dtype())
+            df.loc[df.index[3::17], ["chrom", "start", "end"]] = pd.NA
+        return df
+
+    for nulls in (False, True):
+        df1, df2 = cat_frame(int(rng.integers(20, 140)), used1, nulls), cat_frame(int(rng.integers(20, 90)), used2, nulls)
+        for how in ("left", "inner", "outer"):
+            kw = dict(how=how, return_index=True, return_overlap=True)
+            pd.testing.assert_frame_equal(ours.overlap(df1, df2, **kw), ref.overlap(df1, df2, **kw))
+        for md in (0, None, 5):
+            pd.testing.assert_frame_equal(ours.cluster(df1, min_dist=md), ref.cluster(df1, min_dist=md))
+            pd.testing.assert_frame_equal(ours.merge(df1, min_dist=md), ref.merge(df1, min_dist=md))
+        pd.testing.assert_frame_equal(ours.cluster(df2, return_cluster_ids=False), ref.cluster(df2, return_cluster_ids=False))
+        pd.testing.assert_frame_equal(ours.cluster(df2, return_cluster_intervals=False, return_input=False),
+                                      ref.cluster(df2, return_cluster_intervals=False, return_input=False))
+        pd.testing.assert_frame_equal(ours.coverage(df1.copy(), df2), ref.coverage(df1.copy(), df2))
+        pd.testing.assert_frame_equal(ours.count_overlaps(df1.copy(), df2), ref.count_overlaps(df1.copy(), df2))
+        pd.testing.assert_frame_equal(ours.setdiff(df1, df2), ref.setdiff(df1, df2))
+        pd.testing.assert_frame_equal(ours.subtract(df1, df2, return_index=True), ref.subtract(df1, df2, return_index=True))
+        pd.testing.assert_frame_equal(ours.subtract(df1, df2), ref.subtract(df1, df2))
+        # closest among equal distances goes through an unstable sort in the reference: compare what is defined
+        got, want = ours.closest(df1, df2, k=1), ref.closest(df1, df2, k=1)
+        assert list(got.columns) == list(want.columns) and len(got) == len(want)
+        pd.testing.assert_series_equal(got["distance"].sort_values(ignore_index=True),
+                                       want["distance"].sort_values(ignore_index=True))
+
+
+def test_live_null_rows_under_categorical_chromosome(ref, ours):
+    """`groupby([one categorical column], observed=True, dropna=False).indices` has no group for the null rows
+    (ops._pandas_drops_null_category), so the reference's `_overlap_intidxs` does not return them at all -- unlike
+    null rows under an object column, which come back unpaired.  Same rows here, at the index level, for the
+    frame-level sharded call (one rank) and in the positional attach of count_overlaps / coverage."""
+    import bioframe_b200.ops as ops
+    from bioframe_b200 import sharded
+
+    cats = ["chr2", "chr1", "chrX"]
+
+    def frame(chroms, starts, ends):
+        return pd.DataFrame({"chrom": pd.Categorical(chroms, categories=cats), "start": pd.array(starts, dtype="Int64"),
+                             "end": pd.array(ends, dtype="Int64")})
+
+    df1 = frame(["chr2", "chr2", None, "chr1", "chr1", None, "chrX"], [1, 30, None, 5, 50, None, 7], [10, 40, None, 9, 60, None, 9])
+    df2 = frame(["chr2", None, "chr1", "chr1", "chrX"], [5, None, 1, 55, 100], [8, None, 6, 58, 110])
+    assert ops._pandas_drops_null_category() == (len(df1.groupby(["chrom"], observed=True, dropna=False).indices) == 3)
+    for how in ("left", "inner", "outer", "right"):
+        got, want = ours.ops._overlap_intidxs(df1, df2, how=how), ref.ops._overlap_intidxs(df1, df2, how=how)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), how
+        pd.testing.assert_frame_equal(ours.overlap(df1, df2, how=how, return_index=True, return_overlap=True),
+                                      ref.overlap(df1, df2, how=how, return_index=True, return_overlap=True))
+    if getattr(ops._engine, "__name__", "") == "oracle_engine":  # the sharded frame call: host logic, checked on CPU
+        for how in ("left", "inner"):
+            got, want = sharded.overlap_intidxs_frames(df1, df2, how=how, engine=ops._engine), ref.ops._overlap_intidxs(df1, df2, how=how)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), how
+    pd.testing.assert_frame_equal(ours.count_overlaps(df1.copy(), df2), ref.count_overlaps(df1.copy(), df2))
+    pd.testing.assert_frame_equal(ours.coverage(df1.copy(), df2), ref.coverage(df1.copy(), df2))
+    pd.testing.assert_frame_equal(ours.setdiff(df1, df2), ref.setdiff(df1, df2))
+    # the same rows under an object column stay in the join (the NaN key is a group there)
+    o1, o2 = df1.astype({"chrom": object}), df2.astype({"chrom": object})
+    got, want = ours.ops._overlap_intidxs(o1, o2, how="outer"), ref.ops._overlap_intidxs(o1, o2, how="outer")
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and len(got[0]) > len(df1) - 2
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_live_closest_tie_free(ref, ours, seed):
     """closest picks among equal ends / starts through an unstable argsort in the reference: tie-free draws."""
