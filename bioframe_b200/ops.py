@@ -598,6 +598,10 @@ def overlap(
     # the index columns are only built when they are returned or needed to order the rows (the reference always
     # builds them, ops.py:464-478, and drops them at the end when return_index is False, ops.py:552-553)
     need_index = bool(return_index) or (bool(keep_order) and not device_order)
+    if not all(pd.api.types.is_integer_dtype(ix.dtype) for ix in (df1.index, df2.index)):
+        need_index = True  # labels that are not integers: cast (or refused) exactly as the reference does below
+    if (len(df1) == 0 or len(df2) == 0) and len(ev1):
+        need_index = True  # "no partner" (-1) looked up in an empty index: the reference's IndexError (ops.py:464-478)
     if need_index:
         parts["i1"] = pd.DataFrame({icol1: df1.index[ev1]}, dtype=pd.Int64Dtype())
         parts["i2"] = pd.DataFrame({icol2: df2.index[ev2]}, dtype=pd.Int64Dtype())
@@ -639,7 +643,7 @@ def overlap(
             parts["ov"][miss1 | miss2] = None
 
     kept = [parts[k] for k in ("i1", "in1", "i2", "in2", "ov") if k in parts]
-    out = pd.concat(kept, axis=1) if kept else pd.DataFrame(index=pd.RangeIndex(len(ev1)))
+    out = pd.concat(kept, axis=1) if kept else pd.DataFrame(index=pd.RangeIndex(len(ev1)), columns=pd.Index([], dtype=object))
     if keep_order and not device_order:
         out = out.sort_values([icol1, icol2])
     if need_index and not return_index:
@@ -731,8 +735,7 @@ def _closest_intidxs(
     # kernel rows index the NA-free subsets; map back to frame positions
     if rows1 is not None:
         ev1 = rows1[ev1]
-    if rows2 is not None:
-        ev2 = np.where(ev2 >= 0, rows2[np.maximum(ev2, 0)], -1)
+    ev2 = _frame_positions(ev2, rows2)  # (-1 stays; also when no row of df2 took part)
     return (ev1, ev2, extra) if _coords else (ev1, ev2)
 
 
@@ -906,6 +909,8 @@ def cluster(
     _verify_columns(df, [ck, sk, ek])
     df = df.reset_index(drop=True)
     group_list = _check_min_dist_and_on(df, min_dist, ck, on)
+    if len(df) == 0:
+        raise ValueError("No objects to concatenate")  # pd.concat([]) over the reference's cluster table (ops.py:684)
 
     # every row's cluster span comes straight from the device (row_start / row_end of bf_cluster_emit) unless
     # null rows, which are clusters of their own, have to be spliced in
@@ -979,6 +984,8 @@ def coverage(df1, df2, suffixes=("", "_"), return_input=True, cols1=None, cols2=
     ck2, sk2, ek2 = _get_default_colnames() if cols2 is None else cols2
     df1.reset_index(inplace=True, drop=True)
     checks.is_bedframe(df2, raise_errors=True, cols=[ck2, sk2, ek2])  # merge(df2) validates
+    if len(df2) == 0:
+        raise ValueError("No objects to concatenate")  # merge(df2) of an empty frame in the reference (ops.py:888)
     checks.is_bedframe(df1, raise_errors=True, cols=[ck1, sk1, ek1])  # overlap(df1, ...) validates
 
     codes1, keys1 = _group_keys(df1, [ck1])
@@ -1090,6 +1097,14 @@ def count_overlaps(df1, df2, suffixes=("", "_"), return_input=True, cols1=None, 
     checks.is_bedframe(df1, raise_errors=True, cols=[ck1, sk1, ek1])
     checks.is_bedframe(df2, raise_errors=True, cols=[ck2, sk2, ek2])
     # the reference counts a nullable Int64 index column per query, which yields a nullable Int64 column
+    if len(df2) == 0 and len(df1) > 0:
+        # the reference's left join looks up the label of "no partner" (-1) in df2's index (ops.py:471-478)
+        raise IndexError("index -1 is out of bounds for axis 0 with size 0")
+    if not pd.api.types.is_integer_dtype(df2.index.dtype):
+        # the reference casts the labels of the partners to Int64 (ops.py:471-478): its own join decides whether
+        # such labels are accepted, and with which error they are not
+        overlap(df1, df2, how="left", return_input=False, keep_order=True, suffixes=suffixes, return_index=True, on=on,
+                cols1=cols1, cols2=cols2)
     counts = _overlap_counts(df1, df2, cols1, cols2, on)
     gone = _ungrouped_rows(df1, ck1, on)
     if gone is not None:  # as in coverage: the reference counts the rows its join has and attaches them by position
@@ -1156,6 +1171,7 @@ def subtract(df1, df2, return_index=False, suffixes=("", "_"), cols1=None, cols2
     _verify_columns(df2, [ck2, sk2, ek2])
     ix = df1.index
     fused = pd.api.types.is_integer_dtype(ix.dtype) and ix.is_monotonic_increasing and ix.is_unique
+    fused = fused and pd.api.types.is_integer_dtype(df2.index.dtype)  # other labels: the joins of the composition decide
     if not fused:
         return _subtract_composed(df1, df2, return_index, suffixes, cols1, cols2)
 
