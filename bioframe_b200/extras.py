@@ -7,6 +7,7 @@ import numpy as np
 import pandas as pd
 
 from . import ops
+from .core import checks
 from .core.specs import _get_default_colnames
 
 __all__ = ["pair_by_distance", "mark_runs", "merge_runs"]
@@ -80,8 +81,19 @@ def mark_runs(df, col, *, allow_overlaps=False, reset_counter=True, run_col="run
     arrops.py:459-470 with min_dist=0), the overlap check counts partners without listing pairs
     (bf_count_overlaps), and the value borders and the numbering are array operations over the whole frame."""
     ck, sk, ek = _get_default_colnames() if cols is None else cols
-    if not allow_overlaps and int(ops._overlap_counts(df, df, cols, cols, None).sum()) > len(df):
-        raise ValueError("Not a proper bedGraph: found overlapping intervals.")
+    if not allow_overlaps:
+        # the reference's check is `len(ops.overlap(df, df)) > len(df)` -- with the DEFAULT column names whatever
+        # `cols` says (extras.py:611): the rows of that left join are the pairs plus every row without a partner
+        # (null rows; not those its grouping leaves out altogether, ops._ungrouped_rows)
+        checks.is_bedframe(df, raise_errors=True)
+        if not pd.api.types.is_integer_dtype(df.index.dtype):
+            joined = len(ops.overlap(df, df))  # labels that are not integers: the join itself decides (ops.overlap)
+        else:
+            counts = ops._overlap_counts(df, df, None, None, None)
+            gone = ops._ungrouped_rows(df, _get_default_colnames()[0], None)
+            joined = int(counts.sum()) + int(((counts == 0) & ~gone).sum() if gone is not None else (counts == 0).sum())
+        if joined > len(df):
+            raise ValueError("Not a proper bedGraph: found overlapping intervals.")
 
     codes, _ = pd.factorize(df[ck])  # order of first appearance, -1 for null chromosomes (dropped, as groupby does)
     rows = np.flatnonzero(codes >= 0)
@@ -108,6 +120,8 @@ def mark_runs(df, col, *, allow_overlaps=False, reset_counter=True, run_col="run
     if reset_counter and len(order):  # numbering restarts with every chromosome
         first_of_group = np.r_[True, g[1:] != g[:-1]]
         run = run - np.maximum.accumulate(np.where(first_of_group, run, 0))
+    if len(rows) == 0:
+        raise ValueError("No objects to concatenate")  # pd.concat([]) of the reference's per-chromosome pieces (extras.py:651)
     out = df.iloc[rows[order]].copy()
     out[run_col] = run
     return out

@@ -944,6 +944,8 @@ def cluster(
     out = pd.DataFrame(out, copy=False)
     if return_input:
         out = pd.concat([df, out], axis="columns")
+    if len(out) != len(df):  # nothing asked for: the reference's (discarded) set_index of the input's labels fails (ops.py:706)
+        raise ValueError(f"Length mismatch: Expected {len(out)} rows, received array of length {len(df)}")
     return out
 
 

@@ -1,0 +1,221 @@
+"""Differential fuzz of the frame-level API against the reference itself: random frames (plain / categorical /
+nullable / all-null rows / narrow integer dtypes / odd indexes / custom column names / empty and one-row frames)
+and random arguments go through `bioframe.<fn>` and `bioframe_b200.<fn>`; both must return equal frames or raise
+the same exception class.  Host logic only: the engine is the oracle-backed double (tests/oracle_engine.py), so this
+runs in the build container; the kernels behind the same calls are compared with the oracle in tests/test_gpu_*.py.
+
+Found with it (and fixed): null rows under a categorical chromosome column (in no group of the reference's
+`groupby(...).indices`), closest when no row of df2 has a chromosome, index labels that are not integers, the
+reference's errors on empty inputs.  Known deviation, excluded from the draw: uint64 coordinate columns (the
+reference returns Float64 coordinates or fails to cast) and closest(return_overlap=True) on frames
+with null rows (the reference fails whenever the last row of df2 is one)."""
+import os
+import warnings
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import import_reference, reference_paths
+
+pytestmark = pytest.mark.skipif(reference_paths()[0] is None, reason="reference checkout / vendored copy not present")
+
+KINDS = ["plain", "cat", "nullable", "na", "catna", "int32", "strandna", "strandcat"]
+FUNCTIONS = ["overlap", "closest", "closest_self", "cluster", "merge", "coverage", "count_overlaps", "setdiff", "subtract",
+             "complement", "trim", "assign_view", "pair_by_distance", "mark_runs", "merge_runs"]
+N_SEEDS = int(os.environ.get("BF_FUZZ_SEEDS", "240"))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return import_reference()
+
+
+@pytest.fixture
+def ours(monkeypatch):
+    import oracle_engine
+
+    import bioframe_b200 as bf
+    import bioframe_b200.core.arrops as arrops
+    import bioframe_b200.ops as ops
+
+    monkeypatch.setattr(ops, "_engine", oracle_engine)
+    monkeypatch.setattr(arrops, "_engine", oracle_engine)
+    old = pd.get_option("future.infer_string")
+    pd.set_option("future.infer_string", False)
+    yield bf
+    pd.set_option("future.infer_string", old)
+
+
+def _frame(rng, n, chroms, kind, cols, tie_free):
+    span = int(rng.choice([50, 600, 5000]))
+    if tie_free:  # closest among equal starts / ends goes through an unstable sort in the reference
+        s = rng.choice(np.arange(0, 20000, 7), n, replace=False) if n else np.zeros(0, int)
+        e = s + 1 + 7 * rng.integers(0, 5, n) + rng.integers(0, 6, n)
+    else:
+        s = rng.integers(0, span, n)
+        ln = rng.integers(1, 50, n)
+        ln[rng.random(n) < 0.1] = 0
+        e = s + ln
+    ck, sk, ek = cols
+    df = pd.DataFrame({ck: rng.choice(np.array(chroms, dtype=object), n) if n else np.array([], dtype=object), sk: s, ek: e})
+    df["strand"] = rng.choice(np.array(["+", "-"], dtype=object), n) if n else np.array([], dtype=object)
+    df["score"] = rng.integers(0, 4, n)
+    df["w"] = rng.random(n)
+    if kind == "cat":
+        df[ck] = pd.Categorical(df[ck], categories=list(rng.permutation(sorted(set(chroms) | {"chrZ"}))))
+    elif kind == "nullable":
+        df[sk], df[ek] = df[sk].astype("Int64"), df[ek].astype("Int64")
+    elif kind in ("na", "catna") and n:
+        if kind == "catna":
+            df[ck] = pd.Categorical(df[ck], categories=sorted(set(chroms)))
+        df[sk], df[ek] = df[sk].astype("Int64"), df[ek].astype("Int64")
+        df.loc[df.index[rng.random(n) < 0.15], [ck, sk, ek]] = pd.NA
+    elif kind == "int32":
+        df[sk], df[ek] = df[sk].astype(np.int32), df[ek].astype(np.int32)
+    elif kind == "strandna" and n:
+        df.loc[df.index[rng.random(n) < 0.2], "strand"] = None
+    elif kind == "strandcat":
+        df["strand"] = pd.Categorical(df["strand"], categories=["-", "+", "."])
+    index = rng.choice(["range", "shuffled", "str", "dup", "offset"], p=[0.6, 0.1, 0.1, 0.1, 0.1])
+    if index == "shuffled":
+        df.index = rng.permutation(n)
+    elif index == "str":
+        df.index = [f"r{i}" for i in rng.permutation(n)]
+    elif index == "dup" and n:
+        df.index = rng.integers(0, max(n // 2, 1), n)
+    elif index == "offset":
+        df.index = np.arange(n) + 100
+    return df
+
+
+def _draw(rng):
+    chroms1 = list(rng.choice(["chr1", "chr2", "chrX", "chr10", "chrM"], rng.integers(1, 5), replace=False))
+    chroms2 = list(rng.choice(["chr1", "chr2", "chrX", "chr10", "chr9"], rng.integers(1, 5), replace=False))
+    n1, n2 = int(rng.choice([0, 1, 2, 30, 120])), int(rng.choice([0, 1, 25, 90]))
+    fn = str(rng.choice(FUNCTIONS))
+    custom = rng.random() < 0.15
+    cols1 = ("c", "s", "e") if custom else ("chrom", "start", "end")
+    cols2 = ("C2", "S2", "E2") if custom and rng.random() < 0.5 else cols1
+    tie_free = fn.startswith("closest")
+    df1 = _frame(rng, n1, chroms1, str(rng.choice(KINDS)), cols1, tie_free)
+    df2 = _frame(rng, n2, chroms2, str(rng.choice(KINDS)), cols2, tie_free)
+    one = {"cols": cols1} if custom else {}
+    two = {"cols1": cols1, "cols2": cols2} if custom else {}
+    flip = lambda p: bool(rng.random() < p)  # noqa: E731
+    view = pd.DataFrame({"chrom": ["chr1", "chr1", "chr2", "chrX"], "start": [0, 300, 0, 10], "end": [300, 700, 450, 5000],
+                         "name": ["a", "b", "c", "d"]})
+    if fn == "overlap":
+        kw = dict(two, how=str(rng.choice(["left", "right", "inner", "outer"])))
+        if flip(0.5):
+            kw["return_index"] = True if flip(0.7) else "ix"
+        if flip(0.5):
+            kw["return_overlap"] = True if flip(0.7) else "ov"
+        if flip(0.3):
+            kw["return_input"] = False
+        if flip(0.3):
+            kw["suffixes"] = ("_a", "_b")
+        if flip(0.3):
+            kw["on"] = [["strand"], ["strand", "score"], []][rng.integers(0, 3)]
+        if flip(0.3):
+            kw["ensure_int"] = False
+        if flip(0.3):
+            kw["keep_order"] = flip(0.5)
+        return fn, (df1, df2), kw
+    if fn in ("closest", "closest_self"):
+        kw = dict(two, k=int(rng.choice([1, 2, 5])))
+        for flag in ("ignore_overlaps", "ignore_upstream", "ignore_downstream", "return_index", "return_overlap"):
+            if flip(0.3):
+                kw[flag] = True
+        if flip(0.3):
+            kw["return_distance"] = False
+        if flip(0.2):
+            kw["direction_col"] = "strand"
+        if flip(0.2):
+            kw["suffixes"] = ("_a", "_b")
+        if kw.get("return_overlap") and (df1[cols1[1]].isna().any() or df2[cols2[1]].isna().any()):
+            # the reference looks a missing partner (-1) up as the LAST row of df2; when that is a null row its
+            # `np.where(have_overlap, ...)` fails on pd.NA (ops.py:1195) -- an accident of the row order, not drawn
+            del kw["return_overlap"]
+        if fn == "closest_self":
+            if custom:
+                kw["cols2"] = cols1
+            return "closest", (df1,), kw
+        return fn, (df1, df2), kw
+    if fn in ("cluster", "merge"):
+        kw = dict(one, min_dist=[0, None, 3, 2.5][rng.integers(0, 4)])
+        if flip(0.3):
+            kw["on"] = [["strand"], ["strand", "score"]][rng.integers(0, 2)]
+        if fn == "cluster":
+            for flag in ("return_input", "return_cluster_ids", "return_cluster_intervals"):
+                if flip(0.25):
+                    kw[flag] = False
+        return fn, (df1,), kw
+    if fn in ("coverage", "count_overlaps", "setdiff", "subtract"):
+        kw = dict(two)
+        if fn in ("count_overlaps", "setdiff") and flip(0.3):
+            kw["on"] = ["strand"]
+        if fn == "subtract" and flip(0.4):
+            kw["return_index"] = True
+        if fn in ("coverage", "count_overlaps") and flip(0.2):
+            kw["return_input"] = False
+        return fn, (df1, df2), kw
+    if fn == "complement":
+        kw = dict(one)
+        if flip(0.5):
+            kw["view_df"] = {c: 6000 for c in set(chroms1) | {"chr9"}} if flip(0.5) else view
+        return fn, (df1,), kw
+    if fn in ("trim", "assign_view"):
+        kw = dict(one)
+        if fn == "trim" and flip(0.3):
+            return fn, (df1,), kw
+        kw["view_df"] = view
+        if fn == "assign_view" and flip(0.3):
+            kw["drop_unassigned"] = True
+        if fn == "trim" and flip(0.3):
+            kw["return_view_columns"] = True
+        return fn, (df1,), kw
+    if fn == "pair_by_distance":
+        kw = dict(one, min_sep=int(rng.choice([0, 10, 100])), max_sep=int(rng.choice([150, 1000, 10000])))
+        if flip(0.3):
+            kw["min_intervening"], kw["max_intervening"] = (0, int(rng.choice([1, 3]))) if flip(0.5) else (1, None)
+        if flip(0.3):
+            kw["relative_to"] = "endpoints"
+        if flip(0.3):
+            kw["keep_order"] = False
+        if flip(0.2):
+            kw["suffixes"] = ("_a", "_b")
+        return fn, (df1,), kw
+    kw = dict(one, allow_overlaps=flip(0.6))
+    if fn == "mark_runs" and flip(0.3):
+        kw["reset_counter"] = False
+    return fn, (df1, "score"), kw
+
+
+def _call(module, fn, args, kwargs):
+    args = [a.copy() if isinstance(a, pd.DataFrame) else a for a in args]
+    kwargs = {k: (v.copy() if isinstance(v, pd.DataFrame) else v) for k, v in kwargs.items()}
+    try:
+        return "ok", getattr(module, fn)(*args, **kwargs)
+    except Exception as exc:  # noqa: BLE001 -- the class of whatever is raised is what gets compared
+        return "raised", type(exc)
+
+
+@pytest.mark.parametrize("block", range(8))
+def test_frame_api_matches_the_reference_on_random_calls(ref, ours, block):
+    per_block = N_SEEDS // 8
+    for seed in range(block * per_block, (block + 1) * per_block):
+        rng = np.random.default_rng(90_000 + seed)
+        fn, args, kwargs = _draw(rng)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got, want = _call(ours, fn, args, kwargs), _call(ref, fn, args, kwargs)
+        what = f"seed {seed}: {fn}({', '.join(f'{k}={v!r}' for k, v in kwargs.items() if not isinstance(v, pd.DataFrame))})"
+        assert got[0] == want[0], f"{what}: ours {got}, reference {want}"
+        if got[0] == "raised":
+            assert got[1] is want[1], f"{what}: ours raised {got[1].__name__}, the reference {want[1].__name__}"
+        else:
+            try:
+                pd.testing.assert_frame_equal(got[1], want[1])
+            except AssertionError as exc:
+                raise AssertionError(f"{what}\n{exc}") from None
