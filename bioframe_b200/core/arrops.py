@@ -39,7 +39,21 @@ def _arrays(*vecs):
                 SyntaxWarning,
                 stacklevel=3,
             )
-    return [np.ascontiguousarray(np.asarray(v), dtype=np.int64) for v in vecs]
+    out = []
+    for vec in vecs:
+        arr = np.asarray(vec)
+        if arr.dtype.kind == "f":
+            # the kernels compute in int64: whole-number floats pass (results come back in the input dtype, as the
+            # reference's do), anything else is refused rather than truncated (the reference would carry NaN /
+            # fractions through numpy)
+            if not (np.isfinite(arr).all() and (arr == np.floor(arr)).all()):
+                raise ValueError("coordinates must be whole numbers (NaN / fractional values are not supported)")
+        out.append(np.ascontiguousarray(arr, dtype=np.int64))
+    return out
+
+
+def _dtype_of(vec):
+    return np.asarray(vec).dtype if not isinstance(vec, np.ndarray) else vec.dtype
 
 
 def _host(t):
@@ -79,18 +93,25 @@ def merge_intervals(starts, ends, min_dist=0):
     if md is not None and md < 0:
         raise ValueError("min_dist>=0 currently required")
     res = _engine.cluster(None, s, e, 1, min_dist=md)
-    return _host(res["ids"]), _host(res["cstart"]), _host(res["cend"])
+    # the spans are elements of the inputs (arrops.py:472-473): they keep the inputs' dtypes
+    return (_host(res["ids"]), _host(res["cstart"]).astype(_dtype_of(starts), copy=False),
+            _host(res["cend"]).astype(_dtype_of(ends), copy=False))
 
 
 def complement_intervals(starts, ends, bounds=(0, INT64_MAX)):
     """(starts, ends) of the gaps between the merged intervals inside `bounds`."""
     s, e = _arrays(starts, ends)
+    # the reference builds its result as np.r_[bounds[0], merged ends] / np.r_[merged starts, bounds[1]]
+    # (arrops.py:496-497): dtypes -- and the OverflowError for a bound that does not fit a narrow input dtype --
+    # are those of that concatenation
+    dt_starts = np.r_[bounds[0], np.empty(0, dtype=_dtype_of(ends))].dtype
+    dt_ends = np.r_[np.empty(0, dtype=_dtype_of(starts)), bounds[1]].dtype
     if len(s) == 0:
         # an empty set has the whole bounds as its complement; the reference (arrops.py:482-503 on the numpy of
         # this image) answers the same, ([bounds[0]], [bounds[1]])
-        return np.array([bounds[0]], dtype=np.int64), np.array([bounds[1]], dtype=np.int64)
+        return np.array([bounds[0]], dtype=dt_starts), np.array([bounds[1]], dtype=dt_ends)
     _, gs, ge = _engine.complement(None, s, e, np.array([bounds[0]], np.int64), np.array([bounds[1]], np.int64))
-    return _host(gs), _host(ge)
+    return _host(gs).astype(dt_starts, copy=False), _host(ge).astype(dt_ends, copy=False)
 
 
 def closest_intervals(

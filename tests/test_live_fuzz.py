@@ -224,3 +224,77 @@ def test_frame_api_matches_the_reference_on_random_calls(ref, ours, block, monke
                 pd.testing.assert_frame_equal(got[1], want[1])
             except AssertionError as exc:
                 raise AssertionError(f"{what}\n{exc}") from None
+
+
+# ------------------------------------------------------------------------------------------ array level
+def _intervals(rng, n, unique_ends=False, dtype=np.int64):
+    span = int(rng.choice([20, 300, 100000]))
+    if unique_ends:  # closest: equal ends / starts are ordered by an unstable sort in the reference
+        s = rng.choice(np.arange(-500, 50000, 7), n, replace=False) if n else np.zeros(0, np.int64)
+        e = s + 1 + 7 * rng.integers(0, 5, n) + rng.integers(0, 6, n)
+        while len(set(e.tolist())) < n:
+            dup = pd.Series(e).duplicated().values
+            e[dup] = s[dup] + 1 + rng.integers(0, 80, dup.sum())
+        return s.astype(np.int64), e.astype(np.int64)
+    s = rng.integers(-span // 4, span, n)
+    return s.astype(dtype), (s + rng.integers(0, max(span // 8, 2), n)).astype(dtype)
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_array_api_matches_the_reference_on_random_calls(ref, monkeypatch, block):
+    """`bioframe_b200.core.arrops.*` against `bioframe.core.arrops.*` (the array-level seam, docs/api-lowlevel.md):
+    same index arrays, same dtypes of the returned coordinates (int32 / whole-number float inputs included), same
+    exception classes (e.g. INT64_MAX bounds over int32 coordinates)."""
+    import oracle_engine
+
+    import bioframe_b200.core.arrops as ours
+
+    monkeypatch.setattr(ours, "_engine", oracle_engine)
+    monkeypatch.setattr(ours, "_host", lambda t: np.asarray(t))
+    theirs = ref.core.arrops
+
+    def call(fn, *args, **kwargs):
+        try:
+            return "ok", fn(*args, **kwargs)
+        except Exception as exc:  # noqa: BLE001
+            return "raised", type(exc)
+
+    for seed in range(block * 150, (block + 1) * 150):
+        rng = np.random.default_rng(70_000 + seed)
+        n1, n2 = int(rng.choice([0, 1, 2, 7, 60, 300])), int(rng.choice([0, 1, 3, 50, 200]))
+        dtype = [np.int64, np.int64, np.int32, np.float64][rng.integers(0, 4)]
+        fn = str(rng.choice(["overlap_intervals", "overlap_intervals_outer", "merge_intervals", "complement_intervals",
+                             "closest_intervals", "closest_self"]))
+        kwargs = {}
+        if fn.startswith("overlap"):
+            args = (*_intervals(rng, n1, dtype=dtype), *_intervals(rng, n2, dtype=dtype))
+            kwargs["closed"] = bool(rng.random() < 0.3)
+            if fn == "overlap_intervals":
+                kwargs["sort"] = bool(rng.random() < 0.3)
+        elif fn == "merge_intervals":
+            args, kwargs = _intervals(rng, n1, dtype=dtype), {"min_dist": [0, None, 1, 5, 2.5][rng.integers(0, 5)]}
+        elif fn == "complement_intervals":
+            args = _intervals(rng, n1, dtype=dtype)
+            if rng.random() < 0.5:
+                kwargs["bounds"] = (int(rng.integers(-50, 10)), int(rng.integers(100, 200000)))
+        else:
+            args = _intervals(rng, n1, True) if fn == "closest_self" else (*_intervals(rng, n1, True), *_intervals(rng, n2, True))
+            fn = "closest_intervals"
+            kwargs["k"] = int(rng.choice([1, 2, 4]))
+            for flag in ("ignore_overlaps", "ignore_upstream", "ignore_downstream"):
+                if rng.random() < 0.3:
+                    kwargs[flag] = True
+            if rng.random() < 0.3:
+                kwargs["along"] = rng.random(n1) < 0.5
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got, want = call(getattr(ours, fn), *args, **kwargs), call(getattr(theirs, fn), *args, **kwargs)
+        what = f"seed {seed}: {fn}(n1={n1}, n2={n2}, dtype={np.dtype(dtype)}, {', '.join(k for k in kwargs)})"
+        assert got[0] == want[0], f"{what}: ours {got}, reference {want}"
+        if got[0] == "raised":
+            assert got[1] is want[1], what
+            continue
+        assert len(got[1]) == len(want[1]), what
+        for a, b in zip(got[1], want[1]):
+            a, b = np.asarray(a), np.asarray(b)
+            assert a.dtype == b.dtype and np.array_equal(a, b), what
