@@ -526,8 +526,8 @@ def _taken_rows(df, positions, device_positions, suffix):
     """`df.iloc[positions]` with suffixed column names (ops.py:499-508).  For large results the pair list still
     lives on the device and every column with a fixed-width representation is gathered there
     (`_taken_column`); only object / string columns go through pandas."""
-    if device_positions is None or len(positions) < _DEVICE_GATHER_MIN_ROWS or not df.columns.is_unique:
-        return _suffixed_rows(df, positions, suffix)
+    if device_positions is None or len(positions) < _DEVICE_GATHER_MIN_ROWS or not df.columns.is_unique or len(df) == 0:
+        return _suffixed_rows(df, positions, suffix)  # (an empty frame has nothing to gather from: pandas' IndexError)
     data = {c + suffix: _taken_column(df[c], positions, device_positions) for c in df.columns}
     return pd.DataFrame(data, columns=[c + suffix for c in df.columns], copy=False)
 
