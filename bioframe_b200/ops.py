@@ -602,6 +602,8 @@ def overlap(
         need_index = True  # labels that are not integers: cast (or refused) exactly as the reference does below
     if (len(df1) == 0 or len(df2) == 0) and len(ev1):
         need_index = True  # "no partner" (-1) looked up in an empty index: the reference's IndexError (ops.py:464-478)
+    if not (return_input or return_overlap):
+        need_index = True  # nothing but the (possibly dropped) label columns: the frame they leave behind, as built there
     if need_index:
         parts["i1"] = pd.DataFrame({icol1: df1.index[ev1]}, dtype=pd.Int64Dtype())
         parts["i2"] = pd.DataFrame({icol2: df2.index[ev2]}, dtype=pd.Int64Dtype())
@@ -643,7 +645,7 @@ def overlap(
             parts["ov"][miss1 | miss2] = None
 
     kept = [parts[k] for k in ("i1", "in1", "i2", "in2", "ov") if k in parts]
-    out = pd.concat(kept, axis=1) if kept else pd.DataFrame(index=pd.RangeIndex(len(ev1)), columns=pd.Index([], dtype=object))
+    out = pd.concat(kept, axis=1)
     if keep_order and not device_order:
         out = out.sort_values([icol1, icol2])
     if need_index and not return_index:

@@ -208,6 +208,9 @@ def test_frame_api_matches_the_reference_on_random_calls(ref, ours, block, monke
 
         monkeypatch.setattr(ops, "_DEVICE_GATHER_MIN_ROWS", 0)
         monkeypatch.setattr(ops, "_DEVICE_ENCODE_MIN_ROWS", 0)
+    # blocks 4-7 with pandas 3's string inference on (object columns of the draw become `str` columns); the fixture
+    # restores the option
+    pd.set_option("future.infer_string", block >= 4)
     per_block = N_SEEDS // 8
     for seed in range(block * per_block, (block + 1) * per_block):
         rng = np.random.default_rng(90_000 + seed)
