@@ -86,12 +86,16 @@ def mark_runs(df, col, *, allow_overlaps=False, reset_counter=True, run_col="run
         # `cols` says (extras.py:611): the rows of that left join are the pairs plus every row without a partner
         # (null rows; not those its grouping leaves out altogether, ops._ungrouped_rows)
         checks.is_bedframe(df, raise_errors=True)
-        if not pd.api.types.is_integer_dtype(df.index.dtype):
-            joined = len(ops.overlap(df, df))  # labels that are not integers: the join itself decides (ops.overlap)
-        else:
+        counts = None
+        if pd.api.types.is_integer_dtype(df.index.dtype):
             counts = ops._overlap_counts(df, df, None, None, None)
-            gone = ops._ungrouped_rows(df, _get_default_colnames()[0], None)
-            joined = int(counts.sum()) + int(((counts == 0) & ~gone).sum() if gone is not None else (counts == 0).sum())
+        if counts is None or not counts.all():
+            # labels that are not integers, or rows without a partner (null rows: every other row overlaps itself):
+            # what the join makes of them -- casts, blanked payload columns, rows its grouping drops -- is the
+            # join's business, so it runs as in the reference; the usual frame only needs the pair count
+            joined = len(ops.overlap(df, df))
+        else:
+            joined = int(counts.sum())
         if joined > len(df):
             raise ValueError("Not a proper bedGraph: found overlapping intervals.")
 
