@@ -122,6 +122,10 @@ def _draw(rng):
     flip = lambda p: bool(rng.random() < p)  # noqa: E731
     view = pd.DataFrame({"chrom": ["chr1", "chr1", "chr2", "chrX"], "start": [0, 300, 0, 10], "end": [300, 700, 450, 5000],
                          "name": ["a", "b", "c", "d"]})
+    view_kw = {"view_df": view}
+    if flip(0.3):  # the view under its own column names
+        view_kw = {"view_df": view.rename(columns={"chrom": "vc", "start": "vs", "end": "ve", "name": "region"}),
+                   "cols_view": ("vc", "vs", "ve"), "view_name_col": "region"}
     if fn == "overlap":
         kw = dict(two, how=str(rng.choice(["left", "right", "inner", "outer"])))
         if flip(0.5):
@@ -185,13 +189,16 @@ def _draw(rng):
     if fn == "complement":
         kw = dict(one)
         if flip(0.5):
-            kw["view_df"] = {c: 6000 for c in set(chroms1) | {"chr9"}} if flip(0.5) else view
+            if flip(0.5):
+                kw["view_df"] = {c: 6000 for c in set(chroms1) | {"chr9"}}
+            else:
+                kw.update(view_kw)
         return fn, (df1,), kw
     if fn in ("trim", "assign_view"):
         kw = dict(one)
         if fn == "trim" and flip(0.3):
             return fn, (df1,), kw
-        kw["view_df"] = view
+        kw.update(view_kw)
         if fn == "assign_view" and flip(0.3):
             kw["drop_unassigned"] = True
         if fn == "trim" and flip(0.3):
