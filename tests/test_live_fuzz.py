@@ -54,7 +54,7 @@ def _frame(rng, n, chroms, kind, cols, tie_free):
         s = rng.choice(np.arange(0, 20000, 7), n, replace=False) if n else np.zeros(0, int)
         e = s + 1 + 7 * rng.integers(0, 5, n) + rng.integers(0, 6, n)
     else:
-        s = rng.integers(0, span, n)
+        s = rng.integers(-span // 4 if rng.random() < 0.2 else 0, span, n)  # now and then negative coordinates
         ln = rng.integers(1, 50, n)
         ln[rng.random(n) < 0.1] = 0
         e = s + ln
