@@ -1101,7 +1101,8 @@ def count_overlaps(df1, df2, suffixes=("", "_"), return_input=True, cols1=None, 
     checks.is_bedframe(df1, raise_errors=True, cols=[ck1, sk1, ek1])
     checks.is_bedframe(df2, raise_errors=True, cols=[ck2, sk2, ek2])
     # the reference counts a nullable Int64 index column per query, which yields a nullable Int64 column
-    if len(df2) == 0 and len(df1) > 0:
+    gone = _ungrouped_rows(df1, ck1, on)
+    if len(df2) == 0 and len(df1) - (0 if gone is None else int(gone.sum())) > 0:
         # the reference's left join looks up the label of "no partner" (-1) in df2's index (ops.py:471-478)
         raise IndexError("index -1 is out of bounds for axis 0 with size 0")
     if not pd.api.types.is_integer_dtype(df2.index.dtype):
@@ -1110,7 +1111,6 @@ def count_overlaps(df1, df2, suffixes=("", "_"), return_input=True, cols1=None, 
         overlap(df1, df2, how="left", return_input=False, keep_order=True, suffixes=suffixes, return_index=True, on=on,
                 cols1=cols1, cols2=cols2)
     counts = _overlap_counts(df1, df2, cols1, cols2, on)
-    gone = _ungrouped_rows(df1, ck1, on)
     if gone is not None:  # as in coverage: the reference counts the rows its join has and attaches them by position
         counts = counts[~gone]
     out = pd.DataFrame({"count": pd.array(counts, dtype=pd.Int64Dtype())})
