@@ -53,6 +53,9 @@ def _frame(rng, n, chroms, kind, cols, tie_free):
     if tie_free:  # closest among equal starts / ends goes through an unstable sort in the reference
         s = rng.choice(np.arange(0, 20000, 7), n, replace=False) if n else np.zeros(0, int)
         e = s + 1 + 7 * rng.integers(0, 5, n) + rng.integers(0, 6, n)
+        while len(set(e.tolist())) < n:
+            dup = pd.Series(e).duplicated().values
+            e[dup] = s[dup] + 1 + rng.integers(0, 80, dup.sum())
     else:
         s = rng.integers(-span // 4 if rng.random() < 0.2 else 0, span, n)  # now and then negative coordinates
         ln = rng.integers(1, 50, n)
