@@ -333,3 +333,38 @@ def test_array_api_matches_the_reference_on_random_calls(ref, monkeypatch, block
         for a, b in zip(got[1], want[1]):
             a, b = np.asarray(a), np.asarray(b)
             assert a.dtype == b.dtype and np.array_equal(a, b), what
+
+
+def test_frames_large_enough_for_the_device_assembly_paths(ref, ours):
+    """6e5 x 8e4 rows of the bench's own synthetic frames (categorical chrom, a string column): results above
+    `_DEVICE_GATHER_MIN_ROWS` / `_DEVICE_ENCODE_MIN_ROWS`, so the glue takes its large-frame paths without being forced
+    to -- device group encoding, column gathers, the threaded Arrow string take, cluster spans from the device -- and
+    every frame must equal the reference's, row for row."""
+    import bioframe_b200.ops as ops
+    from bioframe_b200 import synth
+
+    pd.set_option("future.infer_string", True)  # the `name` column as pandas 3 makes it: Arrow-backed `str`
+    n1, n2 = 600_000, 80_000
+    names = ["chr%d" % i for i in range(1, 23)] + ["chrX", "chrY"]
+
+    def frame(sets):
+        g, s, e = sets
+        return pd.DataFrame({"chrom": pd.Categorical.from_codes(g, categories=names), "start": s, "end": e})
+
+    df1, df2 = frame(synth.make_intervals(n1, 1, "geom1k")), frame(synth.make_tie_free(n2, 2, "geom1k"))
+    df1["name"] = np.array([f"q{i}" for i in range(1000)], dtype=object)[np.arange(n1) % 1000]
+    df2["score"] = (np.arange(n2) % 97).astype(np.float64)
+    assert n1 >= ops._DEVICE_GATHER_MIN_ROWS and n1 >= ops._DEVICE_ENCODE_MIN_ROWS
+    for fn, args, kwargs in (
+        ("closest", (df1, df2), {"k": 1}), ("cluster", (df1,), {}), ("merge", (df1,), {}), ("coverage", (df1, df2), {}),
+        ("count_overlaps", (df1, df2), {}), ("subtract", (df1, df2), {}), ("setdiff", (df1, df2), {}),
+        ("overlap", (df1, df2), {"how": "left", "return_overlap": True}), ("overlap", (df1, df2), {"how": "outer"}),
+    ):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got = getattr(ours, fn)(*[a.copy() for a in args], **kwargs)
+            want = getattr(ref, fn)(*[a.copy() for a in args], **kwargs)
+        try:
+            pd.testing.assert_frame_equal(got, want)
+        except AssertionError as exc:
+            raise AssertionError(f"{fn}({kwargs})\n{exc}") from None
