@@ -697,6 +697,8 @@ def frame_leg(args):
             ("cluster", lambda: ours.cluster(heavy), lambda: bf.cluster(heavy), False),
             ("merge", lambda: ours.merge(heavy), lambda: bf.merge(heavy), False),
             ("coverage", lambda: ours.coverage(df1, df2), lambda: bf.coverage(df1, df2), False),
+            ("count_overlaps", lambda: ours.count_overlaps(df1, df2), lambda: bf.count_overlaps(df1, df2), False),
+            ("subtract", lambda: ours.subtract(df1, df2), lambda: bf.subtract(df1, df2), False),
         ):
             ours_fn()
             t_ours, got = wall(ours_fn, 2)
