@@ -151,3 +151,40 @@ def test_arrow_string_take_matches_iloc(monkeypatch):
         pd.testing.assert_extension_array_equal(got, want)
     empty = ops._arrow_string_take(col.iloc[:0].array, np.array([-1, -1]))
     assert empty.isna().all() and len(empty) == 2
+
+
+def test_string_take_through_the_dictionary(monkeypatch, oracle_double):
+    """Large string columns with few distinct values are taken through their dictionary (`_string_dictionary`: encoded
+    slice by slice, unified; codes gathered like a fixed-width column; decoded from the dictionary): same values and
+    dtype as `iloc`, nulls kept, and columns with many distinct values keep the plain take."""
+    import bioframe_b200.ops as ops
+
+    monkeypatch.setattr(ops, "_ARROW_TAKE_THREADS", 3)
+    monkeypatch.setattr(ops, "_DICT_TAKE_MIN_ROWS", 0)
+    rng = np.random.default_rng(9)
+    n = 3 << 18  # three encode slices whose dictionaries differ in order and content
+    labels = np.array([f"gene{i}" for i in range(40)], dtype=object)
+    which = np.concatenate([rng.integers(0, 10, n // 3), rng.integers(5, 25, n // 3), rng.integers(20, 40, n - 2 * (n // 3))])
+    col = pd.Series(labels[which])
+    col[rng.random(n) < 0.05] = None
+    col = col.astype("str")
+    if not isinstance(col.array, pd.arrays.ArrowStringArray):
+        pytest.skip("string columns are not Arrow-backed in this pandas")
+    values = col.array._pa_array.combine_chunks()
+    codes, dictionary = ops._string_dictionary(values, 3)
+    assert len(dictionary) == 40 and codes.dtype == np.int32 and ((codes < 0) == col.isna().to_numpy()).all()
+    assert dictionary.take(codes[codes >= 0][:1000].tolist()).to_pylist() == col[codes >= 0][:1000].tolist()
+    positions = rng.integers(0, n, n)  # most of the column: the dictionary route
+    got = ops._arrow_string_take(col.array, positions, device_positions=positions)
+    pd.testing.assert_extension_array_equal(got, col.iloc[positions].array)
+    with_gaps = np.where(rng.random(n) < 0.1, -1, positions)  # -1: any value will do, the callers blank those rows
+    got = ops._arrow_string_take(col.array, with_gaps, device_positions=with_gaps)
+    keep = with_gaps >= 0
+    pd.testing.assert_extension_array_equal(got[keep], col.iloc[with_gaps[keep]].array)
+    # many distinct values, an all-null column: no dictionary, the plain threaded take answers
+    unique = pd.Series([f"id{i}" for i in range(1 << 17)]).astype("str")
+    assert ops._string_dictionary(unique.array._pa_array.combine_chunks(), 2) is None
+    empty = pd.Series([None] * 1000, dtype="str")
+    assert ops._string_dictionary(empty.array._pa_array.combine_chunks(), 1) is None
+    pos = rng.integers(0, 1000, 900)
+    assert ops._arrow_string_take(empty.array, pos, device_positions=pos).isna().all()

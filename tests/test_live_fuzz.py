@@ -240,6 +240,7 @@ def test_frame_api_matches_the_reference_on_random_calls(ref, ours, block, monke
 
         monkeypatch.setattr(ops, "_DEVICE_GATHER_MIN_ROWS", 0)
         monkeypatch.setattr(ops, "_DEVICE_ENCODE_MIN_ROWS", 0)
+        monkeypatch.setattr(ops, "_DICT_TAKE_MIN_ROWS", 0)  # string columns through their dictionary
     # blocks 4-7 with pandas 3's string inference on (object columns of the draw become `str` columns); the fixture
     # restores the option
     pd.set_option("future.infer_string", block >= 4)
@@ -335,7 +336,7 @@ def test_array_api_matches_the_reference_on_random_calls(ref, monkeypatch, block
             assert a.dtype == b.dtype and np.array_equal(a, b), what
 
 
-def test_frames_large_enough_for_the_device_assembly_paths(ref, ours):
+def test_frames_large_enough_for_the_device_assembly_paths(ref, ours, monkeypatch):
     """6e5 x 8e4 rows of the bench's own synthetic frames (categorical chrom, a string column): results above
     `_DEVICE_GATHER_MIN_ROWS` / `_DEVICE_ENCODE_MIN_ROWS`, so the glue takes its large-frame paths without being forced
     to -- device group encoding, column gathers, the threaded Arrow string take, cluster spans from the device -- and
@@ -344,6 +345,7 @@ def test_frames_large_enough_for_the_device_assembly_paths(ref, ours):
     from bioframe_b200 import synth
 
     pd.set_option("future.infer_string", True)  # the `name` column as pandas 3 makes it: Arrow-backed `str`
+    monkeypatch.setattr(ops, "_DICT_TAKE_MIN_ROWS", 1 << 19)  # (its 1000 distinct names: taken through the dictionary)
     n1, n2 = 600_000, 80_000
     names = ["chr%d" % i for i in range(1, 23)] + ["chrX", "chrY"]
 
