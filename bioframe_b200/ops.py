@@ -487,9 +487,11 @@ def _taken_column(col, positions, device_positions):
 _ARROW_TAKE_THREADS = max(1, min(8, os.cpu_count() or 1))
 
 
-# A string column of this many rows and more, of which at least half are taken, goes through its dictionary when it
-# has few distinct values (names of regions, genes, samples ...): see _arrow_string_take
+# A take of this many values and more out of a string column with few distinct values (names of regions, genes,
+# samples ...) goes through the column's dictionary when every row is taken at least once on average: see
+# _arrow_string_take.  _DICT_TAKE_ALWAYS: tests.
 _DICT_TAKE_MIN_ROWS = 1 << 20
+_DICT_TAKE_ALWAYS = False
 
 
 def _threaded(fn, parts):
@@ -540,10 +542,10 @@ def _arrow_string_take(arr, positions, device_positions=None):
     None when this pandas / pyarrow does not expose what is needed -- the caller falls back to `iloc`.
 
     A take at random positions of a large column is bound by cache misses (290 ms on one thread for 6.5e6 of 1e7
-    values, 50 ms for the same positions sorted).  When most of a large column is taken and it has few distinct
-    values, the column is dictionary-encoded instead (a sequential pass), the 4-byte codes are gathered on the
-    device like any fixed-width column, and the result is decoded from the small, cache-resident dictionary:
-    138 + 23 + 68 ms on one thread for the same take, every stage sliced over the threads."""
+    values, 50 ms for the same positions sorted).  When a column with few distinct values is taken more than once
+    over (joins with fan-out), it is dictionary-encoded instead (a sequential pass, sliced over the threads and
+    unified: ~200 ms per 1e7 rows on one thread), the 4-byte codes are gathered on the device like any fixed-width
+    column, and the result is decoded from the small, cache-resident dictionary (~10 ns a value instead of 25-45)."""
     try:
         import pyarrow as pa
         import pyarrow.compute as pc
@@ -556,12 +558,12 @@ def _arrow_string_take(arr, positions, device_positions=None):
     positions = np.asarray(positions, dtype=np.int64)
     parts = max(1, min(_ARROW_TAKE_THREADS, len(positions) >> 18))
     bounds = np.linspace(0, len(positions), parts + 1).astype(np.int64)
-    # worth it when the sequential pass over the column (~16 ns a row) costs less than what the decode saves per taken
-    # row (~25-45 ns against ~10): most of a large column, or a smaller column taken many times over (the few-row
-    # side of a join with a large result)
+    # worth it when the sequential pass over the column (~20 ns a row: encode, codes, unify) costs less than what the
+    # decode saves per taken row (25 ns from a 1e6-row column, 45 ns from a 1e7-row one, against ~10 ns from the
+    # dictionary): a column taken at least once over (twice for smaller columns), i.e. joins with fan-out
     n_taken, n_rows = len(positions), len(values)
-    through_dictionary = (n_rows >= _DICT_TAKE_MIN_ROWS and 2 * n_taken >= n_rows) or (
-        n_taken >= max(_DICT_TAKE_MIN_ROWS, 2 * n_rows) and n_rows >= (1 << 16))
+    through_dictionary = _DICT_TAKE_ALWAYS or (
+        n_rows >= (1 << 16) and n_taken >= _DICT_TAKE_MIN_ROWS and n_taken >= (n_rows if n_rows >= (1 << 22) else 2 * n_rows))
     if device_positions is not None and through_dictionary:
         encoded = _string_dictionary(values, max(1, min(_ARROW_TAKE_THREADS, len(values) >> 18)))
         if encoded is not None:

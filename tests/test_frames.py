@@ -160,7 +160,7 @@ def test_string_take_through_the_dictionary(monkeypatch, oracle_double):
     import bioframe_b200.ops as ops
 
     monkeypatch.setattr(ops, "_ARROW_TAKE_THREADS", 3)
-    monkeypatch.setattr(ops, "_DICT_TAKE_MIN_ROWS", 0)
+    monkeypatch.setattr(ops, "_DICT_TAKE_ALWAYS", True)
     rng = np.random.default_rng(9)
     n = 3 << 18  # three encode slices whose dictionaries differ in order and content
     labels = np.array([f"gene{i}" for i in range(40)], dtype=object)

@@ -240,7 +240,7 @@ def test_frame_api_matches_the_reference_on_random_calls(ref, ours, block, monke
 
         monkeypatch.setattr(ops, "_DEVICE_GATHER_MIN_ROWS", 0)
         monkeypatch.setattr(ops, "_DEVICE_ENCODE_MIN_ROWS", 0)
-        monkeypatch.setattr(ops, "_DICT_TAKE_MIN_ROWS", 0)  # string columns through their dictionary
+        monkeypatch.setattr(ops, "_DICT_TAKE_ALWAYS", True)  # string columns through their dictionary
     # blocks 4-7 with pandas 3's string inference on (object columns of the draw become `str` columns); the fixture
     # restores the option
     pd.set_option("future.infer_string", block >= 4)
@@ -345,7 +345,7 @@ def test_frames_large_enough_for_the_device_assembly_paths(ref, ours, monkeypatc
     from bioframe_b200 import synth
 
     pd.set_option("future.infer_string", True)  # the `name` column as pandas 3 makes it: Arrow-backed `str`
-    monkeypatch.setattr(ops, "_DICT_TAKE_MIN_ROWS", 1 << 19)  # (its 1000 distinct names: taken through the dictionary)
+    monkeypatch.setattr(ops, "_DICT_TAKE_ALWAYS", True)  # (its 1000 distinct names: taken through the dictionary)
     n1, n2 = 600_000, 80_000
     names = ["chr%d" % i for i in range(1, 23)] + ["chrX", "chrY"]
 
