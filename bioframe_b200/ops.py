@@ -1099,8 +1099,6 @@ def complement(df, view_df=None, view_name_col="name", cols=None, cols_view=None
         columns=dict(zip([ckv, skv, ekv], [ck, sk, ek]))
     )
 
-    clipped = overlap(view_df, df, return_overlap=True, how="inner", suffixes=("", "_df"), cols1=cols, cols2=cols)
-    region_of = clipped[view_name_col].values
     names = sorted(set(view_df[view_name_col]))
     code = {name: r for r, name in enumerate(names)}
     first_row = view_df.drop_duplicates(view_name_col).set_index(view_name_col)
@@ -1108,18 +1106,38 @@ def complement(df, view_df=None, view_name_col="name", cols=None, cols_view=None
     bounds_hi = np.array([first_row.loc[name, ek] for name in names], dtype=np.int64)
     chroms = [first_row.loc[name, ck] for name in names]
 
-    reg, gs, ge = _engine.complement(
-        np.array([code[r] for r in region_of], dtype=np.int32),
-        np.asarray(clipped["overlap_" + sk], dtype=np.int64),
-        np.asarray(clipped["overlap_" + ek], dtype=np.int64),
-        bounds_lo,
-        bounds_hi,
-    )
+    if all(pd.api.types.is_integer_dtype(ix.dtype) for ix in (view_df.index, df.index)):
+        # the clipped pieces straight from the pair list: region of every pair = name of its view row, coordinates
+        # from bf_pair_coords (or the same max / min on the host for nullable columns) -- the frame `overlap` would
+        # assemble around them (every column of both inputs per pair) is never read
+        checks.is_bedframe(view_df, raise_errors=True, cols=[ck, sk, ek])
+        checks.is_bedframe(df, raise_errors=True, cols=[ck, sk, ek])
+        plain = all(_is_plain_int(f[c]) for f in (view_df, df) for c in (sk, ek))
+        res = _overlap_intidxs(view_df, df, how="inner", cols1=cols, cols2=cols, _coords=plain)
+        ev1, ev2 = res[0], res[1]
+        if plain:
+            clip_lo, clip_hi = res[2]
+        else:
+            clip_lo = np.maximum(_int64_coords(view_df, sk)[ev1], _int64_coords(df, sk)[ev2])
+            clip_hi = np.minimum(_int64_coords(view_df, ek)[ev1], _int64_coords(df, ek)[ev2])
+        row_region = np.array([code[name] for name in view_df[view_name_col]], dtype=np.int32)  # per view ROW: few
+        region = row_region[ev1] if len(row_region) else np.empty(0, np.int32)
+    else:  # labels that are not integers: the join decides what becomes of them (ops.overlap)
+        clipped = overlap(view_df, df, return_overlap=True, how="inner", suffixes=("", "_df"), cols1=cols, cols2=cols)
+        region = pd.Index(names).get_indexer(clipped[view_name_col]).astype(np.int32)
+        clip_lo, clip_hi = clipped["overlap_" + sk], clipped["overlap_" + ek]
+
+    reg, gs, ge = _engine.complement(region, np.asarray(clip_lo, dtype=np.int64), np.asarray(clip_hi, dtype=np.int64),
+                                     bounds_lo, bounds_hi)
     reg = _to_host(reg).astype(np.int64)
-    chrom_col = pd.Series([chroms[r] for r in reg], dtype=view_df[ck].dtype if len(reg) else object)
-    return pd.DataFrame(
-        {ck: chrom_col, sk: _to_host(gs), ek: _to_host(ge), "view_region": [names[r] for r in reg]}
-    ).reset_index(drop=True)
+    if len(reg):
+        # one value per region, taken per gap (the reference builds both columns from Python lists of per-gap values,
+        # ops.py:1672-1687: same dtypes -- the view's chromosome dtype, whatever pandas infers for the names)
+        chrom_col = pd.Series(pd.Series(chroms, dtype=view_df[ck].dtype).array.take(reg))
+        region_col = pd.Series(pd.Series(names).array.take(reg))
+    else:
+        chrom_col, region_col = pd.Series([], dtype=object), []
+    return pd.DataFrame({ck: chrom_col, sk: _to_host(gs), ek: _to_host(ge), "view_region": region_col}).reset_index(drop=True)
 
 
 # --------------------------------------------------------------------------
